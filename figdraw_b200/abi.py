@@ -1,0 +1,212 @@
+"""ctypes view of include/figdraw_cuda.h: enums, the 128-byte `fdc_call` record and the library loader.
+
+The product path FAILS LOUDLY when the CUDA extension is missing: `load_library()` raises, there is
+no CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+import os
+from typing import Optional
+
+import numpy as np
+
+ABI_VERSION = 1
+
+
+class Status(enum.IntEnum):
+    OK = 0
+    ERR_INVALID = 1
+    ERR_CUDA = 2
+    ERR_STATE = 3
+    ERR_CAPACITY = 4
+    ERR_MISSING_IMAGE = 5
+
+
+class SdfMode(enum.IntEnum):
+    """figbackend.nim:36-52."""
+
+    sdfModeAtlas = 0
+    sdfModeClipAA = 3
+    sdfModeDropShadow = 7
+    sdfModeDropShadowAA = 8
+    sdfModeInsetShadow = 9
+    sdfModeInsetShadowAnnular = 10
+    sdfModeAnnular = 11
+    sdfModeAnnularAA = 12
+    sdfModeMsdf = 13
+    sdfModeMtsdf = 14
+    sdfModeMsdfAnnular = 15
+    sdfModeMtsdfAnnular = 16
+    sdfModeBackdropBlur = 17
+    sdfModeBezierStrokeAA = 18
+    sdfModeBezierStrokeButtAA = 19
+    sdfModeBezierStrokeSquareAA = 20
+
+
+class FillKindAbi(enum.IntEnum):
+    COLORS4 = 0
+    COLOR = 1
+    LINEAR2 = 2
+    LINEAR3 = 3
+
+
+class Op(enum.IntEnum):
+    NOP = 0
+    SAVE_TRANSFORM = 1
+    RESTORE_TRANSFORM = 2
+    TRANSLATE = 3
+    ROTATE = 4
+    SCALE = 5
+    APPLY_TRANSFORM = 6
+    SET_AA = 7
+    BEGIN_MASK = 8
+    END_MASK = 9
+    POP_MASK = 10
+    BEGIN_RECT_MASK = 11
+    POP_RECT_MASK = 12
+    BACKDROP_BLUR = 13
+    SET_SUBPIXEL = 14
+    ROUNDED_RECT = 32
+    IMAGE = 33
+    MSDF = 34
+    BEZIER = 35
+    FILLED_QUAD = 36
+    RECT = 37
+
+
+FIRST_DRAW_OP = 32
+
+CALL_DTYPE = np.dtype([("op", "<u4"), ("u", "<u4", (9,)), ("f", "<f4", (22,))])
+assert CALL_DTYPE.itemsize == 128
+
+
+class FdcFill(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_uint32),
+        ("axis", ctypes.c_uint32),
+        ("c", ctypes.c_uint32 * 4),
+        ("mid_pos", ctypes.c_float),
+    ]
+
+
+class FdcFrameStats(ctypes.Structure):
+    _fields_ = [
+        ("n_prims", ctypes.c_uint32),
+        ("n_segments", ctypes.c_uint32),
+        ("tiles_x", ctypes.c_uint32),
+        ("tiles_y", ctypes.c_uint32),
+        ("tile_w", ctypes.c_uint32),
+        ("tile_h", ctypes.c_uint32),
+        ("n_tile_entries", ctypes.c_uint64),
+        ("n_launches", ctypes.c_uint32),
+        ("gpu_ms", ctypes.c_float),
+        ("shade_ms", ctypes.c_float),
+        ("bin_ms", ctypes.c_float),
+        ("blur_ms", ctypes.c_float),
+    ]
+
+
+# Every symbol include/figdraw_cuda.h declares (checked by tests/test_abi.py against the header text).
+EXPORTS = [
+    "fdc_create", "fdc_destroy", "fdc_last_error", "fdc_abi_version",
+    "fdc_begin_frame", "fdc_end_frame", "fdc_read_pixels", "fdc_sync",
+    "fdc_translate", "fdc_rotate", "fdc_scale", "fdc_apply_transform", "fdc_save_transform",
+    "fdc_restore_transform", "fdc_transform_mirrors_y", "fdc_get_transform",
+    "fdc_sdf_aa_factor", "fdc_set_sdf_aa_factor", "fdc_set_text_subpixel_positioning_enabled",
+    "fdc_set_text_subpixel_shift", "fdc_pixel_scale",
+    "fdc_draw_rounded_rect_sdf", "fdc_draw_image", "fdc_draw_msdf_image", "fdc_draw_quadratic_bezier_sdf",
+    "fdc_draw_filled_quad", "fdc_draw_rect", "fdc_draw_backdrop_blur",
+    "fdc_begin_mask", "fdc_end_mask", "fdc_pop_mask", "fdc_begin_rect_mask", "fdc_pop_rect_mask",
+    "fdc_submit_calls",
+    "fdc_put_image", "fdc_update_image", "fdc_has_image", "fdc_get_image_rect", "fdc_remove_image",
+    "fdc_reset_image_atlas", "fdc_atlas_size", "fdc_atlas_packed_area",
+    "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers",
+    "fdc_get_frame_stats", "fdc_debug_bins",
+]
+
+_LIB: Optional[ctypes.CDLL] = None
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libfigdraw_cuda.so")
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libfigdraw_cuda.so (built in-tree by `__graft_entry__.build()`); raises if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"figdraw_b200: CUDA extension {path} is not built. Run `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (needs nvcc). There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(path)
+    c = ctypes
+    P = c.c_void_p
+    fp = c.POINTER(c.c_float)
+    u32p = c.POINTER(c.c_uint32)
+
+    def sig(name, res, *args):
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = list(args)
+
+    sig("fdc_create", c.c_int, c.POINTER(P), c.c_int, c.c_int, c.c_float, c.c_int, c.c_int)
+    sig("fdc_destroy", None, P)
+    sig("fdc_last_error", c.c_char_p, P)
+    sig("fdc_abi_version", c.c_int)
+    sig("fdc_begin_frame", c.c_int, P, c.c_int, c.c_int, c.c_int, fp)
+    sig("fdc_end_frame", c.c_int, P)
+    sig("fdc_read_pixels", c.c_int, P, c.c_int, c.c_int, c.c_int, c.c_int, P)
+    sig("fdc_sync", c.c_int, P)
+    sig("fdc_translate", c.c_int, P, c.c_float, c.c_float)
+    sig("fdc_rotate", c.c_int, P, c.c_float)
+    sig("fdc_scale", c.c_int, P, c.c_float, c.c_float)
+    sig("fdc_apply_transform", c.c_int, P, fp)
+    sig("fdc_save_transform", c.c_int, P)
+    sig("fdc_restore_transform", c.c_int, P)
+    sig("fdc_transform_mirrors_y", c.c_int, P)
+    sig("fdc_get_transform", c.c_int, P, fp)
+    sig("fdc_sdf_aa_factor", c.c_float, P)
+    sig("fdc_set_sdf_aa_factor", c.c_int, P, c.c_float)
+    sig("fdc_set_text_subpixel_positioning_enabled", c.c_int, P, c.c_int)
+    sig("fdc_set_text_subpixel_shift", c.c_int, P, c.c_float)
+    sig("fdc_pixel_scale", c.c_float, P)
+    sig("fdc_draw_rounded_rect_sdf", c.c_int, P, fp, c.POINTER(FdcFill), fp, fp, c.c_int, c.c_float, c.c_float, fp)
+    sig("fdc_draw_image", c.c_int, P, c.c_uint64, fp, u32p, fp, c.c_int)
+    sig("fdc_draw_msdf_image", c.c_int, P, c.c_uint64, fp, c.c_uint32, fp, c.c_float, c.c_float, c.c_float,
+        c.c_int, c.c_int)
+    sig("fdc_draw_quadratic_bezier_sdf", c.c_int, P, fp, c.POINTER(FdcFill), fp, fp, fp, c.c_float, c.c_int)
+    sig("fdc_draw_filled_quad", c.c_int, P, fp, u32p)
+    sig("fdc_draw_rect", c.c_int, P, fp, c.c_uint32)
+    sig("fdc_draw_backdrop_blur", c.c_int, P, fp, fp, fp, c.c_float)
+    sig("fdc_begin_mask", c.c_int, P, fp, fp, fp)
+    sig("fdc_end_mask", c.c_int, P)
+    sig("fdc_pop_mask", c.c_int, P)
+    sig("fdc_begin_rect_mask", c.c_int, P, fp, fp, fp)
+    sig("fdc_pop_rect_mask", c.c_int, P)
+    sig("fdc_submit_calls", c.c_int, P, P, c.c_size_t)
+    sig("fdc_put_image", c.c_int, P, c.c_uint64, c.c_int, c.c_int, P, fp, c.POINTER(c.c_int))
+    sig("fdc_update_image", c.c_int, P, c.c_uint64, c.c_int, c.c_int, P)
+    sig("fdc_has_image", c.c_int, P, c.c_uint64)
+    sig("fdc_get_image_rect", c.c_int, P, c.c_uint64, fp)
+    sig("fdc_remove_image", c.c_int, P, c.c_uint64)
+    sig("fdc_reset_image_atlas", c.c_int, P, c.c_int)
+    sig("fdc_atlas_size", c.c_int, P)
+    sig("fdc_atlas_packed_area", c.c_int, P)
+    sig("fdc_bind_framebuffer", c.c_int, P, P)
+    sig("fdc_framebuffer_ptr", P, P)
+    sig("fdc_band_rows", c.c_int, P, c.POINTER(c.c_int), c.POINTER(c.c_int))
+    sig("fdc_stream", P, P)
+    sig("fdc_set_peer_framebuffers", c.c_int, P, c.POINTER(P), c.c_int)
+    sig("fdc_get_frame_stats", c.c_int, P, c.POINTER(FdcFrameStats))
+    sig("fdc_debug_bins", c.c_int, P, c.c_int, u32p, c.c_size_t, u32p, c.c_size_t, c.POINTER(c.c_size_t),
+        c.POINTER(c.c_size_t))
+    if lib.fdc_abi_version() != ABI_VERSION:
+        raise RuntimeError("figdraw_b200: libfigdraw_cuda.so ABI version mismatch; rebuild")
+    _LIB = lib
+    return lib

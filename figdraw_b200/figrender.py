@@ -1,0 +1,482 @@
+"""Front-end: host-side restatement of the `figdraw/figrender` frame entry.
+
+The reference's front-end (src/figdraw/figrender.nim) stays Nim and is reused unchanged on top of the
+new backend; it cannot be compiled in this image (no Nim), so this module restates the part of it
+that decides WHICH backend calls are made, in WHAT order, with WHAT parameters:
+
+  renderFrame   figrender.nim:1960-2002      renderRoot   :1946-1958
+  render        :1756-1839 (stage order)     renderDropShadows :654-689   renderInnerShadows :716-744
+  renderRoundedShapeScaledCorners :806-873   renderText :417-497 (glyph loop only)
+  renderImage/renderMsdfImage/renderMtsdfImage/renderBackdropBlur :1673-1754
+  renderDrawableLine :946-995, Circle :1122-1136, Rect :1138-1142, Ellipse :1617-1635,
+  renderDrawableQuadraticBezierSdf :1330-1370 (3-control Beziers only)
+
+It drives any `BackendContext` (figbackend.py): the trace recorder, the CUDA context, or a test fake.
+All arithmetic the reference does in float32 is float32 here.
+"""
+from __future__ import annotations
+
+import math
+from typing import Sequence
+
+import numpy as np
+
+from .abi import SdfMode
+from .figbackend import BackendContext, BackendFill, ZeroRadii, colors4, solid, toBackendFill
+from .fignodes import (DrawableKind, DrawableOp, Fig, FigFlags, FigKind, Fill, FillGradientAxis, FillKind, Rect,
+                       RenderList, Renders, RenderStroke, ShadowStyle, StrokeCap, f32, rgba, rgba_tuple)
+
+_uiScale = f32(1.0)
+
+
+def setFigUiScale(scale: float) -> None:
+    """common/shared.nim:67-71."""
+    global _uiScale
+    _uiScale = f32(scale)
+
+
+def figUiScale() -> float:
+    return float(_uiScale)
+
+
+def _round(x) -> np.float32:
+    """Nim `round`: half away from zero."""
+    x = float(x)
+    return f32(math.copysign(math.floor(abs(x) + 0.5), x))
+
+
+def scaled(v):
+    if isinstance(v, Rect):
+        return v.scaled(_uiScale)
+    if isinstance(v, (tuple, list)):
+        return tuple(f32(c) * _uiScale for c in v)
+    return f32(v) * _uiScale
+
+
+# ----------------------------------------------------------------------------- fill helpers (figrender.nim:580-640)
+def _lerpColor(a: int, b: int, t) -> int:
+    t = min(max(f32(t), f32(0)), f32(1))
+    inv = f32(1) - t
+    ca, cb = rgba_tuple(a), rgba_tuple(b)
+    return rgba(*[int(_round(f32(x) * inv + f32(y) * t)) for x, y in zip(ca, cb)])
+
+
+def fillAlphaMax(fill: Fill) -> int:
+    if fill.kind == FillKind.flColor:
+        return (fill.color >> 24) & 255
+    if fill.kind == FillKind.flLinear2:
+        return max((fill.start >> 24) & 255, (fill.stop >> 24) & 255)
+    return max((fill.start >> 24) & 255, (fill.mid >> 24) & 255, (fill.stop >> 24) & 255)
+
+
+def sampleGradientColor(fill: Fill, t) -> int:
+    if fill.kind == FillKind.flColor:
+        return fill.color
+    if fill.kind == FillKind.flLinear2:
+        return _lerpColor(fill.start, fill.stop, t)
+    ct = min(max(f32(t), f32(0)), f32(1))
+    mid = min(max(f32(fill.midPos) / f32(255.0), f32(0.01)), f32(0.99))
+    if ct <= mid:
+        return _lerpColor(fill.start, fill.mid, ct / mid)
+    return _lerpColor(fill.mid, fill.stop, (ct - mid) / (f32(1) - mid))
+
+
+def fillCenterColor(fill: Fill) -> int:
+    return sampleGradientColor(fill, 0.5)
+
+
+def gradientColors(fill: Fill):
+    """figrender.nim:623-647; vertex order BL, BR, TR, TL."""
+    ax = fill.axis if fill.kind != FillKind.flColor else FillGradientAxis.fgaX
+    ts = {
+        FillGradientAxis.fgaX: (0.0, 1.0, 1.0, 0.0),
+        FillGradientAxis.fgaY: (1.0, 1.0, 0.0, 0.0),
+        FillGradientAxis.fgaDiagTLBR: (0.5, 1.0, 0.5, 0.0),
+        FillGradientAxis.fgaDiagBLTR: (0.0, 0.5, 1.0, 0.5),
+    }[ax]
+    return [sampleGradientColor(fill, t) for t in ts]
+
+
+# ----------------------------------------------------------------------------- corners (figrender.nim:549-571)
+def _scaledCorners(x: Sequence[float], y: Sequence[float]):
+    return (tuple(float(f32(v) * _uiScale) for v in x), tuple(float(f32(v) * _uiScale) for v in y))
+
+
+def nodeScaledCorners(node: Fig):
+    y = node.cornerRadiiY if (node.flags & FigFlags.NfEllipticalCorners) else node.corners
+    return _scaledCorners(node.corners, y)
+
+
+def _radiusCorner(radius) -> int:
+    if radius <= 0.0:
+        return 0
+    if radius >= 65535.0:
+        return 65535
+    return int(_round(radius))
+
+
+# ----------------------------------------------------------------------------- shadows
+def renderDropShadows(ctx: BackendContext, node: Fig) -> None:
+    for shadow in node.shadows:
+        if shadow.style != ShadowStyle.DropShadow:
+            continue
+        if shadow.blur <= 0.0 and shadow.spread <= 0.0:
+            continue
+        if fillAlphaMax(shadow.fill) == 0:
+            continue
+        box = scaled(node.screenBox)
+        sx, sy = scaled(shadow.x), scaled(shadow.y)
+        blur, spread = scaled(shadow.blur), scaled(shadow.spread)
+        blurPad = _round(f32(1.5) * blur)
+        pad = max(_round(spread) + blurPad, f32(0))
+        srx, sry, srw, srh = box.x + sx, box.y + sy, box.w + f32(0), box.h + f32(0)
+        quad = (srx - pad, sry - pad, srw + f32(2) * pad, srh + f32(2) * pad)
+        ctx.drawRoundedRectSdf(
+            rect=tuple(float(v) for v in quad),
+            fill=toBackendFill(shadow.fill),
+            radii=nodeScaledCorners(node),
+            mode=SdfMode.sdfModeDropShadow,
+            factor=float(blur),
+            spread=float(spread),
+            shapeSize=(float(srw), float(srh)),
+        )
+
+
+def hasActiveInnerShadow(node: Fig) -> bool:
+    for shadow in node.shadows:
+        if shadow.style != ShadowStyle.InnerShadow:
+            continue
+        if shadow.blur <= 0.0 and shadow.spread <= 0.0:
+            continue
+        if fillAlphaMax(shadow.fill) == 0:
+            continue
+        return True
+    return False
+
+
+def renderInnerShadows(ctx: BackendContext, node: Fig) -> None:
+    for shadow in node.shadows:
+        if shadow.style != ShadowStyle.InnerShadow:
+            continue
+        if shadow.blur <= 0.0 and shadow.spread <= 0.0:
+            continue
+        if fillAlphaMax(shadow.fill) == 0:
+            continue
+        ctx.drawRoundedRectSdf(
+            rect=scaled(node.screenBox).tuple(),
+            fill=toBackendFill(shadow.fill),
+            radii=nodeScaledCorners(node),
+            mode=SdfMode.sdfModeInsetShadow,
+            factor=float(scaled(shadow.blur)),
+            spread=float(scaled(shadow.spread)),
+            shapeSize=(float(scaled(shadow.x)), float(scaled(shadow.y))),
+        )
+
+
+# ----------------------------------------------------------------------------- boxes
+def renderRoundedShapeScaledCorners(ctx, shapeBox: Rect, shapeFill: Fill, shapeStroke: RenderStroke, corners) -> None:
+    """figrender.nim:806-873 (SDF branch)."""
+    box = scaled(shapeBox).tuple()
+    hasGradient = shapeFill.kind in (FillKind.flLinear2, FillKind.flLinear3) and fillAlphaMax(shapeFill) > 0
+    if hasGradient:
+        ctx.drawRoundedRectSdf(rect=box, fill=toBackendFill(shapeFill), radii=corners, mode=SdfMode.sdfModeClipAA,
+                               factor=4.0, spread=0.0, shapeSize=(0.0, 0.0))
+    elif fillAlphaMax(shapeFill) > 0:
+        ctx.drawRoundedRectSdf(rect=box, fill=solid(fillCenterColor(shapeFill)), radii=corners,
+                               mode=SdfMode.sdfModeClipAA, factor=4.0, spread=0.0, shapeSize=(0.0, 0.0))
+    if fillAlphaMax(shapeStroke.fill) > 0 and shapeStroke.weight > 0:
+        ctx.drawRoundedRectSdf(rect=box, fill=toBackendFill(shapeStroke.fill), radii=corners,
+                               mode=SdfMode.sdfModeAnnularAA, factor=float(scaled(shapeStroke.weight)), spread=0.0,
+                               shapeSize=(0.0, 0.0))
+
+
+def renderRoundedShape(ctx, shapeBox, shapeFill, shapeStroke, cornersX, cornersY=None) -> None:
+    cornersY = cornersX if cornersY is None else cornersY
+    renderRoundedShapeScaledCorners(ctx, shapeBox, shapeFill, shapeStroke, _scaledCorners(cornersX, cornersY))
+
+
+def renderBoxes(ctx, node: Fig) -> None:
+    y = node.cornerRadiiY if (node.flags & FigFlags.NfEllipticalCorners) else node.corners
+    renderRoundedShape(ctx, node.screenBox, node.fill, node.stroke, node.corners, y)
+
+
+# ----------------------------------------------------------------------------- drawables
+def _vlen(x, y) -> np.float32:
+    return f32(math.sqrt(float(f32(x) * f32(x) + f32(y) * f32(y))))
+
+
+def renderDrawableStrokeCap(ctx, center, radius, fill: Fill) -> None:
+    radius = f32(radius)
+    if radius <= 0.0 or fillAlphaMax(fill) == 0:
+        return
+    d = radius * f32(2)
+    box = Rect(f32(center[0]) - radius, f32(center[1]) - radius, d, d)
+    rc = _radiusCorner(radius)
+    renderRoundedShape(ctx, box, fill, RenderStroke(), (rc, rc, rc, rc))
+
+
+def renderDrawableLine(ctx, origin, op: DrawableOp, stroke: RenderStroke) -> None:
+    """figrender.nim:946-995: a rotated zero-radius box (+ round caps)."""
+    weight = max(f32(0), f32(stroke.weight))
+    if weight <= 0.0 or fillAlphaMax(stroke.fill) == 0:
+        return
+    ax, ay = f32(origin[0]) + f32(op.a[0]), f32(origin[1]) + f32(op.a[1])
+    bx, by = f32(origin[0]) + f32(op.b[0]), f32(origin[1]) + f32(op.b[1])
+    dx, dy = bx - ax, by - ay
+    length = _vlen(dx, dy)
+    if length <= 0.0:
+        return
+    cap = StrokeCap.scButt if stroke.cap == StrokeCap.scAuto else stroke.cap
+    capRadius = weight * f32(0.5)
+    dirx, diry = dx / length, dy / length
+    dax, day, dbx, dby, drawLength = ax, ay, bx, by, length
+    if cap == StrokeCap.scSquare:
+        dax, day = ax - dirx * capRadius, ay - diry * capRadius
+        dbx, dby = bx + dirx * capRadius, by + diry * capRadius
+        drawLength = length + weight
+    cx, cy = (dax + dbx) / f32(2), (day + dby) / f32(2)
+    box = Rect(cx - drawLength / f32(2), cy - weight / f32(2), drawLength, weight)
+    sb = scaled(box)
+    pivot = (sb.x + sb.w / f32(2), sb.y + sb.h / f32(2))
+    angle = f32(math.atan2(float(dy), float(dx)))
+    ctx.saveTransform()
+    try:
+        ctx.translate((float(pivot[0]), float(pivot[1])))
+        ctx.rotate(float(angle))
+        ctx.translate((float(-pivot[0]), float(-pivot[1])))
+        renderRoundedShape(ctx, box, stroke.fill, RenderStroke(), (0, 0, 0, 0))
+    finally:
+        ctx.restoreTransform()
+    if cap == StrokeCap.scRound:
+        renderDrawableStrokeCap(ctx, (ax, ay), capRadius, stroke.fill)
+        renderDrawableStrokeCap(ctx, (bx, by), capRadius, stroke.fill)
+
+
+def _quadraticPoint(p0, p1, p2, t):
+    t = f32(t)
+    inv = f32(1) - t
+    return tuple(f32(a) * (inv * inv) + f32(b) * (f32(2) * inv * t) + f32(c) * (t * t) for a, b, c in zip(p0, p1, p2))
+
+
+def _quadraticBounds(p0, p1, p2, padding):
+    mn = [min(f32(p0[0]), f32(p2[0])), min(f32(p0[1]), f32(p2[1]))]
+    mx = [max(f32(p0[0]), f32(p2[0])), max(f32(p0[1]), f32(p2[1]))]
+    for k in (0, 1):
+        denom = f32(p0[k]) - f32(2) * f32(p1[k]) + f32(p2[k])
+        if abs(denom) > 0.000001:
+            t = (f32(p0[k]) - f32(p1[k])) / denom
+            if 0.0 < t < 1.0:
+                q = _quadraticPoint(p0, p1, p2, t)
+                for j in (0, 1):
+                    mn[j] = min(mn[j], q[j])
+                    mx[j] = max(mx[j], q[j])
+    padding = f32(padding)
+    return Rect(mn[0] - padding, mn[1] - padding, mx[0] - mn[0] + padding * f32(2), mx[1] - mn[1] + padding * f32(2))
+
+
+def renderDrawableQuadraticBezierSdf(ctx, origin, p0, p1, p2, stroke: RenderStroke, cap=StrokeCap.scAuto) -> None:
+    """figrender.nim:1330-1370."""
+    if cap == StrokeCap.scAuto:
+        cap = StrokeCap.scRound if stroke.cap == StrokeCap.scAuto else stroke.cap
+    cr = (f32(p1[0]) - f32(p0[0])) * (f32(p2[1]) - f32(p1[1])) - (f32(p1[1]) - f32(p0[1])) * (f32(p2[0]) - f32(p1[0]))
+    if abs(cr) <= 0.0001:
+        s2 = RenderStroke(weight=stroke.weight, fill=stroke.fill, cap=cap, join=stroke.join)
+        renderDrawableLine(ctx, origin, DrawableOp(kind=DrawableKind.dkLine, a=tuple(p0), b=tuple(p2)), s2)
+        return
+    weight = max(f32(0), f32(stroke.weight))
+    padding = weight * f32(0.5) + f32(2.0) / _uiScale
+    a = (f32(origin[0]) + f32(p0[0]), f32(origin[1]) + f32(p0[1]))
+    b = (f32(origin[0]) + f32(p1[0]), f32(origin[1]) + f32(p1[1]))
+    c = (f32(origin[0]) + f32(p2[0]), f32(origin[1]) + f32(p2[1]))
+    box = _quadraticBounds(a, b, c, padding)
+    if box.w <= 0.0 or box.h <= 0.0:
+        return
+    cx, cy = box.x + box.w * f32(0.5), box.y + box.h * f32(0.5)
+    loc = lambda p: (float((p[0] - cx) * _uiScale), float((p[1] - cy) * _uiScale))
+    ctx.drawQuadraticBezierSdf(rect=scaled(box).tuple(), fill=toBackendFill(stroke.fill), p0=loc(a), p1=loc(b),
+                               p2=loc(c), strokeWeight=float(scaled(weight)), cap=int(cap))
+
+
+def renderDrawableOps(ctx, node: Fig) -> None:
+    origin = (node.screenBox.x, node.screenBox.y)
+    fill, stroke = node.fill, node.drawStroke
+    for op in node.drawOps:
+        if op.kind == DrawableKind.dkLine:
+            renderDrawableLine(ctx, origin, op, stroke)
+        elif op.kind == DrawableKind.dkCircle:
+            radius = max(f32(0), f32(op.radius))
+            if radius <= 0.0:
+                continue
+            d = radius * f32(2)
+            box = Rect(origin[0] + f32(op.center[0]) - radius, origin[1] + f32(op.center[1]) - radius, d, d)
+            rc = _radiusCorner(radius)
+            renderRoundedShape(ctx, box, fill, stroke, (rc, rc, rc, rc))
+        elif op.kind == DrawableKind.dkRectangle:
+            box = Rect(origin[0] + op.box.x, origin[1] + op.box.y, op.box.w, op.box.h)
+            renderRoundedShape(ctx, box, fill, stroke, op.corners)
+        elif op.kind == DrawableKind.dkEllipse:
+            rx, ry = max(f32(0), f32(op.ellipseRadii[0])), max(f32(0), f32(op.ellipseRadii[1]))
+            if rx <= 0.0 or ry <= 0.0:
+                continue
+            box = Rect(origin[0] + f32(op.center[0]) - rx, origin[1] + f32(op.center[1]) - ry, rx * f32(2), ry * f32(2))
+            renderRoundedShape(ctx, box, fill, stroke, (rx,) * 4, (ry,) * 4)
+        elif op.kind == DrawableKind.dkBezier:
+            if len(op.controls) != 3:
+                raise NotImplementedError("only 3-control Beziers are restated (figrender.nim:1507-1517)")
+            if stroke.weight <= 0.0 or fillAlphaMax(stroke.fill) == 0:
+                continue
+            renderDrawableQuadraticBezierSdf(ctx, origin, op.controls[0], op.controls[1], op.controls[2], stroke)
+        else:
+            raise NotImplementedError(f"drawable op {op.kind!r}: upstream of the hot path, not restated")
+
+
+def renderDrawable(ctx, node: Fig) -> None:
+    """figrender.nim:1653-1667."""
+    if node.drawAa <= 0.0:
+        renderDrawableOps(ctx, node)
+        return
+    oldAa = ctx.sdfAaFactor()
+    if oldAa == node.drawAa:
+        renderDrawableOps(ctx, node)
+        return
+    ctx.setSdfAaFactor(node.drawAa)
+    try:
+        renderDrawableOps(ctx, node)
+    finally:
+        ctx.setSdfAaFactor(oldAa)
+
+
+# ----------------------------------------------------------------------------- text / images / blur
+def renderText(ctx, node: Fig) -> None:
+    """figrender.nim:417-497, glyph loop: one atlas quad per glyph, 4 vertex colours from the span fill."""
+    ctx.saveTransform()
+    ctx.translate((float(scaled(node.screenBox.x)), float(scaled(node.screenBox.y))))
+    if node.flags & FigFlags.NfInvertY:
+        ctx.translate((0.0, float(scaled(node.screenBox.h))))
+        ctx.scale((1.0, -1.0))
+    for glyph in node.glyphs:
+        ctx.setTextSubpixelShift(0.0)
+        if not ctx.hasImage(glyph.key):
+            continue
+        ctx.drawImage(glyph.key, (float(glyph.pos[0]), float(glyph.pos[1])), gradientColors(glyph.fill), (0.0, 0.0),
+                      False)
+    ctx.setTextSubpixelShift(0.0)
+    ctx.restoreTransform()
+
+
+def renderImage(ctx, node: Fig) -> None:
+    if node.image.id == 0:
+        return
+    box = scaled(node.screenBox)
+    c = fillCenterColor(node.image.fill)
+    ctx.drawImage(node.image.id, (float(box.x), float(box.y)), [c, c, c, c], (float(box.w), float(box.h)),
+                  bool(node.flags & FigFlags.NfInvertY))
+
+
+def _renderSdfImage(ctx, node: Fig, style, mtsdf: bool) -> None:
+    if style.id == 0:
+        return
+    box = scaled(node.screenBox)
+    pxRange = style.pxRange if style.pxRange > 0.0 else 4.0
+    thr = style.sdThreshold if 0.0 < style.sdThreshold < 1.0 else 0.5
+    sw = float(scaled(max(f32(0), f32(style.strokeWeight))))
+    fn = ctx.drawMtsdfImage if mtsdf else ctx.drawMsdfImage
+    fn(style.id, (float(box.x), float(box.y)), fillCenterColor(style.fill), (float(box.w), float(box.h)), pxRange, thr,
+       sw, bool(node.flags & FigFlags.NfInvertY))
+
+
+def renderBackdropBlur(ctx, node: Fig) -> None:
+    """figrender.nim:1734-1754."""
+    if node.backdropBlur.blur > 0.0:
+        ctx.drawBackdropBlur(scaled(node.screenBox).tuple(), nodeScaledCorners(node),
+                             float(scaled(node.backdropBlur.blur)))
+    if fillAlphaMax(node.fill) == 0:
+        return
+    overlay = Fig(kind=FigKind.nkRectangle, screenBox=node.screenBox, fill=node.fill, corners=node.corners,
+                  cornerRadiiY=node.cornerRadiiY)
+    if node.flags & FigFlags.NfEllipticalCorners:
+        overlay.flags |= FigFlags.NfEllipticalCorners
+    overlay.stroke = RenderStroke(weight=0.0, fill=rgba(0, 0, 0, 0))
+    renderBoxes(ctx, overlay)
+
+
+# ----------------------------------------------------------------------------- the DFS
+def render(ctx: BackendContext, nodes: RenderList, idx: int) -> None:
+    """figrender.nim:1756-1839: paint-order contract.  `finally` stages run in reverse at the end."""
+    node = nodes.nodes[idx]
+    if node.flags & FigFlags.NfDisableRender:
+        return
+    box = scaled(node.screenBox)
+    cleanups = []
+
+    if node.rotation != 0:
+        ctx.saveTransform()
+        c = (float(box.x + box.w / f32(2)), float(box.y + box.h / f32(2)))
+        ctx.translate(c)
+        ctx.rotate(float(f32(node.rotation) / f32(180) * f32(math.pi)))
+        ctx.translate((-c[0], -c[1]))
+        cleanups.append(ctx.restoreTransform)
+
+    if node.kind == FigKind.nkTransform:
+        ctx.saveTransform()
+        tr = node.transform.translation
+        if tr[0] != 0.0 or tr[1] != 0.0:
+            ctx.translate(tuple(float(v) for v in scaled(tr)))
+        if node.transform.useMatrix:
+            ctx.applyTransform(node.transform.matrix)
+        cleanups.append(ctx.restoreTransform)
+
+    if node.kind == FigKind.nkRectangle:
+        renderDropShadows(ctx, node)
+
+    if node.flags & FigFlags.NfClipContent:
+        ctx.beginMask(box.tuple(), nodeScaledCorners(node))
+        ctx.endMask()
+        cleanups.append(ctx.popMask)
+
+    if node.flags & FigFlags.NfRectMaskContent:
+        ctx.beginRectMask(box.tuple(), nodeScaledCorners(node))
+        cleanups.append(ctx.popRectMask)
+
+    if node.kind == FigKind.nkText:
+        renderText(ctx, node)
+    elif node.kind == FigKind.nkDrawable:
+        renderDrawable(ctx, node)
+    elif node.kind == FigKind.nkRectangle:
+        renderBoxes(ctx, node)
+    elif node.kind == FigKind.nkImage:
+        renderImage(ctx, node)
+    elif node.kind == FigKind.nkMsdfImage:
+        _renderSdfImage(ctx, node, node.msdfImage, False)
+    elif node.kind == FigKind.nkMtsdfImage:
+        _renderSdfImage(ctx, node, node.mtsdfImage, True)
+    elif node.kind == FigKind.nkBackdropBlur:
+        renderBackdropBlur(ctx, node)
+
+    if node.kind == FigKind.nkRectangle and hasActiveInnerShadow(node):
+        renderInnerShadows(ctx, node)
+
+    for child in nodes.childIndex(idx):
+        render(ctx, nodes, child)
+
+    for fn in reversed(cleanups):
+        fn()
+
+
+def renderRoot(ctx: BackendContext, renders: Renders) -> None:
+    """figrender.nim:1946-1958: layers in table order (NOT sorted), roots in rootIds order."""
+    for _zlvl, lst in renders.pairs():
+        for root in lst.rootIds:
+            render(ctx, lst, root)
+
+
+def renderFrame(ctx: BackendContext, renders: Renders, frameSize, clearMain=True,
+                clearColor=(1.0, 1.0, 1.0, 1.0)) -> None:
+    """figrender.nim:1960-2002."""
+    fs = scaled(tuple(frameSize))
+    ctx.beginFrame((float(fs[0]), float(fs[1])), clearMain=clearMain, clearMainColor=clearColor)
+    ctx.saveTransform()
+    ctx.scale(ctx.pixelScale())
+    renderRoot(ctx, renders)
+    ctx.restoreTransform()
+    ctx.endFrame()

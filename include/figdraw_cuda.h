@@ -1,0 +1,254 @@
+/*
+ * figdraw_cuda.h -- C ABI of the B200 (sm_100a) render backend for figdraw.
+ *
+ * This is the drop-in boundary for ONE path of elcritch/figdraw: the backend half of the
+ * `figdraw/figrender` frame entry, i.e. what `src/figdraw/opengl/glcontext.nim` plus
+ * `src/figdraw/opengl/glsl/{atlas,atlas_rect_mask,mask,blur}.frag` do today.  Each entry point
+ * replaces one `method` of `BackendContext` (`src/figdraw/figbackend.nim:185-705`), as overridden by
+ * `OpenGlContext`; the reference file:line each one replaces is cited beside it.  A Nim
+ * `CudaContext = ref object of BackendContext` forwards every method to the function of the same
+ * meaning through `{.importc.}` (see INTEGRATION.md and bindings/nim/cuda_context.nim).
+ *
+ * Conventions
+ *  - Plain C: pointers, sizes, POD structs.  No torch / C++ types cross this boundary.
+ *  - Handle based, no globals: several contexts may coexist (multi-window tests in the reference).
+ *  - All calls on one context come from ONE thread (the reference's render thread,
+ *    `figrender.nim:1758` `forbids: [AppMainThreadEff]`).
+ *  - Every function returning `int` returns FDC_OK (0) or an fdc_status error code;
+ *    `fdc_last_error(ctx)` gives the message.  The Nim shim turns non-zero into `FigDrawError`.
+ *  - There is NO CPU fallback: without a usable CUDA device `fdc_create` fails with FDC_ERR_CUDA.
+ *  - Colours are straight-alpha RGBA8 packed little-endian in a uint32_t: r | g<<8 | b<<16 | a<<24
+ *    (the byte order of chroma's `ColorRGBA`).
+ *  - Corner arrays are in `DirectionCorners` order: TopLeft, TopRight, BottomLeft, BottomRight
+ *    (`figbasics.nim:24-28`).  Vertex colour arrays are BL, BR, TR, TL (`figbackend.nim:162`).
+ *  - Matrices are vmath `Mat4`: 16 floats, column-major, m[col*4+row].
+ */
+#ifndef FIGDRAW_CUDA_H
+#define FIGDRAW_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDC_ABI_VERSION 1
+
+typedef struct fdc_ctx fdc_ctx; /* opaque; one per BackendContext */
+
+typedef enum fdc_status {
+  FDC_OK = 0,
+  FDC_ERR_INVALID = 1,     /* bad argument */
+  FDC_ERR_CUDA = 2,        /* CUDA runtime/driver failure, or no device */
+  FDC_ERR_STATE = 3,       /* call order violated (asserts in glcontext.nim:1888-1889, :1985-1986) */
+  FDC_ERR_CAPACITY = 4,    /* a documented fixed limit was exceeded (mask depth) */
+  FDC_ERR_MISSING_IMAGE = 5 /* draw of an image key that is not in the atlas (warn + skip in GL) */
+} fdc_status;
+
+/* `SdfMode` -- values identical to figbackend.nim:36-52. */
+typedef enum fdc_sdf_mode {
+  FDC_SDF_ATLAS = 0,
+  FDC_SDF_CLIP_AA = 3,
+  FDC_SDF_DROP_SHADOW = 7,
+  FDC_SDF_DROP_SHADOW_AA = 8,
+  FDC_SDF_INSET_SHADOW = 9,
+  FDC_SDF_INSET_SHADOW_ANNULAR = 10,
+  FDC_SDF_ANNULAR = 11,
+  FDC_SDF_ANNULAR_AA = 12,
+  FDC_SDF_MSDF = 13,
+  FDC_SDF_MTSDF = 14,
+  FDC_SDF_MSDF_ANNULAR = 15,
+  FDC_SDF_MTSDF_ANNULAR = 16,
+  FDC_SDF_BACKDROP_BLUR = 17,
+  FDC_SDF_BEZIER_STROKE_AA = 18,
+  FDC_SDF_BEZIER_STROKE_BUTT_AA = 19,
+  FDC_SDF_BEZIER_STROKE_SQUARE_AA = 20
+} fdc_sdf_mode;
+
+/* `FillGradientAxis` (common/filltypes.nim:12-16) and `BackendFillKind` (figbackend.nim:91-94). */
+typedef enum fdc_axis { FDC_AXIS_X = 0, FDC_AXIS_Y = 1, FDC_AXIS_DIAG_TLBR = 2, FDC_AXIS_DIAG_BLTR = 3 } fdc_axis;
+typedef enum fdc_fill_kind {
+  FDC_FILL_COLORS4 = 0, /* explicit vertex colours BL,BR,TR,TL (the `colors: array[4,ColorRGBA]` overload) */
+  FDC_FILL_COLOR = 1,   /* bfColor   : c[0] */
+  FDC_FILL_LINEAR2 = 2, /* bfLinear2 : c[0]=start c[1]=stop */
+  FDC_FILL_LINEAR3 = 3  /* bfLinear3 : c[0]=start c[1]=mid c[2]=stop, mid_pos in [0.01,0.99] */
+} fdc_fill_kind;
+
+/* `StrokeCap` (figbasics.nim:62-66). */
+typedef enum fdc_cap { FDC_CAP_AUTO = 0, FDC_CAP_ROUND = 1, FDC_CAP_BUTT = 2, FDC_CAP_SQUARE = 3 } fdc_cap;
+
+/* `BackendFill` (figbackend.nim:96-107) flattened. */
+typedef struct fdc_fill {
+  uint32_t kind;  /* fdc_fill_kind */
+  uint32_t axis;  /* fdc_axis */
+  uint32_t c[4];  /* packed RGBA8, meaning by kind */
+  float mid_pos;  /* lin3MidPos */
+} fdc_fill;
+
+/* ---------------------------------------------------------------------------------------------
+ * Display-list record.  One 128-byte record per backend call; `fdc_submit_calls` replays an array of
+ * them exactly as if the corresponding fdc_* functions had been called one by one.  The same array is
+ * what the test oracle consumes, so both sides see identical input bytes.
+ * ------------------------------------------------------------------------------------------- */
+typedef enum fdc_op {
+  FDC_OP_NOP = 0,
+  FDC_OP_SAVE_TRANSFORM = 1,
+  FDC_OP_RESTORE_TRANSFORM = 2,
+  FDC_OP_TRANSLATE = 3,        /* f[0..1] */
+  FDC_OP_ROTATE = 4,           /* f[0] radians */
+  FDC_OP_SCALE = 5,            /* f[0..1] */
+  FDC_OP_APPLY_TRANSFORM = 6,  /* f[0..15] Mat4 */
+  FDC_OP_SET_AA = 7,           /* f[0] */
+  FDC_OP_BEGIN_MASK = 8,       /* f[0..3] rect, f[4..7] radii.x, f[8..11] radii.y */
+  FDC_OP_END_MASK = 9,
+  FDC_OP_POP_MASK = 10,
+  FDC_OP_BEGIN_RECT_MASK = 11, /* as BEGIN_MASK */
+  FDC_OP_POP_RECT_MASK = 12,
+  FDC_OP_BACKDROP_BLUR = 13,   /* f[0..3] rect, f[4..11] radii, f[12] blurRadius */
+  FDC_OP_SET_SUBPIXEL = 14,    /* u[0] positioning enabled, f[0] shift */
+  /* draws */
+  FDC_OP_ROUNDED_RECT = 32,    /* f[0..3] rect, f[4..7] radii.x, f[8..11] radii.y, f[12] factor, f[13] spread,
+                                  f[14..15] shapeSize, f[16] mid_pos; u[0] SdfMode, u[1] fill kind, u[2] axis,
+                                  u[3..6] fill.c[0..3] */
+  FDC_OP_IMAGE = 33,           /* u[0..1] key lo/hi, u[3..6] colours BL,BR,TR,TL, u[7] flipY; f[0..1] pos, f[2..3] size */
+  FDC_OP_MSDF = 34,            /* u[0..1] key, u[2] 1=MTSDF, u[3] colour, u[7] flipY; f[0..1] pos, f[2..3] size,
+                                  f[4] pxRange, f[5] sdThreshold, f[6] strokeWeight */
+  FDC_OP_BEZIER = 35,          /* f[0..3] rect, f[4..5] p0, f[6..7] p1, f[8..9] p2, f[10] strokeWeight, f[16] mid_pos;
+                                  u[0] StrokeCap, u[1] fill kind, u[2] axis, u[3..6] fill.c */
+  FDC_OP_FILLED_QUAD = 36,     /* f[0..7] four vertices, u[3..6] colours */
+  FDC_OP_RECT = 37             /* f[0..3] rect, u[3] colour (legacy drawRect) */
+} fdc_op;
+
+typedef struct fdc_call {
+  uint32_t op;   /* fdc_op */
+  uint32_t u[9];
+  float f[22];
+} fdc_call; /* sizeof == 128 */
+
+/* ---------------------------------------------------------------------------------------------
+ * Context lifetime.  Replaces `newContext` (glcontext.nim:255-535).
+ *   device     : CUDA ordinal.
+ *   atlas_size : initial atlas edge in texels (GL default 1024), atlas margin is 4 (glcontext.nim:257).
+ *   pixel_scale: `pixelScale` (glcontext.nim:260); returned by fdc_pixel_scale.
+ *   rank/n_ranks: tile-band partition for multi-GPU.  Rank r shades tile rows
+ *               [r*ceil(rows/n), min(rows,(r+1)*ceil(rows/n))) of every frame and leaves other
+ *               rows untouched; n_ranks = 1 renders the full frame.
+ * ------------------------------------------------------------------------------------------- */
+int fdc_create(fdc_ctx** out, int device, int atlas_size, float pixel_scale, int rank, int n_ranks);
+void fdc_destroy(fdc_ctx* ctx);
+const char* fdc_last_error(fdc_ctx* ctx); /* ctx may be NULL: message of the last failed fdc_create */
+int fdc_abi_version(void);
+
+/* --- frame: beginFrame glcontext.nim:2080-2092 (+beginFrameProj :1951-1980), endFrame :1982-1989 --- */
+/* clear_main = 0 keeps the previous frame's pixels, as GL keeps the back buffer. */
+int fdc_begin_frame(fdc_ctx* ctx, int width, int height, int clear_main, const float clear_rgba[4]);
+/* Launches the frame's kernels on the context stream; asynchronous. */
+int fdc_end_frame(fdc_ctx* ctx);
+/* readPixels glcontext.nim:2094-2135: RGBA8, top-left origin, tightly packed; w<=0||h<=0 reads the whole frame.
+ * Synchronises the context stream. */
+int fdc_read_pixels(fdc_ctx* ctx, int x, int y, int w, int h, uint8_t* out_rgba);
+/* Blocks until all submitted frames are complete. */
+int fdc_sync(fdc_ctx* ctx);
+
+/* --- transforms: glcontext.nim:1991-2017 --- */
+int fdc_translate(fdc_ctx* ctx, float x, float y);
+int fdc_rotate(fdc_ctx* ctx, float angle);
+int fdc_scale(fdc_ctx* ctx, float sx, float sy); /* scale(float32) is sx == sy */
+int fdc_apply_transform(fdc_ctx* ctx, const float mat4[16]);
+int fdc_save_transform(fdc_ctx* ctx);
+int fdc_restore_transform(fdc_ctx* ctx);
+int fdc_transform_mirrors_y(fdc_ctx* ctx); /* returns 0/1; glcontext.nim:2019-2024 */
+int fdc_get_transform(fdc_ctx* ctx, float out_mat4[16]);
+
+/* --- AA factor and text flags: glcontext.nim:1157-1167, :2052-2077 --- */
+float fdc_sdf_aa_factor(fdc_ctx* ctx);
+int fdc_set_sdf_aa_factor(fdc_ctx* ctx, float aa);
+int fdc_set_text_subpixel_positioning_enabled(fdc_ctx* ctx, int enabled);
+int fdc_set_text_subpixel_shift(fdc_ctx* ctx, float shift);
+float fdc_pixel_scale(fdc_ctx* ctx);
+
+/* --- draws --- */
+/* drawRoundedRectSdf, all three overloads (glcontext.nim:1420-1617): `fill->kind` selects which. */
+int fdc_draw_rounded_rect_sdf(fdc_ctx* ctx, const float rect[4], const fdc_fill* fill, const float radii_x[4],
+                              const float radii_y[4], int mode, float factor, float spread, const float shape_size[2]);
+/* drawImage(path, pos, colors, size, flipY) glcontext.nim:1350-1367; size<=0 draws 1:1 texels. */
+int fdc_draw_image(fdc_ctx* ctx, uint64_t key, const float pos[2], const uint32_t colors[4], const float size[2],
+                   int flip_y);
+/* drawMsdfImage / drawMtsdfImage glcontext.nim:1097-1155. */
+int fdc_draw_msdf_image(fdc_ctx* ctx, uint64_t key, const float pos[2], uint32_t color, const float size[2],
+                        float px_range, float sd_threshold, float stroke_weight, int flip_y, int is_mtsdf);
+/* drawQuadraticBezierSdf glcontext.nim:1619-1741. */
+int fdc_draw_quadratic_bezier_sdf(fdc_ctx* ctx, const float rect[4], const fdc_fill* fill, const float p0[2],
+                                  const float p1[2], const float p2[2], float stroke_weight, int cap);
+/* drawFilledQuad glcontext.nim:963-982. */
+int fdc_draw_filled_quad(fdc_ctx* ctx, const float verts[8], const uint32_t colors[4]);
+/* drawRect glcontext.nim:1402-1418 (legacy). */
+int fdc_draw_rect(fdc_ctx* ctx, const float rect[4], uint32_t color);
+/* drawBackdropBlur glcontext.nim:1788-1841 (+ runBackdropSeparableBlur :1743-1786). */
+int fdc_draw_backdrop_blur(fdc_ctx* ctx, const float rect[4], const float radii_x[4], const float radii_y[4],
+                           float blur_radius);
+
+/* --- masks: glcontext.nim:1886-1949 --- */
+int fdc_begin_mask(fdc_ctx* ctx, const float rect[4], const float radii_x[4], const float radii_y[4]);
+int fdc_end_mask(fdc_ctx* ctx);
+int fdc_pop_mask(fdc_ctx* ctx);
+int fdc_begin_rect_mask(fdc_ctx* ctx, const float rect[4], const float radii_x[4], const float radii_y[4]);
+int fdc_pop_rect_mask(fdc_ctx* ctx);
+
+/* --- display list --- */
+/* Replays `n` records in order.  Equivalent to the individual calls; runs of draw records are
+ * transferred to the device in one copy straight from `calls`. */
+int fdc_submit_calls(fdc_ctx* ctx, const fdc_call* calls, size_t n);
+
+/* --- atlas: glcontext.nim:536-641, textures.nim:88-119 --- */
+/* putImage: packs (skyline, margin 4), uploads straight-alpha RGBA8 texels + a 2x2-box mip chain.
+ * Re-putting an existing key allocates a new slot like GL does.  `out_rect` receives the
+ * normalised atlas rect (x,y,w,h)/atlasSize that `entries[key]` holds in the reference.
+ * If the atlas is full it doubles (`grow`, glcontext.nim:536-539), drops every entry and returns
+ * FDC_OK with *out_rebuilt = 1: the caller must then `noteAtlasRebuilt()` (replay images). */
+int fdc_put_image(fdc_ctx* ctx, uint64_t key, int w, int h, const uint8_t* rgba, float out_rect[4], int* out_rebuilt);
+/* updateImage glcontext.nim:591-605: same size, in place. */
+int fdc_update_image(fdc_ctx* ctx, uint64_t key, int w, int h, const uint8_t* rgba);
+int fdc_has_image(fdc_ctx* ctx, uint64_t key);
+int fdc_get_image_rect(fdc_ctx* ctx, uint64_t key, float out_rect[4]);
+int fdc_remove_image(fdc_ctx* ctx, uint64_t key);
+int fdc_reset_image_atlas(fdc_ctx* ctx, int minimum_size); /* resetImageAtlas glcontext.nim:634-641 */
+int fdc_atlas_size(fdc_ctx* ctx);
+int fdc_atlas_packed_area(fdc_ctx* ctx);
+
+/* --- multi-GPU / zero-copy plumbing (new; no reference equivalent) --- */
+/* Render into caller-owned device memory (W*H*4 bytes, row pitch W*4) instead of the context's own
+ * framebuffer; NULL restores the internal one.  Lets a host framework all-gather bands in place. */
+int fdc_bind_framebuffer(fdc_ctx* ctx, void* device_rgba8);
+void* fdc_framebuffer_ptr(fdc_ctx* ctx);
+/* Rows [*y0,*y1) this rank owns for the current frame size. */
+int fdc_band_rows(fdc_ctx* ctx, int* y0, int* y1);
+/* The CUDA stream (cudaStream_t) frames are launched on. */
+void* fdc_stream(fdc_ctx* ctx);
+/* Peer framebuffers: when set (n_ranks entries, own entry may be NULL), the shade kernel stores every
+ * finished tile row to all peers directly over NVLink, fusing the band all-gather into the kernel. */
+int fdc_set_peer_framebuffers(fdc_ctx* ctx, void* const* device_ptrs, int n);
+
+/* --- introspection for parity tests and benchmarks --- */
+typedef struct fdc_frame_stats {
+  uint32_t n_prims;        /* primitives shaded (after host/device early-outs) */
+  uint32_t n_segments;     /* 1 + number of backdrop blurs */
+  uint32_t tiles_x, tiles_y, tile_w, tile_h;
+  uint64_t n_tile_entries; /* total (tile, primitive) pairs in the bin lists */
+  uint32_t n_launches;     /* kernels launched for the last frame */
+  float gpu_ms;            /* device time of the last frame (CUDA events on the context stream) */
+  float shade_ms;          /* device time of the shade kernel(s) of the last frame */
+  float bin_ms;            /* setup + binning kernels */
+  float blur_ms;
+} fdc_frame_stats;
+int fdc_get_frame_stats(fdc_ctx* ctx, fdc_frame_stats* out);
+/* Bin lists of segment `segment` of the last frame: tile_offsets has tiles_x*tiles_y+1 entries, entry ids
+ * are indices into that segment's primitive array in emission order.  Pass NULL to query sizes. */
+int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t offsets_cap, uint32_t* entries,
+                   size_t entries_cap, size_t* n_offsets, size_t* n_entries);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIGDRAW_CUDA_H */

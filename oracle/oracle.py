@@ -1,0 +1,112 @@
+"""ctypes binding of the CPU oracle (oracle/figdraw_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Importers allowed: tests/, `__graft_entry__.smoke()`, and bench.py's `cpu_baseline` / `--impl reference`
+legs.  Nothing under figdraw_b200/ imports this module; the product has no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libfigdraw_oracle.so")
+_LIB: Optional[ctypes.CDLL] = None
+
+N_MODES = 24
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "figdraw_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
+    return _SO
+
+
+def _lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        build()
+        lib = ctypes.CDLL(_SO)
+        c = ctypes
+        lib.orc_create.restype = c.c_void_p
+        lib.orc_create.argtypes = [c.c_int]
+        lib.orc_destroy.argtypes = [c.c_void_p]
+        lib.orc_atlas_size.argtypes = [c.c_void_p]
+        lib.orc_rebuilds.argtypes = [c.c_void_p]
+        lib.orc_get_image_rect.argtypes = [c.c_void_p, c.c_uint64, c.POINTER(c.c_float)]
+        lib.orc_put_image.argtypes = [c.c_void_p, c.c_uint64, c.c_int, c.c_int, c.c_void_p, c.POINTER(c.c_float)]
+        lib.orc_render.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.POINTER(c.c_float), c.c_void_p,
+                                   c.c_int64, c.c_void_p, c.c_void_p, c.c_int]
+        lib.orc_max_threads.restype = c.c_int
+        _LIB = lib
+    return _LIB
+
+
+def max_threads() -> int:
+    return int(_lib().orc_max_threads())
+
+
+class Oracle:
+    """One GL-context-equivalent: an atlas plus the frame interpreter."""
+
+    def __init__(self, atlas_size: int = 1024):
+        self._h = _lib().orc_create(int(atlas_size))
+
+    def close(self):
+        if self._h:
+            _lib().orc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def atlas_size(self) -> int:
+        return int(_lib().orc_atlas_size(self._h))
+
+    def put_image(self, key: int, rgba: np.ndarray) -> Tuple[Tuple[float, float, float, float], bool]:
+        rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+        h, w = rgba.shape[:2]
+        out = (ctypes.c_float * 4)()
+        rebuilt = _lib().orc_put_image(self._h, ctypes.c_uint64(key & (2**64 - 1)), w, h, rgba.ctypes.data, out)
+        return tuple(out), bool(rebuilt)
+
+    def get_image_rect(self, key: int):
+        out = (ctypes.c_float * 4)()
+        ok = _lib().orc_get_image_rect(self._h, ctypes.c_uint64(key & (2**64 - 1)), out)
+        return tuple(out) if ok else None
+
+    def render(self, width: int, height: int, calls: np.ndarray, clear=(1.0, 1.0, 1.0, 1.0),
+               fb: Optional[np.ndarray] = None, n_threads: int = 0, want_counts: bool = False):
+        """Returns RGBA8 [H, W, 4] (top-left origin) and optionally per-SdfMode fragment counts."""
+        calls = np.ascontiguousarray(calls)
+        assert calls.dtype.itemsize == 128
+        if fb is None:
+            fb = np.zeros((height, width, 4), dtype=np.uint8)
+        else:
+            fb = np.ascontiguousarray(fb, dtype=np.uint8).copy()
+            assert fb.shape == (height, width, 4)
+        c4 = (ctypes.c_float * 4)(*(clear if clear is not None else (0, 0, 0, 0)))
+        counts = np.zeros(N_MODES, dtype=np.int64)
+        nt = n_threads if n_threads > 0 else max_threads()
+        rc = _lib().orc_render(self._h, width, height, 1 if clear is not None else 0, c4, calls.ctypes.data,
+                               len(calls), fb.ctypes.data, counts.ctypes.data, nt)
+        if rc != 0:
+            raise RuntimeError(f"oracle: render failed with status {rc}")
+        return (fb, counts) if want_counts else fb
+
+
+def render_trace(trace, n_threads: int = 0, want_counts: bool = False, oracle: Optional[Oracle] = None):
+    """Render a figdraw_b200.figbackend.Trace: uploads its images (in order), then replays its calls."""
+    o = oracle or Oracle(trace.atlas_size)
+    for _idx, key, img in trace.images:
+        o.put_image(key, img)
+    return o.render(trace.width, trace.height, trace.calls, clear=trace.clear, n_threads=n_threads,
+                    want_counts=want_counts)

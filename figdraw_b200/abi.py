@@ -111,7 +111,7 @@ class FdcFrameStats(ctypes.Structure):
 # Every symbol include/figdraw_cuda.h declares (checked by tests/test_abi.py against the header text).
 EXPORTS = [
     "fdc_create", "fdc_destroy", "fdc_last_error", "fdc_abi_version",
-    "fdc_begin_frame", "fdc_end_frame", "fdc_read_pixels", "fdc_sync",
+    "fdc_begin_frame", "fdc_end_frame", "fdc_read_pixels", "fdc_sync", "fdc_replay_frame",
     "fdc_translate", "fdc_rotate", "fdc_scale", "fdc_apply_transform", "fdc_save_transform",
     "fdc_restore_transform", "fdc_transform_mirrors_y", "fdc_get_transform",
     "fdc_sdf_aa_factor", "fdc_set_sdf_aa_factor", "fdc_set_text_subpixel_positioning_enabled",
@@ -163,6 +163,7 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_end_frame", c.c_int, P)
     sig("fdc_read_pixels", c.c_int, P, c.c_int, c.c_int, c.c_int, c.c_int, P)
     sig("fdc_sync", c.c_int, P)
+    sig("fdc_replay_frame", c.c_int, P)
     sig("fdc_translate", c.c_int, P, c.c_float, c.c_float)
     sig("fdc_rotate", c.c_int, P, c.c_float)
     sig("fdc_scale", c.c_int, P, c.c_float, c.c_float)

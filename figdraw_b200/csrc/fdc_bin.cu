@@ -1,0 +1,611 @@
+// Primitive setup and order-preserving primitive-to-tile binning (sm_100a).
+//
+// prim_setup_kernel  -- the device restatement of the reference's quad emission: `drawRoundedRectSdfOpenGl`
+//   (glcontext.nim:1449-1559), `drawUvRect*` (:1022-1095, :1169-1302), `drawQuadraticBezierSdfOpenGl` (:1619-1711),
+//   `drawFilledQuad` (:963-982), `roundedRadiiVec` (:745-817), `encodeSdfMode` (:1002-1008) and
+//   `gradientColors` (figbackend.nim:129-183).  One thread per draw record; the host only appends records.
+//   Everything that feeds `ceil` is computed with explicitly rounded float32 ops in the reference's operation
+//   order so the integer quad corners -- and therefore the bin lists -- are bit-exact against the oracle.
+//
+// Binning -- two levels, both tile-major so list order == emission order without sorting or atomics on order:
+//   coarse: the frame (band) is cut into 128x128-px bins; primitives into chunks of 1024.  count[chunk][bin]
+//           by warp ballot + popc over the chunk staged in shared memory, a column scan over chunks, then the
+//           same ballot loop scatters with prefix ranks (stable compaction).
+//   fine:   one CTA per coarse bin walks its list; warp w owns tile row w of the 8x8 tiles; per 32 entries one
+//           ballot per tile column.  Counts -> CTA scan -> one atomicAdd reserves the bin's slice of the tile
+//           list (slice placement is the only non-deterministic thing and is not observable) -> scatter.
+#include <cuda_runtime.h>
+
+#include "fdc_kernels.h"
+
+namespace fdc {
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// `ctx.mat * vec2`, glcontext.nim:905-906, vmath order: (m00*x + m10*y) + m30, every op rounded once.
+__device__ __forceinline__ float2 xf_apply(const Xform& m, float x, float y) {
+  float2 r;
+  r.x = fadd(fadd(fmul(m.m00, x), fmul(m.m10, y)), m.m30);
+  r.y = fadd(fadd(fmul(m.m01, x), fmul(m.m11, y)), m.m31);
+  return r;
+}
+
+__device__ __forceinline__ float nim_round(float x) { return roundf(x); }  // half away from zero
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// clampRadius, glcontext.nim:745-749
+__device__ __forceinline__ float clamp_radius(float r, float maxr) {
+  if (r <= 0.0f) return 0.0f;
+  return nim_round(fmaxf(1.0f, fminf(r, maxr)));
+}
+
+// roundedRadiiVec, glcontext.nim:751-817.  rx/ry: TL,TR,BL,BR.  out: TR,BR,TL,BL.
+__device__ bool rounded_radii_vec(const float* rx, const float* ry, float hx, float hy, float out[4]) {
+  const int order[4] = {1, 3, 0, 2};
+  bool circ = true;
+#pragma unroll
+  for (int i = 0; i < 4; i++) circ = circ && (rx[i] == ry[i]);
+  float mr = fminf(hx, hy);
+  if (circ) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[k] = clamp_radius(rx[order[k]], mr);
+    return false;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int c = order[k];
+    float cx = clamp_radius(rx[c], hx), cy = clamp_radius(ry[c], hy);
+    if (rx[c] == ry[c]) {
+      out[k] = -(clamp_radius(rx[c], mr) + 1.0f);
+    } else if (cx == cy) {
+      out[k] = -(cx + 1.0f);
+    } else {
+      float qx = nim_round(fmul(clampf(fdiv(cx, fmaxf(hx, 0.000001f)), 0.0f, 1.0f), 4095.0f));
+      float qy = nim_round(fmul(clampf(fdiv(cy, fmaxf(hy, 0.000001f)), 0.0f, 1.0f), 4095.0f));
+      out[k] = fadd(qx, fmul(qy, 4096.0f));
+    }
+  }
+  return true;
+}
+
+// lerpColor / sampleColor / gradientColors, figbackend.nim:129-183
+__device__ uint32_t lerp_color(uint32_t a, uint32_t b, float t) {
+  float ct = clampf(t, 0.0f, 1.0f), inv = __fsub_rn(1.0f, ct);
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float av = (float)((a >> (8 * k)) & 255u), bv = (float)((b >> (8 * k)) & 255u);
+    float v = nim_round(fadd(fmul(av, inv), fmul(bv, ct)));
+    r |= ((uint32_t)(int)v & 255u) << (8 * k);
+  }
+  return r;
+}
+__device__ uint32_t sample_color(int kind, const uint32_t* c, float mid, float t) {
+  if (kind == FDC_FILL_COLOR) return c[0];
+  if (kind == FDC_FILL_LINEAR2) return lerp_color(c[0], c[1], t);
+  float ct = clampf(t, 0.0f, 1.0f);
+  if (ct <= mid) return lerp_color(c[0], c[1], fdiv(ct, mid));
+  return lerp_color(c[1], c[2], fdiv(__fsub_rn(ct, mid), __fsub_rn(1.0f, mid)));
+}
+__device__ void gradient_colors(int kind, int axis, const uint32_t* c, float mid, uint32_t out[4]) {
+  const float ts[4][4] = {{0.0f, 1.0f, 1.0f, 0.0f}, {1.0f, 1.0f, 0.0f, 0.0f}, {0.5f, 1.0f, 0.5f, 0.0f}, {0.0f, 0.5f, 1.0f, 0.5f}};
+  if (kind == FDC_FILL_COLORS4) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[k] = c[k];
+    return;
+  }
+  if (kind == FDC_FILL_COLOR) axis = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = sample_color(kind, c, mid, ts[axis & 3][k]);
+}
+
+__device__ __forceinline__ int find_run(const RunState* runs, int n_runs, uint32_t draw) {
+  int lo = 0, hi = n_runs - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (runs[mid].first_draw <= draw) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__device__ bool atlas_lookup(const AtlasView& at, uint64_t key, float rect[4]) {
+  if (!at.table) return false;
+  uint32_t h = atlas_hash(key) & at.table_mask;
+  for (uint32_t probe = 0; probe <= at.table_mask; probe++) {
+    const AtlasEntry& e = at.table[(h + probe) & at.table_mask];
+    if (!e.used) return false;
+    if (e.used == 1 && e.key == key) {
+      rect[0] = e.x; rect[1] = e.y; rect[2] = e.w; rect[3] = e.h;
+      return true;
+    }
+  }
+  return false;
+}
+
+struct QuadPos {
+  float x[4], y[4];  // BL, BR, TR, TL after ceil
+};
+
+__device__ __forceinline__ void quad_from_rect(const Xform& m, float atx, float aty, float tox, float toy, QuadPos& q) {
+  float2 p0 = xf_apply(m, atx, toy), p1 = xf_apply(m, tox, toy), p2 = xf_apply(m, tox, aty), p3 = xf_apply(m, atx, aty);
+  q.x[0] = ceilf(p0.x); q.y[0] = ceilf(p0.y);
+  q.x[1] = ceilf(p1.x); q.y[1] = ceilf(p1.y);
+  q.x[2] = ceilf(p2.x); q.y[2] = ceilf(p2.y);
+  q.x[3] = ceilf(p3.x); q.y[3] = ceilf(p3.y);
+}
+
+__device__ __forceinline__ int clamp_i(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int f2i_sat(float v) {  // float -> int with saturation well inside int16 range
+  v = fminf(fmaxf(v, -30000.0f), 30000.0f);
+  return (int)v;
+}
+
+// Pixel bbox [x0,x1) x [y0,y1) of a quad's ceil'd corners.
+__device__ __forceinline__ void quad_bbox(const QuadPos& q, int& x0, int& y0, int& x1, int& y1) {
+  x0 = f2i_sat(fminf(fminf(q.x[0], q.x[1]), fminf(q.x[2], q.x[3])));
+  x1 = f2i_sat(fmaxf(fmaxf(q.x[0], q.x[1]), fmaxf(q.x[2], q.x[3])));
+  y0 = f2i_sat(fminf(fminf(q.y[0], q.y[1]), fminf(q.y[2], q.y[3])));
+  y1 = f2i_sat(fmaxf(fmaxf(q.y[0], q.y[1]), fmaxf(q.y[2], q.y[3])));
+}
+
+// Clip chain: intersect with the bbox of every enclosing texture-mask primitive (they are ROUNDED_RECT records).
+__device__ void apply_clip_chain(const SetupArgs& a, int clip_draw, int& x0, int& y0, int& x1, int& y1) {
+  for (int guard = 0; clip_draw != -1 && guard < 2 * kMaxMaskDepth; guard++) {
+    if (clip_draw < -1) { x1 = x0; return; }  // -2: the enclosing mask level is empty, nothing under it is visible
+    const fdc_call& d = a.draws[clip_draw];
+    const RunState& rs = a.runs[find_run(a.runs, a.n_runs, (uint32_t)clip_draw)];
+    QuadPos q;
+    quad_from_rect(a.xforms[rs.xform], d.f[0], d.f[1], fadd(d.f[0], d.f[2]), fadd(d.f[1], d.f[3]), q);
+    int cx0, cy0, cx1, cy1;
+    quad_bbox(q, cx0, cy0, cx1, cy1);
+    x0 = max(x0, cx0); y0 = max(y0, cy0); x1 = min(x1, cx1); y1 = min(y1, cy1);
+    clip_draw = rs.clip_draw;
+  }
+}
+
+__global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.count) return;
+  uint32_t di = a.first + i;
+  const fdc_call& d = a.draws[di];
+  int ri = find_run(a.runs, a.n_runs, di);
+  const RunState rs = a.runs[ri];
+  const Xform xf = a.xforms[rs.xform];
+  a.prim_call[i] = rs.call_index + (di - rs.first_draw);
+
+  Prim p;
+  memset(&p, 0, sizeof(p));
+  uint32_t flags = rs.flags & (PF_MASK_WRITE | PF_MASK_BEGIN | PF_DEPTH_MASK);
+  bool empty = false;
+  QuadPos q;
+  float atx = 0, aty = 0, tox = 0, toy = 0;
+  bool have_rect_quad = true;
+  int mode = 0, fill_mode = 0;
+  uint32_t cols[4] = {0, 0, 0, 0};
+  float uax = 0.0f, uay = 0.0f, utx = 1.0f, uty = 1.0f;  // normalised atlas uv corners (atlas modes)
+  bool atlas_mode = false;
+
+  switch (d.op) {
+    case FDC_OP_ROUNDED_RECT: {
+      float w = d.f[2], h = d.f[3];
+      if (w <= 0.0f || h <= 0.0f) { empty = true; break; }
+      mode = (int)d.u[0];
+      int fkind = (int)d.u[1], axis = (int)d.u[2];
+      if (fkind == FDC_FILL_LINEAR3 && (mode == FDC_SDF_CLIP_AA || mode == FDC_SDF_ANNULAR || mode == FDC_SDF_ANNULAR_AA)) {
+        fill_mode = 1 + (axis & 3);
+        cols[0] = cols[1] = cols[2] = cols[3] = d.u[3];
+        p.c_mid = d.u[4];
+        p.c_stop = d.u[5];
+      } else {
+        gradient_colors(fkind, axis, &d.u[3], d.f[16], cols);
+      }
+      float qhx = fmul(w, 0.5f), qhy = fmul(h, 0.5f);
+      bool inset = (mode == FDC_SDF_INSET_SHADOW);
+      float ssx = d.f[14], ssy = d.f[15];
+      float rsx = (ssx > 0.0f && ssy > 0.0f) ? ssx : w, rsy = (ssx > 0.0f && ssy > 0.0f) ? ssy : h;
+      float shx = inset ? qhx : fmul(rsx, 0.5f), shy = inset ? qhy : fmul(rsy, 0.5f);
+      p.qhx = qhx; p.qhy = qhy;
+      p.p2 = inset ? ssx : shx;
+      p.p3 = inset ? ssy : shy;
+      float rr[4];
+      if (rounded_radii_vec(&d.f[4], &d.f[8], shx, shy, rr)) flags |= PF_ELLIPTICAL;
+      p.r0 = rr[0]; p.r1 = rr[1]; p.r2 = rr[2]; p.r3 = rr[3];
+      p.factor = d.f[12];
+      p.spread = fill_mode == 0 ? d.f[13] : clampf(d.f[16], 0.01f, 0.99f);
+      atx = d.f[0]; aty = d.f[1]; tox = fadd(d.f[0], w); toy = fadd(d.f[1], h);
+      break;
+    }
+    case FDC_OP_IMAGE: {
+      float r[4];
+      uint64_t key = (uint64_t)d.u[0] | ((uint64_t)d.u[1] << 32);
+      if (!atlas_lookup(a.atlas, key, r)) { empty = true; break; }
+      float as = (float)a.atlas.size;
+      float sw = d.f[2], sh = d.f[3];
+      if (!(sw > 0.0f && sh > 0.0f)) { sw = fmul(r[2], as); sh = fmul(r[3], as); }
+      uax = r[0]; utx = fadd(r[0], r[2]);
+      uay = r[1]; uty = fadd(r[1], r[3]);
+      if (d.u[7]) { float tmp = uay; uay = uty; uty = tmp; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) cols[k] = d.u[3 + k];
+      mode = FDC_SDF_ATLAS;
+      atlas_mode = true;
+      atx = d.f[0]; aty = d.f[1]; tox = fadd(d.f[0], sw); toy = fadd(d.f[1], sh);
+      break;
+    }
+    case FDC_OP_MSDF: {
+      float r[4];
+      uint64_t key = (uint64_t)d.u[0] | ((uint64_t)d.u[1] << 32);
+      if (!atlas_lookup(a.atlas, key, r)) { empty = true; break; }
+      float stroke_w = fmaxf(0.0f, d.f[6]);
+      bool mtsdf = d.u[2] != 0;
+      mode = stroke_w > 0.0f ? (mtsdf ? FDC_SDF_MTSDF_ANNULAR : FDC_SDF_MSDF_ANNULAR) : (mtsdf ? FDC_SDF_MTSDF : FDC_SDF_MSDF);
+      uax = r[0]; utx = fadd(r[0], r[2]);
+      uay = r[1]; uty = fadd(r[1], r[3]);
+      if (d.u[7]) { float tmp = uay; uay = uty; uty = tmp; }
+      cols[0] = cols[1] = cols[2] = cols[3] = d.u[3];
+      p.qhx = (float)a.atlas.size; p.qhy = stroke_w;
+      p.factor = d.f[4]; p.spread = d.f[5];
+      atlas_mode = true;
+      atx = d.f[0]; aty = d.f[1]; tox = fadd(d.f[0], d.f[2]); toy = fadd(d.f[1], d.f[3]);
+      break;
+    }
+    case FDC_OP_BEZIER: {
+      if (d.f[2] <= 0.0f || d.f[3] <= 0.0f || d.f[10] <= 0.0f) { empty = true; break; }
+      int fkind = (int)d.u[1], axis = (int)d.u[2];
+      if (fkind == FDC_FILL_LINEAR3) {
+        fill_mode = 1 + (axis & 3);
+        cols[0] = cols[1] = cols[2] = cols[3] = d.u[3];
+        p.c_mid = d.u[4];
+        p.c_stop = d.u[5];
+      } else {
+        gradient_colors(fkind, axis, &d.u[3], d.f[16], cols);
+      }
+      p.qhx = fmul(d.f[2], 0.5f); p.qhy = fmul(d.f[3], 0.5f); p.p2 = d.f[4]; p.p3 = d.f[5];
+      p.r0 = d.f[6]; p.r1 = d.f[7]; p.r2 = d.f[8]; p.r3 = d.f[9];
+      p.factor = d.f[10];
+      p.spread = fill_mode == 0 ? 0.0f : clampf(d.f[16], 0.01f, 0.99f);
+      int cap = (int)d.u[0];
+      mode = cap == FDC_CAP_BUTT ? FDC_SDF_BEZIER_STROKE_BUTT_AA
+                                 : (cap == FDC_CAP_SQUARE ? FDC_SDF_BEZIER_STROKE_SQUARE_AA : FDC_SDF_BEZIER_STROKE_AA);
+      atx = d.f[0]; aty = d.f[1]; tox = fadd(d.f[0], d.f[2]); toy = fadd(d.f[1], d.f[3]);
+      break;
+    }
+    case FDC_OP_FILLED_QUAD: {
+      float r[4];
+      if (!atlas_lookup(a.atlas, kRectKey, r)) { empty = true; break; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        float2 v = xf_apply(xf, d.f[2 * k], d.f[2 * k + 1]);
+        q.x[k] = ceilf(v.x); q.y[k] = ceilf(v.y);
+        cols[k] = d.u[3 + k];
+      }
+      have_rect_quad = false;
+      uax = utx = fadd(r[0], fdiv(r[2], 2.0f));
+      uay = uty = fadd(r[1], fdiv(r[3], 2.0f));
+      mode = FDC_SDF_ATLAS;
+      atlas_mode = true;
+      break;
+    }
+    case FDC_OP_RECT: {
+      float r[4];
+      if (!atlas_lookup(a.atlas, kRectKey, r)) { empty = true; break; }
+      uax = utx = fadd(r[0], fdiv(r[2], 2.0f));
+      uay = uty = fadd(r[1], fdiv(r[3], 2.0f));
+      cols[0] = cols[1] = cols[2] = cols[3] = d.u[3];
+      mode = FDC_SDF_ATLAS;
+      atlas_mode = true;
+      atx = d.f[0]; aty = d.f[1]; tox = fadd(d.f[0], d.f[2]); toy = fadd(d.f[1], d.f[3]);
+      break;
+    }
+    default: empty = true; break;
+  }
+
+  int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;
+  if (!empty) {
+    if (have_rect_quad) quad_from_rect(xf, atx, aty, tox, toy, q);
+    quad_bbox(q, bx0, by0, bx1, by1);
+    bool aligned = have_rect_quad && q.x[0] == q.x[3] && q.x[1] == q.x[2] && q.y[0] == q.y[1] && q.y[2] == q.y[3];
+    float X0 = q.x[3], Y0 = q.y[3], X1 = q.x[1], Y1 = q.y[1];
+    if (aligned) {
+      if (X0 == X1 || Y0 == Y1) empty = true;
+      else {
+        // s = (x + .5 - X0) / (X1 - X0)
+        float iw = 1.0f / (X1 - X0), ih = 1.0f / (Y1 - Y0);
+        p.su = iw; p.ou = (0.5f - X0) * iw;
+        p.sv = ih; p.ov = (0.5f - Y0) * ih;
+      }
+    } else {
+      flags |= PF_GENERAL;
+      QuadGeom g;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { g.vx[k] = (int)fminf(fmaxf(q.x[k], -1.0e6f), 1.0e6f); g.vy[k] = (int)fminf(fmaxf(q.y[k], -1.0e6f), 1.0e6f); }
+      a.geoms[i] = g;
+      p.su = __uint_as_float(i);
+    }
+    // clip: frame, band, enclosing texture masks
+    int cx0 = bx0, cy0 = by0, cx1 = bx1, cy1 = by1;
+    apply_clip_chain(a, rs.clip_draw, cx0, cy0, cx1, cy1);
+    cx0 = max(cx0, 0); cx1 = min(cx1, a.frame.W);
+    cy0 = max(cy0, a.frame.band_y0); cy1 = min(cy1, a.frame.band_y1);
+    if (cx0 >= cx1 || cy0 >= cy1) empty = true;
+    p.bx0 = (int16_t)cx0; p.by0 = (int16_t)cy0; p.bx1 = (int16_t)cx1; p.by1 = (int16_t)cy1;
+
+    if (!empty) {
+      p.aa = rs.aa;
+      bool solid = cols[0] == cols[1] && cols[1] == cols[2] && cols[2] == cols[3];
+      if (solid) flags |= PF_SOLID;
+#pragma unroll
+      for (int k = 0; k < 4; k++) p.c[k] = cols[k];
+      if (rs.rectmask && !(flags & PF_MASK_WRITE)) { flags |= PF_RECTMASK; p.aux = rs.rectmask & 0xFFFFu; }
+      if (mode == FDC_SDF_DROP_SHADOW || mode == FDC_SDF_DROP_SHADOW_AA || mode == FDC_SDF_INSET_SHADOW) {
+        float sigma = fmaxf(0.5f * p.factor, 0.5f);
+        p.k = -0.5f * 1.4426950408889634f / (sigma * sigma);  // exp(-.5 z^2) = exp2(k * sd^2)
+      }
+      if (atlas_mode) {
+        float as = (float)a.atlas.size;
+        p.u0 = uax * as - 0.5f; p.du = (utx - uax) * as;
+        p.v0 = uay * as - 0.5f; p.dv = (uty - uay) * as;
+        if (mode == FDC_SDF_ATLAS && rs.subpixel_shift >= 0.0f) {
+          flags |= PF_SUBPIXEL;
+          p.u0 -= rs.subpixel_shift;  // atlasUv.x -= shift * atlasTexelSize.x  (atlas.frag:286-288)
+        }
+        if (aligned) {
+          float ddx = fabsf(p.du * p.su), ddy = fabsf(p.dv * p.sv);  // texels per pixel
+          if (mode == FDC_SDF_ATLAS) {
+            float rho = fmaxf(ddx, ddy);
+            p.k = rho > 0.0f ? log2f(rho) : -1000.0f;
+          } else {
+            // msdfScreenPxRange, atlas.frag:45-49
+            float px_range = p.factor;
+            p.k = fmaxf(0.5f * (px_range / ddx + px_range / ddy), 1.0f);
+          }
+        }
+      }
+      // occluder: opaque ClipAA fill whose inner rect has coverage exactly 1 (see DESIGN.md "work reduction")
+      if (mode == FDC_SDF_CLIP_AA && aligned && !(flags & (PF_MASK_WRITE | PF_ELLIPTICAL | PF_RECTMASK)) &&
+          (flags & PF_DEPTH_MASK) == 0 && X1 > X0 && Y1 > Y0 && rs.aa > 0.0f) {
+        uint32_t amin = min(min(cols[0] >> 24, cols[1] >> 24), min(cols[2] >> 24, cols[3] >> 24));
+        if (fill_mode != 0) amin = min(amin, min(p.c_mid >> 24, p.c_stop >> 24));
+        if (amin == 255u) {
+          float rmax = fmaxf(fmaxf(p.r0, p.r1), fmaxf(p.r2, p.r3));
+          float m = fmaxf(rmax, 0.5f / rs.aa) + 0.01f;
+          float gx = 2.0f * p.qhx * p.su, gy = 2.0f * p.qhy * p.sv;  // d p / d pixel
+          float lox = X0 - 0.5f + (p.qhx - p.p2 + m) / gx, hix = X0 - 0.5f + (p.qhx + p.p2 - m) / gx;
+          float loy = Y0 - 0.5f + (p.qhy - p.p3 + m) / gy, hiy = Y0 - 0.5f + (p.qhy + p.p3 - m) / gy;
+          int ix0 = max((int)ceilf(lox + 1e-3f), cx0), ix1 = min((int)floorf(hix - 1e-3f) + 1, cx1);
+          int iy0 = max((int)ceilf(loy + 1e-3f), cy0), iy1 = min((int)floorf(hiy - 1e-3f) + 1, cy1);
+          if (ix0 < ix1 && iy0 < iy1) {
+            flags |= PF_OCCLUDER;
+            p.ix0 = (int16_t)ix0; p.iy0 = (int16_t)iy0; p.ix1 = (int16_t)ix1; p.iy1 = (int16_t)iy1;
+          }
+        }
+      }
+    }
+  }
+  if (empty) {
+    flags = PF_EMPTY;
+    p.bx0 = p.by0 = p.bx1 = p.by1 = 0;
+  } else {
+    flags |= (uint32_t)mode & PF_MODE_MASK;
+    flags |= ((uint32_t)fill_mode << PF_FILLMODE_SHIFT) & PF_FILLMODE_MASK;
+  }
+  p.mode_flags = flags;
+  a.prims[i] = p;
+}
+
+void launch_prim_setup(const SetupArgs& a, cudaStream_t stream) {
+  if (a.count == 0) return;
+  prim_setup_kernel<<<(a.count + 127) / 128, 128, 0, stream>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------ coarse binning
+// Coarse rect of a primitive in band-local coarse-bin coordinates, inclusive, packed x0 | y0<<8 | x1<<16 | y1<<24.
+// Empty primitives get x0 = 255 > x1 = 0 so they never match.
+__device__ __forceinline__ uint32_t coarse_rect(const Prim* prims, uint32_t idx, uint32_t n, const FrameView& f) {
+  if (idx >= n) return 0x000000FFu;
+  const int4 q6 = __ldg(reinterpret_cast<const int4*>(&prims[idx]) + 6);
+  if ((uint32_t)q6.z & PF_EMPTY) return 0x000000FFu;
+  int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
+  const int cpx = kTileW * kCoarse, cpy = kTileH * kCoarse;
+  int oy = f.cty0 * kTileH;
+  uint32_t x0 = (uint32_t)(bx0 / cpx), x1 = (uint32_t)((bx1 - 1) / cpx);
+  uint32_t y0 = (uint32_t)((by0 - oy) / cpy), y1 = (uint32_t)((by1 - 1 - oy) / cpy);
+  return x0 | (y0 << 8) | (x1 << 16) | (y1 << 24);
+}
+
+__device__ __forceinline__ bool rect_hits(uint32_t r, uint32_t bx, uint32_t by) {
+  return (r & 255u) <= bx && bx <= ((r >> 16) & 255u) && ((r >> 8) & 255u) <= by && by <= (r >> 24);
+}
+
+template <bool kScatter>
+__global__ void __launch_bounds__(256) coarse_bin_kernel(const Prim* __restrict__ prims, uint32_t n, FrameView f,
+                                                         uint32_t* __restrict__ chunk_counts,
+                                                         const uint32_t* __restrict__ cbin_start,
+                                                         uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
+                                                         uint32_t* __restrict__ counters) {
+  __shared__ uint32_t rects[kChunk];
+  const uint32_t chunk = blockIdx.x;
+  const uint32_t base_idx = chunk * kChunk;
+  for (int k = threadIdx.x; k < kChunk; k += blockDim.x) rects[k] = coarse_rect(prims, base_idx + k, n, f);
+  __syncthreads();
+  const int n_bins = f.cbx * f.cby;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  if (kScatter && counters[2] > coarse_cap) return;  // overflow: host regrows and replays
+  for (int b = warp; b < n_bins; b += 8) {
+    const uint32_t bx = (uint32_t)(b % f.cbx), by = (uint32_t)(b / f.cbx);
+    uint32_t running = 0;
+    if (kScatter) running = cbin_start[b] + chunk_counts[(size_t)chunk * n_bins + b];
+#pragma unroll 4
+    for (int s = 0; s < kChunk / 32; s++) {
+      const bool hit = rect_hits(rects[s * 32 + lane], bx, by);
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+      if (kScatter) {
+        if (hit) coarse_list[running + __popc(m & lt_mask)] = base_idx + s * 32 + lane;
+      }
+      running += __popc(m);
+    }
+    if (!kScatter && lane == 0) chunk_counts[(size_t)chunk * n_bins + b] = running;
+  }
+}
+
+// Column scan over chunks per bin, then scan over bins.  One CTA.
+__global__ void __launch_bounds__(1024) coarse_scan_kernel(uint32_t* __restrict__ chunk_counts, int n_chunks, int n_bins,
+                                                           uint32_t* __restrict__ cbin_start, uint32_t coarse_cap,
+                                                           uint32_t* __restrict__ counters) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b0 = 0; b0 < n_bins; b0 += 1024) {
+    const int b = b0 + threadIdx.x;
+    uint32_t total = 0;
+    if (b < n_bins) {
+      for (int c = 0; c < n_chunks; c++) {
+        const uint32_t v = chunk_counts[(size_t)c * n_bins + b];
+        chunk_counts[(size_t)c * n_bins + b] = total;
+        total += v;
+      }
+    }
+    // block exclusive scan of `total`
+    uint32_t incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t ws = warp_sums[lane], wi = ws;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_sums[lane] = wi - ws;
+    }
+    __syncthreads();
+    const uint32_t excl = carry + warp_sums[warp] + incl - total;
+    if (b < n_bins) cbin_start[b] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    cbin_start[n_bins] = carry;
+    counters[2] = carry;
+    if (carry > coarse_cap) atomicOr(&counters[1], 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fine binning
+__global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ prims, FrameView f,
+                                                       const uint32_t* __restrict__ cbin_start,
+                                                       const uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
+                                                       uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile_count,
+                                                       uint32_t* __restrict__ tile_list, uint32_t tile_cap,
+                                                       uint32_t* __restrict__ counters) {
+  __shared__ uint32_t s_cnt[kCoarse * kCoarse];
+  __shared__ uint32_t s_base[kCoarse * kCoarse];
+  __shared__ uint32_t s_alloc;
+  if (counters[2] > coarse_cap) return;
+  const int b = blockIdx.x;
+  const int cbx_i = b % f.cbx, cby_i = b / f.cbx;
+  const uint32_t begin = cbin_start[b], end = cbin_start[b + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  // warp w owns tile row w of the bin
+  const int tile_x0 = cbx_i * kCoarse, tile_y = f.cty0 + cby_i * kCoarse + warp;
+  const int px0 = tile_x0 * kTileW, py0 = tile_y * kTileH, py1 = py0 + kTileH;
+
+  uint32_t cnt[kCoarse];
+#pragma unroll
+  for (int i = 0; i < kCoarse; i++) cnt[i] = 0;
+
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1) {
+      // publish counts, scan, allocate
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kCoarse; i++) s_cnt[warp * kCoarse + i] = cnt[i];
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int t = 0; t < kCoarse * kCoarse; t++) { s_base[t] = tot; tot += s_cnt[t]; }
+        uint32_t at = atomicAdd(&counters[0], tot);
+        if (at + tot > tile_cap) { atomicOr(&counters[1], 2u); s_alloc = 0xFFFFFFFFu; }
+        else s_alloc = at;
+      }
+      __syncthreads();
+      const uint32_t alloc = s_alloc;
+      if (lane < kCoarse) {
+        const int tx = tile_x0 + lane;
+        if (tx < f.tiles_x && tile_y >= f.ty0 && tile_y < f.ty1) {
+          tile_start[tile_y * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : alloc + s_base[warp * kCoarse + lane];
+          tile_count[tile_y * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : s_cnt[warp * kCoarse + lane];
+        }
+      }
+      if (alloc == 0xFFFFFFFFu) return;
+#pragma unroll
+      for (int i = 0; i < kCoarse; i++) cnt[i] = alloc + s_base[warp * kCoarse + i];
+    }
+    for (uint32_t e0 = begin; e0 < end; e0 += 32) {
+      const uint32_t e = e0 + lane;
+      uint32_t pid = 0;
+      uint32_t colmask = 0;
+      if (e < end) {
+        pid = __ldg(&coarse_list[e]);
+        const int4 q6 = __ldg(reinterpret_cast<const int4*>(&prims[pid]) + 6);
+        const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
+        if (by0 < py1 && by1 > py0) {
+          // tile columns [c0, c1] of this bin that the bbox touches
+          int c0 = (bx0 - px0) / kTileW, c1 = (bx1 - 1 - px0) / kTileW;
+          if (bx0 < px0) c0 = 0;
+          c0 = max(c0, 0); c1 = min(c1, kCoarse - 1);
+          if (c1 >= c0 && bx1 > px0) colmask = ((2u << c1) - 1u) & ~((1u << c0) - 1u);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kCoarse; i++) {
+        const bool hit = (colmask >> i) & 1u;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (pass == 1 && hit) tile_list[cnt[i] + __popc(m & lt_mask)] = pid;
+        cnt[i] += __popc(m);
+      }
+    }
+  }
+}
+
+__global__ void fill_u32_kernel(uint32_t* dst, uint32_t v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+}
+void launch_fill_u32(uint32_t* dst, uint32_t value, size_t n, cudaStream_t stream) {
+  if (n == 0) return;
+  fill_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dst, value, n);
+}
+
+void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& f, const BinBuffers& b, cudaStream_t stream,
+                    int* n_launches) {
+  const int n_bins = f.cbx * f.cby;
+  const int n_chunks = (int)((n_prims + kChunk - 1) / kChunk);
+  // tiles of the band start empty; counters: cursor, (overflow kept), coarse total, tile total
+  cudaMemsetAsync(b.tile_count + (size_t)f.ty0 * f.tiles_x, 0, sizeof(uint32_t) * (size_t)(f.ty1 - f.ty0) * f.tiles_x, stream);
+  cudaMemsetAsync(b.counters, 0, sizeof(uint32_t) * 4, stream);
+  if (n_prims == 0 || n_bins == 0) return;
+  coarse_bin_kernel<false><<<n_chunks, 256, 0, stream>>>(prims, n_prims, f, b.chunk_counts, nullptr, nullptr, 0, b.counters);
+  coarse_scan_kernel<<<1, 1024, 0, stream>>>(b.chunk_counts, n_chunks, n_bins, b.cbin_start, b.coarse_cap, b.counters);
+  coarse_bin_kernel<true><<<n_chunks, 256, 0, stream>>>(prims, n_prims, f, b.chunk_counts, b.cbin_start, b.coarse_list,
+                                                        b.coarse_cap, b.counters);
+  fine_bin_kernel<<<n_bins, 256, 0, stream>>>(prims, f, b.cbin_start, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count,
+                                              b.tile_list, b.tile_cap, b.counters);
+  if (n_launches) *n_launches += 4;
+}
+
+}  // namespace fdc

@@ -1,0 +1,1340 @@
+// Host side of the CUDA backend and its C ABI (include/figdraw_cuda.h).
+//
+// This is the C++ counterpart of `OpenGlContext` (src/figdraw/opengl/glcontext.nim): it keeps exactly the state
+// the GL context keeps on the host -- transform stack (:1991-2017), AA factor (:1157-1167), mask / rect-mask
+// stacks (:1873-1949), the atlas skyline packer (:541-586) -- but instead of filling vertex arrays it appends one
+// 128-byte record per draw to a pinned staging buffer.  `fdc_end_frame` uploads the records and launches:
+//     prim_setup -> coarse count -> coarse scan -> coarse scatter -> fine bin -> shade   [-> blur H -> blur V] ...
+// once per segment (a segment ends at each backdrop blur, which must read everything painted before it).
+// All quad arithmetic (ceil, radii packing, gradient colours, mode encoding) happens on the device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "fdc_kernels.h"
+
+using namespace fdc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = std::max(n, cap + cap / 2);
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0, n = 0;
+  bool reserve(size_t want) {
+    if (want <= cap) return true;
+    size_t nc = std::max(want, std::max<size_t>(cap * 2, 1024));
+    T* np = nullptr;
+    if (cudaMallocHost(&np, nc * sizeof(T)) != cudaSuccess) return false;
+    if (p) {
+      memcpy(np, p, n * sizeof(T));
+      cudaFreeHost(p);
+    }
+    p = np;
+    cap = nc;
+    return true;
+  }
+  bool push(const T& v) {
+    if (n == cap && !reserve(n + 1)) return false;
+    p[n++] = v;
+    return true;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = n = 0;
+  }
+};
+
+struct Mat4 {
+  float m[16];  // vmath: m[col*4 + row]
+};
+Mat4 mat_identity() {
+  Mat4 r;
+  memset(r.m, 0, sizeof(r.m));
+  r.m[0] = r.m[5] = r.m[10] = r.m[15] = 1.0f;
+  return r;
+}
+// a * b, each entry summed left to right (vmath `*`); compiled with -ffp-contract=off
+Mat4 mat_mul(const Mat4& a, const Mat4& b) {
+  Mat4 r;
+  for (int c = 0; c < 4; c++)
+    for (int row = 0; row < 4; row++)
+      r.m[c * 4 + row] = a.m[0 * 4 + row] * b.m[c * 4 + 0] + a.m[1 * 4 + row] * b.m[c * 4 + 1] +
+                         a.m[2 * 4 + row] * b.m[c * 4 + 2] + a.m[3 * 4 + row] * b.m[c * 4 + 3];
+  return r;
+}
+// 4x4 inverse by cofactors (`ctx.mat.inverse()`, glcontext.nim:837)
+bool mat_inverse(const Mat4& a, Mat4& out) {
+  const float* m = a.m;
+  float t[16];
+  t[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+  t[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+  t[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+  t[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+  t[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+  t[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+  t[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+  t[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+  t[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+  t[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+  t[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+  t[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+  t[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+  t[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+  t[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+  t[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+  float det = m[0] * t[0] + m[1] * t[4] + m[2] * t[8] + m[3] * t[12];
+  if (det == 0.0f) return false;
+  float id = 1.0f / det;
+  for (int i = 0; i < 16; i++) out.m[i] = t[i] * id;
+  return true;
+}
+
+float clamp_radius_h(float r, float maxr) {
+  if (r <= 0.0f) return 0.0f;
+  return roundf(fmaxf(1.0f, fminf(r, maxr)));
+}
+// roundedRadiiVec (glcontext.nim:751-817), host copy used only for fast rect masks
+bool rounded_radii_vec_h(const float* rx, const float* ry, float hx, float hy, float out[4]) {
+  const int order[4] = {1, 3, 0, 2};
+  bool circ = true;
+  for (int i = 0; i < 4; i++) circ = circ && rx[i] == ry[i];
+  float mr = fminf(hx, hy);
+  if (circ) {
+    for (int k = 0; k < 4; k++) out[k] = clamp_radius_h(rx[order[k]], mr);
+    return false;
+  }
+  for (int k = 0; k < 4; k++) {
+    int c = order[k];
+    float cx = clamp_radius_h(rx[c], hx), cy = clamp_radius_h(ry[c], hy);
+    if (rx[c] == ry[c]) out[k] = -(clamp_radius_h(rx[c], mr) + 1.0f);
+    else if (cx == cy) out[k] = -(cx + 1.0f);
+    else {
+      float qx = roundf(fminf(fmaxf(cx / fmaxf(hx, 0.000001f), 0.0f), 1.0f) * 4095.0f);
+      float qy = roundf(fminf(fmaxf(cy / fmaxf(hy, 0.000001f), 0.0f), 1.0f) * 4095.0f);
+      out[k] = qx + qy * 4096.0f;
+    }
+  }
+  return true;
+}
+
+struct Segment {
+  uint32_t first = 0, count = 0;  // draws
+  bool has_blur = false;          // a backdrop blur follows this segment
+  float blur_radius = 0.0f;
+  int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;  // blur region (superset of the composite quad bbox, clipped to the frame)
+};
+
+struct MaskLevel {
+  std::vector<fdc_call> draws;   // mask primitives of this level (re-emitted at segment boundaries)
+  std::vector<RunState> states;  // their run states (first_draw rewritten on emission)
+  int32_t mask_draw = -1;        // draw index of the single clipping primitive, or -1 when not usable as a clip
+  int32_t clip = -1;             // clip_draw for content at this level
+};
+
+struct RectMaskEntry {
+  bool fast;
+  uint32_t index;  // fast: index+1 into rectmask table
+};
+
+}  // namespace
+
+struct fdc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  float pixel_scale = 1.0f;
+  int rank = 0, n_ranks = 1;
+
+  // ---- atlas
+  int atlas_size = 0, initial_atlas_size = 0, n_levels = 0;
+  uint8_t* levels[kMaxAtlasLevels] = {};
+  std::vector<uint16_t> heights;
+  struct Rect4 { float x, y, w, h; };
+  std::unordered_map<uint64_t, Rect4> entries;
+  DevBuf<AtlasEntry> d_table;
+  uint32_t table_cap = 0;
+  bool table_dirty = true;
+
+  // ---- backend state
+  Mat4 mat = mat_identity();
+  std::vector<Mat4> mats;
+  float aa = 1.2f;  // DefaultSdfAaFactor figbackend.nim:34
+  bool subpixel_enabled = false;
+  float subpixel_shift = 0.0f;
+  bool frame_begun = false, mask_begun = false;
+  int mask_write = 0;
+  MaskLevel mask_levels[kMaxMaskDepth + 2];
+  std::vector<RectMaskEntry> rm_stack;
+
+  // ---- frame recording
+  int W = 0, H = 0;
+  bool clear = true;
+  uint32_t clear_rgba8 = 0xFFFFFFFFu;
+  PinnedBuf<fdc_call> draws;
+  PinnedBuf<RunState> runs;
+  PinnedBuf<Xform> xforms;
+  PinnedBuf<RectMaskRec> rectmasks;
+  std::vector<Segment> segments;
+  bool state_dirty = true, xform_dirty = true, begin_pending = false;
+  uint32_t call_ordinal = 0;       // backend calls seen this frame
+  uint32_t last_draw_ordinal = 0;  // ordinal of the previous draw
+  bool have_frame = false;         // a recorded frame is resident on the device (replay / debug)
+
+  // ---- device frame data
+  DevBuf<fdc_call> d_draws;
+  DevBuf<RunState> d_runs;
+  DevBuf<Xform> d_xforms;
+  DevBuf<RectMaskRec> d_rectmasks;
+  DevBuf<Prim> d_prims;
+  DevBuf<QuadGeom> d_geoms;
+  DevBuf<uint32_t> d_prim_call;
+  DevBuf<uint32_t> d_chunk_counts, d_cbin_start, d_coarse_list, d_tile_start, d_tile_count, d_tile_list, d_counters;
+  DevBuf<uint8_t> d_fb, d_backdrop, d_temp;
+  uint8_t* ext_fb = nullptr;
+  DevBuf<uint8_t*> d_peers;
+  int n_peers = 0;
+  size_t fb_bytes = 0;
+
+  // ---- stats
+  fdc_frame_stats stats = {};
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  struct Span { int a, b, kind; };  // event indices, kind 0 bin 1 shade 2 blur
+  std::vector<Span> spans;
+  size_t ev_used = 0;
+
+  FrameView frame = {};
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    error = buf;
+    return code;
+  }
+  int cuda_fail(cudaError_t e, const char* what) { return fail(FDC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e)); }
+  uint8_t* fb() { return ext_fb ? ext_fb : d_fb.p; }
+};
+
+#define CK(expr)                                              \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return ctx->cuda_fail(_e, #expr);  \
+  } while (0)
+
+namespace {
+
+int atlas_alloc(fdc_ctx* ctx, int size) {
+  for (int l = 0; l < ctx->n_levels; l++) {
+    cudaFree(ctx->levels[l]);
+    ctx->levels[l] = nullptr;
+  }
+  ctx->n_levels = 0;
+  ctx->atlas_size = size;
+  for (int s = size; s >= 1 && ctx->n_levels < kMaxAtlasLevels; s >>= 1) {
+    uint8_t* p = nullptr;
+    CK(cudaMalloc(&p, (size_t)s * s * 4));
+    CK(cudaMemsetAsync(p, 0, (size_t)s * s * 4, ctx->stream));  // glGenerateMipmap of an empty texture
+    ctx->levels[ctx->n_levels++] = p;
+  }
+  ctx->heights.assign((size_t)size, 0);
+  ctx->entries.clear();
+  ctx->table_dirty = true;
+  return FDC_OK;
+}
+
+// findEmptyRect (glcontext.nim:541-579).  *grew is set when the atlas doubled (all entries dropped).
+int find_empty_rect(fdc_ctx* ctx, int width, int height, int* rx, int* ry, bool* grew) {
+  for (;;) {
+    const int imgW = width + kAtlasMargin * 2, imgH = height + kAtlasMargin * 2;
+    int lowest = ctx->atlas_size, at = 0;
+    for (int i = 0; i < ctx->atlas_size; i++) {
+      const int v = ctx->heights[i];
+      if (v < lowest) {
+        bool fit = true;
+        for (int j = 0; j <= imgW; j++) {
+          if (i + j >= ctx->atlas_size) { fit = false; break; }
+          if ((int)ctx->heights[i + j] > v) { fit = false; break; }
+        }
+        if (fit) { lowest = v; at = i; }
+      }
+    }
+    if (lowest + imgH > ctx->atlas_size) {
+      if (ctx->atlas_size >= 16384) return ctx->fail(FDC_ERR_CAPACITY, "atlas cannot grow beyond 16384 for a %dx%d image", width, height);
+      int rc = atlas_alloc(ctx, ctx->atlas_size * 2);  // grow -> resetImageAtlas, glcontext.nim:536-539
+      if (rc) return rc;
+      *grew = true;
+      continue;
+    }
+    for (int j = at; j < at + imgW; j++) ctx->heights[j] = (uint16_t)(lowest + imgH + kAtlasMargin * 2);
+    *rx = at + kAtlasMargin;
+    *ry = lowest + kAtlasMargin;
+    return FDC_OK;
+  }
+}
+
+int upload_chain(fdc_ctx* ctx, int x, int y, int w, int h, const uint8_t* rgba) {
+  // updateSubImage (textures.nim:106-119): level 0 copy, then GPU box filter per level while w>1 && h>1
+  if (!(w > 1 && h > 1)) return FDC_OK;  // the reference's loop uploads nothing for 1-pixel-wide images
+  CK(cudaMemcpy2DAsync(ctx->levels[0] + ((size_t)y * ctx->atlas_size + x) * 4, (size_t)ctx->atlas_size * 4, rgba, (size_t)w * 4,
+                       (size_t)w * 4, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
+  int level = 0;
+  while (true) {
+    int nw = w / 2, nh = h / 2;
+    if (!(nw > 1 && nh > 1) || level + 1 >= ctx->n_levels) break;
+    launch_mip_down(ctx->levels[level], ctx->atlas_size >> level, ctx->levels[level + 1], ctx->atlas_size >> (level + 1), x, y, w, h,
+                    x / 2, y / 2, ctx->stream);
+    x /= 2; y /= 2; w = nw; h = nh;
+    level++;
+  }
+  CK(cudaGetLastError());
+  return FDC_OK;
+}
+
+int sync_table(fdc_ctx* ctx) {
+  if (!ctx->table_dirty) return FDC_OK;
+  uint32_t cap = 64;
+  while (cap < ctx->entries.size() * 2 + 2) cap *= 2;
+  std::vector<AtlasEntry> tab(cap);
+  memset(tab.data(), 0, cap * sizeof(AtlasEntry));
+  for (auto& kv : ctx->entries) {
+    uint32_t h = atlas_hash(kv.first) & (cap - 1);
+    while (tab[h].used) h = (h + 1) & (cap - 1);
+    tab[h].key = kv.first;
+    tab[h].used = 1;
+    tab[h].x = kv.second.x; tab[h].y = kv.second.y; tab[h].w = kv.second.w; tab[h].h = kv.second.h;
+  }
+  CK(ctx->d_table.reserve(cap));
+  CK(cudaMemcpyAsync(ctx->d_table.p, tab.data(), cap * sizeof(AtlasEntry), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // `tab` is pageable and about to go out of scope
+  ctx->table_cap = cap;
+  ctx->table_dirty = false;
+  return FDC_OK;
+}
+
+AtlasView atlas_view(fdc_ctx* ctx) {
+  AtlasView v;
+  memset(&v, 0, sizeof(v));
+  for (int l = 0; l < ctx->n_levels; l++) v.level[l] = ctx->levels[l];
+  v.table = ctx->d_table.p;
+  v.table_mask = ctx->table_cap ? ctx->table_cap - 1 : 0;
+  v.size = ctx->atlas_size;
+  v.n_levels = ctx->n_levels;
+  return v;
+}
+
+int put_image_impl(fdc_ctx* ctx, uint64_t key, int w, int h, const uint8_t* rgba, float out_rect[4], int* out_rebuilt) {
+  if (w <= 0 || h <= 0 || !rgba) return ctx->fail(FDC_ERR_INVALID, "putImage: bad image %dx%d", w, h);
+  int rx = 0, ry = 0;
+  bool grew = false;
+  int rc = find_empty_rect(ctx, w, h, &rx, &ry, &grew);
+  if (rc) return rc;
+  const float as = (float)ctx->atlas_size;
+  fdc_ctx::Rect4 r = {(float)rx / as, (float)ry / as, (float)w / as, (float)h / as};
+  ctx->entries[key] = r;
+  ctx->table_dirty = true;
+  if (out_rect) { out_rect[0] = r.x; out_rect[1] = r.y; out_rect[2] = r.w; out_rect[3] = r.h; }
+  if (out_rebuilt) *out_rebuilt = grew ? 1 : 0;
+  return upload_chain(ctx, rx, ry, w, h, rgba);
+}
+
+int ensure_rect_image(fdc_ctx* ctx) {
+  if (ctx->entries.count(kRectKey)) return FDC_OK;
+  uint8_t white[64];
+  memset(white, 255, sizeof(white));
+  return put_image_impl(ctx, kRectKey, 4, 4, white, nullptr, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------- recording
+uint32_t current_xform(fdc_ctx* ctx) {
+  if (ctx->xform_dirty || ctx->xforms.n == 0) {
+    const float* m = ctx->mat.m;
+    Xform x = {m[0], m[4], m[12], m[1], m[5], m[13]};
+    ctx->xforms.push(x);
+    ctx->xform_dirty = false;
+    ctx->state_dirty = true;
+  }
+  return (uint32_t)ctx->xforms.n - 1;
+}
+
+RunState current_state(fdc_ctx* ctx) {
+  RunState rs;
+  memset(&rs, 0, sizeof(rs));
+  rs.xform = current_xform(ctx);
+  rs.aa = ctx->aa;
+  rs.subpixel_shift = ctx->subpixel_enabled ? fmaxf(0.0f, fminf(ctx->subpixel_shift, 0.999f)) : -1.0f;
+  const int L = ctx->mask_write;
+  if (ctx->mask_begun) {
+    rs.flags = PF_MASK_WRITE | ((uint32_t)L << PF_DEPTH_SHIFT);
+    rs.clip_draw = L >= 1 ? ctx->mask_levels[L - 1].clip : -1;
+    rs.rectmask = 0;  // setRectMaskVert4 returns early while a mask is being drawn (glcontext.nim:865-866)
+  } else {
+    rs.flags = (uint32_t)L << PF_DEPTH_SHIFT;
+    rs.clip_draw = ctx->mask_levels[L].clip;
+    rs.rectmask = 0;
+    for (int i = (int)ctx->rm_stack.size() - 1; i >= 0; i--)
+      if (ctx->rm_stack[i].fast) { rs.rectmask = ctx->rm_stack[i].index; break; }
+  }
+  return rs;
+}
+
+// Appends one draw record under the current backend state.
+int add_draw(fdc_ctx* ctx, const fdc_call& d, uint32_t ordinal) {
+  if (!ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "draw outside beginFrame/endFrame");
+  const uint32_t idx = (uint32_t)ctx->draws.n;
+  if (ctx->xform_dirty) current_xform(ctx);
+  const bool consecutive = ctx->runs.n > 0 && ordinal == ctx->last_draw_ordinal + 1;
+  if (ctx->state_dirty || ctx->begin_pending || !consecutive || ctx->runs.n == 0) {
+    RunState rs = current_state(ctx);
+    rs.first_draw = idx;
+    rs.call_index = ordinal;
+    if (ctx->begin_pending) rs.flags |= PF_MASK_BEGIN;
+    if (!ctx->runs.push(rs)) return ctx->fail(FDC_ERR_CUDA, "out of pinned memory");
+    ctx->state_dirty = ctx->begin_pending;  // the draw after a MASK_BEGIN draw needs its own run
+    ctx->begin_pending = false;
+  }
+  if (!ctx->draws.push(d)) return ctx->fail(FDC_ERR_CUDA, "out of pinned memory");
+  ctx->last_draw_ordinal = ordinal;
+  ctx->segments.back().count++;
+  if (ctx->mask_begun) {
+    MaskLevel& ml = ctx->mask_levels[ctx->mask_write];
+    ml.draws.push_back(d);
+    ml.states.push_back(ctx->runs.p[ctx->runs.n - 1]);
+    if (ml.draws.size() == 1 && d.op == FDC_OP_ROUNDED_RECT) ml.mask_draw = (int32_t)idx;
+    else ml.mask_draw = -1;
+  }
+  return FDC_OK;
+}
+
+void fill_rect_radii(fdc_call& c, const float rect[4], const float rx[4], const float ry[4]) {
+  memcpy(&c.f[0], rect, 16);
+  memcpy(&c.f[4], rx, 16);
+  memcpy(&c.f[8], ry, 16);
+}
+
+int begin_mask_impl(fdc_ctx* ctx, const float rect[4], const float rx[4], const float ry[4], uint32_t ordinal) {
+  if (!ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "ctx.beginFrame has not been called.");
+  if (ctx->mask_begun) return ctx->fail(FDC_ERR_STATE, "ctx.beginMask has already been called.");
+  if (ctx->mask_write + 1 > kMaxMaskDepth)
+    return ctx->fail(FDC_ERR_CAPACITY, "clip masks nest deeper than %d levels", kMaxMaskDepth);
+  ctx->mask_begun = true;
+  ctx->mask_write++;
+  MaskLevel& ml = ctx->mask_levels[ctx->mask_write];
+  ml.draws.clear();
+  ml.states.clear();
+  ml.mask_draw = -1;
+  ml.clip = ctx->mask_levels[ctx->mask_write - 1].clip;
+  ctx->state_dirty = true;
+  ctx->begin_pending = true;
+  // drawRoundedRectSdf(clipRect, rgba(255,0,0,255), radii, sdfModeClipAA, 4, 0)   glcontext.nim:1906-1914
+  fdc_call c;
+  memset(&c, 0, sizeof(c));
+  c.op = FDC_OP_ROUNDED_RECT;
+  fill_rect_radii(c, rect, rx, ry);
+  c.f[12] = 4.0f;
+  c.u[0] = FDC_SDF_CLIP_AA;
+  c.u[1] = FDC_FILL_COLOR;
+  c.u[3] = 0xFF0000FFu;
+  if (rect[2] <= 0.0f || rect[3] <= 0.0f) {
+    // the quad is dropped (early-out) but the level was still cleared: everything under it is invisible.
+    // Emit a zero-sized record so the level exists; its empty bbox clips all content away.
+    ml.clip = -2;  // "clip to nothing"
+    ctx->begin_pending = false;
+    return FDC_OK;
+  }
+  return add_draw(ctx, c, ordinal);
+}
+
+int end_mask_impl(fdc_ctx* ctx) {
+  if (!ctx->mask_begun) return ctx->fail(FDC_ERR_STATE, "ctx.maskBegun has not been called.");
+  ctx->mask_begun = false;
+  MaskLevel& ml = ctx->mask_levels[ctx->mask_write];
+  if (ml.clip != -2 && ml.mask_draw >= 0) ml.clip = ml.mask_draw;
+  ctx->state_dirty = true;
+  return FDC_OK;
+}
+
+int pop_mask_impl(fdc_ctx* ctx) {
+  if (ctx->mask_write <= 0) return ctx->fail(FDC_ERR_STATE, "popMask without beginMask");
+  if (ctx->mask_begun) return ctx->fail(FDC_ERR_STATE, "popMask inside beginMask/endMask");
+  ctx->mask_write--;
+  ctx->state_dirty = true;
+  return FDC_OK;
+}
+
+// Conservative pixel bbox of a transformed rect (superset of the ceil'd quad), clipped to the frame.
+void host_bbox(fdc_ctx* ctx, const float rect[4], int& x0, int& y0, int& x1, int& y1) {
+  const float* m = ctx->mat.m;
+  float xs[4] = {rect[0], rect[0] + rect[2], rect[0] + rect[2], rect[0]};
+  float ys[4] = {rect[1], rect[1], rect[1] + rect[3], rect[1] + rect[3]};
+  float mnx = 1e30f, mny = 1e30f, mxx = -1e30f, mxy = -1e30f;
+  for (int k = 0; k < 4; k++) {
+    float x = m[0] * xs[k] + m[4] * ys[k] + m[12], y = m[1] * xs[k] + m[5] * ys[k] + m[13];
+    mnx = fminf(mnx, x); mxx = fmaxf(mxx, x); mny = fminf(mny, y); mxy = fmaxf(mxy, y);
+  }
+  x0 = std::max(0, (int)floorf(fmaxf(mnx, -1e6f)) - 1);
+  y0 = std::max(0, (int)floorf(fmaxf(mny, -1e6f)) - 1);
+  x1 = std::min(ctx->W, (int)ceilf(fminf(mxx, 1e6f)) + 2);
+  y1 = std::min(ctx->H, (int)ceilf(fminf(mxy, 1e6f)) + 2);
+}
+
+void start_segment(fdc_ctx* ctx) {
+  Segment s;
+  s.first = (uint32_t)ctx->draws.n;
+  ctx->segments.push_back(s);
+}
+
+// Re-emit the mask primitives of every open texture-mask level at the start of a new segment: the shade kernel
+// keeps mask values in registers, so a new launch has to rebuild them (they are pure functions of the pixel).
+int reemit_masks(fdc_ctx* ctx) {
+  for (int L = 1; L <= ctx->mask_write; L++) {
+    MaskLevel& ml = ctx->mask_levels[L];
+    for (size_t k = 0; k < ml.draws.size(); k++) {
+      RunState rs = ml.states[k];
+      rs.first_draw = (uint32_t)ctx->draws.n;
+      if (k == 0) rs.flags |= PF_MASK_BEGIN;
+      if (!ctx->runs.push(rs) || !ctx->draws.push(ml.draws[k])) return ctx->fail(FDC_ERR_CUDA, "out of pinned memory");
+      ctx->segments.back().count++;
+    }
+    if (ml.draws.empty() && L >= 1) {
+      // level cleared but never drawn: nothing to re-emit, content is clipped away anyway
+    }
+  }
+  ctx->state_dirty = true;
+  return FDC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- frame execution
+cudaEvent_t next_event(fdc_ctx* ctx, int* index) {
+  if (ctx->ev_used == ctx->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->ev_pool.push_back(e);
+  }
+  *index = (int)ctx->ev_used;
+  return ctx->ev_pool[ctx->ev_used++];
+}
+
+struct Timed {
+  fdc_ctx* ctx;
+  int a, kind;
+  Timed(fdc_ctx* c, int k) : ctx(c), kind(k) { cudaEventRecord(next_event(c, &a), c->stream); }
+  ~Timed() {
+    int b;
+    cudaEventRecord(next_event(ctx, &b), ctx->stream);
+    ctx->spans.push_back({a, b, kind});
+  }
+};
+
+int ensure_bin_buffers(fdc_ctx* ctx, uint32_t max_prims) {
+  const FrameView& f = ctx->frame;
+  const size_t n_bins = (size_t)f.cbx * f.cby;
+  const size_t n_chunks = (max_prims + kChunk - 1) / kChunk;
+  CK(ctx->d_chunk_counts.reserve(std::max<size_t>(1, n_chunks * n_bins)));
+  CK(ctx->d_cbin_start.reserve(n_bins + 1));
+  CK(ctx->d_tile_start.reserve((size_t)f.tiles_x * f.tiles_y));
+  CK(ctx->d_tile_count.reserve((size_t)f.tiles_x * f.tiles_y));
+  CK(ctx->d_counters.reserve(4));
+  CK(ctx->d_coarse_list.reserve(std::max<size_t>((size_t)max_prims * 3 + n_bins * 4, 1u << 16)));
+  CK(ctx->d_tile_list.reserve(std::max<size_t>((size_t)max_prims * 24 + (size_t)f.tiles_x * f.tiles_y * 2, 1u << 20)));
+  return FDC_OK;
+}
+
+BinBuffers bin_buffers(fdc_ctx* ctx) {
+  BinBuffers b;
+  b.chunk_counts = ctx->d_chunk_counts.p;
+  b.cbin_start = ctx->d_cbin_start.p;
+  b.coarse_list = ctx->d_coarse_list.p;
+  b.coarse_cap = (uint32_t)std::min<size_t>(ctx->d_coarse_list.cap, 0xFFFFFFF0u);
+  b.tile_start = ctx->d_tile_start.p;
+  b.tile_count = ctx->d_tile_count.p;
+  b.tile_list = ctx->d_tile_list.p;
+  b.tile_cap = (uint32_t)std::min<size_t>(ctx->d_tile_list.cap, 0xFFFFFFF0u);
+  b.counters = ctx->d_counters.p;
+  return b;
+}
+
+SetupArgs setup_args(fdc_ctx* ctx, const Segment& s) {
+  SetupArgs a;
+  a.draws = ctx->d_draws.p;
+  a.runs = ctx->d_runs.p;
+  a.n_runs = (int)ctx->runs.n;
+  a.xforms = ctx->d_xforms.p;
+  a.first = s.first;
+  a.count = s.count;
+  a.prims = ctx->d_prims.p + s.first;
+  a.geoms = ctx->d_geoms.p + s.first;
+  a.prim_call = ctx->d_prim_call.p + s.first;
+  a.atlas = atlas_view(ctx);
+  a.frame = ctx->frame;
+  return a;
+}
+
+// Launches every kernel of the recorded frame.  `upload`: copy the recording to the device first.
+int execute_frame(fdc_ctx* ctx, bool upload) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t n_draws = (uint32_t)ctx->draws.n;
+  int rc = sync_table(ctx);
+  if (rc) return rc;
+  ctx->ev_used = 0;
+  ctx->spans.clear();
+  int launches = 0;
+  cudaEventRecord(ctx->ev_begin, st);
+  if (upload) {
+    CK(ctx->d_draws.reserve(std::max<uint32_t>(n_draws, 1)));
+    CK(ctx->d_runs.reserve(std::max<size_t>(ctx->runs.n, 1)));
+    CK(ctx->d_xforms.reserve(std::max<size_t>(ctx->xforms.n, 1)));
+    CK(ctx->d_rectmasks.reserve(std::max<size_t>(ctx->rectmasks.n, 1)));
+    CK(ctx->d_prims.reserve(std::max<uint32_t>(n_draws, 1)));
+    CK(ctx->d_geoms.reserve(std::max<uint32_t>(n_draws, 1)));
+    CK(ctx->d_prim_call.reserve(std::max<uint32_t>(n_draws, 1)));
+    if (n_draws) CK(cudaMemcpyAsync(ctx->d_draws.p, ctx->draws.p, sizeof(fdc_call) * n_draws, cudaMemcpyHostToDevice, st));
+    if (ctx->runs.n) CK(cudaMemcpyAsync(ctx->d_runs.p, ctx->runs.p, sizeof(RunState) * ctx->runs.n, cudaMemcpyHostToDevice, st));
+    if (ctx->xforms.n) CK(cudaMemcpyAsync(ctx->d_xforms.p, ctx->xforms.p, sizeof(Xform) * ctx->xforms.n, cudaMemcpyHostToDevice, st));
+    if (ctx->rectmasks.n)
+      CK(cudaMemcpyAsync(ctx->d_rectmasks.p, ctx->rectmasks.p, sizeof(RectMaskRec) * ctx->rectmasks.n, cudaMemcpyHostToDevice, st));
+  }
+  uint32_t max_prims = 0;
+  for (auto& s : ctx->segments) max_prims = std::max(max_prims, s.count);
+  rc = ensure_bin_buffers(ctx, max_prims);
+  if (rc) return rc;
+  const size_t fb_bytes = (size_t)ctx->W * ctx->H * 4;
+  if (!ctx->ext_fb) CK(ctx->d_fb.reserve(fb_bytes));
+  bool any_blur = false;
+  for (auto& s : ctx->segments) any_blur = any_blur || s.has_blur;
+  if (any_blur) {
+    CK(ctx->d_backdrop.reserve(fb_bytes));
+    CK(ctx->d_temp.reserve(fb_bytes));
+  }
+  for (size_t si = 0; si < ctx->segments.size(); si++) {
+    const Segment& s = ctx->segments[si];
+    {
+      Timed t(ctx, 0);
+      launch_prim_setup(setup_args(ctx, s), st);
+      launches += s.count ? 1 : 0;
+      launch_binning(ctx->d_prims.p + s.first, s.count, ctx->frame, bin_buffers(ctx), st, &launches);
+    }
+    {
+      Timed t(ctx, 1);
+      ShadeArgs sa;
+      memset(&sa, 0, sizeof(sa));
+      sa.prims = ctx->d_prims.p + s.first;
+      sa.geoms = ctx->d_geoms.p + s.first;
+      sa.rectmasks = ctx->d_rectmasks.p;
+      sa.tile_start = ctx->d_tile_start.p;
+      sa.tile_count = ctx->d_tile_count.p;
+      sa.tile_list = ctx->d_tile_list.p;
+      sa.counters = ctx->d_counters.p;
+      sa.fb = ctx->fb();
+      sa.backdrop = ctx->d_backdrop.p;
+      sa.atlas = atlas_view(ctx);
+      sa.frame = ctx->frame;
+      sa.load_dst = (si > 0 || !ctx->clear) ? 1 : 0;
+      sa.clear_rgba8 = ctx->clear_rgba8;
+      const bool last = si + 1 == ctx->segments.size();
+      sa.peers = (last && ctx->n_peers > 0) ? ctx->d_peers.p : nullptr;
+      sa.n_peers = (last && ctx->n_peers > 0) ? ctx->n_peers : 0;
+      launch_shade(sa, st);
+      launches++;
+    }
+    if (s.has_blur) {
+      Timed t(ctx, 2);
+      BlurArgs ba;
+      ba.src = ctx->fb();
+      ba.temp = ctx->d_temp.p;
+      ba.dst = ctx->d_backdrop.p;
+      ba.W = ctx->W; ba.H = ctx->H;
+      ba.x0 = s.rx0; ba.y0 = s.ry0; ba.x1 = s.rx1; ba.y1 = s.ry1;
+      ba.radius = s.blur_radius;
+      launch_backdrop_blur(ba, st, &launches);
+    }
+  }
+  cudaEventRecord(ctx->ev_end, st);
+  CK(cudaGetLastError());
+  ctx->stats.n_prims = n_draws;
+  ctx->stats.n_segments = (uint32_t)ctx->segments.size();
+  ctx->stats.tiles_x = ctx->frame.tiles_x;
+  ctx->stats.tiles_y = ctx->frame.tiles_y;
+  ctx->stats.tile_w = kTileW;
+  ctx->stats.tile_h = kTileH;
+  ctx->stats.n_launches = launches;
+  ctx->have_frame = true;
+  return FDC_OK;
+}
+
+// After a frame: wait, and if a bin list overflowed grow the lists and replay the frame once.
+int resolve_frame(fdc_ctx* ctx) {
+  if (!ctx->have_frame) return FDC_OK;
+  for (int attempt = 0; attempt < 4; attempt++) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint32_t c[4] = {0, 0, 0, 0};
+    if (!ctx->d_counters.p) return FDC_OK;
+    CK(cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+    ctx->stats.n_tile_entries = c[0];
+    if (c[1] == 0) return FDC_OK;
+    // overflow: counters hold the required sizes (coarse total exact, tile cursor = total needed)
+    if (c[1] & 1u) CK(ctx->d_coarse_list.reserve((size_t)c[2] + (c[2] >> 2) + 1024));
+    if (c[1] & 2u) CK(ctx->d_tile_list.reserve((size_t)c[0] + (c[0] >> 2) + 1024));
+    int rc = execute_frame(ctx, false);
+    if (rc) return rc;
+  }
+  return ctx->fail(FDC_ERR_CAPACITY, "bin lists still overflow after regrowing");
+}
+
+void compute_frame_view(fdc_ctx* ctx) {
+  FrameView& f = ctx->frame;
+  f.W = ctx->W; f.H = ctx->H;
+  f.tiles_x = (ctx->W + kTileW - 1) / kTileW;
+  f.tiles_y = (ctx->H + kTileH - 1) / kTileH;
+  const int per = (f.tiles_y + ctx->n_ranks - 1) / ctx->n_ranks;
+  f.ty0 = std::min(ctx->rank * per, f.tiles_y);
+  f.ty1 = std::min(f.ty0 + per, f.tiles_y);
+  f.cty0 = (f.ty0 / kCoarse) * kCoarse;
+  f.cbx = (f.tiles_x + kCoarse - 1) / kCoarse;
+  f.cby = f.ty1 > f.ty0 ? (f.ty1 - f.cty0 + kCoarse - 1) / kCoarse : 0;
+  f.band_y0 = f.ty0 * kTileH;
+  f.band_y1 = std::min(f.ty1 * kTileH, ctx->H);
+}
+
+uint8_t quant8(float x) {
+  x = fminf(fmaxf(x, 0.0f), 1.0f);
+  return (uint8_t)floorf(x * 255.0f + 0.5f);
+}
+
+}  // namespace
+
+// ================================================================================================= C ABI
+extern "C" {
+
+int fdc_abi_version(void) { return FDC_ABI_VERSION; }
+
+const char* fdc_last_error(fdc_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int fdc_create(fdc_ctx** out, int device, int atlas_size, float pixel_scale, int rank, int n_ranks) {
+  if (!out) return FDC_ERR_INVALID;
+  *out = nullptr;
+  if (atlas_size < 16 || atlas_size > 16384 || n_ranks < 1 || rank < 0 || rank >= n_ranks) {
+    g_create_error = "fdc_create: bad arguments";
+    return FDC_ERR_INVALID;
+  }
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) {
+    g_create_error = std::string("fdc_create: no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "bad ordinal") +
+                     "); there is no CPU fallback";
+    return FDC_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = "fdc_create: kernels are built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return FDC_ERR_CUDA;
+  }
+  fdc_ctx* ctx = new fdc_ctx();
+  ctx->device = device;
+  ctx->pixel_scale = pixel_scale;
+  ctx->rank = rank;
+  ctx->n_ranks = n_ranks;
+  ctx->initial_atlas_size = atlas_size;
+  auto bail = [&](cudaError_t err, const char* what) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+    delete ctx;
+    return FDC_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+  if ((e = cudaEventCreate(&ctx->ev_begin)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&ctx->ev_end)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  ctx->mask_levels[0].clip = -1;
+  int rc = atlas_alloc(ctx, atlas_size);
+  if (rc) {
+    g_create_error = ctx->error;
+    delete ctx;
+    return rc;
+  }
+  *out = ctx;
+  return FDC_OK;
+}
+
+void fdc_destroy(fdc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int l = 0; l < ctx->n_levels; l++) cudaFree(ctx->levels[l]);
+  ctx->d_table.release();
+  ctx->draws.release(); ctx->runs.release(); ctx->xforms.release(); ctx->rectmasks.release();
+  ctx->d_draws.release(); ctx->d_runs.release(); ctx->d_xforms.release(); ctx->d_rectmasks.release();
+  ctx->d_prims.release(); ctx->d_geoms.release(); ctx->d_prim_call.release();
+  ctx->d_chunk_counts.release(); ctx->d_cbin_start.release(); ctx->d_coarse_list.release();
+  ctx->d_tile_start.release(); ctx->d_tile_count.release(); ctx->d_tile_list.release(); ctx->d_counters.release();
+  ctx->d_fb.release(); ctx->d_backdrop.release(); ctx->d_temp.release(); ctx->d_peers.release();
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+  if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+// ------------------------------------------------------------------------------------------------- frame
+int fdc_begin_frame(fdc_ctx* ctx, int width, int height, int clear_main, const float clear_rgba[4]) {
+  if (!ctx) return FDC_ERR_INVALID;
+  if (ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "ctx.beginFrame has already been called.");
+  if (width <= 0 || height <= 0 || width > 32640 || height > 32640) return ctx->fail(FDC_ERR_INVALID, "bad frame size %dx%d", width, height);
+  CK(cudaSetDevice(ctx->device));
+  int rc = resolve_frame(ctx);  // previous frame must be complete before its recording is dropped
+  if (rc) return rc;
+  ctx->have_frame = false;
+  if (ctx->ext_fb == nullptr && (width != ctx->W || height != ctx->H)) {
+    // new size: the internal framebuffer starts black/transparent like a fresh GL back buffer
+    CK(ctx->d_fb.reserve((size_t)width * height * 4));
+    CK(cudaMemsetAsync(ctx->d_fb.p, 0, (size_t)width * height * 4, ctx->stream));
+  }
+  ctx->W = width; ctx->H = height;
+  ctx->clear = clear_main != 0;
+  if (clear_main && clear_rgba) {
+    ctx->clear_rgba8 = (uint32_t)quant8(clear_rgba[0]) | ((uint32_t)quant8(clear_rgba[1]) << 8) | ((uint32_t)quant8(clear_rgba[2]) << 16) |
+                       ((uint32_t)quant8(clear_rgba[3]) << 24);
+  }
+  compute_frame_view(ctx);
+  ctx->draws.n = ctx->runs.n = ctx->xforms.n = ctx->rectmasks.n = 0;
+  ctx->segments.clear();
+  start_segment(ctx);
+  ctx->frame_begun = true;
+  ctx->mask_begun = false;
+  ctx->mask_write = 0;
+  ctx->mask_levels[0].clip = -1;
+  ctx->rm_stack.clear();  // beginFrameProj glcontext.nim:1955
+  ctx->state_dirty = ctx->xform_dirty = true;
+  ctx->begin_pending = false;
+  ctx->call_ordinal = 0;
+  ctx->last_draw_ordinal = 0;
+  return FDC_OK;
+}
+
+int fdc_end_frame(fdc_ctx* ctx) {
+  if (!ctx) return FDC_ERR_INVALID;
+  if (!ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "ctx.beginFrame was not called first.");
+  if (ctx->mask_write != 0) return ctx->fail(FDC_ERR_STATE, "Not all masks have been popped.");
+  if (!ctx->rm_stack.empty()) return ctx->fail(FDC_ERR_STATE, "Not all rect masks have been popped.");
+  ctx->frame_begun = false;
+  CK(cudaSetDevice(ctx->device));
+  return execute_frame(ctx, true);
+}
+
+int fdc_replay_frame(fdc_ctx* ctx) {
+  if (!ctx) return FDC_ERR_INVALID;
+  if (!ctx->have_frame || ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "no completed frame to replay");
+  CK(cudaSetDevice(ctx->device));
+  return execute_frame(ctx, false);
+}
+
+int fdc_sync(fdc_ctx* ctx) {
+  if (!ctx) return FDC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  return resolve_frame(ctx);
+}
+
+int fdc_read_pixels(fdc_ctx* ctx, int x, int y, int w, int h, uint8_t* out_rgba) {
+  if (!ctx || !out_rgba) return FDC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc = resolve_frame(ctx);
+  if (rc) return rc;
+  if (!ctx->fb() || ctx->W <= 0) return ctx->fail(FDC_ERR_STATE, "no frame has been rendered");
+  if (w <= 0 || h <= 0) { x = 0; y = 0; w = ctx->W; h = ctx->H; }
+  if (x < 0 || y < 0 || x + w > ctx->W || y + h > ctx->H) return ctx->fail(FDC_ERR_INVALID, "readPixels rect outside the frame");
+  CK(cudaMemcpy2DAsync(out_rgba, (size_t)w * 4, ctx->fb() + ((size_t)y * ctx->W + x) * 4, (size_t)ctx->W * 4, (size_t)w * 4, (size_t)h,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return FDC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- transforms
+static void mark_xform(fdc_ctx* ctx) { ctx->xform_dirty = true; }
+
+int fdc_translate(fdc_ctx* ctx, float x, float y) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->call_ordinal++;
+  Mat4 t = mat_identity();
+  t.m[12] = x; t.m[13] = y;
+  ctx->mat = mat_mul(ctx->mat, t);
+  mark_xform(ctx);
+  return FDC_OK;
+}
+int fdc_rotate(fdc_ctx* ctx, float angle) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->call_ordinal++;
+  Mat4 r = mat_identity();  // vmath rotateZ: +angle turns +x toward -y on screen
+  const float cs = cosf(angle), sn = sinf(angle);
+  r.m[0] = cs; r.m[1] = -sn; r.m[4] = sn; r.m[5] = cs;
+  ctx->mat = mat_mul(ctx->mat, r);
+  mark_xform(ctx);
+  return FDC_OK;
+}
+int fdc_scale(fdc_ctx* ctx, float sx, float sy) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->call_ordinal++;
+  Mat4 s = mat_identity();
+  s.m[0] = sx; s.m[5] = sy;
+  ctx->mat = mat_mul(ctx->mat, s);
+  mark_xform(ctx);
+  return FDC_OK;
+}
+int fdc_apply_transform(fdc_ctx* ctx, const float mat4[16]) {
+  if (!ctx || !mat4) return FDC_ERR_INVALID;
+  ctx->call_ordinal++;
+  Mat4 m;
+  memcpy(m.m, mat4, 64);
+  ctx->mat = mat_mul(ctx->mat, m);
+  mark_xform(ctx);
+  return FDC_OK;
+}
+int fdc_save_transform(fdc_ctx* ctx) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->call_ordinal++;
+  ctx->mats.push_back(ctx->mat);
+  return FDC_OK;
+}
+int fdc_restore_transform(fdc_ctx* ctx) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->call_ordinal++;
+  if (ctx->mats.empty()) return ctx->fail(FDC_ERR_STATE, "restoreTransform on an empty stack");
+  ctx->mat = ctx->mats.back();
+  ctx->mats.pop_back();
+  mark_xform(ctx);
+  return FDC_OK;
+}
+int fdc_transform_mirrors_y(fdc_ctx* ctx) {
+  if (!ctx) return 0;
+  const float* m = ctx->mat.m;  // determinant of the 2x2 linear part (glcontext.nim:2019-2024)
+  return (m[0] * m[5] - m[1] * m[4]) < 0.0f ? 1 : 0;
+}
+int fdc_get_transform(fdc_ctx* ctx, float out_mat4[16]) {
+  if (!ctx || !out_mat4) return FDC_ERR_INVALID;
+  memcpy(out_mat4, ctx->mat.m, 64);
+  return FDC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- AA / text flags
+float fdc_sdf_aa_factor(fdc_ctx* ctx) { return ctx ? ctx->aa : 0.0f; }
+int fdc_set_sdf_aa_factor(fdc_ctx* ctx, float aa) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->call_ordinal++;
+  if (ctx->aa == aa) return FDC_OK;
+  ctx->aa = aa;
+  ctx->state_dirty = true;
+  return FDC_OK;
+}
+int fdc_set_text_subpixel_positioning_enabled(fdc_ctx* ctx, int enabled) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->subpixel_enabled = enabled != 0;
+  ctx->state_dirty = true;
+  return FDC_OK;
+}
+int fdc_set_text_subpixel_shift(fdc_ctx* ctx, float shift) {
+  if (!ctx) return FDC_ERR_INVALID;
+  if (ctx->subpixel_shift != shift) ctx->state_dirty = true;
+  ctx->subpixel_shift = shift;
+  return FDC_OK;
+}
+float fdc_pixel_scale(fdc_ctx* ctx) { return ctx ? ctx->pixel_scale : 1.0f; }
+
+// ------------------------------------------------------------------------------------------------- draws
+static void put_fill(fdc_call& c, const fdc_fill* fill) {
+  c.u[1] = fill->kind;
+  c.u[2] = fill->axis;
+  memcpy(&c.u[3], fill->c, 16);
+  c.f[16] = fill->mid_pos;
+}
+
+int fdc_draw_rounded_rect_sdf(fdc_ctx* ctx, const float rect[4], const fdc_fill* fill, const float radii_x[4], const float radii_y[4],
+                              int mode, float factor, float spread, const float shape_size[2]) {
+  if (!ctx || !rect || !fill || !radii_x || !radii_y) return FDC_ERR_INVALID;
+  const uint32_t ord = ctx->call_ordinal++;
+  if (rect[2] <= 0.0f || rect[3] <= 0.0f) return FDC_OK;  // glcontext.nim:1463-1464
+  fdc_call c;
+  memset(&c, 0, sizeof(c));
+  c.op = FDC_OP_ROUNDED_RECT;
+  fill_rect_radii(c, rect, radii_x, radii_y);
+  c.f[12] = factor; c.f[13] = spread;
+  if (shape_size) { c.f[14] = shape_size[0]; c.f[15] = shape_size[1]; }
+  c.u[0] = (uint32_t)mode;
+  put_fill(c, fill);
+  return add_draw(ctx, c, ord);
+}
+
+int fdc_draw_image(fdc_ctx* ctx, uint64_t key, const float pos[2], const uint32_t colors[4], const float size[2], int flip_y) {
+  if (!ctx || !pos || !colors) return FDC_ERR_INVALID;
+  const uint32_t ord = ctx->call_ordinal++;
+  if (!ctx->entries.count(key)) return ctx->fail(FDC_ERR_MISSING_IMAGE, "missing image in context");
+  fdc_call c;
+  memset(&c, 0, sizeof(c));
+  c.op = FDC_OP_IMAGE;
+  c.u[0] = (uint32_t)key; c.u[1] = (uint32_t)(key >> 32);
+  memcpy(&c.u[3], colors, 16);
+  c.u[7] = flip_y ? 1u : 0u;
+  c.f[0] = pos[0]; c.f[1] = pos[1];
+  if (size) { c.f[2] = size[0]; c.f[3] = size[1]; }
+  return add_draw(ctx, c, ord);
+}
+
+int fdc_draw_msdf_image(fdc_ctx* ctx, uint64_t key, const float pos[2], uint32_t color, const float size[2], float px_range,
+                        float sd_threshold, float stroke_weight, int flip_y, int is_mtsdf) {
+  if (!ctx || !pos || !size) return FDC_ERR_INVALID;
+  const uint32_t ord = ctx->call_ordinal++;
+  if (!ctx->entries.count(key)) return ctx->fail(FDC_ERR_MISSING_IMAGE, "missing image in context");
+  fdc_call c;
+  memset(&c, 0, sizeof(c));
+  c.op = FDC_OP_MSDF;
+  c.u[0] = (uint32_t)key; c.u[1] = (uint32_t)(key >> 32);
+  c.u[2] = is_mtsdf ? 1u : 0u;
+  c.u[3] = color;
+  c.u[7] = flip_y ? 1u : 0u;
+  c.f[0] = pos[0]; c.f[1] = pos[1]; c.f[2] = size[0]; c.f[3] = size[1];
+  c.f[4] = px_range; c.f[5] = sd_threshold; c.f[6] = stroke_weight;
+  return add_draw(ctx, c, ord);
+}
+
+int fdc_draw_quadratic_bezier_sdf(fdc_ctx* ctx, const float rect[4], const fdc_fill* fill, const float p0[2], const float p1[2],
+                                  const float p2[2], float stroke_weight, int cap) {
+  if (!ctx || !rect || !fill || !p0 || !p1 || !p2) return FDC_ERR_INVALID;
+  const uint32_t ord = ctx->call_ordinal++;
+  if (rect[2] <= 0.0f || rect[3] <= 0.0f || stroke_weight <= 0.0f) return FDC_OK;  // glcontext.nim:1631-1632
+  fdc_call c;
+  memset(&c, 0, sizeof(c));
+  c.op = FDC_OP_BEZIER;
+  memcpy(&c.f[0], rect, 16);
+  c.f[4] = p0[0]; c.f[5] = p0[1]; c.f[6] = p1[0]; c.f[7] = p1[1]; c.f[8] = p2[0]; c.f[9] = p2[1];
+  c.f[10] = stroke_weight;
+  c.u[0] = (uint32_t)cap;
+  put_fill(c, fill);
+  return add_draw(ctx, c, ord);
+}
+
+int fdc_draw_filled_quad(fdc_ctx* ctx, const float verts[8], const uint32_t colors[4]) {
+  if (!ctx || !verts || !colors) return FDC_ERR_INVALID;
+  const uint32_t ord = ctx->call_ordinal++;
+  int rc = ensure_rect_image(ctx);
+  if (rc) return rc;
+  fdc_call c;
+  memset(&c, 0, sizeof(c));
+  c.op = FDC_OP_FILLED_QUAD;
+  memcpy(&c.f[0], verts, 32);
+  memcpy(&c.u[3], colors, 16);
+  return add_draw(ctx, c, ord);
+}
+
+int fdc_draw_rect(fdc_ctx* ctx, const float rect[4], uint32_t color) {
+  if (!ctx || !rect) return FDC_ERR_INVALID;
+  const uint32_t ord = ctx->call_ordinal++;
+  int rc = ensure_rect_image(ctx);
+  if (rc) return rc;
+  fdc_call c;
+  memset(&c, 0, sizeof(c));
+  c.op = FDC_OP_RECT;
+  memcpy(&c.f[0], rect, 16);
+  c.u[3] = color;
+  return add_draw(ctx, c, ord);
+}
+
+int fdc_draw_backdrop_blur(fdc_ctx* ctx, const float rect[4], const float radii_x[4], const float radii_y[4], float blur_radius) {
+  if (!ctx || !rect || !radii_x || !radii_y) return FDC_ERR_INVALID;
+  const uint32_t ord = ctx->call_ordinal++;
+  if (blur_radius <= 0.0f || rect[2] <= 0.0f || rect[3] <= 0.0f) return FDC_OK;  // glcontext.nim:1791-1792
+  if (!ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "draw outside beginFrame/endFrame");
+  if (ctx->mask_begun) return ctx->fail(FDC_ERR_STATE, "drawBackdropBlur inside beginMask/endMask is not supported");
+  if (ctx->n_ranks > 1) return ctx->fail(FDC_ERR_STATE, "backdrop blur with tile-band partitioning needs the halo exchange (not built yet)");
+  Segment& s = ctx->segments.back();
+  s.has_blur = true;
+  s.blur_radius = blur_radius;
+  host_bbox(ctx, rect, s.rx0, s.ry0, s.rx1, s.ry1);
+  start_segment(ctx);
+  int rc = reemit_masks(ctx);
+  if (rc) return rc;
+  // composite: drawRoundedRectSdf(rect, whiteColor, radii, sdfModeBackdropBlur, factor = blurRadius)  glcontext.nim:1833-1841
+  fdc_call c;
+  memset(&c, 0, sizeof(c));
+  c.op = FDC_OP_ROUNDED_RECT;
+  fill_rect_radii(c, rect, radii_x, radii_y);
+  c.f[12] = blur_radius;
+  c.u[0] = FDC_SDF_BACKDROP_BLUR;
+  c.u[1] = FDC_FILL_COLOR;
+  c.u[3] = 0xFFFFFFFFu;
+  ctx->state_dirty = true;
+  return add_draw(ctx, c, ord);
+}
+
+// ------------------------------------------------------------------------------------------------- masks
+int fdc_begin_mask(fdc_ctx* ctx, const float rect[4], const float radii_x[4], const float radii_y[4]) {
+  if (!ctx || !rect || !radii_x || !radii_y) return FDC_ERR_INVALID;
+  const uint32_t ord = ctx->call_ordinal++;
+  return begin_mask_impl(ctx, rect, radii_x, radii_y, ord);
+}
+int fdc_end_mask(fdc_ctx* ctx) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->call_ordinal++;
+  return end_mask_impl(ctx);
+}
+int fdc_pop_mask(fdc_ctx* ctx) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->call_ordinal++;
+  return pop_mask_impl(ctx);
+}
+int fdc_begin_rect_mask(fdc_ctx* ctx, const float rect[4], const float radii_x[4], const float radii_y[4]) {
+  if (!ctx || !rect || !radii_x || !radii_y) return FDC_ERR_INVALID;
+  const uint32_t ord = ctx->call_ordinal++;
+  if (!ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "ctx.beginFrame has not been called.");
+  if (ctx->mask_begun) return ctx->fail(FDC_ERR_STATE, "ctx.beginRectMask cannot start inside a mask.");
+  if (ctx->rm_stack.empty() && rect[2] > 0.0f && rect[3] > 0.0f) {
+    // makeRectMask glcontext.nim:831-850
+    RectMaskRec rm;
+    memset(&rm, 0, sizeof(rm));
+    const float hx = rect[2] * 0.5f, hy = rect[3] * 0.5f;
+    Mat4 inv;
+    if (!mat_inverse(ctx->mat, inv)) inv = mat_identity();
+    float rr[4];
+    const bool ell = rounded_radii_vec_h(radii_x, radii_y, hx, hy, rr);
+    rm.cx = rect[0] + hx; rm.cy = rect[1] + hy; rm.hx = hx; rm.hy = hy;
+    rm.r0 = rr[0]; rm.r1 = rr[1]; rm.r2 = rr[2]; rm.r3 = rr[3];
+    rm.ax = inv.m[0]; rm.ay = inv.m[4]; rm.az = inv.m[12];
+    rm.bx = inv.m[1]; rm.by = inv.m[5]; rm.bz = inv.m[13];
+    rm.elliptical = ell ? 1.0f : 0.0f;
+    if (!ctx->rectmasks.push(rm)) return ctx->fail(FDC_ERR_CUDA, "out of pinned memory");
+    ctx->rm_stack.push_back({true, (uint32_t)ctx->rectmasks.n});
+    ctx->state_dirty = true;
+    return FDC_OK;
+  }
+  int rc = begin_mask_impl(ctx, rect, radii_x, radii_y, ord);
+  if (rc) return rc;
+  rc = end_mask_impl(ctx);
+  if (rc) return rc;
+  ctx->rm_stack.push_back({false, 0});
+  return FDC_OK;
+}
+int fdc_pop_rect_mask(fdc_ctx* ctx) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->call_ordinal++;
+  if (ctx->rm_stack.empty()) return ctx->fail(FDC_ERR_STATE, "No rect mask has been pushed.");
+  RectMaskEntry e = ctx->rm_stack.back();
+  ctx->rm_stack.pop_back();
+  ctx->state_dirty = true;
+  if (!e.fast) return pop_mask_impl(ctx);
+  return FDC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- display list
+int fdc_submit_calls(fdc_ctx* ctx, const fdc_call* calls, size_t n) {
+  if (!ctx || (!calls && n)) return FDC_ERR_INVALID;
+  for (size_t i = 0; i < n; i++) {
+    const fdc_call& c = calls[i];
+    int rc = FDC_OK;
+    switch (c.op) {
+      case FDC_OP_NOP: ctx->call_ordinal++; break;
+      case FDC_OP_SAVE_TRANSFORM: rc = fdc_save_transform(ctx); break;
+      case FDC_OP_RESTORE_TRANSFORM: rc = fdc_restore_transform(ctx); break;
+      case FDC_OP_TRANSLATE: rc = fdc_translate(ctx, c.f[0], c.f[1]); break;
+      case FDC_OP_ROTATE: rc = fdc_rotate(ctx, c.f[0]); break;
+      case FDC_OP_SCALE: rc = fdc_scale(ctx, c.f[0], c.f[1]); break;
+      case FDC_OP_APPLY_TRANSFORM: rc = fdc_apply_transform(ctx, c.f); break;
+      case FDC_OP_SET_AA: rc = fdc_set_sdf_aa_factor(ctx, c.f[0]); break;
+      case FDC_OP_SET_SUBPIXEL:
+        ctx->call_ordinal++;
+        fdc_set_text_subpixel_positioning_enabled(ctx, (int)c.u[0]);
+        fdc_set_text_subpixel_shift(ctx, c.f[0]);
+        break;
+      case FDC_OP_BEGIN_MASK: rc = fdc_begin_mask(ctx, &c.f[0], &c.f[4], &c.f[8]); break;
+      case FDC_OP_END_MASK: rc = fdc_end_mask(ctx); break;
+      case FDC_OP_POP_MASK: rc = fdc_pop_mask(ctx); break;
+      case FDC_OP_BEGIN_RECT_MASK: rc = fdc_begin_rect_mask(ctx, &c.f[0], &c.f[4], &c.f[8]); break;
+      case FDC_OP_POP_RECT_MASK: rc = fdc_pop_rect_mask(ctx); break;
+      case FDC_OP_BACKDROP_BLUR: rc = fdc_draw_backdrop_blur(ctx, &c.f[0], &c.f[4], &c.f[8], c.f[12]); break;
+      case FDC_OP_FILLED_QUAD:
+      case FDC_OP_RECT:
+        rc = ensure_rect_image(ctx);
+        if (rc) break;
+        // fallthrough
+      case FDC_OP_ROUNDED_RECT:
+      case FDC_OP_IMAGE:
+      case FDC_OP_MSDF:
+      case FDC_OP_BEZIER: {
+        // Draw records are taken verbatim; early-outs and atlas lookups happen in prim_setup_kernel.
+        const uint32_t ord = ctx->call_ordinal++;
+        rc = add_draw(ctx, c, ord);
+        break;
+      }
+      default: rc = ctx->fail(FDC_ERR_INVALID, "fdc_submit_calls: unknown op %u at record %zu", c.op, i); break;
+    }
+    if (rc != FDC_OK) return rc;
+  }
+  return FDC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- atlas
+int fdc_put_image(fdc_ctx* ctx, uint64_t key, int w, int h, const uint8_t* rgba, float out_rect[4], int* out_rebuilt) {
+  if (!ctx) return FDC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  return put_image_impl(ctx, key, w, h, rgba, out_rect, out_rebuilt);
+}
+int fdc_update_image(fdc_ctx* ctx, uint64_t key, int w, int h, const uint8_t* rgba) {
+  if (!ctx || !rgba) return FDC_ERR_INVALID;
+  auto it = ctx->entries.find(key);
+  if (it == ctx->entries.end()) return ctx->fail(FDC_ERR_MISSING_IMAGE, "updateImage: unknown key");
+  const float as = (float)ctx->atlas_size;
+  if (it->second.w != (float)w / as || it->second.h != (float)h / as) return ctx->fail(FDC_ERR_INVALID, "updateImage: size differs");
+  CK(cudaSetDevice(ctx->device));
+  return upload_chain(ctx, (int)(it->second.x * as), (int)(it->second.y * as), w, h, rgba);
+}
+int fdc_has_image(fdc_ctx* ctx, uint64_t key) { return ctx && ctx->entries.count(key) ? 1 : 0; }
+int fdc_get_image_rect(fdc_ctx* ctx, uint64_t key, float out_rect[4]) {
+  if (!ctx || !out_rect) return FDC_ERR_INVALID;
+  auto it = ctx->entries.find(key);
+  if (it == ctx->entries.end()) return ctx->fail(FDC_ERR_MISSING_IMAGE, "unknown image key");
+  out_rect[0] = it->second.x; out_rect[1] = it->second.y; out_rect[2] = it->second.w; out_rect[3] = it->second.h;
+  return FDC_OK;
+}
+int fdc_remove_image(fdc_ctx* ctx, uint64_t key) {
+  if (!ctx) return FDC_ERR_INVALID;
+  if (ctx->entries.erase(key)) ctx->table_dirty = true;  // entries.del(key): the texels stay, as in GL
+  return FDC_OK;
+}
+int fdc_reset_image_atlas(fdc_ctx* ctx, int minimum_size) {
+  if (!ctx) return FDC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int size = std::max(ctx->initial_atlas_size, 1);  // plannedAtlasSize figbackend.nim:223-227
+  const int minimum = std::max(minimum_size, size);
+  while (size < minimum) size *= 2;
+  return atlas_alloc(ctx, size);
+}
+int fdc_atlas_size(fdc_ctx* ctx) { return ctx ? ctx->atlas_size : 0; }
+int fdc_atlas_packed_area(fdc_ctx* ctx) {
+  if (!ctx) return 0;
+  long long a = 0;
+  for (uint16_t h : ctx->heights) a += h;
+  return (int)std::min<long long>(a, 0x7FFFFFFF);
+}
+
+// ------------------------------------------------------------------------------------------------- plumbing
+int fdc_bind_framebuffer(fdc_ctx* ctx, void* device_rgba8) {
+  if (!ctx) return FDC_ERR_INVALID;
+  if (ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "cannot rebind the framebuffer inside a frame");
+  int rc = resolve_frame(ctx);
+  if (rc) return rc;
+  ctx->ext_fb = (uint8_t*)device_rgba8;
+  return FDC_OK;
+}
+void* fdc_framebuffer_ptr(fdc_ctx* ctx) { return ctx ? ctx->fb() : nullptr; }
+int fdc_band_rows(fdc_ctx* ctx, int* y0, int* y1) {
+  if (!ctx || !y0 || !y1) return FDC_ERR_INVALID;
+  *y0 = ctx->frame.band_y0;
+  *y1 = ctx->frame.band_y1;
+  return FDC_OK;
+}
+void* fdc_stream(fdc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int fdc_set_peer_framebuffers(fdc_ctx* ctx, void* const* device_ptrs, int n) {
+  if (!ctx || n < 0 || (n && !device_ptrs)) return FDC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc = resolve_frame(ctx);
+  if (rc) return rc;
+  ctx->n_peers = n;
+  if (n) {
+    CK(ctx->d_peers.reserve((size_t)n));
+    CK(cudaMemcpy(ctx->d_peers.p, device_ptrs, sizeof(void*) * n, cudaMemcpyHostToDevice));
+  }
+  return FDC_OK;
+}
+
+int fdc_get_frame_stats(fdc_ctx* ctx, fdc_frame_stats* out) {
+  if (!ctx || !out) return FDC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc = resolve_frame(ctx);
+  if (rc) return rc;
+  if (ctx->have_frame) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) ctx->stats.gpu_ms = ms;
+    float acc[3] = {0, 0, 0};
+    for (auto& sp : ctx->spans)
+      if (cudaEventElapsedTime(&ms, ctx->ev_pool[sp.a], ctx->ev_pool[sp.b]) == cudaSuccess) acc[sp.kind] += ms;
+    ctx->stats.bin_ms = acc[0]; ctx->stats.shade_ms = acc[1]; ctx->stats.blur_ms = acc[2];
+  }
+  *out = ctx->stats;
+  return FDC_OK;
+}
+
+int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t offsets_cap, uint32_t* entries, size_t entries_cap,
+                   size_t* n_offsets, size_t* n_entries) {
+  if (!ctx) return FDC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc = resolve_frame(ctx);
+  if (rc) return rc;
+  if (!ctx->have_frame) return ctx->fail(FDC_ERR_STATE, "no completed frame");
+  if (segment < 0 || segment >= (int)ctx->segments.size()) return ctx->fail(FDC_ERR_INVALID, "bad segment index");
+  const Segment& s = ctx->segments[segment];
+  // Re-run setup + binning for this segment (the lists are reused between segments), then read them back.
+  int launches = 0;
+  launch_prim_setup(setup_args(ctx, s), ctx->stream);
+  launch_binning(ctx->d_prims.p + s.first, s.count, ctx->frame, bin_buffers(ctx), ctx->stream, &launches);
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t n_tiles = (size_t)ctx->frame.tiles_x * ctx->frame.tiles_y;
+  std::vector<uint32_t> start(n_tiles, 0), count(n_tiles, 0), calls(std::max<uint32_t>(s.count, 1));
+  uint32_t c[4];
+  CK(cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+  if (c[1]) return ctx->fail(FDC_ERR_CAPACITY, "bin lists overflowed during debug readback");
+  CK(cudaMemcpy(start.data(), ctx->d_tile_start.p, n_tiles * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(count.data(), ctx->d_tile_count.p, n_tiles * 4, cudaMemcpyDeviceToHost));
+  if (s.count) CK(cudaMemcpy(calls.data(), ctx->d_prim_call.p + s.first, (size_t)s.count * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> list(std::max<uint32_t>(c[0], 1));
+  if (c[0]) CK(cudaMemcpy(list.data(), ctx->d_tile_list.p, (size_t)c[0] * 4, cudaMemcpyDeviceToHost));
+  size_t total = 0;
+  const int ty0 = ctx->frame.ty0, ty1 = ctx->frame.ty1, tx_n = ctx->frame.tiles_x;
+  for (int ty = ty0; ty < ty1; ty++)
+    for (int tx = 0; tx < tx_n; tx++) total += count[(size_t)ty * tx_n + tx];
+  if (n_offsets) *n_offsets = n_tiles + 1;
+  if (n_entries) *n_entries = total;
+  if (!tile_offsets || !entries) return FDC_OK;
+  if (offsets_cap < n_tiles + 1 || entries_cap < total) return ctx->fail(FDC_ERR_INVALID, "debug_bins: buffers too small");
+  size_t at = 0;
+  for (size_t t = 0; t < n_tiles; t++) {
+    tile_offsets[t] = (uint32_t)at;
+    const int ty = (int)(t / tx_n);
+    if (ty < ty0 || ty >= ty1) continue;
+    for (uint32_t k = 0; k < count[t]; k++) entries[at++] = calls[list[start[t] + k]];
+  }
+  tile_offsets[n_tiles] = (uint32_t)at;
+  return FDC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// Host-callable launchers of the sm_100a kernels.  All launches are asynchronous on `stream`.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fdc_types.h"
+
+namespace fdc {
+
+struct SetupArgs {
+  const fdc_call* draws;  // all draws of the frame (device)
+  const RunState* runs;
+  int n_runs;
+  const Xform* xforms;
+  uint32_t first, count;  // this segment's draw range [first, first+count)
+  Prim* prims;            // [count] output
+  QuadGeom* geoms;        // [count] output (only PF_GENERAL entries are meaningful)
+  uint32_t* prim_call;    // [count] backend-call ordinal per primitive (debug bins)
+  AtlasView atlas;
+  FrameView frame;
+};
+void launch_prim_setup(const SetupArgs& a, cudaStream_t stream);
+
+struct BinBuffers {
+  uint32_t* chunk_counts;  // [n_chunks * n_cbins]
+  uint32_t* cbin_start;    // [n_cbins + 1]
+  uint32_t* coarse_list;   // [coarse_cap]
+  uint32_t coarse_cap;
+  uint32_t* tile_start;    // [tiles_x * tiles_y]
+  uint32_t* tile_count;    // [tiles_x * tiles_y]
+  uint32_t* tile_list;     // [tile_cap]
+  uint32_t tile_cap;
+  uint32_t* counters;      // [4]: 0 tile cursor, 1 overflow flags, 2 coarse total, 3 tile total
+};
+void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& frame, const BinBuffers& b,
+                    cudaStream_t stream, int* n_launches);
+
+struct ShadeArgs {
+  const Prim* prims;
+  const QuadGeom* geoms;
+  const RectMaskRec* rectmasks;
+  const uint32_t* tile_start;
+  const uint32_t* tile_count;
+  const uint32_t* tile_list;
+  const uint32_t* counters;  // overflow flag: kernel leaves the frame untouched when set
+  uint8_t* fb;               // RGBA8 W*H, top-left origin
+  const uint8_t* backdrop;   // RGBA8 W*H (blurred copy for sdfModeBackdropBlur) or nullptr
+  AtlasView atlas;
+  FrameView frame;
+  int load_dst;              // 0: start from clear colour; 1: read fb
+  uint32_t clear_rgba8;
+  uint8_t* const* peers;     // optional peer framebuffers (device array of n_peers pointers) or nullptr
+  int n_peers;
+};
+void launch_shade(const ShadeArgs& a, cudaStream_t stream);
+
+struct BlurArgs {
+  const uint8_t* src;  // framebuffer
+  uint8_t* temp;       // H-pass output
+  uint8_t* dst;        // backdrop (V-pass output)
+  int W, H;
+  int x0, y0, x1, y1;  // region of dst that is needed (composite quad bbox, clipped)
+  float radius;        // blurRadius as passed to drawBackdropBlur
+};
+void launch_backdrop_blur(const BlurArgs& a, cudaStream_t stream, int* n_launches);
+
+void launch_fill_u32(uint32_t* dst, uint32_t value, size_t n, cudaStream_t stream);
+// Builds mip level `l+1` region from level `l` (premultiplied 2x2 box, see oracle upload_chain).
+void launch_mip_down(const uint8_t* src, int src_size, uint8_t* dst, int dst_size, int sx, int sy, int sw, int sh,
+                     int dx, int dy, cudaStream_t stream);
+
+}  // namespace fdc

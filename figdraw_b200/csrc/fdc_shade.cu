@@ -1,0 +1,557 @@
+// Per-tile SDF shade-and-blend kernel (sm_100a).
+//
+// One CTA per 16x16-pixel tile, 8 warps, each warp owns an 8x4 pixel block, one pixel per thread.  A warp walks
+// the tile's ordered primitive list 32 entries at a time: every lane tests one primitive's clipped bbox against
+// the warp's block (ballot), then the warp shades the survivors one by one, all lanes on the same primitive, so
+// every branch on mode/flags is warp-uniform.  The pixel lives in registers as four floats holding exact RGBA8
+// values (0..255) and is re-quantised after EVERY blended primitive, which is what GL's UNORM8 render target
+// does (SURVEY.md 8a' trap 6).  Texture masks (clip stack) are evaluated analytically and kept per pixel as
+// up to eight UNORM8 levels packed in two registers, including the reference's a*a quirk (mask.frag:233 with
+// GL_BLEND still enabled).
+//
+// The arithmetic restates src/figdraw/opengl/glsl/atlas.frag (main :252-405, sdRoundedBox :51-69,
+// sdEllipticalRoundedBox :71-115, sdBezier :121-160, bezierStrokeSd :178-209, shadowProfile :211-216,
+// evalFillColor :218-250), atlas_rect_mask.frag:222-237, mask.frag:186-234 and the blend state of
+// utils/glutils.nim:150-154, in float32 with fused multiply-adds and MUFU approximations; results are
+// compared against the CPU oracle within +-2 LSB (tests/test_gpu_parity.py).
+//
+// Work that provably cannot change a pixel is skipped (DESIGN.md "work reduction"): primitives before the last
+// opaque full-coverage fill of a warp's block, and blends whose source alpha is exactly zero.
+#include <cuda_runtime.h>
+
+#include "fdc_kernels.h"
+
+namespace fdc {
+
+namespace {
+
+__device__ __forceinline__ float sat(float x) { return __saturatef(x); }
+__device__ __forceinline__ float rint255(float x) {  // round to nearest (even) integer, |x| < 2^22
+  return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f);
+}
+__device__ __forceinline__ float len2(float x, float y) { return sqrtf(fmaf(x, x, y * y)); }
+
+// atlas.frag:51-69
+__device__ __forceinline__ float sd_rounded_box(float px, float py, float bx, float by, float r0, float r1, float r2, float r3) {
+  const float rr = px > 0.0f ? (py > 0.0f ? r0 : r1) : (py > 0.0f ? r2 : r3);
+  const float qx = fabsf(px) - bx + rr, qy = fabsf(py) - by + rr;
+  return fminf(fmaxf(qx, qy), 0.0f) + len2(fmaxf(qx, 0.0f), fmaxf(qy, 0.0f)) - rr;
+}
+
+// atlas.frag:71-79
+__device__ float sd_ellipse(float px, float py, float rx, float ry) {
+  const float sx = fmaxf(rx, 0.000001f), sy = fmaxf(ry, 0.000001f);
+  const float k0 = len2(px / sx, py / sy);
+  if (k0 <= 0.000001f) return -fminf(sx, sy);
+  const float k1 = len2(px / (sx * sx), py / (sy * sy));
+  return k0 * (k0 - 1.0f) / fmaxf(k1, 0.000001f);
+}
+
+// atlas.frag:96-115
+__device__ float sd_elliptical_rounded_box(float px, float py, float bx, float by, float r0, float r1, float r2, float r3) {
+  const float sel = px > 0.0f ? (py > 0.0f ? r0 : r1) : (py > 0.0f ? r2 : r3);
+  if (sel < 0.0f) {
+    const float r = -sel - 1.0f;
+    return sd_rounded_box(px, py, bx, by, r, r, r, r);
+  }
+  const float pv = floorf(sel + 0.5f);
+  const float hi = floorf(pv / 4096.0f);
+  const float rx = (pv - 4096.0f * hi) * bx / 4095.0f, ry = hi * by / 4095.0f;
+  if (rx <= 0.0f || ry <= 0.0f) {
+    const float qx = fabsf(px) - bx, qy = fabsf(py) - by;
+    return fminf(fmaxf(qx, qy), 0.0f) + len2(fmaxf(qx, 0.0f), fmaxf(qy, 0.0f));
+  }
+  if (rx == ry) return sd_rounded_box(px, py, bx, by, rx, rx, rx, rx);
+  const float qx = fabsf(px) - bx + rx, qy = fabsf(py) - by + ry;
+  if (qx > 0.0f && qy > 0.0f) return sd_ellipse(qx, qy, rx, ry);
+  return fmaxf(qx - rx, qy - ry);
+}
+
+__device__ __forceinline__ float signf_(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+
+// atlas.frag:121-160
+__device__ float sd_bezier(float posx, float posy, float Ax, float Ay, float Bx, float By, float Cx, float Cy) {
+  const float ax = Bx - Ax, ay = By - Ay;
+  const float bx = Ax - 2.0f * Bx + Cx, by = Ay - 2.0f * By + Cy;
+  const float bb = bx * bx + by * by;
+  if (bb <= 0.000001f) {
+    const float bax = Cx - Ax, bay = Cy - Ay;
+    const float h = fminf(fmaxf(((posx - Ax) * bax + (posy - Ay) * bay) / fmaxf(bax * bax + bay * bay, 0.000001f), 0.0f), 1.0f);
+    return len2(posx - (Ax + bax * h), posy - (Ay + bay * h));
+  }
+  const float cx = ax * 2.0f, cy = ay * 2.0f;
+  const float dx = Ax - posx, dy = Ay - posy;
+  const float kk = 1.0f / bb;
+  const float kx = kk * (ax * bx + ay * by);
+  const float ky = kk * (2.0f * (ax * ax + ay * ay) + (dx * bx + dy * by)) / 3.0f;
+  const float kz = kk * (dx * ax + dy * ay);
+  const float p = ky - kx * kx;
+  const float p3 = p * p * p;
+  const float q = kx * (2.0f * kx * kx - 3.0f * ky) + kz;
+  float h = q * q + 4.0f * p3;
+  float res;
+  if (h >= 0.0f) {
+    h = sqrtf(h);
+    const float x0 = (h - q) / 2.0f, x1 = (-h - q) / 2.0f;
+    const float r0 = signf_(x0) * powf(fabsf(x0), 1.0f / 3.0f), r1 = signf_(x1) * powf(fabsf(x1), 1.0f / 3.0f);
+    const float t = fminf(fmaxf(r0 + r1 - kx, 0.0f), 1.0f);
+    const float ex = dx + (cx + bx * t) * t, ey = dy + (cy + by * t) * t;
+    res = ex * ex + ey * ey;
+  } else {
+    const float z = sqrtf(-p);
+    const float v = acosf(fminf(fmaxf(q / (p * z * 2.0f), -1.0f), 1.0f)) / 3.0f;
+    const float m = cosf(v), n = sinf(v) * 1.732050808f;
+    const float t1 = fminf(fmaxf((m + m) * z - kx, 0.0f), 1.0f), t2 = fminf(fmaxf((-n - m) * z - kx, 0.0f), 1.0f);
+    const float e1x = dx + (cx + bx * t1) * t1, e1y = dy + (cy + by * t1) * t1;
+    const float e2x = dx + (cx + bx * t2) * t2, e2y = dy + (cy + by * t2) * t2;
+    res = fminf(e1x * e1x + e1y * e1y, e2x * e2x + e2y * e2y);
+  }
+  return sqrtf(res);
+}
+
+__device__ __forceinline__ void safe_normalize(float vx, float vy, float fx, float fy, float& ox, float& oy) {
+  const float len = len2(vx, vy);
+  if (len <= 0.000001f) { ox = fx; oy = fy; } else { ox = vx / len; oy = vy / len; }
+}
+
+// atlas.frag:178-209
+__device__ float bezier_stroke_sd(float dist, float px, float py, float Ax, float Ay, float Bx, float By, float Cx, float Cy,
+                                  float halfW, int mode) {
+  if (mode == FDC_SDF_BEZIER_STROKE_AA) return dist - halfW;
+  float fbx, fby, stx, sty, etx, ety;
+  safe_normalize(Cx - Ax, Cy - Ay, 1.0f, 0.0f, fbx, fby);
+  safe_normalize(Bx - Ax, By - Ay, fbx, fby, stx, sty);
+  safe_normalize(Cx - Bx, Cy - By, fbx, fby, etx, ety);
+  const float startProj = (px - Ax) * stx + (py - Ay) * sty;
+  const float endProj = (px - Cx) * etx + (py - Cy) * ety;
+  const float trim = (mode == FDC_SDF_BEZIER_STROKE_SQUARE_AA) ? halfW : 0.0f;
+  float tube = dist;
+  if (mode == FDC_SDF_BEZIER_STROKE_SQUARE_AA) {
+    if (startProj < 0.0f) tube = fminf(tube, fabsf((px - Ax) * sty - (py - Ay) * stx));
+    if (endProj > 0.0f) tube = fminf(tube, fabsf((px - Cx) * ety - (py - Cy) * etx));
+  }
+  const float cap = fmaxf(-startProj - trim, endProj - trim);
+  return fmaxf(tube - halfW, cap);
+}
+
+__device__ __forceinline__ float4 unpack255(uint32_t c) {
+  return make_float4((float)(c & 255u), (float)((c >> 8) & 255u), (float)((c >> 16) & 255u), (float)(c >> 24));
+}
+
+__device__ __forceinline__ int wrap_i(int i, int n) {
+  int m = i % n;
+  return m < 0 ? m + n : m;
+}
+
+// GL_LINEAR + GL_REPEAT on one RGBA8 level; (tu,tv) are texel coordinates minus 0.5.  Returns 0..255 per channel.
+__device__ float4 tex_bilinear(const uint8_t* __restrict__ img, int size, float tu, float tv) {
+  const float fx = floorf(tu), fy = floorf(tv);
+  const float ax = tu - fx, ay = tv - fy;
+  const int i0 = wrap_i((int)fx, size), i1 = wrap_i((int)fx + 1, size);
+  const int j0 = wrap_i((int)fy, size), j1 = wrap_i((int)fy + 1, size);
+  const uint32_t* im = reinterpret_cast<const uint32_t*>(img);
+  const float4 t00 = unpack255(__ldg(im + (size_t)j0 * size + i0)), t10 = unpack255(__ldg(im + (size_t)j0 * size + i1));
+  const float4 t01 = unpack255(__ldg(im + (size_t)j1 * size + i0)), t11 = unpack255(__ldg(im + (size_t)j1 * size + i1));
+  float4 r;
+  {
+    const float top = fmaf(t10.x - t00.x, ax, t00.x), bot = fmaf(t11.x - t01.x, ax, t01.x);
+    r.x = fmaf(bot - top, ay, top);
+  }
+  {
+    const float top = fmaf(t10.y - t00.y, ax, t00.y), bot = fmaf(t11.y - t01.y, ax, t01.y);
+    r.y = fmaf(bot - top, ay, top);
+  }
+  {
+    const float top = fmaf(t10.z - t00.z, ax, t00.z), bot = fmaf(t11.z - t01.z, ax, t01.z);
+    r.z = fmaf(bot - top, ay, top);
+  }
+  {
+    const float top = fmaf(t10.w - t00.w, ax, t00.w), bot = fmaf(t11.w - t01.w, ax, t01.w);
+    r.w = fmaf(bot - top, ay, top);
+  }
+  return r;
+}
+
+// texture(atlasTex, uv): min LINEAR_MIPMAP_LINEAR / mag LINEAR (glcontext.nim:157-169).  lambda = log2(rho).
+__device__ float4 atlas_sample(const AtlasView& at, float tu, float tv, float lambda) {
+  if (lambda <= 0.0f) return tex_bilinear(at.level[0], at.size, tu, tv);
+  const int maxl = at.n_levels - 1;
+  const float cu = tu + 0.5f, cv = tv + 0.5f;  // level-0 texel-space coordinate
+  if (lambda >= (float)maxl) {
+    const float sc = 1.0f / (float)(1 << maxl);
+    return tex_bilinear(at.level[maxl], at.size >> maxl, cu * sc - 0.5f, cv * sc - 0.5f);
+  }
+  const int d1 = (int)floorf(lambda);
+  const float fr = lambda - (float)d1;
+  const float s1 = 1.0f / (float)(1 << d1), s2 = 0.5f * s1;
+  const float4 a = tex_bilinear(at.level[d1], at.size >> d1, cu * s1 - 0.5f, cv * s1 - 0.5f);
+  const float4 b = tex_bilinear(at.level[d1 + 1], at.size >> (d1 + 1), cu * s2 - 0.5f, cv * s2 - 0.5f);
+  return make_float4(fmaf(b.x - a.x, fr, a.x), fmaf(b.y - a.y, fr, a.y), fmaf(b.z - a.z, fr, a.z), fmaf(b.w - a.w, fr, a.w));
+}
+
+struct Pixel {
+  float r, g, b, a;   // exact UNORM8 values 0..255
+  uint32_t mlo, mhi;  // texture-mask levels 1..8, UNORM8 each
+};
+
+__device__ __forceinline__ float mask_get(const Pixel& px, int level) {  // level 1..8
+  const int i = level - 1;
+  const uint32_t w = i < 4 ? px.mlo : px.mhi;
+  return (float)((w >> ((i & 3) * 8)) & 255u);
+}
+__device__ __forceinline__ void mask_set(Pixel& px, int level, float v) {
+  const int i = level - 1, sh = (i & 3) * 8;
+  const uint32_t b = (uint32_t)(int)v & 255u;
+  if (i < 4) px.mlo = (px.mlo & ~(255u << sh)) | (b << sh);
+  else px.mhi = (px.mhi & ~(255u << sh)) | (b << sh);
+}
+
+// General (rotated) quad: top-left-rule inside test on the two triangles (3,0,1),(2,3,1) and affine (s,t).
+// Mirrors the oracle's raster_tri: exact integer edge functions on doubled coordinates.
+struct GeneralHit {
+  bool inside;
+  float s, t;
+  float dsdx, dsdy, dtdx, dtdy;
+};
+__device__ GeneralHit general_quad(const QuadGeom& g, int ix, int iy) {
+  GeneralHit h;
+  h.inside = false;
+  h.s = h.t = 0.0f;
+  h.dsdx = h.dsdy = h.dtdx = h.dtdy = 0.0f;
+  const float vs[4] = {0.0f, 1.0f, 1.0f, 0.0f}, vt[4] = {1.0f, 1.0f, 0.0f, 0.0f};
+  const int tri[2][3] = {{3, 0, 1}, {2, 3, 1}};
+  const long long px2 = 2ll * ix + 1, py2 = 2ll * iy + 1;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int ia = tri[k][0], ib = tri[k][1], ic = tri[k][2];
+    const long long ex[3] = {2ll * g.vx[ia], 2ll * g.vx[ib], 2ll * g.vx[ic]};
+    const long long ey[3] = {2ll * g.vy[ia], 2ll * g.vy[ib], 2ll * g.vy[ic]};
+    const long long area = (ex[1] - ex[0]) * (ey[2] - ey[0]) - (ey[1] - ey[0]) * (ex[2] - ex[0]);
+    if (area == 0) continue;
+    const long long sgn = area > 0 ? 1 : -1;
+    bool in = true;
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+      const int n = (e + 1) % 3;
+      const long long ea = -sgn * (ey[n] - ey[e]), eb = sgn * (ex[n] - ex[e]);
+      const long long v = ea * (px2 - ex[e]) + eb * (py2 - ey[e]);
+      if (v < 0 || (v == 0 && !(ea > 0 || (ea == 0 && eb > 0)))) in = false;
+    }
+    if (!in) continue;
+    const float Ax = (float)g.vx[ia], Ay = (float)g.vy[ia], Bx = (float)g.vx[ib], By = (float)g.vy[ib];
+    const float Cx = (float)g.vx[ic], Cy = (float)g.vy[ic];
+    const float inv_area = 1.0f / ((Bx - Ax) * (Cy - Ay) - (By - Ay) * (Cx - Ax));
+    const float bcy = (Cy - Ay) * inv_area, bby = (By - Ay) * inv_area, bcx = (Cx - Ax) * inv_area, bbx = (Bx - Ax) * inv_area;
+    h.dsdx = (vs[ib] - vs[ia]) * bcy - (vs[ic] - vs[ia]) * bby;
+    h.dsdy = (vs[ic] - vs[ia]) * bbx - (vs[ib] - vs[ia]) * bcx;
+    h.dtdx = (vt[ib] - vt[ia]) * bcy - (vt[ic] - vt[ia]) * bby;
+    h.dtdy = (vt[ic] - vt[ia]) * bbx - (vt[ib] - vt[ia]) * bcx;
+    const float rx = (float)ix + 0.5f - Ax, ry = (float)iy + 0.5f - Ay;
+    h.s = vs[ia] + (rx * h.dsdx + ry * h.dsdy);
+    h.t = vt[ia] + (rx * h.dtdx + ry * h.dtdy);
+    h.inside = true;
+    break;
+  }
+  return h;
+}
+
+// Vertex colours BL,BR,TR,TL interpolated per triangle: (TL,BL,BR) where t >= s, (TR,TL,BR) otherwise.
+__device__ __forceinline__ float4 vertex_color(const uint4 c, float s, float t) {
+  const float4 bl = unpack255(c.x), br = unpack255(c.y), tr = unpack255(c.z), tl = unpack255(c.w);
+  const bool lower = t >= s;
+  float4 o;
+  o.x = lower ? fmaf(bl.x - tl.x, t, fmaf(br.x - bl.x, s, tl.x)) : fmaf(br.x - tr.x, t, fmaf(tr.x - tl.x, s, tl.x));
+  o.y = lower ? fmaf(bl.y - tl.y, t, fmaf(br.y - bl.y, s, tl.y)) : fmaf(br.y - tr.y, t, fmaf(tr.y - tl.y, s, tl.y));
+  o.z = lower ? fmaf(bl.z - tl.z, t, fmaf(br.z - bl.z, s, tl.z)) : fmaf(br.z - tr.z, t, fmaf(tr.z - tl.z, s, tl.z));
+  o.w = lower ? fmaf(bl.w - tl.w, t, fmaf(br.w - bl.w, s, tl.w)) : fmaf(br.w - tr.w, t, fmaf(tr.w - tl.w, s, tl.w));
+  return o;
+}
+
+// evalFillColor, atlas.frag:218-250 (colours in 0..255)
+__device__ __forceinline__ float4 linear3_color(uint32_t c0, uint32_t c1, uint32_t c2, int fill_mode, float mid, float s, float t) {
+  float tt = fill_mode == 1 ? s : (fill_mode == 2 ? t : (fill_mode == 3 ? 0.5f * (s + t) : 0.5f * (s + (1.0f - t))));
+  tt = sat(tt);
+  const float4 a = unpack255(c0), m = unpack255(c1), b = unpack255(c2);
+  if (tt <= mid) {
+    const float k = tt / mid;
+    return make_float4(fmaf(m.x - a.x, k, a.x), fmaf(m.y - a.y, k, a.y), fmaf(m.z - a.z, k, a.z), fmaf(m.w - a.w, k, a.w));
+  }
+  const float k = (tt - mid) / (1.0f - mid);
+  return make_float4(fmaf(b.x - m.x, k, m.x), fmaf(b.y - m.y, k, m.y), fmaf(b.z - m.z, k, m.z), fmaf(b.w - m.w, k, m.w));
+}
+
+// atlas_rect_mask.frag:222-237
+__device__ float rect_mask_alpha(const RectMaskRec& rm, float aa, float px, float py) {
+  if (rm.hx < 0.0f || rm.hy < 0.0f) return 1.0f;
+  const float lx = fmaf(rm.ax, px, rm.ay * py) + rm.az, ly = fmaf(rm.bx, px, rm.by * py) + rm.bz;
+  const float qx = lx - rm.cx, qy = -(ly - rm.cy);
+  const float dist = rm.elliptical > 0.5f ? sd_elliptical_rounded_box(qx, qy, rm.hx, rm.hy, rm.r0, rm.r1, rm.r2, rm.r3)
+                                          : sd_rounded_box(qx, qy, rm.hx, rm.hy, rm.r0, rm.r1, rm.r2, rm.r3);
+  return 1.0f - sat(fmaf(aa, dist, 0.5f));
+}
+
+__device__ __forceinline__ void blend(Pixel& px, float sr, float sg, float sb, float sa) {
+  // rgb = s*sa + d*(1-sa); a = sa + da*(1-sa)  (glBlendFuncSeparate, glutils.nim:150-154), then UNORM8 store
+  px.r = rint255(fmaf(sr - px.r, sa, px.r));
+  px.g = rint255(fmaf(sg - px.g, sa, px.g));
+  px.b = rint255(fmaf(sb - px.b, sa, px.b));
+  px.a = rint255(fmaf(255.0f - px.a, sa, px.a));
+}
+
+__device__ void shade_prim(const ShadeArgs& a, const Prim* __restrict__ P, int ix, int iy, Pixel& px) {
+  const float4* Q = reinterpret_cast<const float4*>(P);
+  const int4 q6 = __ldg(reinterpret_cast<const int4*>(P) + 6);
+  const uint32_t flags = (uint32_t)q6.z;
+  const int mode = (int)(flags & PF_MODE_MASK);
+  const int depth = (int)((flags & PF_DEPTH_MASK) >> PF_DEPTH_SHIFT);
+  const bool mask_write = flags & PF_MASK_WRITE;
+  if (flags & PF_MASK_BEGIN) mask_set(px, depth, 0.0f);  // glClear(0) of the mask level, glcontext.nim:1901-1902
+
+  const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
+  bool inside = ix >= bx0 && ix < bx1 && iy >= by0 && iy < by1;
+  const float4 q0 = __ldg(Q + 0);
+  float s, t;
+  float dsdx = q0.x, dsdy = 0.0f, dtdx = 0.0f, dtdy = q0.z;
+  if (flags & PF_GENERAL) {
+    GeneralHit h;
+    h.inside = false;
+    if (inside) h = general_quad(a.geoms[__float_as_uint(q0.x)], ix, iy);
+    inside = inside && h.inside;
+    s = h.s; t = h.t;
+    dsdx = h.dsdx; dsdy = h.dsdy; dtdx = h.dtdx; dtdy = h.dtdy;
+  } else {
+    s = fmaf((float)ix, q0.x, q0.y);
+    t = fmaf((float)iy, q0.z, q0.w);
+  }
+  if (!__any_sync(0xFFFFFFFFu, inside)) return;
+
+  const float4 q1 = __ldg(Q + 1), q2 = __ldg(Q + 2), q3 = __ldg(Q + 3);
+  const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(P) + 4);
+  const uint4 q5 = __ldg(reinterpret_cast<const uint4*>(P) + 5);
+  const float aa = q3.z;
+  const int fill_mode = (int)((flags & PF_FILLMODE_MASK) >> PF_FILLMODE_SHIFT);
+
+  // fill colour (0..255)
+  float4 col;
+  if (fill_mode != 0) col = linear3_color(q4.x, q5.x, q5.y, fill_mode, q3.y, s, t);
+  else if (flags & PF_SOLID) col = unpack255(q4.x);
+  else col = vertex_color(q4, s, t);
+
+  // p = (uv - .5) * 2 * quadHalf ; the SDF is evaluated at (p.x, -p.y)
+  const float ppx = (s - 0.5f) * 2.0f * q1.x, ppy = (t - 0.5f) * 2.0f * q1.y;
+  float cov = 0.0f;        // coverage alpha
+  float sr = col.x, sg = col.y, sb = col.z, salpha = col.w;  // source colour 0..255 and its alpha 0..255
+
+  const bool is_bezier = mode >= FDC_SDF_BEZIER_STROKE_AA && mode <= FDC_SDF_BEZIER_STROKE_SQUARE_AA;
+  const bool is_msdf = mode >= FDC_SDF_MSDF && mode <= FDC_SDF_MTSDF_ANNULAR;
+  if (mode == FDC_SDF_ATLAS) {
+    const float4 q7 = __ldg(Q + 7);
+    const float tu = fmaf(s, q7.y, q7.x), tv = fmaf(t, q7.w, q7.z);
+    float lambda = q3.w;
+    if (flags & PF_GENERAL) {
+      const float rx = len2(q7.y * dsdx, q7.w * dtdx), ry = len2(q7.y * dsdy, q7.w * dtdy);
+      const float rho = fmaxf(rx, ry);
+      lambda = rho > 0.0f ? log2f(rho) : -1000.0f;
+    }
+    float4 tex = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inside) tex = atlas_sample(a.atlas, tu, tv, lambda);
+    if (mask_write) {
+      cov = tex.w * (1.0f / 255.0f);  // mask.frag:196-197: alpha = tex.a * color.a
+    } else {
+      sr = tex.x * col.x * (1.0f / 255.0f); sg = tex.y * col.y * (1.0f / 255.0f); sb = tex.z * col.z * (1.0f / 255.0f);
+      salpha = tex.w * col.w * (1.0f / 255.0f);
+      cov = 1.0f;
+    }
+  } else if (is_msdf && !mask_write) {
+    const float4 q7 = __ldg(Q + 7);
+    const float tu = fmaf(s, q7.y, q7.x), tv = fmaf(t, q7.w, q7.z);
+    float4 tex = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inside) tex = tex_bilinear(a.atlas.level[0], a.atlas.size, tu, tv);  // textureLod(.., 0)
+    const bool mtsdf = mode == FDC_SDF_MTSDF || mode == FDC_SDF_MTSDF_ANNULAR;
+    const bool stroke = mode == FDC_SDF_MSDF_ANNULAR || mode == FDC_SDF_MTSDF_ANNULAR;
+    const float sd = (mtsdf ? tex.w : fmaxf(fminf(tex.x, tex.y), fminf(fmaxf(tex.x, tex.y), tex.z))) * (1.0f / 255.0f);
+    float spr = q3.w;
+    if (flags & PF_GENERAL) {
+      const float fwx = fabsf(q7.y * dsdx) + fabsf(q7.y * dsdy), fwy = fabsf(q7.w * dtdx) + fabsf(q7.w * dtdy);
+      spr = fmaxf(0.5f * (q3.x / fwx + q3.x / fwy), 1.0f);
+    }
+    const float spd = spr * (sd - q3.y);
+    cov = stroke ? sat(fmaxf(q1.y, 0.0f) * 0.5f - fabsf(spd) + 0.5f) : sat(spd + 0.5f);
+  } else {
+    float dist;
+    const bool ell = flags & PF_ELLIPTICAL;
+    const bool inset = mode == FDC_SDF_INSET_SHADOW && !mask_write;
+    const float shx = inset ? q1.x : q1.z, shy = inset ? q1.y : q1.w;
+    if (is_bezier) dist = sd_bezier(ppx, ppy, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
+    else if (ell) dist = sd_elliptical_rounded_box(ppx, -ppy, shx, shy, q2.x, q2.y, q2.z, q2.w);
+    else dist = sd_rounded_box(ppx, -ppy, shx, shy, q2.x, q2.y, q2.z, q2.w);
+
+    if (mask_write) {
+      // mask.frag:199-226
+      if (is_bezier) dist = bezier_stroke_sd(dist, ppx, ppy, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, fmaxf(q3.x, 0.0f) * 0.5f, mode);
+      if (mode == FDC_SDF_ANNULAR_AA) {
+        const float hw = fmaxf(q3.x, 0.0f) * 0.5f;
+        dist = fabsf(dist + hw) - hw;
+      }
+      cov = 1.0f - sat(fmaf(aa, dist, 0.5f));
+    } else {
+      switch (mode) {
+        case FDC_SDF_BEZIER_STROKE_AA:
+        case FDC_SDF_BEZIER_STROKE_BUTT_AA:
+        case FDC_SDF_BEZIER_STROKE_SQUARE_AA: {
+          const float sd = bezier_stroke_sd(dist, ppx, ppy, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, fmaxf(q3.x, 0.0f) * 0.5f, mode);
+          cov = 1.0f - sat(fmaf(aa, sd, 0.5f));
+          break;
+        }
+        case FDC_SDF_ANNULAR: {
+          const float f = q3.x * 0.5f;
+          cov = (fabsf(dist + f) - f) < 0.0f ? 1.0f : 0.0f;
+          break;
+        }
+        case FDC_SDF_ANNULAR_AA: {
+          const float f = q3.x * 0.5f;
+          cov = 1.0f - sat(fmaf(aa, fabsf(dist + f) - f, 0.5f));
+          break;
+        }
+        case FDC_SDF_DROP_SHADOW: {
+          const float spread = fill_mode == 0 ? q3.y : 0.0f;
+          const float sd = dist - spread;
+          cov = sd > 0.0f ? fminf(exp2f(q3.w * sd * sd), 1.0f) : 1.0f;
+          break;
+        }
+        case FDC_SDF_DROP_SHADOW_AA: {
+          const float spread = fill_mode == 0 ? q3.y : 0.0f;
+          const float sd = dist - spread;
+          cov = sd >= 0.0f ? fminf(exp2f(q3.w * sd * sd), 1.0f) : 1.0f - sat(fmaf(aa, dist, 0.5f));
+          break;
+        }
+        case FDC_SDF_INSET_SHADOW: {
+          // atlas.frag:364-379: clip against the quad-sized box, shadow from the same box offset by params.zw
+          const float clip_a = 1.0f - sat(fmaf(aa, dist, 0.5f));
+          const float sx = ppx - q1.z, sy = -ppy - (-q1.w);
+          const float sdist = ell ? sd_elliptical_rounded_box(sx, sy, q1.x, q1.y, q2.x, q2.y, q2.z, q2.w)
+                                  : sd_rounded_box(sx, sy, q1.x, q1.y, q2.x, q2.y, q2.z, q2.w);
+          const float spread = fill_mode == 0 ? q3.y : 0.0f;
+          const float sd = sdist + spread;
+          const float ia = sd < 0.0f ? fminf(exp2f(q3.w * sd * sd), 1.0f) : 1.0f;
+          cov = clip_a * ia;
+          break;
+        }
+        case FDC_SDF_BACKDROP_BLUR: {
+          cov = 1.0f - sat(fmaf(aa, dist, 0.5f));
+          if (inside && a.backdrop) {
+            const float4 b = unpack255(__ldg(reinterpret_cast<const uint32_t*>(a.backdrop) + (size_t)iy * a.frame.W + ix));
+            sr = b.x; sg = b.y; sb = b.z; salpha = b.w;
+          }
+          break;
+        }
+        default: cov = 1.0f - sat(fmaf(aa, dist, 0.5f)); break;
+      }
+    }
+  }
+
+  if (mask_write) {
+    // alpha = cov * color.a * prevMask ; R8 target with blending on: r = a*a + dst*(1-a)   (SURVEY 8a' trap 1)
+    float al = cov * (flags & PF_SOLID || fill_mode != 0 ? col.w : col.w) * (1.0f / 255.0f);
+    if (depth > 1) al *= mask_get(px, depth - 1) * (1.0f / 255.0f);
+    if (inside) {
+      const float m = mask_get(px, depth);
+      mask_set(px, depth, rint255(fmaf(al, 255.0f * al, m * (1.0f - al))));
+    }
+    return;
+  }
+  float sa = salpha * (1.0f / 255.0f) * cov;
+  if (depth > 0) sa *= mask_get(px, depth) * (1.0f / 255.0f);
+  if (flags & PF_RECTMASK) {
+    const RectMaskRec rm = a.rectmasks[((uint32_t)q6.w & 0xFFFFu) - 1u];
+    sa *= rect_mask_alpha(rm, aa, (float)ix + 0.5f, (float)iy + 0.5f);
+  }
+  if (inside && sa > 0.0f) blend(px, sr, sg, sb, sa);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256) shade_kernel(ShadeArgs a) {
+  if (a.counters[1] != 0) return;  // a bin list overflowed: host regrows and replays the frame
+  const FrameView& f = a.frame;
+  const int tile = blockIdx.x;
+  const int tx = tile % f.tiles_x, ty = f.ty0 + tile / f.tiles_x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wx0 = tx * kTileW + (warp & 1) * 8, wy0 = ty * kTileH + (warp >> 1) * 4;
+  const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
+  const bool valid = ix < f.W && iy < f.H;
+  uint32_t* fb32 = reinterpret_cast<uint32_t*>(a.fb);
+
+  Pixel px;
+  {
+    uint32_t c = a.clear_rgba8;
+    if (a.load_dst && valid) c = fb32[(size_t)iy * f.W + ix];
+    const float4 d = unpack255(c);
+    px.r = d.x; px.g = d.y; px.b = d.z; px.a = d.w;
+    px.mlo = px.mhi = 0;
+  }
+
+  const uint32_t n = a.tile_count[ty * f.tiles_x + tx];
+  const uint32_t* __restrict__ list = a.tile_list + a.tile_start[ty * f.tiles_x + tx];
+  // block rect clipped to the frame
+  const int wx1 = min(wx0 + 8, f.W), wy1 = min(wy0 + 4, f.H);
+
+  // Occlusion: find the last primitive whose opaque inner rect covers this warp's whole block; nothing before
+  // it can influence these pixels.
+  uint32_t start = 0;
+  if (wx0 < wx1 && wy0 < wy1) {
+    for (int base = (int)n - 1; base >= 0; base -= 32) {
+      const int idx = base - lane;
+      bool occ = false;
+      if (idx >= 0) {
+        const Prim* P = a.prims + __ldg(&list[idx]);
+        const uint32_t fl = (uint32_t)__ldg(reinterpret_cast<const int*>(P) + 26);
+        if (fl & PF_OCCLUDER) {
+          const int2 ir = __ldg(reinterpret_cast<const int2*>(P) + 11);
+          const int x0 = (int16_t)(ir.x & 0xFFFF), y0 = (int16_t)(ir.x >> 16), x1 = (int16_t)(ir.y & 0xFFFF), y1 = (int16_t)(ir.y >> 16);
+          occ = x0 <= wx0 && y0 <= wy0 && x1 >= wx1 && y1 >= wy1;
+        }
+      }
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, occ);
+      if (m) { start = (uint32_t)(base - (__ffs(m) - 1)); break; }
+    }
+  } else {
+    start = n;  // block entirely outside the frame
+  }
+
+  for (uint32_t base = start; base < n; base += 32) {
+    const uint32_t idx = base + lane;
+    uint32_t pid = 0;
+    bool hit = false;
+    if (idx < n) {
+      pid = __ldg(&list[idx]);
+      const int4 q6 = __ldg(reinterpret_cast<const int4*>(a.prims + pid) + 6);
+      const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
+      hit = (bx0 < wx1 && bx1 > wx0 && by0 < wy1 && by1 > wy0) || ((uint32_t)q6.z & PF_MASK_BEGIN);
+    }
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t p = __shfl_sync(0xFFFFFFFFu, pid, j);
+      shade_prim(a, a.prims + p, ix, iy, px);
+    }
+  }
+
+  if (valid) {
+    const uint32_t out = (uint32_t)(int)px.r | ((uint32_t)(int)px.g << 8) | ((uint32_t)(int)px.b << 16) | ((uint32_t)(int)px.a << 24);
+    fb32[(size_t)iy * f.W + ix] = out;
+    for (int k = 0; k < a.n_peers; k++) {
+      uint32_t* peer = reinterpret_cast<uint32_t*>(a.peers[k]);
+      if (peer && peer != fb32) peer[(size_t)iy * f.W + ix] = out;
+    }
+  }
+}
+
+void launch_shade(const ShadeArgs& a, cudaStream_t stream) {
+  const int n_tiles = a.frame.tiles_x * (a.frame.ty1 - a.frame.ty0);
+  if (n_tiles <= 0) return;
+  shade_kernel<<<n_tiles, 256, 0, stream>>>(a);
+}
+
+}  // namespace fdc

@@ -1,0 +1,132 @@
+// Shared host/device types of the figdraw CUDA backend (sm_100a).
+//
+// Data layout in HBM for one frame (see DESIGN.md "Data layout"):
+//   RawDraw[n]   the draw records exactly as they crossed the C ABI (fdc_call, 128 B) -- what GL's ten vertex
+//                attribute arrays carried, once per quad instead of four times.
+//   RunState[r]  per-run state (transform, AA, mask depth, rect mask, clip parent); a run is a maximal range
+//                of draws issued under the same backend state.  Draw i finds its run by binary search.
+//   Prim[n]      128-byte shading record produced on the device by prim_setup_kernel.
+//   coarse/tile lists: u32 primitive indices, order preserving.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/figdraw_cuda.h"
+
+namespace fdc {
+
+constexpr int kTileW = 16;         // pixels
+constexpr int kTileH = 16;
+constexpr int kCoarse = 8;         // coarse bin = kCoarse x kCoarse tiles (128 x 128 px)
+constexpr int kChunk = 1024;       // primitives per coarse-binning chunk
+constexpr int kMaxMaskDepth = 8;   // texture-mask nesting the tile kernel keeps per pixel (GL: unbounded)
+constexpr int kAtlasMargin = 4;    // glcontext.nim:257
+constexpr int kMaxAtlasLevels = 14;
+constexpr uint64_t kRectKey = 0x7265637472656374ull;  // stands for hash("rect"), glcontext.nim:966
+
+// Prim.mode_flags layout
+constexpr uint32_t PF_MODE_MASK = 0x1Fu;        // SdfMode 0..20
+constexpr uint32_t PF_ELLIPTICAL = 1u << 5;     // sdfMode + 128 in the reference
+constexpr uint32_t PF_FILLMODE_SHIFT = 6;       // 3 bits: 0 vertex colours, 1..4 linear3 X/Y/TLBR/BLTR
+constexpr uint32_t PF_FILLMODE_MASK = 7u << 6;
+constexpr uint32_t PF_MASK_WRITE = 1u << 9;     // drawn between beginMask/endMask: blends into mask level `depth`
+constexpr uint32_t PF_MASK_BEGIN = 1u << 10;    // first primitive of a mask level: level is cleared to 0 first
+constexpr uint32_t PF_GENERAL = 1u << 11;       // not an axis-aligned quad: use QuadGeom
+constexpr uint32_t PF_SOLID = 1u << 12;         // four equal vertex colours
+constexpr uint32_t PF_OCCLUDER = 1u << 13;      // opaque ClipAA fill: inner rect (ix0..iy1) has alpha exactly 1
+constexpr uint32_t PF_RECTMASK = 1u << 14;      // fast rect mask applies (index in aux)
+constexpr uint32_t PF_SUBPIXEL = 1u << 15;      // atlas: subpixel shift enabled
+constexpr uint32_t PF_DEPTH_SHIFT = 16;         // 4 bits: texture-mask level read (content) or written (mask)
+constexpr uint32_t PF_DEPTH_MASK = 0xFu << 16;
+constexpr uint32_t PF_EMPTY = 1u << 31;         // dropped (early-out or empty clipped bbox)
+
+// 128-byte shading record, eight 16-byte quads q0..q7.
+struct alignas(16) Prim {
+  // q0: quad-local (s,t) in [0,1] from the integer pixel index: s = x*su + ou, t = y*sv + ov (axis aligned).
+  //     PF_GENERAL: su's bits hold the QuadGeom index.
+  float su, ou, sv, ov;
+  // q1: sdfParams (quadHalf.xy, shapeHalf.xy | inset offset | bezier p0 | (atlasSize, strokeW))
+  float qhx, qhy, p2, p3;
+  // q2: sdfRadii (TR,BR,TL,BL | packed elliptical | bezier p1,p2)
+  float r0, r1, r2, r3;
+  // q3: factor, spread (or midPos), aa factor, k: shadows -0.5*log2(e)/sigma^2; atlas lambda (LOD); msdf screenPxRange
+  float factor, spread, aa, k;
+  // q4: vertex colours BL, BR, TR, TL
+  uint32_t c[4];
+  // q5: 3-stop colours and the occluder inner rect [ix0,ix1) x [iy0,iy1) (pixels)
+  uint32_t c_mid, c_stop;
+  int16_t ix0, iy0, ix1, iy1;
+  // q6: clipped bin bbox [bx0,bx1) x [by0,by1) (pixels), flags, aux: rect mask index+1 (low 16) | subpixel shift*65535 (high 16)
+  int16_t bx0, by0, bx1, by1;
+  uint32_t mode_flags, aux;
+  // q7: atlas texel mapping: tu = s*du + u0, tv = t*dv + v0 (level-0 texels, already minus 0.5)
+  float u0, du, v0, dv;
+};
+static_assert(sizeof(Prim) == 128, "Prim must be 128 bytes");
+
+// Geometry of a general (rotated / arbitrary) quad: ceil'd integer vertices BL, BR, TR, TL.
+struct alignas(16) QuadGeom {
+  int32_t vx[4], vy[4];
+};
+
+// Per-run backend state, resolved on the host (cheap, sequential) and consumed by prim_setup_kernel.
+struct alignas(16) RunState {
+  uint32_t first_draw;  // index of the first draw of this run (ascending)
+  uint32_t xform;       // index into the transform table
+  float aa;
+  float subpixel_shift;  // already clamped; < 0 when positioning is disabled
+  uint32_t flags;        // PF_MASK_WRITE | PF_MASK_BEGIN | depth bits
+  uint32_t rectmask;     // 0 = none, else index+1 into the rect mask table
+  int32_t clip_draw;     // draw index of the mask primitive whose bbox clips this run's draws, or -1
+  uint32_t call_index;   // backend-call ordinal of the first draw (draws of a run are consecutive calls)
+};
+static_assert(sizeof(RunState) == 32, "RunState must be 32 bytes");
+
+// 2-D affine part of the transform (vmath Mat4 columns 0, 1, 3; rows x, y).
+struct alignas(8) Xform {
+  float m00, m10, m30, m01, m11, m31;  // x' = (m00*x + m10*y) + m30 ; y' = (m01*x + m11*y) + m31
+};
+
+// Fast rect mask, atlas_rect_mask.frag:222-237 / glcontext.nim:831-850.
+struct alignas(16) RectMaskRec {
+  float cx, cy, hx, hy;          // params
+  float r0, r1, r2, r3;          // radii (TR,BR,TL,BL or packed)
+  float ax, ay, az, elliptical;  // matX.xyz, matY.w
+  float bx, by, bz, pad;         // matY.xyz
+};
+
+// Atlas entry table mirrored on the device (open addressing, linear probing) so image draws resolve their
+// atlas rect in prim_setup_kernel instead of on the host.
+struct alignas(16) AtlasEntry {
+  uint64_t key;
+  uint32_t used, pad;
+  float x, y, w, h;  // normalised rect (x,y,w,h)/atlasSize, as `entries[key]` in the reference
+};
+static_assert(sizeof(AtlasEntry) == 32, "AtlasEntry must be 32 bytes");
+
+struct AtlasView {
+  const uint8_t* level[kMaxAtlasLevels];  // RGBA8, level l is (size >> l)^2
+  const AtlasEntry* table;
+  uint32_t table_mask;  // capacity - 1 (power of two)
+  int size;
+  int n_levels;
+};
+
+struct FrameView {
+  int W, H;              // frame size in pixels
+  int tiles_x, tiles_y;  // full frame tile grid
+  int ty0, ty1;          // tile rows this rank owns (band)
+  int cbx, cby;          // coarse bin grid covering the band
+  int cty0;              // first tile row of coarse row 0 (= ty0 rounded down to a multiple of kCoarse)
+  int band_y0, band_y1;  // pixel rows of the band
+};
+
+__host__ __device__ inline uint32_t atlas_hash(uint64_t key) {
+  key ^= key >> 33;
+  key *= 0xff51afd7ed558ccdull;
+  key ^= key >> 33;
+  key *= 0xc4ceb9fe1a85ec53ull;
+  key ^= key >> 33;
+  return (uint32_t)key;
+}
+
+}  // namespace fdc

@@ -1,0 +1,307 @@
+"""`CudaContext`: the B200 backend behind figdraw's `BackendContext` interface.
+
+Python twin of the Nim shim in bindings/nim/cuda_context.nim: every `BackendContext` method
+(src/figdraw/figbackend.nim:245-705, as overridden by `OpenGlContext` in src/figdraw/opengl/glcontext.nim)
+forwards to the C-ABI function of the same meaning in libfigdraw_cuda.so.  No arithmetic happens here.
+
+There is no CPU path: constructing a context without the built extension or without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+from .abi import FdcFill, FdcFrameStats, SdfMode, Status
+from .figbackend import BackendContext, BackendFill, Radii, Trace, _rect4
+
+
+class FigDrawError(RuntimeError):
+    """common/shared.nim:19 `FigDrawError`; carries the fdc_status code."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[fdc_status {code}] {message}")
+        self.code = code
+
+
+def _f4(v) -> ctypes.Array:
+    return (ctypes.c_float * 4)(*[float(x) for x in v])
+
+
+def _f2(v) -> ctypes.Array:
+    return (ctypes.c_float * 2)(*[float(x) for x in v])
+
+
+def _u4(v) -> ctypes.Array:
+    return (ctypes.c_uint32 * 4)(*[int(x) & 0xFFFFFFFF for x in v])
+
+
+def _fill(fill: BackendFill) -> FdcFill:
+    f = FdcFill()
+    f.kind = int(fill.kind)
+    f.axis = int(fill.axis)
+    for i in range(4):
+        f.c[i] = int(fill.c[i]) & 0xFFFFFFFF
+    f.mid_pos = float(fill.midPos)
+    return f
+
+
+class CudaContext(BackendContext):
+    def __init__(self, atlasSize: int = 1024, pixelScale: float = 1.0, device: int = 0, rank: int = 0,
+                 nRanks: int = 1):
+        self._lib = abi.load_library()
+        self._h = ctypes.c_void_p()
+        rc = self._lib.fdc_create(ctypes.byref(self._h), int(device), int(atlasSize), float(pixelScale), int(rank),
+                                  int(nRanks))
+        if rc != 0:
+            msg = self._lib.fdc_last_error(None)
+            self._h = None
+            raise FigDrawError(rc, msg.decode() if msg else "fdc_create failed")
+        self.missing_images = 0
+        self._frame: Optional[Tuple[int, int]] = None
+
+    # -- plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fdc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            msg = self._lib.fdc_last_error(self._h)
+            raise FigDrawError(rc, msg.decode() if msg else "")
+
+    # -- frame
+    def beginFrame(self, frameSize, clearMain=False, clearMainColor=(1.0, 1.0, 1.0, 1.0)):
+        w, h = int(frameSize[0]), int(frameSize[1])
+        self._frame = (w, h)
+        self._ck(self._lib.fdc_begin_frame(self._h, w, h, 1 if clearMain else 0, _f4(clearMainColor)))
+
+    def endFrame(self):
+        self._ck(self._lib.fdc_end_frame(self._h))
+
+    def replayFrame(self):
+        self._ck(self._lib.fdc_replay_frame(self._h))
+
+    def sync(self):
+        self._ck(self._lib.fdc_sync(self._h))
+
+    def readPixels(self, frame=(0, 0, 0, 0), readFront=False, out: Optional[np.ndarray] = None) -> np.ndarray:
+        x, y, w, h = (int(v) for v in frame)
+        if w <= 0 or h <= 0:
+            x, y = 0, 0
+            w, h = self._frame
+        if out is None:
+            out = np.empty((h, w, 4), dtype=np.uint8)
+        self._ck(self._lib.fdc_read_pixels(self._h, x, y, w, h, out.ctypes.data))
+        return out
+
+    def pixelScale(self) -> float:
+        return float(self._lib.fdc_pixel_scale(self._h))
+
+    # -- AA / text
+    def sdfAaFactor(self) -> float:
+        return float(self._lib.fdc_sdf_aa_factor(self._h))
+
+    def setSdfAaFactor(self, aaFactor: float):
+        self._ck(self._lib.fdc_set_sdf_aa_factor(self._h, float(aaFactor)))
+
+    def setTextSubpixelPositioningEnabled(self, enabled: bool):
+        self._ck(self._lib.fdc_set_text_subpixel_positioning_enabled(self._h, 1 if enabled else 0))
+
+    def setTextSubpixelShift(self, shift: float):
+        self._ck(self._lib.fdc_set_text_subpixel_shift(self._h, float(shift)))
+
+    # -- atlas
+    def atlasSize(self) -> int:
+        return int(self._lib.fdc_atlas_size(self._h))
+
+    def atlasPackedArea(self) -> int:
+        return int(self._lib.fdc_atlas_packed_area(self._h))
+
+    def hasImage(self, key: int) -> bool:
+        return bool(self._lib.fdc_has_image(self._h, ctypes.c_uint64(key & (2**64 - 1))))
+
+    def putImage(self, key: int, image: np.ndarray):
+        """Returns (normalised atlas rect, atlas_rebuilt)."""
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        h, w = image.shape[:2]
+        rect = (ctypes.c_float * 4)()
+        rebuilt = ctypes.c_int(0)
+        self._ck(self._lib.fdc_put_image(self._h, ctypes.c_uint64(key & (2**64 - 1)), w, h, image.ctypes.data, rect,
+                                         ctypes.byref(rebuilt)))
+        return tuple(rect), bool(rebuilt.value)
+
+    def updateImage(self, key: int, image: np.ndarray):
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        h, w = image.shape[:2]
+        self._ck(self._lib.fdc_update_image(self._h, ctypes.c_uint64(key & (2**64 - 1)), w, h, image.ctypes.data))
+
+    def imageRect(self, key: int):
+        rect = (ctypes.c_float * 4)()
+        self._ck(self._lib.fdc_get_image_rect(self._h, ctypes.c_uint64(key & (2**64 - 1)), rect))
+        return tuple(rect)
+
+    def removeImage(self, key: int):
+        self._ck(self._lib.fdc_remove_image(self._h, ctypes.c_uint64(key & (2**64 - 1))))
+
+    def resetImageAtlas(self, minimumSize: int):
+        self._ck(self._lib.fdc_reset_image_atlas(self._h, int(minimumSize)))
+
+    # -- draws
+    def drawRoundedRectSdf(self, rect, fill, radii, mode=SdfMode.sdfModeClipAA, factor=4.0, spread=0.0,
+                           shapeSize=(0.0, 0.0)):
+        f = _fill(fill)
+        self._ck(self._lib.fdc_draw_rounded_rect_sdf(self._h, _f4(_rect4(rect)), ctypes.byref(f), _f4(radii[0]),
+                                                     _f4(radii[1]), int(mode), float(factor), float(spread),
+                                                     _f2(shapeSize)))
+
+    def drawImage(self, key, pos, colors, size=(0.0, 0.0), flipY=False):
+        rc = self._lib.fdc_draw_image(self._h, ctypes.c_uint64(key & (2**64 - 1)), _f2(pos), _u4(colors), _f2(size),
+                                      1 if flipY else 0)
+        if rc == Status.ERR_MISSING_IMAGE:  # glcontext.nim:1305-1310: warn and skip
+            self.missing_images += 1
+            return
+        self._ck(rc)
+
+    def _msdf(self, mtsdf, key, pos, color, size, pxRange, sdThreshold, strokeWeight, flipY):
+        rc = self._lib.fdc_draw_msdf_image(self._h, ctypes.c_uint64(key & (2**64 - 1)), _f2(pos),
+                                           int(color) & 0xFFFFFFFF, _f2(size), float(pxRange), float(sdThreshold),
+                                           float(strokeWeight), 1 if flipY else 0, 1 if mtsdf else 0)
+        if rc == Status.ERR_MISSING_IMAGE:
+            self.missing_images += 1
+            return
+        self._ck(rc)
+
+    def drawMsdfImage(self, key, pos, color, size, pxRange, sdThreshold=0.5, strokeWeight=0.0, flipY=False):
+        self._msdf(False, key, pos, color, size, pxRange, sdThreshold, strokeWeight, flipY)
+
+    def drawMtsdfImage(self, key, pos, color, size, pxRange, sdThreshold=0.5, strokeWeight=0.0, flipY=False):
+        self._msdf(True, key, pos, color, size, pxRange, sdThreshold, strokeWeight, flipY)
+
+    def drawQuadraticBezierSdf(self, rect, fill, p0, p1, p2, strokeWeight, cap):
+        f = _fill(fill)
+        self._ck(self._lib.fdc_draw_quadratic_bezier_sdf(self._h, _f4(_rect4(rect)), ctypes.byref(f), _f2(p0), _f2(p1),
+                                                         _f2(p2), float(strokeWeight), int(cap)))
+
+    def drawFilledQuad(self, verts, colors):
+        v = (ctypes.c_float * 8)(*[float(c) for p in verts for c in p])
+        self._ck(self._lib.fdc_draw_filled_quad(self._h, v, _u4(colors)))
+
+    def drawRect(self, rect, color):
+        self._ck(self._lib.fdc_draw_rect(self._h, _f4(_rect4(rect)), int(color) & 0xFFFFFFFF))
+
+    def drawBackdropBlur(self, rect, radii, blurRadius):
+        self._ck(self._lib.fdc_draw_backdrop_blur(self._h, _f4(_rect4(rect)), _f4(radii[0]), _f4(radii[1]),
+                                                  float(blurRadius)))
+
+    # -- masks
+    def beginMask(self, clipRect, radii):
+        self._ck(self._lib.fdc_begin_mask(self._h, _f4(_rect4(clipRect)), _f4(radii[0]), _f4(radii[1])))
+
+    def endMask(self):
+        self._ck(self._lib.fdc_end_mask(self._h))
+
+    def popMask(self):
+        self._ck(self._lib.fdc_pop_mask(self._h))
+
+    def beginRectMask(self, maskRect, radii):
+        self._ck(self._lib.fdc_begin_rect_mask(self._h, _f4(_rect4(maskRect)), _f4(radii[0]), _f4(radii[1])))
+
+    def popRectMask(self):
+        self._ck(self._lib.fdc_pop_rect_mask(self._h))
+
+    # -- transforms
+    def translate(self, v):
+        self._ck(self._lib.fdc_translate(self._h, float(v[0]), float(v[1])))
+
+    def rotate(self, angle):
+        self._ck(self._lib.fdc_rotate(self._h, float(angle)))
+
+    def scale(self, s):
+        if np.isscalar(s):
+            s = (s, s)
+        self._ck(self._lib.fdc_scale(self._h, float(s[0]), float(s[1])))
+
+    def applyTransform(self, m):
+        arr = (ctypes.c_float * 16)(*[float(x) for x in np.asarray(m, dtype=np.float32).reshape(16)])
+        self._ck(self._lib.fdc_apply_transform(self._h, arr))
+
+    def saveTransform(self):
+        self._ck(self._lib.fdc_save_transform(self._h))
+
+    def restoreTransform(self):
+        self._ck(self._lib.fdc_restore_transform(self._h))
+
+    def transformMirrorsY(self) -> bool:
+        return bool(self._lib.fdc_transform_mirrors_y(self._h))
+
+    def getTransform(self) -> np.ndarray:
+        out = (ctypes.c_float * 16)()
+        self._ck(self._lib.fdc_get_transform(self._h, out))
+        return np.array(out, dtype=np.float32)
+
+    # -- display list + introspection
+    def submitCalls(self, calls: np.ndarray):
+        calls = np.ascontiguousarray(calls)
+        assert calls.dtype.itemsize == 128
+        self._ck(self._lib.fdc_submit_calls(self._h, calls.ctypes.data, len(calls)))
+
+    def frameStats(self) -> FdcFrameStats:
+        st = FdcFrameStats()
+        self._ck(self._lib.fdc_get_frame_stats(self._h, ctypes.byref(st)))
+        return st
+
+    def debugBins(self, segment: int = 0):
+        """(tile_offsets[tiles+1], entries) -- entries are backend-call ordinals in paint order."""
+        n_off, n_ent = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        self._ck(self._lib.fdc_debug_bins(self._h, segment, None, 0, None, 0, ctypes.byref(n_off), ctypes.byref(n_ent)))
+        off = np.zeros(n_off.value, dtype=np.uint32)
+        ent = np.zeros(max(n_ent.value, 1), dtype=np.uint32)
+        self._ck(self._lib.fdc_debug_bins(self._h, segment, off.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                          off.size, ent.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ent.size,
+                                          ctypes.byref(n_off), ctypes.byref(n_ent)))
+        return off, ent[: n_ent.value]
+
+    def bandRows(self) -> Tuple[int, int]:
+        y0, y1 = ctypes.c_int(0), ctypes.c_int(0)
+        self._ck(self._lib.fdc_band_rows(self._h, ctypes.byref(y0), ctypes.byref(y1)))
+        return y0.value, y1.value
+
+    def bindFramebuffer(self, device_ptr: Optional[int]):
+        self._ck(self._lib.fdc_bind_framebuffer(self._h, ctypes.c_void_p(device_ptr or 0)))
+
+    def framebufferPtr(self) -> int:
+        return int(self._lib.fdc_framebuffer_ptr(self._h) or 0)
+
+    def stream(self) -> int:
+        return int(self._lib.fdc_stream(self._h) or 0)
+
+    def setPeerFramebuffers(self, ptrs: Sequence[int]):
+        arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])
+        self._ck(self._lib.fdc_set_peer_framebuffers(self._h, arr, len(ptrs)))
+
+
+def render_trace(trace: Trace, ctx: Optional[CudaContext] = None, device: int = 0) -> np.ndarray:
+    """Render a recorded frame through the C ABI: putImage for its images, one fdc_submit_calls, readPixels."""
+    own = ctx is None
+    ctx = ctx or CudaContext(atlasSize=trace.atlas_size, device=device)
+    try:
+        for _idx, key, img in trace.images:
+            ctx.putImage(key, img)
+        ctx.beginFrame((trace.width, trace.height), clearMain=trace.clear is not None,
+                       clearMainColor=trace.clear or (1.0, 1.0, 1.0, 1.0))
+        ctx.submitCalls(trace.calls)
+        ctx.endFrame()
+        return ctx.readPixels()
+    finally:
+        if own:
+            ctx.close()

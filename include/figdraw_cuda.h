@@ -150,6 +150,9 @@ int fdc_end_frame(fdc_ctx* ctx);
 int fdc_read_pixels(fdc_ctx* ctx, int x, int y, int w, int h, uint8_t* out_rgba);
 /* Blocks until all submitted frames are complete. */
 int fdc_sync(fdc_ctx* ctx);
+/* Re-launches the kernels of the last completed frame on the data already resident in device memory (no
+ * host->device copy).  Used to time the device path alone and by CUDA-graph style frame loops. */
+int fdc_replay_frame(fdc_ctx* ctx);
 
 /* --- transforms: glcontext.nim:1991-2017 --- */
 int fdc_translate(fdc_ctx* ctx, float x, float y);

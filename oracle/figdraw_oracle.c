@@ -421,6 +421,7 @@ typedef struct quad {
   int has_rm;
   rect_mask_t rm;
   int call_index;
+  int is_rounded_rect;
 } oquad_t;
 
 typedef struct shared {
@@ -431,8 +432,12 @@ typedef struct shared {
   uint8_t* backdrop;         /* RGBA8 */
   uint8_t* temp;
   int64_t frag_counts[N_MODES][8]; /* reduced at the end */
-  /* reference binning */
-  int collect_quads;
+  /* reference binning (orc_collect_quads): quads are recorded instead of rasterised */
+  int collect;
+  int32_t* rec;      /* 8 ints per record: segment, call_index, x0, y0, x1, y1, is_mask, level */
+  int64_t rec_cap, rec_n;
+  int band_y0, band_y1;
+  int segment;
 } shared_t;
 
 typedef struct tctx {
@@ -449,6 +454,12 @@ typedef struct tctx {
   int n_rm;
   int64_t frag_counts[N_MODES];
   int error;
+  /* reference binning: clip rect of every texture-mask level (x0,y0,x1,y1), number of mask quads drawn into it,
+   * and the quads themselves so they can be re-emitted after a backdrop blur */
+  int clip[MAX_MASKS][4];
+  int level_quads[MAX_MASKS];
+  int level_ok[MAX_MASKS];
+  struct { int call_index; int box[4]; } level_rec[MAX_MASKS][8];
 } tctx;
 
 /* vmath: m[col*4+row]; a*b with each entry summed left to right. */
@@ -768,6 +779,64 @@ static void raster_tri(tctx* t, const oquad_t* q, int ia, int ib, int ic, int ma
 #undef GRADY
 }
 
+
+/* ------------------------------------------------------------------------------------------------ reference binning
+ * The binning RULE of the product (DESIGN.md "Binning rule"), restated the plainest way: a quad's bin box is the
+ * bbox of its four ceil'd corners, intersected with the frame, the rank's row band and the clip box of the
+ * texture-mask level it lives under (content) or of the parent level (mask quads).  A level's clip box is the bin
+ * box of its single mask quad; a level with several mask quads does not clip; a level whose mask quad was dropped
+ * clips everything.  Segments end at each backdrop blur; open mask levels are re-emitted at the start of the next. */
+static int sat_i(float v) { v = fminf(fmaxf(v, -30000.0f), 30000.0f); return (int)v; }
+static void emit_record(tctx* t, int call_index, const int box[4], int is_mask, int level) {
+  shared_t* sh = t->sh;
+  if (sh->rec_n < sh->rec_cap) {
+    int32_t* r = sh->rec + sh->rec_n * 8;
+    r[0] = sh->segment; r[1] = call_index; r[2] = box[0]; r[3] = box[1]; r[4] = box[2]; r[5] = box[3]; r[6] = is_mask; r[7] = level;
+  }
+  sh->rec_n++;
+}
+static void collect_quad(tctx* t, const oquad_t* q) {
+  shared_t* sh = t->sh;
+  int box[4];
+  box[0] = sat_i(fminf(fminf(q->pos[0].x, q->pos[1].x), fminf(q->pos[2].x, q->pos[3].x)));
+  box[2] = sat_i(fmaxf(fmaxf(q->pos[0].x, q->pos[1].x), fmaxf(q->pos[2].x, q->pos[3].x)));
+  box[1] = sat_i(fminf(fminf(q->pos[0].y, q->pos[1].y), fminf(q->pos[2].y, q->pos[3].y)));
+  box[3] = sat_i(fmaxf(fmaxf(q->pos[0].y, q->pos[1].y), fmaxf(q->pos[2].y, q->pos[3].y)));
+  const int L = t->mask_write;
+  const int* clip = t->mask_begun ? t->clip[L - 1] : t->clip[L];
+  if (box[0] < clip[0]) box[0] = clip[0];
+  if (box[1] < clip[1]) box[1] = clip[1];
+  if (box[2] > clip[2]) box[2] = clip[2];
+  if (box[3] > clip[3]) box[3] = clip[3];
+  if (box[0] < 0) box[0] = 0;
+  if (box[2] > sh->W) box[2] = sh->W;
+  if (box[1] < sh->band_y0) box[1] = sh->band_y0;
+  if (box[3] > sh->band_y1) box[3] = sh->band_y1;
+  int empty = box[0] >= box[2] || box[1] >= box[3];
+  if (t->mask_begun) {
+    int k = t->level_quads[L]++;
+    int is_rect = q->is_rounded_rect;
+    if (k == 0 && is_rect) {
+      t->level_ok[L] = 1;
+      if (empty) { t->clip[L][0] = t->clip[L][1] = t->clip[L][2] = t->clip[L][3] = 0; }
+      else memcpy(t->clip[L], box, sizeof(box));
+    } else {
+      t->level_ok[L] = 0;
+      memcpy(t->clip[L], t->clip[L - 1], sizeof(box));
+    }
+    if (k < 8) { t->level_rec[L][k].call_index = q->call_index; memcpy(t->level_rec[L][k].box, box, sizeof(box)); }
+  }
+  if (!empty) emit_record(t, q->call_index, box, t->mask_begun, L);
+}
+static void collect_begin_segment(tctx* t) {
+  t->sh->segment++;
+  for (int L = 1; L <= t->mask_write; L++)
+    for (int k = 0; k < t->level_quads[L] && k < 8; k++) {
+      const int* b = t->level_rec[L][k].box;
+      if (!(b[0] >= b[2] || b[1] >= b[3])) emit_record(t, t->level_rec[L][k].call_index, b, 1, L);
+    }
+}
+
 static void draw_quad(tctx* t, oquad_t* q) {
   int mask_read;
   if (t->mask_begun) {
@@ -780,6 +849,7 @@ static void draw_quad(tctx* t, oquad_t* q) {
       if (t->rm_stack[i].fast) { q->has_rm = 1; q->rm = t->rm_stack[i]; break; }
   }
   q->subpixel = t->subpixel_enabled ? fmaxf(0.0f, fminf(t->subpixel_shift, 0.999f)) : 0.0f;
+  if (t->sh->collect) { collect_quad(t, q); return; }
   raster_tri(t, q, 3, 0, 1, mask_read); /* indices glcontext.nim:418-429 */
   raster_tri(t, q, 2, 3, 1, mask_read);
 }
@@ -869,6 +939,7 @@ static void op_rounded_rect(tctx* t, const float* rect, const float* rx, const f
   oquad_t q;
   memset(&q, 0, sizeof(q));
   q.call_index = call_index;
+  q.is_rounded_rect = 1;
   int fillMode = 0;
   uint32_t cols[4], mid = 0, stop = 0;
   float fMid = 0.5f;
@@ -936,8 +1007,12 @@ static void begin_mask(tctx* t, const float* rect, const float* rx, const float*
   t->mask_begun = 1;
   t->mask_write++;
   if (t->mask_write >= MAX_MASKS) { t->error = 4; t->mask_write = MAX_MASKS - 1; return; }
+  t->level_quads[t->mask_write] = 0;
+  t->level_ok[t->mask_write] = 0;
+  /* until a mask quad is drawn the level is all zero: it clips everything */
+  t->clip[t->mask_write][0] = t->clip[t->mask_write][1] = t->clip[t->mask_write][2] = t->clip[t->mask_write][3] = 0;
   /* glClear(0) of the whole mask texture, glcontext.nim:1901-1902 (own rows) */
-  memset(sh->masks[t->mask_write] + (size_t)t->y0 * sh->W, 0, (size_t)(t->y1 - t->y0) * sh->W);
+  if (!sh->collect) memset(sh->masks[t->mask_write] + (size_t)t->y0 * sh->W, 0, (size_t)(t->y1 - t->y0) * sh->W);
   uint32_t red[4] = {0xFF0000FFu, 0, 0, 0};
   op_rounded_rect(t, rect, rx, ry, M_CLIP_AA, 4.0f, 0.0f, 0.0f, 0.0f, FILL_COLOR, 0, red, 0.5f, call_index);
 }
@@ -1015,6 +1090,12 @@ static void exec_call(tctx* t, const call_t* c, int idx) {
       break;
     case OP_BACKDROP_BLUR: {
       if (f[12] <= 0.0f || f[2] <= 0.0f || f[3] <= 0.0f) break;
+      if (sh->collect) {
+        collect_begin_segment(t);
+        uint32_t whitec[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        op_rounded_rect(t, f, f + 4, f + 8, M_BACKDROP, f[12], 0.0f, 0.0f, 0.0f, FILL_COLORS4, 0, whitec, 0.5f, idx);
+        break;
+      }
       /* glCopyTexSubImage2D(full frame) then H and V passes over the whole frame */
       barrier();
       memcpy(sh->backdrop + (size_t)t->y0 * sh->W * 4, sh->fb + (size_t)t->y0 * sh->W * 4, (size_t)(t->y1 - t->y0) * sh->W * 4);
@@ -1187,4 +1268,32 @@ int orc_max_threads(void) {
 #else
   return 1;
 #endif
+}
+
+/* Reference bin boxes.  Writes up to `cap` records of 8 int32 (segment, call_index, x0, y0, x1, y1, is_mask, level)
+ * in emission order and returns how many the frame has.  Single threaded. */
+int64_t orc_collect_quads(oracle* o, int W, int H, int band_y0, int band_y1, const call_t* calls, int64_t n_calls,
+                          int32_t* out, int64_t cap) {
+  int needs_rect = 0;
+  for (int64_t i = 0; i < n_calls; i++)
+    if (calls[i].op == OP_FILLED_QUAD || calls[i].op == OP_RECT) needs_rect = 1;
+  float dummy[4];
+  if (needs_rect && !orc_get_image_rect(o, RECT_KEY, dummy)) {
+    uint8_t white[64];
+    memset(white, 255, 64);
+    orc_put_image(o, RECT_KEY, 4, 4, white, NULL);
+  }
+  shared_t sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.o = o; sh.W = W; sh.H = H;
+  sh.collect = 1; sh.rec = out; sh.rec_cap = cap; sh.band_y0 = band_y0; sh.band_y1 = band_y1;
+  tctx* t = (tctx*)calloc(1, sizeof(tctx));
+  t->sh = &sh;
+  t->y0 = 0; t->y1 = H;
+  mat_identity(t->mat);
+  t->aa = 1.2f;
+  t->clip[0][0] = -40000; t->clip[0][1] = -40000; t->clip[0][2] = 40000; t->clip[0][3] = 40000;
+  for (int64_t i = 0; i < n_calls; i++) exec_call(t, &calls[i], (int)i);
+  free(t);
+  return sh.rec_n;
 }

@@ -42,6 +42,9 @@ def _lib() -> ctypes.CDLL:
         lib.orc_render.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.POINTER(c.c_float), c.c_void_p,
                                    c.c_int64, c.c_void_p, c.c_void_p, c.c_int]
         lib.orc_max_threads.restype = c.c_int
+        lib.orc_collect_quads.restype = c.c_int64
+        lib.orc_collect_quads.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int64,
+                                          c.c_void_p, c.c_int64]
         _LIB = lib
     return _LIB
 
@@ -101,6 +104,44 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"oracle: render failed with status {rc}")
         return (fb, counts) if want_counts else fb
+
+
+def reference_bins(trace, tile_w: int = 16, tile_h: int = 16, band: Optional[Tuple[int, int]] = None,
+                   oracle: Optional["Oracle"] = None):
+    """Reference bin lists per segment: list of (tile_offsets[tiles+1], entries) with entries = backend-call
+    ordinals in paint order -- the same form `fdc_debug_bins` returns."""
+    o = oracle or Oracle(trace.atlas_size)
+    if oracle is None:
+        for _idx, key, img in trace.images:
+            o.put_image(key, img)
+    W, H = trace.width, trace.height
+    y0, y1 = band if band is not None else (0, H)
+    calls = np.ascontiguousarray(trace.calls)
+    n = _lib().orc_collect_quads(o._h, W, H, y0, y1, calls.ctypes.data, len(calls), None, 0)
+    rec = np.zeros((max(n, 1), 8), dtype=np.int32)
+    _lib().orc_collect_quads(o._h, W, H, y0, y1, calls.ctypes.data, len(calls), rec.ctypes.data, n)
+    rec = rec[:n]
+    tx_n, ty_n = (W + tile_w - 1) // tile_w, (H + tile_h - 1) // tile_h
+    out = []
+    n_seg = int(rec[:, 0].max()) + 1 if n else 1
+    for s in range(n_seg):
+        r = rec[rec[:, 0] == s]
+        tx0, ty0 = r[:, 2] // tile_w, r[:, 3] // tile_h
+        tx1, ty1 = (r[:, 4] - 1) // tile_w, (r[:, 5] - 1) // tile_h
+        nx, ny = tx1 - tx0 + 1, ty1 - ty0 + 1
+        cnt = (nx * ny).astype(np.int64)
+        total = int(cnt.sum())
+        prim = np.repeat(np.arange(len(r)), cnt)
+        start = np.repeat(np.cumsum(cnt) - cnt, cnt)
+        local = np.arange(total) - start
+        nxr = np.repeat(nx, cnt)
+        tiles = (np.repeat(ty0, cnt) + local // nxr) * tx_n + np.repeat(tx0, cnt) + local % nxr
+        order = np.argsort(tiles, kind="stable")  # stable: emission order inside each tile
+        counts = np.bincount(tiles, minlength=tx_n * ty_n)
+        offsets = np.zeros(tx_n * ty_n + 1, dtype=np.uint32)
+        offsets[1:] = np.cumsum(counts)
+        out.append((offsets, r[prim[order], 1].astype(np.uint32)))
+    return out
 
 
 def render_trace(trace, n_threads: int = 0, want_counts: bool = False, oracle: Optional[Oracle] = None):

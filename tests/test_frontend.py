@@ -1,0 +1,111 @@
+"""Host logic: the front-end emits the reference's backend-call sequence (cf. tests/ttransform.nim RecordingBackend)."""
+import numpy as np
+import pytest
+
+from figdraw_b200 import scenes
+from figdraw_b200.abi import Op, SdfMode
+from figdraw_b200.figbackend import BackendContext, TraceBackend, toBackendFill
+from figdraw_b200.fignodes import (Fig, FigFlags, FigKind, FillGradientAxis, RenderList, RenderShadow, RenderStroke,
+                                   Renders, ShadowStyle, linear, rect, rgba)
+from figdraw_b200.figrender import renderFrame, renderRoot, setFigUiScale
+
+
+def ops(trace):
+    return [Op(int(o)) for o in trace.calls["op"]]
+
+
+def test_rgb_boxes_call_sequence():
+    tr = scenes.golden_trace("rgb_boxes_sdf")
+    draws = tr.calls[tr.calls["op"] == Op.ROUNDED_RECT]
+    modes = [SdfMode(int(u[0])) for u in draws["u"]]
+    # root fill; red fill + stroke; drop shadow + gradient fill; blue fill + two inset shadows
+    assert modes == [SdfMode.sdfModeClipAA, SdfMode.sdfModeClipAA, SdfMode.sdfModeAnnularAA, SdfMode.sdfModeDropShadow,
+                     SdfMode.sdfModeClipAA, SdfMode.sdfModeClipAA, SdfMode.sdfModeInsetShadow,
+                     SdfMode.sdfModeInsetShadow]
+    sh = draws[3]
+    # pad = round(spread) + round(1.5*blur) = 10 + 15 (figrender.nim:668-676); shapeSize = box size
+    assert list(sh["f"][0:4]) == [320 + 10 - 25, 120 + 10 - 25, 220 + 50, 140 + 50]
+    assert list(sh["f"][14:16]) == [220, 140] and sh["f"][12] == 10 and sh["f"][13] == 10
+    ins = draws[6]
+    assert list(ins["f"][14:16]) == [-6, -6]  # inset mode carries the offset in shapeSize (figrender.nim:731-744)
+    assert ops(tr)[:2] == [Op.SAVE_TRANSFORM, Op.SCALE] and ops(tr)[-1] == Op.RESTORE_TRANSFORM
+
+
+def test_clip_node_order_and_layers_not_sorted():
+    tr = scenes.golden_trace("layers_clip")
+    o = ops(tr)
+    i = o.index(Op.BEGIN_MASK)
+    # beginMask; endMask; the node's own fill INSIDE its mask; child; popMask (figrender.nim:1795-1820)
+    assert o[i:i + 5] == [Op.BEGIN_MASK, Op.END_MASK, Op.ROUNDED_RECT, Op.ROUNDED_RECT, Op.POP_MASK]
+    # renderRoot iterates the table in insertion order and never sorts (figrender.nim:1951)
+    r = Renders()
+    for z in (5, -3, 1):
+        lst = RenderList()
+        lst.addRoot(Fig(kind=FigKind.nkRectangle, zlevel=z, screenBox=rect(0, 0, 10 + z, 10), fill=rgba(1, 2, 3, 255)))
+        r.setLayer(z, lst)
+    tb = TraceBackend()
+    tb.beginFrame((64, 64))
+    renderRoot(tb, r)
+    assert [float(c["f"][2]) for c in tb.trace().calls] == [15.0, 7.0, 11.0]
+
+
+def test_rect_mask_and_rotation_emit_reference_calls():
+    tr = scenes.trace_scene(scenes.layers_rect_mask, 800, 375)
+    o = ops(tr)
+    assert Op.BEGIN_RECT_MASK in o and Op.POP_RECT_MASK in o and Op.BEGIN_MASK not in o
+    tr = scenes.golden_trace("line_rect")
+    o = ops(tr)
+    i = o.index(Op.ROTATE)
+    # save; translate(pivot); rotate(atan2); translate(-pivot); box; restore  (figrender.nim:982-990)
+    assert o[i - 2:i + 4] == [Op.SAVE_TRANSFORM, Op.TRANSLATE, Op.ROTATE, Op.TRANSLATE, Op.ROUNDED_RECT,
+                             Op.RESTORE_TRANSFORM]
+    ang = float(tr.calls[i]["f"][0])
+    assert abs(ang - np.arctan2(350.0, 620.0)) < 1e-6
+
+
+def test_disabled_and_transparent_nodes_are_skipped():
+    lst = RenderList()
+    root = lst.addRoot(Fig(kind=FigKind.nkRectangle, screenBox=rect(0, 0, 8, 8), fill=rgba(0, 0, 0, 0)))
+    lst.addChild(root, Fig(kind=FigKind.nkRectangle, screenBox=rect(0, 0, 8, 8), fill=rgba(9, 9, 9, 255),
+                           flags=FigFlags.NfDisableRender))
+    lst.addChild(root, Fig(kind=FigKind.nkRectangle, screenBox=rect(0, 0, 8, 8), fill=rgba(9, 9, 9, 255),
+                           shadows=[RenderShadow(style=ShadowStyle.DropShadow, blur=0, spread=0, fill=rgba(0, 0, 0, 255)),
+                                    RenderShadow(style=ShadowStyle.DropShadow, blur=4, spread=0, fill=rgba(0, 0, 0, 0))]))
+    r = Renders()
+    r.setLayer(0, lst)
+    tb = TraceBackend()
+    tb.beginFrame((8, 8))
+    renderRoot(tb, r)
+    assert ops(tb.trace()) == [Op.ROUNDED_RECT]  # only the third node's fill
+
+
+def test_ui_scale_multiplies_every_coordinate():
+    def build(w, h):
+        lst = RenderList()
+        lst.addRoot(Fig(kind=FigKind.nkRectangle, screenBox=rect(10, 20, 30, 40), corners=(4, 4, 4, 4),
+                        fill=rgba(1, 2, 3, 255), stroke=RenderStroke(weight=2.0, fill=rgba(0, 0, 0, 255))))
+        r = Renders()
+        r.setLayer(0, lst)
+        return r
+
+    tr = scenes.trace_scene(build, 100, 100, uiScale=2.0)
+    setFigUiScale(1.0)
+    assert (tr.width, tr.height) == (200, 200)
+    d = tr.calls[tr.calls["op"] == Op.ROUNDED_RECT]
+    assert list(d[0]["f"][0:8]) == [20, 40, 60, 80, 8, 8, 8, 8]
+    assert d[1]["f"][12] == 4.0  # stroke weight scaled
+
+
+def test_backend_fill_conversion():
+    f = toBackendFill(linear(rgba(1, 2, 3, 4), rgba(5, 6, 7, 8), rgba(9, 9, 9, 9), axis=FillGradientAxis.fgaY, midPos=0))
+    assert f.kind == 3 and f.axis == 1 and abs(f.midPos - 0.01) < 1e-7  # clamp(u8/255, .01, .99), figbackend.nim:125
+    with pytest.raises(ValueError):
+        BackendContext().drawRect((0, 0, 1, 1), 0)  # "Backend drawRect unavailable", figbackend.nim:503-505
+
+
+def test_figidx_capacity():
+    lst = RenderList()
+    root = lst.addRoot(Fig(kind=FigKind.nkFrame))
+    with pytest.raises(OverflowError):
+        for _ in range(40000):
+            lst.addChild(root, Fig(kind=FigKind.nkFrame))

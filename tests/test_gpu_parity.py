@@ -1,0 +1,196 @@
+"""Parity of the CUDA backend (through the C ABI) against the CPU oracle and the reference's golden images.
+
+Tolerance: per-channel RGBA8 within +-2 LSB (BASELINE.json north_star); bin lists and draw order bit-exact.
+The shading arithmetic is float32 on both sides but the kernel uses FMA contraction and MUFU approximations,
+so a pixel whose exact value sits on a rounding boundary may land one LSB away; MAX_DIFF states the bar and
+MAX_FRACTION bounds how many pixels may differ at all.
+"""
+import numpy as np
+import pytest
+
+from figdraw_b200 import scenes
+from figdraw_b200 import scenes_synth as ss
+from figdraw_b200.abi import Op
+from figdraw_b200.cuda_context import CudaContext, render_trace
+from figdraw_b200.figbackend import Trace
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+MAX_DIFF = 2  # LSB, north_star tolerance
+MAX_FRACTION = 0.01  # pixels allowed to differ from the oracle at all
+
+
+def diff_stats(a, b):
+    d = np.abs(a.astype(np.int16) - b.astype(np.int16)).max(axis=2)
+    return int(d.max()), float((d > 0).mean())
+
+
+def check(trace, max_diff=MAX_DIFF, max_fraction=MAX_FRACTION):
+    got = render_trace(trace)
+    want = oracle.render_trace(trace)
+    mx, frac = diff_stats(got, want)
+    assert mx <= max_diff, f"max diff {mx} LSB"
+    assert frac <= max_fraction, f"{frac:.4%} of pixels differ"
+    return got, want
+
+
+@pytest.mark.parametrize("name", sorted(scenes.GOLDEN_SCENES))
+def test_golden_scenes(name):
+    tr = scenes.golden_trace(name)
+    got, _ = check(tr)
+    mx, _ = diff_stats(got, scenes.load_golden(name))
+    assert mx <= MAX_DIFF  # against the reference's own PNG
+
+
+def test_rect_mask_scenes():
+    check(scenes.trace_scene(scenes.layers_rect_mask, 800, 375))
+    check(scenes.trace_scene(scenes.mixed_rect_mask_batch, 480, 180))
+
+
+def test_cfg2_renderlist_100():
+    check(ss.config_trace(2))
+
+
+def test_cfg2_without_blur_is_one_segment():
+    tr = ss.config_trace(2, with_blur=False)
+    ctx = CudaContext(atlasSize=tr.atlas_size)
+    render_trace(tr, ctx)
+    assert ctx.frameStats().n_segments == 1
+    ctx.close()
+
+
+def test_cfg3_text_and_msdf():
+    check(ss.config_trace(3, 1920, 1080, n_glyphs=6000, msdf_glyphs=500))
+
+
+@pytest.mark.parametrize("rect_mask", [False, True])
+def test_cfg4_clip_table(rect_mask):
+    check(ss.config_trace(4, 1920, 1080, rows=60, cols=8, rect_mask=rect_mask))
+
+
+def test_cfg5_small():
+    check(ss.config_trace(5, 1280, 720, n_rects=12000, n_glyphs=2400))
+
+
+def test_cfg5_scaled_x2():
+    check(ss.config_trace(5, 1920, 1080, n_rects=6000, n_glyphs=1200, scale=2.0))
+
+
+@pytest.mark.parametrize("builder", [
+    lambda: scenes.golden_trace("layers_clip"),
+    lambda: ss.config_trace(2),
+    lambda: ss.config_trace(4, 1280, 720, rows=24, cols=6),
+    lambda: ss.config_trace(5, 1280, 720, n_rects=6000, n_glyphs=1000),
+])
+def test_bin_lists_bit_exact(builder):
+    tr = builder()
+    ctx = CudaContext(atlasSize=tr.atlas_size)
+    render_trace(tr, ctx)
+    ref = oracle.reference_bins(tr)
+    st = ctx.frameStats()
+    assert st.n_segments == len(ref)
+    assert (st.tile_w, st.tile_h) == (16, 16)
+    for seg, (off_ref, ent_ref) in enumerate(ref):
+        off, ent = ctx.debugBins(seg)
+        assert np.array_equal(off, off_ref), f"segment {seg}: tile offsets differ"
+        assert np.array_equal(ent, ent_ref), f"segment {seg}: draw order differs"
+    ctx.close()
+
+
+def test_replay_and_rerender_are_idempotent():
+    tr = ss.config_trace(5, 1280, 720, n_rects=4000, n_glyphs=800)
+    ctx = CudaContext(atlasSize=tr.atlas_size)
+    a = render_trace(tr, ctx).copy()
+    ctx.replayFrame()
+    b = ctx.readPixels().copy()
+    c = render_trace(tr, ctx)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    ctx.close()
+
+
+def test_split_frame_equals_single_frame():
+    """Per-draw UNORM8 quantisation makes the frame splittable at any draw: second half with clearMain=false."""
+    tr = ss.config_trace(5, 1280, 720, n_rects=4000, n_glyphs=0)
+    full = render_trace(tr)
+    calls = tr.calls
+    k = len(calls) // 2
+    while calls[k]["op"] < 32:
+        k += 1
+    ctx = CudaContext(atlasSize=tr.atlas_size)
+    for _i, key, img in tr.images:
+        ctx.putImage(key, img)
+    ctx.beginFrame((tr.width, tr.height), clearMain=True)
+    ctx.submitCalls(calls[:k])
+    ctx.restoreTransform()
+    ctx.endFrame()
+    ctx.beginFrame((tr.width, tr.height), clearMain=False)
+    ctx.saveTransform()
+    ctx.submitCalls(calls[k:])
+    ctx.endFrame()
+    assert np.array_equal(ctx.readPixels(), full)
+    ctx.close()
+
+
+def test_tile_bands_reassemble_the_frame():
+    tr = ss.config_trace(5, 1280, 720, n_rects=4000, n_glyphs=800)
+    full = render_trace(tr)
+    out = np.zeros_like(full)
+    for n in (2, 3):
+        for r in range(n):
+            ctx = CudaContext(atlasSize=tr.atlas_size, rank=r, nRanks=n)
+            img = render_trace(tr, ctx)
+            y0, y1 = ctx.bandRows()
+            out[y0:y1] = img[y0:y1]
+            ctx.close()
+        assert np.array_equal(out, full)
+
+
+def test_empty_and_degenerate_inputs():
+    ctx = CudaContext()
+    ctx.beginFrame((64, 48), clearMain=True, clearMainColor=(0.2, 0.4, 0.6, 1.0))
+    ctx.endFrame()
+    img = ctx.readPixels()
+    assert img.shape == (48, 64, 4) and tuple(img[0, 0]) == (51, 102, 153, 255)
+    from figdraw_b200.figbackend import ZeroRadii, solid
+
+    ctx.beginFrame((64, 48), clearMain=True)
+    ctx.drawRoundedRectSdf((10, 10, 0, 5), solid(0xFF000000), ZeroRadii)      # zero width: dropped
+    ctx.drawRoundedRectSdf((-500, -500, 100, 100), solid(0xFF000000), ZeroRadii)  # off-screen
+    ctx.drawImage(12345, (0, 0), [0xFFFFFFFF] * 4)                              # missing image: warn + skip
+    ctx.endFrame()
+    assert ctx.missing_images == 1
+    assert (ctx.readPixels() == 255).all()
+    ctx.close()
+
+
+def test_state_errors_match_reference_asserts():
+    from figdraw_b200.cuda_context import FigDrawError
+    from figdraw_b200.figbackend import ZeroRadii
+
+    ctx = CudaContext()
+    with pytest.raises(FigDrawError):
+        ctx.endFrame()  # "ctx.beginFrame was not called first."
+    ctx.beginFrame((32, 32), clearMain=True)
+    ctx.beginMask((0, 0, 8, 8), ZeroRadii)
+    with pytest.raises(FigDrawError):
+        ctx.beginMask((0, 0, 8, 8), ZeroRadii)  # "ctx.beginMask has already been called."
+    ctx.endMask()
+    with pytest.raises(FigDrawError):
+        ctx.endFrame()  # "Not all masks have been popped."
+    ctx.close()
+
+
+def test_atlas_packer_matches_reference_placement():
+    """putImage places images exactly where the reference's skyline packer would (glcontext.nim:541-586)."""
+    ctx = CudaContext(atlasSize=256)
+    o = oracle.Oracle(256)
+    rng = np.random.default_rng(7)
+    for k in range(40):
+        w, h = int(rng.integers(2, 60)), int(rng.integers(2, 60))
+        img = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+        r1, g1 = ctx.putImage(1000 + k, img)
+        r2, g2 = o.put_image(1000 + k, img)
+        assert r1 == pytest.approx(r2, abs=0) and g1 == g2
+    assert ctx.atlasSize() == o.atlas_size and ctx.atlasSize() > 256  # it grew
+    ctx.close()

@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the figdraw B200 render path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg5_4k|cfg5_8k|...]
+
+A "step" is ONE FRAME of the hot path (setup + binning + shade [+ blur]) over one synthetic scene.
+  N = 1   : BASELINE.json's target scene -- 100k shadowed rounded rects + 20k glyph quads at 3840x2160 (cfg5).
+  N > 1   : the same scene at 7680x4320 (all sizes x2, configs[4]), framebuffer partitioned into tile-row bands,
+            one rank per GPU, NCCL all-gather of the bands at the end of every frame (strong scaling of one frame).
+`value` is Mpixels/s with the frame's inputs already resident in HBM (kernels only, CUDA events on the context's
+stream, max over ranks); `e2e` is the same metric through the C ABI with HOST buffers: fdc_begin_frame +
+fdc_submit_calls(host records) + fdc_end_frame + fdc_read_pixels(host), copies inside the timed region.
+`--impl reference` times the CPU restatement of the reference's GL path (oracle/) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpixels/s"
+
+# Algorithmic flops per fragment by SdfMode (FMA = 2, sqrt/exp/div/cvt = 1).
+FLOPS = {0: 89, 3: 62, 7: 63, 8: 68, 9: 88, 11: 66, 12: 66, 13: 99, 14: 99, 15: 99, 16: 99, 17: 78, 18: 150, 19: 150, 20: 150}
+FLOPS_GRADIENT_EXTRA = 16
+FLOPS_BLUR_PER_PIXEL_PASS = 140
+N_MODES = 24
+
+
+def workload_trace(name: str):
+    from figdraw_b200 import scenes_synth as ss
+
+    if name == "cfg5_4k":
+        return ss.config_trace(5, 3840, 2160), "cfg5: 100k shadowed rounded rects + 20k glyph quads, 3840x2160, seed 5"
+    if name == "cfg5_8k":
+        return ss.config_trace(5, 7680, 4320, scale=2.0), "cfg5 x2: 100k shadowed rounded rects + 20k glyph quads, 7680x4320, seed 5"
+    if name == "cfg2":
+        return ss.config_trace(2), "cfg2: renderlist_100 shape (300 boxes, shadows, elliptical corners, 1 backdrop blur), 1920x1080"
+    if name == "cfg3":
+        return ss.config_trace(3), "cfg3: 20k atlas glyph quads + MSDF/MTSDF star, 3840x2160"
+    if name == "cfg4":
+        return ss.config_trace(4), "cfg4: clip-mask table 180x12 (sub-clip), 3-stop gradients, 2 backdrop blurs, 3840x2160"
+    if name == "cfg4_rectmask":
+        return ss.config_trace(4, rect_mask=True), "cfg4: clip-mask table 180x12 (rect-mask), 2 backdrop blurs, 3840x2160"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def algorithmic_flops(counts: np.ndarray) -> float:
+    total = 0.0
+    for m, f in FLOPS.items():
+        total += float(counts[m]) * f + float(counts[N_MODES + m]) * (f + FLOPS_GRADIENT_EXTRA)
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def run_reference(args, rank: int):
+    """CPU arm: the oracle port of the reference's GL path, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+
+    name = args.workload or ("cfg5_4k" if args.gpus == 1 else "cfg5_8k")
+    trace, desc = workload_trace(name)
+    cores = orc.max_threads()
+    o = orc.Oracle(trace.atlas_size)
+    for _i, key, img in trace.images:
+        o.put_image(key, img)
+    has_blur = bool((trace.calls["op"] == 13).any())
+    H = trace.height
+    rows = (0, H) if has_blur else (H // 2 - H // 32, H // 2 + H // 32)  # 1/16 of the frame, centred
+    for _ in range(args.warmup):
+        o.render(trace.width, H, trace.calls, clear=trace.clear, n_threads=cores, rows=rows)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.render(trace.width, H, trace.calls, clear=trace.clear, n_threads=cores, rows=rows)
+    dt = (time.perf_counter() - t0) / args.steps
+    px = trace.width * (rows[1] - rows[0])
+    val = px / dt / 1e6
+    sample = f"rows {rows[0]}..{rows[1]} of {H} ({px} px) of the same frame per step"
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": METRIC, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3 * (trace.width * H) / px, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "note": "restated-reference CPU rasteriser (oracle port of the GL path), not llvmpipe; "
+                       "ms_per_step extrapolated from the sample to the whole frame"},
+            "cpu_baseline": {"value": round(val, 3), "unit": METRIC, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(val, 3), "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "frames_per_s": round(val * 1e6 / (trace.width * H), 4)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import __graft_entry__ as ge
+
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    from figdraw_b200.cuda_context import CudaContext
+
+    name = args.workload or ("cfg5_4k" if world == 1 else "cfg5_8k")
+    trace, desc = workload_trace(name)
+    W, H = trace.width, trace.height
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    ctx = CudaContext(atlasSize=trace.atlas_size, device=local_rank, rank=rank, nRanks=world)
+    for _i, key, img in trace.images:
+        ctx.putImage(key, img)
+
+    # Framebuffer owned by torch so NCCL can all-gather the bands in place; rows padded to equal bands.
+    tiles_y = (H + 15) // 16
+    band_rows = ((tiles_y + world - 1) // world) * 16
+    fb = torch.zeros((band_rows * world, W, 4), dtype=torch.uint8, device=dev)
+    ctx.bindFramebuffer(fb.data_ptr())
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    calls_host = torch.from_numpy(trace.calls.view(np.uint8).reshape(-1, 128).copy()).pin_memory()
+    calls_np = calls_host.numpy().view(trace.calls.dtype).reshape(-1)
+    out_host = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+    out_np = out_host.numpy()
+
+    def gather():
+        if world > 1:
+            band = fb[rank * band_rows:(rank + 1) * band_rows]
+            dist.all_gather_into_tensor(fb, band)
+
+    def frame_e2e():
+        ctx.beginFrame((W, H), clearMain=trace.clear is not None, clearMainColor=trace.clear or (1, 1, 1, 1))
+        ctx.submitCalls(calls_np)
+        ctx.endFrame()
+        with torch.cuda.stream(stream):
+            gather()
+        y0, y1 = ctx.bandRows() if world > 1 else (0, H)
+        ctx.readPixels((0, y0, W, y1 - y0), out=out_np[y0:y1])
+
+    # first frame: uploads the recording, allocates everything
+    frame_e2e()
+    st = ctx.frameStats()
+    launches_per_frame = int(st.n_launches)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn_step, steps):
+        """Each step individually bracketed by CUDA events on the context stream; L2 flushed between steps."""
+        evs = []
+        for _ in range(steps):
+            with torch.cuda.stream(stream):
+                flush.fill_(0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn_step()
+                e1.record(stream)
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def step_resident():
+        ctx.replayFrame()
+        gather()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    times = timed_loop(step_resident, args.steps)
+    barrier()
+    stats = ctx.frameStats()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = float(np.sum(times)) / args.steps
+
+    # e2e: host records in, host pixels out, wall clock bracketed by synchronisation (copies are inside)
+    for _ in range(2):
+        frame_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(5, min(args.steps, 20))
+    for _ in range(e2e_steps):
+        frame_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    if world > 1:
+        t = torch.tensor([ms_step, e2e_ms, stats.shade_ms, stats.bin_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms, shade_ms, bin_ms = (float(v) for v in t.tolist())
+    else:
+        shade_ms, bin_ms = float(stats.shade_ms), float(stats.bin_ms)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        mpx = W * H / 1e6
+        value = mpx / (ms_step * 1e-3)
+        # roofline of the dominant kernel (shade): algorithmic flops from the oracle's exact fragment counts
+        cpu_base, roof = None, None
+        sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        peak_fp32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s, non-tensor FP32 at the clock seen under load
+        n_frag = None
+        if not args.no_cpu_baseline:
+            from oracle import oracle as orc
+
+            cores = orc.max_threads()
+            o = orc.Oracle(trace.atlas_size)
+            for _i, key, img in trace.images:
+                o.put_image(key, img)
+            t0 = time.perf_counter()
+            ref_img, counts = o.render(W, H, trace.calls, clear=trace.clear, n_threads=cores, want_counts=True)
+            cpu_s = time.perf_counter() - t0
+            n_frag = int(counts.sum())
+            flops = algorithmic_flops(counts)
+            d = np.abs(out_np.astype(np.int16) - ref_img.astype(np.int16)).max(axis=2) if world == 1 else None
+            cpu_base = {"value": round(mpx / cpu_s, 3), "unit": METRIC, "cores": cores, "kind": "port",
+                        "sample": f"1 full frame of the same scene ({W}x{H}, {n_frag} fragments) in {cpu_s:.2f} s"}
+            bytes_alg = W * H * 4 + trace.n_draws * 128 * 2 + int(stats.n_tile_entries) * 4
+            roof = {"bound": "fp32", "kernel": "shade_kernel", "achieved": round(flops / (shade_ms * 1e-3) / 1e12, 3),
+                    "peak": round(peak_fp32, 2), "unit": "TFLOP/s", "frac": round(flops / (shade_ms * 1e-3) / 1e12 / peak_fp32, 4),
+                    "traffic": None, "algorithmic_flops_per_frame": flops, "fragments_per_frame": n_frag,
+                    "peak_source": f"148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",
+                    "shade_ms": round(shade_ms, 4), "bin_ms": round(bin_ms, 4),
+                    "hbm": {"algorithmic_bytes": bytes_alg, "achieved_gbs": round(bytes_alg / (ms_step * 1e-3) / 1e9, 1),
+                            "peak_gbs": peaks.get("hbm_gbs"), "frac": round(bytes_alg / (ms_step * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), 4),
+                            "peak_source": peak_src}}
+            if d is not None:
+                roof["parity_vs_oracle"] = {"max_abs_diff_lsb": int(d.max()), "pixels_differing": int((d > 0).sum())}
+        h2d = int(calls_np.nbytes)
+        d2h = int(W * H * 4)
+        line = {"metric": METRIC, "value": round(value, 2), "unit": METRIC, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "frame": [W, H], "primitives": trace.n_draws, "l2": "flushed between steps (256 MiB fill)",
+                           "partition": "single GPU" if world == 1 else f"{world} tile-row bands + NCCL all-gather"},
+                "frames_per_s": round(1e3 / ms_step, 2),
+                "e2e": {"value": round(mpx / (e2e_ms * 1e-3), 2), "unit": METRIC, "ms_per_step": round(e2e_ms, 4),
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches_per_frame * args.steps, "launches_per_frame": launches_per_frame,
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

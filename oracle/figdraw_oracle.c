@@ -452,7 +452,7 @@ typedef struct tctx {
   int mask_write, mask_begun;
   rect_mask_t rm_stack[MAX_MASKS];
   int n_rm;
-  int64_t frag_counts[N_MODES];
+  int64_t frag_counts[2 * N_MODES]; /* [mode] solid fill, [N_MODES + mode] gradient fill (3-stop or vertex colours) */
   int error;
   /* reference binning: clip rect of every texture-mask level (x0,y0,x1,y1), number of mask quads drawn into it,
    * and the quads themselves so they can be re-emitted after a backdrop blur */
@@ -774,7 +774,11 @@ static void raster_tri(tctx* t, const oquad_t* q, int ia, int ib, int ic, int ma
       }
     }
   }
-  if (mode < N_MODES) t->frag_counts[mode] += nfrag;
+  {
+    int grad = (packed / 256) != 0 || memcmp(&q->color[0], &q->color[1], sizeof(v4)) != 0 ||
+               memcmp(&q->color[0], &q->color[2], sizeof(v4)) != 0 || memcmp(&q->color[0], &q->color[3], sizeof(v4)) != 0;
+    if (mode < N_MODES) t->frag_counts[mode + (grad ? N_MODES : 0)] += nfrag;
+  }
 #undef GRADX
 #undef GRADY
 }
@@ -1191,11 +1195,23 @@ static void exec_call(tctx* t, const call_t* c, int idx) {
 
 /* Renders one frame.  fb_inout: W*H*4 RGBA8 top-left origin; when clear != 0 it is first filled with clear_rgba
  * (glClear, glcontext.nim:2086-2091), otherwise its content is kept (GL keeps the back buffer).
- * frag_counts: optional int64[N_MODES] = fragments shaded per SdfMode (for algorithmic flop counts).
+ * frag_counts: optional int64[2*N_MODES] = fragments shaded per SdfMode, solid fills then gradient fills
+ * (for algorithmic flop counts).
  * Returns 0 or an fdc_status-like code. */
+int orc_render_rows(oracle* o, int W, int H, int clear, const float* clear_rgba, const call_t* calls, int64_t n_calls,
+                    uint8_t* fb_inout, int64_t* frag_counts, int n_threads, int row0, int row1);
 int orc_render(oracle* o, int W, int H, int clear, const float* clear_rgba, const call_t* calls, int64_t n_calls,
                uint8_t* fb_inout, int64_t* frag_counts, int n_threads) {
+  return orc_render_rows(o, W, H, clear, clear_rgba, calls, n_calls, fb_inout, frag_counts, n_threads, 0, H);
+}
+/* As orc_render but only rows [row0,row1) are produced (a bounded sample of a large frame for CPU timing).
+ * Backdrop blurs read rows outside the sample, so samples are only meaningful for scenes without blur. */
+int orc_render_rows(oracle* o, int W, int H, int clear, const float* clear_rgba, const call_t* calls, int64_t n_calls,
+                    uint8_t* fb_inout, int64_t* frag_counts, int n_threads, int row0, int row1) {
   if (W <= 0 || H <= 0) return 1;
+  if (row0 < 0) row0 = 0;
+  if (row1 > H) row1 = H;
+  if (row1 <= row0) return 1;
   int needs_rect = 0, max_depth = 1, depth = 0, needs_blur = 0;
   for (int64_t i = 0; i < n_calls; i++) {
     uint32_t op = calls[i].op;
@@ -1221,9 +1237,9 @@ int orc_render(oracle* o, int W, int H, int clear, const float* clear_rgba, cons
     for (size_t i = 0; i < (size_t)W * H; i++) memcpy(fb_inout + i * 4, c8, 4);
   }
   if (n_threads < 1) n_threads = 1;
-  if (n_threads > H) n_threads = H;
+  if (n_threads > row1 - row0) n_threads = row1 - row0;
   int err = 0;
-  int64_t totals[N_MODES];
+  int64_t totals[2 * N_MODES];
   memset(totals, 0, sizeof(totals));
 #ifdef _OPENMP
 #pragma omp parallel num_threads(n_threads)
@@ -1237,10 +1253,10 @@ int orc_render(oracle* o, int W, int H, int clear, const float* clear_rgba, cons
     tctx* t = (tctx*)calloc(1, sizeof(tctx));
     t->sh = &sh;
     /* bands of whole 16-row groups keep the split independent of nothing but nt */
-    int rows = (H + nt - 1) / nt;
-    t->y0 = tid * rows; t->y1 = t->y0 + rows;
-    if (t->y0 > H) t->y0 = H;
-    if (t->y1 > H) t->y1 = H;
+    int rows = (row1 - row0 + nt - 1) / nt;
+    t->y0 = row0 + tid * rows; t->y1 = t->y0 + rows;
+    if (t->y0 > row1) t->y0 = row1;
+    if (t->y1 > row1) t->y1 = row1;
     mat_identity(t->mat);
     t->aa = 1.2f; /* DefaultSdfAaFactor, figbackend.nim:34 */
     for (int64_t i = 0; i < n_calls; i++) exec_call(t, &calls[i], (int)i);
@@ -1250,7 +1266,7 @@ int orc_render(oracle* o, int W, int H, int clear, const float* clear_rgba, cons
 #endif
     {
       if (t->error && !err) err = t->error;
-      for (int m = 0; m < N_MODES; m++) totals[m] += t->frag_counts[m];
+      for (int m = 0; m < 2 * N_MODES; m++) totals[m] += t->frag_counts[m];
     }
     free(t);
   }

@@ -41,6 +41,7 @@ def _lib() -> ctypes.CDLL:
         lib.orc_put_image.argtypes = [c.c_void_p, c.c_uint64, c.c_int, c.c_int, c.c_void_p, c.POINTER(c.c_float)]
         lib.orc_render.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.POINTER(c.c_float), c.c_void_p,
                                    c.c_int64, c.c_void_p, c.c_void_p, c.c_int]
+        lib.orc_render_rows.argtypes = lib.orc_render.argtypes + [c.c_int, c.c_int]
         lib.orc_max_threads.restype = c.c_int
         lib.orc_collect_quads.restype = c.c_int64
         lib.orc_collect_quads.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int64,
@@ -87,8 +88,10 @@ class Oracle:
         return tuple(out) if ok else None
 
     def render(self, width: int, height: int, calls: np.ndarray, clear=(1.0, 1.0, 1.0, 1.0),
-               fb: Optional[np.ndarray] = None, n_threads: int = 0, want_counts: bool = False):
-        """Returns RGBA8 [H, W, 4] (top-left origin) and optionally per-SdfMode fragment counts."""
+               fb: Optional[np.ndarray] = None, n_threads: int = 0, want_counts: bool = False,
+               rows: Optional[Tuple[int, int]] = None):
+        """Returns RGBA8 [H, W, 4] (top-left origin) and optionally per-SdfMode fragment counts.
+        `rows=(r0, r1)` renders only that row range (bounded CPU-timing sample)."""
         calls = np.ascontiguousarray(calls)
         assert calls.dtype.itemsize == 128
         if fb is None:
@@ -97,10 +100,11 @@ class Oracle:
             fb = np.ascontiguousarray(fb, dtype=np.uint8).copy()
             assert fb.shape == (height, width, 4)
         c4 = (ctypes.c_float * 4)(*(clear if clear is not None else (0, 0, 0, 0)))
-        counts = np.zeros(N_MODES, dtype=np.int64)
+        counts = np.zeros(2 * N_MODES, dtype=np.int64)  # [mode] solid, [N_MODES + mode] gradient fills
         nt = n_threads if n_threads > 0 else max_threads()
-        rc = _lib().orc_render(self._h, width, height, 1 if clear is not None else 0, c4, calls.ctypes.data,
-                               len(calls), fb.ctypes.data, counts.ctypes.data, nt)
+        r0, r1 = rows if rows is not None else (0, height)
+        rc = _lib().orc_render_rows(self._h, width, height, 1 if clear is not None else 0, c4, calls.ctypes.data,
+                                    len(calls), fb.ctypes.data, counts.ctypes.data, nt, int(r0), int(r1))
         if rc != 0:
             raise RuntimeError(f"oracle: render failed with status {rc}")
         return (fb, counts) if want_counts else fb
@@ -144,10 +148,12 @@ def reference_bins(trace, tile_w: int = 16, tile_h: int = 16, band: Optional[Tup
     return out
 
 
-def render_trace(trace, n_threads: int = 0, want_counts: bool = False, oracle: Optional[Oracle] = None):
+def render_trace(trace, n_threads: int = 0, want_counts: bool = False, oracle: Optional[Oracle] = None,
+                 rows: Optional[Tuple[int, int]] = None):
     """Render a figdraw_b200.figbackend.Trace: uploads its images (in order), then replays its calls."""
     o = oracle or Oracle(trace.atlas_size)
-    for _idx, key, img in trace.images:
-        o.put_image(key, img)
+    if oracle is None:
+        for _idx, key, img in trace.images:
+            o.put_image(key, img)
     return o.render(trace.width, trace.height, trace.calls, clear=trace.clear, n_threads=n_threads,
-                    want_counts=want_counts)
+                    want_counts=want_counts, rows=rows)

@@ -40,7 +40,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-c", os.path.join(CSRC, src), "-o", obj]
+        extra = os.environ.get("FDC_NVCC_EXTRA", "").split()
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-ccbin", "/usr/bin/g++", "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False

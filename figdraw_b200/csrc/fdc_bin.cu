@@ -364,24 +364,90 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
           }
         }
       }
-      // occluder: opaque ClipAA fill whose inner rect has coverage exactly 1 (see DESIGN.md "work reduction")
-      if (mode == FDC_SDF_CLIP_AA && aligned && !(flags & (PF_MASK_WRITE | PF_ELLIPTICAL | PF_RECTMASK)) &&
-          (flags & PF_DEPTH_MASK) == 0 && X1 > X0 && Y1 > Y0 && rs.aa > 0.0f) {
-        uint32_t amin = min(min(cols[0] >> 24, cols[1] >> 24), min(cols[2] >> 24, cols[3] >> 24));
-        if (fill_mode != 0) amin = min(amin, min(p.c_mid >> 24, p.c_stop >> 24));
-        if (amin == 255u) {
-          float rmax = fmaxf(fmaxf(p.r0, p.r1), fmaxf(p.r2, p.r3));
-          float m = fmaxf(rmax, 0.5f / rs.aa) + 0.01f;
-          float gx = 2.0f * p.qhx * p.su, gy = 2.0f * p.qhy * p.sv;  // d p / d pixel
-          float lox = X0 - 0.5f + (p.qhx - p.p2 + m) / gx, hix = X0 - 0.5f + (p.qhx + p.p2 - m) / gx;
-          float loy = Y0 - 0.5f + (p.qhy - p.p3 + m) / gy, hiy = Y0 - 0.5f + (p.qhy + p.p3 - m) / gy;
-          int ix0 = max((int)ceilf(lox + 1e-3f), cx0), ix1 = min((int)floorf(hix - 1e-3f) + 1, cx1);
-          int iy0 = max((int)ceilf(loy + 1e-3f), cy0), iy1 = min((int)floorf(hiy - 1e-3f) + 1, cy1);
-          if (ix0 < ix1 && iy0 < iy1) {
-            flags |= PF_OCCLUDER;
-            p.ix0 = (int16_t)ix0; p.iy0 = (int16_t)iy0; p.ix1 = (int16_t)ix1; p.iy1 = (int16_t)iy1;
+      // SDF modes: direct pixel -> SDF-space mapping.  p.x = (s - .5) * 2 * qhx with s = x*su + ou.
+      const bool sdf_rect = d.op == FDC_OP_ROUNDED_RECT;
+      if (sdf_rect && aligned) {
+        p.u0 = 2.0f * p.qhx * p.su; p.du = (2.0f * p.ou - 1.0f) * p.qhx;
+        p.v0 = -2.0f * p.qhy * p.sv; p.dv = -(2.0f * p.ov - 1.0f) * p.qhy;
+      }
+      const bool circ = !(flags & PF_ELLIPTICAL);
+      const bool content = !(flags & PF_MASK_WRITE);
+      if (sdf_rect && aligned && circ && content && !(flags & PF_RECTMASK) &&
+          (mode == FDC_SDF_CLIP_AA || mode == FDC_SDF_ANNULAR_AA || mode == FDC_SDF_DROP_SHADOW)) {
+        // gradient colours as float coefficients of the pixel index (PrimExt)
+        bool fast = true;
+        if (fill_mode != 0) {
+          PrimExt e;
+          const float hs = 0.5f;
+          if (fill_mode == 1) { e.ta = p.su; e.tb = 0.0f; e.tc = p.ou; }
+          else if (fill_mode == 2) { e.ta = 0.0f; e.tb = p.sv; e.tc = p.ov; }
+          else if (fill_mode == 3) { e.ta = hs * p.su; e.tb = hs * p.sv; e.tc = hs * (p.ou + p.ov); }
+          else { e.ta = hs * p.su; e.tb = -hs * p.sv; e.tc = hs * (p.ou + 1.0f - p.ov); }
+          const float mid = p.spread;  // already clamped to [0.01, 0.99]
+          e.mid = mid;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float c0 = (float)((cols[0] >> (8 * k)) & 255u), c1 = (float)((p.c_mid >> (8 * k)) & 255u),
+                        c2 = (float)((p.c_stop >> (8 * k)) & 255u);
+            e.a0[k] = c0; e.d0[k] = (c1 - c0) / mid;
+            e.d1[k] = (c2 - c1) / (1.0f - mid); e.a1[k] = c1 - e.d1[k] * mid;
+          }
+          a.exts[i] = e;
+        } else if (!solid) {
+          // BL,BR,TR,TL at (s,t) = (0,1),(1,1),(1,0),(0,0): one affine function iff BL + TR == TL + BR per channel
+          PrimExt e;
+          e.ta = e.tb = e.tc = e.mid = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int bl = (cols[0] >> (8 * k)) & 255, br = (cols[1] >> (8 * k)) & 255, tr = (cols[2] >> (8 * k)) & 255,
+                      tl = (cols[3] >> (8 * k)) & 255;
+            if (bl + tr != tl + br) fast = false;
+            const float ds = (float)(tr - tl), dt = (float)(bl - tl);
+            e.a0[k] = (float)tl + ds * p.ou + dt * p.ov; e.d0[k] = ds * p.su; e.a1[k] = dt * p.sv; e.d1[k] = 0.0f;
+          }
+          if (fast) a.exts[i] = e;
+        }
+        if (fast) flags |= PF_FAST;
+      }
+      // Inner rect: the pixels where coverage is exactly 1 (ClipAA, DropShadow) or exactly 0 (inside an AnnularAA
+      // stroke).  In the cross region |p| <= b - rmax the rounded-box SDF is d = max(|px|-bx, |py|-by).
+      if (sdf_rect && aligned && circ && content && X1 > X0 && Y1 > Y0 && rs.aa > 0.0f &&
+          (mode == FDC_SDF_CLIP_AA || mode == FDC_SDF_ANNULAR_AA || mode == FDC_SDF_DROP_SHADOW)) {
+        // {d <= -D} of a rounded box is the box shrunk by D with corner radius max(r - D, 0); the largest axis-aligned
+        // rect inside it is inset by D + (1 - 1/sqrt2) * max(r - D, 0) from the original edges (rmax is conservative).
+        const float rmax = fmaxf(fmaxf(p.r0, p.r1), fmaxf(p.r2, p.r3));
+        float D;
+        bool ok = true;
+        if (mode == FDC_SDF_CLIP_AA) D = 0.5f / rs.aa;                                   // coverage == 1
+        else if (mode == FDC_SDF_DROP_SHADOW) D = -(fill_mode == 0 ? p.spread : 0.0f);   // sd = d - spread <= 0
+        else { ok = p.factor >= 0.0f; D = p.factor + 0.5f / rs.aa; }                     // inside the stroke: coverage == 0
+        float m = D + 0.29290f * fmaxf(rmax - D, 0.0f) + 0.02f;
+        const float gx = 2.0f * p.qhx * p.su, gy = 2.0f * p.qhy * p.sv;  // d p / d pixel
+        const float lox = X0 - 0.5f + (p.qhx - p.p2 + m) / gx, hix = X0 - 0.5f + (p.qhx + p.p2 - m) / gx;
+        const float loy = Y0 - 0.5f + (p.qhy - p.p3 + m) / gy, hiy = Y0 - 0.5f + (p.qhy + p.p3 - m) / gy;
+        const int ix0 = max((int)ceilf(lox + 1e-3f), cx0), ix1 = min((int)floorf(hix - 1e-3f) + 1, cx1);
+        const int iy0 = max((int)ceilf(loy + 1e-3f), cy0), iy1 = min((int)floorf(hiy - 1e-3f) + 1, cy1);
+        if (ok && ix0 < ix1 && iy0 < iy1) {
+          flags |= PF_INNER;
+          if (mode == FDC_SDF_ANNULAR_AA) flags |= PF_INNER_EMPTY;
+          p.ix0 = (int16_t)ix0; p.iy0 = (int16_t)iy0; p.ix1 = (int16_t)ix1; p.iy1 = (int16_t)iy1;
+          // occluder: opaque unmasked ClipAA fill -- nothing painted before it survives inside the inner rect
+          // (PF_FAST only: the fast path stores the colour directly for such visits, independent of the destination)
+          if (mode == FDC_SDF_CLIP_AA && (flags & PF_FAST) && (flags & PF_DEPTH_MASK) == 0) {
+            uint32_t amin = min(min(cols[0] >> 24, cols[1] >> 24), min(cols[2] >> 24, cols[3] >> 24));
+            if (fill_mode != 0) amin = min(amin, min(p.c_mid >> 24, p.c_stop >> 24));
+            if (amin == 255u) flags |= PF_OCCLUDER;
           }
         }
+      }
+      if (solid && fill_mode == 0) {
+        // the colour as floats 0..255 so the shade kernel never converts
+        p.c[0] = __float_as_uint((float)(cols[0] & 255u));
+        p.c[1] = __float_as_uint((float)((cols[0] >> 8) & 255u));
+        p.c[2] = __float_as_uint((float)((cols[0] >> 16) & 255u));
+        p.c[3] = __float_as_uint((float)(cols[0] >> 24));
+      } else {
+        flags &= ~PF_SOLID;
       }
     }
   }

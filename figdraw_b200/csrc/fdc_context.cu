@@ -219,6 +219,7 @@ struct fdc_ctx {
   DevBuf<RectMaskRec> d_rectmasks;
   DevBuf<Prim> d_prims;
   DevBuf<QuadGeom> d_geoms;
+  DevBuf<PrimExt> d_exts;
   DevBuf<uint32_t> d_prim_call;
   DevBuf<uint32_t> d_chunk_counts, d_cbin_start, d_coarse_list, d_tile_start, d_tile_count, d_tile_list, d_counters;
   DevBuf<uint8_t> d_fb, d_backdrop, d_temp;
@@ -598,6 +599,7 @@ SetupArgs setup_args(fdc_ctx* ctx, const Segment& s) {
   a.count = s.count;
   a.prims = ctx->d_prims.p + s.first;
   a.geoms = ctx->d_geoms.p + s.first;
+  a.exts = ctx->d_exts.p + s.first;
   a.prim_call = ctx->d_prim_call.p + s.first;
   a.atlas = atlas_view(ctx);
   a.frame = ctx->frame;
@@ -621,6 +623,7 @@ int execute_frame(fdc_ctx* ctx, bool upload) {
     CK(ctx->d_rectmasks.reserve(std::max<size_t>(ctx->rectmasks.n, 1)));
     CK(ctx->d_prims.reserve(std::max<uint32_t>(n_draws, 1)));
     CK(ctx->d_geoms.reserve(std::max<uint32_t>(n_draws, 1)));
+    CK(ctx->d_exts.reserve(std::max<uint32_t>(n_draws, 1)));
     CK(ctx->d_prim_call.reserve(std::max<uint32_t>(n_draws, 1)));
     if (n_draws) CK(cudaMemcpyAsync(ctx->d_draws.p, ctx->draws.p, sizeof(fdc_call) * n_draws, cudaMemcpyHostToDevice, st));
     if (ctx->runs.n) CK(cudaMemcpyAsync(ctx->d_runs.p, ctx->runs.p, sizeof(RunState) * ctx->runs.n, cudaMemcpyHostToDevice, st));
@@ -654,6 +657,7 @@ int execute_frame(fdc_ctx* ctx, bool upload) {
       memset(&sa, 0, sizeof(sa));
       sa.prims = ctx->d_prims.p + s.first;
       sa.geoms = ctx->d_geoms.p + s.first;
+      sa.exts = ctx->d_exts.p + s.first;
       sa.rectmasks = ctx->d_rectmasks.p;
       sa.tile_start = ctx->d_tile_start.p;
       sa.tile_count = ctx->d_tile_count.p;
@@ -798,7 +802,7 @@ void fdc_destroy(fdc_ctx* ctx) {
   ctx->d_table.release();
   ctx->draws.release(); ctx->runs.release(); ctx->xforms.release(); ctx->rectmasks.release();
   ctx->d_draws.release(); ctx->d_runs.release(); ctx->d_xforms.release(); ctx->d_rectmasks.release();
-  ctx->d_prims.release(); ctx->d_geoms.release(); ctx->d_prim_call.release();
+  ctx->d_prims.release(); ctx->d_geoms.release(); ctx->d_exts.release(); ctx->d_prim_call.release();
   ctx->d_chunk_counts.release(); ctx->d_cbin_start.release(); ctx->d_coarse_list.release();
   ctx->d_tile_start.release(); ctx->d_tile_count.release(); ctx->d_tile_list.release(); ctx->d_counters.release();
   ctx->d_fb.release(); ctx->d_backdrop.release(); ctx->d_temp.release(); ctx->d_peers.release();

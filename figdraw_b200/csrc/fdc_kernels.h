@@ -14,6 +14,7 @@ struct SetupArgs {
   uint32_t first, count;  // this segment's draw range [first, first+count)
   Prim* prims;            // [count] output
   QuadGeom* geoms;        // [count] output (only PF_GENERAL entries are meaningful)
+  PrimExt* exts;          // [count] output (only gradient PF_FAST entries are meaningful)
   uint32_t* prim_call;    // [count] backend-call ordinal per primitive (debug bins)
   AtlasView atlas;
   FrameView frame;
@@ -37,6 +38,7 @@ void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& frame,
 struct ShadeArgs {
   const Prim* prims;
   const QuadGeom* geoms;
+  const PrimExt* exts;
   const RectMaskRec* rectmasks;
   const uint32_t* tile_start;
   const uint32_t* tile_count;

@@ -21,15 +21,34 @@
 
 #include "fdc_kernels.h"
 
+#ifndef FDC_SHADE_MIN_BLOCKS
+#define FDC_SHADE_MIN_BLOCKS 4
+#endif
+
 namespace fdc {
 
 namespace {
 
 __device__ __forceinline__ float sat(float x) { return __saturatef(x); }
+// Pixel channels are kept BIASED: value + kBias with kBias = 1.5 * 2^23, where one ulp is exactly 1.  Any float add or
+// FMA whose result lands in that binade is therefore rounded to an integer by the hardware (round-to-nearest-even),
+// which is the UNORM8 store of the blended value for free; the low byte of the bit pattern is the UNORM8 value.
+constexpr float kBias = 12582912.0f;
+constexpr uint32_t kBiasBits = 0x4B400000u;
 __device__ __forceinline__ float rint255(float x) {  // round to nearest (even) integer, |x| < 2^22
-  return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f);
+  return __fadd_rn(__fadd_rn(x, kBias), -kBias);
 }
-__device__ __forceinline__ float len2(float x, float y) { return sqrtf(fmaf(x, x, y * y)); }
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float len2(float x, float y) { return fast_sqrt(fmaf(x, x, y * y)); }
 
 // atlas.frag:51-69
 __device__ __forceinline__ float sd_rounded_box(float px, float py, float bx, float by, float r0, float r1, float r2, float r3) {
@@ -190,7 +209,7 @@ __device__ float4 atlas_sample(const AtlasView& at, float tu, float tv, float la
 }
 
 struct Pixel {
-  float r, g, b, a;   // exact UNORM8 values 0..255
+  float r, g, b, a;   // exact UNORM8 values 0..255, biased by kBias
   uint32_t mlo, mhi;  // texture-mask levels 1..8, UNORM8 each
 };
 
@@ -291,14 +310,76 @@ __device__ float rect_mask_alpha(const RectMaskRec& rm, float aa, float px, floa
 }
 
 __device__ __forceinline__ void blend(Pixel& px, float sr, float sg, float sb, float sa) {
-  // rgb = s*sa + d*(1-sa); a = sa + da*(1-sa)  (glBlendFuncSeparate, glutils.nim:150-154), then UNORM8 store
-  px.r = rint255(fmaf(sr - px.r, sa, px.r));
-  px.g = rint255(fmaf(sg - px.g, sa, px.g));
-  px.b = rint255(fmaf(sb - px.b, sa, px.b));
-  px.a = rint255(fmaf(255.0f - px.a, sa, px.a));
+  // rgb = s*sa + d*(1-sa); a = sa + da*(1-sa)  (glBlendFuncSeparate, glutils.nim:150-154), then UNORM8 store:
+  // d + (s - d)*sa evaluated by one FMA into the biased binade = rounded to the UNORM8 grid.  sa == 0 is a no-op.
+  px.r = fmaf(sr - (px.r - kBias), sa, px.r);
+  px.g = fmaf(sg - (px.g - kBias), sa, px.g);
+  px.b = fmaf(sb - (px.b - kBias), sa, px.b);
+  px.a = fmaf(255.0f - (px.a - kBias), sa, px.a);
 }
 
-__device__ void shade_prim(const ShadeArgs& a, const Prim* __restrict__ P, int ix, int iy, Pixel& px) {
+// Hot path: axis-aligned, circular corners, ClipAA / AnnularAA / DropShadow, content (not a mask write), no rect mask.
+// PF_VISIT_FULL in `flags`: the warp's whole block lies in the primitive's inner rect where coverage is exactly 1.
+template <bool kMasked>
+__device__ __forceinline__ void shade_fast(const Prim* __restrict__ P, const PrimExt* __restrict__ E, uint32_t flags, float fx,
+                                           float fy, Pixel& px) {
+  const float4* Q = reinterpret_cast<const float4*>(P);
+  float4 col;
+  if (flags & PF_SOLID) {
+    col = __ldg(Q + 4);
+  } else {
+    const float4* X = reinterpret_cast<const float4*>(E);
+    const float4 a0 = __ldg(X + 1), d0 = __ldg(X + 2), a1 = __ldg(X + 3);
+    if (flags & PF_FILLMODE_MASK) {
+      const float4 e0 = __ldg(X + 0), d1 = __ldg(X + 4);
+      const float tt = sat(fmaf(fx, e0.x, fmaf(fy, e0.y, e0.z)));
+      const bool lo = tt <= e0.w;
+      col.x = fmaf(lo ? d0.x : d1.x, tt, lo ? a0.x : a1.x);
+      col.y = fmaf(lo ? d0.y : d1.y, tt, lo ? a0.y : a1.y);
+      col.z = fmaf(lo ? d0.z : d1.z, tt, lo ? a0.z : a1.z);
+      col.w = fmaf(lo ? d0.w : d1.w, tt, lo ? a0.w : a1.w);
+    } else {
+      col.x = fmaf(d0.x, fx, fmaf(a1.x, fy, a0.x));
+      col.y = fmaf(d0.y, fx, fmaf(a1.y, fy, a0.y));
+      col.z = fmaf(d0.z, fx, fmaf(a1.z, fy, a0.z));
+      col.w = fmaf(d0.w, fx, fmaf(a1.w, fy, a0.w));
+    }
+  }
+  if ((flags & (PF_VISIT_FULL | PF_OCCLUDER)) == (PF_VISIT_FULL | PF_OCCLUDER)) {
+    // opaque, coverage exactly 1 on the whole block: dst*(1-1) vanishes, the store is round(src) whatever dst was.
+    // (Earlier primitives were skipped for this block, so the result must not depend on dst even in the last ulp.)
+    px.r = col.x + kBias; px.g = col.y + kBias; px.b = col.z + kBias; px.a = 255.0f + kBias;
+    return;
+  }
+  float sa = col.w * (1.0f / 255.0f);
+  if (!(flags & PF_VISIT_FULL)) {
+    const float4 q7 = __ldg(Q + 7), q1 = __ldg(Q + 1), q2 = __ldg(Q + 2), q3 = __ldg(Q + 3);
+    const float ppx = fmaf(fx, q7.x, q7.y), ppy = fmaf(fy, q7.z, q7.w);  // (p.x, -p.y)
+    const float apx = fabsf(ppx), apy = fabsf(ppy);
+    const bool inside = apx < q1.x && apy < q1.y;  // pixel centre inside the ceil'd quad
+    const float rr = ppx > 0.0f ? (ppy > 0.0f ? q2.x : q2.y) : (ppy > 0.0f ? q2.z : q2.w);
+    const float qx = apx - q1.z + rr, qy = apy - q1.w + rr;
+    const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
+    const float dist = fminf(fmaxf(qx, qy), 0.0f) + fast_sqrt(fmaf(mx, mx, my * my)) - rr;
+    const uint32_t mode = flags & PF_MODE_MASK;
+    float cov;
+    if (mode == FDC_SDF_DROP_SHADOW) {  // sd > 0 ? exp(-.5 (sd/sigma)^2) : 1
+      const float sd = fmaxf(dist - q3.y, 0.0f);
+      cov = fast_ex2(q3.w * sd * sd);
+    } else if (mode == FDC_SDF_CLIP_AA) {
+      cov = sat(fmaf(-q3.z, dist, 0.5f));
+    } else {  // AnnularAA
+      const float f = q3.x * 0.5f;
+      cov = sat(fmaf(-q3.z, fabsf(dist + f) - f, 0.5f));
+    }
+    sa = inside ? sa * cov : 0.0f;
+  }
+  if (kMasked) sa *= mask_get(px, (int)((flags & PF_DEPTH_MASK) >> PF_DEPTH_SHIFT)) * (1.0f / 255.0f);
+  blend(px, col.x, col.y, col.z, sa);
+}
+
+__device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const Prim* __restrict__ P, int ix, int iy, Pixel px) {
+  const ShadeArgs& a = *ap;
   const float4* Q = reinterpret_cast<const float4*>(P);
   const int4 q6 = __ldg(reinterpret_cast<const int4*>(P) + 6);
   const uint32_t flags = (uint32_t)q6.z;
@@ -323,7 +404,7 @@ __device__ void shade_prim(const ShadeArgs& a, const Prim* __restrict__ P, int i
     s = fmaf((float)ix, q0.x, q0.y);
     t = fmaf((float)iy, q0.z, q0.w);
   }
-  if (!__any_sync(0xFFFFFFFFu, inside)) return;
+  if (!__any_sync(0xFFFFFFFFu, inside)) return px;
 
   const float4 q1 = __ldg(Q + 1), q2 = __ldg(Q + 2), q3 = __ldg(Q + 3);
   const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(P) + 4);
@@ -334,7 +415,7 @@ __device__ void shade_prim(const ShadeArgs& a, const Prim* __restrict__ P, int i
   // fill colour (0..255)
   float4 col;
   if (fill_mode != 0) col = linear3_color(q4.x, q5.x, q5.y, fill_mode, q3.y, s, t);
-  else if (flags & PF_SOLID) col = unpack255(q4.x);
+  else if (flags & PF_SOLID) col = __ldg(Q + 4);
   else col = vertex_color(q4, s, t);
 
   // p = (uv - .5) * 2 * quadHalf ; the SDF is evaluated at (p.x, -p.y)
@@ -452,13 +533,13 @@ __device__ void shade_prim(const ShadeArgs& a, const Prim* __restrict__ P, int i
 
   if (mask_write) {
     // alpha = cov * color.a * prevMask ; R8 target with blending on: r = a*a + dst*(1-a)   (SURVEY 8a' trap 1)
-    float al = cov * (flags & PF_SOLID || fill_mode != 0 ? col.w : col.w) * (1.0f / 255.0f);
+    float al = cov * col.w * (1.0f / 255.0f);
     if (depth > 1) al *= mask_get(px, depth - 1) * (1.0f / 255.0f);
     if (inside) {
       const float m = mask_get(px, depth);
       mask_set(px, depth, rint255(fmaf(al, 255.0f * al, m * (1.0f - al))));
     }
-    return;
+    return px;
   }
   float sa = salpha * (1.0f / 255.0f) * cov;
   if (depth > 0) sa *= mask_get(px, depth) * (1.0f / 255.0f);
@@ -467,11 +548,12 @@ __device__ void shade_prim(const ShadeArgs& a, const Prim* __restrict__ P, int i
     sa *= rect_mask_alpha(rm, aa, (float)ix + 0.5f, (float)iy + 0.5f);
   }
   if (inside && sa > 0.0f) blend(px, sr, sg, sb, sa);
+  return px;
 }
 
 }  // namespace
 
-__global__ void __launch_bounds__(256) shade_kernel(ShadeArgs a) {
+__global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ ShadeArgs a) {
   if (a.counters[1] != 0) return;  // a bin list overflowed: host regrows and replays the frame
   const FrameView& f = a.frame;
   const int tile = blockIdx.x;
@@ -481,13 +563,16 @@ __global__ void __launch_bounds__(256) shade_kernel(ShadeArgs a) {
   const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
   const bool valid = ix < f.W && iy < f.H;
   uint32_t* fb32 = reinterpret_cast<uint32_t*>(a.fb);
+  const float fx = (float)ix, fy = (float)iy;
 
   Pixel px;
   {
     uint32_t c = a.clear_rgba8;
     if (a.load_dst && valid) c = fb32[(size_t)iy * f.W + ix];
-    const float4 d = unpack255(c);
-    px.r = d.x; px.g = d.y; px.b = d.z; px.a = d.w;
+    px.r = __uint_as_float(kBiasBits | (c & 255u));
+    px.g = __uint_as_float(kBiasBits | ((c >> 8) & 255u));
+    px.b = __uint_as_float(kBiasBits | ((c >> 16) & 255u));
+    px.a = __uint_as_float(kBiasBits | (c >> 24));
     px.mlo = px.mhi = 0;
   }
 
@@ -521,25 +606,43 @@ __global__ void __launch_bounds__(256) shade_kernel(ShadeArgs a) {
 
   for (uint32_t base = start; base < n; base += 32) {
     const uint32_t idx = base + lane;
-    uint32_t pid = 0;
-    bool hit = false;
+    uint32_t pid = 0, flags = 0;
+    int cls = 0;  // 0 culled, 1 shade, 2 shade with full coverage
     if (idx < n) {
       pid = __ldg(&list[idx]);
-      const int4 q6 = __ldg(reinterpret_cast<const int4*>(a.prims + pid) + 6);
+      const Prim* P = a.prims + pid;
+      const int4 q6 = __ldg(reinterpret_cast<const int4*>(P) + 6);
+      flags = (uint32_t)q6.z;
       const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
-      hit = (bx0 < wx1 && bx1 > wx0 && by0 < wy1 && by1 > wy0) || ((uint32_t)q6.z & PF_MASK_BEGIN);
+      if (bx0 < wx1 && bx1 > wx0 && by0 < wy1 && by1 > wy0) {
+        cls = 1;
+        if (flags & PF_INNER) {
+          const int2 ir = __ldg(reinterpret_cast<const int2*>(P) + 11);
+          const int x0 = (int16_t)(ir.x & 0xFFFF), y0 = (int16_t)(ir.x >> 16), x1 = (int16_t)(ir.y & 0xFFFF), y1 = (int16_t)(ir.y >> 16);
+          if (x0 <= wx0 && y0 <= wy0 && x1 >= wx1 && y1 >= wy1) cls = (flags & PF_INNER_EMPTY) ? 0 : 2;
+        }
+      }
+      if (flags & PF_MASK_BEGIN) cls = max(cls, 1);
     }
-    uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (cls == 2) flags |= PF_VISIT_FULL;
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, cls != 0);
     while (m) {
       const int j = __ffs(m) - 1;
       m &= m - 1;
       const uint32_t p = __shfl_sync(0xFFFFFFFFu, pid, j);
-      shade_prim(a, a.prims + p, ix, iy, px);
+      const uint32_t fl = __shfl_sync(0xFFFFFFFFu, flags, j);
+      if (fl & PF_FAST) {
+        if (fl & PF_DEPTH_MASK) shade_fast<true>(a.prims + p, a.exts + p, fl, fx, fy, px);
+        else shade_fast<false>(a.prims + p, a.exts + p, fl, fx, fy, px);
+      } else {
+        px = shade_prim(&a, a.prims + p, ix, iy, px);
+      }
     }
   }
 
   if (valid) {
-    const uint32_t out = (uint32_t)(int)px.r | ((uint32_t)(int)px.g << 8) | ((uint32_t)(int)px.b << 16) | ((uint32_t)(int)px.a << 24);
+    const uint32_t out = (__float_as_uint(px.r) & 255u) | ((__float_as_uint(px.g) & 255u) << 8) |
+                         ((__float_as_uint(px.b) & 255u) << 16) | ((__float_as_uint(px.a) & 255u) << 24);
     fb32[(size_t)iy * f.W + ix] = out;
     for (int k = 0; k < a.n_peers; k++) {
       uint32_t* peer = reinterpret_cast<uint32_t*>(a.peers[k]);

@@ -37,6 +37,10 @@ constexpr uint32_t PF_RECTMASK = 1u << 14;      // fast rect mask applies (index
 constexpr uint32_t PF_SUBPIXEL = 1u << 15;      // atlas: subpixel shift enabled
 constexpr uint32_t PF_DEPTH_SHIFT = 16;         // 4 bits: texture-mask level read (content) or written (mask)
 constexpr uint32_t PF_DEPTH_MASK = 0xFu << 16;
+constexpr uint32_t PF_FAST = 1u << 20;          // axis-aligned circular-corner ClipAA / AnnularAA / DropShadow content quad
+constexpr uint32_t PF_INNER = 1u << 21;         // inner rect (ix0..iy1) valid: coverage is exactly 1 there ...
+constexpr uint32_t PF_INNER_EMPTY = 1u << 22;   // ... or exactly 0 (interior of an AnnularAA stroke)
+constexpr uint32_t PF_VISIT_FULL = 1u << 23;    // shade kernel only: the warp's block lies inside the inner rect
 constexpr uint32_t PF_EMPTY = 1u << 31;         // dropped (early-out or empty clipped bbox)
 
 // 128-byte shading record, eight 16-byte quads q0..q7.
@@ -50,7 +54,7 @@ struct alignas(16) Prim {
   float r0, r1, r2, r3;
   // q3: factor, spread (or midPos), aa factor, k: shadows -0.5*log2(e)/sigma^2; atlas lambda (LOD); msdf screenPxRange
   float factor, spread, aa, k;
-  // q4: vertex colours BL, BR, TR, TL
+  // q4: vertex colours BL, BR, TR, TL packed RGBA8; PF_SOLID: the colour as four floats 0..255 (bit patterns)
   uint32_t c[4];
   // q5: 3-stop colours and the occluder inner rect [ix0,ix1) x [iy0,iy1) (pixels)
   uint32_t c_mid, c_stop;
@@ -58,10 +62,20 @@ struct alignas(16) Prim {
   // q6: clipped bin bbox [bx0,bx1) x [by0,by1) (pixels), flags, aux: rect mask index+1 (low 16) | subpixel shift*65535 (high 16)
   int16_t bx0, by0, bx1, by1;
   uint32_t mode_flags, aux;
-  // q7: atlas texel mapping: tu = s*du + u0, tv = t*dv + v0 (level-0 texels, already minus 0.5)
+  // q7: atlas modes: texel mapping tu = s*du + u0, tv = t*dv + v0 (level-0 texels, already minus 0.5)
+  //     SDF modes:   SDF-space position from the pixel index: p.x = x*u0 + du ; -p.y = y*v0 + dv
   float u0, du, v0, dv;
 };
 static_assert(sizeof(Prim) == 128, "Prim must be 128 bytes");
+
+// Gradient colours of a PF_FAST primitive as floats (0..255), evaluated straight from the pixel index.
+//   3-stop (fill mode 1..4): tt = sat(x*ta + y*tb + tc); colour = tt <= mid ? a0 + d0*tt : a1 + d1*tt
+//   vertex colours (affine): colour = a0 + d0*x + a1*y
+struct alignas(16) PrimExt {
+  float ta, tb, tc, mid;
+  float a0[4], d0[4], a1[4], d1[4];
+};
+static_assert(sizeof(PrimExt) == 80, "PrimExt must be 80 bytes");
 
 // Geometry of a general (rotated / arbitrary) quad: ceil'd integer vertices BL, BR, TR, TL.
 struct alignas(16) QuadGeom {

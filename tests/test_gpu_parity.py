@@ -128,7 +128,9 @@ def test_split_frame_equals_single_frame():
     ctx.saveTransform()
     ctx.submitCalls(calls[k:])
     ctx.endFrame()
-    assert np.array_equal(ctx.readPixels(), full)
+    got = ctx.readPixels()
+    mx, frac = diff_stats(got, full)
+    assert np.array_equal(got, full), f"split frame differs: max {mx} LSB, {frac:.5%} of pixels"
     ctx.close()
 
 

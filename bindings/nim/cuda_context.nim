@@ -1,0 +1,275 @@
+## cuda_context.nim -- the B200 backend as a sibling of `OpenGlContext`, `VulkanContext` and `MetalContext`.
+##
+## Drop this file at `src/figdraw/cuda/cuda_context.nim` in a figdraw checkout, build with `-d:figdraw.cuda=on`
+## (INTEGRATION.md shows the three-line switch in `commons.nim` / `figrender.nim`) and link `libfigdraw_cuda.so`.
+##
+## It is deliberately thin: every `BackendContext` method (src/figdraw/figbackend.nim:245-705) forwards to the
+## C-ABI function of the same meaning in include/figdraw_cuda.h.  The transform stack, `ceil`, radii packing, mode
+## encoding and gradient vertex colours that `glcontext.nim` does on the host all happen behind the ABI (on the
+## device, in prim_setup_kernel), so the shim keeps no rendering state of its own except the `entries` table that
+## the front-end reads directly (figrender.nim:59-60, :477).
+##
+## NOT COMPILED in the build container (no Nim toolchain there); kept reviewable against the header.
+
+import std/[hashes, tables]
+import pkg/chroma
+import pkg/pixie
+import pkg/vmath
+import pkg/bumpy
+
+import ../commons
+import ../figbackend as figbackend
+import ../common/filltypes
+import ../common/shared
+import ../fignodes
+
+{.passL: "-lfigdraw_cuda".}
+
+type
+  FdcCtx = distinct pointer
+
+  FdcFill {.bycopy.} = object
+    kind, axis: uint32
+    c: array[4, uint32]
+    midPos: float32
+
+  CudaContext* = ref object of figbackend.BackendContext
+    h: FdcCtx
+    entries*: Table[Hash, Rect] ## image key -> normalised atlas rect, as in OpenGlContext
+    atlasEntryMeta: Table[Hash, figbackend.AtlasEntryMeta]
+    frameSize: Vec2
+
+const hdr = "figdraw_cuda.h"
+
+proc fdc_create(outCtx: ptr FdcCtx, device, atlasSize: cint, pixelScale: cfloat, rank, nRanks: cint): cint {.importc, header: hdr.}
+proc fdc_destroy(ctx: FdcCtx) {.importc, header: hdr.}
+proc fdc_last_error(ctx: FdcCtx): cstring {.importc, header: hdr.}
+proc fdc_begin_frame(ctx: FdcCtx, w, h, clearMain: cint, clearRgba: ptr cfloat): cint {.importc, header: hdr.}
+proc fdc_end_frame(ctx: FdcCtx): cint {.importc, header: hdr.}
+proc fdc_read_pixels(ctx: FdcCtx, x, y, w, h: cint, outRgba: ptr uint8): cint {.importc, header: hdr.}
+proc fdc_translate(ctx: FdcCtx, x, y: cfloat): cint {.importc, header: hdr.}
+proc fdc_rotate(ctx: FdcCtx, angle: cfloat): cint {.importc, header: hdr.}
+proc fdc_scale(ctx: FdcCtx, sx, sy: cfloat): cint {.importc, header: hdr.}
+proc fdc_apply_transform(ctx: FdcCtx, m: ptr cfloat): cint {.importc, header: hdr.}
+proc fdc_save_transform(ctx: FdcCtx): cint {.importc, header: hdr.}
+proc fdc_restore_transform(ctx: FdcCtx): cint {.importc, header: hdr.}
+proc fdc_transform_mirrors_y(ctx: FdcCtx): cint {.importc, header: hdr.}
+proc fdc_sdf_aa_factor(ctx: FdcCtx): cfloat {.importc, header: hdr.}
+proc fdc_set_sdf_aa_factor(ctx: FdcCtx, aa: cfloat): cint {.importc, header: hdr.}
+proc fdc_set_text_subpixel_positioning_enabled(ctx: FdcCtx, enabled: cint): cint {.importc, header: hdr.}
+proc fdc_set_text_subpixel_shift(ctx: FdcCtx, shift: cfloat): cint {.importc, header: hdr.}
+proc fdc_pixel_scale(ctx: FdcCtx): cfloat {.importc, header: hdr.}
+proc fdc_draw_rounded_rect_sdf(ctx: FdcCtx, rect: ptr cfloat, fill: ptr FdcFill, rx, ry: ptr cfloat, mode: cint,
+                               factor, spread: cfloat, shapeSize: ptr cfloat): cint {.importc, header: hdr.}
+proc fdc_draw_image(ctx: FdcCtx, key: uint64, pos: ptr cfloat, colors: ptr uint32, size: ptr cfloat,
+                    flipY: cint): cint {.importc, header: hdr.}
+proc fdc_draw_msdf_image(ctx: FdcCtx, key: uint64, pos: ptr cfloat, color: uint32, size: ptr cfloat,
+                         pxRange, sdThreshold, strokeWeight: cfloat, flipY, isMtsdf: cint): cint {.importc, header: hdr.}
+proc fdc_draw_quadratic_bezier_sdf(ctx: FdcCtx, rect: ptr cfloat, fill: ptr FdcFill, p0, p1, p2: ptr cfloat,
+                                   strokeWeight: cfloat, cap: cint): cint {.importc, header: hdr.}
+proc fdc_draw_filled_quad(ctx: FdcCtx, verts: ptr cfloat, colors: ptr uint32): cint {.importc, header: hdr.}
+proc fdc_draw_rect(ctx: FdcCtx, rect: ptr cfloat, color: uint32): cint {.importc, header: hdr.}
+proc fdc_draw_backdrop_blur(ctx: FdcCtx, rect, rx, ry: ptr cfloat, blurRadius: cfloat): cint {.importc, header: hdr.}
+proc fdc_begin_mask(ctx: FdcCtx, rect, rx, ry: ptr cfloat): cint {.importc, header: hdr.}
+proc fdc_end_mask(ctx: FdcCtx): cint {.importc, header: hdr.}
+proc fdc_pop_mask(ctx: FdcCtx): cint {.importc, header: hdr.}
+proc fdc_begin_rect_mask(ctx: FdcCtx, rect, rx, ry: ptr cfloat): cint {.importc, header: hdr.}
+proc fdc_pop_rect_mask(ctx: FdcCtx): cint {.importc, header: hdr.}
+proc fdc_put_image(ctx: FdcCtx, key: uint64, w, h: cint, rgba: ptr uint8, outRect: ptr cfloat,
+                   outRebuilt: ptr cint): cint {.importc, header: hdr.}
+proc fdc_update_image(ctx: FdcCtx, key: uint64, w, h: cint, rgba: ptr uint8): cint {.importc, header: hdr.}
+proc fdc_remove_image(ctx: FdcCtx, key: uint64): cint {.importc, header: hdr.}
+proc fdc_reset_image_atlas(ctx: FdcCtx, minimumSize: cint): cint {.importc, header: hdr.}
+proc fdc_atlas_size(ctx: FdcCtx): cint {.importc, header: hdr.}
+proc fdc_atlas_packed_area(ctx: FdcCtx): cint {.importc, header: hdr.}
+
+template ck(ctx: CudaContext, call: untyped) =
+  ## Non-zero fdc_status -> FigDrawError (common/shared.nim:19), like GL errors surface as exceptions.
+  let rc = call
+  if rc != 0 and rc != 5: # 5 = FDC_ERR_MISSING_IMAGE: GL only warns (glcontext.nim:1305-1310)
+    raise newException(FigDrawError, "cuda backend: " & $fdc_last_error(ctx.h))
+
+func pack(c: ColorRGBA): uint32 =
+  c.r.uint32 or (c.g.uint32 shl 8) or (c.b.uint32 shl 16) or (c.a.uint32 shl 24)
+
+func toFdc(fill: figbackend.BackendFill): FdcFill =
+  case fill.kind
+  of figbackend.bfColor:
+    FdcFill(kind: 1, c: [fill.color.pack, 0, 0, 0], midPos: 0.5)
+  of figbackend.bfLinear2:
+    FdcFill(kind: 2, axis: fill.lin2Axis.uint32, c: [fill.lin2Start.pack, fill.lin2Stop.pack, 0, 0], midPos: 0.5)
+  of figbackend.bfLinear3:
+    FdcFill(kind: 3, axis: fill.lin3Axis.uint32,
+            c: [fill.lin3Start.pack, fill.lin3Mid.pack, fill.lin3Stop.pack, 0], midPos: fill.lin3MidPos)
+
+template rectArr(r: Rect): array[4, cfloat] = [r.x.cfloat, r.y.cfloat, r.w.cfloat, r.h.cfloat]
+template radX(r: CornerRadii2D[float32]): array[4, cfloat] =
+  [r.x[dcTopLeft].cfloat, r.x[dcTopRight].cfloat, r.x[dcBottomLeft].cfloat, r.x[dcBottomRight].cfloat]
+template radY(r: CornerRadii2D[float32]): array[4, cfloat] =
+  [r.y[dcTopLeft].cfloat, r.y[dcTopRight].cfloat, r.y[dcBottomLeft].cfloat, r.y[dcBottomRight].cfloat]
+
+proc newContext*(atlasSize = 1024, pixelScale = 1.0, device = 0, rank = 0, nRanks = 1): CudaContext =
+  ## Mirrors `newContext` of glcontext.nim:255.  Raises when there is no B200: there is no CPU fallback.
+  result = CudaContext()
+  if fdc_create(result.h.addr, device.cint, atlasSize.cint, pixelScale.cfloat, rank.cint, nRanks.cint) != 0:
+    raise newException(FigDrawError, "cuda backend: " & $fdc_last_error(FdcCtx(nil)))
+  result.entries = initTable[Hash, Rect]()
+  result.atlasEntryMeta = initTable[Hash, figbackend.AtlasEntryMeta]()
+  result.ensureImageMessageSubscription()
+  result.noteAtlasCreated()
+
+method kind*(ctx: CudaContext): figbackend.RendererBackendKind = figbackend.RendererBackendKind.rbOpenGL # or a new rbCuda
+method entriesPtr*(ctx: CudaContext): ptr Table[Hash, Rect] = ctx.entries.addr
+method atlasEntryMetaPtr*(ctx: CudaContext): var Table[Hash, figbackend.AtlasEntryMeta] = ctx.atlasEntryMeta
+method atlasSize*(ctx: CudaContext): int = fdc_atlas_size(ctx.h).int
+method atlasPackedArea*(ctx: CudaContext): int = fdc_atlas_packed_area(ctx.h).int
+method pixelScale*(ctx: CudaContext): float32 = fdc_pixel_scale(ctx.h)
+method hasImage*(ctx: CudaContext, key: Hash): bool = key in ctx.entries
+
+method putImage*(ctx: CudaContext, path: Hash, image: Image) =
+  ## glcontext.nim:581-586.  pixie stores premultiplied RGBX; the ABI takes straight alpha like glTexSubImage2D gets
+  ## after the `ColorRGBX -> ColorRGBA` conversion of textures.nim:90-92.
+  var data = newSeq[ColorRGBA](image.width * image.height)
+  for i in 0 ..< data.len: data[i] = image.data[i].rgba()
+  var r: array[4, cfloat]
+  var rebuilt: cint
+  ctx.ck fdc_put_image(ctx.h, cast[uint64](path), image.width.cint, image.height.cint,
+                       cast[ptr uint8](data[0].addr), r[0].addr, rebuilt.addr)
+  if rebuilt != 0:
+    ctx.entries.clear()
+    ctx.atlasEntryMeta.clear()
+  ctx.entries[path] = rect(r[0], r[1], r[2], r[3])
+  ctx.markGeneratedEntry(path)
+  if rebuilt != 0: ctx.noteAtlasRebuilt() # replays every live image, figbackend.nim:202-207
+
+method addImage*(ctx: CudaContext, key: Hash, image: Image) = ctx.putImage(key, image)
+
+method updateImage*(ctx: CudaContext, path: Hash, image: Image) =
+  var data = newSeq[ColorRGBA](image.width * image.height)
+  for i in 0 ..< data.len: data[i] = image.data[i].rgba()
+  ctx.ck fdc_update_image(ctx.h, cast[uint64](path), image.width.cint, image.height.cint, cast[ptr uint8](data[0].addr))
+
+method putImage*(ctx: CudaContext, imgObj: ImgObj) =
+  case imgObj.kind
+  of PixieImg: ctx.putImage(imgObj.id.Hash, imgObj.pimg)
+  of FlippyImg: ctx.putImage(imgObj.id.Hash, imgObj.flippy.mipmaps[0]) # the mip chain is rebuilt on the device
+  ctx.markImageEntry(imgObj.id)
+
+method resetImageAtlas*(ctx: CudaContext, minimumSize: int) =
+  ctx.ck fdc_reset_image_atlas(ctx.h, minimumSize.cint)
+  ctx.entries.clear()
+  ctx.atlasEntryMeta.clear()
+  ctx.noteAtlasRebuilt()
+
+method clearImageAtlas*(ctx: CudaContext) = ctx.resetImageAtlas(0)
+
+method beginFrame*(ctx: CudaContext, frameSize: Vec2, clearMain = false, clearMainColor: Color = whiteColor) =
+  var c = [clearMainColor.r.cfloat, clearMainColor.g.cfloat, clearMainColor.b.cfloat, clearMainColor.a.cfloat]
+  ctx.frameSize = frameSize
+  ctx.ck fdc_begin_frame(ctx.h, frameSize.x.cint, frameSize.y.cint, clearMain.cint, c[0].addr)
+
+method endFrame*(ctx: CudaContext) = ctx.ck fdc_end_frame(ctx.h)
+
+method readPixels*(ctx: CudaContext, frame: Rect, readFront: bool): Image =
+  var (x, y, w, h) = (frame.x.int, frame.y.int, frame.w.int, frame.h.int)
+  if w <= 0 or h <= 0: (x, y, w, h) = (0, 0, ctx.frameSize.x.int, ctx.frameSize.y.int)
+  if w <= 0 or h <= 0: return newImage(0, 0)
+  result = newImage(w, h)
+  var data = newSeq[ColorRGBA](w * h)
+  ctx.ck fdc_read_pixels(ctx.h, x.cint, y.cint, w.cint, h.cint, cast[ptr uint8](data[0].addr))
+  for i in 0 ..< data.len: result.data[i] = data[i].rgbx() # already top-left origin: no flipVertical needed
+
+method translate*(ctx: CudaContext, v: Vec2) = ctx.ck fdc_translate(ctx.h, v.x, v.y)
+method rotate*(ctx: CudaContext, angle: float32) = ctx.ck fdc_rotate(ctx.h, angle)
+method scale*(ctx: CudaContext, s: float32) = ctx.ck fdc_scale(ctx.h, s, s)
+method scale*(ctx: CudaContext, s: Vec2) = ctx.ck fdc_scale(ctx.h, s.x, s.y)
+method applyTransform*(ctx: CudaContext, m: Mat4) =
+  var a: array[16, cfloat]
+  for i in 0 ..< 4:
+    for j in 0 ..< 4: a[i * 4 + j] = m[i, j] # vmath: m[col, row]
+  ctx.ck fdc_apply_transform(ctx.h, a[0].addr)
+method saveTransform*(ctx: CudaContext) = ctx.ck fdc_save_transform(ctx.h)
+method restoreTransform*(ctx: CudaContext) = ctx.ck fdc_restore_transform(ctx.h)
+method transformMirrorsY*(ctx: CudaContext): bool = fdc_transform_mirrors_y(ctx.h) != 0
+
+method sdfAaFactor*(ctx: CudaContext): float32 = fdc_sdf_aa_factor(ctx.h)
+method setSdfAaFactor*(ctx: CudaContext, aaFactor: float32) = ctx.ck fdc_set_sdf_aa_factor(ctx.h, aaFactor)
+method setTextSubpixelPositioningEnabled*(ctx: CudaContext, enabled: bool) =
+  ctx.ck fdc_set_text_subpixel_positioning_enabled(ctx.h, enabled.cint)
+method setTextSubpixelShift*(ctx: CudaContext, shift: float32) = ctx.ck fdc_set_text_subpixel_shift(ctx.h, shift)
+
+proc drawRR(ctx: CudaContext, rect: Rect, fill: FdcFill, radii: CornerRadii2D[float32], mode: figbackend.SdfMode,
+            factor, spread: float32, shapeSize: Vec2) =
+  var (r, f, rx, ry) = (rectArr(rect), fill, radX(radii), radY(radii))
+  var ss = [shapeSize.x.cfloat, shapeSize.y.cfloat]
+  ctx.ck fdc_draw_rounded_rect_sdf(ctx.h, r[0].addr, f.addr, rx[0].addr, ry[0].addr, mode.cint, factor, spread, ss[0].addr)
+
+method drawRoundedRectSdf*(ctx: CudaContext, rect: Rect, colors: array[4, ColorRGBA], radii: CornerRadii2D[float32],
+                           mode: figbackend.SdfMode = sdfModeClipAA, factor: float32 = 4.0, spread: float32 = 0.0,
+                           shapeSize: Vec2 = vec2(0, 0)) =
+  ctx.drawRR(rect, FdcFill(kind: 0, c: [colors[0].pack, colors[1].pack, colors[2].pack, colors[3].pack], midPos: 0.5),
+             radii, mode, factor, spread, shapeSize)
+
+method drawRoundedRectSdf*(ctx: CudaContext, rect: Rect, fill: figbackend.BackendFill, radii: CornerRadii2D[float32],
+                           mode: figbackend.SdfMode = sdfModeClipAA, factor: float32 = 4.0, spread: float32 = 0.0,
+                           shapeSize: Vec2 = vec2(0, 0)) =
+  ctx.drawRR(rect, fill.toFdc, radii, mode, factor, spread, shapeSize)
+
+method drawRoundedRectSdf*(ctx: CudaContext, rect: Rect, color: Color, radii: CornerRadii2D[float32],
+                           mode: figbackend.SdfMode = sdfModeClipAA, factor: float32 = 4.0, spread: float32 = 0.0,
+                           shapeSize: Vec2 = vec2(0, 0)) =
+  ctx.drawRR(rect, FdcFill(kind: 1, c: [color.rgba().pack, 0, 0, 0], midPos: 0.5), radii, mode, factor, spread, shapeSize)
+
+method drawImage*(ctx: CudaContext, imageId: Hash, pos: Vec2, colors: array[4, ColorRGBA], size: Vec2, flipY: bool) =
+  var (p, s) = ([pos.x.cfloat, pos.y.cfloat], [size.x.cfloat, size.y.cfloat])
+  var c = [colors[0].pack, colors[1].pack, colors[2].pack, colors[3].pack]
+  ctx.ck fdc_draw_image(ctx.h, cast[uint64](imageId), p[0].addr, c[0].addr, s[0].addr, flipY.cint)
+
+proc drawSdfImage(ctx: CudaContext, imageId: Hash, pos: Vec2, color: Color, size: Vec2, pxRange, sdThreshold,
+                  strokeWeight: float32, flipY, mtsdf: bool) =
+  var (p, s) = ([pos.x.cfloat, pos.y.cfloat], [size.x.cfloat, size.y.cfloat])
+  ctx.ck fdc_draw_msdf_image(ctx.h, cast[uint64](imageId), p[0].addr, color.rgba().pack, s[0].addr, pxRange, sdThreshold,
+                             strokeWeight, flipY.cint, mtsdf.cint)
+
+method drawMsdfImage*(ctx: CudaContext, imageId: Hash, pos: Vec2 = vec2(0, 0), color = color(1, 1, 1, 1), size: Vec2,
+                      pxRange: float32, sdThreshold: float32 = 0.5, strokeWeight: float32 = 0.0, flipY = false) =
+  ctx.drawSdfImage(imageId, pos, color, size, pxRange, sdThreshold, strokeWeight, flipY, false)
+
+method drawMtsdfImage*(ctx: CudaContext, imageId: Hash, pos: Vec2 = vec2(0, 0), color = color(1, 1, 1, 1), size: Vec2,
+                       pxRange: float32, sdThreshold: float32 = 0.5, strokeWeight: float32 = 0.0, flipY = false) =
+  ctx.drawSdfImage(imageId, pos, color, size, pxRange, sdThreshold, strokeWeight, flipY, true)
+
+method drawQuadraticBezierSdf*(ctx: CudaContext, rect: Rect, fill: figbackend.BackendFill, p0, p1, p2: Vec2,
+                               strokeWeight: float32, cap: StrokeCap) =
+  var (r, f) = (rectArr(rect), fill.toFdc)
+  var (a, b, c) = ([p0.x.cfloat, p0.y.cfloat], [p1.x.cfloat, p1.y.cfloat], [p2.x.cfloat, p2.y.cfloat])
+  ctx.ck fdc_draw_quadratic_bezier_sdf(ctx.h, r[0].addr, f.addr, a[0].addr, b[0].addr, c[0].addr, strokeWeight, cap.cint)
+
+method drawFilledQuad*(ctx: CudaContext, verts: array[4, Vec2], colors: array[4, ColorRGBA]) =
+  var v: array[8, cfloat]
+  for i in 0 ..< 4: (v[2 * i], v[2 * i + 1]) = (verts[i].x.cfloat, verts[i].y.cfloat)
+  var c = [colors[0].pack, colors[1].pack, colors[2].pack, colors[3].pack]
+  ctx.ck fdc_draw_filled_quad(ctx.h, v[0].addr, c[0].addr)
+
+method drawRect*(ctx: CudaContext, rect: Rect, color: Color) =
+  var r = rectArr(rect)
+  ctx.ck fdc_draw_rect(ctx.h, r[0].addr, color.rgba().pack)
+
+method drawBackdropBlur*(ctx: CudaContext, rect: Rect, radii: CornerRadii2D[float32], blurRadius: float32) =
+  var (r, rx, ry) = (rectArr(rect), radX(radii), radY(radii))
+  ctx.ck fdc_draw_backdrop_blur(ctx.h, r[0].addr, rx[0].addr, ry[0].addr, blurRadius)
+
+method beginMask*(ctx: CudaContext, clipRect: Rect, radii: CornerRadii2D[float32]) =
+  var (r, rx, ry) = (rectArr(clipRect), radX(radii), radY(radii))
+  ctx.ck fdc_begin_mask(ctx.h, r[0].addr, rx[0].addr, ry[0].addr)
+method endMask*(ctx: CudaContext) = ctx.ck fdc_end_mask(ctx.h)
+method popMask*(ctx: CudaContext) = ctx.ck fdc_pop_mask(ctx.h)
+method beginRectMask*(ctx: CudaContext, maskRect: Rect, radii: CornerRadii2D[float32]) =
+  var (r, rx, ry) = (rectArr(maskRect), radX(radii), radY(radii))
+  ctx.ck fdc_begin_rect_mask(ctx.h, r[0].addr, rx[0].addr, ry[0].addr)
+method popRectMask*(ctx: CudaContext) = ctx.ck fdc_pop_rect_mask(ctx.h)
+
+proc close*(ctx: CudaContext) =
+  if pointer(ctx.h) != nil:
+    fdc_destroy(ctx.h)
+    ctx.h = FdcCtx(nil)

@@ -486,59 +486,147 @@ __device__ __forceinline__ bool rect_hits(uint32_t r, uint32_t bx, uint32_t by) 
   return (r & 255u) <= bx && bx <= ((r >> 16) & 255u) && ((r >> 8) & 255u) <= by && by <= (r >> 24);
 }
 
+// One CTA = one chunk of kChunk primitives x one range of coarse-bin rows.  A warp owns 4 consecutive groups of 32
+// primitives.  Per group: every lane marks the bins its primitive touches in a per-warp bitmap (one 32-bit word per
+// lane; a bin row takes `wpr` words), then the warp visits only the marked bins; for each, one ballot over the 32
+// primitives gives the count (popc) and the stable ranks (popc of lower lanes).  Counts accumulate per warp, a
+// prefix over the 8 warps orders them inside the chunk, the chunk/bin matrix orders chunks globally.
+constexpr int kSlots = 1024;  // bitmap bits per CTA: 32 words x 32 bins
+
 template <bool kScatter>
-__global__ void __launch_bounds__(256) coarse_bin_kernel(const Prim* __restrict__ prims, uint32_t n, FrameView f,
-                                                         uint32_t* __restrict__ chunk_counts,
+__global__ void __launch_bounds__(256) coarse_bin_kernel(const Prim* __restrict__ prims, uint32_t n, FrameView f, int wpr,
+                                                         int rows_per_cta, uint32_t* __restrict__ chunk_counts,
                                                          const uint32_t* __restrict__ cbin_start,
                                                          uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
                                                          uint32_t* __restrict__ counters) {
   __shared__ uint32_t rects[kChunk];
+  __shared__ uint16_t wcnt[8][kSlots];  // per-warp counts, then exclusive prefix over warps
+  __shared__ uint32_t bitmap[8][32];
+  __shared__ uint32_t gbase[kScatter ? kSlots : 1];  // global position of this chunk's slice of each bin
   const uint32_t chunk = blockIdx.x;
   const uint32_t base_idx = chunk * kChunk;
-  for (int k = threadIdx.x; k < kChunk; k += blockDim.x) rects[k] = coarse_rect(prims, base_idx + k, n, f);
-  __syncthreads();
+  const int row0 = blockIdx.y * rows_per_cta;
+  const int row1 = min(row0 + rows_per_cta, f.cby);
   const int n_bins = f.cbx * f.cby;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   if (kScatter && counters[2] > coarse_cap) return;  // overflow: host regrows and replays
-  for (int b = warp; b < n_bins; b += 8) {
-    const uint32_t bx = (uint32_t)(b % f.cbx), by = (uint32_t)(b / f.cbx);
-    uint32_t running = 0;
-    if (kScatter) running = cbin_start[b] + chunk_counts[(size_t)chunk * n_bins + b];
-#pragma unroll 4
-    for (int s = 0; s < kChunk / 32; s++) {
-      const bool hit = rect_hits(rects[s * 32 + lane], bx, by);
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-      if (kScatter) {
-        if (hit) coarse_list[running + __popc(m & lt_mask)] = base_idx + s * 32 + lane;
+  for (int k = threadIdx.x; k < kChunk; k += blockDim.x) rects[k] = coarse_rect(prims, base_idx + k, n, f);
+  for (int k = threadIdx.x; k < 8 * kSlots / 2; k += blockDim.x) reinterpret_cast<uint32_t*>(&wcnt[0][0])[k] = 0;
+  __syncthreads();
+
+  for (int pass = 0; pass < (kScatter ? 2 : 1); pass++) {
+    if (pass == 1) {
+      // exclusive prefix over the 8 warps: offset of each warp's first entry inside this chunk's slice of the bin
+      __syncthreads();
+      for (int sl = threadIdx.x; sl < kSlots; sl += blockDim.x) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const uint32_t c = wcnt[w][sl]; wcnt[w][sl] = (uint16_t)run; run += c; }
+        const int r = row0 + (sl >> 5) / wpr, x = ((sl >> 5) % wpr) * 32 + (sl & 31);
+        if (kScatter && r < row1 && x < f.cbx) {
+          const int b = r * f.cbx + x;
+          gbase[sl] = cbin_start[b] + chunk_counts[(size_t)chunk * n_bins + b];
+        }
       }
-      running += __popc(m);
+      __syncthreads();
     }
-    if (!kScatter && lane == 0) chunk_counts[(size_t)chunk * n_bins + b] = running;
+    for (int gi = 0; gi < 4; gi++) {
+      const int g = warp * 4 + gi;
+      const uint32_t rect = rects[g * 32 + lane];
+      bitmap[warp][lane] = 0;
+      __syncwarp();
+      {
+        const int x0 = rect & 255u, y0 = (rect >> 8) & 255u, x1 = (rect >> 16) & 255u, y1 = rect >> 24;
+        const int ya = max(y0, row0), yb = min(y1, row1 - 1);
+        for (int y = ya; y <= yb; y++) {
+          for (int wi = x0 >> 5; wi <= (x1 >> 5); wi++) {
+            const int lo = max(x0 - wi * 32, 0), hi = min(x1 - wi * 32, 31);
+            const uint32_t bits = (hi == 31 ? 0xFFFFFFFFu : ((2u << hi) - 1u)) & ~((1u << lo) - 1u);
+            atomicOr(&bitmap[warp][(y - row0) * wpr + wi], bits);
+          }
+        }
+      }
+      __syncwarp();
+      const uint32_t myword = bitmap[warp][lane];
+      uint32_t words = __ballot_sync(0xFFFFFFFFu, myword != 0);
+      while (words) {
+        const int wi = __ffs(words) - 1;
+        words &= words - 1;
+        uint32_t bits = __shfl_sync(0xFFFFFFFFu, myword, wi);
+        const uint32_t by = (uint32_t)(row0 + wi / wpr), bxw = (uint32_t)((wi % wpr) * 32);
+        while (bits) {
+          const int bit = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const bool hit = rect_hits(rect, bxw + bit, by);
+          const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+          const int sl = wi * 32 + bit;
+          if (pass == 0) {
+            if (lane == 0) wcnt[warp][sl] += (uint16_t)__popc(m);
+          } else {
+            const uint32_t off = wcnt[warp][sl];
+            const uint32_t pos = gbase[kScatter ? sl : 0] + off;
+            if (hit) coarse_list[pos + __popc(m & lt_mask)] = base_idx + g * 32 + lane;
+            __syncwarp();
+            if (lane == 0) wcnt[warp][sl] = (uint16_t)(off + __popc(m));
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (!kScatter) {
+      __syncthreads();
+      for (int sl = threadIdx.x; sl < kSlots; sl += blockDim.x) {
+        const int r = row0 + (sl >> 5) / wpr, x = ((sl >> 5) % wpr) * 32 + (sl & 31);
+        if (r < row1 && x < f.cbx) {
+          uint32_t tot = 0;
+#pragma unroll
+          for (int w = 0; w < 8; w++) tot += wcnt[w][sl];
+          chunk_counts[(size_t)chunk * n_bins + r * f.cbx + x] = tot;
+        }
+      }
+    }
   }
 }
 
-// Column scan over chunks per bin, then scan over bins.  One CTA.
-__global__ void __launch_bounds__(1024) coarse_scan_kernel(uint32_t* __restrict__ chunk_counts, int n_chunks, int n_bins,
-                                                           uint32_t* __restrict__ cbin_start, uint32_t coarse_cap,
-                                                           uint32_t* __restrict__ counters) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
+// Exclusive scan over chunks for every bin (one warp per bin), then -- in the last CTA to finish -- the scan over
+// bins that yields cbin_start.  counters[3] is the completion ticket.
+__global__ void __launch_bounds__(256) coarse_scan_kernel(uint32_t* __restrict__ chunk_counts, int n_chunks, int n_bins,
+                                                          uint32_t* __restrict__ cbin_start, uint32_t coarse_cap,
+                                                          uint32_t* __restrict__ counters) {
+  __shared__ uint32_t warp_sums[8];
+  __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int b0 = 0; b0 < n_bins; b0 += 1024) {
-    const int b = b0 + threadIdx.x;
-    uint32_t total = 0;
-    if (b < n_bins) {
-      for (int c = 0; c < n_chunks; c++) {
-        const uint32_t v = chunk_counts[(size_t)c * n_bins + b];
-        chunk_counts[(size_t)c * n_bins + b] = total;
-        total += v;
+  const int b = blockIdx.x * 8 + warp;
+  if (b < n_bins) {
+    uint32_t carry = 0;
+    for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+      const int c = c0 + lane;
+      const uint32_t v = c < n_chunks ? chunk_counts[(size_t)c * n_bins + b] : 0u;
+      uint32_t incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
       }
+      if (c < n_chunks) chunk_counts[(size_t)c * n_bins + b] = carry + incl - v;
+      carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
-    // block exclusive scan of `total`
-    uint32_t incl = total;
+    if (lane == 0) cbin_start[b + 1] = carry;  // bin totals, shifted by one; turned into offsets by the last CTA
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&counters[3], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // inclusive scan of the totals stored at cbin_start[1..n_bins]
+  uint32_t carry = 0;
+  volatile uint32_t* vs = cbin_start;
+  for (int b0 = 0; b0 < n_bins; b0 += 256) {
+    const int i = b0 + threadIdx.x;
+    const uint32_t v = i < n_bins ? vs[i + 1] : 0u;
+    uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -546,36 +634,37 @@ __global__ void __launch_bounds__(1024) coarse_scan_kernel(uint32_t* __restrict_
     }
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-      uint32_t ws = warp_sums[lane], wi = ws;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-        if (lane >= o) wi += t;
-      }
-      warp_sums[lane] = wi - ws;
-    }
-    __syncthreads();
-    const uint32_t excl = carry + warp_sums[warp] + incl - total;
-    if (b < n_bins) cbin_start[b] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + total;
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; w++) wbase += warp_sums[w];
+    uint32_t blk = 0;
+    for (int w = 0; w < 8; w++) blk += warp_sums[w];
+    if (i < n_bins) vs[i + 1] = carry + wbase + incl;
+    carry += blk;
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    cbin_start[n_bins] = carry;
+    cbin_start[0] = 0;
     counters[2] = carry;
     if (carry > coarse_cap) atomicOr(&counters[1], 1u);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ fine binning
+// One CTA per coarse bin.  The bin's list is staged in shared memory 2048 entries at a time (each thread gathers the
+// bboxes of 8 entries -> a 16-bit tile-row/tile-column mask), then warp w owns tile row w: per 32 staged entries one
+// ballot per tile column gives counts and stable ranks.  Counts -> CTA scan -> one atomicAdd reserves the bin's slice
+// of the tile list -> second walk scatters.
+constexpr int kStage = 2048;
+static_assert(kTileW == 16 && kTileH == 16 && kCoarse == 8, "fine_bin_kernel shifts assume 16x16 tiles, 8x8 tiles per bin");
+
 __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ prims, FrameView f,
                                                        const uint32_t* __restrict__ cbin_start,
                                                        const uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
                                                        uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile_count,
                                                        uint32_t* __restrict__ tile_list, uint32_t tile_cap,
                                                        uint32_t* __restrict__ counters) {
+  __shared__ uint32_t s_pid[kStage];
+  __shared__ uint16_t s_mask[kStage];  // low byte: tile columns, high byte: tile rows
   __shared__ uint32_t s_cnt[kCoarse * kCoarse];
   __shared__ uint32_t s_base[kCoarse * kCoarse];
   __shared__ uint32_t s_alloc;
@@ -585,9 +674,9 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
   const uint32_t begin = cbin_start[b], end = cbin_start[b + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  // warp w owns tile row w of the bin
-  const int tile_x0 = cbx_i * kCoarse, tile_y = f.cty0 + cby_i * kCoarse + warp;
-  const int px0 = tile_x0 * kTileW, py0 = tile_y * kTileH, py1 = py0 + kTileH;
+  const int tile_x0 = cbx_i * kCoarse, tile_y0 = f.cty0 + cby_i * kCoarse;
+  const int px0 = tile_x0 * kTileW, py0 = tile_y0 * kTileH;
+  const bool single = end - begin <= (uint32_t)kStage;
 
   uint32_t cnt[kCoarse];
 #pragma unroll
@@ -595,7 +684,6 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
 
   for (int pass = 0; pass < 2; pass++) {
     if (pass == 1) {
-      // publish counts, scan, allocate
       if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < kCoarse; i++) s_cnt[warp * kCoarse + i] = cnt[i];
@@ -604,12 +692,13 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
       if (threadIdx.x == 0) {
         uint32_t tot = 0;
         for (int t = 0; t < kCoarse * kCoarse; t++) { s_base[t] = tot; tot += s_cnt[t]; }
-        uint32_t at = atomicAdd(&counters[0], tot);
+        const uint32_t at = atomicAdd(&counters[0], tot);
         if (at + tot > tile_cap) { atomicOr(&counters[1], 2u); s_alloc = 0xFFFFFFFFu; }
         else s_alloc = at;
       }
       __syncthreads();
       const uint32_t alloc = s_alloc;
+      const int tile_y = tile_y0 + warp;
       if (lane < kCoarse) {
         const int tx = tile_x0 + lane;
         if (tx < f.tiles_x && tile_y >= f.ty0 && tile_y < f.ty1) {
@@ -621,28 +710,39 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
 #pragma unroll
       for (int i = 0; i < kCoarse; i++) cnt[i] = alloc + s_base[warp * kCoarse + i];
     }
-    for (uint32_t e0 = begin; e0 < end; e0 += 32) {
-      const uint32_t e = e0 + lane;
-      uint32_t pid = 0;
-      uint32_t colmask = 0;
-      if (e < end) {
-        pid = __ldg(&coarse_list[e]);
-        const int4 q6 = __ldg(reinterpret_cast<const int4*>(&prims[pid]) + 6);
-        const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
-        if (by0 < py1 && by1 > py0) {
-          // tile columns [c0, c1] of this bin that the bbox touches
-          int c0 = (bx0 - px0) / kTileW, c1 = (bx1 - 1 - px0) / kTileW;
-          if (bx0 < px0) c0 = 0;
-          c0 = max(c0, 0); c1 = min(c1, kCoarse - 1);
-          if (c1 >= c0 && bx1 > px0) colmask = ((2u << c1) - 1u) & ~((1u << c0) - 1u);
+    for (uint32_t s0 = begin; s0 < end; s0 += kStage) {
+      const uint32_t ns = min((uint32_t)kStage, end - s0);
+      if (pass == 0 || !single) {
+        __syncthreads();  // previous stage fully consumed
+        for (uint32_t k = threadIdx.x; k < ns; k += blockDim.x) {
+          const uint32_t pid = __ldg(&coarse_list[s0 + k]);
+          const int4 q6 = __ldg(reinterpret_cast<const int4*>(&prims[pid]) + 6);
+          const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
+          // tile columns / rows of this bin touched by the bbox (the bbox is known to intersect the bin)
+          const int c0 = max((bx0 - px0) >> 4, 0), c1 = min((bx1 - 1 - px0) >> 4, kCoarse - 1);
+          const int r0 = max((by0 - py0) >> 4, 0), r1 = min((by1 - 1 - py0) >> 4, kCoarse - 1);
+          uint32_t cm = 0, rm = 0;
+          if (c1 >= c0 && r1 >= r0) { cm = ((2u << c1) - 1u) & ~((1u << c0) - 1u); rm = ((2u << r1) - 1u) & ~((1u << r0) - 1u); }
+          s_pid[k] = pid;
+          s_mask[k] = (uint16_t)(cm | (rm << 8));
         }
+        __syncthreads();
       }
+      for (uint32_t k0 = 0; k0 < ns; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        uint32_t colmask = 0, pid = 0;
+        if (k < ns) {
+          const uint32_t mk = s_mask[k];
+          if ((mk >> (8 + warp)) & 1u) colmask = mk & 255u;
+          pid = s_pid[k];
+        }
 #pragma unroll
-      for (int i = 0; i < kCoarse; i++) {
-        const bool hit = (colmask >> i) & 1u;
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-        if (pass == 1 && hit) tile_list[cnt[i] + __popc(m & lt_mask)] = pid;
-        cnt[i] += __popc(m);
+        for (int i = 0; i < kCoarse; i++) {
+          const bool hit = (colmask >> i) & 1u;
+          const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+          if (pass == 1 && hit) tile_list[cnt[i] + __popc(m & lt_mask)] = pid;
+          cnt[i] += __popc(m);
+        }
       }
     }
   }
@@ -661,14 +761,18 @@ void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& f, con
                     int* n_launches) {
   const int n_bins = f.cbx * f.cby;
   const int n_chunks = (int)((n_prims + kChunk - 1) / kChunk);
-  // tiles of the band start empty; counters: cursor, (overflow kept), coarse total, tile total
+  // tiles of the band start empty; counters: tile cursor, overflow flags, coarse total, scan ticket
   cudaMemsetAsync(b.tile_count + (size_t)f.ty0 * f.tiles_x, 0, sizeof(uint32_t) * (size_t)(f.ty1 - f.ty0) * f.tiles_x, stream);
   cudaMemsetAsync(b.counters, 0, sizeof(uint32_t) * 4, stream);
   if (n_prims == 0 || n_bins == 0) return;
-  coarse_bin_kernel<false><<<n_chunks, 256, 0, stream>>>(prims, n_prims, f, b.chunk_counts, nullptr, nullptr, 0, b.counters);
-  coarse_scan_kernel<<<1, 1024, 0, stream>>>(b.chunk_counts, n_chunks, n_bins, b.cbin_start, b.coarse_cap, b.counters);
-  coarse_bin_kernel<true><<<n_chunks, 256, 0, stream>>>(prims, n_prims, f, b.chunk_counts, b.cbin_start, b.coarse_list,
-                                                        b.coarse_cap, b.counters);
+  const int wpr = (f.cbx + 31) / 32;             // bitmap words per coarse-bin row
+  const int rows_per_cta = 32 / wpr;             // 32 words per CTA
+  dim3 grid(n_chunks, (f.cby + rows_per_cta - 1) / rows_per_cta);
+  coarse_bin_kernel<false><<<grid, 256, 0, stream>>>(prims, n_prims, f, wpr, rows_per_cta, b.chunk_counts, nullptr, nullptr, 0,
+                                                    b.counters);
+  coarse_scan_kernel<<<(n_bins + 7) / 8, 256, 0, stream>>>(b.chunk_counts, n_chunks, n_bins, b.cbin_start, b.coarse_cap, b.counters);
+  coarse_bin_kernel<true><<<grid, 256, 0, stream>>>(prims, n_prims, f, wpr, rows_per_cta, b.chunk_counts, b.cbin_start,
+                                                   b.coarse_list, b.coarse_cap, b.counters);
   fine_bin_kernel<<<n_bins, 256, 0, stream>>>(prims, f, b.cbin_start, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count,
                                               b.tile_list, b.tile_cap, b.counters);
   if (n_launches) *n_launches += 4;

@@ -492,16 +492,19 @@ __device__ __forceinline__ bool rect_hits(uint32_t r, uint32_t bx, uint32_t by) 
 // primitives gives the count (popc) and the stable ranks (popc of lower lanes).  Counts accumulate per warp, a
 // prefix over the 8 warps orders them inside the chunk, the chunk/bin matrix orders chunks globally.
 constexpr int kSlots = 1024;  // bitmap bits per CTA: 32 words x 32 bins
+constexpr int kWarps = kChunk / 32;
 
+// kScatter == false: counts.  Writes chunk_counts[chunk][bin] and the per-warp counts (u8) to `warp_counts`.
+// kScatter == true : reads the per-warp counts back, orders warps with a prefix, and scatters primitive indices.
 template <bool kScatter>
-__global__ void __launch_bounds__(256) coarse_bin_kernel(const Prim* __restrict__ prims, uint32_t n, FrameView f, int wpr,
-                                                         int rows_per_cta, uint32_t* __restrict__ chunk_counts,
-                                                         const uint32_t* __restrict__ cbin_start,
-                                                         uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
-                                                         uint32_t* __restrict__ counters) {
-  __shared__ uint32_t rects[kChunk];
-  __shared__ uint16_t wcnt[8][kSlots];  // per-warp counts, then exclusive prefix over warps
-  __shared__ uint32_t bitmap[8][32];
+__global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restrict__ prims, uint32_t n, FrameView f, int wpr,
+                                                            int rows_per_cta, uint32_t* __restrict__ chunk_counts,
+                                                            uint8_t* __restrict__ warp_counts,
+                                                            const uint32_t* __restrict__ cbin_start,
+                                                            uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
+                                                            uint32_t* __restrict__ counters) {
+  __shared__ uint16_t wcnt[kWarps][kSlots];  // per-warp counts (count pass) / running offsets inside the chunk (scatter)
+  __shared__ uint32_t bitmap[kWarps][32];
   __shared__ uint32_t gbase[kScatter ? kSlots : 1];  // global position of this chunk's slice of each bin
   const uint32_t chunk = blockIdx.x;
   const uint32_t base_idx = chunk * kChunk;
@@ -511,80 +514,68 @@ __global__ void __launch_bounds__(256) coarse_bin_kernel(const Prim* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   if (kScatter && counters[2] > coarse_cap) return;  // overflow: host regrows and replays
-  for (int k = threadIdx.x; k < kChunk; k += blockDim.x) rects[k] = coarse_rect(prims, base_idx + k, n, f);
-  for (int k = threadIdx.x; k < 8 * kSlots / 2; k += blockDim.x) reinterpret_cast<uint32_t*>(&wcnt[0][0])[k] = 0;
+  uint8_t* wc_global = warp_counts + ((size_t)chunk * gridDim.y + blockIdx.y) * (size_t)(kWarps * kSlots);
+  const uint32_t rect = coarse_rect(prims, base_idx + threadIdx.x, n, f);
+
+  if (!kScatter) {
+    for (int k = threadIdx.x; k < kWarps * kSlots / 2; k += blockDim.x) reinterpret_cast<uint32_t*>(&wcnt[0][0])[k] = 0;
+  } else {
+    // per-warp counts -> exclusive prefix over warps; base of this chunk's slice of each bin
+    for (int sl = threadIdx.x; sl < kSlots; sl += blockDim.x) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; w++) { const uint32_t c = wc_global[w * kSlots + sl]; wcnt[w][sl] = (uint16_t)run; run += c; }
+      const int r = row0 + (sl >> 5) / wpr, x = ((sl >> 5) % wpr) * 32 + (sl & 31);
+      if (r < row1 && x < f.cbx) {
+        const int b = r * f.cbx + x;
+        gbase[sl] = cbin_start[b] + chunk_counts[(size_t)chunk * n_bins + b];
+      }
+    }
+  }
+  bitmap[warp][lane] = 0;
   __syncthreads();
 
-  for (int pass = 0; pass < (kScatter ? 2 : 1); pass++) {
-    if (pass == 1) {
-      // exclusive prefix over the 8 warps: offset of each warp's first entry inside this chunk's slice of the bin
-      __syncthreads();
-      for (int sl = threadIdx.x; sl < kSlots; sl += blockDim.x) {
-        uint32_t run = 0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) { const uint32_t c = wcnt[w][sl]; wcnt[w][sl] = (uint16_t)run; run += c; }
-        const int r = row0 + (sl >> 5) / wpr, x = ((sl >> 5) % wpr) * 32 + (sl & 31);
-        if (kScatter && r < row1 && x < f.cbx) {
-          const int b = r * f.cbx + x;
-          gbase[sl] = cbin_start[b] + chunk_counts[(size_t)chunk * n_bins + b];
-        }
+  // mark the bins my primitive touches: one 32-bit word per lane, a bin row takes `wpr` words
+  {
+    const int x0 = rect & 255u, y0 = (rect >> 8) & 255u, x1 = (rect >> 16) & 255u, y1 = rect >> 24;
+    const int ya = max(y0, row0), yb = min(y1, row1 - 1);
+    for (int y = ya; y <= yb; y++) {
+      for (int wi = x0 >> 5; wi <= (x1 >> 5); wi++) {
+        const int lo = max(x0 - wi * 32, 0), hi = min(x1 - wi * 32, 31);
+        const uint32_t bits = (hi == 31 ? 0xFFFFFFFFu : ((2u << hi) - 1u)) & ~((1u << lo) - 1u);
+        atomicOr(&bitmap[warp][(y - row0) * wpr + wi], bits);
       }
-      __syncthreads();
     }
-    for (int gi = 0; gi < 4; gi++) {
-      const int g = warp * 4 + gi;
-      const uint32_t rect = rects[g * 32 + lane];
-      bitmap[warp][lane] = 0;
-      __syncwarp();
-      {
-        const int x0 = rect & 255u, y0 = (rect >> 8) & 255u, x1 = (rect >> 16) & 255u, y1 = rect >> 24;
-        const int ya = max(y0, row0), yb = min(y1, row1 - 1);
-        for (int y = ya; y <= yb; y++) {
-          for (int wi = x0 >> 5; wi <= (x1 >> 5); wi++) {
-            const int lo = max(x0 - wi * 32, 0), hi = min(x1 - wi * 32, 31);
-            const uint32_t bits = (hi == 31 ? 0xFFFFFFFFu : ((2u << hi) - 1u)) & ~((1u << lo) - 1u);
-            atomicOr(&bitmap[warp][(y - row0) * wpr + wi], bits);
-          }
-        }
+  }
+  __syncwarp();
+  const uint32_t myword = bitmap[warp][lane];
+  uint32_t words = __ballot_sync(0xFFFFFFFFu, myword != 0);
+  while (words) {
+    const int wi = __ffs(words) - 1;
+    words &= words - 1;
+    uint32_t bits = __shfl_sync(0xFFFFFFFFu, myword, wi);
+    const uint32_t by = (uint32_t)(row0 + wi / wpr), bxw = (uint32_t)((wi % wpr) * 32);
+    while (bits) {
+      const int bit = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const bool hit = rect_hits(rect, bxw + bit, by);
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+      const int sl = wi * 32 + bit;
+      if (!kScatter) {
+        if (lane == 0) wcnt[warp][sl] = (uint16_t)__popc(m);  // each warp visits a bin once
+      } else {
+        if (hit) coarse_list[gbase[sl] + wcnt[warp][sl] + __popc(m & lt_mask)] = base_idx + threadIdx.x;
       }
-      __syncwarp();
-      const uint32_t myword = bitmap[warp][lane];
-      uint32_t words = __ballot_sync(0xFFFFFFFFu, myword != 0);
-      while (words) {
-        const int wi = __ffs(words) - 1;
-        words &= words - 1;
-        uint32_t bits = __shfl_sync(0xFFFFFFFFu, myword, wi);
-        const uint32_t by = (uint32_t)(row0 + wi / wpr), bxw = (uint32_t)((wi % wpr) * 32);
-        while (bits) {
-          const int bit = __ffs(bits) - 1;
-          bits &= bits - 1;
-          const bool hit = rect_hits(rect, bxw + bit, by);
-          const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-          const int sl = wi * 32 + bit;
-          if (pass == 0) {
-            if (lane == 0) wcnt[warp][sl] += (uint16_t)__popc(m);
-          } else {
-            const uint32_t off = wcnt[warp][sl];
-            const uint32_t pos = gbase[kScatter ? sl : 0] + off;
-            if (hit) coarse_list[pos + __popc(m & lt_mask)] = base_idx + g * 32 + lane;
-            __syncwarp();
-            if (lane == 0) wcnt[warp][sl] = (uint16_t)(off + __popc(m));
-          }
-        }
-      }
-      __syncwarp();
     }
-    if (!kScatter) {
-      __syncthreads();
-      for (int sl = threadIdx.x; sl < kSlots; sl += blockDim.x) {
-        const int r = row0 + (sl >> 5) / wpr, x = ((sl >> 5) % wpr) * 32 + (sl & 31);
-        if (r < row1 && x < f.cbx) {
-          uint32_t tot = 0;
+  }
+  if (!kScatter) {
+    __syncthreads();
+    for (int sl = threadIdx.x; sl < kSlots; sl += blockDim.x) {
+      const int r = row0 + (sl >> 5) / wpr, x = ((sl >> 5) % wpr) * 32 + (sl & 31);
+      uint32_t tot = 0;
 #pragma unroll
-          for (int w = 0; w < 8; w++) tot += wcnt[w][sl];
-          chunk_counts[(size_t)chunk * n_bins + r * f.cbx + x] = tot;
-        }
-      }
+      for (int w = 0; w < kWarps; w++) { const uint32_t c = wcnt[w][sl]; wc_global[w * kSlots + sl] = (uint8_t)c; tot += c; }
+      if (r < row1 && x < f.cbx) chunk_counts[(size_t)chunk * n_bins + r * f.cbx + x] = tot;
     }
   }
 }
@@ -689,12 +680,23 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
         for (int i = 0; i < kCoarse; i++) s_cnt[warp * kCoarse + i] = cnt[i];
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int t = 0; t < kCoarse * kCoarse; t++) { s_base[t] = tot; tot += s_cnt[t]; }
-        const uint32_t at = atomicAdd(&counters[0], tot);
-        if (at + tot > tile_cap) { atomicOr(&counters[1], 2u); s_alloc = 0xFFFFFFFFu; }
-        else s_alloc = at;
+      if (warp == 0) {
+        // exclusive scan of the 64 tile counts: two per lane
+        const uint32_t c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
+        uint32_t incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        s_base[2 * lane] = incl - c0 - c1;
+        s_base[2 * lane + 1] = incl - c1;
+        if (lane == 31) {
+          const uint32_t tot = incl;
+          const uint32_t at = atomicAdd(&counters[0], tot);
+          if (at + tot > tile_cap) { atomicOr(&counters[1], 2u); s_alloc = 0xFFFFFFFFu; }
+          else s_alloc = at;
+        }
       }
       __syncthreads();
       const uint32_t alloc = s_alloc;
@@ -768,11 +770,11 @@ void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& f, con
   const int wpr = (f.cbx + 31) / 32;             // bitmap words per coarse-bin row
   const int rows_per_cta = 32 / wpr;             // 32 words per CTA
   dim3 grid(n_chunks, (f.cby + rows_per_cta - 1) / rows_per_cta);
-  coarse_bin_kernel<false><<<grid, 256, 0, stream>>>(prims, n_prims, f, wpr, rows_per_cta, b.chunk_counts, nullptr, nullptr, 0,
-                                                    b.counters);
+  coarse_bin_kernel<false><<<grid, kChunk, 0, stream>>>(prims, n_prims, f, wpr, rows_per_cta, b.chunk_counts, b.warp_counts, nullptr,
+                                                       nullptr, 0, b.counters);
   coarse_scan_kernel<<<(n_bins + 7) / 8, 256, 0, stream>>>(b.chunk_counts, n_chunks, n_bins, b.cbin_start, b.coarse_cap, b.counters);
-  coarse_bin_kernel<true><<<grid, 256, 0, stream>>>(prims, n_prims, f, wpr, rows_per_cta, b.chunk_counts, b.cbin_start,
-                                                   b.coarse_list, b.coarse_cap, b.counters);
+  coarse_bin_kernel<true><<<grid, kChunk, 0, stream>>>(prims, n_prims, f, wpr, rows_per_cta, b.chunk_counts, b.warp_counts, b.cbin_start,
+                                                      b.coarse_list, b.coarse_cap, b.counters);
   fine_bin_kernel<<<n_bins, 256, 0, stream>>>(prims, f, b.cbin_start, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count,
                                               b.tile_list, b.tile_cap, b.counters);
   if (n_launches) *n_launches += 4;

@@ -17,7 +17,7 @@ namespace fdc {
 constexpr int kTileW = 16;         // pixels
 constexpr int kTileH = 16;
 constexpr int kCoarse = 8;         // coarse bin = kCoarse x kCoarse tiles (128 x 128 px)
-constexpr int kChunk = 1024;       // primitives per coarse-binning chunk
+constexpr int kChunk = 512;        // primitives per coarse-binning chunk (16 warps x 32)
 constexpr int kMaxMaskDepth = 8;   // texture-mask nesting the tile kernel keeps per pixel (GL: unbounded)
 constexpr int kAtlasMargin = 4;    // glcontext.nim:257
 constexpr int kMaxAtlasLevels = 14;

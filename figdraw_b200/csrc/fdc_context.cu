@@ -40,6 +40,23 @@ struct DevBuf {
     if (e == cudaSuccess) cap = want;
     return e;
   }
+  // grow keeping the first `keep` elements (device-to-device copy on `st`)
+  cudaError_t reserve_keep(size_t n, size_t keep, cudaStream_t st) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = std::max(n, cap * 2);
+    T* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    keep = std::min(keep, cap);
+    if (p && keep) {
+      e = cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (p) cudaFree(p);
+    p = np;
+    cap = want;
+    return e;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -202,7 +219,10 @@ struct fdc_ctx {
   int W = 0, H = 0;
   bool clear = true;
   uint32_t clear_rgba8 = 0xFFFFFFFFu;
-  PinnedBuf<fdc_call> draws;
+  PinnedBuf<fdc_call> draws;  // staged draw records (individually issued draws and short runs)
+  struct Upload { uint32_t dst, count; size_t staged_off; };
+  std::vector<Upload> uploads;  // staged ranges still to be copied to d_draws at endFrame
+  uint32_t n_draws = 0;         // draws of the frame so far (staged + directly uploaded)
   PinnedBuf<RunState> runs;
   PinnedBuf<Xform> xforms;
   PinnedBuf<RectMaskRec> rectmasks;
@@ -414,10 +434,23 @@ RunState current_state(fdc_ctx* ctx) {
   return rs;
 }
 
+// Stages one draw record; it gets global draw index ctx->n_draws.
+bool stage_draw(fdc_ctx* ctx, const fdc_call& d) {
+  const size_t off = ctx->draws.n;
+  if (!ctx->draws.push(d)) return false;
+  if (!ctx->uploads.empty() && ctx->uploads.back().dst + ctx->uploads.back().count == ctx->n_draws &&
+      ctx->uploads.back().staged_off + ctx->uploads.back().count == off)
+    ctx->uploads.back().count++;
+  else
+    ctx->uploads.push_back({ctx->n_draws, 1u, off});
+  ctx->n_draws++;
+  return true;
+}
+
 // Appends one draw record under the current backend state.
 int add_draw(fdc_ctx* ctx, const fdc_call& d, uint32_t ordinal) {
   if (!ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "draw outside beginFrame/endFrame");
-  const uint32_t idx = (uint32_t)ctx->draws.n;
+  const uint32_t idx = ctx->n_draws;
   if (ctx->xform_dirty) current_xform(ctx);
   const bool consecutive = ctx->runs.n > 0 && ordinal == ctx->last_draw_ordinal + 1;
   if (ctx->state_dirty || ctx->begin_pending || !consecutive || ctx->runs.n == 0) {
@@ -429,7 +462,7 @@ int add_draw(fdc_ctx* ctx, const fdc_call& d, uint32_t ordinal) {
     ctx->state_dirty = ctx->begin_pending;  // the draw after a MASK_BEGIN draw needs its own run
     ctx->begin_pending = false;
   }
-  if (!ctx->draws.push(d)) return ctx->fail(FDC_ERR_CUDA, "out of pinned memory");
+  if (!stage_draw(ctx, d)) return ctx->fail(FDC_ERR_CUDA, "out of pinned memory");
   ctx->last_draw_ordinal = ordinal;
   ctx->segments.back().count++;
   if (ctx->mask_begun) {
@@ -516,7 +549,7 @@ void host_bbox(fdc_ctx* ctx, const float rect[4], int& x0, int& y0, int& x1, int
 
 void start_segment(fdc_ctx* ctx) {
   Segment s;
-  s.first = (uint32_t)ctx->draws.n;
+  s.first = ctx->n_draws;
   ctx->segments.push_back(s);
 }
 
@@ -527,9 +560,9 @@ int reemit_masks(fdc_ctx* ctx) {
     MaskLevel& ml = ctx->mask_levels[L];
     for (size_t k = 0; k < ml.draws.size(); k++) {
       RunState rs = ml.states[k];
-      rs.first_draw = (uint32_t)ctx->draws.n;
+      rs.first_draw = ctx->n_draws;
       if (k == 0) rs.flags |= PF_MASK_BEGIN;
-      if (!ctx->runs.push(rs) || !ctx->draws.push(ml.draws[k])) return ctx->fail(FDC_ERR_CUDA, "out of pinned memory");
+      if (!ctx->runs.push(rs) || !stage_draw(ctx, ml.draws[k])) return ctx->fail(FDC_ERR_CUDA, "out of pinned memory");
       ctx->segments.back().count++;
     }
     if (ml.draws.empty() && L >= 1) {
@@ -616,7 +649,7 @@ SetupArgs setup_args(fdc_ctx* ctx, const Segment& s) {
 // Launches every kernel of the recorded frame.  `upload`: copy the recording to the device first.
 int execute_frame(fdc_ctx* ctx, bool upload) {
   cudaStream_t st = ctx->stream;
-  const uint32_t n_draws = (uint32_t)ctx->draws.n;
+  const uint32_t n_draws = ctx->n_draws;
   int rc = sync_table(ctx);
   if (rc) return rc;
   ctx->ev_used = 0;
@@ -624,7 +657,7 @@ int execute_frame(fdc_ctx* ctx, bool upload) {
   int launches = 0;
   cudaEventRecord(ctx->ev_begin, st);
   if (upload) {
-    CK(ctx->d_draws.reserve(std::max<uint32_t>(n_draws, 1)));
+    CK(ctx->d_draws.reserve_keep(std::max<uint32_t>(n_draws, 1), n_draws, st));
     CK(ctx->d_runs.reserve(std::max<size_t>(ctx->runs.n, 1)));
     CK(ctx->d_xforms.reserve(std::max<size_t>(ctx->xforms.n, 1)));
     CK(ctx->d_rectmasks.reserve(std::max<size_t>(ctx->rectmasks.n, 1)));
@@ -632,7 +665,9 @@ int execute_frame(fdc_ctx* ctx, bool upload) {
     CK(ctx->d_geoms.reserve(std::max<uint32_t>(n_draws, 1)));
     CK(ctx->d_exts.reserve(std::max<uint32_t>(n_draws, 1)));
     CK(ctx->d_prim_call.reserve(std::max<uint32_t>(n_draws, 1)));
-    if (n_draws) CK(cudaMemcpyAsync(ctx->d_draws.p, ctx->draws.p, sizeof(fdc_call) * n_draws, cudaMemcpyHostToDevice, st));
+    for (auto& u : ctx->uploads)
+      CK(cudaMemcpyAsync(ctx->d_draws.p + u.dst, ctx->draws.p + u.staged_off, sizeof(fdc_call) * u.count, cudaMemcpyHostToDevice, st));
+    ctx->uploads.clear();
     if (ctx->runs.n) CK(cudaMemcpyAsync(ctx->d_runs.p, ctx->runs.p, sizeof(RunState) * ctx->runs.n, cudaMemcpyHostToDevice, st));
     if (ctx->xforms.n) CK(cudaMemcpyAsync(ctx->d_xforms.p, ctx->xforms.p, sizeof(Xform) * ctx->xforms.n, cudaMemcpyHostToDevice, st));
     if (ctx->rectmasks.n)
@@ -842,6 +877,8 @@ int fdc_begin_frame(fdc_ctx* ctx, int width, int height, int clear_main, const f
   }
   compute_frame_view(ctx);
   ctx->draws.n = ctx->runs.n = ctx->xforms.n = ctx->rectmasks.n = 0;
+  ctx->n_draws = 0;
+  ctx->uploads.clear();
   ctx->segments.clear();
   start_segment(ctx);
   ctx->frame_begun = true;
@@ -1167,11 +1204,49 @@ int fdc_pop_rect_mask(fdc_ctx* ctx) {
 }
 
 // ------------------------------------------------------------------------------------------------- display list
+static inline bool is_draw_op(uint32_t op) { return op >= FDC_OP_ROUNDED_RECT && op <= FDC_OP_RECT; }
+constexpr size_t kDirectRunMin = 2048;  // records; shorter runs are staged
+
+// A long run of draw records issued under one backend state: one RunState, and the records go to the device in a
+// single copy straight from the caller's buffer (no host-side staging pass over 128 bytes per draw).
+static int add_direct_run(fdc_ctx* ctx, const fdc_call* calls, size_t count, uint32_t first_ordinal) {
+  RunState rs = current_state(ctx);
+  rs.first_draw = ctx->n_draws;
+  rs.call_index = first_ordinal;
+  if (!ctx->runs.push(rs)) return ctx->fail(FDC_ERR_CUDA, "out of pinned memory");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->d_draws.reserve_keep((size_t)ctx->n_draws + count, ctx->n_draws, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_draws.p + ctx->n_draws, calls, sizeof(fdc_call) * count, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->n_draws += (uint32_t)count;
+  ctx->segments.back().count += (uint32_t)count;
+  ctx->last_draw_ordinal = first_ordinal + (uint32_t)count - 1;
+  ctx->state_dirty = true;  // the next draw starts its own run
+  return FDC_OK;
+}
+
 int fdc_submit_calls(fdc_ctx* ctx, const fdc_call* calls, size_t n) {
   if (!ctx || (!calls && n)) return FDC_ERR_INVALID;
+  size_t short_until = 0;  // records before this index belong to a draw run already found too short
   for (size_t i = 0; i < n; i++) {
     const fdc_call& c = calls[i];
     int rc = FDC_OK;
+    if (i >= short_until && is_draw_op(c.op) && ctx->frame_begun && !ctx->mask_begun && n - i >= kDirectRunMin) {
+      size_t j = i;
+      bool need_rect = false;
+      while (j < n && is_draw_op(calls[j].op)) {
+        need_rect = need_rect || calls[j].op == FDC_OP_FILLED_QUAD || calls[j].op == FDC_OP_RECT;
+        j++;
+      }
+      if (j - i >= kDirectRunMin) {
+        if (need_rect && (rc = ensure_rect_image(ctx)) != FDC_OK) return rc;
+        rc = add_direct_run(ctx, calls + i, j - i, ctx->call_ordinal);
+        if (rc != FDC_OK) return rc;
+        ctx->call_ordinal += (uint32_t)(j - i);
+        i = j - 1;
+        continue;
+      }
+      short_until = j;
+    }
     switch (c.op) {
       case FDC_OP_NOP: ctx->call_ordinal++; break;
       case FDC_OP_SAVE_TRANSFORM: rc = fdc_save_transform(ctx); break;

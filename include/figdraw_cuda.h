@@ -200,8 +200,9 @@ int fdc_begin_rect_mask(fdc_ctx* ctx, const float rect[4], const float radii_x[4
 int fdc_pop_rect_mask(fdc_ctx* ctx);
 
 /* --- display list --- */
-/* Replays `n` records in order.  Equivalent to the individual calls; runs of draw records are
- * transferred to the device in one copy straight from `calls`. */
+/* Replays `n` records in order.  Equivalent to the individual calls.  Runs of >= 2048 consecutive draw records
+ * are transferred to the device in one asynchronous copy straight from `calls` (no host staging pass): if that
+ * memory is page-locked it must stay unmodified until the next fdc_sync / fdc_read_pixels / fdc_begin_frame. */
 int fdc_submit_calls(fdc_ctx* ctx, const fdc_call* calls, size_t n);
 
 /* --- atlas: glcontext.nim:536-641, textures.nim:88-119 --- */

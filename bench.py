@@ -196,8 +196,9 @@ def main():
         ctx.putImage(key, img)
 
     # Framebuffer owned by torch so NCCL can all-gather the bands in place; rows padded to equal bands.
-    tiles_y = (H + 15) // 16
-    band_rows = ((tiles_y + world - 1) // world) * 16
+    from figdraw_b200 import bands
+
+    band_rows, _layout = bands.band_layout(H, world)
     fb = torch.zeros((band_rows * world, W, 4), dtype=torch.uint8, device=dev)
     ctx.bindFramebuffer(fb.data_ptr())
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
@@ -209,9 +210,7 @@ def main():
     out_np = out_host.numpy()
 
     def gather():
-        if world > 1:
-            band = fb[rank * band_rows:(rank + 1) * band_rows]
-            dist.all_gather_into_tensor(fb, band)
+        bands.allgather_bands(fb, rank, world)
 
     def frame_e2e():
         ctx.beginFrame((W, H), clearMain=trace.clear is not None, clearMainColor=trace.clear or (1, 1, 1, 1))

@@ -432,6 +432,7 @@ typedef struct shared {
   uint8_t* backdrop;         /* RGBA8 */
   uint8_t* temp;
   int64_t frag_counts[N_MODES][8]; /* reduced at the end */
+  int count_only; /* orc_count_fragments: rasterise coverage, skip shading */
   /* reference binning (orc_collect_quads): quads are recorded instead of rasterised */
   int collect;
   int32_t* rec;      /* 8 ints per record: segment, call_index, x0, y0, x1, y1, is_mask, level */
@@ -746,6 +747,7 @@ static void raster_tri(tctx* t, const oquad_t* q, int ia, int ib, int ic, int ma
       }
       if (!inside) continue;
       nfrag++;
+      if (sh->count_only) continue;
       frag_in in;
       in.px = (float)x + 0.5f; in.py = (float)y + 0.5f;
       float rx = in.px - A->x, ry = in.py - A->y;
@@ -854,6 +856,19 @@ static void draw_quad(tctx* t, oquad_t* q) {
   }
   q->subpixel = t->subpixel_enabled ? fmaxf(0.0f, fminf(t->subpixel_shift, 0.999f)) : 0.0f;
   if (t->sh->collect) { collect_quad(t, q); return; }
+  if (t->sh->count_only && q->pos[0].x == q->pos[3].x && q->pos[1].x == q->pos[2].x && q->pos[0].y == q->pos[1].y &&
+      q->pos[2].y == q->pos[3].y) {
+    /* axis-aligned: the two triangles cover exactly [X0,X1) x [Y0,Y1) */
+    float xa = fminf(q->pos[3].x, q->pos[1].x), xb = fmaxf(q->pos[3].x, q->pos[1].x);
+    float ya = fminf(q->pos[3].y, q->pos[1].y), yb = fmaxf(q->pos[3].y, q->pos[1].y);
+    int x0 = clamp_i((int)fminf(fmaxf(xa, -1e6f), 1e6f), 0, t->sh->W), x1 = clamp_i((int)fminf(fmaxf(xb, -1e6f), 1e6f), 0, t->sh->W);
+    int y0 = clamp_i((int)fminf(fmaxf(ya, -1e6f), 1e6f), t->y0, t->y1), y1 = clamp_i((int)fminf(fmaxf(yb, -1e6f), 1e6f), t->y0, t->y1);
+    int mode = (q->mode_packed % 256) % 128;
+    int grad = (q->mode_packed / 256) != 0 || memcmp(&q->color[0], &q->color[1], sizeof(v4)) != 0 ||
+               memcmp(&q->color[0], &q->color[2], sizeof(v4)) != 0 || memcmp(&q->color[0], &q->color[3], sizeof(v4)) != 0;
+    if (x1 > x0 && y1 > y0 && mode < N_MODES) t->frag_counts[mode + (grad ? N_MODES : 0)] += (int64_t)(x1 - x0) * (y1 - y0);
+    return;
+  }
   raster_tri(t, q, 3, 0, 1, mask_read); /* indices glcontext.nim:418-429 */
   raster_tri(t, q, 2, 3, 1, mask_read);
 }
@@ -1275,6 +1290,67 @@ int orc_render_rows(oracle* o, int W, int H, int clear, const float* clear_rgba,
   free(sh.backdrop);
   free(sh.temp);
   return err;
+}
+
+/* Fragment counts per SdfMode ([mode] solid, [N_MODES+mode] gradient) without shading anything. */
+int orc_count_fragments(oracle* o, int W, int H, const call_t* calls, int64_t n_calls, int64_t* frag_counts, int n_threads) {
+  if (W <= 0 || H <= 0) return 1;
+  int needs_rect = 0, max_depth = 1, depth = 0;
+  for (int64_t i = 0; i < n_calls; i++) {
+    uint32_t op = calls[i].op;
+    if (op == OP_FILLED_QUAD || op == OP_RECT) needs_rect = 1;
+    if (op == OP_BEGIN_MASK || op == OP_BEGIN_RECT_MASK) { depth++; if (depth + 1 > max_depth) max_depth = depth + 1; }
+    if (op == OP_POP_MASK || op == OP_POP_RECT_MASK) depth--;
+  }
+  if (max_depth >= MAX_MASKS) return 4;
+  float dummy[4];
+  if (needs_rect && !orc_get_image_rect(o, RECT_KEY, dummy)) {
+    uint8_t white[64];
+    memset(white, 255, 64);
+    orc_put_image(o, RECT_KEY, 4, 4, white, NULL);
+  }
+  shared_t sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.o = o; sh.W = W; sh.H = H; sh.count_only = 1;
+  uint8_t* scratch = (uint8_t*)calloc((size_t)W * H, 1); /* one shared dummy mask level: only cleared, never read */
+  for (int l = 1; l <= max_depth; l++) sh.masks[l] = scratch;
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > H) n_threads = H;
+  int64_t totals[2 * N_MODES];
+  memset(totals, 0, sizeof(totals));
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads)
+#endif
+  {
+#ifdef _OPENMP
+    int tid = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+    int tid = 0, nt = 1;
+#endif
+    tctx* t = (tctx*)calloc(1, sizeof(tctx));
+    t->sh = &sh;
+    int rows = (H + nt - 1) / nt;
+    t->y0 = tid * rows; t->y1 = t->y0 + rows;
+    if (t->y0 > H) t->y0 = H;
+    if (t->y1 > H) t->y1 = H;
+    mat_identity(t->mat);
+    t->aa = 1.2f;
+    for (int64_t i = 0; i < n_calls; i++)
+      if (calls[i].op != OP_BACKDROP_BLUR) exec_call(t, &calls[i], (int)i);
+      else if (calls[i].f[12] > 0.0f && calls[i].f[2] > 0.0f && calls[i].f[3] > 0.0f) {
+        uint32_t whitec[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        op_rounded_rect(t, calls[i].f, calls[i].f + 4, calls[i].f + 8, M_BACKDROP, calls[i].f[12], 0.0f, 0.0f, 0.0f, FILL_COLORS4, 0,
+                        whitec, 0.5f, (int)i);
+      }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+    for (int m = 0; m < 2 * N_MODES; m++) totals[m] += t->frag_counts[m];
+    free(t);
+  }
+  memcpy(frag_counts, totals, sizeof(totals));
+  free(scratch);
+  return 0;
 }
 
 int orc_n_modes(void) { return N_MODES; }

@@ -43,6 +43,7 @@ def _lib() -> ctypes.CDLL:
                                    c.c_int64, c.c_void_p, c.c_void_p, c.c_int]
         lib.orc_render_rows.argtypes = lib.orc_render.argtypes + [c.c_int, c.c_int]
         lib.orc_max_threads.restype = c.c_int
+        lib.orc_count_fragments.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_int64, c.c_void_p, c.c_int]
         lib.orc_collect_quads.restype = c.c_int64
         lib.orc_collect_quads.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int64,
                                           c.c_void_p, c.c_int64]
@@ -51,7 +52,12 @@ def _lib() -> ctypes.CDLL:
 
 
 def max_threads() -> int:
-    return int(_lib().orc_max_threads())
+    """Host threads the oracle may use.  Launchers such as torchrun export OMP_NUM_THREADS=1; the oracle passes an
+    explicit num_threads() clause, so the core count is what matters."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
 
 
 class Oracle:
@@ -108,6 +114,21 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"oracle: render failed with status {rc}")
         return (fb, counts) if want_counts else fb
+
+
+def count_fragments(trace, n_threads: int = 0, oracle: Optional["Oracle"] = None) -> np.ndarray:
+    """Exact fragments per SdfMode ([mode] solid fills, [N_MODES+mode] gradient fills) without shading."""
+    o = oracle or Oracle(trace.atlas_size)
+    if oracle is None:
+        for _idx, key, img in trace.images:
+            o.put_image(key, img)
+    calls = np.ascontiguousarray(trace.calls)
+    counts = np.zeros(2 * N_MODES, dtype=np.int64)
+    nt = n_threads if n_threads > 0 else max_threads()
+    rc = _lib().orc_count_fragments(o._h, trace.width, trace.height, calls.ctypes.data, len(calls), counts.ctypes.data, nt)
+    if rc != 0:
+        raise RuntimeError(f"oracle: count failed with status {rc}")
+    return counts
 
 
 def reference_bins(trace, tile_w: int = 16, tile_h: int = 16, band: Optional[Tuple[int, int]] = None,

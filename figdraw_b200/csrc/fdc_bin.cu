@@ -725,7 +725,9 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
           const int r0 = max((by0 - py0) >> 4, 0), r1 = min((by1 - 1 - py0) >> 4, kCoarse - 1);
           uint32_t cm = 0, rm = 0;
           if (c1 >= c0 && r1 >= r0) { cm = ((2u << c1) - 1u) & ~((1u << c0) - 1u); rm = ((2u << r1) - 1u) & ~((1u << r0) - 1u); }
-          s_pid[k] = pid;
+          // bit 31 of a tile-list entry: the primitive is an occluder candidate (saves the shade kernel's backward
+          // occlusion scan a dependent load per entry)
+          s_pid[k] = pid | (((uint32_t)q6.z & PF_OCCLUDER) ? 0x80000000u : 0u);
           s_mask[k] = (uint16_t)(cm | (rm << 8));
         }
         __syncthreads();

@@ -1417,7 +1417,7 @@ int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t off
     tile_offsets[t] = (uint32_t)at;
     const int ty = (int)(t / tx_n);
     if (ty < ty0 || ty >= ty1) continue;
-    for (uint32_t k = 0; k < count[t]; k++) entries[at++] = calls[list[start[t] + k]];
+    for (uint32_t k = 0; k < count[t]; k++) entries[at++] = calls[list[start[t] + k] & 0x7FFFFFFFu];
   }
   tile_offsets[n_tiles] = (uint32_t)at;
   return FDC_OK;

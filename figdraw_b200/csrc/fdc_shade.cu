@@ -24,6 +24,15 @@
 #ifndef FDC_SHADE_MIN_BLOCKS
 #define FDC_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef FDC_STAGE
+// How a warp gets at the records of the primitives it shades:
+//   0  uniform-address loads from global memory (L1-resident: 93 % hit rate)          <- default, measured fastest
+//   1  staged into per-warp shared memory with 16-byte cp.async, one batch ahead
+//   2  staged with one cp.async.bulk (TMA) per primitive + mbarrier, one batch ahead
+// profiles/r01_shade_staging.md has the measurements (0.90 / 1.03 / 1.07 ms per cfg5 4K frame).
+#define FDC_STAGE 0
+#endif
+#define FDC_STAGE_TMA (FDC_STAGE == 2)
 
 namespace fdc {
 
@@ -49,6 +58,27 @@ __device__ __forceinline__ float fast_ex2(float x) {
   return r;
 }
 __device__ __forceinline__ float len2(float x, float y) { return fast_sqrt(fmaf(x, x, y * y)); }
+
+// ---- TMA (bulk async copy) + mbarrier plumbing, one barrier per warp and buffer
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 // atlas.frag:51-69
 __device__ __forceinline__ float sd_rounded_box(float px, float py, float bx, float by, float r0, float r1, float r2, float r3) {
@@ -320,13 +350,19 @@ __device__ __forceinline__ void blend(Pixel& px, float sr, float sg, float sb, f
 
 // Hot path: axis-aligned, circular corners, ClipAA / AnnularAA / DropShadow, content (not a mask write), no rect mask.
 // PF_VISIT_FULL in `flags`: the warp's whole block lies in the primitive's inner rect where coverage is exactly 1.
-template <bool kMasked>
-__device__ __forceinline__ void shade_fast(const Prim* __restrict__ P, const PrimExt* __restrict__ E, uint32_t flags, float fx,
+template <bool kSmem>
+__device__ __forceinline__ float4 ldq(const float4* p) {
+  if (kSmem) return *p;
+  return __ldg(p);
+}
+
+template <bool kMasked, bool kSmem>
+__device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const PrimExt* __restrict__ E, uint32_t flags, float fx,
                                            float fy, Pixel& px) {
-  const float4* Q = reinterpret_cast<const float4*>(P);
+  // S: q0..q4 of the primitive -- in global memory (all lanes load the same address), or staged in shared memory
   float4 col;
   if (flags & PF_SOLID) {
-    col = __ldg(Q + 4);
+    col = ldq<kSmem>(S + 4);
   } else {
     const float4* X = reinterpret_cast<const float4*>(E);
     const float4 a0 = __ldg(X + 1), d0 = __ldg(X + 2), a1 = __ldg(X + 3);
@@ -353,8 +389,8 @@ __device__ __forceinline__ void shade_fast(const Prim* __restrict__ P, const Pri
   }
   float sa = col.w * (1.0f / 255.0f);
   if (!(flags & PF_VISIT_FULL)) {
-    const float4 q7 = __ldg(Q + 7), q1 = __ldg(Q + 1), q2 = __ldg(Q + 2), q3 = __ldg(Q + 3);
-    const float ppx = fmaf(fx, q7.x, q7.y), ppy = fmaf(fy, q7.z, q7.w);  // (p.x, -p.y)
+    const float4 q0 = ldq<kSmem>(S + 0), q1 = ldq<kSmem>(S + 1), q2 = ldq<kSmem>(S + 2), q3 = ldq<kSmem>(S + 3);
+    const float ppx = fmaf(fx, q0.x, q0.y), ppy = fmaf(fy, q0.z, q0.w);  // (p.x, -p.y)
     const float apx = fabsf(ppx), apy = fabsf(ppy);
     const bool inside = apx < q1.x && apy < q1.y;  // pixel centre inside the ceil'd quad
     const float rr = ppx > 0.0f ? (ppy > 0.0f ? q2.x : q2.y) : (ppy > 0.0f ? q2.z : q2.w);
@@ -390,7 +426,7 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
 
   const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
   bool inside = ix >= bx0 && ix < bx1 && iy >= by0 && iy < by1;
-  const float4 q0 = __ldg(Q + 0);
+  const float4 q0 = __ldg(Q + 7);  // (su, ou, sv, ov)
   float s, t;
   float dsdx = q0.x, dsdy = 0.0f, dtdx = 0.0f, dtdy = q0.z;
   if (flags & PF_GENERAL) {
@@ -426,7 +462,7 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
   const bool is_bezier = mode >= FDC_SDF_BEZIER_STROKE_AA && mode <= FDC_SDF_BEZIER_STROKE_SQUARE_AA;
   const bool is_msdf = mode >= FDC_SDF_MSDF && mode <= FDC_SDF_MTSDF_ANNULAR;
   if (mode == FDC_SDF_ATLAS) {
-    const float4 q7 = __ldg(Q + 7);
+    const float4 q7 = __ldg(Q + 0);  // atlas texel map
     const float tu = fmaf(s, q7.y, q7.x), tv = fmaf(t, q7.w, q7.z);
     float lambda = q3.w;
     if (flags & PF_GENERAL) {
@@ -444,7 +480,7 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
       cov = 1.0f;
     }
   } else if (is_msdf && !mask_write) {
-    const float4 q7 = __ldg(Q + 7);
+    const float4 q7 = __ldg(Q + 0);  // atlas texel map
     const float tu = fmaf(s, q7.y, q7.x), tv = fmaf(t, q7.w, q7.z);
     float4 tex = make_float4(0.f, 0.f, 0.f, 0.f);
     if (inside) tex = tex_bilinear(a.atlas.level[0], a.atlas.size, tu, tv);  // textureLod(.., 0)
@@ -554,7 +590,18 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
 }  // namespace
 
 __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ ShadeArgs a) {
+#if FDC_STAGE != 0
+  __shared__ __align__(128) float4 s_prims[8][2][32 * 5];  // per warp, double buffered: q0..q4 of up to 32 primitives
+#endif
+#if FDC_STAGE == 2
+  __shared__ __align__(8) uint64_t s_bar[8][2];
+#endif
   if (a.counters[1] != 0) return;  // a bin list overflowed: host regrows and replays the frame
+#if FDC_STAGE == 2
+  if (threadIdx.x < 16) mbar_init(&s_bar[threadIdx.x >> 1][threadIdx.x & 1], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+#endif
   const FrameView& f = a.frame;
   const int tile = blockIdx.x;
   const int tx = tile % f.tiles_x, ty = f.ty0 + tile / f.tiles_x;
@@ -589,9 +636,9 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
       const int idx = base - lane;
       bool occ = false;
       if (idx >= 0) {
-        const Prim* P = a.prims + __ldg(&list[idx]);
-        const uint32_t fl = (uint32_t)__ldg(reinterpret_cast<const int*>(P) + 26);
-        if (fl & PF_OCCLUDER) {
+        const uint32_t e = __ldg(&list[idx]);
+        if (e & 0x80000000u) {  // occluder candidate (flagged by fine_bin_kernel)
+          const Prim* P = a.prims + (e & 0x7FFFFFFFu);
           const int2 ir = __ldg(reinterpret_cast<const int2*>(P) + 11);
           const int x0 = (int16_t)(ir.x & 0xFFFF), y0 = (int16_t)(ir.x >> 16), x1 = (int16_t)(ir.y & 0xFFFF), y1 = (int16_t)(ir.y >> 16);
           occ = x0 <= wx0 && y0 <= wy0 && x1 >= wx1 && y1 >= wy1;
@@ -604,12 +651,26 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
     start = n;  // block entirely outside the frame
   }
 
-  for (uint32_t base = start; base < n; base += 32) {
+  // Per-warp software pipeline over batches of 32 list entries:
+  //   classify(batch k+1): every lane loads one primitive's bbox/flags/inner rect and classifies it against the block;
+  //   stage(batch k+1):    every surviving fast primitive is copied (q0..q4, 80 bytes) into this warp's shared-memory
+  //                        buffer by one cp.async.bulk (TMA) per lane, completion counted on the buffer's mbarrier;
+  //   visit(batch k):      wait on batch k's mbarrier, then shade its survivors out of shared memory.
+  // The copies of batch k+1 fly while batch k is being shaded.
+#if FDC_STAGE != 0
+  float4* const my_buf = &s_prims[warp][0][0];
+#endif
+#if FDC_STAGE == 2
+  uint64_t* const my_bar = &s_bar[warp][0];
+#endif
+
+  auto classify = [&](uint32_t base, uint32_t& pid, uint32_t& flags) -> uint32_t {
     const uint32_t idx = base + lane;
-    uint32_t pid = 0, flags = 0;
+    pid = 0;
+    flags = 0;
     int cls = 0;  // 0 culled, 1 shade, 2 shade with full coverage
     if (idx < n) {
-      pid = __ldg(&list[idx]);
+      pid = __ldg(&list[idx]) & 0x7FFFFFFFu;
       const Prim* P = a.prims + pid;
       const int4 q6 = __ldg(reinterpret_cast<const int4*>(P) + 6);
       flags = (uint32_t)q6.z;
@@ -625,20 +686,95 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
       if (flags & PF_MASK_BEGIN) cls = max(cls, 1);
     }
     if (cls == 2) flags |= PF_VISIT_FULL;
-    uint32_t m = __ballot_sync(0xFFFFFFFFu, cls != 0);
+    return __ballot_sync(0xFFFFFFFFu, cls != 0);
+  };
+#if FDC_STAGE == 2
+  auto stage = [&](int buf, uint32_t pid, uint32_t flags, uint32_t m) -> bool {
+    const bool mine = ((m >> lane) & 1u) && (flags & PF_FAST);
+    const uint32_t fm = __ballot_sync(0xFFFFFFFFu, mine);
+    if (fm == 0) return false;
+    if (lane == 0) mbar_arrive_expect_tx(my_bar + buf, (uint32_t)kPrimFastBytes * __popc(fm));
+    if (mine) bulk_copy_g2s(my_buf + (buf * 32 + lane) * 5, a.prims + pid, kPrimFastBytes, my_bar + buf);
+    return true;
+  };
+#elif FDC_STAGE == 1
+  // LDGSTS variant: five 16-byte cp.async per surviving lane, one commit group per batch
+  auto stage = [&](int buf, uint32_t pid, uint32_t flags, uint32_t m) -> bool {
+    if (((m >> lane) & 1u) && (flags & PF_FAST)) {
+      const uint32_t dst = smem_u32(my_buf + (buf * 32 + lane) * 5);
+      const char* src = reinterpret_cast<const char*>(a.prims + pid);
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * k), "l"(src + 16 * k) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    return true;
+  };
+#endif
+
+#if FDC_STAGE == 0
+  for (uint32_t base = start; base < n; base += 32) {
+    uint32_t pid_c, fl_c;
+    uint32_t m = classify(base, pid_c, fl_c);
     while (m) {
       const int j = __ffs(m) - 1;
       m &= m - 1;
-      const uint32_t p = __shfl_sync(0xFFFFFFFFu, pid, j);
-      const uint32_t fl = __shfl_sync(0xFFFFFFFFu, flags, j);
+      const uint32_t p = __shfl_sync(0xFFFFFFFFu, pid_c, j);
+      const uint32_t fl = __shfl_sync(0xFFFFFFFFu, fl_c, j);
       if (fl & PF_FAST) {
-        if (fl & PF_DEPTH_MASK) shade_fast<true>(a.prims + p, a.exts + p, fl, fx, fy, px);
-        else shade_fast<false>(a.prims + p, a.exts + p, fl, fx, fy, px);
+        const float4* S = reinterpret_cast<const float4*>(a.prims + p);
+        if (fl & PF_DEPTH_MASK) shade_fast<true, false>(S, a.exts + p, fl, fx, fy, px);
+        else shade_fast<false, false>(S, a.exts + p, fl, fx, fy, px);
       } else {
         px = shade_prim(&a, a.prims + p, ix, iy, px);
       }
     }
   }
+#else
+  uint32_t pid_c = 0, fl_c = 0, m_c = 0, phases = 0;
+  bool staged_c = false;
+  if (start < n) {
+    m_c = classify(start, pid_c, fl_c);
+    staged_c = stage(0, pid_c, fl_c, m_c);
+  }
+  int buf = 0;
+  for (uint32_t base = start; base < n; base += 32, buf ^= 1) {
+    uint32_t pid_n = 0, fl_n = 0, m_n = 0;
+    bool staged_n = false;
+    if (base + 32 < n) {
+      m_n = classify(base + 32, pid_n, fl_n);
+      staged_n = stage(buf ^ 1, pid_n, fl_n, m_n);
+    }
+#if FDC_STAGE_TMA
+    if (staged_c) {
+      mbar_wait(my_bar + buf, (phases >> buf) & 1u);
+      phases ^= 1u << buf;
+    }
+#else
+    // all but the newest group (batch k+1) have landed
+    if (base + 32 < n) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+#endif
+    uint32_t m = m_c;
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t p = __shfl_sync(0xFFFFFFFFu, pid_c, j);
+      const uint32_t fl = __shfl_sync(0xFFFFFFFFu, fl_c, j);
+      if (fl & PF_FAST) {
+        const float4* S = my_buf + (buf * 32 + j) * 5;
+        if (fl & PF_DEPTH_MASK) shade_fast<true, true>(S, a.exts + p, fl, fx, fy, px);
+        else shade_fast<false, true>(S, a.exts + p, fl, fx, fy, px);
+      } else {
+        px = shade_prim(&a, a.prims + p, ix, iy, px);
+      }
+    }
+    __syncwarp();  // every lane is done reading this buffer before the next round's copies may land in it
+    pid_c = pid_n; fl_c = fl_n; m_c = m_n; staged_c = staged_n;
+  }
+
+#endif
 
   if (valid) {
     const uint32_t out = (__float_as_uint(px.r) & 255u) | ((__float_as_uint(px.g) & 255u) << 8) |

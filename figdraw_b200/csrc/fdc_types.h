@@ -21,6 +21,7 @@ constexpr int kChunk = 512;        // primitives per coarse-binning chunk (16 wa
 constexpr int kMaxMaskDepth = 8;   // texture-mask nesting the tile kernel keeps per pixel (GL: unbounded)
 constexpr int kAtlasMargin = 4;    // glcontext.nim:257
 constexpr int kMaxAtlasLevels = 14;
+constexpr int kPrimFastBytes = 80; // q0..q4
 constexpr uint64_t kRectKey = 0x7265637472656374ull;  // stands for hash("rect"), glcontext.nim:966
 
 // Prim.mode_flags layout
@@ -43,11 +44,12 @@ constexpr uint32_t PF_INNER_EMPTY = 1u << 22;   // ... or exactly 0 (interior of
 constexpr uint32_t PF_VISIT_FULL = 1u << 23;    // shade kernel only: the warp's block lies inside the inner rect
 constexpr uint32_t PF_EMPTY = 1u << 31;         // dropped (early-out or empty clipped bbox)
 
-// 128-byte shading record, eight 16-byte quads q0..q7.
+// 128-byte shading record, eight 16-byte quads q0..q7.  q0..q4 (80 bytes) are everything the shade kernel's fast path
+// reads; they are the part each warp stages into shared memory with one bulk (TMA) copy per primitive.
 struct alignas(16) Prim {
-  // q0: quad-local (s,t) in [0,1] from the integer pixel index: s = x*su + ou, t = y*sv + ov (axis aligned).
-  //     PF_GENERAL: su's bits hold the QuadGeom index.
-  float su, ou, sv, ov;
+  // q0: SDF modes:   SDF-space position from the pixel index: p.x = x*u0 + du ; -p.y = y*v0 + dv
+  //     atlas modes: texel mapping tu = s*du + u0, tv = t*dv + v0 (level-0 texels, already minus 0.5)
+  float u0, du, v0, dv;
   // q1: sdfParams (quadHalf.xy, shapeHalf.xy | inset offset | bezier p0 | (atlasSize, strokeW))
   float qhx, qhy, p2, p3;
   // q2: sdfRadii (TR,BR,TL,BL | packed elliptical | bezier p1,p2)
@@ -56,15 +58,15 @@ struct alignas(16) Prim {
   float factor, spread, aa, k;
   // q4: vertex colours BL, BR, TR, TL packed RGBA8; PF_SOLID: the colour as four floats 0..255 (bit patterns)
   uint32_t c[4];
-  // q5: 3-stop colours and the occluder inner rect [ix0,ix1) x [iy0,iy1) (pixels)
+  // q5: 3-stop colours and the inner rect [ix0,ix1) x [iy0,iy1) (pixels)
   uint32_t c_mid, c_stop;
   int16_t ix0, iy0, ix1, iy1;
-  // q6: clipped bin bbox [bx0,bx1) x [by0,by1) (pixels), flags, aux: rect mask index+1 (low 16) | subpixel shift*65535 (high 16)
+  // q6: clipped bin bbox [bx0,bx1) x [by0,by1) (pixels), flags, aux: rect mask index+1 (low 16)
   int16_t bx0, by0, bx1, by1;
   uint32_t mode_flags, aux;
-  // q7: atlas modes: texel mapping tu = s*du + u0, tv = t*dv + v0 (level-0 texels, already minus 0.5)
-  //     SDF modes:   SDF-space position from the pixel index: p.x = x*u0 + du ; -p.y = y*v0 + dv
-  float u0, du, v0, dv;
+  // q7: quad-local (s,t) in [0,1] from the integer pixel index: s = x*su + ou, t = y*sv + ov (axis aligned).
+  //     PF_GENERAL: su's bits hold the QuadGeom index.
+  float su, ou, sv, ov;
 };
 static_assert(sizeof(Prim) == 128, "Prim must be 128 bytes");
 

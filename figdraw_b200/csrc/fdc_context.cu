@@ -242,10 +242,13 @@ struct fdc_ctx {
   DevBuf<PrimExt> d_exts;
   DevBuf<uint32_t> d_prim_call;
   DevBuf<uint8_t> d_warp_counts;
-  DevBuf<uint32_t> d_chunk_counts, d_cbin_start, d_coarse_list, d_tile_start, d_tile_count, d_tile_list, d_counters;
+  DevBuf<uint32_t> d_chunk_counts, d_cbin_start, d_coarse_list, d_tile_start, d_tile_count, d_counters;
+  DevBuf<TileEntry> d_tile_list;
   DevBuf<uint8_t> d_fb, d_backdrop, d_temp;
   uint8_t* ext_fb = nullptr;
   DevBuf<uint8_t*> d_peers;
+  DevBuf<unsigned long long> d_stats;
+  bool want_stats = false;
   int n_peers = 0;
   size_t fb_bytes = 0;
 
@@ -712,6 +715,7 @@ int execute_frame(fdc_ctx* ctx, bool upload) {
       sa.load_dst = (si > 0 || !ctx->clear) ? 1 : 0;
       sa.clear_rgba8 = ctx->clear_rgba8;
       const bool last = si + 1 == ctx->segments.size();
+      sa.stats = ctx->want_stats ? ctx->d_stats.p : nullptr;
       sa.peers = (last && ctx->n_peers > 0) ? ctx->d_peers.p : nullptr;
       sa.n_peers = (last && ctx->n_peers > 0) ? ctx->n_peers : 0;
       launch_shade(sa, st);
@@ -1380,6 +1384,23 @@ int fdc_get_frame_stats(fdc_ctx* ctx, fdc_frame_stats* out) {
   return FDC_OK;
 }
 
+int fdc_debug_shade_stats(fdc_ctx* ctx, uint64_t out[8]) {
+  if (!ctx || !out) return FDC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc = resolve_frame(ctx);
+  if (rc) return rc;
+  if (!ctx->have_frame) return ctx->fail(FDC_ERR_STATE, "no completed frame");
+  CK(ctx->d_stats.reserve(8));
+  CK(cudaMemsetAsync(ctx->d_stats.p, 0, 64, ctx->stream));
+  ctx->want_stats = true;
+  rc = execute_frame(ctx, false);
+  ctx->want_stats = false;
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, ctx->d_stats.p, 64, cudaMemcpyDeviceToHost));
+  return FDC_OK;
+}
+
 int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t offsets_cap, uint32_t* entries, size_t entries_cap,
                    size_t* n_offsets, size_t* n_entries) {
   if (!ctx) return FDC_ERR_INVALID;
@@ -1402,8 +1423,8 @@ int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t off
   CK(cudaMemcpy(start.data(), ctx->d_tile_start.p, n_tiles * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(count.data(), ctx->d_tile_count.p, n_tiles * 4, cudaMemcpyDeviceToHost));
   if (s.count) CK(cudaMemcpy(calls.data(), ctx->d_prim_call.p + s.first, (size_t)s.count * 4, cudaMemcpyDeviceToHost));
-  std::vector<uint32_t> list(std::max<uint32_t>(c[0], 1));
-  if (c[0]) CK(cudaMemcpy(list.data(), ctx->d_tile_list.p, (size_t)c[0] * 4, cudaMemcpyDeviceToHost));
+  std::vector<TileEntry> list(std::max<uint32_t>(c[0], 1));
+  if (c[0]) CK(cudaMemcpy(list.data(), ctx->d_tile_list.p, (size_t)c[0] * sizeof(TileEntry), cudaMemcpyDeviceToHost));
   size_t total = 0;
   const int ty0 = ctx->frame.ty0, ty1 = ctx->frame.ty1, tx_n = ctx->frame.tiles_x;
   for (int ty = ty0; ty < ty1; ty++)
@@ -1417,7 +1438,7 @@ int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t off
     tile_offsets[t] = (uint32_t)at;
     const int ty = (int)(t / tx_n);
     if (ty < ty0 || ty >= ty1) continue;
-    for (uint32_t k = 0; k < count[t]; k++) entries[at++] = calls[list[start[t] + k] & 0x7FFFFFFFu];
+    for (uint32_t k = 0; k < count[t]; k++) entries[at++] = calls[list[start[t] + k].pid];
   }
   tile_offsets[n_tiles] = (uint32_t)at;
   return FDC_OK;

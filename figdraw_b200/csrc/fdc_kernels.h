@@ -29,7 +29,7 @@ struct BinBuffers {
   uint32_t coarse_cap;
   uint32_t* tile_start;    // [tiles_x * tiles_y]
   uint32_t* tile_count;    // [tiles_x * tiles_y]
-  uint32_t* tile_list;     // [tile_cap]
+  TileEntry* tile_list;    // [tile_cap]
   uint32_t tile_cap;
   uint32_t* counters;      // [4]: 0 tile cursor, 1 overflow flags, 2 coarse total, 3 tile total
 };
@@ -43,7 +43,7 @@ struct ShadeArgs {
   const RectMaskRec* rectmasks;
   const uint32_t* tile_start;
   const uint32_t* tile_count;
-  const uint32_t* tile_list;
+  const TileEntry* tile_list;
   const uint32_t* counters;  // overflow flag: kernel leaves the frame untouched when set
   uint8_t* fb;               // RGBA8 W*H, top-left origin
   const uint8_t* backdrop;   // RGBA8 W*H (blurred copy for sdfModeBackdropBlur) or nullptr
@@ -51,6 +51,7 @@ struct ShadeArgs {
   FrameView frame;
   int load_dst;              // 0: start from clear colour; 1: read fb
   uint32_t clear_rgba8;
+  unsigned long long* stats; // optional [8] debug counters (nullptr in production): visits partial/full/slow, entries, occl steps
   uint8_t* const* peers;     // optional peer framebuffers (device array of n_peers pointers) or nullptr
   int n_peers;
 };

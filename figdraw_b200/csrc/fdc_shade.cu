@@ -24,15 +24,8 @@
 #ifndef FDC_SHADE_MIN_BLOCKS
 #define FDC_SHADE_MIN_BLOCKS 4
 #endif
-#ifndef FDC_STAGE
-// How a warp gets at the records of the primitives it shades:
-//   0  uniform-address loads from global memory (L1-resident: 93 % hit rate)          <- default, measured fastest
-//   1  staged into per-warp shared memory with 16-byte cp.async, one batch ahead
-//   2  staged with one cp.async.bulk (TMA) per primitive + mbarrier, one batch ahead
-// profiles/r01_shade_staging.md has the measurements (0.90 / 1.03 / 1.07 ms per cfg5 4K frame).
-#define FDC_STAGE 0
-#endif
-#define FDC_STAGE_TMA (FDC_STAGE == 2)
+// (r01: staging primitive records into shared memory with cp.async or per-record cp.async.bulk/TMA + mbarrier was
+// built and measured slower than L1-resident uniform loads -- profiles/r01_shade_staging.md, commit 4cc6a20.)
 
 namespace fdc {
 
@@ -58,27 +51,6 @@ __device__ __forceinline__ float fast_ex2(float x) {
   return r;
 }
 __device__ __forceinline__ float len2(float x, float y) { return fast_sqrt(fmaf(x, x, y * y)); }
-
-// ---- TMA (bulk async copy) + mbarrier plumbing, one barrier per warp and buffer
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\t"
-      "DONE:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
 
 // atlas.frag:51-69
 __device__ __forceinline__ float sd_rounded_box(float px, float py, float bx, float by, float r0, float r1, float r2, float r3) {
@@ -350,23 +322,19 @@ __device__ __forceinline__ void blend(Pixel& px, float sr, float sg, float sb, f
 
 // Hot path: axis-aligned, circular corners, ClipAA / AnnularAA / DropShadow, content (not a mask write), no rect mask.
 // PF_VISIT_FULL in `flags`: the warp's whole block lies in the primitive's inner rect where coverage is exactly 1.
-template <bool kSmem>
-__device__ __forceinline__ float4 ldq(const float4* p) {
-  if (kSmem) return *p;
-  return __ldg(p);
-}
-
-template <bool kMasked, bool kSmem>
-__device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const PrimExt* __restrict__ E, uint32_t flags, float fx,
-                                           float fy, Pixel& px) {
-  // S: q0..q4 of the primitive -- in global memory (all lanes load the same address), or staged in shared memory
+// Hot path: axis-aligned, circular corners, ClipAA / AnnularAA / DropShadow, content (not a mask write), no rect mask.
+// `info` is the TileEntry word; `full`: the warp's whole block lies in the primitive's inner rect (coverage exactly 1).
+template <bool kMasked>
+__device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const PrimExt* __restrict__ E, uint32_t info, bool full,
+                                           float fx, float fy, Pixel& px) {
+  // S: q0..q4 of the primitive in global memory; all lanes load the same address (L1-resident, one transaction)
   float4 col;
-  if (flags & PF_SOLID) {
-    col = ldq<kSmem>(S + 4);
+  if (info & TE_SOLID) {
+    col = __ldg(S + 4);
   } else {
     const float4* X = reinterpret_cast<const float4*>(E);
     const float4 a0 = __ldg(X + 1), d0 = __ldg(X + 2), a1 = __ldg(X + 3);
-    if (flags & PF_FILLMODE_MASK) {
+    if (info & TE_GRAD3) {
       const float4 e0 = __ldg(X + 0), d1 = __ldg(X + 4);
       const float tt = sat(fmaf(fx, e0.x, fmaf(fy, e0.y, e0.z)));
       const bool lo = tt <= e0.w;
@@ -381,15 +349,15 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
       col.w = fmaf(d0.w, fx, fmaf(a1.w, fy, a0.w));
     }
   }
-  if ((flags & (PF_VISIT_FULL | PF_OCCLUDER)) == (PF_VISIT_FULL | PF_OCCLUDER)) {
+  if (full && (info & TE_OCCLUDER)) {
     // opaque, coverage exactly 1 on the whole block: dst*(1-1) vanishes, the store is round(src) whatever dst was.
     // (Earlier primitives were skipped for this block, so the result must not depend on dst even in the last ulp.)
     px.r = col.x + kBias; px.g = col.y + kBias; px.b = col.z + kBias; px.a = 255.0f + kBias;
     return;
   }
   float sa = col.w * (1.0f / 255.0f);
-  if (!(flags & PF_VISIT_FULL)) {
-    const float4 q0 = ldq<kSmem>(S + 0), q1 = ldq<kSmem>(S + 1), q2 = ldq<kSmem>(S + 2), q3 = ldq<kSmem>(S + 3);
+  if (!full) {
+    const float4 q0 = __ldg(S + 0), q1 = __ldg(S + 1), q2 = __ldg(S + 2), q3 = __ldg(S + 3);
     const float ppx = fmaf(fx, q0.x, q0.y), ppy = fmaf(fy, q0.z, q0.w);  // (p.x, -p.y)
     const float apx = fabsf(ppx), apy = fabsf(ppy);
     const bool inside = apx < q1.x && apy < q1.y;  // pixel centre inside the ceil'd quad
@@ -397,12 +365,12 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
     const float qx = apx - q1.z + rr, qy = apy - q1.w + rr;
     const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
     const float dist = fminf(fmaxf(qx, qy), 0.0f) + fast_sqrt(fmaf(mx, mx, my * my)) - rr;
-    const uint32_t mode = flags & PF_MODE_MASK;
+    const uint32_t kind = (info >> TE_KIND_SHIFT) & 3u;
     float cov;
-    if (mode == FDC_SDF_DROP_SHADOW) {  // sd > 0 ? exp(-.5 (sd/sigma)^2) : 1
+    if (kind == 2u) {  // DropShadow: sd > 0 ? exp(-.5 (sd/sigma)^2) : 1
       const float sd = fmaxf(dist - q3.y, 0.0f);
       cov = fast_ex2(q3.w * sd * sd);
-    } else if (mode == FDC_SDF_CLIP_AA) {
+    } else if (kind == 0u) {  // ClipAA
       cov = sat(fmaf(-q3.z, dist, 0.5f));
     } else {  // AnnularAA
       const float f = q3.x * 0.5f;
@@ -410,7 +378,7 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
     }
     sa = inside ? sa * cov : 0.0f;
   }
-  if (kMasked) sa *= mask_get(px, (int)((flags & PF_DEPTH_MASK) >> PF_DEPTH_SHIFT)) * (1.0f / 255.0f);
+  if (kMasked) sa *= mask_get(px, (int)((info >> TE_DEPTH_SHIFT) & 15u)) * (1.0f / 255.0f);
   blend(px, col.x, col.y, col.z, sa);
 }
 
@@ -589,200 +557,112 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
 
 }  // namespace
 
+// One CTA owns kTilesPerCta consecutive tiles = 8*kTilesPerCta blocks of 8x4 pixels.  Its 8 warps pull blocks from a
+// shared-memory counter instead of being pinned to one block of one tile: a warp that finishes a cheap block moves
+// on immediately (no intra-CTA tail: the slowest block of a tile used to hold 7 idle warps' registers), while the
+// warps of a CTA still work on neighbouring blocks of the same tiles at the same time, so the primitive records
+// they load stay shared in L1.
+constexpr int kTilesPerCta = 8;
+
 __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ ShadeArgs a) {
-#if FDC_STAGE != 0
-  __shared__ __align__(128) float4 s_prims[8][2][32 * 5];  // per warp, double buffered: q0..q4 of up to 32 primitives
-#endif
-#if FDC_STAGE == 2
-  __shared__ __align__(8) uint64_t s_bar[8][2];
-#endif
+  __shared__ uint32_t s_next;
   if (a.counters[1] != 0) return;  // a bin list overflowed: host regrows and replays the frame
-#if FDC_STAGE == 2
-  if (threadIdx.x < 16) mbar_init(&s_bar[threadIdx.x >> 1][threadIdx.x & 1], 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (threadIdx.x == 0) s_next = 0;
   __syncthreads();
-#endif
   const FrameView& f = a.frame;
-  const int tile = blockIdx.x;
-  const int tx = tile % f.tiles_x, ty = f.ty0 + tile / f.tiles_x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wx0 = tx * kTileW + (warp & 1) * 8, wy0 = ty * kTileH + (warp >> 1) * 4;
-  const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
-  const bool valid = ix < f.W && iy < f.H;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = f.tiles_x * (f.ty1 - f.ty0);
+  const int tile0 = blockIdx.x * kTilesPerCta;
+  const uint32_t n_blocks = (uint32_t)min(kTilesPerCta, n_tiles - tile0) * 8u;
   uint32_t* fb32 = reinterpret_cast<uint32_t*>(a.fb);
-  const float fx = (float)ix, fy = (float)iy;
 
-  Pixel px;
-  {
-    uint32_t c = a.clear_rgba8;
-    if (a.load_dst && valid) c = fb32[(size_t)iy * f.W + ix];
-    px.r = __uint_as_float(kBiasBits | (c & 255u));
-    px.g = __uint_as_float(kBiasBits | ((c >> 8) & 255u));
-    px.b = __uint_as_float(kBiasBits | ((c >> 16) & 255u));
-    px.a = __uint_as_float(kBiasBits | (c >> 24));
-    px.mlo = px.mhi = 0;
-  }
+  for (;;) {
+    uint32_t blk = 0;
+    if (lane == 0) blk = atomicAdd(&s_next, 1u);
+    blk = __shfl_sync(0xFFFFFFFFu, blk, 0);
+    if (blk >= n_blocks) break;
+    const int tile = tile0 + (int)(blk >> 3), sub = (int)(blk & 7u);
+    const int tx = tile % f.tiles_x, ty = f.ty0 + tile / f.tiles_x;
+    const int wx0 = tx * kTileW + (sub & 1) * 8, wy0 = ty * kTileH + (sub >> 1) * 4;
+    const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
+    const bool valid = ix < f.W && iy < f.H;
+    const float fx = (float)ix, fy = (float)iy;
 
-  const uint32_t n = a.tile_count[ty * f.tiles_x + tx];
-  const uint32_t* __restrict__ list = a.tile_list + a.tile_start[ty * f.tiles_x + tx];
-  // block rect clipped to the frame
-  const int wx1 = min(wx0 + 8, f.W), wy1 = min(wy0 + 4, f.H);
+    Pixel px;
+    {
+      uint32_t c = a.clear_rgba8;
+      if (a.load_dst && valid) c = fb32[(size_t)iy * f.W + ix];
+      px.r = __uint_as_float(kBiasBits | (c & 255u));
+      px.g = __uint_as_float(kBiasBits | ((c >> 8) & 255u));
+      px.b = __uint_as_float(kBiasBits | ((c >> 16) & 255u));
+      px.a = __uint_as_float(kBiasBits | (c >> 24));
+      px.mlo = px.mhi = 0;
+    }
 
-  // Occlusion: find the last primitive whose opaque inner rect covers this warp's whole block; nothing before
-  // it can influence these pixels.
-  uint32_t start = 0;
-  if (wx0 < wx1 && wy0 < wy1) {
-    for (int base = (int)n - 1; base >= 0; base -= 32) {
-      const int idx = base - lane;
-      bool occ = false;
-      if (idx >= 0) {
-        const uint32_t e = __ldg(&list[idx]);
-        if (e & 0x80000000u) {  // occluder candidate (flagged by fine_bin_kernel)
-          const Prim* P = a.prims + (e & 0x7FFFFFFFu);
-          const int2 ir = __ldg(reinterpret_cast<const int2*>(P) + 11);
-          const int x0 = (int16_t)(ir.x & 0xFFFF), y0 = (int16_t)(ir.x >> 16), x1 = (int16_t)(ir.y & 0xFFFF), y1 = (int16_t)(ir.y >> 16);
-          occ = x0 <= wx0 && y0 <= wy0 && x1 >= wx1 && y1 >= wy1;
+    const uint32_t n = a.tile_count[ty * f.tiles_x + tx];
+    const uint2* __restrict__ list = reinterpret_cast<const uint2*>(a.tile_list + a.tile_start[ty * f.tiles_x + tx]);
+    // Everything a warp needs to cull is in the 8-byte tile entries (fine_bin_kernel computed it once per tile):
+    // bit `sub` of info = "bbox overlaps my block", bit `8+sub` = "my block lies inside the inner rect".
+    const uint32_t ov_bit = 1u << (TE_OV_SHIFT + sub), full_bit = 1u << (TE_FULL_SHIFT + sub);
+
+    // Occlusion: the last opaque fill whose inner rect covers this whole block makes everything before it
+    // irrelevant for these pixels.  Scan the entries backwards, 32 at a time.
+    uint32_t start = 0;
+    if (wx0 < f.W && wy0 < f.H) {
+      for (int base = (int)n - 1; base >= 0; base -= 32) {
+        const int idx = base - lane;
+        bool occ = false;
+        if (idx >= 0) {
+          const uint32_t info = __ldg(&list[idx]).y;
+          occ = (info & full_bit) && (info & TE_OCCLUDER);
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, occ);
+        if (a.stats && lane == 0) atomicAdd(&a.stats[4], 1ull);
+        if (m) { start = (uint32_t)(base - (__ffs(m) - 1)); break; }
+      }
+    } else {
+      start = n;  // block entirely outside the frame
+    }
+
+    for (uint32_t base = start; base < n; base += 32) {
+      const uint32_t idx = base + lane;
+      uint2 e = make_uint2(0u, 0u);
+      if (idx < n) e = __ldg(&list[idx]);
+      uint32_t m = __ballot_sync(0xFFFFFFFFu, (e.y & ov_bit) != 0u);
+      if (a.stats) {
+        const uint32_t mf = __ballot_sync(0xFFFFFFFFu, (e.y & ov_bit) && (e.y & full_bit));
+        const uint32_t ms = __ballot_sync(0xFFFFFFFFu, (e.y & ov_bit) && !(e.y & TE_FAST));
+        if (lane == 0) {
+          atomicAdd(&a.stats[3], 1ull);
+          atomicAdd(&a.stats[0], (unsigned long long)__popc(m));
+          atomicAdd(&a.stats[1], (unsigned long long)__popc(mf));
+          atomicAdd(&a.stats[2], (unsigned long long)__popc(ms));
         }
       }
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, occ);
-      if (m) { start = (uint32_t)(base - (__ffs(m) - 1)); break; }
-    }
-  } else {
-    start = n;  // block entirely outside the frame
-  }
-
-  // Per-warp software pipeline over batches of 32 list entries:
-  //   classify(batch k+1): every lane loads one primitive's bbox/flags/inner rect and classifies it against the block;
-  //   stage(batch k+1):    every surviving fast primitive is copied (q0..q4, 80 bytes) into this warp's shared-memory
-  //                        buffer by one cp.async.bulk (TMA) per lane, completion counted on the buffer's mbarrier;
-  //   visit(batch k):      wait on batch k's mbarrier, then shade its survivors out of shared memory.
-  // The copies of batch k+1 fly while batch k is being shaded.
-#if FDC_STAGE != 0
-  float4* const my_buf = &s_prims[warp][0][0];
-#endif
-#if FDC_STAGE == 2
-  uint64_t* const my_bar = &s_bar[warp][0];
-#endif
-
-  auto classify = [&](uint32_t base, uint32_t& pid, uint32_t& flags) -> uint32_t {
-    const uint32_t idx = base + lane;
-    pid = 0;
-    flags = 0;
-    int cls = 0;  // 0 culled, 1 shade, 2 shade with full coverage
-    if (idx < n) {
-      pid = __ldg(&list[idx]) & 0x7FFFFFFFu;
-      const Prim* P = a.prims + pid;
-      const int4 q6 = __ldg(reinterpret_cast<const int4*>(P) + 6);
-      flags = (uint32_t)q6.z;
-      const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
-      if (bx0 < wx1 && bx1 > wx0 && by0 < wy1 && by1 > wy0) {
-        cls = 1;
-        if (flags & PF_INNER) {
-          const int2 ir = __ldg(reinterpret_cast<const int2*>(P) + 11);
-          const int x0 = (int16_t)(ir.x & 0xFFFF), y0 = (int16_t)(ir.x >> 16), x1 = (int16_t)(ir.y & 0xFFFF), y1 = (int16_t)(ir.y >> 16);
-          if (x0 <= wx0 && y0 <= wy0 && x1 >= wx1 && y1 >= wy1) cls = (flags & PF_INNER_EMPTY) ? 0 : 2;
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t p = __shfl_sync(0xFFFFFFFFu, e.x, j);
+        const uint32_t info = __shfl_sync(0xFFFFFFFFu, e.y, j);
+        if (info & TE_FAST) {
+          const float4* S = reinterpret_cast<const float4*>(a.prims + p);
+          const bool full = (info & full_bit) != 0u;
+          if (info & (15u << TE_DEPTH_SHIFT)) shade_fast<true>(S, a.exts + p, info, full, fx, fy, px);
+          else shade_fast<false>(S, a.exts + p, info, full, fx, fy, px);
+        } else {
+          px = shade_prim(&a, a.prims + p, ix, iy, px);
         }
       }
-      if (flags & PF_MASK_BEGIN) cls = max(cls, 1);
     }
-    if (cls == 2) flags |= PF_VISIT_FULL;
-    return __ballot_sync(0xFFFFFFFFu, cls != 0);
-  };
-#if FDC_STAGE == 2
-  auto stage = [&](int buf, uint32_t pid, uint32_t flags, uint32_t m) -> bool {
-    const bool mine = ((m >> lane) & 1u) && (flags & PF_FAST);
-    const uint32_t fm = __ballot_sync(0xFFFFFFFFu, mine);
-    if (fm == 0) return false;
-    if (lane == 0) mbar_arrive_expect_tx(my_bar + buf, (uint32_t)kPrimFastBytes * __popc(fm));
-    if (mine) bulk_copy_g2s(my_buf + (buf * 32 + lane) * 5, a.prims + pid, kPrimFastBytes, my_bar + buf);
-    return true;
-  };
-#elif FDC_STAGE == 1
-  // LDGSTS variant: five 16-byte cp.async per surviving lane, one commit group per batch
-  auto stage = [&](int buf, uint32_t pid, uint32_t flags, uint32_t m) -> bool {
-    if (((m >> lane) & 1u) && (flags & PF_FAST)) {
-      const uint32_t dst = smem_u32(my_buf + (buf * 32 + lane) * 5);
-      const char* src = reinterpret_cast<const char*>(a.prims + pid);
-#pragma unroll
-      for (int k = 0; k < 5; k++)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * k), "l"(src + 16 * k) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    return true;
-  };
-#endif
 
-#if FDC_STAGE == 0
-  for (uint32_t base = start; base < n; base += 32) {
-    uint32_t pid_c, fl_c;
-    uint32_t m = classify(base, pid_c, fl_c);
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      const uint32_t p = __shfl_sync(0xFFFFFFFFu, pid_c, j);
-      const uint32_t fl = __shfl_sync(0xFFFFFFFFu, fl_c, j);
-      if (fl & PF_FAST) {
-        const float4* S = reinterpret_cast<const float4*>(a.prims + p);
-        if (fl & PF_DEPTH_MASK) shade_fast<true, false>(S, a.exts + p, fl, fx, fy, px);
-        else shade_fast<false, false>(S, a.exts + p, fl, fx, fy, px);
-      } else {
-        px = shade_prim(&a, a.prims + p, ix, iy, px);
+    if (valid) {
+      const uint32_t out = (__float_as_uint(px.r) & 255u) | ((__float_as_uint(px.g) & 255u) << 8) |
+                           ((__float_as_uint(px.b) & 255u) << 16) | ((__float_as_uint(px.a) & 255u) << 24);
+      fb32[(size_t)iy * f.W + ix] = out;
+      for (int k = 0; k < a.n_peers; k++) {
+        uint32_t* peer = reinterpret_cast<uint32_t*>(a.peers[k]);
+        if (peer && peer != fb32) peer[(size_t)iy * f.W + ix] = out;
       }
-    }
-  }
-#else
-  uint32_t pid_c = 0, fl_c = 0, m_c = 0, phases = 0;
-  bool staged_c = false;
-  if (start < n) {
-    m_c = classify(start, pid_c, fl_c);
-    staged_c = stage(0, pid_c, fl_c, m_c);
-  }
-  int buf = 0;
-  for (uint32_t base = start; base < n; base += 32, buf ^= 1) {
-    uint32_t pid_n = 0, fl_n = 0, m_n = 0;
-    bool staged_n = false;
-    if (base + 32 < n) {
-      m_n = classify(base + 32, pid_n, fl_n);
-      staged_n = stage(buf ^ 1, pid_n, fl_n, m_n);
-    }
-#if FDC_STAGE_TMA
-    if (staged_c) {
-      mbar_wait(my_bar + buf, (phases >> buf) & 1u);
-      phases ^= 1u << buf;
-    }
-#else
-    // all but the newest group (batch k+1) have landed
-    if (base + 32 < n) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-#endif
-    uint32_t m = m_c;
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      const uint32_t p = __shfl_sync(0xFFFFFFFFu, pid_c, j);
-      const uint32_t fl = __shfl_sync(0xFFFFFFFFu, fl_c, j);
-      if (fl & PF_FAST) {
-        const float4* S = my_buf + (buf * 32 + j) * 5;
-        if (fl & PF_DEPTH_MASK) shade_fast<true, true>(S, a.exts + p, fl, fx, fy, px);
-        else shade_fast<false, true>(S, a.exts + p, fl, fx, fy, px);
-      } else {
-        px = shade_prim(&a, a.prims + p, ix, iy, px);
-      }
-    }
-    __syncwarp();  // every lane is done reading this buffer before the next round's copies may land in it
-    pid_c = pid_n; fl_c = fl_n; m_c = m_n; staged_c = staged_n;
-  }
-
-#endif
-
-  if (valid) {
-    const uint32_t out = (__float_as_uint(px.r) & 255u) | ((__float_as_uint(px.g) & 255u) << 8) |
-                         ((__float_as_uint(px.b) & 255u) << 16) | ((__float_as_uint(px.a) & 255u) << 24);
-    fb32[(size_t)iy * f.W + ix] = out;
-    for (int k = 0; k < a.n_peers; k++) {
-      uint32_t* peer = reinterpret_cast<uint32_t*>(a.peers[k]);
-      if (peer && peer != fb32) peer[(size_t)iy * f.W + ix] = out;
     }
   }
 }
@@ -790,7 +670,7 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
 void launch_shade(const ShadeArgs& a, cudaStream_t stream) {
   const int n_tiles = a.frame.tiles_x * (a.frame.ty1 - a.frame.ty0);
   if (n_tiles <= 0) return;
-  shade_kernel<<<n_tiles, 256, 0, stream>>>(a);
+  shade_kernel<<<(n_tiles + kTilesPerCta - 1) / kTilesPerCta, 256, 0, stream>>>(a);
 }
 
 }  // namespace fdc

@@ -44,6 +44,21 @@ constexpr uint32_t PF_INNER_EMPTY = 1u << 22;   // ... or exactly 0 (interior of
 constexpr uint32_t PF_VISIT_FULL = 1u << 23;    // shade kernel only: the warp's block lies inside the inner rect
 constexpr uint32_t PF_EMPTY = 1u << 31;         // dropped (early-out or empty clipped bbox)
 
+// Tile-list entry (8 bytes): .x = primitive index (bit 31: unused), .y = everything the shade kernel needs to decide
+// what each of the tile's 8 warps (8x4-pixel blocks; block = row*2 + col) does with the primitive, precomputed once
+// per (tile, primitive) by fine_bin_kernel instead of 8 times per pair by the shading warps.
+constexpr uint32_t TE_OV_SHIFT = 0;      // bits 0..7 : the primitive's clipped bbox overlaps block b
+constexpr uint32_t TE_FULL_SHIFT = 8;    // bits 8..15: block b lies inside the inner rect (coverage exactly 1)
+constexpr uint32_t TE_FAST = 1u << 16;   // PF_FAST
+constexpr uint32_t TE_SOLID = 1u << 17;  // PF_SOLID
+constexpr uint32_t TE_GRAD3 = 1u << 18;  // 3-stop fill (fill mode != 0)
+constexpr uint32_t TE_KIND_SHIFT = 19;   // 2 bits: 0 ClipAA, 1 AnnularAA, 2 DropShadow (fast primitives)
+constexpr uint32_t TE_OCCLUDER = 1u << 21;
+constexpr uint32_t TE_DEPTH_SHIFT = 24;  // 4 bits: texture-mask level read by content
+struct alignas(8) TileEntry {
+  uint32_t pid, info;
+};
+
 // 128-byte shading record, eight 16-byte quads q0..q7.  q0..q4 (80 bytes) are everything the shade kernel's fast path
 // reads; they are the part each warp stages into shared memory with one bulk (TMA) copy per primitive.
 struct alignas(16) Prim {

@@ -271,6 +271,11 @@ class CudaContext(BackendContext):
                                           ctypes.byref(n_off), ctypes.byref(n_ent)))
         return off, ent[: n_ent.value]
 
+    def shadeStats(self):
+        out = (ctypes.c_uint64 * 8)()
+        self._ck(self._lib.fdc_debug_shade_stats(self._h, out))
+        return {"visits": out[0], "visits_full": out[1], "visits_general": out[2], "list_steps": out[3], "occl_steps": out[4]}
+
     def bandRows(self) -> Tuple[int, int]:
         y0, y1 = ctypes.c_int(0), ctypes.c_int(0)
         self._ck(self._lib.fdc_band_rows(self._h, ctypes.byref(y0), ctypes.byref(y1)))

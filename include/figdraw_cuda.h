@@ -252,6 +252,10 @@ int fdc_get_frame_stats(fdc_ctx* ctx, fdc_frame_stats* out);
 int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t offsets_cap, uint32_t* entries,
                    size_t entries_cap, size_t* n_offsets, size_t* n_entries);
 
+/* Replays the last frame with counters enabled: out[0] primitive visits by shading warps, [1] of which with full
+ * coverage, [2] of which on the general path, [3] 32-entry list steps walked, [4] occlusion-scan steps. */
+int fdc_debug_shade_stats(fdc_ctx* ctx, uint64_t out[8]);
+
 #ifdef __cplusplus
 }
 #endif

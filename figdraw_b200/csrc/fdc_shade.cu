@@ -234,7 +234,7 @@ struct GeneralHit {
   float s, t;
   float dsdx, dsdy, dtdx, dtdy;
 };
-__device__ GeneralHit general_quad(const QuadGeom& g, int ix, int iy) {
+__device__ GeneralHit general_quad(const QuadGeom& g, int ix, int iy, int which) {
   GeneralHit h;
   h.inside = false;
   h.s = h.t = 0.0f;
@@ -242,13 +242,13 @@ __device__ GeneralHit general_quad(const QuadGeom& g, int ix, int iy) {
   const float vs[4] = {0.0f, 1.0f, 1.0f, 0.0f}, vt[4] = {1.0f, 1.0f, 0.0f, 0.0f};
   const int tri[2][3] = {{3, 0, 1}, {2, 3, 1}};
   const long long px2 = 2ll * ix + 1, py2 = 2ll * iy + 1;
-#pragma unroll
-  for (int k = 0; k < 2; k++) {
+  {
+    const int k = which;
     const int ia = tri[k][0], ib = tri[k][1], ic = tri[k][2];
     const long long ex[3] = {2ll * g.vx[ia], 2ll * g.vx[ib], 2ll * g.vx[ic]};
     const long long ey[3] = {2ll * g.vy[ia], 2ll * g.vy[ib], 2ll * g.vy[ic]};
     const long long area = (ex[1] - ex[0]) * (ey[2] - ey[0]) - (ey[1] - ey[0]) * (ex[2] - ex[0]);
-    if (area == 0) continue;
+    if (area == 0) return h;
     const long long sgn = area > 0 ? 1 : -1;
     bool in = true;
 #pragma unroll
@@ -258,7 +258,7 @@ __device__ GeneralHit general_quad(const QuadGeom& g, int ix, int iy) {
       const long long v = ea * (px2 - ex[e]) + eb * (py2 - ey[e]);
       if (v < 0 || (v == 0 && !(ea > 0 || (ea == 0 && eb > 0)))) in = false;
     }
-    if (!in) continue;
+    if (!in) return h;
     const float Ax = (float)g.vx[ia], Ay = (float)g.vy[ia], Bx = (float)g.vx[ib], By = (float)g.vy[ib];
     const float Cx = (float)g.vx[ic], Cy = (float)g.vy[ic];
     const float inv_area = 1.0f / ((Bx - Ax) * (Cy - Ay) - (By - Ay) * (Cx - Ax));
@@ -271,15 +271,13 @@ __device__ GeneralHit general_quad(const QuadGeom& g, int ix, int iy) {
     h.s = vs[ia] + (rx * h.dsdx + ry * h.dsdy);
     h.t = vt[ia] + (rx * h.dtdx + ry * h.dtdy);
     h.inside = true;
-    break;
   }
   return h;
 }
 
 // Vertex colours BL,BR,TR,TL interpolated per triangle: (TL,BL,BR) where t >= s, (TR,TL,BR) otherwise.
-__device__ __forceinline__ float4 vertex_color(const uint4 c, float s, float t) {
+__device__ __forceinline__ float4 vertex_color(const uint4 c, float s, float t, bool lower) {
   const float4 bl = unpack255(c.x), br = unpack255(c.y), tr = unpack255(c.z), tl = unpack255(c.w);
-  const bool lower = t >= s;
   float4 o;
   o.x = lower ? fmaf(bl.x - tl.x, t, fmaf(br.x - bl.x, s, tl.x)) : fmaf(br.x - tr.x, t, fmaf(tr.x - tl.x, s, tl.x));
   o.y = lower ? fmaf(bl.y - tl.y, t, fmaf(br.y - bl.y, s, tl.y)) : fmaf(br.y - tr.y, t, fmaf(tr.y - tl.y, s, tl.y));
@@ -393,14 +391,19 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
   if (flags & PF_MASK_BEGIN) mask_set(px, depth, 0.0f);  // glClear(0) of the mask level, glcontext.nim:1901-1902
 
   const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
-  bool inside = ix >= bx0 && ix < bx1 && iy >= by0 && iy < by1;
+  const bool in_box = ix >= bx0 && ix < bx1 && iy >= by0 && iy < by1;
   const float4 q0 = __ldg(Q + 7);  // (su, ou, sv, ov)
+  // A rotated / arbitrary quad is two triangles (3,0,1),(2,3,1) drawn one after the other (glcontext.nim:418-429): a
+  // pixel inside both (folded quads) is shaded and blended twice, exactly as GL does.
+  const int n_tri = (flags & PF_GENERAL) ? 2 : 1;
+  for (int tri = 0; tri < n_tri; tri++) {
+  bool inside = in_box;
   float s, t;
   float dsdx = q0.x, dsdy = 0.0f, dtdx = 0.0f, dtdy = q0.z;
   if (flags & PF_GENERAL) {
     GeneralHit h;
     h.inside = false;
-    if (inside) h = general_quad(a.geoms[__float_as_uint(q0.x)], ix, iy);
+    if (inside) h = general_quad(a.geoms[__float_as_uint(q0.x)], ix, iy, tri);
     inside = inside && h.inside;
     s = h.s; t = h.t;
     dsdx = h.dsdx; dsdy = h.dsdy; dtdx = h.dtdx; dtdy = h.dtdy;
@@ -408,7 +411,7 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
     s = fmaf((float)ix, q0.x, q0.y);
     t = fmaf((float)iy, q0.z, q0.w);
   }
-  if (!__any_sync(0xFFFFFFFFu, inside)) return px;
+  if (!__any_sync(0xFFFFFFFFu, inside)) continue;
 
   const float4 q1 = __ldg(Q + 1), q2 = __ldg(Q + 2), q3 = __ldg(Q + 3);
   const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(P) + 4);
@@ -420,7 +423,7 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
   float4 col;
   if (fill_mode != 0) col = linear3_color(q4.x, q5.x, q5.y, fill_mode, q3.y, s, t);
   else if (flags & PF_SOLID) col = __ldg(Q + 4);
-  else col = vertex_color(q4, s, t);
+  else col = vertex_color(q4, s, t, (flags & PF_GENERAL) ? tri == 0 : t >= s);
 
   // p = (uv - .5) * 2 * quadHalf ; the SDF is evaluated at (p.x, -p.y)
   const float ppx = (s - 0.5f) * 2.0f * q1.x, ppy = (t - 0.5f) * 2.0f * q1.y;
@@ -543,7 +546,7 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
       const float m = mask_get(px, depth);
       mask_set(px, depth, rint255(fmaf(al, 255.0f * al, m * (1.0f - al))));
     }
-    return px;
+    continue;
   }
   float sa = salpha * (1.0f / 255.0f) * cov;
   if (depth > 0) sa *= mask_get(px, depth) * (1.0f / 255.0f);
@@ -552,6 +555,7 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
     sa *= rect_mask_alpha(rm, aa, (float)ix + 0.5f, (float)iy + 0.5f);
   }
   if (inside && sa > 0.0f) blend(px, sr, sg, sb, sa);
+  }  // triangles
   return px;
 }
 

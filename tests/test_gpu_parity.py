@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from figdraw_b200 import scenes
+from figdraw_b200 import scenes_fuzz
 from figdraw_b200 import scenes_synth as ss
 from figdraw_b200.abi import Op
 from figdraw_b200.cuda_context import CudaContext, render_trace
@@ -95,6 +96,22 @@ def test_bin_lists_bit_exact(builder):
         off, ent = ctx.debugBins(seg)
         assert np.array_equal(off, off_ref), f"segment {seg}: tile offsets differ"
         assert np.array_equal(ent, ent_ref), f"segment {seg}: draw order differs"
+    ctx.close()
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_fuzzed_call_streams(seed):
+    """Random streams over every op/mode: rotation, mirroring, nested clips, rect masks, elliptical corners, Beziers,
+    filled quads, minified/flipped images, MSDF strokes, AA changes, backdrop blurs."""
+    tr = scenes_fuzz.random_trace(seed)
+    got, want = check(tr, max_fraction=0.03)
+    ctx = CudaContext(atlasSize=tr.atlas_size)
+    render_trace(tr, ctx)
+    ref = oracle.reference_bins(tr)
+    assert ctx.frameStats().n_segments == len(ref)
+    for seg, (off_ref, ent_ref) in enumerate(ref):
+        off, ent = ctx.debugBins(seg)
+        assert np.array_equal(off, off_ref) and np.array_equal(ent, ent_ref), f"segment {seg}: bins differ"
     ctx.close()
 
 

@@ -62,3 +62,16 @@ def test_reference_spot_pixels():
     assert close(mix[88, 160], (255, 255, 255), 12)
     assert close(mix[88, 204], (56, 168, 88), 12)
     assert close(mix[88, 336], (54, 118, 230), 12)
+
+
+def test_fuzz_streams_are_deterministic_on_the_oracle():
+    from figdraw_b200 import scenes_fuzz
+
+    for seed in (0, 5):
+        tr = scenes_fuzz.random_trace(seed)
+        a = oracle.render_trace(tr, n_threads=1)
+        b = oracle.render_trace(tr, n_threads=5)
+        assert np.array_equal(a, b)
+        c1 = oracle.count_fragments(tr)
+        _img, c2 = oracle.render_trace(tr, want_counts=True)
+        assert np.array_equal(c1, c2)

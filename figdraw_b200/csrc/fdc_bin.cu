@@ -649,27 +649,33 @@ __global__ void __launch_bounds__(256) coarse_scan_kernel(uint32_t* __restrict__
 constexpr int kStage = 1024;
 static_assert(kTileW == 16 && kTileH == 16 && kCoarse == 8, "fine_bin_kernel shifts assume 16x16 tiles, 8x8 tiles per bin");
 
-// bit r (0..3) set when [lo,hi) overlaps rows [y0 + 4r, y0 + 4r + 4)
-__device__ __forceinline__ uint32_t span_bits4(int lo, int hi, int y0) {
-  const int a = max((lo - y0) >> 2, 0), b = min((hi - 1 - y0) >> 2, 3);
-  return b >= a ? (((2u << b) - 1u) & ~((1u << a) - 1u)) : 0u;
+// bits [a..b] of a 32-bit word (empty when b < a)
+__device__ __forceinline__ uint32_t bit_range(int a, int b) {
+  if (b < a) return 0u;
+  const uint32_t hi = b >= 31 ? 0xFFFFFFFFu : ((2u << b) - 1u);
+  return hi & ~((1u << a) - 1u);
 }
-// bit r set when [lo,hi) covers rows [y0 + 4r, min(y0 + 4r + 4, limit))
-__device__ __forceinline__ uint32_t cover_bits4(int lo, int hi, int y0, int limit) {
-  uint32_t m = 0;
-#pragma unroll
-  for (int r = 0; r < 4; r++) {
-    const int b0 = y0 + 4 * r, b1 = min(b0 + 4, limit);
-    if (b0 < b1 && lo <= b0 && hi >= b1) m |= 1u << r;
-  }
-  return m;
+// Blocks of `bs` pixels starting at p0: which of them does [lo,hi) overlap / fully cover (a block's extent is clipped to
+// `limit`, the frame edge, when deciding "covered")?
+__device__ __forceinline__ uint32_t blocks_overlapped(int lo, int hi, int p0, int shift, int nblk) {
+  return bit_range(max((lo - p0) >> shift, 0), min((hi - 1 - p0) >> shift, nblk - 1));
 }
-// rows (4 bits) x cols (2 bits) -> 8 block bits, block = row*2 + col
-__device__ __forceinline__ uint32_t outer8(uint32_t rows, uint32_t cols) {
-  const uint32_t sp = ((rows & 1u) ? 0x03u : 0u) | ((rows & 2u) ? 0x0Cu : 0u) | ((rows & 4u) ? 0x30u : 0u) | ((rows & 8u) ? 0xC0u : 0u);
-  const uint32_t cm = ((cols & 1u) ? 0x55u : 0u) | ((cols & 2u) ? 0xAAu : 0u);
-  return sp & cm;
+__device__ __forceinline__ uint32_t blocks_covered(int lo, int hi, int p0, int shift, int nblk, int limit) {
+  const int bs = 1 << shift;
+  const int a = max((lo - p0 + bs - 1) >> shift, 0);
+  const int b = hi >= limit ? min((limit - 1 - p0) >> shift, nblk - 1) : min(((hi - p0) >> shift) - 1, nblk - 1);
+  return bit_range(a, b);
 }
+// 4 row bits -> each duplicated into a pair (block = row*2 + col)
+__device__ __forceinline__ uint32_t spread_rows(uint32_t r) {
+  uint32_t x = (r | (r << 2)) & 0x33u;
+  x = (x | (x << 1)) & 0x55u;
+  return x * 3u;
+}
+__device__ __forceinline__ uint32_t spread_cols(uint32_t c) { return (c & 1u) * 0x55u | (c >> 1) * 0xAAu; }
+
+constexpr uint32_t kInfoEmptyInner = 1u << 30;  // staging-only markers, stripped before the entry is written
+constexpr uint32_t kInfoBegin = 1u << 31;
 
 __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ prims, FrameView f,
                                                        const uint32_t* __restrict__ cbin_start,
@@ -677,11 +683,12 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
                                                        uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile_count,
                                                        TileEntry* __restrict__ tile_list, uint32_t tile_cap,
                                                        uint32_t* __restrict__ counters) {
+  // per staged coarse entry, computed once: 16 block columns (8 px) and 32 block rows (4 px) of this 128x128-px bin
   __shared__ uint32_t s_pid[kStage];
-  __shared__ uint2 s_box[kStage];    // clipped bbox (bx0|by0<<16, bx1|by1<<16)
-  __shared__ uint2 s_inner[kStage];  // inner rect, same packing
-  __shared__ uint32_t s_flags[kStage];
-  __shared__ uint16_t s_mask[kStage];  // low byte: tile columns, high byte: tile rows
+  __shared__ uint32_t s_cols[kStage];     // overlap bits 0..15 | covered-by-inner bits 16..31
+  __shared__ uint32_t s_rows_ov[kStage];
+  __shared__ uint32_t s_rows_full[kStage];
+  __shared__ uint32_t s_info[kStage];
   __shared__ uint32_t s_cnt[kCoarse * kCoarse];
   __shared__ uint32_t s_base[kCoarse * kCoarse];
   __shared__ uint32_t s_alloc;
@@ -694,7 +701,6 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
   const int tile_x0 = cbx_i * kCoarse, tile_y0 = f.cty0 + cby_i * kCoarse;
   const int px0 = tile_x0 * kTileW, py0 = tile_y0 * kTileH;
   const bool single = end - begin <= (uint32_t)kStage;
-  const int my_ty0 = py0 + warp * kTileH;  // pixel row of this warp's tile row
 
   uint32_t cnt[kCoarse];
 #pragma unroll
@@ -746,69 +752,59 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
         for (uint32_t k = threadIdx.x; k < ns; k += blockDim.x) {
           const uint32_t pid = __ldg(&coarse_list[s0 + k]);
           const int4 q6 = __ldg(reinterpret_cast<const int4*>(&prims[pid]) + 6);
+          const uint32_t fl = (uint32_t)q6.z;
           const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
-          // tile columns / rows of this bin touched by the bbox (the bbox is known to intersect the bin)
-          const int c0 = max((bx0 - px0) >> 4, 0), c1 = min((bx1 - 1 - px0) >> 4, kCoarse - 1);
-          const int r0 = max((by0 - py0) >> 4, 0), r1 = min((by1 - 1 - py0) >> 4, kCoarse - 1);
-          uint32_t cm = 0, rm = 0;
-          if (c1 >= c0 && r1 >= r0) { cm = ((2u << c1) - 1u) & ~((1u << c0) - 1u); rm = ((2u << r1) - 1u) & ~((1u << r0) - 1u); }
-          s_pid[k] = pid;
-          s_mask[k] = (uint16_t)(cm | (rm << 8));
-          s_box[k] = make_uint2((uint32_t)q6.x, (uint32_t)q6.y);
-          s_flags[k] = (uint32_t)q6.z;
-          uint2 inner = make_uint2(0u, 0u);
-          if ((uint32_t)q6.z & PF_INNER) {
+          uint32_t cols = blocks_overlapped(bx0, bx1, px0, 3, 16);
+          uint32_t rows_ov = blocks_overlapped(by0, by1, py0, 2, 32), rows_full = 0;
+          if (fl & PF_INNER) {
             const int2 ir = __ldg(reinterpret_cast<const int2*>(&prims[pid]) + 11);
-            inner = make_uint2((uint32_t)ir.x, (uint32_t)ir.y);
+            const int ix0 = (int16_t)(ir.x & 0xFFFF), iy0 = (int16_t)(ir.x >> 16), ix1 = (int16_t)(ir.y & 0xFFFF), iy1 = (int16_t)(ir.y >> 16);
+            cols |= blocks_covered(ix0, ix1, px0, 3, 16, f.W) << 16;
+            rows_full = blocks_covered(iy0, iy1, py0, 2, 32, f.H);
           }
-          s_inner[k] = inner;
+          const uint32_t mode = fl & PF_MODE_MASK;
+          const uint32_t kind = mode == FDC_SDF_CLIP_AA ? 0u : (mode == FDC_SDF_ANNULAR_AA ? 1u : 2u);
+          uint32_t info = ((fl & PF_FAST) ? TE_FAST : 0u) | ((fl & PF_SOLID) ? TE_SOLID : 0u) |
+                          ((fl & PF_FILLMODE_MASK) ? TE_GRAD3 : 0u) | (kind << TE_KIND_SHIFT) |
+                          ((fl & PF_OCCLUDER) ? TE_OCCLUDER : 0u) | (((fl & PF_DEPTH_MASK) >> PF_DEPTH_SHIFT) << TE_DEPTH_SHIFT);
+          if (fl & PF_INNER_EMPTY) info |= kInfoEmptyInner;
+          if (fl & PF_MASK_BEGIN) info |= kInfoBegin;
+          s_pid[k] = pid;
+          s_cols[k] = cols;
+          s_rows_ov[k] = rows_ov;
+          s_rows_full[k] = rows_full;
+          s_info[k] = info;
         }
         __syncthreads();
       }
       for (uint32_t k0 = 0; k0 < ns; k0 += 32) {
         const uint32_t k = k0 + lane;
-        uint32_t colmask = 0, pid = 0, info_base = 0, row_ov = 0, row_full = 0;
-        int bx0 = 0, bx1 = 0, ix0 = 0, ix1 = 0;
+        uint32_t cols = 0, pid = 0, info = 0, sp_ov = 0, sp_full = 0;
         if (k < ns) {
-          const uint32_t mk = s_mask[k];
-          if ((mk >> (8 + warp)) & 1u) colmask = mk & 255u;
-          pid = s_pid[k];
-          if (pass == 1 && colmask) {
-            const uint2 bb = s_box[k], in = s_inner[k];
-            const uint32_t fl = s_flags[k];
-            bx0 = (int16_t)(bb.x & 0xFFFF); bx1 = (int16_t)(bb.y & 0xFFFF);
-            const int by0 = (int16_t)(bb.x >> 16), by1 = (int16_t)(bb.y >> 16);
-            ix0 = (int16_t)(in.x & 0xFFFF); ix1 = (int16_t)(in.y & 0xFFFF);
-            const int iy0 = (int16_t)(in.x >> 16), iy1 = (int16_t)(in.y >> 16);
-            row_ov = span_bits4(by0, by1, my_ty0);
-            row_full = (fl & PF_INNER) ? cover_bits4(iy0, iy1, my_ty0, f.H) : 0u;
-            if (fl & PF_INNER_EMPTY) row_full |= 0x10u;  // marker: inner means coverage 0
-            const uint32_t mode = fl & PF_MODE_MASK;
-            const uint32_t kind = mode == FDC_SDF_CLIP_AA ? 0u : (mode == FDC_SDF_ANNULAR_AA ? 1u : 2u);
-            info_base = ((fl & PF_FAST) ? TE_FAST : 0u) | ((fl & PF_SOLID) ? TE_SOLID : 0u) |
-                        ((fl & PF_FILLMODE_MASK) ? TE_GRAD3 : 0u) | (kind << TE_KIND_SHIFT) |
-                        ((fl & PF_OCCLUDER) ? TE_OCCLUDER : 0u) |
-                        (((fl & PF_DEPTH_MASK) >> PF_DEPTH_SHIFT) << TE_DEPTH_SHIFT);
-            if (fl & PF_MASK_BEGIN) info_base |= 0x80000000u;  // marker: every block must visit (level reset)
+          const uint32_t r_ov = (s_rows_ov[k] >> (4 * warp)) & 15u;  // my tile row's four block rows
+          if (r_ov) {
+            cols = s_cols[k];
+            pid = s_pid[k];
+            if (pass == 1) {
+              info = s_info[k];
+              sp_ov = spread_rows(r_ov);
+              sp_full = spread_rows((s_rows_full[k] >> (4 * warp)) & 15u);
+            }
           }
         }
 #pragma unroll
         for (int i = 0; i < kCoarse; i++) {
-          const bool hit = (colmask >> i) & 1u;
+          const uint32_t c_ov = (cols >> (2 * i)) & 3u;
+          const bool hit = c_ov != 0u;
           const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
           if (pass == 1 && hit) {
-            const int tx0 = px0 + i * kTileW;
-            // two 8-px block columns of tile column i
-            const uint32_t col_ov = ((bx0 < tx0 + 8 && bx1 > tx0) ? 1u : 0u) | ((bx0 < tx0 + 16 && bx1 > tx0 + 8) ? 2u : 0u);
-            const int e0 = min(tx0 + 8, f.W), e1 = min(tx0 + 16, f.W);
-            const uint32_t col_full = ((tx0 < e0 && ix0 <= tx0 && ix1 >= e0) ? 1u : 0u) |
-                                      ((tx0 + 8 < e1 && ix0 <= tx0 + 8 && ix1 >= e1) ? 2u : 0u);
-            uint32_t ov = outer8(row_ov, col_ov), full = outer8(row_full & 15u, col_full);
-            if (row_full & 0x10u) { ov &= ~full; full = 0; }      // inside an AnnularAA stroke: nothing to shade
-            if (info_base & 0x80000000u) ov = 0xFFu;               // PF_MASK_BEGIN
+            uint32_t ov = sp_ov & spread_cols(c_ov);
+            uint32_t full = sp_full & spread_cols((cols >> (16 + 2 * i)) & 3u);
+            if (info & kInfoEmptyInner) { ov &= ~full; full = 0; }  // inside an AnnularAA stroke: nothing to shade
+            if (info & kInfoBegin) ov = 0xFFu;                      // PF_MASK_BEGIN: every block resets the level
             TileEntry e;
             e.pid = pid;
-            e.info = (info_base & 0x7FFFFFFFu) | (ov << TE_OV_SHIFT) | (full << TE_FULL_SHIFT);
+            e.info = (info & 0x3FFFFFFFu) | (ov << TE_OV_SHIFT) | (full << TE_FULL_SHIFT);
             tile_list[cnt[i] + __popc(m & lt_mask)] = e;
           }
           cnt[i] += __popc(m);

@@ -295,8 +295,12 @@ def main():
         flops = algorithmic_flops(counts)
         bytes_alg = W * H * 4 + trace.n_draws * 128 * 2 + int(stats.n_tile_entries) * 4 * world
         ach = flops / (shade_ms * 1e-3) / 1e12 / world  # per GPU: every rank shades 1/world of the frame in shade_ms
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_shade_traffic.json")
+        if name == "cfg5_4k" and world == 1 and os.path.exists(tp):
+            traffic = json.load(open(tp)).get("traffic_bytes_per_launch")  # dram read+write from the ncu --set full capture
         roof = {"bound": "fp32", "kernel": "shade_kernel", "achieved": round(ach, 3), "peak": round(peak_fp32, 2),
-                "unit": "TFLOP/s", "frac": round(ach / peak_fp32, 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(ach / peak_fp32, 4), "traffic": traffic,
                 "algorithmic_flops_per_frame": flops, "fragments_per_frame": n_frag,
                 "note": "algorithmic = every fragment the reference's GL path would shade; the kernel provably skips "
                         "occluded and trivially covered ones, so this can exceed what is executed (see profiles/)",

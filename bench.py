@@ -118,7 +118,7 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def run_reference(args, rank: int):
+def run_reference(args, rank: int, out=sys.stdout):
     """CPU arm: the oracle port of the reference's GL path, all host threads, bounded sample per step."""
     if rank != 0:
         return
@@ -150,10 +150,20 @@ def run_reference(args, rank: int):
             "cpu_baseline": {"value": round(val, 3), "unit": METRIC, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(val, 3), "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "frames_per_s": round(val * 1e6 / (trace.width * H), 4)}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def _claim_stdout():
+    """Libraries (NCCL's version banner, torchrun warnings) print to fd 1; the driver wants ONE JSON line there.
+    Point fd 1 at stderr for the run and keep the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -161,6 +171,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="nccl", choices=["p2p", "nccl"],
+                    help="N>1: fused peer stores from the shade kernel (p2p) or NCCL all-gather of the bands")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
 
@@ -169,7 +181,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, real_stdout)
         return
 
     import torch
@@ -195,13 +207,25 @@ def main():
     for _i, key, img in trace.images:
         ctx.putImage(key, img)
 
-    # Framebuffer owned by torch so NCCL can all-gather the bands in place; rows padded to equal bands.
     from figdraw_b200 import bands
 
     band_rows, _layout = bands.band_layout(H, world)
-    fb = torch.zeros((band_rows * world, W, 4), dtype=torch.uint8, device=dev)
-    ctx.bindFramebuffer(fb.data_ptr())
+    use_p2p = world > 1 and args.gather == "p2p"
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    if use_p2p:
+        # Fused all-gather: every rank's shade kernel stores its finished pixels into all peers' framebuffers over
+        # NVLink (CUDA IPC mappings); a one-element NCCL all-reduce on the same stream is the completion barrier.
+        ctx.reserveFramebuffer(W, band_rows * world)
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.framebufferIpcHandle())
+        peers = [0 if r == rank else ctx.openPeerFramebuffer(handles[r]) for r in range(world)]
+        ctx.setPeerFramebuffers(peers)
+        token = torch.zeros(1, dtype=torch.int32, device=dev)
+        fb = None
+    else:
+        # Framebuffer owned by torch so NCCL can all-gather the bands in place; rows padded to equal bands.
+        fb = torch.zeros((band_rows * world, W, 4), dtype=torch.uint8, device=dev)
+        ctx.bindFramebuffer(fb.data_ptr())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     calls_host = torch.from_numpy(trace.calls.view(np.uint8).reshape(-1, 128).copy()).pin_memory()
@@ -210,7 +234,10 @@ def main():
     out_np = out_host.numpy()
 
     def gather():
-        bands.allgather_bands(fb, rank, world)
+        if use_p2p:
+            dist.all_reduce(token)  # all ranks' shade kernels (and their peer stores) are complete after this
+        else:
+            bands.allgather_bands(fb, rank, world)
 
     def frame_e2e():
         ctx.beginFrame((W, H), clearMain=trace.clear is not None, clearMainColor=trace.clear or (1, 1, 1, 1))
@@ -273,6 +300,34 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
 
+    gathered_ok = None
+    if world > 1 and rank == 0:
+        # the gathered frame on rank 0 must equal a single-context render of the whole frame, bit for bit
+        ctx.replayFrame()
+        with torch.cuda.stream(stream):
+            gather()
+        torch.cuda.synchronize()
+    if world > 1 and rank != 0:
+        ctx.replayFrame()
+        with torch.cuda.stream(stream):
+            gather()
+        torch.cuda.synchronize()
+    if world > 1 and rank == 0:
+        import ctypes
+
+        whole = np.empty((H, W, 4), dtype=np.uint8)
+        if use_p2p:
+            ctx._ck(ctx._lib.fdc_read_pixels(ctx._h, 0, 0, W, H, whole.ctypes.data))
+        else:
+            whole[:] = fb[:H].cpu().numpy()
+        ref_ctx = CudaContext(atlasSize=trace.atlas_size, device=local_rank)
+        for _i, key, img in trace.images:
+            ref_ctx.putImage(key, img)
+        ref_ctx.beginFrame((W, H), clearMain=trace.clear is not None, clearMainColor=trace.clear or (1, 1, 1, 1))
+        ref_ctx.submitCalls(calls_np)
+        ref_ctx.endFrame()
+        gathered_ok = bool(np.array_equal(ref_ctx.readPixels(), whole))
+        ref_ctx.close()
     if world > 1:
         t = torch.tensor([ms_step, e2e_ms, stats.shade_ms, stats.bin_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -328,13 +383,17 @@ def main():
                 "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "frame": [W, H], "primitives": trace.n_draws, "l2": "flushed between steps (256 MiB fill)",
-                           "partition": "single GPU" if world == 1 else f"{world} tile-row bands + NCCL all-gather"},
+                           "partition": "single GPU" if world == 1 else (
+                               f"{world} tile-row bands, band all-gather fused into the shade kernel (peer stores over NVLink)"
+                               if use_p2p else f"{world} tile-row bands + NCCL all-gather")},
                 "frames_per_s": round(1e3 / ms_step, 2),
                 "e2e": {"value": round(mpx / (e2e_ms * 1e-3), 2), "unit": METRIC, "ms_per_step": round(e2e_ms, 4),
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches_per_frame * args.steps, "launches_per_frame": launches_per_frame,
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base}
-        print(json.dumps(line), flush=True)
+        if gathered_ok is not None:
+            line["gathered_frame_equals_single_gpu"] = gathered_ok
+        print(json.dumps(line), file=real_stdout, flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -122,7 +122,7 @@ EXPORTS = [
     "fdc_submit_calls",
     "fdc_put_image", "fdc_update_image", "fdc_has_image", "fdc_get_image_rect", "fdc_remove_image",
     "fdc_reset_image_atlas", "fdc_atlas_size", "fdc_atlas_packed_area",
-    "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers",
+    "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers", "fdc_reserve_framebuffer", "fdc_framebuffer_ipc_handle", "fdc_open_peer_framebuffer",
     "fdc_get_frame_stats", "fdc_debug_bins", "fdc_debug_shade_stats",
 ]
 
@@ -204,6 +204,9 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_band_rows", c.c_int, P, c.POINTER(c.c_int), c.POINTER(c.c_int))
     sig("fdc_stream", P, P)
     sig("fdc_set_peer_framebuffers", c.c_int, P, c.POINTER(P), c.c_int)
+    sig("fdc_reserve_framebuffer", c.c_int, P, c.c_int, c.c_int)
+    sig("fdc_framebuffer_ipc_handle", c.c_int, P, c.POINTER(c.c_uint8))
+    sig("fdc_open_peer_framebuffer", c.c_int, P, c.POINTER(c.c_uint8), c.POINTER(P))
     sig("fdc_get_frame_stats", c.c_int, P, c.POINTER(FdcFrameStats))
     sig("fdc_debug_shade_stats", c.c_int, P, c.POINTER(c.c_uint64))
     sig("fdc_debug_bins", c.c_int, P, c.c_int, u32p, c.c_size_t, u32p, c.c_size_t, c.POINTER(c.c_size_t),

@@ -1367,6 +1367,41 @@ int fdc_set_peer_framebuffers(fdc_ctx* ctx, void* const* device_ptrs, int n) {
   return FDC_OK;
 }
 
+int fdc_reserve_framebuffer(fdc_ctx* ctx, int width, int rows) {
+  if (!ctx || width <= 0 || rows <= 0) return FDC_ERR_INVALID;
+  if (ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "cannot resize the framebuffer inside a frame");
+  CK(cudaSetDevice(ctx->device));
+  int rc = resolve_frame(ctx);
+  if (rc) return rc;
+  const size_t bytes = (size_t)width * rows * 4;
+  if (ctx->d_fb.cap < bytes) {
+    CK(ctx->d_fb.reserve(bytes));
+    CK(cudaMemsetAsync(ctx->d_fb.p, 0, ctx->d_fb.cap, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return FDC_OK;
+}
+
+int fdc_framebuffer_ipc_handle(fdc_ctx* ctx, uint8_t out_handle[64]) {
+  if (!ctx || !out_handle) return FDC_ERR_INVALID;
+  if (!ctx->d_fb.p) return ctx->fail(FDC_ERR_STATE, "no internal framebuffer yet (fdc_reserve_framebuffer)");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaIpcGetMemHandle(&h, ctx->d_fb.p));
+  memcpy(out_handle, &h, 64);
+  return FDC_OK;
+}
+
+int fdc_open_peer_framebuffer(fdc_ctx* ctx, const uint8_t handle[64], void** out_device_ptr) {
+  if (!ctx || !handle || !out_device_ptr) return FDC_ERR_INVALID;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaIpcOpenMemHandle(out_device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return FDC_OK;
+}
+
 int fdc_get_frame_stats(fdc_ctx* ctx, fdc_frame_stats* out) {
   if (!ctx || !out) return FDC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));

@@ -663,12 +663,14 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
       const uint32_t out = (__float_as_uint(px.r) & 255u) | ((__float_as_uint(px.g) & 255u) << 8) |
                            ((__float_as_uint(px.b) & 255u) << 16) | ((__float_as_uint(px.a) & 255u) << 24);
       fb32[(size_t)iy * f.W + ix] = out;
+      // fused band all-gather: the finished pixel goes straight to every peer's framebuffer over NVLink
       for (int k = 0; k < a.n_peers; k++) {
         uint32_t* peer = reinterpret_cast<uint32_t*>(a.peers[k]);
         if (peer && peer != fb32) peer[(size_t)iy * f.W + ix] = out;
       }
     }
   }
+  if (a.n_peers > 0) __threadfence_system();
 }
 
 void launch_shade(const ShadeArgs& a, cudaStream_t stream) {

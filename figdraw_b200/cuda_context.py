@@ -290,6 +290,20 @@ class CudaContext(BackendContext):
     def stream(self) -> int:
         return int(self._lib.fdc_stream(self._h) or 0)
 
+    def reserveFramebuffer(self, width: int, rows: int):
+        self._ck(self._lib.fdc_reserve_framebuffer(self._h, int(width), int(rows)))
+
+    def framebufferIpcHandle(self) -> bytes:
+        buf = (ctypes.c_uint8 * 64)()
+        self._ck(self._lib.fdc_framebuffer_ipc_handle(self._h, buf))
+        return bytes(buf)
+
+    def openPeerFramebuffer(self, handle: bytes) -> int:
+        buf = (ctypes.c_uint8 * 64)(*handle)
+        out = ctypes.c_void_p()
+        self._ck(self._lib.fdc_open_peer_framebuffer(self._h, buf, ctypes.byref(out)))
+        return int(out.value)
+
     def setPeerFramebuffers(self, ptrs: Sequence[int]):
         arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])
         self._ck(self._lib.fdc_set_peer_framebuffers(self._h, arr, len(ptrs)))

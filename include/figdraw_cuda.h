@@ -231,8 +231,16 @@ int fdc_band_rows(fdc_ctx* ctx, int* y0, int* y1);
 /* The CUDA stream (cudaStream_t) frames are launched on. */
 void* fdc_stream(fdc_ctx* ctx);
 /* Peer framebuffers: when set (n_ranks entries, own entry may be NULL), the shade kernel stores every
- * finished tile row to all peers directly over NVLink, fusing the band all-gather into the kernel. */
+ * finished pixel of its band to all peers directly over NVLink, fusing the band all-gather into the kernel.
+ * After every rank's frame has completed (any cross-rank barrier on fdc_stream) each framebuffer holds the
+ * whole frame. */
 int fdc_set_peer_framebuffers(fdc_ctx* ctx, void* const* device_ptrs, int n);
+/* CUDA IPC plumbing for the above between processes (one process per GPU): make sure the context owns a
+ * framebuffer of `rows` x width x 4 bytes (rows >= height; a dedicated cudaMalloc), export its 64-byte
+ * cudaIpcMemHandle_t, and map a peer's handle into this process. */
+int fdc_reserve_framebuffer(fdc_ctx* ctx, int width, int rows);
+int fdc_framebuffer_ipc_handle(fdc_ctx* ctx, uint8_t out_handle[64]);
+int fdc_open_peer_framebuffer(fdc_ctx* ctx, const uint8_t handle[64], void** out_device_ptr);
 
 /* --- introspection for parity tests and benchmarks --- */
 typedef struct fdc_frame_stats {

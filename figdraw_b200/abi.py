@@ -119,7 +119,7 @@ EXPORTS = [
     "fdc_draw_rounded_rect_sdf", "fdc_draw_image", "fdc_draw_msdf_image", "fdc_draw_quadratic_bezier_sdf",
     "fdc_draw_filled_quad", "fdc_draw_rect", "fdc_draw_backdrop_blur",
     "fdc_begin_mask", "fdc_end_mask", "fdc_pop_mask", "fdc_begin_rect_mask", "fdc_pop_rect_mask",
-    "fdc_submit_calls",
+    "fdc_submit_calls", "fdc_submit_draws",
     "fdc_put_image", "fdc_update_image", "fdc_has_image", "fdc_get_image_rect", "fdc_remove_image",
     "fdc_reset_image_atlas", "fdc_atlas_size", "fdc_atlas_packed_area",
     "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers", "fdc_reserve_framebuffer", "fdc_framebuffer_ipc_handle", "fdc_open_peer_framebuffer",
@@ -191,6 +191,7 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_begin_rect_mask", c.c_int, P, fp, fp, fp)
     sig("fdc_pop_rect_mask", c.c_int, P)
     sig("fdc_submit_calls", c.c_int, P, P, c.c_size_t)
+    sig("fdc_submit_draws", c.c_int, P, P, c.c_size_t)
     sig("fdc_put_image", c.c_int, P, c.c_uint64, c.c_int, c.c_int, P, fp, c.POINTER(c.c_int))
     sig("fdc_update_image", c.c_int, P, c.c_uint64, c.c_int, c.c_int, P)
     sig("fdc_has_image", c.c_int, P, c.c_uint64)

@@ -1292,6 +1292,18 @@ int fdc_submit_calls(fdc_ctx* ctx, const fdc_call* calls, size_t n) {
   return FDC_OK;
 }
 
+int fdc_submit_draws(fdc_ctx* ctx, const fdc_call* draws, size_t n) {
+  if (!ctx || (!draws && n)) return FDC_ERR_INVALID;
+  if (n == 0) return FDC_OK;
+  if (!ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "draw outside beginFrame/endFrame");
+  if (ctx->mask_begun || n < kDirectRunMin) return fdc_submit_calls(ctx, draws, n);  // small or mask content: per record
+  int rc = ensure_rect_image(ctx);  // FILLED_QUAD / RECT records may be inside; the 4x4 white image is cheap
+  if (rc) return rc;
+  rc = add_direct_run(ctx, draws, n, ctx->call_ordinal);
+  if (rc == FDC_OK) ctx->call_ordinal += (uint32_t)n;
+  return rc;
+}
+
 // ------------------------------------------------------------------------------------------------- atlas
 int fdc_put_image(fdc_ctx* ctx, uint64_t key, int w, int h, const uint8_t* rgba, float out_rect[4], int* out_rebuilt) {
   if (!ctx) return FDC_ERR_INVALID;

@@ -255,6 +255,20 @@ class CudaContext(BackendContext):
         assert calls.dtype.itemsize == 128
         self._ck(self._lib.fdc_submit_calls(self._h, calls.ctypes.data, len(calls)))
 
+    def submitDraws(self, draws: np.ndarray):
+        """`draws` holds only draw records (op >= 32): one run, the host never reads them."""
+        assert draws.dtype.itemsize == 128 and draws.flags["C_CONTIGUOUS"]
+        self._ck(self._lib.fdc_submit_draws(self._h, draws.ctypes.data, len(draws)))
+
+    def submitPrepared(self, prepared):
+        """Replay a `prepare_calls()` result: state ops record by record, runs of draws through fdc_submit_draws."""
+        calls, runs = prepared
+        for is_draw, a, b in runs:
+            if is_draw:
+                self._ck(self._lib.fdc_submit_draws(self._h, calls[a:b].ctypes.data, b - a))
+            else:
+                self._ck(self._lib.fdc_submit_calls(self._h, calls[a:b].ctypes.data, b - a))
+
     def frameStats(self) -> FdcFrameStats:
         st = FdcFrameStats()
         self._ck(self._lib.fdc_get_frame_stats(self._h, ctypes.byref(st)))
@@ -307,6 +321,17 @@ class CudaContext(BackendContext):
     def setPeerFramebuffers(self, ptrs: Sequence[int]):
         arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])
         self._ck(self._lib.fdc_set_peer_framebuffers(self._h, arr, len(ptrs)))
+
+
+def prepare_calls(calls: np.ndarray):
+    """Split a call array once into maximal runs of draw records / other records (what a host that emits the calls
+    knows anyway), so replaying it needs no per-record inspection."""
+    calls = np.ascontiguousarray(calls)
+    is_draw = calls["op"] >= abi.FIRST_DRAW_OP
+    edges = np.flatnonzero(np.diff(is_draw.astype(np.int8))) + 1
+    bounds = [0, *edges.tolist(), len(calls)]
+    runs = [(bool(is_draw[a]), a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    return calls, runs
 
 
 def render_trace(trace: Trace, ctx: Optional[CudaContext] = None, device: int = 0) -> np.ndarray:

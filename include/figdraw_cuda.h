@@ -204,6 +204,10 @@ int fdc_pop_rect_mask(fdc_ctx* ctx);
  * are transferred to the device in one asynchronous copy straight from `calls` (no host staging pass): if that
  * memory is page-locked it must stay unmodified until the next fdc_sync / fdc_read_pixels / fdc_begin_frame. */
 int fdc_submit_calls(fdc_ctx* ctx, const fdc_call* calls, size_t n);
+/* As fdc_submit_calls for an array the caller KNOWS holds only draw records (op >= FDC_OP_ROUNDED_RECT) issued under
+ * the current state: the host does not even read them -- one run, one asynchronous copy; records with any other op
+ * are dropped on the device.  Same lifetime rule for page-locked memory. */
+int fdc_submit_draws(fdc_ctx* ctx, const fdc_call* draws, size_t n);
 
 /* --- atlas: glcontext.nim:536-641, textures.nim:88-119 --- */
 /* putImage: packs (skyline, margin 4), uploads straight-alpha RGBA8 texels + a 2x2-box mip chain.

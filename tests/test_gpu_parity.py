@@ -213,3 +213,24 @@ def test_atlas_packer_matches_reference_placement():
         assert r1 == pytest.approx(r2, abs=0) and g1 == g2
     assert ctx.atlasSize() == o.atlas_size and ctx.atlasSize() > 256  # it grew
     ctx.close()
+
+
+def test_submit_draws_equals_submit_calls():
+    """fdc_submit_draws (no host inspection, one async copy per run) renders exactly what fdc_submit_calls does."""
+    from figdraw_b200.cuda_context import prepare_calls
+
+    tr = ss.config_trace(5, 1280, 720, n_rects=6000, n_glyphs=1200)
+    want = render_trace(tr)
+    ctx = CudaContext(atlasSize=tr.atlas_size)
+    for _i, key, img in tr.images:
+        ctx.putImage(key, img)
+    prepared = prepare_calls(tr.calls)
+    assert any(is_draw and b - a >= 2048 for is_draw, a, b in prepared[1])
+    ctx.beginFrame((tr.width, tr.height), clearMain=True)
+    ctx.submitPrepared(prepared)
+    ctx.endFrame()
+    assert np.array_equal(ctx.readPixels(), want)
+    off, ent = ctx.debugBins(0)
+    ref_off, ref_ent = oracle.reference_bins(tr)[0]
+    assert np.array_equal(off, ref_off) and np.array_equal(ent, ref_ent)
+    ctx.close()

@@ -41,9 +41,20 @@ constexpr int kMaxReach = 66;   // ceil(8 * 64/8) + 1 + slack
 
 // One pass.  kVertical=false: taps along x, reads `src` rows; kVertical=true: taps along y.
 // Region [x0,x1) x [y0,y1) of dst is produced.  Source indices clamp to the frame (CLAMP_TO_EDGE).
+struct RowSources {
+  const uint32_t* rank[kMaxRanks];
+  int n, band_px;
+};
+__device__ __forceinline__ const uint32_t* row_base(const RowSources& rs, const uint32_t* src, int y) {
+  if (rs.n == 0) return src;
+  const int r = min(y / rs.band_px, rs.n - 1);
+  return rs.rank[r];
+}
+
 template <bool kVertical>
 __global__ void __launch_bounds__(kBlurTile) blur_pass_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
-                                                             int W, int H, int x0, int y0, int x1, int y1, BlurParams bp) {
+                                                             int W, int H, int x0, int y0, int x1, int y1, BlurParams bp,
+                                                             RowSources rs) {
   __shared__ uint32_t line[kBlurLines][kBlurTile + 2 * kMaxReach];
   const int along0 = (kVertical ? y0 : x0) + blockIdx.x * kBlurTile;  // first pixel along the pass axis
   const int across0 = (kVertical ? x0 : y0) + blockIdx.y * kBlurLines;
@@ -56,7 +67,11 @@ __global__ void __launch_bounds__(kBlurTile) blur_pass_kernel(const uint32_t* __
     for (int k = threadIdx.x; k < span; k += kBlurTile) {
       int a = along0 - bp.reach + k;
       a = a < 0 ? 0 : (a >= limit ? limit - 1 : a);
-      line[l][k] = kVertical ? __ldg(src + (size_t)a * W + across) : __ldg(src + (size_t)across * W + a);
+      // H pass: row `across` may live in a neighbour's framebuffer (halo rows of a band partition): volatile load, the
+      // line must come from the owner's L2, not from a stale local cache
+      if (kVertical) line[l][k] = __ldg(src + (size_t)a * W + across);
+      else if (rs.n == 0) line[l][k] = __ldg(src + (size_t)across * W + a);
+      else line[l][k] = __ldcv(row_base(rs, src, across) + (size_t)across * W + a);
     }
   }
   __syncthreads();
@@ -145,19 +160,66 @@ void launch_backdrop_blur(const BlurArgs& a, cudaStream_t stream, int* n_launche
   bp.inv_sum = 1.0f / fmaxf(sum, 1e-5f);
   bp.reach = bp.copy_only ? 0 : (int)ceilf(8.0f * bp.step) + 1;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(a.src);
+  RowSources rs;
+  rs.n = a.n_src;
+  rs.band_px = a.band_px > 0 ? a.band_px : 1;
+  for (int r = 0; r < kMaxRanks; r++) rs.rank[r] = r < a.n_src ? reinterpret_cast<const uint32_t*>(a.src_rank[r]) : nullptr;
   uint32_t* temp = reinterpret_cast<uint32_t*>(a.temp);
   uint32_t* dst = reinterpret_cast<uint32_t*>(a.dst);
   // H pass over the rows the V pass will read
   const int hy0 = max(a.y0 - bp.reach, 0), hy1 = min(a.y1 + bp.reach, a.H);
   {
     dim3 grid((a.x1 - a.x0 + kBlurTile - 1) / kBlurTile, (hy1 - hy0 + kBlurLines - 1) / kBlurLines);
-    blur_pass_kernel<false><<<grid, kBlurTile, 0, stream>>>(src, temp, a.W, a.H, a.x0, hy0, a.x1, hy1, bp);
+    blur_pass_kernel<false><<<grid, kBlurTile, 0, stream>>>(src, temp, a.W, a.H, a.x0, hy0, a.x1, hy1, bp, rs);
   }
   {
     dim3 grid((a.y1 - a.y0 + kBlurTile - 1) / kBlurTile, (a.x1 - a.x0 + kBlurLines - 1) / kBlurLines);
-    blur_pass_kernel<true><<<grid, kBlurTile, 0, stream>>>(temp, dst, a.W, a.H, a.x0, a.y0, a.x1, a.y1, bp);
+    blur_pass_kernel<true><<<grid, kBlurTile, 0, stream>>>(temp, dst, a.W, a.H, a.x0, a.y0, a.x1, a.y1, bp, RowSources{{}, 0, 1});
   }
   if (n_launches) *n_launches += 2;
+}
+
+namespace {
+struct FlagPtrs {
+  uint32_t* p[kMaxRanks];
+};
+__global__ void signal_flags_kernel(FlagPtrs f, int n, int my_rank, uint32_t value) {
+  const int r = threadIdx.x;
+  if (r >= n) return;
+  __threadfence_system();  // everything this stream wrote before (the segment's pixels) is visible system-wide first
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[r] + my_rank), "r"(value) : "memory");
+}
+// Spin until every rank's slot reached `value`.  A peer that never arrives (crashed process, a frame submitted on
+// one rank only) must not hang the GPU: after kBarrierTimeoutNs the kernel records the failure in flags[kFlagError]
+// and lets the stream continue; the host reports it when the frame is resolved.
+constexpr unsigned long long kBarrierTimeoutNs = 2000000000ull;
+__global__ void wait_flags_kernel(uint32_t* flags, int n, uint32_t value) {
+  const int r = threadIdx.x;
+  if (r >= n) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  uint32_t v;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+    if ((int32_t)(v - value) >= 0) break;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > kBarrierTimeoutNs) {
+      atomicOr(flags + kFlagError, 1u << r);
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+}  // namespace
+
+void launch_signal_flags(uint32_t* const* flag_arrays, int n, int my_rank, uint32_t value, cudaStream_t stream) {
+  FlagPtrs f;
+  for (int r = 0; r < kMaxRanks; r++) f.p[r] = r < n ? flag_arrays[r] : nullptr;
+  signal_flags_kernel<<<1, 32, 0, stream>>>(f, n, my_rank, value);
+}
+void launch_wait_flags(uint32_t* my_flags, int n, uint32_t value, cudaStream_t stream) {
+  wait_flags_kernel<<<1, 32, 0, stream>>>(my_flags, n, value);
 }
 
 void launch_mip_down(const uint8_t* src, int src_size, uint8_t* dst, int dst_size, int sx, int sy, int sw, int sh, int dx,

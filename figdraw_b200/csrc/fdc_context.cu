@@ -32,7 +32,8 @@ struct DevBuf {
   size_t cap = 0;
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
-    size_t want = std::max(n, cap + cap / 2);
+    // slack: a scene that grows by a few records per frame must not reallocate (cudaFree is a device-wide sync)
+    size_t want = std::max(n + n / 8 + 64, cap + cap / 2);
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -43,7 +44,7 @@ struct DevBuf {
   // grow keeping the first `keep` elements (device-to-device copy on `st`)
   cudaError_t reserve_keep(size_t n, size_t keep, cudaStream_t st) {
     if (n <= cap) return cudaSuccess;
-    size_t want = std::max(n, cap * 2);
+    size_t want = std::max(n + n / 8 + 64, cap * 2);
     T* np = nullptr;
     cudaError_t e = cudaMalloc(&np, want * sizeof(T));
     if (e != cudaSuccess) return e;
@@ -247,6 +248,10 @@ struct fdc_ctx {
   DevBuf<uint8_t> d_fb, d_backdrop, d_temp;
   uint8_t* ext_fb = nullptr;
   DevBuf<uint8_t*> d_peers;
+  std::vector<uint8_t*> h_peers;   // host copy of the peer framebuffer pointers (own entry = own framebuffer)
+  size_t flag_off = 0;             // byte offset of the cross-rank flag array inside a reserved framebuffer (0: none)
+  uint32_t frame_barrier_base = 0; // barrier_seq at the start of the frame in flight
+  uint32_t barrier_seq = 0;        // cross-rank barrier values handed out so far (every rank runs the same sequence)
   DevBuf<unsigned long long> d_stats;
   bool want_stats = false;
   int n_peers = 0;
@@ -681,13 +686,29 @@ int execute_frame(fdc_ctx* ctx, bool upload) {
   rc = ensure_bin_buffers(ctx, max_prims);
   if (rc) return rc;
   const size_t fb_bytes = (size_t)ctx->W * ctx->H * 4;
-  if (!ctx->ext_fb) CK(ctx->d_fb.reserve(fb_bytes));
+  if (!ctx->ext_fb) {
+    if (ctx->flag_off && fb_bytes > ctx->flag_off)
+      return ctx->fail(FDC_ERR_CAPACITY, "frame larger than the framebuffer reserved with fdc_reserve_framebuffer");
+    CK(ctx->d_fb.reserve(fb_bytes));
+  }
   bool any_blur = false;
   for (auto& s : ctx->segments) any_blur = any_blur || s.has_blur;
   if (any_blur) {
     CK(ctx->d_backdrop.reserve(fb_bytes));
     CK(ctx->d_temp.reserve(fb_bytes));
   }
+  ctx->frame_barrier_base = ctx->barrier_seq;
+  const bool banded_blur = ctx->n_ranks > 1 && any_blur;
+  uint32_t* flag_ptrs[kMaxRanks] = {};
+  if (banded_blur) {
+    if (ctx->n_peers != ctx->n_ranks || ctx->flag_off == 0 || ctx->ext_fb)
+      return ctx->fail(FDC_ERR_STATE, "backdrop blur under a tile-band partition needs fdc_reserve_framebuffer + fdc_set_peer_framebuffers");
+    for (int r = 0; r < ctx->n_ranks; r++) {
+      uint8_t* base = (r == ctx->rank || !ctx->h_peers[r]) ? ctx->d_fb.p : ctx->h_peers[r];
+      flag_ptrs[r] = reinterpret_cast<uint32_t*>(base + ctx->flag_off);
+    }
+  }
+  uint32_t pending_wait = 0;  // "neighbours finished reading my halo rows" value to wait for before the next shade
   for (size_t si = 0; si < ctx->segments.size(); si++) {
     const Segment& s = ctx->segments[si];
     {
@@ -718,20 +739,54 @@ int execute_frame(fdc_ctx* ctx, bool upload) {
       sa.stats = ctx->want_stats ? ctx->d_stats.p : nullptr;
       sa.peers = (last && ctx->n_peers > 0) ? ctx->d_peers.p : nullptr;
       sa.n_peers = (last && ctx->n_peers > 0) ? ctx->n_peers : 0;
+      if (pending_wait) {
+        launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, pending_wait, st);
+        pending_wait = 0;
+        launches++;
+      }
       launch_shade(sa, st);
       launches++;
     }
     if (s.has_blur) {
       Timed t(ctx, 2);
       BlurArgs ba;
+      memset(&ba, 0, sizeof(ba));
+      int by0 = s.ry0, by1 = s.ry1;
+      uint32_t v_done = 0;
+      if (banded_blur) {
+        // Halo exchange over peer memory: (1) everyone has finished shading this segment, (2) the H pass reads the rows
+        // it needs straight out of the owners' framebuffers, (3) tell everyone the halo has been read so the next
+        // segment may overwrite those rows.  Every rank runs the same barrier sequence, with or without work.
+        const uint32_t v_shaded = ++ctx->barrier_seq;
+        v_done = ++ctx->barrier_seq;
+        launch_signal_flags(flag_ptrs, ctx->n_ranks, ctx->rank, v_shaded, st);
+        launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, v_shaded, st);
+        launches += 2;
+        by0 = std::max(by0, ctx->frame.band_y0);
+        by1 = std::min(by1, ctx->frame.band_y1);
+        ba.n_src = ctx->n_ranks;
+        ba.band_px = std::max(1, ((ctx->frame.tiles_y + ctx->n_ranks - 1) / ctx->n_ranks) * kTileH);
+        for (int r = 0; r < ctx->n_ranks; r++)
+          ba.src_rank[r] = (r == ctx->rank || !ctx->h_peers[r]) ? ctx->d_fb.p : ctx->h_peers[r];
+      }
       ba.src = ctx->fb();
       ba.temp = ctx->d_temp.p;
       ba.dst = ctx->d_backdrop.p;
       ba.W = ctx->W; ba.H = ctx->H;
-      ba.x0 = s.rx0; ba.y0 = s.ry0; ba.x1 = s.rx1; ba.y1 = s.ry1;
+      ba.x0 = s.rx0; ba.y0 = by0; ba.x1 = s.rx1; ba.y1 = by1;
       ba.radius = s.blur_radius;
       launch_backdrop_blur(ba, st, &launches);
+      if (banded_blur) {
+        // (the H pass is the only reader of remote rows and precedes this signal in stream order)
+        launch_signal_flags(flag_ptrs, ctx->n_ranks, ctx->rank, v_done, st);
+        launches++;
+        pending_wait = v_done;
+      }
     }
+  }
+  if (pending_wait) {  // do not let the next frame's shade overwrite rows a neighbour may still be reading
+    launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, pending_wait, st);
+    launches++;
   }
   cudaEventRecord(ctx->ev_end, st);
   CK(cudaGetLastError());
@@ -755,10 +810,24 @@ int resolve_frame(fdc_ctx* ctx) {
     if (!ctx->d_counters.p) return FDC_OK;
     CK(cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
     ctx->stats.n_tile_entries = c[0];
+    if (ctx->n_ranks > 1 && ctx->flag_off && ctx->barrier_seq != ctx->frame_barrier_base) {
+      uint32_t late = 0;
+      uint32_t* err = reinterpret_cast<uint32_t*>(ctx->d_fb.p + ctx->flag_off) + kFlagError;
+      CK(cudaMemcpy(&late, err, 4, cudaMemcpyDeviceToHost));
+      if (late) {
+        CK(cudaMemset(err, 0, 4));
+        ctx->have_frame = false;
+        return ctx->fail(FDC_ERR_STATE, "blur halo barrier timed out waiting for rank mask 0x%x (did every rank submit the frame?)", late);
+      }
+    }
     if (c[1] == 0) return FDC_OK;
     // overflow: counters hold the required sizes (coarse total exact, tile cursor = total needed)
     if (c[1] & 1u) CK(ctx->d_coarse_list.reserve((size_t)c[2] + (c[2] >> 2) + 1024));
     if (c[1] & 2u) CK(ctx->d_tile_list.reserve((size_t)c[0] + (c[0] >> 2) + 1024));
+    // A private replay must not advance the cross-rank barrier sequence (the other ranks do not replay): it re-uses
+    // this frame's values, which the flags have already reached.  Blur halo rows then show the neighbours' current
+    // state; lists only overflow on the first frame of a much larger scene.
+    ctx->barrier_seq = ctx->frame_barrier_base;
     int rc = execute_frame(ctx, false);
     if (rc) return rc;
   }
@@ -1128,7 +1197,9 @@ int fdc_draw_backdrop_blur(fdc_ctx* ctx, const float rect[4], const float radii_
   if (blur_radius <= 0.0f || rect[2] <= 0.0f || rect[3] <= 0.0f) return FDC_OK;  // glcontext.nim:1791-1792
   if (!ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "draw outside beginFrame/endFrame");
   if (ctx->mask_begun) return ctx->fail(FDC_ERR_STATE, "drawBackdropBlur inside beginMask/endMask is not supported");
-  if (ctx->n_ranks > 1) return ctx->fail(FDC_ERR_STATE, "backdrop blur with tile-band partitioning needs the halo exchange (not built yet)");
+  if (ctx->n_ranks > 1 && (ctx->n_peers != ctx->n_ranks || ctx->flag_off == 0 || ctx->ext_fb))
+    return ctx->fail(FDC_ERR_STATE, "backdrop blur under a tile-band partition reads halo rows from the neighbours' framebuffers: "
+                                    "call fdc_reserve_framebuffer and fdc_set_peer_framebuffers (all ranks) first");
   Segment& s = ctx->segments.back();
   s.has_blur = true;
   s.blur_radius = blur_radius;
@@ -1372,7 +1443,20 @@ int fdc_set_peer_framebuffers(fdc_ctx* ctx, void* const* device_ptrs, int n) {
   int rc = resolve_frame(ctx);
   if (rc) return rc;
   ctx->n_peers = n;
+  ctx->h_peers.assign(n, nullptr);
   if (n) {
+    if (n > kMaxRanks) return ctx->fail(FDC_ERR_CAPACITY, "at most %d ranks", kMaxRanks);
+    for (int r = 0; r < n; r++) ctx->h_peers[r] = (uint8_t*)device_ptrs[r];
+    // pointers that live on another device of this process need peer access (IPC mappings already have it)
+    for (int r = 0; r < n; r++) {
+      if (!device_ptrs[r]) continue;
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, device_ptrs[r]) == cudaSuccess && at.device != ctx->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return ctx->cuda_fail(e, "cudaDeviceEnablePeerAccess");
+        cudaGetLastError();
+      }
+    }
     CK(ctx->d_peers.reserve((size_t)n));
     CK(cudaMemcpy(ctx->d_peers.p, device_ptrs, sizeof(void*) * n, cudaMemcpyHostToDevice));
   }
@@ -1385,11 +1469,18 @@ int fdc_reserve_framebuffer(fdc_ctx* ctx, int width, int rows) {
   CK(cudaSetDevice(ctx->device));
   int rc = resolve_frame(ctx);
   if (rc) return rc;
-  const size_t bytes = (size_t)width * rows * 4;
-  if (ctx->d_fb.cap < bytes) {
-    CK(ctx->d_fb.reserve(bytes));
-    CK(cudaMemsetAsync(ctx->d_fb.p, 0, ctx->d_fb.cap, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+  // pixels, then (256-byte aligned) a small array of cross-rank flags that peers write for the blur halo barrier
+  const size_t pix = (((size_t)width * rows * 4) + 255) & ~(size_t)255;
+  const size_t bytes = pix + 4096;
+  ctx->d_fb.release();
+  CK(ctx->d_fb.reserve(bytes));
+  CK(cudaMemsetAsync(ctx->d_fb.p, 0, ctx->d_fb.cap, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->flag_off = pix;
+  ctx->barrier_seq = 0;
+  if (ctx->n_ranks > 1) {  // blur scratch up front: no allocation (an implicit device sync) while peers spin on our flags
+    CK(ctx->d_backdrop.reserve((size_t)width * rows * 4));
+    CK(ctx->d_temp.reserve((size_t)width * rows * 4));
   }
   return FDC_OK;
 }

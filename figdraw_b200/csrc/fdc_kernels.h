@@ -57,8 +57,14 @@ struct ShadeArgs {
 };
 void launch_shade(const ShadeArgs& a, cudaStream_t stream);
 
+constexpr int kMaxRanks = 16;
+constexpr int kFlagError = 32;  // word of a rank's flag array that records barrier time-outs (bit r: rank r never arrived)
 struct BlurArgs {
   const uint8_t* src;  // framebuffer
+  // Tile-band partition: rows [r*band_px, (r+1)*band_px) of the frame live in src_rank[r] (this rank's own framebuffer or
+  // a peer's, read over NVLink for the blur halo).  n_src == 0: everything is in `src`.
+  const uint8_t* src_rank[kMaxRanks];
+  int n_src, band_px;
   uint8_t* temp;       // H-pass output
   uint8_t* dst;        // backdrop (V-pass output)
   int W, H;
@@ -66,6 +72,10 @@ struct BlurArgs {
   float radius;        // blurRadius as passed to drawBackdropBlur
 };
 void launch_backdrop_blur(const BlurArgs& a, cudaStream_t stream, int* n_launches);
+// Cross-rank stream-ordered barrier over peer memory: store `value` into slot `my_rank` of every rank's flag array,
+// then (wait) spin until all `n` slots of the local array have reached `value`.
+void launch_signal_flags(uint32_t* const* flag_arrays, int n, int my_rank, uint32_t value, cudaStream_t stream);
+void launch_wait_flags(uint32_t* my_flags, int n, uint32_t value, cudaStream_t stream);
 
 void launch_fill_u32(uint32_t* dst, uint32_t value, size_t n, cudaStream_t stream);
 // Builds mip level `l+1` region from level `l` (premultiplied 2x2 box, see oracle upload_chain).

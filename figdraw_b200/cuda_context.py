@@ -334,6 +334,16 @@ def prepare_calls(calls: np.ndarray):
     return calls, runs
 
 
+def submit_trace(trace: Trace, ctx: CudaContext) -> None:
+    """putImage + beginFrame + fdc_submit_calls + endFrame; the frame is left in flight on the context's stream."""
+    for _idx, key, img in trace.images:
+        ctx.putImage(key, img)
+    ctx.beginFrame((trace.width, trace.height), clearMain=trace.clear is not None,
+                   clearMainColor=trace.clear or (1.0, 1.0, 1.0, 1.0))
+    ctx.submitCalls(trace.calls)
+    ctx.endFrame()
+
+
 def render_trace(trace: Trace, ctx: Optional[CudaContext] = None, device: int = 0) -> np.ndarray:
     """Render a recorded frame through the C ABI: putImage for its images, one fdc_submit_calls, readPixels."""
     own = ctx is None

@@ -12,7 +12,7 @@ from figdraw_b200 import scenes
 from figdraw_b200 import scenes_fuzz
 from figdraw_b200 import scenes_synth as ss
 from figdraw_b200.abi import Op
-from figdraw_b200.cuda_context import CudaContext, render_trace
+from figdraw_b200.cuda_context import CudaContext, FigDrawError, render_trace
 from figdraw_b200.figbackend import Trace
 from oracle import oracle
 
@@ -163,6 +163,82 @@ def test_tile_bands_reassemble_the_frame():
             out[y0:y1] = img[y0:y1]
             ctx.close()
         assert np.array_equal(out, full)
+
+
+def _band_contexts(tr, n):
+    from figdraw_b200.bands import padded_rows
+
+    ctxs = [CudaContext(atlasSize=tr.atlas_size, rank=r, nRanks=n) for r in range(n)]
+    for c in ctxs:
+        c.reserveFramebuffer(tr.width, padded_rows(tr.height, n))
+    ptrs = [c.framebufferPtr() for c in ctxs]
+    for c in ctxs:
+        c.setPeerFramebuffers(ptrs)
+        for _idx, key, img in tr.images:
+            c.putImage(key, img)
+    return ctxs
+
+
+def _submit(c, tr, calls):
+    c.beginFrame((tr.width, tr.height), clearMain=tr.clear is not None, clearMainColor=tr.clear or (1.0, 1.0, 1.0, 1.0))
+    c.submitCalls(calls)
+    c.endFrame()
+
+
+def _render_banded_with_peers(tr, n):
+    """n band contexts on one device, framebuffers cross-registered as peers: every rank submits the frame, the shade
+    kernel's last segment stores each band into every framebuffer, blur halo rows are read from the owner."""
+    ctxs = _band_contexts(tr, n)
+    try:
+        # Size every context's buffers one rank at a time with the blur calls removed (no cross-rank waits): all ranks
+        # share this process and device, and an allocation while a peer spins on our flags would stall both.
+        for c in ctxs:
+            _submit(c, tr, tr.calls[tr.calls["op"] != Op.BACKDROP_BLUR])
+            c.sync()
+        for _ in range(2):  # twice: the cross-rank flags carry over from frame to frame
+            for c in ctxs:
+                _submit(c, tr, tr.calls)
+            for c in ctxs:
+                c.sync()
+        return [c.readPixels() for c in ctxs]
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_blur_halo_barrier_times_out_instead_of_hanging():
+    tr = ss.config_trace(2, 640, 360)
+    ctxs = _band_contexts(tr, 2)
+    try:
+        _submit(ctxs[0], tr, tr.calls)  # rank 1 never submits
+        with pytest.raises(FigDrawError, match="timed out"):
+            ctxs[0].sync()
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_backdrop_blur_halo_exchange_across_bands(n):
+    """north_star: 'halo exchange for blur'.  A blur panel straddling band boundaries reads rows the neighbours shaded."""
+    traces = [ss.config_trace(2, 1280, 720), ss.config_trace(4, 1280, 720, rows=40, cols=8)]
+    from figdraw_b200.scenes_fuzz import random_trace
+    traces += [t for t in (random_trace(s) for s in range(40)) if (t.calls["op"] == Op.BACKDROP_BLUR).any()][:4]
+    assert len(traces) >= 4
+    for tr in traces:
+        # same frame sequence on one context: state such as the SDF AA factor carries over from frame to frame
+        full = _render_banded_with_peers(tr, 1)[0]
+        for r, img in enumerate(_render_banded_with_peers(tr, n)):
+            mx, frac = diff_stats(img, full)
+            assert np.array_equal(img, full), f"rank {r}/{n}: max {mx} LSB, {frac:.5%} of pixels"
+
+
+def test_backdrop_blur_under_bands_needs_peers():
+    tr = ss.config_trace(2, 640, 360)
+    ctx = CudaContext(atlasSize=tr.atlas_size, rank=0, nRanks=2)
+    with pytest.raises(FigDrawError, match="fdc_set_peer_framebuffers"):
+        render_trace(tr, ctx)
+    ctx.close()
 
 
 def test_empty_and_degenerate_inputs():

@@ -210,7 +210,9 @@ def main():
     from figdraw_b200 import bands
 
     band_rows, _layout = bands.band_layout(H, world)
-    use_p2p = world > 1 and args.gather == "p2p"
+    # a backdrop blur under a band partition reads halo rows out of the neighbours' framebuffers: peer mappings needed
+    has_blur = bool((trace.calls["op"] == 13).any())
+    use_p2p = world > 1 and (args.gather == "p2p" or has_blur)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
     if use_p2p:
         # Fused all-gather: every rank's shade kernel stores its finished pixels into all peers' framebuffers over

@@ -372,8 +372,11 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
       }
       const bool circ = !(flags & PF_ELLIPTICAL);
       const bool content = !(flags & PF_MASK_WRITE);
-      if (sdf_rect && aligned && circ && content && !(flags & PF_RECTMASK) &&
-          (mode == FDC_SDF_CLIP_AA || mode == FDC_SDF_ANNULAR_AA || mode == FDC_SDF_DROP_SHADOW)) {
+      // Atlas quads (glyphs, images, drawRect) magnified or 1:1 -- one bilinear fetch of level 0 -- take the fast path too.
+      const bool atlas_fast = mode == FDC_SDF_ATLAS && aligned && p.k <= 0.0f;
+      if (aligned && content && !(flags & PF_RECTMASK) &&
+          (atlas_fast || (sdf_rect && circ &&
+                          (mode == FDC_SDF_CLIP_AA || mode == FDC_SDF_ANNULAR_AA || mode == FDC_SDF_DROP_SHADOW)))) {
         // gradient colours as float coefficients of the pixel index (PrimExt)
         bool fast = true;
         if (fill_mode != 0) {
@@ -763,7 +766,7 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
             rows_full = blocks_covered(iy0, iy1, py0, 2, 32, f.H);
           }
           const uint32_t mode = fl & PF_MODE_MASK;
-          const uint32_t kind = mode == FDC_SDF_CLIP_AA ? 0u : (mode == FDC_SDF_ANNULAR_AA ? 1u : 2u);
+          const uint32_t kind = mode == FDC_SDF_CLIP_AA ? 0u : (mode == FDC_SDF_ANNULAR_AA ? 1u : (mode == FDC_SDF_ATLAS ? 3u : 2u));
           uint32_t info = ((fl & PF_FAST) ? TE_FAST : 0u) | ((fl & PF_SOLID) ? TE_SOLID : 0u) |
                           ((fl & PF_FILLMODE_MASK) ? TE_GRAD3 : 0u) | (kind << TE_KIND_SHIFT) |
                           ((fl & PF_OCCLUDER) ? TE_OCCLUDER : 0u) | (((fl & PF_DEPTH_MASK) >> PF_DEPTH_SHIFT) << TE_DEPTH_SHIFT);

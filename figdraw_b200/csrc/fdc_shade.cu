@@ -160,6 +160,7 @@ __device__ __forceinline__ float4 unpack255(uint32_t c) {
 }
 
 __device__ __forceinline__ int wrap_i(int i, int n) {
+  if ((n & (n - 1)) == 0) return i & (n - 1);  // power-of-two atlas (the usual case): no integer division
   int m = i % n;
   return m < 0 ? m + n : m;
 }
@@ -323,8 +324,8 @@ __device__ __forceinline__ void blend(Pixel& px, float sr, float sg, float sb, f
 // Hot path: axis-aligned, circular corners, ClipAA / AnnularAA / DropShadow, content (not a mask write), no rect mask.
 // `info` is the TileEntry word; `full`: the warp's whole block lies in the primitive's inner rect (coverage exactly 1).
 template <bool kMasked>
-__device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const PrimExt* __restrict__ E, uint32_t info, bool full,
-                                           float fx, float fy, Pixel& px) {
+__device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const PrimExt* __restrict__ E, const AtlasView& at,
+                                           uint32_t info, bool full, float fx, float fy, Pixel& px) {
   // S: q0..q4 of the primitive in global memory; all lanes load the same address (L1-resident, one transaction)
   float4 col;
   if (info & TE_SOLID) {
@@ -346,6 +347,21 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
       col.z = fmaf(d0.z, fx, fmaf(a1.z, fy, a0.z));
       col.w = fmaf(d0.w, fx, fmaf(a1.w, fy, a0.w));
     }
+  }
+  if (((info >> TE_KIND_SHIFT) & 3u) == 3u) {
+    // Atlas quad, magnified or 1:1 (atlas.frag:284-292): src = texture(atlas, uv) * vertex colour, coverage 1.
+    const float4 q0 = __ldg(S + 0), q7 = __ldg(S + 7);  // texel map (u0,du,v0,dv); pixel -> (s,t) map
+    const int4 q6 = __ldg(reinterpret_cast<const int4*>(S) + 6);
+    const int ix = (int)fx, iy = (int)fy;
+    const bool inside = ix >= (int16_t)(q6.x & 0xFFFF) && iy >= (int16_t)(q6.x >> 16) && ix < (int16_t)(q6.y & 0xFFFF) &&
+                        iy < (int16_t)(q6.y >> 16);
+    const float s = fmaf(fx, q7.x, q7.y), t = fmaf(fy, q7.z, q7.w);
+    float4 tex = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inside) tex = tex_bilinear(at.level[0], at.size, fmaf(s, q0.y, q0.x), fmaf(t, q0.w, q0.z));
+    float sa = tex.w * col.w * (1.0f / 255.0f) * (1.0f / 255.0f);
+    if (kMasked) sa *= mask_get(px, (int)((info >> TE_DEPTH_SHIFT) & 15u)) * (1.0f / 255.0f);
+    blend(px, tex.x * col.x * (1.0f / 255.0f), tex.y * col.y * (1.0f / 255.0f), tex.z * col.z * (1.0f / 255.0f), inside ? sa : 0.0f);
+    return;
   }
   if (full && (info & TE_OCCLUDER)) {
     // opaque, coverage exactly 1 on the whole block: dst*(1-1) vanishes, the store is round(src) whatever dst was.
@@ -651,8 +667,8 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
         if (info & TE_FAST) {
           const float4* S = reinterpret_cast<const float4*>(a.prims + p);
           const bool full = (info & full_bit) != 0u;
-          if (info & (15u << TE_DEPTH_SHIFT)) shade_fast<true>(S, a.exts + p, info, full, fx, fy, px);
-          else shade_fast<false>(S, a.exts + p, info, full, fx, fy, px);
+          if (info & (15u << TE_DEPTH_SHIFT)) shade_fast<true>(S, a.exts + p, a.atlas, info, full, fx, fy, px);
+          else shade_fast<false>(S, a.exts + p, a.atlas, info, full, fx, fy, px);
         } else {
           px = shade_prim(&a, a.prims + p, ix, iy, px);
         }

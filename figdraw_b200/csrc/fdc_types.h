@@ -52,7 +52,7 @@ constexpr uint32_t TE_FULL_SHIFT = 8;    // bits 8..15: block b lies inside the 
 constexpr uint32_t TE_FAST = 1u << 16;   // PF_FAST
 constexpr uint32_t TE_SOLID = 1u << 17;  // PF_SOLID
 constexpr uint32_t TE_GRAD3 = 1u << 18;  // 3-stop fill (fill mode != 0)
-constexpr uint32_t TE_KIND_SHIFT = 19;   // 2 bits: 0 ClipAA, 1 AnnularAA, 2 DropShadow (fast primitives)
+constexpr uint32_t TE_KIND_SHIFT = 19;   // 2 bits: 0 ClipAA, 1 AnnularAA, 2 DropShadow, 3 atlas quad (fast primitives)
 constexpr uint32_t TE_OCCLUDER = 1u << 21;
 constexpr uint32_t TE_DEPTH_SHIFT = 24;  // 4 bits: texture-mask level read by content
 struct alignas(8) TileEntry {

@@ -373,9 +373,12 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
       const bool circ = !(flags & PF_ELLIPTICAL);
       const bool content = !(flags & PF_MASK_WRITE);
       // Atlas quads (glyphs, images, drawRect) magnified or 1:1 -- one bilinear fetch of level 0 -- take the fast path too.
-      const bool atlas_fast = mode == FDC_SDF_ATLAS && aligned && p.k <= 0.0f;
-      if (aligned && content && !(flags & PF_RECTMASK) &&
-          (atlas_fast || (sdf_rect && circ &&
+      // MSDF / MTSDF quads always sample level 0 (textureLod) and carry one solid colour.
+      const bool atlas_fast = FDC_FAST_TEX && aligned && ((mode == FDC_SDF_ATLAS && p.k <= 0.0f) || (mode >= FDC_SDF_MSDF && mode <= FDC_SDF_MTSDF_ANNULAR));
+      // ClipAA mask writes (beginMask's clip shape) update a mask level instead of the pixel: same SDF, fast path too.
+      const bool mask_fast = FDC_FAST_MASK && (flags & PF_MASK_WRITE) && sdf_rect && circ && mode == FDC_SDF_CLIP_AA && solid && fill_mode == 0;
+      if (aligned && (content || mask_fast) && (FDC_FAST_MASK || !(flags & PF_RECTMASK)) &&
+          ((atlas_fast && content) || (sdf_rect && circ &&
                           (mode == FDC_SDF_CLIP_AA || mode == FDC_SDF_ANNULAR_AA || mode == FDC_SDF_DROP_SHADOW)))) {
         // gradient colours as float coefficients of the pixel index (PrimExt)
         bool fast = true;
@@ -414,7 +417,7 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
       }
       // Inner rect: the pixels where coverage is exactly 1 (ClipAA, DropShadow) or exactly 0 (inside an AnnularAA
       // stroke).  In the cross region |p| <= b - rmax the rounded-box SDF is d = max(|px|-bx, |py|-by).
-      if (sdf_rect && aligned && circ && content && X1 > X0 && Y1 > Y0 && rs.aa > 0.0f &&
+      if (sdf_rect && aligned && circ && (content || mask_fast) && X1 > X0 && Y1 > Y0 && rs.aa > 0.0f &&
           (mode == FDC_SDF_CLIP_AA || mode == FDC_SDF_ANNULAR_AA || mode == FDC_SDF_DROP_SHADOW)) {
         // {d <= -D} of a rounded box is the box shrunk by D with corner radius max(r - D, 0); the largest axis-aligned
         // rect inside it is inset by D + (1 - 1/sqrt2) * max(r - D, 0) from the original edges (rmax is conservative).
@@ -436,7 +439,7 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
           p.ix0 = (int16_t)ix0; p.iy0 = (int16_t)iy0; p.ix1 = (int16_t)ix1; p.iy1 = (int16_t)iy1;
           // occluder: opaque unmasked ClipAA fill -- nothing painted before it survives inside the inner rect
           // (PF_FAST only: the fast path stores the colour directly for such visits, independent of the destination)
-          if (mode == FDC_SDF_CLIP_AA && (flags & PF_FAST) && (flags & PF_DEPTH_MASK) == 0) {
+          if (mode == FDC_SDF_CLIP_AA && (flags & PF_FAST) && (flags & PF_DEPTH_MASK) == 0 && !(flags & (PF_RECTMASK | PF_MASK_WRITE))) {
             uint32_t amin = min(min(cols[0] >> 24, cols[1] >> 24), min(cols[2] >> 24, cols[3] >> 24));
             if (fill_mode != 0) amin = min(amin, min(p.c_mid >> 24, p.c_stop >> 24));
             if (amin == 255u) flags |= PF_OCCLUDER;
@@ -766,10 +769,18 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
             rows_full = blocks_covered(iy0, iy1, py0, 2, 32, f.H);
           }
           const uint32_t mode = fl & PF_MODE_MASK;
-          const uint32_t kind = mode == FDC_SDF_CLIP_AA ? 0u : (mode == FDC_SDF_ANNULAR_AA ? 1u : (mode == FDC_SDF_ATLAS ? 3u : 2u));
-          uint32_t info = ((fl & PF_FAST) ? TE_FAST : 0u) | ((fl & PF_SOLID) ? TE_SOLID : 0u) |
+          uint32_t kind = mode == FDC_SDF_CLIP_AA ? 0u : (mode == FDC_SDF_ANNULAR_AA ? 1u : 2u), tex = 0u;
+          if (mode == FDC_SDF_ATLAS) { tex = TE_TEX; kind = 0u; }
+          else if (mode == FDC_SDF_MSDF) { tex = TE_TEX; kind = 1u; }
+          else if (mode == FDC_SDF_MTSDF) { tex = TE_TEX; kind = 2u; }
+          else if (mode == FDC_SDF_MSDF_ANNULAR) { tex = TE_TEX | TE_GRAD3; kind = 1u; }
+          else if (mode == FDC_SDF_MTSDF_ANNULAR) { tex = TE_TEX | TE_GRAD3; kind = 2u; }
+          uint32_t info = ((fl & PF_FAST) ? TE_FAST : 0u) | ((fl & PF_SOLID) ? TE_SOLID : 0u) | tex |
                           ((fl & PF_FILLMODE_MASK) ? TE_GRAD3 : 0u) | (kind << TE_KIND_SHIFT) |
                           ((fl & PF_OCCLUDER) ? TE_OCCLUDER : 0u) | (((fl & PF_DEPTH_MASK) >> PF_DEPTH_SHIFT) << TE_DEPTH_SHIFT);
+          if (fl & PF_MASK_WRITE) info |= TE_MASKW;
+          if (fl & PF_MASK_BEGIN) info |= TE_MASKB;
+          if (fl & PF_RECTMASK) info |= TE_RECTMASK;
           if (fl & PF_INNER_EMPTY) info |= kInfoEmptyInner;
           if (fl & PF_MASK_BEGIN) info |= kInfoBegin;
           s_pid[k] = pid;

@@ -310,6 +310,15 @@ __device__ float rect_mask_alpha(const RectMaskRec& rm, float aa, float px, floa
   return 1.0f - sat(fmaf(aa, dist, 0.5f));
 }
 
+// Out-of-line versions for the fast path: rare, large (elliptical SDF with IEEE divisions / four texel fetches), scalar in,
+// scalar out -- inlining them into the visit loop costs the hot SDF path registers.
+__device__ __noinline__ float rect_mask_alpha_call(const RectMaskRec* __restrict__ rm, float aa, float px, float py) {
+  return rect_mask_alpha(*rm, aa, px, py);
+}
+__device__ __noinline__ float4 tex_bilinear_call(const uint8_t* __restrict__ img, int size, float tu, float tv) {
+  return tex_bilinear(img, size, tu, tv);
+}
+
 __device__ __forceinline__ void blend(Pixel& px, float sr, float sg, float sb, float sa) {
   // rgb = s*sa + d*(1-sa); a = sa + da*(1-sa)  (glBlendFuncSeparate, glutils.nim:150-154), then UNORM8 store:
   // d + (s - d)*sa evaluated by one FMA into the biased binade = rounded to the UNORM8 grid.  sa == 0 is a no-op.
@@ -325,7 +334,8 @@ __device__ __forceinline__ void blend(Pixel& px, float sr, float sg, float sb, f
 // `info` is the TileEntry word; `full`: the warp's whole block lies in the primitive's inner rect (coverage exactly 1).
 template <bool kMasked>
 __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const PrimExt* __restrict__ E, const AtlasView& at,
-                                           uint32_t info, bool full, float fx, float fy, Pixel& px) {
+                                           const RectMaskRec* __restrict__ rectmasks, uint32_t info, bool full, float fx, float fy,
+                                           Pixel& px) {
   // S: q0..q4 of the primitive in global memory; all lanes load the same address (L1-resident, one transaction)
   float4 col;
   if (info & TE_SOLID) {
@@ -333,7 +343,7 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
   } else {
     const float4* X = reinterpret_cast<const float4*>(E);
     const float4 a0 = __ldg(X + 1), d0 = __ldg(X + 2), a1 = __ldg(X + 3);
-    if (info & TE_GRAD3) {
+    if ((info & (TE_GRAD3 | TE_TEX)) == TE_GRAD3) {
       const float4 e0 = __ldg(X + 0), d1 = __ldg(X + 4);
       const float tt = sat(fmaf(fx, e0.x, fmaf(fy, e0.y, e0.z)));
       const bool lo = tt <= e0.w;
@@ -348,8 +358,9 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
       col.w = fmaf(d0.w, fx, fmaf(a1.w, fy, a0.w));
     }
   }
-  if (((info >> TE_KIND_SHIFT) & 3u) == 3u) {
-    // Atlas quad, magnified or 1:1 (atlas.frag:284-292): src = texture(atlas, uv) * vertex colour, coverage 1.
+  if (FDC_FAST_TEX && (info & TE_TEX)) {
+    // Atlas-sampling quads.  kind 0: texture(atlas, uv) * vertex colour, magnified or 1:1 (atlas.frag:284-292);
+    // kind 1/2: MSDF / MTSDF coverage from textureLod(.., 0) (atlas.frag:294-318), TE_GRAD3 = annular stroke.
     const float4 q0 = __ldg(S + 0), q7 = __ldg(S + 7);  // texel map (u0,du,v0,dv); pixel -> (s,t) map
     const int4 q6 = __ldg(reinterpret_cast<const int4*>(S) + 6);
     const int ix = (int)fx, iy = (int)fy;
@@ -357,10 +368,25 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
                         iy < (int16_t)(q6.y >> 16);
     const float s = fmaf(fx, q7.x, q7.y), t = fmaf(fy, q7.z, q7.w);
     float4 tex = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (inside) tex = tex_bilinear(at.level[0], at.size, fmaf(s, q0.y, q0.x), fmaf(t, q0.w, q0.z));
-    float sa = tex.w * col.w * (1.0f / 255.0f) * (1.0f / 255.0f);
-    if (kMasked) sa *= mask_get(px, (int)((info >> TE_DEPTH_SHIFT) & 15u)) * (1.0f / 255.0f);
-    blend(px, tex.x * col.x * (1.0f / 255.0f), tex.y * col.y * (1.0f / 255.0f), tex.z * col.z * (1.0f / 255.0f), inside ? sa : 0.0f);
+    if (inside) tex = tex_bilinear_call(at.level[0], at.size, fmaf(s, q0.y, q0.x), fmaf(t, q0.w, q0.z));
+    const uint32_t kind = (info >> TE_KIND_SHIFT) & 3u;
+    float sr = col.x, sg = col.y, sb = col.z, sa;
+    if (kind == 0u) {
+      sr = tex.x * col.x * (1.0f / 255.0f); sg = tex.y * col.y * (1.0f / 255.0f); sb = tex.z * col.z * (1.0f / 255.0f);
+      sa = tex.w * col.w * (1.0f / 255.0f) * (1.0f / 255.0f);
+    } else {
+      const float4 q1 = __ldg(S + 1), q3 = __ldg(S + 3);  // q1.y stroke weight; q3 = (pxRange, sdThreshold, aa, screenPxRange)
+      const float sd = (kind == 2u ? tex.w : fmaxf(fminf(tex.x, tex.y), fminf(fmaxf(tex.x, tex.y), tex.z))) * (1.0f / 255.0f);
+      const float spd = q3.w * (sd - q3.y);
+      const float cov = (info & TE_GRAD3) ? sat(fmaxf(q1.y, 0.0f) * 0.5f - fabsf(spd) + 0.5f) : sat(spd + 0.5f);
+      sa = col.w * (1.0f / 255.0f) * cov;
+    }
+    if (kMasked && (info & (15u << TE_DEPTH_SHIFT))) sa *= mask_get(px, (int)((info >> TE_DEPTH_SHIFT) & 15u)) * (1.0f / 255.0f);
+    if (FDC_FAST_MASK && kMasked && (info & TE_RECTMASK)) {
+      const float aa = __ldg(S + 3).z;
+      if (inside) sa *= rect_mask_alpha_call(rectmasks + (((uint32_t)q6.w & 0xFFFFu) - 1u), aa, fx + 0.5f, fy + 0.5f);
+    }
+    blend(px, sr, sg, sb, inside ? sa : 0.0f);
     return;
   }
   if (full && (info & TE_OCCLUDER)) {
@@ -369,12 +395,14 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
     px.r = col.x + kBias; px.g = col.y + kBias; px.b = col.z + kBias; px.a = 255.0f + kBias;
     return;
   }
+  if (FDC_FAST_MASK && kMasked && (info & TE_MASKB)) mask_set(px, (int)((info >> TE_DEPTH_SHIFT) & 15u), 0.0f);  // glClear(0) of the level, glcontext.nim:1901-1902
   float sa = col.w * (1.0f / 255.0f);
+  bool inside = true;
   if (!full) {
     const float4 q0 = __ldg(S + 0), q1 = __ldg(S + 1), q2 = __ldg(S + 2), q3 = __ldg(S + 3);
     const float ppx = fmaf(fx, q0.x, q0.y), ppy = fmaf(fy, q0.z, q0.w);  // (p.x, -p.y)
     const float apx = fabsf(ppx), apy = fabsf(ppy);
-    const bool inside = apx < q1.x && apy < q1.y;  // pixel centre inside the ceil'd quad
+    inside = apx < q1.x && apy < q1.y;  // pixel centre inside the ceil'd quad
     const float rr = ppx > 0.0f ? (ppy > 0.0f ? q2.x : q2.y) : (ppy > 0.0f ? q2.z : q2.w);
     const float qx = apx - q1.z + rr, qy = apy - q1.w + rr;
     const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
@@ -392,7 +420,23 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
     }
     sa = inside ? sa * cov : 0.0f;
   }
-  if (kMasked) sa *= mask_get(px, (int)((info >> TE_DEPTH_SHIFT) & 15u)) * (1.0f / 255.0f);
+  if (FDC_FAST_MASK && kMasked && (info & TE_MASKW)) {
+    // mask.frag:219-233 for a ClipAA clip shape: alpha = cov * colour.a * previous level; the R8 target is written
+    // with blending still on, so the stored value is a*a + m*(1-a) (SURVEY 8a' trap 1), quantised.
+    const int depth = (int)((info >> TE_DEPTH_SHIFT) & 15u);
+    float al = sa;
+    if (depth > 1) al *= mask_get(px, depth - 1) * (1.0f / 255.0f);
+    if (inside) {
+      const float m = mask_get(px, depth);
+      mask_set(px, depth, rint255(fmaf(al, 255.0f * al, m * (1.0f - al))));
+    }
+    return;
+  }
+  if (kMasked && (info & (15u << TE_DEPTH_SHIFT))) sa *= mask_get(px, (int)((info >> TE_DEPTH_SHIFT) & 15u)) * (1.0f / 255.0f);
+  if (FDC_FAST_MASK && kMasked && (info & TE_RECTMASK)) {
+    const uint32_t aux = (uint32_t)__ldg(reinterpret_cast<const int4*>(S) + 6).w;
+    if (sa > 0.0f) sa *= rect_mask_alpha_call(rectmasks + ((aux & 0xFFFFu) - 1u), __ldg(S + 3).z, fx + 0.5f, fy + 0.5f);
+  }
   blend(px, col.x, col.y, col.z, sa);
 }
 
@@ -667,8 +711,8 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
         if (info & TE_FAST) {
           const float4* S = reinterpret_cast<const float4*>(a.prims + p);
           const bool full = (info & full_bit) != 0u;
-          if (info & (15u << TE_DEPTH_SHIFT)) shade_fast<true>(S, a.exts + p, a.atlas, info, full, fx, fy, px);
-          else shade_fast<false>(S, a.exts + p, a.atlas, info, full, fx, fy, px);
+          if (info & ((15u << TE_DEPTH_SHIFT) | TE_RECTMASK)) shade_fast<true>(S, a.exts + p, a.atlas, a.rectmasks, info, full, fx, fy, px);
+          else shade_fast<false>(S, a.exts + p, a.atlas, a.rectmasks, info, full, fx, fy, px);
         } else {
           px = shade_prim(&a, a.prims + p, ix, iy, px);
         }

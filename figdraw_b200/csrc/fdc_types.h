@@ -47,14 +47,26 @@ constexpr uint32_t PF_EMPTY = 1u << 31;         // dropped (early-out or empty c
 // Tile-list entry (8 bytes): .x = primitive index (bit 31: unused), .y = everything the shade kernel needs to decide
 // what each of the tile's 8 warps (8x4-pixel blocks; block = row*2 + col) does with the primitive, precomputed once
 // per (tile, primitive) by fine_bin_kernel instead of 8 times per pair by the shading warps.
+// Compile-time switches for the optional fast paths (A/B measurements; all on by default).
+#ifndef FDC_FAST_TEX
+#define FDC_FAST_TEX 1
+#endif
+#ifndef FDC_FAST_MASK
+#define FDC_FAST_MASK 1
+#endif
+
 constexpr uint32_t TE_OV_SHIFT = 0;      // bits 0..7 : the primitive's clipped bbox overlaps block b
 constexpr uint32_t TE_FULL_SHIFT = 8;    // bits 8..15: block b lies inside the inner rect (coverage exactly 1)
 constexpr uint32_t TE_FAST = 1u << 16;   // PF_FAST
 constexpr uint32_t TE_SOLID = 1u << 17;  // PF_SOLID
 constexpr uint32_t TE_GRAD3 = 1u << 18;  // 3-stop fill (fill mode != 0)
-constexpr uint32_t TE_KIND_SHIFT = 19;   // 2 bits: 0 ClipAA, 1 AnnularAA, 2 DropShadow, 3 atlas quad (fast primitives)
+constexpr uint32_t TE_KIND_SHIFT = 19;   // 2 bits: 0 ClipAA, 1 AnnularAA, 2 DropShadow; with TE_TEX: 0 atlas, 1 MSDF, 2 MTSDF (fast primitives)
 constexpr uint32_t TE_OCCLUDER = 1u << 21;
-constexpr uint32_t TE_DEPTH_SHIFT = 24;  // 4 bits: texture-mask level read by content
+constexpr uint32_t TE_TEX = 1u << 22;    // fast primitive that samples the atlas (kind selects atlas / MSDF / MTSDF; TE_GRAD3 = annular stroke)
+constexpr uint32_t TE_MASKW = 1u << 23;  // fast ClipAA mask write (PF_MASK_WRITE): updates mask level DEPTH instead of the pixel
+constexpr uint32_t TE_DEPTH_SHIFT = 24;  // 4 bits: texture-mask level read by content (written by TE_MASKW)
+constexpr uint32_t TE_MASKB = 1u << 28;  // PF_MASK_BEGIN: clear the level first
+constexpr uint32_t TE_RECTMASK = 1u << 29;  // content under a first-level analytic rect mask (PF_RECTMASK)
 struct alignas(8) TileEntry {
   uint32_t pid, info;
 };

@@ -91,6 +91,48 @@ class FdcFill(ctypes.Structure):
     ]
 
 
+# ---- scene PODs of the native front-end (include/figdraw_cuda.h, "Scene flattening in native code")
+NODE_FILL_DTYPE = np.dtype([("kind", "u1"), ("axis", "u1"), ("mid_pos", "u1"), ("_pad", "u1"), ("c", "<u4", (3,))])
+NODE_SHADOW_DTYPE = np.dtype([("style", "<u4"), ("fill", NODE_FILL_DTYPE), ("blur", "<f4"), ("spread", "<f4"), ("x", "<f4"),
+                              ("y", "<f4")])
+NODE_STROKE_DTYPE = np.dtype([("weight", "<f4"), ("fill", NODE_FILL_DTYPE), ("cap", "u1"), ("join", "u1"), ("_pad", "u1", (2,))])
+FIG_PAYLOAD_BYTES = 168
+FIG_DTYPE = np.dtype({
+    "names": ["kind", "zlevel", "flags", "parent", "child_count", "screen_box", "rotation", "fill", "corners",
+              "corner_radii_y", "payload"],
+    "formats": ["u1", "i1", "<u2", "<i4", "<i4", ("<f4", (4,)), "<f4", NODE_FILL_DTYPE, ("<f4", (4,)), ("<f4", (4,)),
+                ("u1", (FIG_PAYLOAD_BYTES,))],
+    "offsets": [0, 1, 2, 4, 8, 12, 28, 32, 48, 64, 80],
+    "itemsize": 248,
+})
+# kind-specific views of `payload` (the C union)
+FIG_RECT_DTYPE = np.dtype([("shadows", NODE_SHADOW_DTYPE, (4,)), ("stroke", NODE_STROKE_DTYPE)])
+FIG_TEXT_DTYPE = np.dtype([("first_glyph", "<u4"), ("n_glyphs", "<u4")])
+FIG_DRAWABLE_DTYPE = np.dtype([("stroke", NODE_STROKE_DTYPE), ("steps", "<i4"), ("aa", "<f4"), ("first_op", "<u4"),
+                               ("n_ops", "<u4")])
+FIG_IMAGE_DTYPE = np.dtype([("id", "<u8"), ("fill", NODE_FILL_DTYPE)])
+FIG_MSDF_DTYPE = np.dtype([("id", "<u8"), ("fill", NODE_FILL_DTYPE), ("px_range", "<f4"), ("sd_threshold", "<f4"),
+                           ("stroke_weight", "<f4")])
+FIG_BACKDROP_DTYPE = np.dtype([("blur", "<f4")])
+FIG_TRANSFORM_DTYPE = np.dtype([("translation", "<f4", (2,)), ("matrix", "<f4", (16,)), ("use_matrix", "<u4")])
+GLYPH_DTYPE = np.dtype([("key", "<u8"), ("pos", "<f4", (2,)), ("fill", NODE_FILL_DTYPE)])
+DRAW_OP_DTYPE = np.dtype([("kind", "<u4"), ("a", "<f4", (2,)), ("b", "<f4", (2,)), ("center", "<f4", (2,)), ("radius", "<f4"),
+                          ("box", "<f4", (4,)), ("corners", "<f4", (4,)), ("ellipse_radii", "<f4", (2,)),
+                          ("controls", "<f4", (6,)), ("n_controls", "<u4")])
+assert NODE_FILL_DTYPE.itemsize == 16 and NODE_SHADOW_DTYPE.itemsize == 36 and NODE_STROKE_DTYPE.itemsize == 24
+assert FIG_RECT_DTYPE.itemsize == FIG_PAYLOAD_BYTES and GLYPH_DTYPE.itemsize == 32 and DRAW_OP_DTYPE.itemsize == 100
+
+
+class FdcRenderList(ctypes.Structure):
+    _fields_ = [("nodes", ctypes.c_void_p), ("n_nodes", ctypes.c_uint32), ("root_ids", ctypes.c_void_p),
+                ("n_roots", ctypes.c_uint32)]
+
+
+class FdcFlattenEnv(ctypes.Structure):
+    _fields_ = [("ui_scale", ctypes.c_float), ("pixel_scale", ctypes.c_float), ("aa_factor", ctypes.c_float),
+                ("subpixel_enabled", ctypes.c_uint32), ("image_keys", ctypes.c_void_p), ("n_image_keys", ctypes.c_size_t)]
+
+
 class FdcFrameStats(ctypes.Structure):
     _fields_ = [
         ("n_prims", ctypes.c_uint32),
@@ -124,6 +166,7 @@ EXPORTS = [
     "fdc_reset_image_atlas", "fdc_atlas_size", "fdc_atlas_packed_area",
     "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers", "fdc_reserve_framebuffer", "fdc_framebuffer_ipc_handle", "fdc_open_peer_framebuffer",
     "fdc_get_frame_stats", "fdc_debug_bins", "fdc_debug_shade_stats",
+    "fdc_flatten_renders", "fdc_render_frame",
 ]
 
 _LIB: Optional[ctypes.CDLL] = None
@@ -210,6 +253,10 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_open_peer_framebuffer", c.c_int, P, c.POINTER(c.c_uint8), c.POINTER(P))
     sig("fdc_get_frame_stats", c.c_int, P, c.POINTER(FdcFrameStats))
     sig("fdc_debug_shade_stats", c.c_int, P, c.POINTER(c.c_uint64))
+    sig("fdc_flatten_renders", c.c_int, c.POINTER(FdcRenderList), c.c_uint32, c.c_void_p, c.c_void_p,
+        c.POINTER(FdcFlattenEnv), c.c_void_p, c.c_size_t, c.POINTER(c.c_size_t))
+    sig("fdc_render_frame", c.c_int, P, c.POINTER(FdcRenderList), c.c_uint32, c.c_void_p, c.c_void_p, c.c_float,
+        c.c_float, c.c_float, c.c_int, c.POINTER(c.c_float))
     sig("fdc_debug_bins", c.c_int, P, c.c_int, u32p, c.c_size_t, u32p, c.c_size_t, c.POINTER(c.c_size_t),
         c.POINTER(c.c_size_t))
     if lib.fdc_abi_version() != ABI_VERSION:

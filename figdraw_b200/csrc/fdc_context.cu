@@ -18,6 +18,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "fdc_flatten.h"
 #include "fdc_kernels.h"
 
 using namespace fdc;
@@ -201,6 +202,7 @@ struct fdc_ctx {
   std::vector<uint16_t> heights;
   struct Rect4 { float x, y, w, h; };
   std::unordered_map<uint64_t, Rect4> entries;
+  std::vector<fdc_call> flat_calls;  // scratch of fdc_render_frame
   DevBuf<AtlasEntry> d_table;
   uint32_t table_cap = 0;
   bool table_dirty = true;
@@ -1537,6 +1539,39 @@ int fdc_debug_shade_stats(fdc_ctx* ctx, uint64_t out[8]) {
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(out, ctx->d_stats.p, 64, cudaMemcpyDeviceToHost));
   return FDC_OK;
+}
+
+// renderFrame (figrender.nim:1960-2002) with the front-end DFS run natively: beginFrame, the flattened scene, endFrame.
+int fdc_render_frame(fdc_ctx* ctx, const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs,
+                     const fdc_draw_op* ops, float ui_scale, float frame_w, float frame_h, int clear_main,
+                     const float clear_rgba[4]) {
+  if (!ctx || (!lists && n_lists)) return FDC_ERR_INVALID;
+  if (!(ui_scale > 0.0f)) return ctx->fail(FDC_ERR_INVALID, "ui_scale must be positive");
+  std::vector<uint64_t> keys;
+  keys.reserve(ctx->entries.size());
+  for (auto& kv : ctx->entries) keys.push_back(kv.first);
+  std::sort(keys.begin(), keys.end());
+  fdc_flatten_env env;
+  env.ui_scale = ui_scale;
+  env.pixel_scale = ctx->pixel_scale;
+  env.aa_factor = ctx->aa;
+  env.subpixel_enabled = ctx->subpixel_enabled ? 1u : 0u;
+  env.image_keys = keys.data();
+  env.n_image_keys = keys.size();
+  // the scratch keeps last frame's size: a steady scene flattens in one pass into memory that is already mapped
+  if (ctx->flat_calls.size() < 1024) ctx->flat_calls.resize(1024);
+  size_t n_calls = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    const char* err = fdc::flatten_renders(lists, n_lists, glyphs, ops, env, ctx->flat_calls.data(), ctx->flat_calls.size(), &n_calls);
+    if (err) return ctx->fail(FDC_ERR_INVALID, "%s", err);
+    if (n_calls <= ctx->flat_calls.size()) break;
+    ctx->flat_calls.resize(n_calls + n_calls / 8);
+  }
+  int rc = fdc_begin_frame(ctx, (int)(frame_w * ui_scale), (int)(frame_h * ui_scale), clear_main, clear_rgba);
+  if (rc) return rc;
+  rc = fdc_submit_calls(ctx, ctx->flat_calls.data(), n_calls);
+  if (rc) return rc;
+  return fdc_end_frame(ctx);
 }
 
 int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t offsets_cap, uint32_t* entries, size_t entries_cap,

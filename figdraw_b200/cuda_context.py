@@ -269,6 +269,15 @@ class CudaContext(BackendContext):
             else:
                 self._ck(self._lib.fdc_submit_calls(self._h, calls[a:b].ctypes.data, b - a))
 
+    def renderFrameNative(self, scene, frameSize, uiScale: float = 1.0, clearMain: bool = True,
+                          clearColor=(1.0, 1.0, 1.0, 1.0)):
+        """renderFrame (figrender.nim:1960-2002) with the scene DFS run natively: `scene` is a
+        native_scene.PackedScene (POD `fdc_fig` arrays); one FFI call per frame instead of one per backend call."""
+        from . import native_scene
+
+        self._frame = (int(float(frameSize[0]) * uiScale), int(float(frameSize[1]) * uiScale))
+        native_scene.render_frame(self, scene, frameSize, uiScale, clearMain, clearColor)
+
     def frameStats(self) -> FdcFrameStats:
         st = FdcFrameStats()
         self._ck(self._lib.fdc_get_frame_stats(self._h, ctypes.byref(st)))

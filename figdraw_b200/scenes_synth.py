@@ -306,12 +306,8 @@ def _rounded_rect_calls(n: int) -> np.ndarray:
     return c
 
 
-def rects_and_glyphs(width: int, height: int, n_rects: int = 100_000, n_glyphs: int = 20_000, seed: int = 5,
-                     scale: float = 1.0, layers: int = 4) -> Trace:
-    """cfg5 (SURVEY 8d): n_rects rounded rects, each with a drop shadow, 25 % with a 2 px stroke, 30 % with a
-    3-stop gradient, plus n_glyphs atlas glyph quads, spread over `layers` z-levels in emission order.
-    Emits exactly the calls figrender.nim makes per node: drop shadow (:654-689) -> fill -> stroke (:806-873);
-    text: save/translate, one drawImage per glyph, restore (:417-497)."""
+def _cfg5_params(width: int, height: int, n_rects: int, seed: int, scale: float):
+    """The random node parameters of cfg5, shared by the call-level generator and the node-level one."""
     rng = Rng(seed)
     S = f32(scale)
     W, H = f32(width), f32(height)
@@ -333,6 +329,21 @@ def rects_and_glyphs(width: int, height: int, n_rects: int = 100_000, n_glyphs: 
     base_col = pack_rgba(cr, cg, cb, alpha)
     mid_col = pack_rgba((cr + 40) % 256, (cg + 90) % 256, cb, 255)
     stop_col = pack_rgba(cb, cr, (cg + 128) % 256, 255)
+
+    return dict(rng=rng, S=S, w=w, h=h, x=x, y=y, radii=radii, cr=cr, cg=cg, cb=cb, alpha=alpha, grad=grad, axis=axis, blur=blur,
+                spread=spread, sx=sx, sy=sy, stroke=stroke, base_col=base_col, mid_col=mid_col, stop_col=stop_col)
+
+
+def rects_and_glyphs(width: int, height: int, n_rects: int = 100_000, n_glyphs: int = 20_000, seed: int = 5,
+                     scale: float = 1.0, layers: int = 4) -> Trace:
+    """cfg5 (SURVEY 8d): n_rects rounded rects, each with a drop shadow, 25 % with a 2 px stroke, 30 % with a
+    3-stop gradient, plus n_glyphs atlas glyph quads, spread over `layers` z-levels in emission order.
+    Emits exactly the calls figrender.nim makes per node: drop shadow (:654-689) -> fill -> stroke (:806-873);
+    text: save/translate, one drawImage per glyph, restore (:417-497)."""
+    P = _cfg5_params(width, height, n_rects, seed, scale)
+    rng, S, w, h, x, y, radii = P["rng"], P["S"], P["w"], P["h"], P["x"], P["y"], P["radii"]
+    cr, cg, cb, grad, axis, blur, spread = P["cr"], P["cg"], P["cb"], P["grad"], P["axis"], P["blur"], P["spread"]
+    sx, sy, stroke, base_col, mid_col, stop_col = P["sx"], P["sy"], P["stroke"], P["base_col"], P["mid_col"], P["stop_col"]
 
     # drop shadow quads
     sh = _rounded_rect_calls(n_rects)
@@ -416,6 +427,89 @@ def rects_and_glyphs(width: int, height: int, n_rects: int = 100_000, n_glyphs: 
     tb.restoreTransform()
     tb.endFrame()
     return tb.trace()
+
+
+def rects_and_glyphs_scene(width: int, height: int, n_rects: int = 100_000, n_glyphs: int = 20_000, seed: int = 5,
+                           scale: float = 1.0, layers: int = 4):
+    """cfg5 as a SCENE: the `Fig` records (one nkRectangle per rect with its drop shadow and stroke, one nkText per layer)
+    whose flattening is exactly the call stream of `rects_and_glyphs`.  Built straight into the POD arrays of the native
+    front-end (abi.FIG_DTYPE) -- 100k Python `Fig` objects would take longer to build than a thousand frames to render."""
+    import ctypes
+
+    from . import abi
+    from .native_scene import PackedScene
+
+    P = _cfg5_params(width, height, n_rects, seed, scale)
+    rng, S = P["rng"], P["S"]
+    nodes = np.zeros(n_rects, dtype=abi.FIG_DTYPE)
+    nodes["kind"] = 2  # nkRectangle
+    nodes["parent"] = -1
+    nodes["screen_box"] = np.stack([P["x"], P["y"], P["w"], P["h"]], axis=1)
+    nodes["corners"] = P["radii"]
+    nodes["corner_radii_y"] = P["radii"]
+    g = P["grad"]
+    nodes["fill"]["kind"] = np.where(g, 2, 0)
+    nodes["fill"]["axis"] = np.where(g, P["axis"], 0)
+    nodes["fill"]["mid_pos"] = 128
+    nodes["fill"]["c"][:, 0] = np.where(g, pack_rgba(P["cr"], P["cg"], P["cb"], 255), P["base_col"])
+    nodes["fill"]["c"][:, 1] = np.where(g, P["mid_col"], 0)
+    nodes["fill"]["c"][:, 2] = np.where(g, P["stop_col"], 0)
+    pay = nodes["payload"].view(abi.FIG_RECT_DTYPE).reshape(n_rects)
+    sh = pay["shadows"][:, 0]
+    sh["style"] = 1  # DropShadow
+    sh["fill"]["mid_pos"] = 128
+    sh["fill"]["c"][:, 0] = pack_rgba(0, 0, 0, 90)
+    # the call-level generator applies `scale` to the already-scaled values; uiScale stays 1
+    sh["blur"], sh["spread"], sh["x"], sh["y"] = P["blur"], P["spread"], P["sx"], P["sy"]
+    pay["stroke"]["weight"] = np.where(P["stroke"], f32(2.0) * S, f32(0.0))
+    pay["stroke"]["fill"]["mid_pos"] = 128
+    pay["stroke"]["fill"]["c"][:, 0] = pack_rgba(P["cb"] // 3, P["cr"] // 3, P["cg"] // 3, 255)
+
+    gw, gh = GLYPH_W, GLYPH_H
+    cols = max(1, int(width) // gw)
+    which = rng.integers(n_glyphs, 0, N_GLYPHS)
+    glyphs = np.zeros(max(n_glyphs, 1), dtype=abi.GLYPH_DTYPE)
+    gi = np.arange(n_glyphs)
+    glyphs["key"][:n_glyphs] = (GLYPH_KEY0 + which).astype(np.uint64)
+    glyphs["pos"][:n_glyphs, 0] = (gi % cols) * gw
+    glyphs["pos"][:n_glyphs, 1] = (gi // cols) * gh
+    glyphs["fill"]["mid_pos"] = 128
+    glyphs["fill"]["c"][:n_glyphs, 0] = pack_rgba(rng.integers(n_glyphs, 0, 256), rng.integers(n_glyphs, 0, 256),
+                                                  rng.integers(n_glyphs, 0, 256), 255)
+
+    node_arrays, root_arrays = [], []
+    for L in range(layers):
+        r0, r1 = n_rects * L // layers, n_rects * (L + 1) // layers
+        g0, g1 = n_glyphs * L // layers, n_glyphs * (L + 1) // layers
+        extra = (1 if L == 0 else 0) + (1 if g1 > g0 else 0)
+        arr = np.zeros(r1 - r0 + extra, dtype=abi.FIG_DTYPE)
+        k = 0
+        if L == 0:  # background
+            arr[0]["kind"], arr[0]["parent"] = 2, -1
+            arr[0]["screen_box"] = (0.0, 0.0, float(width), float(height))
+            arr[0]["fill"]["mid_pos"] = 128
+            arr[0]["fill"]["c"][0] = rgba(250, 250, 252, 255)
+            k = 1
+        arr[k : k + r1 - r0] = nodes[r0:r1]
+        if g1 > g0:
+            t = arr[-1]
+            t["kind"], t["parent"] = 1, -1  # nkText
+            t["fill"]["mid_pos"] = 128
+            tv = t["payload"][: abi.FIG_TEXT_DTYPE.itemsize].view(abi.FIG_TEXT_DTYPE)[0]
+            tv["first_glyph"], tv["n_glyphs"] = g0, g1 - g0
+        arr["zlevel"] = L
+        node_arrays.append(arr)
+        root_arrays.append(np.arange(len(arr), dtype=np.int32))
+    lists = (abi.FdcRenderList * layers)()
+    for i, (na, ra) in enumerate(zip(node_arrays, root_arrays)):
+        lists[i].nodes, lists[i].n_nodes = na.ctypes.data, len(na)
+        lists[i].root_ids, lists[i].n_roots = ra.ctypes.data, len(ra)
+    ops = np.zeros(1, dtype=abi.DRAW_OP_DTYPE)
+    return PackedScene(node_arrays, root_arrays, glyphs, ops, lists)
+
+
+def glyph_image_keys():
+    return [GLYPH_KEY0 + i for i in range(N_GLYPHS)]
 
 
 # ----------------------------------------------------------------------------- trace helpers

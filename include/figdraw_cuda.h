@@ -268,6 +268,116 @@ int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t off
  * coverage, [2] of which on the general path, [3] 32-entry list steps walked, [4] occlusion-scan steps. */
 int fdc_debug_shade_stats(fdc_ctx* ctx, uint64_t out[8]);
 
+/* ---------------------------------------------------------------------------------------------
+ * Scene flattening in native code.  Replaces the Nim front-end DFS for hosts that hand
+ * over the scene itself instead of making ~45 backend calls per node:
+ *   renderFrame figrender.nim:1960-2002, renderRoot :1946-1958, render :1756-1839 (stage order),
+ *   renderDropShadows :654-689, renderInnerShadows :716-744, renderRoundedShapeScaledCorners :806-873,
+ *   renderText :417-497 (glyph loop), renderImage/renderMsdfImage/renderMtsdfImage/renderBackdropBlur :1673-1754,
+ *   renderDrawable :1653-1667 (line :946-995, circle :1122-1136, rect :1138-1142, ellipse :1617-1635,
+ *   3-control Bezier :1330-1370), gradientColors :623-647, toBackendFill figbackend.nim:109-127.
+ * The node records are PODs mirroring `Fig` (fignodes.nim:53-92); `seq` members (glyphs, drawable ops) live in
+ * side arrays the nodes index.  Layers are rendered in array order (the reference does not sort, figrender.nim:1951).
+ */
+typedef struct fdc_node_fill { /* Fill, common/filltypes.nim:34-42 */
+  uint8_t kind;                /* 0 flColor, 1 flLinear2, 2 flLinear3 */
+  uint8_t axis;                /* fdc_axis */
+  uint8_t mid_pos;             /* uint8, flLinear3 */
+  uint8_t _pad;
+  uint32_t c[3];               /* flColor: c[0]; flLinear2: start c[0], stop c[2]; flLinear3: start, mid, stop */
+} fdc_node_fill;               /* 16 bytes */
+
+typedef struct fdc_node_shadow { /* RenderShadow, figbasics.nim:78-90 */
+  uint32_t style;              /* 0 none, 1 DropShadow, 2 InnerShadow */
+  fdc_node_fill fill;
+  float blur, spread, x, y;
+} fdc_node_shadow;             /* 36 bytes */
+
+typedef struct fdc_node_stroke { /* RenderStroke, figbasics.nim:92-100 */
+  float weight;
+  fdc_node_fill fill;
+  uint8_t cap;                 /* 0 auto, 1 round, 2 butt, 3 square */
+  uint8_t join;
+  uint8_t _pad[2];
+} fdc_node_stroke;             /* 24 bytes */
+
+typedef enum fdc_fig_kind { /* FigKind, figbasics.nim:14-26 */
+  FDC_NK_FRAME = 0, FDC_NK_TEXT = 1, FDC_NK_RECTANGLE = 2, FDC_NK_DRAWABLE = 3, FDC_NK_SCROLLBAR = 4, FDC_NK_IMAGE = 5,
+  FDC_NK_MSDF_IMAGE = 6, FDC_NK_MTSDF_IMAGE = 7, FDC_NK_BACKDROP_BLUR = 8, FDC_NK_TRANSFORM = 9
+} fdc_fig_kind;
+
+typedef enum fdc_fig_flags { /* FigFlags, figbasics.nim:28-38 */
+  FDC_NF_CLIP_CONTENT = 1, FDC_NF_DISABLE_RENDER = 2, FDC_NF_ROOT_WINDOW = 4, FDC_NF_INACTIVE = 8, FDC_NF_SELECT_TEXT = 16,
+  FDC_NF_INVERT_Y = 32, FDC_NF_RECT_MASK_CONTENT = 64, FDC_NF_ELLIPTICAL_CORNERS = 128
+} fdc_fig_flags;
+
+typedef struct fdc_fig {
+  uint8_t kind;                /* fdc_fig_kind */
+  int8_t zlevel;
+  uint16_t flags;              /* fdc_fig_flags */
+  int32_t parent;              /* index in the same list, -1 for roots */
+  int32_t child_count;
+  float screen_box[4];         /* x, y, w, h (before uiScale) */
+  float rotation;              /* degrees */
+  fdc_node_fill fill;
+  float corners[4];            /* TL, TR, BL, BR */
+  float corner_radii_y[4];     /* used with FDC_NF_ELLIPTICAL_CORNERS */
+  union {                      /* kind-specific payload (the reference's variant object) */
+    struct { fdc_node_shadow shadows[4]; fdc_node_stroke stroke; } rect;                       /* nkRectangle */
+    struct { uint32_t first_glyph, n_glyphs; } text;                                           /* nkText -> fdc_glyph[] */
+    struct { fdc_node_stroke stroke; int32_t steps; float aa; uint32_t first_op, n_ops; } drawable; /* -> fdc_draw_op[] */
+    struct { uint64_t id; fdc_node_fill fill; } image;                                         /* nkImage */
+    struct { uint64_t id; fdc_node_fill fill; float px_range, sd_threshold, stroke_weight; } msdf; /* nkMsdfImage / nkMtsdfImage */
+    struct { float blur; } backdrop;                                                           /* nkBackdropBlur */
+    struct { float translation[2]; float matrix[16]; uint32_t use_matrix; } transform;         /* nkTransform */
+  } u;
+} fdc_fig;                     /* 248 bytes */
+
+typedef struct fdc_glyph {     /* what renderText consumes per glyph (figrender.nim:456-493) */
+  uint64_t key;                /* atlas key of the glyph bitmap */
+  float pos[2];                /* glyphLocalPos + imageOffset, already scaled */
+  fdc_node_fill fill;
+} fdc_glyph;                   /* 32 bytes */
+
+typedef struct fdc_draw_op {   /* DrawableOp, figbasics.nim (drawables) */
+  uint32_t kind;               /* 0 line, 1 circle, 2 rectangle, 3 bezier, 4 arc, 5 ellipse */
+  float a[2], b[2];            /* line */
+  float center[2];             /* circle, ellipse */
+  float radius;                /* circle */
+  float box[4];                /* rectangle */
+  float corners[4];            /* rectangle */
+  float ellipse_radii[2];
+  float controls[6];           /* bezier: p0, p1, p2 */
+  uint32_t n_controls;
+} fdc_draw_op;                 /* 100 bytes */
+
+typedef struct fdc_render_list { /* RenderList, fignodes.nim:44-46 */
+  const fdc_fig* nodes;
+  uint32_t n_nodes;
+  const int32_t* root_ids;
+  uint32_t n_roots;
+} fdc_render_list;
+
+typedef struct fdc_flatten_env {
+  float ui_scale;              /* figUiScale(), common/shared.nim:67-71 */
+  float pixel_scale;           /* BackendContext.pixelScale */
+  float aa_factor;             /* sdfAaFactor at frame start */
+  uint32_t subpixel_enabled;   /* textSubpixelPositioningEnabled at frame start */
+  const uint64_t* image_keys;  /* sorted ascending: keys for which hasImage() is true */
+  size_t n_image_keys;
+} fdc_flatten_env;
+
+/* Pure host function (no context, no GPU): the body of renderFrame between beginFrame and endFrame as `fdc_call`
+ * records -- saveTransform, scale(pixelScale), every layer's roots in order, restoreTransform.  Writes at most `cap`
+ * records; *n_out is the number needed (FDC_ERR_CAPACITY when cap was too small). */
+int fdc_flatten_renders(const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs, const fdc_draw_op* ops,
+                        const fdc_flatten_env* env, fdc_call* out, size_t cap, size_t* n_out);
+
+/* renderFrame on a context: beginFrame(frame size * uiScale), the flattened scene, endFrame. */
+int fdc_render_frame(fdc_ctx* ctx, const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs,
+                     const fdc_draw_op* ops, float ui_scale, float frame_w, float frame_h, int clear_main,
+                     const float clear_rgba[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,8 @@ The shading arithmetic is float32 on both sides but the kernel uses FMA contract
 so a pixel whose exact value sits on a rounding boundary may land one LSB away; MAX_DIFF states the bar and
 MAX_FRACTION bounds how many pixels may differ at all.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -309,4 +311,46 @@ def test_submit_draws_equals_submit_calls():
     off, ent = ctx.debugBins(0)
     ref_off, ref_ent = oracle.reference_bins(tr)[0]
     assert np.array_equal(off, ref_off) and np.array_equal(ent, ref_ent)
+    ctx.close()
+
+
+# ------------------------------------------------------------------ native front-end (fdc_render_frame)
+def test_native_front_end_renders_the_same_pixels():
+    """One fdc_render_frame call over POD scene records == the per-call front-end driving the same backend."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_flatten import random_renders
+
+    from figdraw_b200 import figrender, native_scene
+
+    cases = [(scenes.rgb_boxes_sdf(800.0, 600.0), 800, 600, []), (scenes.layers_clip(800.0, 600.0), 800, 600, []),
+             (scenes.image_scene(800.0, 600.0), 800, 600, [(scenes.IMG1_KEY, scenes.load_img1())]),
+             (ss.renderlist_100(1280.0, 720.0), 1280, 720, []),
+             (ss.text_page(1280.0, 720.0, n_glyphs=2000, msdf_glyphs=300), 1280, 720, ss.text_page_images()),
+             (ss.clip_mask_table(1280.0, 720.0, rows=30, cols=6), 1280, 720, [])]
+    cases += [(random_renders(s), 640, 480, [(1000 + k, np.full((6, 5, 4), 200, np.uint8)) for k in range(0, 40, 3)]) for s in range(6)]
+    for renders, w, h, images in cases:
+        a, b = CudaContext(atlasSize=2048), CudaContext(atlasSize=2048)
+        for key, img in images:
+            a.putImage(key, img)
+            b.putImage(key, img)
+        figrender.setFigUiScale(1.0)
+        figrender.renderFrame(a, renders, (float(w), float(h)))
+        b.renderFrameNative(native_scene.pack_renders(renders), (w, h))
+        pa, pb = a.readPixels(), b.readPixels()
+        assert np.array_equal(pa, pb)
+        a.close()
+        b.close()
+
+
+def test_native_front_end_cfg5_scene_equals_call_stream():
+    tr = ss.config_trace(5, 1280, 720, n_rects=6000, n_glyphs=1500)
+    scene = ss.rects_and_glyphs_scene(1280, 720, n_rects=6000, n_glyphs=1500)
+    want = render_trace(tr)
+    ctx = CudaContext(atlasSize=tr.atlas_size)
+    for _i, key, img in tr.images:
+        ctx.putImage(key, img)
+    ctx.renderFrameNative(scene, (1280, 720))
+    assert np.array_equal(ctx.readPixels(), want)
     ctx.close()

@@ -153,6 +153,31 @@ def run_reference(args, rank: int, out=sys.stdout):
     print(json.dumps(line), file=out, flush=True)
 
 
+def native_frontend_probe(name: str, calls_np):
+    """Informational: host time of fdc_flatten_renders for the node-level form of the workload --
+    100k nkRectangle + nkText records -> the call stream the timed steps replay (checked byte for byte)."""
+    import ctypes
+
+    from figdraw_b200 import abi, scenes_synth as ss
+
+    lib = abi.load_library()
+    big = name == "cfg5_8k"
+    scene = ss.rects_and_glyphs_scene(7680 if big else 3840, 4320 if big else 2160, scale=2.0 if big else 1.0)
+    keys = np.asarray(sorted(ss.glyph_image_keys()), dtype=np.uint64)
+    env = abi.FdcFlattenEnv(1.0, 1.0, 1.2, 0, keys.ctypes.data, len(keys))
+    out = np.zeros(len(calls_np) + 64, dtype=abi.CALL_DTYPE)
+    n = ctypes.c_size_t(0)
+    ts = []
+    for _ in range(7):
+        t0 = time.perf_counter()
+        rc = lib.fdc_flatten_renders(scene.lists, len(scene.nodes), scene.glyphs.ctypes.data, scene.ops.ctypes.data,
+                                     ctypes.byref(env), out.ctypes.data, len(out), ctypes.byref(n))
+        ts.append(time.perf_counter() - t0)
+    same = rc == 0 and n.value == len(calls_np) and out[: n.value].tobytes() == calls_np.tobytes()
+    return {"nodes": scene.n_nodes, "records": int(n.value), "flatten_ms": round(float(np.median(ts[1:])) * 1e3, 3),
+            "threads": min(16, os.cpu_count() or 1), "records_equal_benchmark_stream": bool(same)}
+
+
 def _claim_stdout():
     """Libraries (NCCL's version banner, torchrun warnings) print to fd 1; the driver wants ONE JSON line there.
     Point fd 1 at stderr for the run and keep the real stdout for the final line."""
@@ -435,6 +460,8 @@ def main():
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base}
         if gathered_ok is not None:
             line["gathered_frame_equals_single_gpu"] = gathered_ok
+        if world == 1 and name in ("cfg5_4k", "cfg5_8k"):
+            line["native_frontend"] = native_frontend_probe(name, calls_np)
         print(json.dumps(line), file=real_stdout, flush=True)
     ctx.close()
     if world > 1:

@@ -492,6 +492,18 @@ __device__ __forceinline__ bool rect_hits(uint32_t r, uint32_t bx, uint32_t by) 
   return (r & 255u) <= bx && bx <= ((r >> 16) & 255u) && ((r >> 8) & 255u) <= by && by <= (r >> 24);
 }
 
+// 32x32 bit-matrix transpose across a warp: lane i passes row i (bit k = A[i][k]) and receives column i (bit k = A[k][i]).
+// Five butterfly steps swapping off-diagonal blocks of size 16, 8, 4, 2, 1.
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, j);
+    x = (lane & j) ? (((y >> j) & m) | (x & ~m)) : ((x & m) | ((y & m) << j));
+  }
+  return x;
+}
+
 // One CTA = one chunk of kChunk primitives x one range of coarse-bin rows.  A warp owns 4 consecutive groups of 32
 // primitives.  Per group: every lane marks the bins its primitive touches in a per-warp bitmap (one 32-bit word per
 // lane; a bin row takes `wpr` words), then the warp visits only the marked bins; for each, one ballot over the 32
@@ -518,16 +530,21 @@ __global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restri
   const int row1 = min(row0 + rows_per_cta, f.cby);
   const int n_bins = f.cbx * f.cby;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   if (kScatter && counters[2] > coarse_cap) return;  // overflow: host regrows and replays
   uint8_t* wc_global = warp_counts + ((size_t)chunk * gridDim.y + blockIdx.y) * (size_t)(kWarps * kSlots);
   const uint32_t rect = coarse_rect(prims, base_idx + threadIdx.x, n, f);
 
+  // slots in use: (rows of this CTA) x (words per row) x 32 -- 544 of the 1024 at 4K; everything per-slot below is
+  // bounded by it (zeroing, the prefix over warps and the per-warp count array are the fixed cost of this kernel)
+  const int used = (row1 - row0) * wpr * 32;
   if (!kScatter) {
-    for (int k = threadIdx.x; k < kWarps * kSlots / 2; k += blockDim.x) reinterpret_cast<uint32_t*>(&wcnt[0][0])[k] = 0;
+    for (int k = threadIdx.x; k < kWarps * (used / 2); k += blockDim.x) {
+      const int w = k / (used / 2), j = k % (used / 2);
+      reinterpret_cast<uint32_t*>(&wcnt[w][0])[j] = 0;
+    }
   } else {
     // per-warp counts -> exclusive prefix over warps; base of this chunk's slice of each bin
-    for (int sl = threadIdx.x; sl < kSlots; sl += blockDim.x) {
+    for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {
       uint32_t run = 0;
 #pragma unroll
       for (int w = 0; w < kWarps; w++) { const uint32_t c = wc_global[w * kSlots + sl]; wcnt[w][sl] = (uint16_t)run; run += c; }
@@ -556,27 +573,38 @@ __global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restri
   __syncwarp();
   const uint32_t myword = bitmap[warp][lane];
   uint32_t words = __ballot_sync(0xFFFFFFFFu, myword != 0);
+  // One marked bitmap word = 32 bins of one bin row.  Each lane builds the hit bits of ITS primitive inside the word,
+  // a 32x32 bit transpose across the warp turns "bins per primitive" into "primitives per bin": lane b then owns bin
+  // b of the word -- its count is a popc, its stable ranks are the order of the set bits.  The cost per word does not
+  // depend on how many bins are marked, so a full-frame primitive (510 bins at 4K) no longer serialises its warp
+  // (it used to: one ballot per marked bin, a 20-40 us tail in both passes, profiles/r01_binning.md).
+  const int rx0 = rect & 255u, ry0 = (rect >> 8) & 255u, rx1 = (rect >> 16) & 255u, ry1 = rect >> 24;
   while (words) {
     const int wi = __ffs(words) - 1;
     words &= words - 1;
-    uint32_t bits = __shfl_sync(0xFFFFFFFFu, myword, wi);
-    const uint32_t by = (uint32_t)(row0 + wi / wpr), bxw = (uint32_t)((wi % wpr) * 32);
-    while (bits) {
-      const int bit = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const bool hit = rect_hits(rect, bxw + bit, by);
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-      const int sl = wi * 32 + bit;
-      if (!kScatter) {
-        if (lane == 0) wcnt[warp][sl] = (uint16_t)__popc(m);  // each warp visits a bin once
-      } else {
-        if (hit) coarse_list[gbase[sl] + wcnt[warp][sl] + __popc(m & lt_mask)] = base_idx + threadIdx.x;
+    const int by = row0 + wi / wpr, bxw = (wi % wpr) * 32;
+    uint32_t hm = 0;
+    if (ry0 <= by && by <= ry1 && rx0 <= bxw + 31 && rx1 >= bxw && rx0 <= rx1) {
+      const int lo = max(rx0 - bxw, 0), hi = min(rx1 - bxw, 31);
+      hm = (hi == 31 ? 0xFFFFFFFFu : ((2u << hi) - 1u)) & ~((1u << lo) - 1u);
+    }
+    uint32_t cm = transpose32(hm, lane);
+    const int sl = wi * 32 + lane;
+    if (!kScatter) {
+      if (cm) wcnt[warp][sl] = (uint16_t)__popc(cm);  // each warp visits a word once
+    } else if (cm) {
+      uint32_t pos = gbase[sl] + wcnt[warp][sl];
+      const uint32_t first = base_idx + (uint32_t)warp * 32u;
+      while (cm) {
+        const int pl = __ffs(cm) - 1;
+        cm &= cm - 1;
+        coarse_list[pos++] = first + (uint32_t)pl;
       }
     }
   }
   if (!kScatter) {
     __syncthreads();
-    for (int sl = threadIdx.x; sl < kSlots; sl += blockDim.x) {
+    for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {
       const int r = row0 + (sl >> 5) / wpr, x = ((sl >> 5) % wpr) * 32 + (sl & 31);
       uint32_t tot = 0;
 #pragma unroll

@@ -166,11 +166,34 @@ __device__ void apply_clip_chain(const SetupArgs& a, int clip_draw, int& x0, int
   }
 }
 
+// One staged draw record (fdc_call layout: op, u[9], f[22]) in shared memory.
+struct DrawView {
+  const uint32_t* w;
+  __device__ __forceinline__ uint32_t op() const { return w[0]; }
+  __device__ __forceinline__ uint32_t u(int k) const { return w[1 + k]; }
+  __device__ __forceinline__ float f(int k) const { return __uint_as_float(w[10 + k]); }
+};
+
 __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
+  // The CTA's 128 records (16 KB) come in with coalesced 16-byte loads and are read back from shared memory at a
+  // 33-word stride (no bank conflicts): one record per thread straight from global memory was a 128-byte-stride
+  // gather that left the kernel waiting on loads (issue slot utilisation 0.17, profiles/r01_binning.md).
+  __shared__ uint32_t s_draw[128][33];
+  {
+    const uint32_t first = blockIdx.x * 128u;
+    const uint32_t n_here = min(128u, a.count - first);
+    const uint4* src = reinterpret_cast<const uint4*>(a.draws + a.first + first);
+    for (uint32_t k = threadIdx.x; k < n_here * 8u; k += 128u) {
+      const uint4 v = __ldg(src + k);
+      uint32_t* dst = &s_draw[k >> 3][(k & 7u) * 4u];
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+  }
+  __syncthreads();
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.count) return;
   uint32_t di = a.first + i;
-  const fdc_call& d = a.draws[di];
+  const DrawView d{s_draw[threadIdx.x]};
   int ri = find_run(a.runs, a.n_runs, di);
   const RunState rs = a.runs[ri];
   const Xform xf = a.xforms[rs.xform];
@@ -188,89 +211,89 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
   float uax = 0.0f, uay = 0.0f, utx = 1.0f, uty = 1.0f;  // normalised atlas uv corners (atlas modes)
   bool atlas_mode = false;
 
-  switch (d.op) {
+  switch (d.op()) {
     case FDC_OP_ROUNDED_RECT: {
-      float w = d.f[2], h = d.f[3];
+      float w = d.f(2), h = d.f(3);
       if (w <= 0.0f || h <= 0.0f) { empty = true; break; }
-      mode = (int)d.u[0];
-      int fkind = (int)d.u[1], axis = (int)d.u[2];
+      mode = (int)d.u(0);
+      int fkind = (int)d.u(1), axis = (int)d.u(2);
       if (fkind == FDC_FILL_LINEAR3 && (mode == FDC_SDF_CLIP_AA || mode == FDC_SDF_ANNULAR || mode == FDC_SDF_ANNULAR_AA)) {
         fill_mode = 1 + (axis & 3);
-        cols[0] = cols[1] = cols[2] = cols[3] = d.u[3];
-        p.c_mid = d.u[4];
-        p.c_stop = d.u[5];
+        cols[0] = cols[1] = cols[2] = cols[3] = d.u(3);
+        p.c_mid = d.u(4);
+        p.c_stop = d.u(5);
       } else {
-        gradient_colors(fkind, axis, &d.u[3], d.f[16], cols);
+        gradient_colors(fkind, axis, d.w + 4, d.f(16), cols);
       }
       float qhx = fmul(w, 0.5f), qhy = fmul(h, 0.5f);
       bool inset = (mode == FDC_SDF_INSET_SHADOW);
-      float ssx = d.f[14], ssy = d.f[15];
+      float ssx = d.f(14), ssy = d.f(15);
       float rsx = (ssx > 0.0f && ssy > 0.0f) ? ssx : w, rsy = (ssx > 0.0f && ssy > 0.0f) ? ssy : h;
       float shx = inset ? qhx : fmul(rsx, 0.5f), shy = inset ? qhy : fmul(rsy, 0.5f);
       p.qhx = qhx; p.qhy = qhy;
       p.p2 = inset ? ssx : shx;
       p.p3 = inset ? ssy : shy;
       float rr[4];
-      if (rounded_radii_vec(&d.f[4], &d.f[8], shx, shy, rr)) flags |= PF_ELLIPTICAL;
+      if (rounded_radii_vec(reinterpret_cast<const float*>(d.w + 14), reinterpret_cast<const float*>(d.w + 18), shx, shy, rr)) flags |= PF_ELLIPTICAL;
       p.r0 = rr[0]; p.r1 = rr[1]; p.r2 = rr[2]; p.r3 = rr[3];
-      p.factor = d.f[12];
-      p.spread = fill_mode == 0 ? d.f[13] : clampf(d.f[16], 0.01f, 0.99f);
-      atx = d.f[0]; aty = d.f[1]; tox = fadd(d.f[0], w); toy = fadd(d.f[1], h);
+      p.factor = d.f(12);
+      p.spread = fill_mode == 0 ? d.f(13) : clampf(d.f(16), 0.01f, 0.99f);
+      atx = d.f(0); aty = d.f(1); tox = fadd(d.f(0), w); toy = fadd(d.f(1), h);
       break;
     }
     case FDC_OP_IMAGE: {
       float r[4];
-      uint64_t key = (uint64_t)d.u[0] | ((uint64_t)d.u[1] << 32);
+      uint64_t key = (uint64_t)d.u(0) | ((uint64_t)d.u(1) << 32);
       if (!atlas_lookup(a.atlas, key, r)) { empty = true; break; }
       float as = (float)a.atlas.size;
-      float sw = d.f[2], sh = d.f[3];
+      float sw = d.f(2), sh = d.f(3);
       if (!(sw > 0.0f && sh > 0.0f)) { sw = fmul(r[2], as); sh = fmul(r[3], as); }
       uax = r[0]; utx = fadd(r[0], r[2]);
       uay = r[1]; uty = fadd(r[1], r[3]);
-      if (d.u[7]) { float tmp = uay; uay = uty; uty = tmp; }
+      if (d.u(7)) { float tmp = uay; uay = uty; uty = tmp; }
 #pragma unroll
-      for (int k = 0; k < 4; k++) cols[k] = d.u[3 + k];
+      for (int k = 0; k < 4; k++) cols[k] = d.u(3 + k);
       mode = FDC_SDF_ATLAS;
       atlas_mode = true;
-      atx = d.f[0]; aty = d.f[1]; tox = fadd(d.f[0], sw); toy = fadd(d.f[1], sh);
+      atx = d.f(0); aty = d.f(1); tox = fadd(d.f(0), sw); toy = fadd(d.f(1), sh);
       break;
     }
     case FDC_OP_MSDF: {
       float r[4];
-      uint64_t key = (uint64_t)d.u[0] | ((uint64_t)d.u[1] << 32);
+      uint64_t key = (uint64_t)d.u(0) | ((uint64_t)d.u(1) << 32);
       if (!atlas_lookup(a.atlas, key, r)) { empty = true; break; }
-      float stroke_w = fmaxf(0.0f, d.f[6]);
-      bool mtsdf = d.u[2] != 0;
+      float stroke_w = fmaxf(0.0f, d.f(6));
+      bool mtsdf = d.u(2) != 0;
       mode = stroke_w > 0.0f ? (mtsdf ? FDC_SDF_MTSDF_ANNULAR : FDC_SDF_MSDF_ANNULAR) : (mtsdf ? FDC_SDF_MTSDF : FDC_SDF_MSDF);
       uax = r[0]; utx = fadd(r[0], r[2]);
       uay = r[1]; uty = fadd(r[1], r[3]);
-      if (d.u[7]) { float tmp = uay; uay = uty; uty = tmp; }
-      cols[0] = cols[1] = cols[2] = cols[3] = d.u[3];
+      if (d.u(7)) { float tmp = uay; uay = uty; uty = tmp; }
+      cols[0] = cols[1] = cols[2] = cols[3] = d.u(3);
       p.qhx = (float)a.atlas.size; p.qhy = stroke_w;
-      p.factor = d.f[4]; p.spread = d.f[5];
+      p.factor = d.f(4); p.spread = d.f(5);
       atlas_mode = true;
-      atx = d.f[0]; aty = d.f[1]; tox = fadd(d.f[0], d.f[2]); toy = fadd(d.f[1], d.f[3]);
+      atx = d.f(0); aty = d.f(1); tox = fadd(d.f(0), d.f(2)); toy = fadd(d.f(1), d.f(3));
       break;
     }
     case FDC_OP_BEZIER: {
-      if (d.f[2] <= 0.0f || d.f[3] <= 0.0f || d.f[10] <= 0.0f) { empty = true; break; }
-      int fkind = (int)d.u[1], axis = (int)d.u[2];
+      if (d.f(2) <= 0.0f || d.f(3) <= 0.0f || d.f(10) <= 0.0f) { empty = true; break; }
+      int fkind = (int)d.u(1), axis = (int)d.u(2);
       if (fkind == FDC_FILL_LINEAR3) {
         fill_mode = 1 + (axis & 3);
-        cols[0] = cols[1] = cols[2] = cols[3] = d.u[3];
-        p.c_mid = d.u[4];
-        p.c_stop = d.u[5];
+        cols[0] = cols[1] = cols[2] = cols[3] = d.u(3);
+        p.c_mid = d.u(4);
+        p.c_stop = d.u(5);
       } else {
-        gradient_colors(fkind, axis, &d.u[3], d.f[16], cols);
+        gradient_colors(fkind, axis, d.w + 4, d.f(16), cols);
       }
-      p.qhx = fmul(d.f[2], 0.5f); p.qhy = fmul(d.f[3], 0.5f); p.p2 = d.f[4]; p.p3 = d.f[5];
-      p.r0 = d.f[6]; p.r1 = d.f[7]; p.r2 = d.f[8]; p.r3 = d.f[9];
-      p.factor = d.f[10];
-      p.spread = fill_mode == 0 ? 0.0f : clampf(d.f[16], 0.01f, 0.99f);
-      int cap = (int)d.u[0];
+      p.qhx = fmul(d.f(2), 0.5f); p.qhy = fmul(d.f(3), 0.5f); p.p2 = d.f(4); p.p3 = d.f(5);
+      p.r0 = d.f(6); p.r1 = d.f(7); p.r2 = d.f(8); p.r3 = d.f(9);
+      p.factor = d.f(10);
+      p.spread = fill_mode == 0 ? 0.0f : clampf(d.f(16), 0.01f, 0.99f);
+      int cap = (int)d.u(0);
       mode = cap == FDC_CAP_BUTT ? FDC_SDF_BEZIER_STROKE_BUTT_AA
                                  : (cap == FDC_CAP_SQUARE ? FDC_SDF_BEZIER_STROKE_SQUARE_AA : FDC_SDF_BEZIER_STROKE_AA);
-      atx = d.f[0]; aty = d.f[1]; tox = fadd(d.f[0], d.f[2]); toy = fadd(d.f[1], d.f[3]);
+      atx = d.f(0); aty = d.f(1); tox = fadd(d.f(0), d.f(2)); toy = fadd(d.f(1), d.f(3));
       break;
     }
     case FDC_OP_FILLED_QUAD: {
@@ -278,9 +301,9 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
       if (!atlas_lookup(a.atlas, kRectKey, r)) { empty = true; break; }
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        float2 v = xf_apply(xf, d.f[2 * k], d.f[2 * k + 1]);
+        float2 v = xf_apply(xf, d.f(2 * k), d.f(2 * k + 1));
         q.x[k] = ceilf(v.x); q.y[k] = ceilf(v.y);
-        cols[k] = d.u[3 + k];
+        cols[k] = d.u(3 + k);
       }
       have_rect_quad = false;
       uax = utx = fadd(r[0], fdiv(r[2], 2.0f));
@@ -294,10 +317,10 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
       if (!atlas_lookup(a.atlas, kRectKey, r)) { empty = true; break; }
       uax = utx = fadd(r[0], fdiv(r[2], 2.0f));
       uay = uty = fadd(r[1], fdiv(r[3], 2.0f));
-      cols[0] = cols[1] = cols[2] = cols[3] = d.u[3];
+      cols[0] = cols[1] = cols[2] = cols[3] = d.u(3);
       mode = FDC_SDF_ATLAS;
       atlas_mode = true;
-      atx = d.f[0]; aty = d.f[1]; tox = fadd(d.f[0], d.f[2]); toy = fadd(d.f[1], d.f[3]);
+      atx = d.f(0); aty = d.f(1); tox = fadd(d.f(0), d.f(2)); toy = fadd(d.f(1), d.f(3));
       break;
     }
     default: empty = true; break;
@@ -365,7 +388,7 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
         }
       }
       // SDF modes: direct pixel -> SDF-space mapping.  p.x = (s - .5) * 2 * qhx with s = x*su + ou.
-      const bool sdf_rect = d.op == FDC_OP_ROUNDED_RECT;
+      const bool sdf_rect = d.op() == FDC_OP_ROUNDED_RECT;
       if (sdf_rect && aligned) {
         p.u0 = 2.0f * p.qhx * p.su; p.du = (2.0f * p.ou - 1.0f) * p.qhx;
         p.v0 = -2.0f * p.qhy * p.sv; p.dv = -(2.0f * p.ov - 1.0f) * p.qhy;
@@ -512,7 +535,7 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 constexpr int kSlots = 1024;  // bitmap bits per CTA: 32 words x 32 bins
 constexpr int kWarps = kChunk / 32;
 
-// kScatter == false: counts.  Writes chunk_counts[chunk][bin] and the per-warp counts (u8) to `warp_counts`.
+// kScatter == false: counts.  Writes chunk_counts[bin][chunk] and the per-warp counts (u8) to `warp_counts`.
 // kScatter == true : reads the per-warp counts back, orders warps with a prefix, and scatters primitive indices.
 template <bool kScatter>
 __global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restrict__ prims, uint32_t n, FrameView f, int wpr,
@@ -551,7 +574,7 @@ __global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restri
       const int r = row0 + (sl >> 5) / wpr, x = ((sl >> 5) % wpr) * 32 + (sl & 31);
       if (r < row1 && x < f.cbx) {
         const int b = r * f.cbx + x;
-        gbase[sl] = cbin_start[b] + chunk_counts[(size_t)chunk * n_bins + b];
+        gbase[sl] = cbin_start[b] + chunk_counts[(size_t)b * gridDim.x + chunk];
       }
     }
   }
@@ -609,7 +632,7 @@ __global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restri
       uint32_t tot = 0;
 #pragma unroll
       for (int w = 0; w < kWarps; w++) { const uint32_t c = wcnt[w][sl]; wc_global[w * kSlots + sl] = (uint8_t)c; tot += c; }
-      if (r < row1 && x < f.cbx) chunk_counts[(size_t)chunk * n_bins + r * f.cbx + x] = tot;
+      if (r < row1 && x < f.cbx) chunk_counts[(size_t)(r * f.cbx + x) * gridDim.x + chunk] = tot;
     }
   }
 }
@@ -624,18 +647,29 @@ __global__ void __launch_bounds__(256) coarse_scan_kernel(uint32_t* __restrict__
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * 8 + warp;
   if (b < n_bins) {
+    // [bin][chunk] layout: a warp reads 32 consecutive chunk counts per step.  The loads of 16 steps (512 chunks) are
+    // issued together; only the carry chains the steps.
     uint32_t carry = 0;
-    for (int c0 = 0; c0 < n_chunks; c0 += 32) {
-      const int c = c0 + lane;
-      const uint32_t v = c < n_chunks ? chunk_counts[(size_t)c * n_bins + b] : 0u;
-      uint32_t incl = v;
+    uint32_t* row = chunk_counts + (size_t)b * n_chunks;
+    for (int blk0 = 0; blk0 < n_chunks; blk0 += 512) {
+      uint32_t v[16];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += t;
+      for (int k = 0; k < 16; k++) {
+        const int c = blk0 + k * 32 + lane;
+        v[k] = c < n_chunks ? row[c] : 0u;
       }
-      if (c < n_chunks) chunk_counts[(size_t)c * n_bins + b] = carry + incl - v;
-      carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const int c = blk0 + k * 32 + lane;
+        uint32_t incl = v[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (c < n_chunks) row[c] = carry + incl - v[k];
+        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+      }
     }
     if (lane == 0) cbin_start[b + 1] = carry;  // bin totals, shifted by one; turned into offsets by the last CTA
   }

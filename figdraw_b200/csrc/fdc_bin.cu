@@ -745,6 +745,34 @@ __device__ __forceinline__ uint32_t spread_cols(uint32_t c) { return (c & 1u) * 
 constexpr uint32_t kInfoEmptyInner = 1u << 30;  // staging-only markers, stripped before the entry is written
 constexpr uint32_t kInfoBegin = 1u << 31;
 
+// tile-row hit bits (8) from 32 block-row bits: bit r = "nibble r is non-zero"
+__device__ __forceinline__ uint32_t nibbles_nonzero(uint32_t x) {
+  x |= x >> 1;
+  x |= x >> 2;
+  x &= 0x11111111u;                       // bit 4r
+  x = (x | (x >> 3)) & 0x03030303u;       // bits 8j, 8j+1
+  x = (x | (x >> 6)) & 0x000F000Fu;       // bits 16j .. 16j+3
+  return (x | (x >> 12)) & 0xFFu;
+}
+// tile-column hit bits (8) from 16 block-column bits: bit c = "pair c is non-zero"
+__device__ __forceinline__ uint32_t pairs_nonzero(uint32_t x) {
+  x = (x | (x >> 1)) & 0x5555u;
+  x = (x | (x >> 1)) & 0x3333u;
+  x = (x | (x >> 2)) & 0x0F0Fu;
+  return (x | (x >> 4)) & 0xFFu;
+}
+// bit i of a nibble -> bit 8i
+__device__ __forceinline__ uint32_t spread_nibble_to_bytes(uint32_t r) {
+  return (r & 1u) | ((r & 2u) << 7) | ((r & 4u) << 14) | ((r & 8u) << 21);
+}
+
+constexpr int kGroups = kStage / 32;
+
+// One CTA per coarse bin (8x8 tiles).  Staged entries are handled 32 at a time ("groups"), one group per warp: every
+// lane turns its entry into a 64-bit tile-hit mask (tile rows x tile columns), two 32x32 bit transposes across the
+// warp turn "tiles per entry" into "entries per tile", and lane t then owns tiles t and 32+t of the bin: the count is
+// a popc, the emission order is the order of the set bits.  (Before: warp w owned tile row w and every warp walked
+// every entry with one ballot per tile column -- 8x the instructions for the same lists; profiles/r01_binning.md.)
 __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ prims, FrameView f,
                                                        const uint32_t* __restrict__ cbin_start,
                                                        const uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
@@ -757,33 +785,28 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
   __shared__ uint32_t s_rows_ov[kStage];
   __shared__ uint32_t s_rows_full[kStage];
   __shared__ uint32_t s_info[kStage];
-  __shared__ uint32_t s_cnt[kCoarse * kCoarse];
-  __shared__ uint32_t s_base[kCoarse * kCoarse];
+  __shared__ uint32_t s_lo[kStage], s_hi[kStage];  // tile-hit masks: tile rows 0-3 / 4-7, bit = row*8 + column
+  __shared__ uint8_t s_gcnt[kGroups][64];          // entries of group g in tile t
+  __shared__ uint32_t s_gpos[kGroups][64];         // where group g's entries of tile t go in the tile list
+  __shared__ uint32_t s_run[64];                   // pass 0: running tile counts; pass 1: write cursors
+  __shared__ uint32_t s_base[64];
   __shared__ uint32_t s_alloc;
   if (counters[2] > coarse_cap) return;
   const int b = blockIdx.x;
   const int cbx_i = b % f.cbx, cby_i = b / f.cbx;
   const uint32_t begin = cbin_start[b], end = cbin_start[b + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   const int tile_x0 = cbx_i * kCoarse, tile_y0 = f.cty0 + cby_i * kCoarse;
   const int px0 = tile_x0 * kTileW, py0 = tile_y0 * kTileH;
   const bool single = end - begin <= (uint32_t)kStage;
-
-  uint32_t cnt[kCoarse];
-#pragma unroll
-  for (int i = 0; i < kCoarse; i++) cnt[i] = 0;
+  if (threadIdx.x < 64) s_run[threadIdx.x] = 0;
 
   for (int pass = 0; pass < 2; pass++) {
     if (pass == 1) {
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < kCoarse; i++) s_cnt[warp * kCoarse + i] = cnt[i];
-      }
       __syncthreads();
       if (warp == 0) {
         // exclusive scan of the 64 tile counts: two per lane
-        const uint32_t c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
+        const uint32_t c0 = s_run[2 * lane], c1 = s_run[2 * lane + 1];
         uint32_t incl = c0 + c1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -801,20 +824,21 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
       }
       __syncthreads();
       const uint32_t alloc = s_alloc;
-      const int tile_y = tile_y0 + warp;
-      if (lane < kCoarse) {
-        const int tx = tile_x0 + lane;
-        if (tx < f.tiles_x && tile_y >= f.ty0 && tile_y < f.ty1) {
-          tile_start[tile_y * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : alloc + s_base[warp * kCoarse + lane];
-          tile_count[tile_y * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : s_cnt[warp * kCoarse + lane];
+      if (threadIdx.x < 64) {
+        const int t = threadIdx.x;
+        const int tx = tile_x0 + (t & 7), ty = tile_y0 + (t >> 3);
+        if (tx < f.tiles_x && ty >= f.ty0 && ty < f.ty1) {
+          tile_start[ty * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : alloc + s_base[t];
+          tile_count[ty * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : s_run[t];
         }
       }
       if (alloc == 0xFFFFFFFFu) return;
-#pragma unroll
-      for (int i = 0; i < kCoarse; i++) cnt[i] = alloc + s_base[warp * kCoarse + i];
+      __syncthreads();
+      if (threadIdx.x < 64) s_run[threadIdx.x] = alloc + s_base[threadIdx.x];
     }
     for (uint32_t s0 = begin; s0 < end; s0 += kStage) {
       const uint32_t ns = min((uint32_t)kStage, end - s0);
+      const int n_groups = (int)((ns + 31u) >> 5);
       if (pass == 0 || !single) {
         __syncthreads();  // previous stage fully consumed
         for (uint32_t k = threadIdx.x; k < ns; k += blockDim.x) {
@@ -845,45 +869,59 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
           if (fl & PF_RECTMASK) info |= TE_RECTMASK;
           if (fl & PF_INNER_EMPTY) info |= kInfoEmptyInner;
           if (fl & PF_MASK_BEGIN) info |= kInfoBegin;
+          const uint32_t tr = nibbles_nonzero(rows_ov), tc = pairs_nonzero(cols & 0xFFFFu);
           s_pid[k] = pid;
           s_cols[k] = cols;
           s_rows_ov[k] = rows_ov;
           s_rows_full[k] = rows_full;
           s_info[k] = info;
+          s_lo[k] = tc * spread_nibble_to_bytes(tr & 15u);
+          s_hi[k] = tc * spread_nibble_to_bytes(tr >> 4);
+        }
+        __syncthreads();
+        // entries per (group, tile)
+        for (int g = warp; g < n_groups; g += 8) {
+          const uint32_t k = (uint32_t)g * 32u + lane;
+          const uint32_t lo = k < ns ? s_lo[k] : 0u, hi = k < ns ? s_hi[k] : 0u;
+          s_gcnt[g][lane] = (uint8_t)__popc(transpose32(lo, lane));
+          s_gcnt[g][32 + lane] = (uint8_t)__popc(transpose32(hi, lane));
         }
         __syncthreads();
       }
-      for (uint32_t k0 = 0; k0 < ns; k0 += 32) {
-        const uint32_t k = k0 + lane;
-        uint32_t cols = 0, pid = 0, info = 0, sp_ov = 0, sp_full = 0;
-        if (k < ns) {
-          const uint32_t r_ov = (s_rows_ov[k] >> (4 * warp)) & 15u;  // my tile row's four block rows
-          if (r_ov) {
-            cols = s_cols[k];
-            pid = s_pid[k];
-            if (pass == 1) {
-              info = s_info[k];
-              sp_ov = spread_rows(r_ov);
-              sp_full = spread_rows((s_rows_full[k] >> (4 * warp)) & 15u);
-            }
-          }
+      // per tile: running count (pass 0) or the groups' write positions (pass 1)
+      if (threadIdx.x < 64) {
+        const int t = threadIdx.x;
+        uint32_t run = s_run[t];
+        for (int g = 0; g < n_groups; g++) {
+          if (pass == 1) s_gpos[g][t] = run;
+          run += s_gcnt[g][t];
         }
+        s_run[t] = run;
+      }
+      if (pass == 0) continue;
+      __syncthreads();
+      for (int g = warp; g < n_groups; g += 8) {
+        const uint32_t k = (uint32_t)g * 32u + lane;
+        const uint32_t lo = k < ns ? s_lo[k] : 0u, hi = k < ns ? s_hi[k] : 0u;
 #pragma unroll
-        for (int i = 0; i < kCoarse; i++) {
-          const uint32_t c_ov = (cols >> (2 * i)) & 3u;
-          const bool hit = c_ov != 0u;
-          const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-          if (pass == 1 && hit) {
-            uint32_t ov = sp_ov & spread_cols(c_ov);
-            uint32_t full = sp_full & spread_cols((cols >> (16 + 2 * i)) & 3u);
+        for (int half = 0; half < 2; half++) {
+          uint32_t m = transpose32(half ? hi : lo, lane);  // entries of this group that hit tile t
+          const int t = half * 32 + lane, r = t >> 3, c = t & 7;
+          uint32_t pos = s_gpos[g][t];
+          while (m) {
+            const int e = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t ke = (uint32_t)g * 32u + (uint32_t)e;
+            const uint32_t cols = s_cols[ke], info = s_info[ke];
+            uint32_t ov = spread_rows((s_rows_ov[ke] >> (4 * r)) & 15u) & spread_cols((cols >> (2 * c)) & 3u);
+            uint32_t full = spread_rows((s_rows_full[ke] >> (4 * r)) & 15u) & spread_cols((cols >> (16 + 2 * c)) & 3u);
             if (info & kInfoEmptyInner) { ov &= ~full; full = 0; }  // inside an AnnularAA stroke: nothing to shade
             if (info & kInfoBegin) ov = 0xFFu;                      // PF_MASK_BEGIN: every block resets the level
-            TileEntry e;
-            e.pid = pid;
-            e.info = (info & 0x3FFFFFFFu) | (ov << TE_OV_SHIFT) | (full << TE_FULL_SHIFT);
-            tile_list[cnt[i] + __popc(m & lt_mask)] = e;
+            TileEntry te;
+            te.pid = s_pid[ke];
+            te.info = (info & 0x3FFFFFFFu) | (ov << TE_OV_SHIFT) | (full << TE_FULL_SHIFT);
+            tile_list[pos++] = te;
           }
-          cnt[i] += __popc(m);
         }
       }
     }

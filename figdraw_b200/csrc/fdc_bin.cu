@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(256) coarse_scan_kernel(uint32_t* __restrict__
 // column gives counts and stable ranks.  Counts -> CTA scan -> one atomicAdd reserves the bin's slice of the tile list
 // -> second walk scatters 8-byte TileEntry records that already carry, for each of the tile's eight 8x4 blocks,
 // "bbox overlaps" and "inside the inner rect" bits, so the shading warps never touch the primitive for culling.
-constexpr int kStage = 1024;
+constexpr int kStage = 1024;  // = 4 entries per thread of a 256-thread CTA
 static_assert(kTileW == 16 && kTileH == 16 && kCoarse == 8, "fine_bin_kernel shifts assume 16x16 tiles, 8x8 tiles per bin");
 
 // bits [a..b] of a 32-bit word (empty when b < a)
@@ -764,6 +764,44 @@ __device__ __forceinline__ uint32_t pairs_nonzero(uint32_t x) {
 // bit i of a nibble -> bit 8i
 __device__ __forceinline__ uint32_t spread_nibble_to_bytes(uint32_t r) {
   return (r & 1u) | ((r & 2u) << 7) | ((r & 4u) << 14) | ((r & 8u) << 21);
+}
+
+// Everything the shade kernel needs per (tile, primitive), derived once per staged coarse entry.
+__device__ __forceinline__ void stage_entry(uint32_t k, uint32_t pid, const int4& q6, const int2& ir, int px0, int py0, const FrameView& f,
+                                            uint32_t* s_pid, uint32_t* s_cols, uint32_t* s_rows_ov, uint32_t* s_rows_full,
+                                            uint32_t* s_info, uint32_t* s_lo, uint32_t* s_hi) {
+  const uint32_t fl = (uint32_t)q6.z;
+  const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
+  uint32_t cols = blocks_overlapped(bx0, bx1, px0, 3, 16);
+  uint32_t rows_ov = blocks_overlapped(by0, by1, py0, 2, 32), rows_full = 0;
+  if (fl & PF_INNER) {
+    const int ix0 = (int16_t)(ir.x & 0xFFFF), iy0 = (int16_t)(ir.x >> 16), ix1 = (int16_t)(ir.y & 0xFFFF), iy1 = (int16_t)(ir.y >> 16);
+    cols |= blocks_covered(ix0, ix1, px0, 3, 16, f.W) << 16;
+    rows_full = blocks_covered(iy0, iy1, py0, 2, 32, f.H);
+  }
+  const uint32_t mode = fl & PF_MODE_MASK;
+  uint32_t kind = mode == FDC_SDF_CLIP_AA ? 0u : (mode == FDC_SDF_ANNULAR_AA ? 1u : 2u), tex = 0u;
+  if (mode == FDC_SDF_ATLAS) { tex = TE_TEX; kind = 0u; }
+  else if (mode == FDC_SDF_MSDF) { tex = TE_TEX; kind = 1u; }
+  else if (mode == FDC_SDF_MTSDF) { tex = TE_TEX; kind = 2u; }
+  else if (mode == FDC_SDF_MSDF_ANNULAR) { tex = TE_TEX | TE_GRAD3; kind = 1u; }
+  else if (mode == FDC_SDF_MTSDF_ANNULAR) { tex = TE_TEX | TE_GRAD3; kind = 2u; }
+  uint32_t info = ((fl & PF_FAST) ? TE_FAST : 0u) | ((fl & PF_SOLID) ? TE_SOLID : 0u) | tex |
+                  ((fl & PF_FILLMODE_MASK) ? TE_GRAD3 : 0u) | (kind << TE_KIND_SHIFT) |
+                  ((fl & PF_OCCLUDER) ? TE_OCCLUDER : 0u) | (((fl & PF_DEPTH_MASK) >> PF_DEPTH_SHIFT) << TE_DEPTH_SHIFT);
+  if (fl & PF_MASK_WRITE) info |= TE_MASKW;
+  if (fl & PF_MASK_BEGIN) info |= TE_MASKB;
+  if (fl & PF_RECTMASK) info |= TE_RECTMASK;
+  if (fl & PF_INNER_EMPTY) info |= kInfoEmptyInner;
+  if (fl & PF_MASK_BEGIN) info |= kInfoBegin;
+  const uint32_t tr = nibbles_nonzero(rows_ov), tc = pairs_nonzero(cols & 0xFFFFu);
+  s_pid[k] = pid;
+  s_cols[k] = cols;
+  s_rows_ov[k] = rows_ov;
+  s_rows_full[k] = rows_full;
+  s_info[k] = info;
+  s_lo[k] = tc * spread_nibble_to_bytes(tr & 15u);
+  s_hi[k] = tc * spread_nibble_to_bytes(tr >> 4);
 }
 
 constexpr int kGroups = kStage / 32;
@@ -841,42 +879,30 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
       const int n_groups = (int)((ns + 31u) >> 5);
       if (pass == 0 || !single) {
         __syncthreads();  // previous stage fully consumed
-        for (uint32_t k = threadIdx.x; k < ns; k += blockDim.x) {
-          const uint32_t pid = __ldg(&coarse_list[s0 + k]);
-          const int4 q6 = __ldg(reinterpret_cast<const int4*>(&prims[pid]) + 6);
-          const uint32_t fl = (uint32_t)q6.z;
-          const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
-          uint32_t cols = blocks_overlapped(bx0, bx1, px0, 3, 16);
-          uint32_t rows_ov = blocks_overlapped(by0, by1, py0, 2, 32), rows_full = 0;
-          if (fl & PF_INNER) {
-            const int2 ir = __ldg(reinterpret_cast<const int2*>(&prims[pid]) + 11);
-            const int ix0 = (int16_t)(ir.x & 0xFFFF), iy0 = (int16_t)(ir.x >> 16), ix1 = (int16_t)(ir.y & 0xFFFF), iy1 = (int16_t)(ir.y >> 16);
-            cols |= blocks_covered(ix0, ix1, px0, 3, 16, f.W) << 16;
-            rows_full = blocks_covered(iy0, iy1, py0, 2, 32, f.H);
+        // Four entries per thread with the three dependent gathers (list -> bbox -> inner rect) issued level by level,
+        // so a stage costs three memory latencies instead of twelve.
+        {
+          uint32_t pid[4];
+          int4 q6[4];
+          int2 ir[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t k = threadIdx.x + j * 256u;
+            pid[j] = k < ns ? __ldg(&coarse_list[s0 + k]) : 0xFFFFFFFFu;
           }
-          const uint32_t mode = fl & PF_MODE_MASK;
-          uint32_t kind = mode == FDC_SDF_CLIP_AA ? 0u : (mode == FDC_SDF_ANNULAR_AA ? 1u : 2u), tex = 0u;
-          if (mode == FDC_SDF_ATLAS) { tex = TE_TEX; kind = 0u; }
-          else if (mode == FDC_SDF_MSDF) { tex = TE_TEX; kind = 1u; }
-          else if (mode == FDC_SDF_MTSDF) { tex = TE_TEX; kind = 2u; }
-          else if (mode == FDC_SDF_MSDF_ANNULAR) { tex = TE_TEX | TE_GRAD3; kind = 1u; }
-          else if (mode == FDC_SDF_MTSDF_ANNULAR) { tex = TE_TEX | TE_GRAD3; kind = 2u; }
-          uint32_t info = ((fl & PF_FAST) ? TE_FAST : 0u) | ((fl & PF_SOLID) ? TE_SOLID : 0u) | tex |
-                          ((fl & PF_FILLMODE_MASK) ? TE_GRAD3 : 0u) | (kind << TE_KIND_SHIFT) |
-                          ((fl & PF_OCCLUDER) ? TE_OCCLUDER : 0u) | (((fl & PF_DEPTH_MASK) >> PF_DEPTH_SHIFT) << TE_DEPTH_SHIFT);
-          if (fl & PF_MASK_WRITE) info |= TE_MASKW;
-          if (fl & PF_MASK_BEGIN) info |= TE_MASKB;
-          if (fl & PF_RECTMASK) info |= TE_RECTMASK;
-          if (fl & PF_INNER_EMPTY) info |= kInfoEmptyInner;
-          if (fl & PF_MASK_BEGIN) info |= kInfoBegin;
-          const uint32_t tr = nibbles_nonzero(rows_ov), tc = pairs_nonzero(cols & 0xFFFFu);
-          s_pid[k] = pid;
-          s_cols[k] = cols;
-          s_rows_ov[k] = rows_ov;
-          s_rows_full[k] = rows_full;
-          s_info[k] = info;
-          s_lo[k] = tc * spread_nibble_to_bytes(tr & 15u);
-          s_hi[k] = tc * spread_nibble_to_bytes(tr >> 4);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            q6[j] = pid[j] != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const int4*>(&prims[pid[j]]) + 6) : make_int4(0, 0, 0, 0);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            ir[j] = (pid[j] != 0xFFFFFFFFu && ((uint32_t)q6[j].z & PF_INNER)) ? __ldg(reinterpret_cast<const int2*>(&prims[pid[j]]) + 11)
+                                                                              : make_int2(0, 0);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t k = threadIdx.x + j * 256u;
+            if (k >= ns) break;
+            stage_entry(k, pid[j], q6[j], ir[j], px0, py0, f, s_pid, s_cols, s_rows_ov, s_rows_full, s_info, s_lo, s_hi);
+          }
         }
         __syncthreads();
         // entries per (group, tile)

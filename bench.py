@@ -62,7 +62,8 @@ def algorithmic_flops(counts: np.ndarray) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled in-process every ~2 ms (the timed region
+    of the default run is only ~25 ms long), `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
 
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -71,8 +72,38 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.gpu = gpu_index
+        self.nvml = None
+        self.samples = []   # (sm_mhz, reasons bitmask)
+        self.stop_flag = False
+        self.sm_max = None
+
+    def _nvml_loop(self):
+        nv, h = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nvml = (nv, h)
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -86,6 +117,16 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            nv, _h = self.nvml
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+            reasons = sorted({n for _sm, bits in self.samples for n, b in names if bits & b})
+            sm = [float(x) for x, _ in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -399,6 +440,15 @@ def main():
         ref_ctx.submitCalls(calls_np)
         ref_ctx.endFrame()
         gathered_ok = bool(np.array_equal(ref_ctx.readPixels(), whole))
+        # the same frame on ONE GPU, measured here so that a strong-scaling ratio for this workload can be formed
+        # (the N = 1 bench line runs the 4K target frame, BASELINE's multi-GPU config is the 8K one)
+        single_ms = []
+        for _ in range(7):
+            flush.fill_(0)
+            torch.cuda.synchronize()
+            ref_ctx.replayFrame()
+            single_ms.append(float(ref_ctx.frameStats().gpu_ms))
+        single_gpu_ms = float(np.median(single_ms[2:]))
         ref_ctx.close()
     if world > 1:
         t = torch.tensor([ms_step, e2e_ms, stats.shade_ms, stats.bin_ms], device=dev, dtype=torch.float64)
@@ -468,6 +518,9 @@ def main():
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base}
         if gathered_ok is not None:
             line["gathered_frame_equals_single_gpu"] = gathered_ok
+            line["single_gpu_same_workload"] = {"ms_per_step": round(single_gpu_ms, 4), "value": round(mpx / (single_gpu_ms * 1e-3), 2),
+                                                "unit": METRIC, "note": "this rank-0 GPU alone on the same frame (no gather); "
+                                                "value / (n_gpus x this) is the strong-scaling efficiency of the workload"}
         if world == 1 and name in ("cfg5_4k", "cfg5_8k"):
             line["native_frontend"] = native_frontend_probe(name, calls_np)
         print(json.dumps(line), file=real_stdout, flush=True)

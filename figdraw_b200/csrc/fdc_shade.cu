@@ -21,6 +21,9 @@
 
 #include "fdc_kernels.h"
 
+#ifndef FDC_SHADE_WAVES
+#define FDC_SHADE_WAVES 6
+#endif
 #ifndef FDC_SHADE_MIN_BLOCKS
 #define FDC_SHADE_MIN_BLOCKS 4
 #endif
@@ -626,8 +629,8 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
 // on immediately (no intra-CTA tail: the slowest block of a tile used to hold 7 idle warps' registers), while the
 // warps of a CTA still work on neighbouring blocks of the same tiles at the same time, so the primitive records
 // they load stay shared in L1.
-constexpr int kTilesPerCta = 8;
 
+template <int kTilesPerCta>
 __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ ShadeArgs a) {
   __shared__ uint32_t s_next;
   if (a.counters[1] != 0) return;  // a bin list overflowed: host regrows and replays the frame
@@ -736,7 +739,13 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
 void launch_shade(const ShadeArgs& a, cudaStream_t stream) {
   const int n_tiles = a.frame.tiles_x * (a.frame.ty1 - a.frame.ty0);
   if (n_tiles <= 0) return;
-  shade_kernel<<<(n_tiles + kTilesPerCta - 1) / kTilesPerCta, 256, 0, stream>>>(a);
+  // Tiles per CTA: 8 keeps neighbouring blocks' records shared in L1, but a band of an 8-GPU partition or a small frame
+  // must still give every SM several waves of CTAs (148 SMs x 4 resident CTAs): aim for >= 6 waves.
+  const int slots = 148 * FDC_SHADE_MIN_BLOCKS * FDC_SHADE_WAVES;
+  if (n_tiles >= 8 * slots) shade_kernel<8><<<(n_tiles + 7) / 8, 256, 0, stream>>>(a);
+  else if (n_tiles >= 4 * slots) shade_kernel<4><<<(n_tiles + 3) / 4, 256, 0, stream>>>(a);
+  else if (n_tiles >= 2 * slots) shade_kernel<2><<<(n_tiles + 1) / 2, 256, 0, stream>>>(a);
+  else shade_kernel<1><<<n_tiles, 256, 0, stream>>>(a);
 }
 
 }  // namespace fdc

@@ -805,6 +805,10 @@ __device__ __forceinline__ void stage_entry(uint32_t k, uint32_t pid, const int4
 }
 
 constexpr int kGroups = kStage / 32;
+#ifndef FDC_DIRECT_FINE_LIMIT
+#define FDC_DIRECT_FINE_LIMIT 262144
+#endif
+constexpr size_t kDirectFineLimit = FDC_DIRECT_FINE_LIMIT;  // primitives x coarse bins below which the coarse pass is skipped
 
 // One CTA per coarse bin (8x8 tiles).  Staged entries are handled 32 at a time ("groups"), one group per warp: every
 // lane turns its entry into a 64-bit tile-hit mask (tile rows x tile columns), two 32x32 bit transposes across the
@@ -816,7 +820,9 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
                                                        const uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
                                                        uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile_count,
                                                        TileEntry* __restrict__ tile_list, uint32_t tile_cap,
-                                                       uint32_t* __restrict__ counters) {
+                                                       uint32_t* __restrict__ counters, uint32_t n_direct) {
+  // n_direct != 0: small scene, no coarse pass was run -- every bin stages primitives 0..n_direct-1 themselves (those
+  // that miss the bin get an empty tile mask); otherwise the bin's coarse list.
   // per staged coarse entry, computed once: 16 block columns (8 px) and 32 block rows (4 px) of this 128x128-px bin
   __shared__ uint32_t s_pid[kStage];
   __shared__ uint32_t s_cols[kStage];     // overlap bits 0..15 | covered-by-inner bits 16..31
@@ -829,10 +835,10 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
   __shared__ uint32_t s_run[64];                   // pass 0: running tile counts; pass 1: write cursors
   __shared__ uint32_t s_base[64];
   __shared__ uint32_t s_alloc;
-  if (counters[2] > coarse_cap) return;
+  if (!n_direct && counters[2] > coarse_cap) return;
   const int b = blockIdx.x;
   const int cbx_i = b % f.cbx, cby_i = b / f.cbx;
-  const uint32_t begin = cbin_start[b], end = cbin_start[b + 1];
+  const uint32_t begin = n_direct ? 0u : cbin_start[b], end = n_direct ? n_direct : cbin_start[b + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_x0 = cbx_i * kCoarse, tile_y0 = f.cty0 + cby_i * kCoarse;
   const int px0 = tile_x0 * kTileW, py0 = tile_y0 * kTileH;
@@ -888,7 +894,7 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             const uint32_t k = threadIdx.x + j * 256u;
-            pid[j] = k < ns ? __ldg(&coarse_list[s0 + k]) : 0xFFFFFFFFu;
+            pid[j] = k < ns ? (n_direct ? s0 + k : __ldg(&coarse_list[s0 + k])) : 0xFFFFFFFFu;
           }
 #pragma unroll
           for (int j = 0; j < 4; j++)
@@ -971,6 +977,13 @@ void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& f, con
   cudaMemsetAsync(b.tile_count + (size_t)f.ty0 * f.tiles_x, 0, sizeof(uint32_t) * (size_t)(f.ty1 - f.ty0) * f.tiles_x, stream);
   cudaMemsetAsync(b.counters, 0, sizeof(uint32_t) * 4, stream);
   if (n_prims == 0 || n_bins == 0) return;
+  if ((size_t)n_prims * (size_t)n_bins <= (size_t)kDirectFineLimit) {
+    // Small scene: three launches of coarse binning cost more than letting every bin look at every primitive.
+    fine_bin_kernel<<<n_bins, 256, 0, stream>>>(prims, f, b.cbin_start, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count,
+                                                b.tile_list, b.tile_cap, b.counters, n_prims);
+    if (n_launches) *n_launches += 1;
+    return;
+  }
   const int wpr = (f.cbx + 31) / 32;             // bitmap words per coarse-bin row
   const int rows_per_cta = 32 / wpr;             // 32 words per CTA
   dim3 grid(n_chunks, (f.cby + rows_per_cta - 1) / rows_per_cta);
@@ -980,7 +993,7 @@ void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& f, con
   coarse_bin_kernel<true><<<grid, kChunk, 0, stream>>>(prims, n_prims, f, wpr, rows_per_cta, b.chunk_counts, b.warp_counts, b.cbin_start,
                                                       b.coarse_list, b.coarse_cap, b.counters);
   fine_bin_kernel<<<n_bins, 256, 0, stream>>>(prims, f, b.cbin_start, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count,
-                                              b.tile_list, b.tile_cap, b.counters);
+                                              b.tile_list, b.tile_cap, b.counters, 0u);
   if (n_launches) *n_launches += 4;
 }
 

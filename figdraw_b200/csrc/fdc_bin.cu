@@ -551,7 +551,6 @@ __global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restri
   const uint32_t base_idx = chunk * kChunk;
   const int row0 = blockIdx.y * rows_per_cta;
   const int row1 = min(row0 + rows_per_cta, f.cby);
-  const int n_bins = f.cbx * f.cby;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (kScatter && counters[2] > coarse_cap) return;  // overflow: host regrows and replays
   uint8_t* wc_global = warp_counts + ((size_t)chunk * gridDim.y + blockIdx.y) * (size_t)(kWarps * kSlots);

@@ -36,7 +36,10 @@ __device__ __forceinline__ uint32_t quant_pack(float4 v) {  // values already in
 }
 
 constexpr int kBlurTile = 128;  // pixels along the pass axis per CTA
-constexpr int kBlurLines = 4;   // lines (rows for H, columns for V) per CTA
+#ifndef FDC_BLUR_LINES
+#define FDC_BLUR_LINES 1
+#endif
+constexpr int kBlurLines = FDC_BLUR_LINES;   // lines (rows for H, columns for V) per CTA
 constexpr int kMaxReach = 66;   // ceil(8 * 64/8) + 1 + slack
 
 // One pass.  kVertical=false: taps along x, reads `src` rows; kVertical=true: taps along y.
@@ -114,6 +117,60 @@ __global__ void __launch_bounds__(kBlurTile) blur_pass_kernel(const uint32_t* __
   }
 }
 
+// Vertical pass as a 2-D tile: 32 columns x kVTile rows of output per CTA.  The source rows (tile + tap halo) are staged
+// row by row, so every global load and store is 32 consecutive pixels (the line-per-thread layout of the horizontal
+// pass would make a warp touch 32 different rows); a thread then walks down its column in shared memory (bank = column).
+constexpr int kVTile = 64;
+constexpr int kVRows = 8;  // thread rows per CTA
+__global__ void __launch_bounds__(32 * kVRows) blur_v_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int W, int H,
+                                                             int x0, int y0, int x1, int y1, BlurParams bp) {
+  __shared__ uint32_t col[kVTile + 2 * kMaxReach][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = x0 + blockIdx.x * 32 + tx;
+  const int ybase = y0 + blockIdx.y * kVTile;
+  const int span = kVTile + 2 * bp.reach;
+  const int xs = min(x, W - 1);
+  for (int k = ty; k < span; k += kVRows) {
+    int a = ybase - bp.reach + k;
+    a = a < 0 ? 0 : (a >= H ? H - 1 : a);  // CLAMP_TO_EDGE
+    col[k][tx] = __ldg(src + (size_t)a * W + xs);
+  }
+  __syncthreads();
+  if (x >= x1) return;
+  for (int r = ty; r < kVTile; r += kVRows) {
+    const int y = ybase + r;
+    if (y >= y1) break;
+    const int c = r + bp.reach;
+    uint32_t out;
+    if (bp.copy_only) {
+      out = col[c][tx];
+    } else {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = -8; i <= 8; i++) {
+        const float off = (float)i * bp.step;
+        const float fo = floorf(off);
+        const float fr = off - fo;
+        const int k0 = c + (int)fo;
+        const float4 t0 = unpack255(col[k0][tx]);
+        const float w = bp.w[i < 0 ? -i : i];
+        if (fr > 0.0f) {
+          const float4 t1 = unpack255(col[k0 + 1][tx]);
+          acc.x = fmaf(fmaf(t1.x - t0.x, fr, t0.x), w, acc.x);
+          acc.y = fmaf(fmaf(t1.y - t0.y, fr, t0.y), w, acc.y);
+          acc.z = fmaf(fmaf(t1.z - t0.z, fr, t0.z), w, acc.z);
+          acc.w = fmaf(fmaf(t1.w - t0.w, fr, t0.w), w, acc.w);
+        } else {
+          acc.x = fmaf(t0.x, w, acc.x); acc.y = fmaf(t0.y, w, acc.y); acc.z = fmaf(t0.z, w, acc.z); acc.w = fmaf(t0.w, w, acc.w);
+        }
+      }
+      acc.x *= bp.inv_sum; acc.y *= bp.inv_sum; acc.z *= bp.inv_sum; acc.w *= bp.inv_sum;
+      out = quant_pack(acc);
+    }
+    dst[(size_t)y * W + x] = out;
+  }
+}
+
 // 2x2 box on premultiplied colour, back to straight alpha (same integer arithmetic as the oracle's upload_chain).
 __global__ void mip_down_kernel(const uint8_t* __restrict__ src, int src_size, uint8_t* __restrict__ dst, int dst_size,
                                 int sx, int sy, int dw, int dh, int dx, int dy) {
@@ -173,8 +230,8 @@ void launch_backdrop_blur(const BlurArgs& a, cudaStream_t stream, int* n_launche
     blur_pass_kernel<false><<<grid, kBlurTile, 0, stream>>>(src, temp, a.W, a.H, a.x0, hy0, a.x1, hy1, bp, rs);
   }
   {
-    dim3 grid((a.y1 - a.y0 + kBlurTile - 1) / kBlurTile, (a.x1 - a.x0 + kBlurLines - 1) / kBlurLines);
-    blur_pass_kernel<true><<<grid, kBlurTile, 0, stream>>>(temp, dst, a.W, a.H, a.x0, a.y0, a.x1, a.y1, bp, RowSources{{}, 0, 1});
+    dim3 grid((a.x1 - a.x0 + 31) / 32, (a.y1 - a.y0 + kVTile - 1) / kVTile);
+    blur_v_kernel<<<grid, 32 * kVRows, 0, stream>>>(temp, dst, a.W, a.H, a.x0, a.y0, a.x1, a.y1, bp);
   }
   if (n_launches) *n_launches += 2;
 }

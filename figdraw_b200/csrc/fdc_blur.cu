@@ -22,6 +22,8 @@ struct BlurParams {
   float step;      // tap spacing in pixels
   int reach;       // ceil(8*step) + 1
   int copy_only;   // radius <= 0.5: texture() pass-through
+  int tap_off[17]; // floor(i * step), i = -8..8  (the same float arithmetic as blur.frag, done once on the host)
+  float tap_fr[17];// i * step - floor(i * step)
 };
 
 __device__ __forceinline__ float4 unpack255(uint32_t c) {
@@ -36,14 +38,8 @@ __device__ __forceinline__ uint32_t quant_pack(float4 v) {  // values already in
 }
 
 constexpr int kBlurTile = 128;  // pixels along the pass axis per CTA
-#ifndef FDC_BLUR_LINES
-#define FDC_BLUR_LINES 1
-#endif
-constexpr int kBlurLines = FDC_BLUR_LINES;   // lines (rows for H, columns for V) per CTA
 constexpr int kMaxReach = 66;   // ceil(8 * 64/8) + 1 + slack
 
-// One pass.  kVertical=false: taps along x, reads `src` rows; kVertical=true: taps along y.
-// Region [x0,x1) x [y0,y1) of dst is produced.  Source indices clamp to the frame (CLAMP_TO_EDGE).
 struct RowSources {
   const uint32_t* rank[kMaxRanks];
   int n, band_px;
@@ -54,77 +50,67 @@ __device__ __forceinline__ const uint32_t* row_base(const RowSources& rs, const 
   return rs.rank[r];
 }
 
-template <bool kVertical>
-__global__ void __launch_bounds__(kBlurTile) blur_pass_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
-                                                             int W, int H, int x0, int y0, int x1, int y1, BlurParams bp,
-                                                             RowSources rs) {
-  __shared__ uint32_t line[kBlurLines][kBlurTile + 2 * kMaxReach];
-  const int along0 = (kVertical ? y0 : x0) + blockIdx.x * kBlurTile;  // first pixel along the pass axis
-  const int across0 = (kVertical ? x0 : y0) + blockIdx.y * kBlurLines;
-  const int along_end = kVertical ? y1 : x1, across_end = kVertical ? x1 : y1;
-  const int limit = kVertical ? H : W;
-  const int span = kBlurTile + 2 * bp.reach;
-  for (int l = 0; l < kBlurLines; l++) {
-    const int across = across0 + l;
-    if (across >= across_end) break;
-    for (int k = threadIdx.x; k < span; k += kBlurTile) {
-      int a = along0 - bp.reach + k;
-      a = a < 0 ? 0 : (a >= limit ? limit - 1 : a);
-      // H pass: row `across` may live in a neighbour's framebuffer (halo rows of a band partition): volatile load, the
-      // line must come from the owner's L2, not from a stale local cache
-      if (kVertical) line[l][k] = __ldg(src + (size_t)a * W + across);
-      else if (rs.n == 0) line[l][k] = __ldg(src + (size_t)across * W + a);
-      else line[l][k] = __ldcv(row_base(rs, src, across) + (size_t)across * W + a);
+// 17 taps over a line of unpacked texels (`stride` float4s apart); c = index of the centre texel.  Frame-edge clamping
+// happened when staging; (k0, k0+1) are neighbours in the clamped line only when the unclamped indices are both inside
+// or both outside the frame, which holds because clamping is monotone.
+__device__ __forceinline__ uint32_t blur_taps(const float4* __restrict__ line, int stride, int c, const BlurParams& bp) {
+  if (bp.copy_only) {
+    const float4 t = line[c * stride];
+    return quant_pack(t);
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 17; i++) {
+    const int k0 = c + bp.tap_off[i];
+    const float fr = bp.tap_fr[i];
+    const float w = bp.w[i < 8 ? 8 - i : i - 8];
+    const float4 t0 = line[k0 * stride];
+    if (fr > 0.0f) {
+      const float4 t1 = line[(k0 + 1) * stride];
+      acc.x = fmaf(fmaf(t1.x - t0.x, fr, t0.x), w, acc.x);
+      acc.y = fmaf(fmaf(t1.y - t0.y, fr, t0.y), w, acc.y);
+      acc.z = fmaf(fmaf(t1.z - t0.z, fr, t0.z), w, acc.z);
+      acc.w = fmaf(fmaf(t1.w - t0.w, fr, t0.w), w, acc.w);
+    } else {
+      acc.x = fmaf(t0.x, w, acc.x); acc.y = fmaf(t0.y, w, acc.y); acc.z = fmaf(t0.z, w, acc.z); acc.w = fmaf(t0.w, w, acc.w);
     }
+  }
+  acc.x *= bp.inv_sum; acc.y *= bp.inv_sum; acc.z *= bp.inv_sum; acc.w *= bp.inv_sum;
+  return quant_pack(acc);
+}
+
+// Horizontal pass: one row segment of kBlurTile pixels per CTA, staged UNPACKED (float4 per texel: each staged texel
+// is converted once instead of once per tap that touches it) with its tap halo.  Region [x0,x1) x [y0,y1) of dst is
+// produced.  Source indices clamp to the frame (CLAMP_TO_EDGE).  Row `y` may live in a neighbour's framebuffer (halo
+// rows of a band partition): volatile loads, the line must come from the owner's L2, not from a stale local cache.
+__global__ void __launch_bounds__(kBlurTile) blur_h_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int W, int H,
+                                                           int x0, int y0, int x1, int y1, BlurParams bp, RowSources rs) {
+  __shared__ float4 line[kBlurTile + 2 * kMaxReach];
+  const int xa = x0 + blockIdx.x * kBlurTile;
+  const int y = y0 + blockIdx.y;
+  if (y >= y1) return;
+  const int span = kBlurTile + 2 * bp.reach;
+  const uint32_t* row = row_base(rs, src, y) + (size_t)y * W;
+  for (int k = threadIdx.x; k < span; k += kBlurTile) {
+    int a = xa - bp.reach + k;
+    a = a < 0 ? 0 : (a >= W ? W - 1 : a);
+    line[k] = unpack255(rs.n == 0 ? __ldg(row + a) : __ldcv(row + a));
   }
   __syncthreads();
-  const int along = along0 + threadIdx.x;
-  if (along >= along_end) return;
-  for (int l = 0; l < kBlurLines; l++) {
-    const int across = across0 + l;
-    if (across >= across_end) break;
-    uint32_t out;
-    const int c = threadIdx.x + bp.reach;  // centre index in the staged line
-    if (bp.copy_only) {
-      out = line[l][c];
-    } else {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int i = -8; i <= 8; i++) {
-        const float off = (float)i * bp.step;
-        const float fo = floorf(off);
-        const float fr = off - fo;
-        const int k0 = c + (int)fo;
-        // Frame-edge clamping happened when staging; (k0, k0+1) are neighbours in the clamped line only when the
-        // unclamped indices are both inside or both outside the frame, which holds because clamping is monotone.
-        const float4 t0 = unpack255(line[l][k0]);
-        const float w = bp.w[i < 0 ? -i : i];
-        if (fr > 0.0f) {
-          const float4 t1 = unpack255(line[l][k0 + 1]);
-          acc.x = fmaf(fmaf(t1.x - t0.x, fr, t0.x), w, acc.x);
-          acc.y = fmaf(fmaf(t1.y - t0.y, fr, t0.y), w, acc.y);
-          acc.z = fmaf(fmaf(t1.z - t0.z, fr, t0.z), w, acc.z);
-          acc.w = fmaf(fmaf(t1.w - t0.w, fr, t0.w), w, acc.w);
-        } else {
-          acc.x = fmaf(t0.x, w, acc.x); acc.y = fmaf(t0.y, w, acc.y); acc.z = fmaf(t0.z, w, acc.z); acc.w = fmaf(t0.w, w, acc.w);
-        }
-      }
-      acc.x *= bp.inv_sum; acc.y *= bp.inv_sum; acc.z *= bp.inv_sum; acc.w *= bp.inv_sum;
-      out = quant_pack(acc);
-    }
-    if (kVertical) dst[(size_t)along * W + across] = out;
-    else dst[(size_t)across * W + along] = out;
-  }
+  const int x = xa + threadIdx.x;
+  if (x >= x1) return;
+  dst[(size_t)y * W + x] = blur_taps(line, 1, threadIdx.x + bp.reach, bp);
 }
 
 // Vertical pass as a 2-D tile: 32 columns x kVTile rows of output per CTA.  The source rows (tile + tap halo) are staged
-// row by row, so every global load and store is 32 consecutive pixels (the line-per-thread layout of the horizontal
-// pass would make a warp touch 32 different rows); a thread then walks down its column in shared memory (bank = column).
-constexpr int kVTile = 64;
+// row by row, so every global load and store is 32 consecutive pixels (a line-per-thread layout would make a warp
+// touch 32 different rows); a thread then walks down its column in shared memory.  Dynamic shared memory:
+// (kVTile + 2*reach) x 32 float4.
+constexpr int kVTile = 32;
 constexpr int kVRows = 8;  // thread rows per CTA
 __global__ void __launch_bounds__(32 * kVRows) blur_v_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int W, int H,
                                                              int x0, int y0, int x1, int y1, BlurParams bp) {
-  __shared__ uint32_t col[kVTile + 2 * kMaxReach][32];
+  extern __shared__ float4 col[];  // [span][32]
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int x = x0 + blockIdx.x * 32 + tx;
   const int ybase = y0 + blockIdx.y * kVTile;
@@ -133,41 +119,14 @@ __global__ void __launch_bounds__(32 * kVRows) blur_v_kernel(const uint32_t* __r
   for (int k = ty; k < span; k += kVRows) {
     int a = ybase - bp.reach + k;
     a = a < 0 ? 0 : (a >= H ? H - 1 : a);  // CLAMP_TO_EDGE
-    col[k][tx] = __ldg(src + (size_t)a * W + xs);
+    col[k * 32 + tx] = unpack255(__ldg(src + (size_t)a * W + xs));
   }
   __syncthreads();
   if (x >= x1) return;
   for (int r = ty; r < kVTile; r += kVRows) {
     const int y = ybase + r;
     if (y >= y1) break;
-    const int c = r + bp.reach;
-    uint32_t out;
-    if (bp.copy_only) {
-      out = col[c][tx];
-    } else {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int i = -8; i <= 8; i++) {
-        const float off = (float)i * bp.step;
-        const float fo = floorf(off);
-        const float fr = off - fo;
-        const int k0 = c + (int)fo;
-        const float4 t0 = unpack255(col[k0][tx]);
-        const float w = bp.w[i < 0 ? -i : i];
-        if (fr > 0.0f) {
-          const float4 t1 = unpack255(col[k0 + 1][tx]);
-          acc.x = fmaf(fmaf(t1.x - t0.x, fr, t0.x), w, acc.x);
-          acc.y = fmaf(fmaf(t1.y - t0.y, fr, t0.y), w, acc.y);
-          acc.z = fmaf(fmaf(t1.z - t0.z, fr, t0.z), w, acc.z);
-          acc.w = fmaf(fmaf(t1.w - t0.w, fr, t0.w), w, acc.w);
-        } else {
-          acc.x = fmaf(t0.x, w, acc.x); acc.y = fmaf(t0.y, w, acc.y); acc.z = fmaf(t0.z, w, acc.z); acc.w = fmaf(t0.w, w, acc.w);
-        }
-      }
-      acc.x *= bp.inv_sum; acc.y *= bp.inv_sum; acc.z *= bp.inv_sum; acc.w *= bp.inv_sum;
-      out = quant_pack(acc);
-    }
-    dst[(size_t)y * W + x] = out;
+    dst[(size_t)y * W + x] = blur_taps(col + tx, 32, r + bp.reach, bp);
   }
 }
 
@@ -216,6 +175,12 @@ void launch_backdrop_blur(const BlurArgs& a, cudaStream_t stream, int* n_launche
   }
   bp.inv_sum = 1.0f / fmaxf(sum, 1e-5f);
   bp.reach = bp.copy_only ? 0 : (int)ceilf(8.0f * bp.step) + 1;
+  for (int i = -8; i <= 8; i++) {
+    const float off = (float)i * bp.step;
+    const float fo = floorf(off);
+    bp.tap_off[i + 8] = (int)fo;
+    bp.tap_fr[i + 8] = off - fo;
+  }
   const uint32_t* src = reinterpret_cast<const uint32_t*>(a.src);
   RowSources rs;
   rs.n = a.n_src;
@@ -226,12 +191,16 @@ void launch_backdrop_blur(const BlurArgs& a, cudaStream_t stream, int* n_launche
   // H pass over the rows the V pass will read
   const int hy0 = max(a.y0 - bp.reach, 0), hy1 = min(a.y1 + bp.reach, a.H);
   {
-    dim3 grid((a.x1 - a.x0 + kBlurTile - 1) / kBlurTile, (hy1 - hy0 + kBlurLines - 1) / kBlurLines);
-    blur_pass_kernel<false><<<grid, kBlurTile, 0, stream>>>(src, temp, a.W, a.H, a.x0, hy0, a.x1, hy1, bp, rs);
+    dim3 grid((a.x1 - a.x0 + kBlurTile - 1) / kBlurTile, hy1 - hy0);
+    blur_h_kernel<<<grid, kBlurTile, 0, stream>>>(src, temp, a.W, a.H, a.x0, hy0, a.x1, hy1, bp, rs);
   }
   {
+    // (kVTile + 2*kMaxReach) x 32 float4 = 82 KB at the largest radius: above the 48 KB default, per device
+    const size_t max_smem = (size_t)(kVTile + 2 * kMaxReach) * 32 * sizeof(float4);
+    cudaFuncSetAttribute(blur_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+    const size_t smem = (size_t)(kVTile + 2 * bp.reach) * 32 * sizeof(float4);
     dim3 grid((a.x1 - a.x0 + 31) / 32, (a.y1 - a.y0 + kVTile - 1) / kVTile);
-    blur_v_kernel<<<grid, 32 * kVRows, 0, stream>>>(temp, dst, a.W, a.H, a.x0, a.y0, a.x1, a.y1, bp);
+    blur_v_kernel<<<grid, 32 * kVRows, smem, stream>>>(temp, dst, a.W, a.H, a.x0, a.y0, a.x1, a.y1, bp);
   }
   if (n_launches) *n_launches += 2;
 }

@@ -654,11 +654,16 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
     const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
     const bool valid = ix < f.W && iy < f.H;
     const float fx = (float)ix, fy = (float)iy;
+    const uint32_t n = a.tile_count[ty * f.tiles_x + tx];
 
     Pixel px;
     {
       uint32_t c = a.clear_rgba8;
       if (a.load_dst && valid) c = fb32[(size_t)iy * f.W + ix];
+      // A later segment of the frame (after a backdrop blur) that paints nothing in this tile leaves its pixels alone.
+      // (Both loads above are in flight together; peers still need the band's final pixels, so not when the gather is
+      // fused into this kernel.)
+      if (n == 0u && a.load_dst && a.n_peers == 0) continue;
       px.r = __uint_as_float(kBiasBits | (c & 255u));
       px.g = __uint_as_float(kBiasBits | ((c >> 8) & 255u));
       px.b = __uint_as_float(kBiasBits | ((c >> 16) & 255u));
@@ -666,7 +671,6 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
       px.mlo = px.mhi = 0;
     }
 
-    const uint32_t n = a.tile_count[ty * f.tiles_x + tx];
     const uint2* __restrict__ list = reinterpret_cast<const uint2*>(a.tile_list + a.tile_start[ty * f.tiles_x + tx]);
     // Everything a warp needs to cull is in the 8-byte tile entries (fine_bin_kernel computed it once per tile):
     // bit `sub` of info = "bbox overlaps my block", bit `8+sub` = "my block lies inside the inner rect".

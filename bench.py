@@ -237,8 +237,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="nccl", choices=["p2p", "nccl"],
-                    help="N>1: fused peer stores from the shade kernel (p2p) or NCCL all-gather of the bands")
+    ap.add_argument("--gather", default="nccl", choices=["p2p", "nccl", "ce"],
+                    help="N>1: NCCL all-gather of the bands (nccl), fused peer stores from the shade kernel (p2p), or copy "
+                         "engines shipping finished band slices to the peers while the next slice is shaded (ce)")
+    ap.add_argument("--sub-bands", type=int, default=4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
 
@@ -278,7 +280,7 @@ def main():
     band_rows, _layout = bands.band_layout(H, world)
     # a backdrop blur under a band partition reads halo rows out of the neighbours' framebuffers: peer mappings needed
     has_blur = bool((trace.calls["op"] == 13).any())
-    use_p2p = world > 1 and (args.gather == "p2p" or has_blur)
+    use_p2p = world > 1 and (args.gather in ("p2p", "ce") or has_blur)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
     if use_p2p:
         # Fused all-gather: every rank's shade kernel stores its finished pixels into all peers' framebuffers over
@@ -288,6 +290,8 @@ def main():
         dist.all_gather_object(handles, ctx.framebufferIpcHandle())
         peers = [0 if r == rank else ctx.openPeerFramebuffer(handles[r]) for r in range(world)]
         ctx.setPeerFramebuffers(peers)
+        if args.gather == "ce":
+            ctx.setPeerGather("copy", args.sub_bands)
         token = torch.zeros(1, dtype=torch.int32, device=dev)
         fb = None
     else:
@@ -506,7 +510,9 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "frame": [W, H], "primitives": trace.n_draws, "l2": "flushed between steps (256 MiB fill)",
                            "partition": "single GPU" if world == 1 else (
-                               f"{world} tile-row bands, band all-gather fused into the shade kernel (peer stores over NVLink)"
+                               (f"{world} tile-row bands, finished band slices copied to the peers by the copy engines (NVLink) while "
+                                "the next slice is shaded" if args.gather == "ce" else
+                                f"{world} tile-row bands, band all-gather fused into the shade kernel (peer stores over NVLink)")
                                if use_p2p else f"{world} tile-row bands + NCCL all-gather")},
                 "frames_per_s": round(1e3 / ms_step, 2),
                 "e2e": {"value": round(mpx / ((e2e_pipe_ms or e2e_ms) * 1e-3), 2), "unit": METRIC,

@@ -164,7 +164,7 @@ EXPORTS = [
     "fdc_submit_calls", "fdc_submit_draws",
     "fdc_put_image", "fdc_update_image", "fdc_has_image", "fdc_get_image_rect", "fdc_remove_image",
     "fdc_reset_image_atlas", "fdc_atlas_size", "fdc_atlas_packed_area",
-    "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers", "fdc_reserve_framebuffer", "fdc_framebuffer_ipc_handle", "fdc_open_peer_framebuffer",
+    "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers", "fdc_set_peer_gather", "fdc_reserve_framebuffer", "fdc_framebuffer_ipc_handle", "fdc_open_peer_framebuffer",
     "fdc_get_frame_stats", "fdc_debug_bins", "fdc_debug_shade_stats",
     "fdc_flatten_renders", "fdc_render_frame",
 ]
@@ -253,6 +253,7 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_open_peer_framebuffer", c.c_int, P, c.POINTER(c.c_uint8), c.POINTER(P))
     sig("fdc_get_frame_stats", c.c_int, P, c.POINTER(FdcFrameStats))
     sig("fdc_debug_shade_stats", c.c_int, P, c.POINTER(c.c_uint64))
+    sig("fdc_set_peer_gather", c.c_int, P, c.c_int, c.c_int)
     sig("fdc_flatten_renders", c.c_int, c.POINTER(FdcRenderList), c.c_uint32, c.c_void_p, c.c_void_p,
         c.POINTER(FdcFlattenEnv), c.c_void_p, c.c_size_t, c.POINTER(c.c_size_t))
     sig("fdc_render_frame", c.c_int, P, c.POINTER(FdcRenderList), c.c_uint32, c.c_void_p, c.c_void_p, c.c_float,

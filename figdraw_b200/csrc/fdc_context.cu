@@ -262,6 +262,10 @@ struct fdc_ctx {
   // ---- stats
   fdc_frame_stats stats = {};
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  int gather_mode = FDC_GATHER_STORES, gather_sub_bands = 4;
+  static constexpr int kCopyStreams = 4, kMaxSubBands = 16;
+  cudaStream_t copy_streams[kCopyStreams] = {};
+  cudaEvent_t ev_sub[kMaxSubBands] = {}, ev_copy[kCopyStreams] = {};
   std::vector<cudaEvent_t> ev_pool;
   struct Span { int a, b, kind; };  // event indices, kind 0 bin 1 shade 2 blur
   std::vector<Span> spans;
@@ -656,6 +660,14 @@ SetupArgs setup_args(fdc_ctx* ctx, const Segment& s) {
   return a;
 }
 
+int ensure_copy_streams(fdc_ctx* ctx) {
+  if (ctx->copy_streams[0]) return FDC_OK;
+  for (auto& cs : ctx->copy_streams) CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  for (auto& e : ctx->ev_sub) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : ctx->ev_copy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return FDC_OK;
+}
+
 // Launches every kernel of the recorded frame.  `upload`: copy the recording to the device first.
 int execute_frame(fdc_ctx* ctx, bool upload) {
   cudaStream_t st = ctx->stream;
@@ -746,8 +758,43 @@ int execute_frame(fdc_ctx* ctx, bool upload) {
         pending_wait = 0;
         launches++;
       }
-      launch_shade(sa, st);
-      launches++;
+      if (last && ctx->n_peers > 0 && ctx->gather_mode == FDC_GATHER_COPY && !ctx->ext_fb) {
+        // Copy-engine gather: shade the band slice by slice; a finished slice travels to every peer over NVLink
+        // (cudaMemcpyAsync on side streams) while the SMs shade the next one.
+        sa.peers = nullptr;
+        sa.n_peers = 0;
+        rc = ensure_copy_streams(ctx);
+        if (rc) return rc;
+        const int rows = ctx->frame.ty1 - ctx->frame.ty0;
+        const int n_sub = std::max(1, std::min(std::min(ctx->gather_sub_bands, (int)fdc_ctx::kMaxSubBands), rows));
+        for (int sb = 0; sb < n_sub; sb++) {
+          const int r0 = ctx->frame.ty0 + rows * sb / n_sub, r1 = ctx->frame.ty0 + rows * (sb + 1) / n_sub;
+          if (r1 <= r0) continue;
+          ShadeArgs ss = sa;
+          ss.frame.ty0 = r0;
+          ss.frame.ty1 = r1;
+          launch_shade(ss, st);
+          launches++;
+          CK(cudaEventRecord(ctx->ev_sub[sb], st));
+          const int y0 = r0 * kTileH, y1 = std::min(r1 * kTileH, ctx->H);
+          const size_t off = (size_t)y0 * ctx->W * 4, bytes = (size_t)(y1 - y0) * ctx->W * 4;
+          int k = 0;
+          for (int r = 0; r < ctx->n_peers; r++) {
+            uint8_t* peer = ctx->h_peers[r];
+            if (!peer || peer == ctx->d_fb.p || r == ctx->rank) continue;
+            cudaStream_t cs = ctx->copy_streams[(k++ + sb) % fdc_ctx::kCopyStreams];
+            CK(cudaStreamWaitEvent(cs, ctx->ev_sub[sb], 0));
+            CK(cudaMemcpyAsync(peer + off, ctx->d_fb.p + off, bytes, cudaMemcpyDeviceToDevice, cs));
+          }
+        }
+        for (int c = 0; c < fdc_ctx::kCopyStreams; c++) {
+          CK(cudaEventRecord(ctx->ev_copy[c], ctx->copy_streams[c]));
+          CK(cudaStreamWaitEvent(st, ctx->ev_copy[c], 0));
+        }
+      } else {
+        launch_shade(sa, st);
+        launches++;
+      }
     }
     if (s.has_blur) {
       Timed t(ctx, 2);
@@ -924,6 +971,9 @@ void fdc_destroy(fdc_ctx* ctx) {
   ctx->d_tile_start.release(); ctx->d_tile_count.release(); ctx->d_tile_list.release(); ctx->d_counters.release();
   ctx->d_fb.release(); ctx->d_backdrop.release(); ctx->d_temp.release(); ctx->d_peers.release();
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  for (auto& cs : ctx->copy_streams) if (cs) cudaStreamDestroy(cs);
+  for (auto& e : ctx->ev_sub) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->ev_copy) if (e) cudaEventDestroy(e);
   if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
   if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1462,6 +1512,15 @@ int fdc_set_peer_framebuffers(fdc_ctx* ctx, void* const* device_ptrs, int n) {
     CK(ctx->d_peers.reserve((size_t)n));
     CK(cudaMemcpy(ctx->d_peers.p, device_ptrs, sizeof(void*) * n, cudaMemcpyHostToDevice));
   }
+  return FDC_OK;
+}
+
+int fdc_set_peer_gather(fdc_ctx* ctx, int mode, int sub_bands) {
+  if (!ctx || (mode != FDC_GATHER_STORES && mode != FDC_GATHER_COPY)) return FDC_ERR_INVALID;
+  int rc = resolve_frame(ctx);
+  if (rc) return rc;
+  ctx->gather_mode = mode;
+  if (sub_bands > 0) ctx->gather_sub_bands = sub_bands;
   return FDC_OK;
 }
 

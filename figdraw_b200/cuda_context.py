@@ -327,6 +327,10 @@ class CudaContext(BackendContext):
         self._ck(self._lib.fdc_open_peer_framebuffer(self._h, buf, ctypes.byref(out)))
         return int(out.value)
 
+    def setPeerGather(self, mode: str = "stores", subBands: int = 4):
+        """"stores": the shade kernel writes every pixel to every peer; "copy": copy engines ship finished slices."""
+        self._ck(self._lib.fdc_set_peer_gather(self._h, {"stores": 0, "copy": 1}[mode], int(subBands)))
+
     def setPeerFramebuffers(self, ptrs: Sequence[int]):
         arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])
         self._ck(self._lib.fdc_set_peer_framebuffers(self._h, arr, len(ptrs)))

@@ -239,6 +239,12 @@ void* fdc_stream(fdc_ctx* ctx);
  * After every rank's frame has completed (any cross-rank barrier on fdc_stream) each framebuffer holds the
  * whole frame. */
 int fdc_set_peer_framebuffers(fdc_ctx* ctx, void* const* device_ptrs, int n);
+/* How the band reaches the peers registered above.  FDC_GATHER_STORES (default): the shade kernel stores every finished
+ * pixel to every peer (fused, SM-driven).  FDC_GATHER_COPY: the last segment is shaded in `sub_bands` slices of tile
+ * rows and each finished slice is copied to every peer by the copy engines (cudaMemcpyAsync over NVLink) while the
+ * next slice is being shaded; fdc_stream waits for the copies, so the same cross-rank barrier completes the frame. */
+typedef enum fdc_gather_mode { FDC_GATHER_STORES = 0, FDC_GATHER_COPY = 1 } fdc_gather_mode;
+int fdc_set_peer_gather(fdc_ctx* ctx, int mode, int sub_bands);
 /* CUDA IPC plumbing for the above between processes (one process per GPU): make sure the context owns a
  * framebuffer of `rows` x width x 4 bytes (rows >= height; a dedicated cudaMalloc), export its 64-byte
  * cudaIpcMemHandle_t, and map a peer's handle into this process. */

@@ -167,7 +167,7 @@ def test_tile_bands_reassemble_the_frame():
         assert np.array_equal(out, full)
 
 
-def _band_contexts(tr, n):
+def _band_contexts(tr, n, gather="stores"):
     from figdraw_b200.bands import padded_rows
 
     ctxs = [CudaContext(atlasSize=tr.atlas_size, rank=r, nRanks=n) for r in range(n)]
@@ -176,6 +176,7 @@ def _band_contexts(tr, n):
     ptrs = [c.framebufferPtr() for c in ctxs]
     for c in ctxs:
         c.setPeerFramebuffers(ptrs)
+        c.setPeerGather(gather, 3)
         for _idx, key, img in tr.images:
             c.putImage(key, img)
     return ctxs
@@ -187,10 +188,11 @@ def _submit(c, tr, calls):
     c.endFrame()
 
 
-def _render_banded_with_peers(tr, n):
+def _render_banded_with_peers(tr, n, gather="stores"):
     """n band contexts on one device, framebuffers cross-registered as peers: every rank submits the frame, the shade
-    kernel's last segment stores each band into every framebuffer, blur halo rows are read from the owner."""
-    ctxs = _band_contexts(tr, n)
+    kernel's last segment stores each band into every framebuffer (or the copy engines ship it slice by slice), blur
+    halo rows are read from the owner."""
+    ctxs = _band_contexts(tr, n, gather)
     try:
         # Size every context's buffers one rank at a time with the blur calls removed (no cross-rank waits): all ranks
         # share this process and device, and an allocation while a peer spins on our flags would stall both.
@@ -233,6 +235,17 @@ def test_backdrop_blur_halo_exchange_across_bands(n):
         for r, img in enumerate(_render_banded_with_peers(tr, n)):
             mx, frac = diff_stats(img, full)
             assert np.array_equal(img, full), f"rank {r}/{n}: max {mx} LSB, {frac:.5%} of pixels"
+
+
+@pytest.mark.parametrize("n", [2])
+def test_copy_engine_gather_assembles_the_frame(n):
+    """FDC_GATHER_COPY: the last segment is shaded in slices, finished slices are copied to the peers.
+    (Two ranks only: all ranks of this test share one process, and with 1 + 4 streams per context a third context
+    exceeds the device's 8 hardware queues -- a context's kernels could then queue behind another context's barrier.)"""
+    for tr in (ss.config_trace(5, 1280, 720, n_rects=3000, n_glyphs=600), ss.config_trace(2, 1280, 720)):
+        full = _render_banded_with_peers(tr, 1)[0]
+        for r, img in enumerate(_render_banded_with_peers(tr, n, gather="copy")):
+            assert np.array_equal(img, full), f"rank {r}/{n}"
 
 
 def test_backdrop_blur_under_bands_needs_peers():

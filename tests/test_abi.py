@@ -57,3 +57,62 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "figdraw_oracle" not in text, f
+
+
+def test_scene_pod_layouts_match_the_header(tmp_path):
+    """The numpy/ctypes mirrors of the scene PODs (abi.py) against the C compiler's view of include/figdraw_cuda.h."""
+    import subprocess
+
+    from figdraw_b200 import abi
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include <stdio.h>
+#include "figdraw_cuda.h"
+#define S(t) printf(#t " %zu\n", sizeof(t))
+#define O(t, f) printf(#t "." #f " %zu\n", offsetof(t, f))
+int main(void) {
+  S(fdc_call); S(fdc_node_fill); S(fdc_node_shadow); S(fdc_node_stroke); S(fdc_fig); S(fdc_glyph); S(fdc_draw_op);
+  S(fdc_render_list); S(fdc_flatten_env);
+  O(fdc_fig, flags); O(fdc_fig, parent); O(fdc_fig, child_count); O(fdc_fig, screen_box); O(fdc_fig, rotation); O(fdc_fig, fill);
+  O(fdc_fig, corners); O(fdc_fig, corner_radii_y); O(fdc_fig, u);
+  O(fdc_fig, u.rect.stroke); O(fdc_fig, u.drawable.steps); O(fdc_fig, u.drawable.first_op); O(fdc_fig, u.msdf.px_range);
+  O(fdc_fig, u.transform.matrix); O(fdc_fig, u.transform.use_matrix);
+  O(fdc_draw_op, center); O(fdc_draw_op, box); O(fdc_draw_op, controls); O(fdc_draw_op, n_controls);
+  O(fdc_render_list, root_ids); O(fdc_flatten_env, image_keys);
+  return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.rsplit(" ", 1) for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    c = {k: int(v) for k, v in out.items()}
+    assert c["fdc_call"] == abi.CALL_DTYPE.itemsize == 128
+    assert c["fdc_node_fill"] == abi.NODE_FILL_DTYPE.itemsize
+    assert c["fdc_node_shadow"] == abi.NODE_SHADOW_DTYPE.itemsize
+    assert c["fdc_node_stroke"] == abi.NODE_STROKE_DTYPE.itemsize
+    assert c["fdc_fig"] == abi.FIG_DTYPE.itemsize
+    assert c["fdc_glyph"] == abi.GLYPH_DTYPE.itemsize
+    assert c["fdc_draw_op"] == abi.DRAW_OP_DTYPE.itemsize
+    import ctypes
+
+    assert c["fdc_render_list"] == ctypes.sizeof(abi.FdcRenderList)
+    assert c["fdc_flatten_env"] == ctypes.sizeof(abi.FdcFlattenEnv)
+    f = abi.FIG_DTYPE.fields
+    for name in ("flags", "parent", "child_count", "screen_box", "rotation", "fill", "corners", "corner_radii_y"):
+        assert c[f"fdc_fig.{name}"] == f[name][1], name
+    pay = f["payload"][1]
+    assert c["fdc_fig.u"] == pay
+    assert c["fdc_fig.u.rect.stroke"] == pay + abi.FIG_RECT_DTYPE.fields["stroke"][1]
+    assert c["fdc_fig.u.drawable.steps"] == pay + abi.FIG_DRAWABLE_DTYPE.fields["steps"][1]
+    assert c["fdc_fig.u.drawable.first_op"] == pay + abi.FIG_DRAWABLE_DTYPE.fields["first_op"][1]
+    assert c["fdc_fig.u.msdf.px_range"] == pay + abi.FIG_MSDF_DTYPE.fields["px_range"][1]
+    assert c["fdc_fig.u.transform.matrix"] == pay + abi.FIG_TRANSFORM_DTYPE.fields["matrix"][1]
+    assert c["fdc_fig.u.transform.use_matrix"] == pay + abi.FIG_TRANSFORM_DTYPE.fields["use_matrix"][1]
+    d = abi.DRAW_OP_DTYPE.fields
+    for name in ("center", "box", "controls", "n_controls"):
+        assert c[f"fdc_draw_op.{name}"] == d[name][1], name
+    assert c["fdc_render_list.root_ids"] == abi.FdcRenderList.root_ids.offset
+    assert c["fdc_flatten_env.image_keys"] == abi.FdcFlattenEnv.image_keys.offset

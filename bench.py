@@ -375,12 +375,13 @@ def main():
 
     # e2e, pipelined (N = 1): three contexts on three streams, like a three-image swap chain.  Every step still copies
     # its own records host->device and its own frame device->host; in steady state frame k's readback, frame k+1's
-    # kernels and frame k+2's upload are in flight together.  Throughput over the steps, not latency.
+    # kernels and frame k+2's upload are in flight together.  Throughput over the steps, not latency.  (Measured: deeper
+    # rings and fdc_read_pixels_async change nothing -- 33 MB down + 31 MB up per frame is what PCIe sustains in ~0.96 ms.)
     e2e_pipe_ms = None
     if world == 1:
         ring = [(ctx, prepared, out_np)]
         extra_ctx = []
-        for _ in range(2):
+        for _ in range(max(1, int(os.environ.get("FDC_E2E_RING", "3")) - 1)):
             c2 = CudaContext(atlasSize=trace.atlas_size, device=local_rank)
             for _i, key, img in trace.images:
                 c2.putImage(key, img)
@@ -517,7 +518,7 @@ def main():
                 "frames_per_s": round(1e3 / ms_step, 2),
                 "e2e": {"value": round(mpx / ((e2e_pipe_ms or e2e_ms) * 1e-3), 2), "unit": METRIC,
                         "ms_per_step": round(e2e_pipe_ms or e2e_ms, 4), "latency_ms": round(e2e_ms, 4),
-                        "mode": ("three contexts in flight: step k's readback, step k+1's kernels and step k+2's upload overlap"
+                        "mode": (f"{depth} contexts in flight: step k's readback, step k+1's kernels and step k+2's upload overlap"
                                  if e2e_pipe_ms else "one frame at a time"),
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches_per_frame * args.steps, "launches_per_frame": launches_per_frame,

@@ -153,7 +153,7 @@ class FdcFrameStats(ctypes.Structure):
 # Every symbol include/figdraw_cuda.h declares (checked by tests/test_abi.py against the header text).
 EXPORTS = [
     "fdc_create", "fdc_destroy", "fdc_last_error", "fdc_abi_version",
-    "fdc_begin_frame", "fdc_end_frame", "fdc_read_pixels", "fdc_sync", "fdc_replay_frame",
+    "fdc_begin_frame", "fdc_end_frame", "fdc_read_pixels", "fdc_read_pixels_async", "fdc_sync", "fdc_replay_frame",
     "fdc_translate", "fdc_rotate", "fdc_scale", "fdc_apply_transform", "fdc_save_transform",
     "fdc_restore_transform", "fdc_transform_mirrors_y", "fdc_get_transform",
     "fdc_sdf_aa_factor", "fdc_set_sdf_aa_factor", "fdc_set_text_subpixel_positioning_enabled",
@@ -253,6 +253,7 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_open_peer_framebuffer", c.c_int, P, c.POINTER(c.c_uint8), c.POINTER(P))
     sig("fdc_get_frame_stats", c.c_int, P, c.POINTER(FdcFrameStats))
     sig("fdc_debug_shade_stats", c.c_int, P, c.POINTER(c.c_uint64))
+    sig("fdc_read_pixels_async", c.c_int, P, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p)
     sig("fdc_set_peer_gather", c.c_int, P, c.c_int, c.c_int)
     sig("fdc_flatten_renders", c.c_int, c.POINTER(FdcRenderList), c.c_uint32, c.c_void_p, c.c_void_p,
         c.POINTER(FdcFlattenEnv), c.c_void_p, c.c_size_t, c.POINTER(c.c_size_t))

@@ -203,6 +203,7 @@ struct fdc_ctx {
   struct Rect4 { float x, y, w, h; };
   std::unordered_map<uint64_t, Rect4> entries;
   std::vector<fdc_call> flat_calls;  // scratch of fdc_render_frame
+  struct { uint8_t* out = nullptr; int x = 0, y = 0, w = 0, h = 0; } pending_read;  // fdc_read_pixels_async in flight
   DevBuf<AtlasEntry> d_table;
   uint32_t table_cap = 0;
   bool table_dirty = true;
@@ -234,6 +235,7 @@ struct fdc_ctx {
   uint32_t call_ordinal = 0;       // backend calls seen this frame
   uint32_t last_draw_ordinal = 0;  // ordinal of the previous draw
   bool have_frame = false;         // a recorded frame is resident on the device (replay / debug)
+  uint32_t n_replays = 0;          // frames re-run by resolve_frame after a bin-list regrow
 
   // ---- device frame data
   DevBuf<fdc_call> d_draws;
@@ -877,6 +879,7 @@ int resolve_frame(fdc_ctx* ctx) {
     // this frame's values, which the flags have already reached.  Blur halo rows then show the neighbours' current
     // state; lists only overflow on the first frame of a much larger scene.
     ctx->barrier_seq = ctx->frame_barrier_base;
+    ctx->n_replays++;
     int rc = execute_frame(ctx, false);
     if (rc) return rc;
   }
@@ -981,12 +984,14 @@ void fdc_destroy(fdc_ctx* ctx) {
 }
 
 // ------------------------------------------------------------------------------------------------- frame
+static int sync_frame(fdc_ctx* ctx);
+
 int fdc_begin_frame(fdc_ctx* ctx, int width, int height, int clear_main, const float clear_rgba[4]) {
   if (!ctx) return FDC_ERR_INVALID;
   if (ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "ctx.beginFrame has already been called.");
   if (width <= 0 || height <= 0 || width > 32640 || height > 32640) return ctx->fail(FDC_ERR_INVALID, "bad frame size %dx%d", width, height);
   CK(cudaSetDevice(ctx->device));
-  int rc = resolve_frame(ctx);  // previous frame must be complete before its recording is dropped
+  int rc = sync_frame(ctx);  // previous frame (and its read-back) must be complete before its recording is dropped
   if (rc) return rc;
   ctx->have_frame = false;
   if (ctx->ext_fb == nullptr && (width != ctx->W || height != ctx->H)) {
@@ -1035,10 +1040,44 @@ int fdc_replay_frame(fdc_ctx* ctx) {
   return execute_frame(ctx, false);
 }
 
+static int enqueue_readback(fdc_ctx* ctx) {
+  auto& r = ctx->pending_read;
+  CK(cudaMemcpy2DAsync(r.out, (size_t)r.w * 4, ctx->fb() + ((size_t)r.y * ctx->W + r.x) * 4, (size_t)ctx->W * 4, (size_t)r.w * 4,
+                       (size_t)r.h, cudaMemcpyDeviceToHost, ctx->stream));
+  return FDC_OK;
+}
+
+// resolve_frame + completion of an asynchronous read-back
+static int sync_frame(fdc_ctx* ctx) {
+  const uint32_t replays_before = ctx->n_replays;
+  int rc = resolve_frame(ctx);
+  if (rc == FDC_OK && ctx->pending_read.out) {
+    if (ctx->n_replays != replays_before) {  // the frame was re-run after a list regrow: the copy read the aborted one
+      rc = enqueue_readback(ctx);
+      if (rc == FDC_OK) CK(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  ctx->pending_read.out = nullptr;
+  return rc;
+}
+
 int fdc_sync(fdc_ctx* ctx) {
   if (!ctx) return FDC_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
-  return resolve_frame(ctx);
+  return sync_frame(ctx);
+}
+
+// Asynchronous readPixels: the device-to-host copy is queued behind the frame on fdc_stream and this call returns;
+// `out_rgba` (pinned host memory for a truly asynchronous copy) is valid after the next fdc_sync.
+int fdc_read_pixels_async(fdc_ctx* ctx, int x, int y, int w, int h, uint8_t* out_rgba) {
+  if (!ctx || !out_rgba) return FDC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->have_frame || !ctx->fb() || ctx->W <= 0) return ctx->fail(FDC_ERR_STATE, "no frame has been rendered");
+  if (w <= 0 || h <= 0) { x = 0; y = 0; w = ctx->W; h = ctx->H; }
+  if (x < 0 || y < 0 || x + w > ctx->W || y + h > ctx->H) return ctx->fail(FDC_ERR_INVALID, "readPixels rect outside the frame");
+  ctx->pending_read.out = out_rgba;
+  ctx->pending_read.x = x; ctx->pending_read.y = y; ctx->pending_read.w = w; ctx->pending_read.h = h;
+  return enqueue_readback(ctx);
 }
 
 int fdc_read_pixels(fdc_ctx* ctx, int x, int y, int w, int h, uint8_t* out_rgba) {

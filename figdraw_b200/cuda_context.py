@@ -104,6 +104,11 @@ class CudaContext(BackendContext):
         self._ck(self._lib.fdc_read_pixels(self._h, x, y, w, h, out.ctypes.data))
         return out
 
+    def readPixelsAsync(self, out: np.ndarray, frame=(0, 0, 0, 0)) -> None:
+        """Queue the read-back behind the frame and return; `out` (pinned host memory) is valid after `sync()`."""
+        x, y, w, h = (int(v) for v in frame)
+        self._ck(self._lib.fdc_read_pixels_async(self._h, x, y, w, h, out.ctypes.data))
+
     def pixelScale(self) -> float:
         return float(self._lib.fdc_pixel_scale(self._h))
 

@@ -148,6 +148,9 @@ int fdc_end_frame(fdc_ctx* ctx);
 /* readPixels glcontext.nim:2094-2135: RGBA8, top-left origin, tightly packed; w<=0||h<=0 reads the whole frame.
  * Synchronises the context stream. */
 int fdc_read_pixels(fdc_ctx* ctx, int x, int y, int w, int h, uint8_t* out_rgba);
+/* Asynchronous variant for a pipelined presenter: queues the device-to-host copy behind the frame on fdc_stream and
+ * returns; `out_rgba` (pinned host memory) holds the pixels after the next fdc_sync.  One request per frame. */
+int fdc_read_pixels_async(fdc_ctx* ctx, int x, int y, int w, int h, uint8_t* out_rgba);
 /* Blocks until all submitted frames are complete. */
 int fdc_sync(fdc_ctx* ctx);
 /* Re-launches the kernels of the last completed frame on the data already resident in device memory (no

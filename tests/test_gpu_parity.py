@@ -367,3 +367,30 @@ def test_native_front_end_cfg5_scene_equals_call_stream():
     ctx.renderFrameNative(scene, (1280, 720))
     assert np.array_equal(ctx.readPixels(), want)
     ctx.close()
+
+
+def test_async_readback_matches_readpixels():
+    import torch
+
+    tr = ss.config_trace(2, 1280, 720)
+    ctx = CudaContext(atlasSize=tr.atlas_size)
+    want = render_trace(tr, ctx)
+    host = torch.empty((tr.height, tr.width, 4), dtype=torch.uint8).pin_memory().numpy()
+    for _ in range(2):
+        host[:] = 0
+        ctx.beginFrame((tr.width, tr.height), clearMain=tr.clear is not None, clearMainColor=tr.clear or (1.0, 1.0, 1.0, 1.0))
+        ctx.submitCalls(tr.calls)
+        ctx.endFrame()
+        ctx.readPixelsAsync(host)
+        ctx.sync()
+        assert np.array_equal(host, want)
+    # a much larger scene on the same context: the bin lists overflow, the frame is re-run at sync and read back again
+    big = ss.config_trace(5, 1280, 720, n_rects=6000, n_glyphs=0)
+    want_big = render_trace(big)
+    ctx.beginFrame((big.width, big.height), clearMain=True)
+    ctx.submitCalls(big.calls)
+    ctx.endFrame()
+    ctx.readPixelsAsync(host)
+    ctx.sync()
+    assert np.array_equal(host, want_big)
+    ctx.close()

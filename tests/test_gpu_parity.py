@@ -13,6 +13,7 @@ import pytest
 from figdraw_b200 import scenes
 from figdraw_b200 import scenes_fuzz
 from figdraw_b200 import scenes_synth as ss
+from figdraw_b200 import abi
 from figdraw_b200.abi import Op
 from figdraw_b200.cuda_context import CudaContext, FigDrawError, render_trace
 from figdraw_b200.figbackend import Trace
@@ -393,4 +394,71 @@ def test_async_readback_matches_readpixels():
     ctx.readPixelsAsync(host)
     ctx.sync()
     assert np.array_equal(host, want_big)
+    ctx.close()
+
+
+def test_ragged_and_extreme_sizes():
+    """Frames that are not a multiple of the 16-px tile / 128-px bin, a 1x1 frame, a very wide one, huge coordinates."""
+    from figdraw_b200.figbackend import TraceBackend, circularRadii, solid
+    from figdraw_b200.fignodes import rgba
+
+    def scene(w, h):
+        tb = TraceBackend()
+        tb.beginFrame((w, h), clearMain=True, clearMainColor=(0.9, 0.9, 0.8, 1.0))
+        tb.drawRoundedRectSdf((-3.5, -2.25, w * 0.7, h * 0.6), solid(rgba(200, 30, 40, 200)), circularRadii((9, 3, 0, 14)))
+        tb.drawRoundedRectSdf((w * 0.3, h * 0.2, w, h), solid(rgba(10, 90, 220, 255)), circularRadii((5, 5, 5, 5)),
+                              mode=abi.SdfMode.sdfModeDropShadow, factor=6.0, spread=3.0, shapeSize=(w * 0.5, h * 0.5))
+        tb.drawRoundedRectSdf((-1.0e6, -1.0e6, 2.0e6, 2.0e6), solid(rgba(0, 0, 0, 20)), circularRadii((0, 0, 0, 0)))
+        tb.saveTransform()
+        tb.translate((w * 0.5, h * 0.5))
+        tb.rotate(0.4)
+        tb.drawRoundedRectSdf((-w * 0.2, -h * 0.1, w * 0.4, h * 0.2), solid(rgba(20, 160, 60, 180)), circularRadii((4, 4, 4, 4)))
+        tb.restoreTransform()
+        tb.endFrame()
+        return tb.trace()
+
+    for w, h in ((1, 1), (17, 5), (333, 217), (4099, 33), (130, 2051)):
+        tr = scene(w, h)
+        got, want = render_trace(tr), oracle.render_trace(tr)
+        mx, frac = diff_stats(got, want)
+        assert mx <= MAX_DIFF, f"{w}x{h}: max {mx} LSB"
+    # ragged bands: 217 rows = 14 tile rows over 3 ranks (5 + 5 + 4), the last tile row only 9 px high
+    tr = scene(333, 217)
+    full = render_trace(tr)
+    out = np.zeros_like(full)
+    for r in range(3):
+        ctx = CudaContext(rank=r, nRanks=3)
+        img = render_trace(tr, ctx)
+        y0, y1 = ctx.bandRows()
+        out[y0:y1] = img[y0:y1]
+        ctx.close()
+    assert np.array_equal(out, full)
+
+
+def test_mask_nesting_limit():
+    """Eight nested texture-mask levels render like the reference; the ninth is refused with FDC_ERR_CAPACITY."""
+    from figdraw_b200.figbackend import TraceBackend, circularRadii, solid
+    from figdraw_b200.fignodes import rgba
+
+    tb = TraceBackend()
+    tb.beginFrame((256, 256), clearMain=True)
+    for d in range(8):
+        tb.beginMask((8.0 + 9 * d, 6.0 + 7 * d, 230.0 - 15 * d, 236.0 - 13 * d), circularRadii((20, 6, 12, 0)))
+        tb.endMask()
+        tb.drawRoundedRectSdf((0.0, 0.0, 256.0, 256.0), solid(rgba(30 * d, 255 - 25 * d, 90, 130)), circularRadii((0, 0, 0, 0)))
+    for _ in range(8):
+        tb.popMask()
+    tb.endFrame()
+    tr = tb.trace()
+    got, want = render_trace(tr), oracle.render_trace(tr)
+    mx, _ = diff_stats(got, want)
+    assert mx <= MAX_DIFF
+    ctx = CudaContext()
+    ctx.beginFrame((64, 64), clearMain=True)
+    for d in range(8):
+        ctx.beginMask((0, 0, 64, 64), circularRadii((0, 0, 0, 0)))
+        ctx.endMask()
+    with pytest.raises(FigDrawError) as e:
+        ctx.beginMask((0, 0, 64, 64), circularRadii((0, 0, 0, 0)))
+    assert e.value.code == 4  # FDC_ERR_CAPACITY
     ctx.close()

@@ -202,7 +202,10 @@ struct fdc_ctx {
   std::vector<uint16_t> heights;
   struct Rect4 { float x, y, w, h; };
   std::unordered_map<uint64_t, Rect4> entries;
-  std::vector<fdc_call> flat_calls;  // scratch of fdc_render_frame
+  // fdc_render_frame: two page-locked record buffers used alternately -- frame k+1 is flattened into one while the
+  // asynchronous upload of frame k may still be reading the other (fdc_begin_frame(k+1) then waits for frame k)
+  PinnedBuf<fdc_call> flat[2];
+  int flat_idx = 0;
   struct { uint8_t* out = nullptr; int x = 0, y = 0, w = 0, h = 0; } pending_read;  // fdc_read_pixels_async in flight
   DevBuf<AtlasEntry> d_table;
   uint32_t table_cap = 0;
@@ -968,6 +971,7 @@ void fdc_destroy(fdc_ctx* ctx) {
   for (int l = 0; l < ctx->n_levels; l++) cudaFree(ctx->levels[l]);
   ctx->d_table.release();
   ctx->draws.release(); ctx->runs.release(); ctx->xforms.release(); ctx->rectmasks.release();
+  ctx->flat[0].release(); ctx->flat[1].release();
   ctx->d_draws.release(); ctx->d_runs.release(); ctx->d_xforms.release(); ctx->d_rectmasks.release();
   ctx->d_prims.release(); ctx->d_geoms.release(); ctx->d_exts.release(); ctx->d_prim_call.release();
   ctx->d_chunk_counts.release(); ctx->d_warp_counts.release(); ctx->d_cbin_start.release(); ctx->d_coarse_list.release();
@@ -1656,18 +1660,21 @@ int fdc_render_frame(fdc_ctx* ctx, const fdc_render_list* lists, uint32_t n_list
   env.subpixel_enabled = ctx->subpixel_enabled ? 1u : 0u;
   env.image_keys = keys.data();
   env.n_image_keys = keys.size();
-  // the scratch keeps last frame's size: a steady scene flattens in one pass into memory that is already mapped
-  if (ctx->flat_calls.size() < 1024) ctx->flat_calls.resize(1024);
+  ctx->flat_idx ^= 1;
+  PinnedBuf<fdc_call>& buf = ctx->flat[ctx->flat_idx];
+  // the buffer keeps its size: a steady scene flattens in one pass
+  if (buf.cap < 1024 && !buf.reserve(1024)) return ctx->fail(FDC_ERR_CUDA, "cudaMallocHost failed");
   size_t n_calls = 0;
   for (int pass = 0; pass < 2; pass++) {
-    const char* err = fdc::flatten_renders(lists, n_lists, glyphs, ops, env, ctx->flat_calls.data(), ctx->flat_calls.size(), &n_calls);
+    const char* err = fdc::flatten_renders(lists, n_lists, glyphs, ops, env, buf.p, buf.cap, &n_calls);
     if (err) return ctx->fail(FDC_ERR_INVALID, "%s", err);
-    if (n_calls <= ctx->flat_calls.size()) break;
-    ctx->flat_calls.resize(n_calls + n_calls / 8);
+    if (n_calls <= buf.cap) break;
+    buf.n = 0;  // nothing to keep
+    if (!buf.reserve(n_calls + n_calls / 8)) return ctx->fail(FDC_ERR_CUDA, "cudaMallocHost failed");
   }
   int rc = fdc_begin_frame(ctx, (int)(frame_w * ui_scale), (int)(frame_h * ui_scale), clear_main, clear_rgba);
   if (rc) return rc;
-  rc = fdc_submit_calls(ctx, ctx->flat_calls.data(), n_calls);
+  rc = fdc_submit_calls(ctx, buf.p, n_calls);
   if (rc) return rc;
   return fdc_end_frame(ctx);
 }

@@ -515,6 +515,19 @@ __device__ __forceinline__ bool rect_hits(uint32_t r, uint32_t bx, uint32_t by) 
   return (r & 255u) <= bx && bx <= ((r >> 16) & 255u) && ((r >> 8) & 255u) <= by && by <= (r >> 24);
 }
 
+// Sum of bytes 0..k-1 of 16 bytes (k = 0..15).
+__device__ __forceinline__ uint32_t bytes_below(const uint4& v, int k) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int n = k - 4 * j;  // bytes of word j that count
+    if (n >= 4) s = __dp4a(w[j], 0x01010101u, s);
+    else if (n > 0) s = __dp4a(w[j] & ((1u << (8 * n)) - 1u), 0x01010101u, s);
+  }
+  return s;
+}
+
 // 32x32 bit-matrix transpose across a warp: lane i passes row i (bit k = A[i][k]) and receives column i (bit k = A[k][i]).
 // Five butterfly steps swapping off-diagonal blocks of size 16, 8, 4, 2, 1.
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
@@ -544,7 +557,7 @@ __global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restri
                                                             const uint32_t* __restrict__ cbin_start,
                                                             uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
                                                             uint32_t* __restrict__ counters) {
-  __shared__ uint16_t wcnt[kWarps][kSlots];  // per-warp counts (count pass) / running offsets inside the chunk (scatter)
+  __shared__ uint4 wc8[kSlots];  // per slot: the 16 warps' counts, one byte each (a warp contributes at most 32)
   __shared__ uint32_t bitmap[kWarps][32];
   __shared__ uint32_t gbase[kScatter ? kSlots : 1];  // global position of this chunk's slice of each bin
   const uint32_t chunk = blockIdx.x;
@@ -553,23 +566,18 @@ __global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restri
   const int row1 = min(row0 + rows_per_cta, f.cby);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (kScatter && counters[2] > coarse_cap) return;  // overflow: host regrows and replays
-  uint8_t* wc_global = warp_counts + ((size_t)chunk * gridDim.y + blockIdx.y) * (size_t)(kWarps * kSlots);
+  uint4* wc_global = reinterpret_cast<uint4*>(warp_counts + ((size_t)chunk * gridDim.y + blockIdx.y) * (size_t)(kWarps * kSlots));
   const uint32_t rect = coarse_rect(prims, base_idx + threadIdx.x, n, f);
 
   // slots in use: (rows of this CTA) x (words per row) x 32 -- 544 of the 1024 at 4K; everything per-slot below is
   // bounded by it (zeroing, the prefix over warps and the per-warp count array are the fixed cost of this kernel)
   const int used = (row1 - row0) * wpr * 32;
   if (!kScatter) {
-    for (int k = threadIdx.x; k < kWarps * (used / 2); k += blockDim.x) {
-      const int w = k / (used / 2), j = k % (used / 2);
-      reinterpret_cast<uint32_t*>(&wcnt[w][0])[j] = 0;
-    }
+    for (int sl = threadIdx.x; sl < used; sl += blockDim.x) wc8[sl] = make_uint4(0u, 0u, 0u, 0u);
   } else {
-    // per-warp counts -> exclusive prefix over warps; base of this chunk's slice of each bin
+    // per-warp counts of the count pass; base of this chunk's slice of each bin
     for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {
-      uint32_t run = 0;
-#pragma unroll
-      for (int w = 0; w < kWarps; w++) { const uint32_t c = wc_global[w * kSlots + sl]; wcnt[w][sl] = (uint16_t)run; run += c; }
+      wc8[sl] = __ldg(&wc_global[sl]);
       const int r = row0 + (sl >> 5) / wpr, x = ((sl >> 5) % wpr) * 32 + (sl & 31);
       if (r < row1 && x < f.cbx) {
         const int b = r * f.cbx + x;
@@ -613,9 +621,9 @@ __global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restri
     uint32_t cm = transpose32(hm, lane);
     const int sl = wi * 32 + lane;
     if (!kScatter) {
-      if (cm) wcnt[warp][sl] = (uint16_t)__popc(cm);  // each warp visits a word once
+      if (cm) reinterpret_cast<uint8_t*>(wc8)[sl * 16 + warp] = (uint8_t)__popc(cm);  // each warp visits a word once
     } else if (cm) {
-      uint32_t pos = gbase[sl] + wcnt[warp][sl];
+      uint32_t pos = gbase[sl] + bytes_below(wc8[sl], warp);  // entries of earlier warps of this chunk come first
       const uint32_t first = base_idx + (uint32_t)warp * 32u;
       while (cm) {
         const int pl = __ffs(cm) - 1;
@@ -628,9 +636,9 @@ __global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restri
     __syncthreads();
     for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {
       const int r = row0 + (sl >> 5) / wpr, x = ((sl >> 5) % wpr) * 32 + (sl & 31);
-      uint32_t tot = 0;
-#pragma unroll
-      for (int w = 0; w < kWarps; w++) { const uint32_t c = wcnt[w][sl]; wc_global[w * kSlots + sl] = (uint8_t)c; tot += c; }
+      const uint4 v = wc8[sl];
+      wc_global[sl] = v;
+      const uint32_t tot = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
       if (r < row1 && x < f.cbx) chunk_counts[(size_t)(r * f.cbx + x) * gridDim.x + chunk] = tot;
     }
   }

@@ -293,16 +293,16 @@ type
 proc fdc_submit_calls(ctx: FdcCtx, calls: ptr FdcCall, n: csize_t): cint {.importc, header: "figdraw_cuda.h".}
 proc fdc_submit_draws(ctx: FdcCtx, draws: ptr FdcCall, n: csize_t): cint {.importc, header: "figdraw_cuda.h".}
 proc fdc_render_frame(ctx: FdcCtx, lists: ptr FdcRenderList, nLists: uint32, glyphs: ptr FdcGlyph, ops: ptr FdcDrawOp,
-                      uiScale, frameW, frameH: cfloat, clearMain: cint, clearRgba: ptr cfloat): cint {.importc, header: "figdraw_cuda.h".}
+                      points: ptr cfloat, uiScale, frameW, frameH: cfloat, clearMain: cint, clearRgba: ptr cfloat): cint {.importc, header: "figdraw_cuda.h".}
 
 proc submitCalls*(ctx: CudaContext, calls: openArray[FdcCall]) =
   ## A recorded display list (one record per backend call) replayed as if the methods above had been called.
   if calls.len > 0: ctx.ck fdc_submit_calls(ctx.h, calls[0].unsafeAddr, calls.len.csize_t)
 
 proc renderFrameNative*(ctx: CudaContext, lists: openArray[FdcRenderList], glyphs: ptr FdcGlyph, ops: ptr FdcDrawOp,
-                        frameSize: Vec2, clearMain: bool, clearColor: Color) =
+                        points: ptr cfloat, frameSize: Vec2, clearMain: bool, clearColor: Color) =
   ## renderFrame (figrender.nim:1960-2002) with the node DFS done inside the library: `lists` point at POD copies of
   ## `Renders.layers[*].nodes` (fdc_fig), in table order.
   var rgba = [clearColor.r.cfloat, clearColor.g.cfloat, clearColor.b.cfloat, clearColor.a.cfloat]
-  ctx.ck fdc_render_frame(ctx.h, lists[0].unsafeAddr, lists.len.uint32, glyphs, ops, figUiScale().cfloat,
+  ctx.ck fdc_render_frame(ctx.h, lists[0].unsafeAddr, lists.len.uint32, glyphs, ops, points, figUiScale().cfloat,
                           frameSize.x.cfloat, frameSize.y.cfloat, clearMain.cint, rgba[0].addr)

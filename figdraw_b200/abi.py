@@ -118,9 +118,10 @@ FIG_TRANSFORM_DTYPE = np.dtype([("translation", "<f4", (2,)), ("matrix", "<f4", 
 GLYPH_DTYPE = np.dtype([("key", "<u8"), ("pos", "<f4", (2,)), ("fill", NODE_FILL_DTYPE)])
 DRAW_OP_DTYPE = np.dtype([("kind", "<u4"), ("a", "<f4", (2,)), ("b", "<f4", (2,)), ("center", "<f4", (2,)), ("radius", "<f4"),
                           ("box", "<f4", (4,)), ("corners", "<f4", (4,)), ("ellipse_radii", "<f4", (2,)),
-                          ("controls", "<f4", (6,)), ("n_controls", "<u4")])
+                          ("start_angle", "<f4"), ("sweep_angle", "<f4"), ("first_point", "<u4"), ("n_points", "<u4"),
+                          ("steps", "<u4")])
 assert NODE_FILL_DTYPE.itemsize == 16 and NODE_SHADOW_DTYPE.itemsize == 36 and NODE_STROKE_DTYPE.itemsize == 24
-assert FIG_RECT_DTYPE.itemsize == FIG_PAYLOAD_BYTES and GLYPH_DTYPE.itemsize == 32 and DRAW_OP_DTYPE.itemsize == 100
+assert FIG_RECT_DTYPE.itemsize == FIG_PAYLOAD_BYTES and GLYPH_DTYPE.itemsize == 32 and DRAW_OP_DTYPE.itemsize == 92
 
 
 class FdcRenderList(ctypes.Structure):
@@ -255,9 +256,9 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_debug_shade_stats", c.c_int, P, c.POINTER(c.c_uint64))
     sig("fdc_read_pixels_async", c.c_int, P, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p)
     sig("fdc_set_peer_gather", c.c_int, P, c.c_int, c.c_int)
-    sig("fdc_flatten_renders", c.c_int, c.POINTER(FdcRenderList), c.c_uint32, c.c_void_p, c.c_void_p,
+    sig("fdc_flatten_renders", c.c_int, c.POINTER(FdcRenderList), c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,
         c.POINTER(FdcFlattenEnv), c.c_void_p, c.c_size_t, c.POINTER(c.c_size_t))
-    sig("fdc_render_frame", c.c_int, P, c.POINTER(FdcRenderList), c.c_uint32, c.c_void_p, c.c_void_p, c.c_float,
+    sig("fdc_render_frame", c.c_int, P, c.POINTER(FdcRenderList), c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p, c.c_float,
         c.c_float, c.c_float, c.c_int, c.POINTER(c.c_float))
     sig("fdc_debug_bins", c.c_int, P, c.c_int, u32p, c.c_size_t, u32p, c.c_size_t, c.POINTER(c.c_size_t),
         c.POINTER(c.c_size_t))

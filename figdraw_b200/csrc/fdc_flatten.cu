@@ -116,20 +116,49 @@ float radius_corner(float radius) {  // figrender.nim:560-571 (uint16 corner)
   return (float)(int)nim_round(radius);
 }
 
+struct V2 {
+  float x, y;
+};
+inline V2 operator+(V2 a, V2 b) { return {a.x + b.x, a.y + b.y}; }
+inline V2 operator-(V2 a, V2 b) { return {a.x - b.x, a.y - b.y}; }
+inline V2 operator*(V2 a, float k) { return {a.x * k, a.y * k}; }
+inline float vlen(V2 v) { return sqrtf(v.x * v.x + v.y * v.y); }
+inline V2 normalized_or(V2 v, V2 fallback) {  // figrender.nim:911-916
+  const float len = vlen(v);
+  if (len <= 0.000001f) return fallback;
+  return {v.x / len, v.y / len};
+}
+inline V2 normal_left(V2 d) { return {-d.y, d.x}; }
+inline float cross2(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
+// Transcendentals in double, rounded to float32: what the Python mirror does (the reference calls cosf/sinf/acosf).
+inline float cos32(float a) { return (float)cos((double)a); }
+inline float sin32(float a) { return (float)sin((double)a); }
+
+struct Span {  // DrawableQuadraticSpan, figrender.nim:1203-1214
+  V2 p0, p1, p2;
+  V2 start_tangent() const { return normalized_or(p1 - p0, normalized_or(p2 - p0, V2{1.0f, 0.0f})); }
+  V2 end_tangent() const { return normalized_or(p2 - p1, normalized_or(p2 - p0, V2{1.0f, 0.0f})); }
+};
+
+constexpr float kAdaptiveTolerancePx = 0.5f;
+constexpr int kMaxAdaptiveSteps = 192;  // max(DefaultDrawableBezierSteps * 4, 64), fignodes.nim:100
+constexpr int kMaxAdaptiveDepth = 8;
+
 struct Flattener {
   fdc_call* out;       // caller's buffer: records past `cap` are counted, not stored
   size_t cap, n = 0;
   fdc_call spill;      // where a record past the capacity is "written"
   const fdc_glyph* glyphs;
   const fdc_draw_op* ops;
+  const float* points;
   const fdc_flatten_env& env;
   float ui;
   float aa;
   bool subpixel;
   const char* error = nullptr;
 
-  Flattener(fdc_call* o, size_t c, const fdc_glyph* g, const fdc_draw_op* d, const fdc_flatten_env& e)
-      : out(o), cap(c), glyphs(g), ops(d), env(e), ui(e.ui_scale), aa(e.aa_factor), subpixel(e.subpixel_enabled != 0) {}
+  Flattener(fdc_call* o, size_t c, const fdc_glyph* g, const fdc_draw_op* d, const float* pts, const fdc_flatten_env& e)
+      : out(o), cap(c), glyphs(g), ops(d), points(pts), env(e), ui(e.ui_scale), aa(e.aa_factor), subpixel(e.subpixel_enabled != 0) {}
 
   // ---- the backend calls, recorded
   fdc_call& rec(uint32_t op) {
@@ -334,9 +363,10 @@ struct Flattener {
     box[0] = mn[0] - padding; box[1] = mn[1] - padding;
     box[2] = mx[0] - mn[0] + padding * 2.0f; box[3] = mx[1] - mn[1] + padding * 2.0f;
   }
-  // figrender.nim:1330-1370
-  void quadratic_bezier(float ox, float oy, const float p0[2], const float p1[2], const float p2[2], const fdc_node_stroke& stroke) {
-    const int cap = stroke.cap == 0 ? 1 : stroke.cap;  // scAuto -> scRound
+  // figrender.nim:1327-1366.  cap 0 (scAuto) resolves through the stroke.
+  void quadratic_bezier(float ox, float oy, V2 q0, V2 q1, V2 q2, const fdc_node_stroke& stroke, int cap_in) {
+    const int cap = cap_in != 0 ? cap_in : (stroke.cap == 0 ? 1 : stroke.cap);  // scAuto -> scRound
+    const float p0[2] = {q0.x, q0.y}, p1[2] = {q1.x, q1.y}, p2[2] = {q2.x, q2.y};
     const float cr = (p1[0] - p0[0]) * (p2[1] - p1[1]) - (p1[1] - p0[1]) * (p2[0] - p1[0]);
     if (fabs((double)cr) <= 0.0001) {
       fdc_node_stroke s2 = stroke;
@@ -361,6 +391,225 @@ struct Flattener {
     r.f[10] = weight * ui;
     r.u[0] = (uint32_t)cap;
     put_fill(r, to_backend_fill(stroke.fill));
+  }
+  void line_v(float ox, float oy, V2 a, V2 b, const fdc_node_stroke& stroke) {
+    const float pa[2] = {a.x, a.y}, pb[2] = {b.x, b.y};
+    drawable_line(ox, oy, pa, pb, stroke);
+  }
+  // figrender.nim:1010-1039
+  void endpoint_cap(float ox, float oy, V2 point, V2 tangent, float radius, const fdc_node_stroke& stroke, int cap, bool is_start) {
+    if (radius <= 0.0f || fill_alpha_max(stroke.fill) == 0) return;
+    if (cap == 1) {
+      stroke_cap(ox + point.x, oy + point.y, radius, stroke.fill);
+    } else if (cap == 3) {
+      const V2 dir = normalized_or(tangent, V2{1.0f, 0.0f});
+      const V2 a = is_start ? point - dir * radius : point;
+      const V2 b = is_start ? point : point + dir * radius;
+      fdc_node_stroke s2 = stroke;
+      s2.cap = 2;  // scButt
+      line_v(ox, oy, a, b, s2);
+    }
+  }
+  // figrender.nim:1049-1057
+  void filled_quad(const V2 v[4], const fdc_node_fill& fill) {
+    if (fill_alpha_max(fill) == 0) return;
+    const uint32_t color = fill_center_color(fill);
+    fdc_call& c = rec(FDC_OP_FILLED_QUAD);
+    for (int k = 0; k < 4; k++) {
+      c.f[2 * k] = v[k].x * ui;
+      c.f[2 * k + 1] = v[k].y * ui;
+      c.u[3 + k] = color;
+    }
+  }
+  // figrender.nim:1059-1109
+  void stroke_join(float ox, float oy, V2 point, V2 incoming_tangent, V2 outgoing_tangent, float radius, const fdc_node_fill& fill, int join) {
+    if (radius <= 0.0f || fill_alpha_max(fill) == 0) return;
+    if (join == 1) {  // sjRound
+      stroke_cap(ox + point.x, oy + point.y, radius, fill);
+      return;
+    }
+    if (join != 2 && join != 3) return;  // sjBevel, sjMiter
+    const V2 incoming = normalized_or(incoming_tangent, V2{1.0f, 0.0f});
+    const V2 outgoing = normalized_or(outgoing_tangent, incoming);
+    const float turn = cross2(incoming, outgoing);
+    if (fabs((double)turn) <= 0.0001) return;
+    const float side = turn > 0.0f ? -1.0f : 1.0f;
+    const V2 in_outer = point + normal_left(incoming) * (radius * side);
+    const V2 out_outer = point + normal_left(outgoing) * (radius * side);
+    const V2 origin{ox, oy};
+    if (join == 3) {
+      const float denom = cross2(incoming, outgoing);  // lineIntersection(p = in_outer, r = incoming, q = out_outer, s = outgoing)
+      if (!(fabs((double)denom) <= 0.000001)) {
+        const float t = cross2(out_outer - in_outer, outgoing) / denom;
+        const V2 miter = in_outer + incoming * t;
+        if (vlen(miter - point) <= radius * 4.0f) {
+          const V2 q[4] = {origin + point, origin + in_outer, origin + miter, origin + out_outer};
+          filled_quad(q, fill);
+          return;
+        }
+      }
+    }
+    const V2 q[4] = {origin + point, origin + in_outer, origin + out_outer, origin + out_outer};
+    filled_quad(q, fill);
+  }
+  // De Casteljau, figrender.nim:1134-1147
+  V2 bezier_point(const float* ctrl, uint32_t n, float t) const {
+    if (n == 0) return V2{0.0f, 0.0f};
+    V2 work[64];
+    std::vector<V2> big;
+    V2* w = work;
+    if (n > 64) { big.resize(n); w = big.data(); }
+    for (uint32_t i = 0; i < n; i++) w[i] = V2{ctrl[2 * i], ctrl[2 * i + 1]};
+    for (uint32_t count = n; count > 1; count--)
+      for (uint32_t i = 0; i + 1 < count; i++) w[i] = w[i] * (1.0f - t) + w[i + 1] * t;
+    return w[0];
+  }
+  static V2 quadratic_point_v(V2 p0, V2 p1, V2 p2, float t) {
+    const float inv = 1.0f - t;
+    return p0 * (inv * inv) + p1 * (2.0f * inv * t) + p2 * (t * t);
+  }
+  static int explicit_steps(uint32_t steps, int32_t node_steps) {  // figrender.nim:1195-1201
+    if (steps != 0) return std::max(1, (int)steps);
+    if (node_steps != 0) return std::max(1, (int)node_steps);
+    return 0;
+  }
+  Span bezier_span(const float* ctrl, uint32_t n, float t0, float t2) const {  // figrender.nim:1230-1239
+    const float tm = (t0 + t2) * 0.5f;
+    const V2 p0 = bezier_point(ctrl, n, t0), pm = bezier_point(ctrl, n, tm), p2 = bezier_point(ctrl, n, t2);
+    return Span{p0, pm * 2.0f - (p0 + p2) * 0.5f, p2};
+  }
+  float approx_error_px(const float* ctrl, uint32_t n, const Span& s, float t0, float t2) const {  // :1248-1256
+    float result = 0.0f;
+    const float locals[2] = {0.25f, 0.75f};
+    for (float local_t : locals) {
+      const float t = t0 + (t2 - t0) * local_t;
+      const V2 actual = bezier_point(ctrl, n, t);
+      const V2 approx = quadratic_point_v(s.p0, s.p1, s.p2, local_t);
+      result = std::max(result, vlen((actual - approx) * ui));
+    }
+    return result;
+  }
+  void adaptive_spans(const float* ctrl, uint32_t n, float t0, float t2, int depth, std::vector<Span>& spans) const {  // :1258-1272
+    const Span s = bezier_span(ctrl, n, t0, t2);
+    const float error = approx_error_px(ctrl, n, s, t0, t2);
+    if (error <= kAdaptiveTolerancePx || depth >= kMaxAdaptiveDepth || (int)spans.size() >= kMaxAdaptiveSteps - 1) {
+      spans.push_back(s);
+    } else {
+      const float tm = (t0 + t2) * 0.5f;
+      adaptive_spans(ctrl, n, t0, tm, depth + 1, spans);
+      adaptive_spans(ctrl, n, tm, t2, depth + 1, spans);
+    }
+  }
+  // shared body of renderDrawableBezierQuadratics (:1414-1457) and renderDrawableArcQuadratics (:1551-1593)
+  void quadratic_spans(float ox, float oy, const std::vector<Span>& spans, const fdc_node_stroke& stroke) {
+    const int cap = stroke.cap == 0 ? 1 : stroke.cap, join = stroke.join == 0 ? 1 : stroke.join;
+    const bool simple_round = cap == 1 && join == 1;
+    const int span_cap = simple_round ? 1 : 2;
+    const float cap_radius = std::max(0.0f, stroke.weight) / 2.0f;
+    for (size_t step = 0; step < spans.size(); step++) {
+      const Span& s = spans[step];
+      quadratic_bezier(ox, oy, s.p0, s.p1, s.p2, stroke, span_cap);
+      if (!simple_round) {
+        if (step == 0) endpoint_cap(ox, oy, s.p0, s.start_tangent(), cap_radius, stroke, cap, true);
+        else stroke_join(ox, oy, s.p0, spans[step - 1].end_tangent(), s.start_tangent(), cap_radius, stroke.fill, join);
+        if (step + 1 == spans.size()) endpoint_cap(ox, oy, s.p2, s.end_tangent(), cap_radius, stroke, cap, false);
+      }
+    }
+  }
+  static float distance_to_line(V2 p, V2 a, V2 b) {  // figrender.nim:1219-1225
+    const V2 ab = b - a;
+    const float denom = ab.x * ab.x + ab.y * ab.y;
+    if (denom <= 0.000001f) return vlen(p - a);
+    const V2 pa = p - a;
+    const float h = clampf((pa.x * ab.x + pa.y * ab.y) / denom, 0.0f, 1.0f);
+    return vlen(p - (a + ab * h));
+  }
+  void adaptive_segment_points(const float* ctrl, uint32_t n, float t0, float t2, int depth, std::vector<V2>& pts) const {  // :1283-1297
+    const V2 p0 = bezier_point(ctrl, n, t0), p2 = bezier_point(ctrl, n, t2);
+    const float tm = (t0 + t2) * 0.5f;
+    const V2 pm = bezier_point(ctrl, n, tm);
+    const float error = distance_to_line(pm * ui, p0 * ui, p2 * ui);
+    if (error <= kAdaptiveTolerancePx || depth >= kMaxAdaptiveDepth || (int)pts.size() >= kMaxAdaptiveSteps) {
+      pts.push_back(p2);
+    } else {
+      adaptive_segment_points(ctrl, n, t0, tm, depth + 1, pts);
+      adaptive_segment_points(ctrl, n, tm, t2, depth + 1, pts);
+    }
+  }
+  // figrender.nim:1368-1412: polyline with endpoint caps and joins (what a 2-control Bezier takes)
+  void bezier_segments(float ox, float oy, const float* ctrl, uint32_t n, const fdc_node_stroke& stroke, int fixed_steps) {
+    std::vector<V2> pts;
+    pts.push_back(bezier_point(ctrl, n, 0.0f));
+    if (fixed_steps > 0) {
+      for (int step = 1; step <= fixed_steps; step++) pts.push_back(bezier_point(ctrl, n, (float)step / (float)fixed_steps));
+    } else {
+      adaptive_segment_points(ctrl, n, 0.0f, 1.0f, 0, pts);
+    }
+    if (pts.size() < 2) return;
+    const int cap = stroke.cap == 0 ? 1 : stroke.cap, join = stroke.join == 0 ? 1 : stroke.join;
+    const float cap_radius = std::max(0.0f, stroke.weight) / 2.0f;
+    fdc_node_stroke seg = stroke;
+    seg.cap = 2;  // scButt
+    V2 previous = pts[0], previous_tangent{1.0f, 0.0f};
+    for (size_t step = 1; step < pts.size(); step++) {
+      const V2 current = pts[step], tangent = current - previous;
+      line_v(ox, oy, previous, current, seg);
+      if (step == 1) endpoint_cap(ox, oy, previous, tangent, cap_radius, stroke, cap, true);
+      else stroke_join(ox, oy, previous, previous_tangent, tangent, cap_radius, stroke.fill, join);
+      if (step + 1 == pts.size()) endpoint_cap(ox, oy, current, tangent, cap_radius, stroke, cap, false);
+      previous = current;
+      previous_tangent = tangent;
+    }
+  }
+  // figrender.nim:1459-1486 (SDF build)
+  void bezier(float ox, float oy, const fdc_draw_op& op, const fdc_node_stroke& stroke, int32_t node_steps) {
+    const uint32_t n = op.n_points;
+    if (n < 2) return;
+    if (stroke.weight <= 0.0f || fill_alpha_max(stroke.fill) == 0) return;
+    const float* ctrl = points + 2 * (size_t)op.first_point;
+    if (n == 3) {
+      quadratic_bezier(ox, oy, V2{ctrl[0], ctrl[1]}, V2{ctrl[2], ctrl[3]}, V2{ctrl[4], ctrl[5]}, stroke, stroke.cap == 0 ? 1 : stroke.cap);
+    } else if (n > 3) {
+      const int fixed = explicit_steps(op.steps, node_steps);
+      std::vector<Span> spans;
+      if (fixed > 0) {
+        for (int step = 0; step < fixed; step++) spans.push_back(bezier_span(ctrl, n, (float)step / (float)fixed, (float)(step + 1) / (float)fixed));
+      } else {
+        adaptive_spans(ctrl, n, 0.0f, 1.0f, 0, spans);
+      }
+      quadratic_spans(ox, oy, spans, stroke);
+    } else {
+      bezier_segments(ox, oy, ctrl, n, stroke, explicit_steps(op.steps, node_steps));
+    }
+  }
+  int adaptive_arc_steps(float radius, float sweep) const {  // figrender.nim:1307-1318
+    const float radius_px = std::max(0.0f, radius * ui);
+    const float abs_sweep = fabsf(sweep);
+    if (radius_px <= 0.0f || abs_sweep <= 0.0f) return 1;
+    const float cos_limit = clampf(1.0f - kAdaptiveTolerancePx / radius_px, -1.0f, 1.0f);
+    const float max_angle = std::max(0.01f, 2.0f * (float)acos((double)cos_limit));
+    const int n = (int)ceil((double)(abs_sweep / max_angle));
+    return std::min(std::max(n, 1), kMaxAdaptiveSteps);
+  }
+  // figrender.nim:1595-1611 -> :1551-1593, arcQuadraticSpan :1535-1549
+  void arc(float ox, float oy, const fdc_draw_op& op, const fdc_node_stroke& stroke, int32_t node_steps) {
+    const float radius = std::max(0.0f, op.radius);
+    if (radius <= 0.0f || op.sweep_angle == 0.0f) return;
+    if (stroke.weight <= 0.0f || fill_alpha_max(stroke.fill) == 0) return;
+    int steps = explicit_steps(op.steps, node_steps);
+    if (steps == 0) steps = adaptive_arc_steps(op.radius, op.sweep_angle);
+    const V2 center{op.center[0], op.center[1]};
+    auto arc_point = [&](float angle) { return V2{center.x + cos32(angle) * radius, center.y + sin32(angle) * radius}; };
+    std::vector<Span> spans;
+    for (int step = 0; step < steps; step++) {
+      const float t0 = (float)step / (float)steps, t2 = (float)(step + 1) / (float)steps;
+      const float tm = (t0 + t2) * 0.5f;
+      const V2 p0 = arc_point(op.start_angle + op.sweep_angle * t0);
+      const V2 pm = arc_point(op.start_angle + op.sweep_angle * tm);
+      const V2 p2 = arc_point(op.start_angle + op.sweep_angle * t2);
+      spans.push_back(Span{p0, pm * 2.0f - (p0 + p2) * 0.5f, p2});
+    }
+    quadratic_spans(ox, oy, spans, stroke);
   }
   void drawable_ops(const fdc_fig& n) {
     const float ox = n.screen_box[0], oy = n.screen_box[1];
@@ -392,13 +641,9 @@ struct Flattener {
           rounded_shape(box, n.fill, stroke, cx4, cy4);
           break;
         }
-        case 3: {
-          if (op.n_controls != 3) { error = "only 3-control Beziers are restated (figrender.nim:1507-1517)"; break; }
-          if (stroke.weight <= 0.0f || fill_alpha_max(stroke.fill) == 0) break;
-          quadratic_bezier(ox, oy, op.controls, op.controls + 2, op.controls + 4, stroke);
-          break;
-        }
-        default: error = "drawable op upstream of the hot path, not restated"; break;
+        case 3: bezier(ox, oy, op, stroke, n.u.drawable.steps); break;
+        case 4: arc(ox, oy, op, stroke, n.u.drawable.steps); break;
+        default: error = "unknown drawable op kind"; break;
       }
     }
   }
@@ -547,8 +792,9 @@ struct RootRef {
 
 // Flattens roots [r0, r1) of `roots` into out[0..cap); returns the record count needed.
 size_t flatten_roots(const fdc_render_list* lists, const std::vector<RootRef>& roots, size_t r0, size_t r1, const fdc_glyph* glyphs,
-                     const fdc_draw_op* ops, const fdc_flatten_env& env, fdc_call* out, size_t cap, const char** error) {
-  Flattener F(out, cap, glyphs, ops, env);
+                     const fdc_draw_op* ops, const float* points, const fdc_flatten_env& env, fdc_call* out, size_t cap,
+                     const char** error) {
+  Flattener F(out, cap, glyphs, ops, points, env);
   for (size_t r = r0; r < r1 && !F.error; r++) F.render(lists[roots[r].list], roots[r].root, 0);
   if (F.error) *error = F.error;
   return F.n;
@@ -560,7 +806,7 @@ size_t flatten_roots(const fdc_render_list* lists, const std::vector<RootRef>& r
 // one root to the next), so a large scene is flattened by several threads: one counting pass per chunk of roots gives
 // every chunk its output offset, the second pass writes the records in place.
 const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs, const fdc_draw_op* ops,
-                            const fdc_flatten_env& env, fdc_call* out, size_t cap, size_t* n_out) {
+                            const float* points, const fdc_flatten_env& env, fdc_call* out, size_t cap, size_t* n_out) {
   *n_out = 0;
   if (!(env.ui_scale > 0.0f)) return "ui_scale must be positive";
   std::vector<RootRef> roots;
@@ -573,7 +819,7 @@ const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, cons
   const char* error = nullptr;
   size_t n = 0;
   {  // renderFrame prologue: saveTransform, scale(pixelScale)
-    Flattener F(out, cap, glyphs, ops, env);
+    Flattener F(out, cap, glyphs, ops, points, env);
     F.save();
     F.scale(env.pixel_scale, env.pixel_scale);
     n = F.n;
@@ -584,7 +830,7 @@ const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, cons
   if (const char* e = getenv("FDC_FLATTEN_THREADS")) n_threads = (unsigned)std::max(1, atoi(e));
   if (total_nodes < 8192 || roots.size() < 4 * n_threads) n_threads = 1;
   if (n_threads == 1) {
-    n += flatten_roots(lists, roots, 0, roots.size(), glyphs, ops, env, n < cap ? out + n : nullptr, n < cap ? cap - n : 0, &error);
+    n += flatten_roots(lists, roots, 0, roots.size(), glyphs, ops, points, env, n < cap ? out + n : nullptr, n < cap ? cap - n : 0, &error);
   } else {
     std::vector<size_t> count(n_threads, 0), r0(n_threads + 1, 0);
     std::vector<const char*> errs(n_threads, nullptr);
@@ -596,7 +842,7 @@ const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, cons
           fdc_call* dst = nullptr;
           size_t room = 0;
           if (write && offset[t] < cap) { dst = out + offset[t]; room = std::min(count[t], cap - offset[t]); }
-          const size_t c = flatten_roots(lists, roots, r0[t], r0[t + 1], glyphs, ops, env, dst, room, &errs[t]);
+          const size_t c = flatten_roots(lists, roots, r0[t], r0[t + 1], glyphs, ops, points, env, dst, room, &errs[t]);
           if (!write) count[t] = c;
         });
       for (auto& x : th) x.join();
@@ -611,7 +857,7 @@ const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, cons
     if (!error && n + 1 <= cap) run(true, offset);
   }
   {  // epilogue: restoreTransform
-    Flattener F(n < cap ? out + n : nullptr, n < cap ? cap - n : 0, glyphs, ops, env);
+    Flattener F(n < cap ? out + n : nullptr, n < cap ? cap - n : 0, glyphs, ops, points, env);
     F.restore();
     n += F.n;
   }
@@ -622,12 +868,12 @@ const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, cons
 }  // namespace fdc
 
 static_assert(sizeof(fdc_node_fill) == 16 && sizeof(fdc_node_shadow) == 36 && sizeof(fdc_node_stroke) == 24, "scene POD layout");
-static_assert(sizeof(fdc_fig) == 248 && sizeof(fdc_glyph) == 32 && sizeof(fdc_draw_op) == 100, "scene POD layout");
+static_assert(sizeof(fdc_fig) == 248 && sizeof(fdc_glyph) == 32 && sizeof(fdc_draw_op) == 92, "scene POD layout");
 
 extern "C" int fdc_flatten_renders(const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs, const fdc_draw_op* ops,
-                                   const fdc_flatten_env* env, fdc_call* out, size_t cap, size_t* n_out) {
+                                   const float* points, const fdc_flatten_env* env, fdc_call* out, size_t cap, size_t* n_out) {
   if ((!lists && n_lists) || !env || !n_out || (!out && cap)) return FDC_ERR_INVALID;
-  const char* err = fdc::flatten_renders(lists, n_lists, glyphs, ops, *env, out, cap, n_out);
+  const char* err = fdc::flatten_renders(lists, n_lists, glyphs, ops, points, *env, out, cap, n_out);
   if (err) return FDC_ERR_INVALID;
   return *n_out > cap ? FDC_ERR_CAPACITY : FDC_OK;
 }

@@ -211,16 +211,20 @@ class TransformStyle:
 
 @dataclass
 class DrawableOp:
+    """fignodes.nim:21-42 (variant object flattened)."""
+
     kind: DrawableKind
     a: Tuple[float, float] = (0.0, 0.0)
     b: Tuple[float, float] = (0.0, 0.0)
-    center: Tuple[float, float] = (0.0, 0.0)
-    radius: float = 0.0
+    center: Tuple[float, float] = (0.0, 0.0)  # circle / ellipse centre, arcCenter
+    radius: float = 0.0                        # circle radius, arcRadius
     box: Optional[Rect] = None
     corners: Sequence[int] = (0, 0, 0, 0)
     ellipseRadii: Tuple[float, float] = (0.0, 0.0)
     controls: Sequence[Tuple[float, float]] = ()
-    steps: int = 0
+    steps: int = 0                             # dkBezier steps / dkArc arcSteps (uint16, 0 = adaptive)
+    startAngle: float = 0.0
+    sweepAngle: float = 0.0
 
 
 def drawableLine(a, b) -> DrawableOp:
@@ -239,8 +243,16 @@ def drawableEllipse(center, radii) -> DrawableOp:
     return DrawableOp(kind=DrawableKind.dkEllipse, center=tuple(center), ellipseRadii=tuple(radii))
 
 
-def drawableBezier(p0, p1, p2) -> DrawableOp:
-    return DrawableOp(kind=DrawableKind.dkBezier, controls=(tuple(p0), tuple(p1), tuple(p2)))
+def drawableBezier(*args, steps: int = 0) -> DrawableOp:
+    """`drawableBezier(controls, steps)` / `drawableBezier(p0, p1, p2, steps)` (fignodes.nim:258-270)."""
+    controls = args[0] if len(args) == 1 else args
+    return DrawableOp(kind=DrawableKind.dkBezier, controls=tuple(tuple(p) for p in controls), steps=int(steps))
+
+
+def drawableArc(center, radius, startAngle, sweepAngle, steps: int = 0) -> DrawableOp:
+    """fignodes.nim:278-307."""
+    return DrawableOp(kind=DrawableKind.dkArc, center=tuple(center), radius=radius, startAngle=startAngle,
+                      sweepAngle=sweepAngle, steps=int(steps))
 
 
 @dataclass

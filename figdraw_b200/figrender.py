@@ -24,7 +24,7 @@ import numpy as np
 from .abi import SdfMode
 from .figbackend import BackendContext, BackendFill, ZeroRadii, colors4, solid, toBackendFill
 from .fignodes import (DrawableKind, DrawableOp, Fig, FigFlags, FigKind, Fill, FillGradientAxis, FillKind, Rect,
-                       RenderList, Renders, RenderStroke, ShadowStyle, StrokeCap, f32, rgba, rgba_tuple)
+                       RenderList, Renders, RenderStroke, ShadowStyle, StrokeCap, StrokeJoin, f32, rgba, rgba_tuple)
 
 _uiScale = f32(1.0)
 
@@ -297,6 +297,311 @@ def renderDrawableQuadraticBezierSdf(ctx, origin, p0, p1, p2, stroke: RenderStro
                                p2=loc(c), strokeWeight=float(scaled(weight)), cap=int(cap))
 
 
+# ----------------------------------------------------------------------------- curves (figrender.nim:908-1130, :1134-1611)
+# Transcendentals (cos, sin, arccos, arctan2) are evaluated in double and rounded to float32 -- the reference calls the
+# float32 libm entry points, which may differ in the last ulp; the native flattener does exactly what is done here.
+DrawableAdaptiveTolerancePx = f32(0.5)
+MaxAdaptiveDrawableSteps = max(48 * 4, 64)   # DefaultDrawableBezierSteps = 48 (fignodes.nim:100)
+MaxAdaptiveCurveDepth = 8
+
+
+def _v(p):
+    return (f32(p[0]), f32(p[1]))
+
+
+def _add(a, b):
+    return (a[0] + b[0], a[1] + b[1])
+
+
+def _sub(a, b):
+    return (a[0] - b[0], a[1] - b[1])
+
+
+def _mul(a, k):
+    return (a[0] * k, a[1] * k)
+
+
+def _normalizedOr(v, fallback):
+    ln = _vlen(v[0], v[1])
+    if ln <= 0.000001:
+        return fallback
+    return (v[0] / ln, v[1] / ln)
+
+
+def _normalLeft(d):
+    return (-d[1], d[0])
+
+
+def _cross2(a, b):
+    return a[0] * b[1] - a[1] * b[0]
+
+
+def _withCap(stroke: RenderStroke, cap) -> RenderStroke:
+    return RenderStroke(weight=stroke.weight, fill=stroke.fill, cap=cap, join=stroke.join)
+
+
+def resolveCurveCap(stroke: RenderStroke):
+    return StrokeCap.scRound if stroke.cap == StrokeCap.scAuto else stroke.cap
+
+
+def resolveCurveJoin(stroke: RenderStroke):
+    return StrokeJoin.sjRound if stroke.join == StrokeJoin.sjAuto else stroke.join
+
+
+def renderDrawableEndpointCap(ctx, origin, point, tangent, radius, stroke: RenderStroke, cap, isStart: bool) -> None:
+    """figrender.nim:1010-1039."""
+    if radius <= 0.0 or fillAlphaMax(stroke.fill) == 0:
+        return
+    if cap == StrokeCap.scRound:
+        renderDrawableStrokeCap(ctx, _add(origin, point), radius, stroke.fill)
+    elif cap == StrokeCap.scSquare:
+        d = _normalizedOr(tangent, (f32(1), f32(0)))
+        a = _sub(point, _mul(d, radius)) if isStart else point
+        b = point if isStart else _add(point, _mul(d, radius))
+        renderDrawableLine(ctx, origin, DrawableOp(kind=DrawableKind.dkLine, a=a, b=b), _withCap(stroke, StrokeCap.scButt))
+
+
+def _lineIntersection(p, r, q, s):
+    denom = _cross2(r, s)
+    if abs(denom) <= 0.000001:
+        return None
+    t = _cross2(_sub(q, p), s) / denom
+    return _add(p, _mul(r, t))
+
+
+def renderDrawableFilledQuad(ctx, verts, fill: Fill) -> None:
+    """figrender.nim:1049-1057."""
+    if fillAlphaMax(fill) == 0:
+        return
+    color = fillCenterColor(fill)
+    ctx.drawFilledQuad([tuple(float(c * _uiScale) for c in v) for v in verts], [color] * 4)
+
+
+def renderDrawableStrokeJoin(ctx, origin, point, incomingTangent, outgoingTangent, radius, fill: Fill, join) -> None:
+    """figrender.nim:1059-1109."""
+    if radius <= 0.0 or fillAlphaMax(fill) == 0:
+        return
+    if join == StrokeJoin.sjRound:
+        renderDrawableStrokeCap(ctx, _add(origin, point), radius, fill)
+    elif join in (StrokeJoin.sjBevel, StrokeJoin.sjMiter):
+        incoming = _normalizedOr(incomingTangent, (f32(1), f32(0)))
+        outgoing = _normalizedOr(outgoingTangent, incoming)
+        turn = _cross2(incoming, outgoing)
+        if abs(turn) <= 0.0001:
+            return
+        side = f32(-1.0) if turn > 0.0 else f32(1.0)
+        incomingOuter = _add(point, _mul(_normalLeft(incoming), radius * side))
+        outgoingOuter = _add(point, _mul(_normalLeft(outgoing), radius * side))
+        if join == StrokeJoin.sjMiter:
+            mp = _lineIntersection(incomingOuter, incoming, outgoingOuter, outgoing)
+            if mp is not None:
+                dm = _sub(mp, point)
+                if _vlen(dm[0], dm[1]) <= radius * f32(4.0):
+                    renderDrawableFilledQuad(ctx, [_add(origin, point), _add(origin, incomingOuter), _add(origin, mp),
+                                                   _add(origin, outgoingOuter)], fill)
+                    return
+        renderDrawableFilledQuad(ctx, [_add(origin, point), _add(origin, incomingOuter), _add(origin, outgoingOuter),
+                                       _add(origin, outgoingOuter)], fill)
+
+
+def bezierPoint(controls, t):
+    """De Casteljau, figrender.nim:1134-1147."""
+    if not controls:
+        return (f32(0), f32(0))
+    t = f32(t)
+    work = [_v(p) for p in controls]
+    count = len(work)
+    while count > 1:
+        for i in range(count - 1):
+            work[i] = _add(_mul(work[i], f32(1) - t), _mul(work[i + 1], t))
+        count -= 1
+    return work[0]
+
+
+def explicitDrawableStepCount(steps: int, nodeSteps: int) -> int:
+    if steps != 0:
+        return max(1, int(steps))
+    if nodeSteps != 0:
+        return max(1, int(nodeSteps))
+    return 0
+
+
+def _spanStartTangent(span):
+    p0, p1, p2 = span
+    return _normalizedOr(_sub(p1, p0), _normalizedOr(_sub(p2, p0), (f32(1), f32(0))))
+
+
+def _spanEndTangent(span):
+    p0, p1, p2 = span
+    return _normalizedOr(_sub(p2, p1), _normalizedOr(_sub(p2, p0), (f32(1), f32(0))))
+
+
+def _pointDistancePx(a, b):
+    d = _mul(_sub(a, b), _uiScale)
+    return _vlen(d[0], d[1])
+
+
+def _distanceToLine(p, a, b):
+    ab = _sub(b, a)
+    denom = ab[0] * ab[0] + ab[1] * ab[1]
+    if denom <= 0.000001:
+        d = _sub(p, a)
+        return _vlen(d[0], d[1])
+    pa = _sub(p, a)
+    h = min(max((pa[0] * ab[0] + pa[1] * ab[1]) / denom, f32(0)), f32(1))
+    d = _sub(p, _add(a, _mul(ab, h)))
+    return _vlen(d[0], d[1])
+
+
+def bezierQuadraticSpan(controls, t0, t2):
+    t0, t2 = f32(t0), f32(t2)
+    tm = (t0 + t2) * f32(0.5)
+    p0, pm, p2 = bezierPoint(controls, t0), bezierPoint(controls, tm), bezierPoint(controls, t2)
+    p1 = _sub(_mul(pm, f32(2)), _mul(_add(p0, p2), f32(0.5)))
+    return (p0, p1, p2)
+
+
+def _quadraticApproxErrorPx(controls, span, t0, t2):
+    result = f32(0)
+    for localT in (f32(0.25), f32(0.75)):
+        t = t0 + (t2 - t0) * localT
+        actual = bezierPoint(controls, t)
+        approx = _quadraticPoint(span[0], span[1], span[2], localT)
+        result = max(result, _pointDistancePx(actual, approx))
+    return result
+
+
+def _appendAdaptiveBezierSpan(controls, t0, t2, depth, spans):
+    span = bezierQuadraticSpan(controls, t0, t2)
+    error = _quadraticApproxErrorPx(controls, span, f32(t0), f32(t2))
+    if error <= DrawableAdaptiveTolerancePx or depth >= MaxAdaptiveCurveDepth or len(spans) >= MaxAdaptiveDrawableSteps - 1:
+        spans.append(span)
+    else:
+        tm = (f32(t0) + f32(t2)) * f32(0.5)
+        _appendAdaptiveBezierSpan(controls, t0, tm, depth + 1, spans)
+        _appendAdaptiveBezierSpan(controls, tm, t2, depth + 1, spans)
+
+
+def _bezierSpans(controls, fixedSteps):
+    if fixedSteps > 0:
+        return [bezierQuadraticSpan(controls, f32(step) / f32(fixedSteps), f32(step + 1) / f32(fixedSteps))
+                for step in range(fixedSteps)]
+    spans = []
+    _appendAdaptiveBezierSpan(controls, f32(0), f32(1), 0, spans)
+    return spans
+
+
+def _renderQuadraticSpans(ctx, origin, spans, stroke: RenderStroke) -> None:
+    """Shared body of renderDrawableBezierQuadratics (:1414-1457) and renderDrawableArcQuadratics (:1551-1593)."""
+    cap, join = resolveCurveCap(stroke), resolveCurveJoin(stroke)
+    simpleRoundSpans = cap == StrokeCap.scRound and join == StrokeJoin.sjRound
+    spanCap = StrokeCap.scRound if simpleRoundSpans else StrokeCap.scButt
+    capRadius = max(f32(0), f32(stroke.weight)) / f32(2)
+    previous = None
+    for step, span in enumerate(spans):
+        renderDrawableQuadraticBezierSdf(ctx, origin, span[0], span[1], span[2], stroke, spanCap)
+        if not simpleRoundSpans:
+            if step == 0:
+                renderDrawableEndpointCap(ctx, origin, span[0], _spanStartTangent(span), capRadius, stroke, cap, True)
+            else:
+                renderDrawableStrokeJoin(ctx, origin, span[0], _spanEndTangent(previous), _spanStartTangent(span), capRadius,
+                                         stroke.fill, join)
+            if step == len(spans) - 1:
+                renderDrawableEndpointCap(ctx, origin, span[2], _spanEndTangent(span), capRadius, stroke, cap, False)
+        previous = span
+
+
+def _appendAdaptiveBezierSegmentPoint(controls, t0, t2, depth, points):
+    p0, p2 = bezierPoint(controls, t0), bezierPoint(controls, t2)
+    tm = (f32(t0) + f32(t2)) * f32(0.5)
+    pm = bezierPoint(controls, tm)
+    error = _distanceToLine(_mul(pm, _uiScale), _mul(p0, _uiScale), _mul(p2, _uiScale))
+    if error <= DrawableAdaptiveTolerancePx or depth >= MaxAdaptiveCurveDepth or len(points) >= MaxAdaptiveDrawableSteps:
+        points.append(p2)
+    else:
+        _appendAdaptiveBezierSegmentPoint(controls, t0, tm, depth + 1, points)
+        _appendAdaptiveBezierSegmentPoint(controls, tm, t2, depth + 1, points)
+
+
+def renderDrawableBezierSegments(ctx, origin, op: DrawableOp, stroke: RenderStroke, nodeSteps: int) -> None:
+    """figrender.nim:1368-1412: polyline with endpoint caps and joins (what a 2-control Bezier takes)."""
+    fixedSteps = explicitDrawableStepCount(op.steps, nodeSteps)
+    points = [bezierPoint(op.controls, f32(0))]
+    if fixedSteps > 0:
+        for step in range(1, fixedSteps + 1):
+            points.append(bezierPoint(op.controls, f32(step) / f32(fixedSteps)))
+    else:
+        _appendAdaptiveBezierSegmentPoint(op.controls, f32(0), f32(1), 0, points)
+    if len(points) < 2:
+        return
+    cap, join = resolveCurveCap(stroke), resolveCurveJoin(stroke)
+    capRadius = max(f32(0), f32(stroke.weight)) / f32(2)
+    segmentStroke = _withCap(stroke, StrokeCap.scButt)
+    previous, previousTangent = points[0], (f32(1), f32(0))
+    for step in range(1, len(points)):
+        current = points[step]
+        tangent = _sub(current, previous)
+        renderDrawableLine(ctx, origin, DrawableOp(kind=DrawableKind.dkLine, a=previous, b=current), segmentStroke)
+        if step == 1:
+            renderDrawableEndpointCap(ctx, origin, previous, tangent, capRadius, stroke, cap, True)
+        else:
+            renderDrawableStrokeJoin(ctx, origin, previous, previousTangent, tangent, capRadius, stroke.fill, join)
+        if step == len(points) - 1:
+            renderDrawableEndpointCap(ctx, origin, current, tangent, capRadius, stroke, cap, False)
+        previous, previousTangent = current, tangent
+
+
+def renderDrawableBezier(ctx, origin, op: DrawableOp, stroke: RenderStroke, nodeSteps: int) -> None:
+    """figrender.nim:1459-1486 (SDF build: 3 controls -> one quadratic SDF, more -> quadratic spans, 2 -> segments)."""
+    if len(op.controls) < 2:
+        return
+    if stroke.weight <= 0.0 or fillAlphaMax(stroke.fill) == 0:
+        return
+    if len(op.controls) == 3:
+        renderDrawableQuadraticBezierSdf(ctx, origin, op.controls[0], op.controls[1], op.controls[2], stroke,
+                                         resolveCurveCap(stroke))
+    elif len(op.controls) > 3:
+        _renderQuadraticSpans(ctx, origin, _bezierSpans(op.controls, explicitDrawableStepCount(op.steps, nodeSteps)), stroke)
+    else:
+        renderDrawableBezierSegments(ctx, origin, op, stroke, nodeSteps)
+
+
+def _arcPoint(center, radius, angle):
+    a = float(angle)
+    return (f32(center[0]) + f32(math.cos(a)) * radius, f32(center[1]) + f32(math.sin(a)) * radius)
+
+
+def adaptiveArcStepCount(radius, sweepAngle) -> int:
+    """figrender.nim:1307-1318."""
+    radiusPx = max(f32(0), f32(radius) * _uiScale)
+    absSweep = abs(f32(sweepAngle))
+    if radiusPx <= 0.0 or absSweep <= 0.0:
+        return 1
+    cosLimit = min(max(f32(1) - DrawableAdaptiveTolerancePx / radiusPx, f32(-1)), f32(1))
+    maxAngle = max(f32(0.01), f32(2) * f32(math.acos(float(cosLimit))))
+    return min(max(int(math.ceil(float(absSweep / maxAngle))), 1), MaxAdaptiveDrawableSteps)
+
+
+def renderDrawableArc(ctx, origin, op: DrawableOp, stroke: RenderStroke, nodeSteps: int) -> None:
+    """figrender.nim:1595-1611 -> renderDrawableArcQuadratics :1551-1593, arcQuadraticSpan :1535-1549."""
+    radius = max(f32(0), f32(op.radius))
+    if radius <= 0.0 or f32(op.sweepAngle) == 0.0:
+        return
+    if stroke.weight <= 0.0 or fillAlphaMax(stroke.fill) == 0:
+        return
+    steps = explicitDrawableStepCount(op.steps, nodeSteps) or adaptiveArcStepCount(op.radius, op.sweepAngle)
+    start, sweep = f32(op.startAngle), f32(op.sweepAngle)
+    spans = []
+    for step in range(steps):
+        t0, t2 = f32(step) / f32(steps), f32(step + 1) / f32(steps)
+        tm = (t0 + t2) * f32(0.5)
+        p0 = _arcPoint(op.center, radius, start + sweep * t0)
+        pm = _arcPoint(op.center, radius, start + sweep * tm)
+        p2 = _arcPoint(op.center, radius, start + sweep * t2)
+        spans.append((p0, _sub(_mul(pm, f32(2)), _mul(_add(p0, p2), f32(0.5))), p2))
+    _renderQuadraticSpans(ctx, origin, spans, stroke)
+
+
 def renderDrawableOps(ctx, node: Fig) -> None:
     origin = (node.screenBox.x, node.screenBox.y)
     fill, stroke = node.fill, node.drawStroke
@@ -321,13 +626,11 @@ def renderDrawableOps(ctx, node: Fig) -> None:
             box = Rect(origin[0] + f32(op.center[0]) - rx, origin[1] + f32(op.center[1]) - ry, rx * f32(2), ry * f32(2))
             renderRoundedShape(ctx, box, fill, stroke, (rx,) * 4, (ry,) * 4)
         elif op.kind == DrawableKind.dkBezier:
-            if len(op.controls) != 3:
-                raise NotImplementedError("only 3-control Beziers are restated (figrender.nim:1507-1517)")
-            if stroke.weight <= 0.0 or fillAlphaMax(stroke.fill) == 0:
-                continue
-            renderDrawableQuadraticBezierSdf(ctx, origin, op.controls[0], op.controls[1], op.controls[2], stroke)
+            renderDrawableBezier(ctx, origin, op, stroke, node.drawSteps)
+        elif op.kind == DrawableKind.dkArc:
+            renderDrawableArc(ctx, origin, op, stroke, node.drawSteps)
         else:
-            raise NotImplementedError(f"drawable op {op.kind!r}: upstream of the hot path, not restated")
+            raise NotImplementedError(f"drawable op {op.kind!r}")
 
 
 def renderDrawable(ctx, node: Fig) -> None:

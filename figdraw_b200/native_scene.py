@@ -51,6 +51,11 @@ class PackedScene:
     glyphs: np.ndarray
     ops: np.ndarray
     lists: ctypes.Array
+    points: Optional[np.ndarray] = None  # Bezier control points (x, y pairs) the ops index
+
+    def __post_init__(self):
+        if self.points is None:
+            self.points = np.zeros(2, dtype=np.float32)
 
     @property
     def n_nodes(self) -> int:
@@ -120,6 +125,7 @@ def pack_renders(renders: Renders) -> PackedScene:
         garr[i]["pos"] = tuple(g.pos)
         _put_fill(garr[i]["fill"], g.fill)
     oarr = np.zeros(max(len(op_rows), 1), dtype=abi.DRAW_OP_DTYPE)
+    pts: List[float] = []
     for i, op in enumerate(op_rows):
         o = oarr[i]
         o["kind"] = int(op.kind)
@@ -128,17 +134,19 @@ def pack_renders(renders: Renders) -> PackedScene:
             o["box"] = op.box.tuple()
         o["corners"] = tuple(op.corners)
         o["ellipse_radii"] = tuple(op.ellipseRadii)
-        o["n_controls"] = len(op.controls)
-        if len(op.controls) <= 3:
-            flat = [c for p in op.controls for c in p]
-            o["controls"][: len(flat)] = flat
+        o["start_angle"], o["sweep_angle"] = op.startAngle, op.sweepAngle
+        o["first_point"], o["n_points"] = len(pts) // 2, len(op.controls)
+        o["steps"] = int(op.steps)
+        for p in op.controls:
+            pts.extend((float(p[0]), float(p[1])))
+    parr = np.asarray(pts if pts else [0.0, 0.0], dtype=np.float32)
     lists = (abi.FdcRenderList * max(len(node_arrays), 1))()
     for i, (na, ra) in enumerate(zip(node_arrays, root_arrays)):
         lists[i].nodes = na.ctypes.data
         lists[i].n_nodes = len(na)
         lists[i].root_ids = ra.ctypes.data
         lists[i].n_roots = len(ra)
-    return PackedScene(node_arrays, root_arrays, garr, oarr, lists)
+    return PackedScene(node_arrays, root_arrays, garr, oarr, lists, parr)
 
 
 def flatten(scene: PackedScene, ui_scale: float = 1.0, pixel_scale: float = 1.0, aa_factor: float = 1.2,
@@ -149,11 +157,11 @@ def flatten(scene: PackedScene, ui_scale: float = 1.0, pixel_scale: float = 1.0,
     env = abi.FdcFlattenEnv(ui_scale, pixel_scale, aa_factor, 1 if subpixel_enabled else 0,
                             keys.ctypes.data if len(keys) else None, len(keys))
     n = ctypes.c_size_t(0)
-    cap = 64 + 8 * scene.n_nodes
+    cap = 64 + 8 * scene.n_nodes + 16 * len(scene.ops)
     for _ in range(2):
         out = np.zeros(cap, dtype=abi.CALL_DTYPE)
         rc = lib.fdc_flatten_renders(scene.lists, len(scene.nodes), scene.glyphs.ctypes.data, scene.ops.ctypes.data,
-                                     ctypes.byref(env), out.ctypes.data, cap, ctypes.byref(n))
+                                     scene.points.ctypes.data, ctypes.byref(env), out.ctypes.data, cap, ctypes.byref(n))
         if rc == 0:
             return out[: n.value].copy()
         if rc != 4:  # FDC_ERR_CAPACITY
@@ -167,4 +175,4 @@ def render_frame(ctx, scene: PackedScene, frame_size: Sequence[float], ui_scale:
     """`fdc_render_frame` on a CudaContext: renderFrame with the DFS done natively."""
     rgba = (ctypes.c_float * 4)(*clear_color)
     ctx._ck(ctx._lib.fdc_render_frame(ctx._h, scene.lists, len(scene.nodes), scene.glyphs.ctypes.data, scene.ops.ctypes.data,
-                                      float(ui_scale), float(frame_size[0]), float(frame_size[1]), 1 if clear_main else 0, rgba))
+                                      scene.points.ctypes.data, float(ui_scale), float(frame_size[0]), float(frame_size[1]), 1 if clear_main else 0, rgba))

@@ -283,10 +283,11 @@ int fdc_debug_shade_stats(fdc_ctx* ctx, uint64_t out[8]);
  *   renderFrame figrender.nim:1960-2002, renderRoot :1946-1958, render :1756-1839 (stage order),
  *   renderDropShadows :654-689, renderInnerShadows :716-744, renderRoundedShapeScaledCorners :806-873,
  *   renderText :417-497 (glyph loop), renderImage/renderMsdfImage/renderMtsdfImage/renderBackdropBlur :1673-1754,
- *   renderDrawable :1653-1667 (line :946-995, circle :1122-1136, rect :1138-1142, ellipse :1617-1635,
- *   3-control Bezier :1330-1370), gradientColors :623-647, toBackendFill figbackend.nim:109-127.
- * The node records are PODs mirroring `Fig` (fignodes.nim:53-92); `seq` members (glyphs, drawable ops) live in
- * side arrays the nodes index.  Layers are rendered in array order (the reference does not sort, figrender.nim:1951).
+ *   renderDrawable :1653-1667 (line :946-995, circle :1111-1126, rect :1128-1132, ellipse :1613-1630, Beziers of any
+ *   order :1327-1486 incl. adaptive quadratic spans, arcs :1535-1611, endpoint caps :1010-1039, bevel/miter/round
+ *   joins :1059-1109), gradientColors :623-647, toBackendFill figbackend.nim:109-127.
+ * The node records are PODs mirroring `Fig` (fignodes.nim:53-92); `seq` members (glyphs, drawable ops, Bezier control
+ * points) live in side arrays the nodes index.  Layers are rendered in array order (the reference does not sort, figrender.nim:1951).
  */
 typedef struct fdc_node_fill { /* Fill, common/filltypes.nim:34-42 */
   uint8_t kind;                /* 0 flColor, 1 flLinear2, 2 flLinear3 */
@@ -348,17 +349,18 @@ typedef struct fdc_glyph {     /* what renderText consumes per glyph (figrender.
   fdc_node_fill fill;
 } fdc_glyph;                   /* 32 bytes */
 
-typedef struct fdc_draw_op {   /* DrawableOp, figbasics.nim (drawables) */
+typedef struct fdc_draw_op {   /* DrawableOp, fignodes.nim:21-42 */
   uint32_t kind;               /* 0 line, 1 circle, 2 rectangle, 3 bezier, 4 arc, 5 ellipse */
   float a[2], b[2];            /* line */
-  float center[2];             /* circle, ellipse */
-  float radius;                /* circle */
+  float center[2];             /* circle, ellipse, arc */
+  float radius;                /* circle, arc */
   float box[4];                /* rectangle */
   float corners[4];            /* rectangle */
   float ellipse_radii[2];
-  float controls[6];           /* bezier: p0, p1, p2 */
-  uint32_t n_controls;
-} fdc_draw_op;                 /* 100 bytes */
+  float start_angle, sweep_angle; /* arc, radians */
+  uint32_t first_point, n_points; /* bezier: control points in the `points` side array (x, y pairs), any count >= 2 */
+  uint32_t steps;              /* bezier `steps` / arc `arcSteps`; 0 = adaptive (or the node's drawSteps) */
+} fdc_draw_op;                 /* 92 bytes */
 
 typedef struct fdc_render_list { /* RenderList, fignodes.nim:44-46 */
   const fdc_fig* nodes;
@@ -380,12 +382,12 @@ typedef struct fdc_flatten_env {
  * records -- saveTransform, scale(pixelScale), every layer's roots in order, restoreTransform.  Writes at most `cap`
  * records; *n_out is the number needed (FDC_ERR_CAPACITY when cap was too small). */
 int fdc_flatten_renders(const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs, const fdc_draw_op* ops,
-                        const fdc_flatten_env* env, fdc_call* out, size_t cap, size_t* n_out);
+                        const float* points, const fdc_flatten_env* env, fdc_call* out, size_t cap, size_t* n_out);
 
 /* renderFrame on a context: beginFrame(frame size * uiScale), the flattened scene, endFrame. */
 int fdc_render_frame(fdc_ctx* ctx, const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs,
-                     const fdc_draw_op* ops, float ui_scale, float frame_w, float frame_h, int clear_main,
-                     const float clear_rgba[4]);
+                     const fdc_draw_op* ops, const float* points, float ui_scale, float frame_w, float frame_h,
+                     int clear_main, const float clear_rgba[4]);
 
 #ifdef __cplusplus
 }

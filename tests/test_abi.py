@@ -80,7 +80,7 @@ int main(void) {
   O(fdc_fig, corners); O(fdc_fig, corner_radii_y); O(fdc_fig, u);
   O(fdc_fig, u.rect.stroke); O(fdc_fig, u.drawable.steps); O(fdc_fig, u.drawable.first_op); O(fdc_fig, u.msdf.px_range);
   O(fdc_fig, u.transform.matrix); O(fdc_fig, u.transform.use_matrix);
-  O(fdc_draw_op, center); O(fdc_draw_op, box); O(fdc_draw_op, controls); O(fdc_draw_op, n_controls);
+  O(fdc_draw_op, center); O(fdc_draw_op, box); O(fdc_draw_op, start_angle); O(fdc_draw_op, first_point); O(fdc_draw_op, steps);
   O(fdc_render_list, root_ids); O(fdc_flatten_env, image_keys);
   return 0;
 }
@@ -112,7 +112,7 @@ int main(void) {
     assert c["fdc_fig.u.transform.matrix"] == pay + abi.FIG_TRANSFORM_DTYPE.fields["matrix"][1]
     assert c["fdc_fig.u.transform.use_matrix"] == pay + abi.FIG_TRANSFORM_DTYPE.fields["use_matrix"][1]
     d = abi.DRAW_OP_DTYPE.fields
-    for name in ("center", "box", "controls", "n_controls"):
+    for name in ("center", "box", "start_angle", "first_point", "steps"):
         assert c[f"fdc_draw_op.{name}"] == d[name][1], name
     assert c["fdc_render_list.root_ids"] == abi.FdcRenderList.root_ids.offset
     assert c["fdc_flatten_env.image_keys"] == abi.FdcFlattenEnv.image_keys.offset

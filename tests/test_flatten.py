@@ -8,7 +8,7 @@ import pytest
 from figdraw_b200 import figrender, native_scene, scenes, scenes_synth as ss
 from figdraw_b200.figbackend import TraceBackend
 from figdraw_b200.fignodes import (BackdropBlurStyle, Fig, FigFlags, FigKind, FillGradientAxis, Glyph, ImageStyle, MsdfImageStyle,
-                                   Renders, RenderShadow, RenderStroke, ShadowStyle, StrokeCap, TransformStyle, drawableBezier,
+                                   Renders, RenderShadow, RenderStroke, ShadowStyle, StrokeCap, StrokeJoin, TransformStyle, drawableArc, drawableBezier,
                                    drawableCircle, drawableEllipse, drawableLine, drawableRect, figCircle, figLine, fill, linear,
                                    rect, rgba)
 from figdraw_b200.scenes_synth import Rng
@@ -117,10 +117,11 @@ def random_renders(seed: int) -> Renders:
                          for _ in range(ri(5))]
             n.stroke = RenderStroke(weight=u(-1, 6), fill=rfill())
         elif kind == FigKind.nkDrawable:
-            n.drawStroke = RenderStroke(weight=u(-1, 8), fill=rfill(), cap=StrokeCap(ri(4)))
+            n.drawStroke = RenderStroke(weight=u(-1, 8), fill=rfill(), cap=StrokeCap(ri(4)), join=StrokeJoin(ri(4)))
             n.drawAa = (0.0, 0.0, 1.2, 0.8, 2.0)[ri(5)]
+            n.drawSteps = (0, 0, 3, 6)[ri(4)]
             for _ in range(ri(5)):
-                k = ri(6)
+                k = ri(10)
                 if k == 0:
                     n.drawOps.append(drawableLine((u(0, 100), u(0, 100)), (u(0, 100), u(0, 100))))
                 elif k == 1:
@@ -131,9 +132,16 @@ def random_renders(seed: int) -> Renders:
                     n.drawOps.append(drawableEllipse((u(0, 100), u(0, 100)), (u(-2, 40), u(-2, 30))))
                 elif k == 4:
                     n.drawOps.append(drawableBezier((u(0, 100), u(0, 100)), (u(0, 100), u(0, 100)), (u(0, 100), u(0, 100))))
-                else:  # collinear controls: the line fallback of the Bezier path
+                elif k == 5:  # collinear controls: the line fallback of the Bezier path
                     a, d = (u(0, 50), u(0, 50)), (u(1, 20), u(1, 20))
                     n.drawOps.append(drawableBezier(a, (a[0] + d[0], a[1] + d[1]), (a[0] + 2 * d[0], a[1] + 2 * d[1])))
+                elif k in (6, 7):  # higher-order (and 2-control) Beziers: adaptive or fixed spans, caps and joins
+                    nc = (2, 4, 5, 7)[ri(4)]
+                    sc = (1.0, 4.0, 12.0)[ri(3)]
+                    n.drawOps.append(drawableBezier([(u(0, 60) * sc, u(-30, 60) * sc) for _ in range(nc)], steps=(0, 0, 2, 5)[ri(4)]))
+                else:
+                    n.drawOps.append(drawableArc((u(0, 100), u(0, 100)), u(-2, 120), u(-7, 7), (0.0, u(-7, 7), u(-2, 2))[ri(3)],
+                                                 steps=(0, 0, 1, 4)[ri(4)]))
         elif kind == FigKind.nkText:
             n.glyphs = [Glyph(key=1000 + ri(40), pos=(u(0, 300), u(0, 100)), fill=rfill()) for _ in range(ri(12))]
         elif kind == FigKind.nkImage:
@@ -176,24 +184,41 @@ def test_random_trees_flatten_identically(seed):
     assert_same(native_records(r, keys, ui_scale=ui), per_call_records(r, 640, 480, keys, ui_scale=ui))
 
 
-def test_unsupported_drawables_are_refused_like_the_front_end():
-    from figdraw_b200.fignodes import DrawableKind, DrawableOp
-
+def test_unknown_drawable_kind_is_refused():
     r = Renders()
     n = Fig(kind=FigKind.nkDrawable, screenBox=rect(0, 0, 10, 10), fill=fill(rgba(0, 0, 0, 255)))
     n.drawStroke = RenderStroke(weight=2.0, fill=fill(rgba(0, 0, 0, 255)))
-    n.drawOps.append(DrawableOp(kind=DrawableKind.dkArc))
+    n.drawOps.append(drawableLine((0, 0), (5, 5)))
     r.addRoot(0, n)
+    packed = native_scene.pack_renders(r)
+    packed.ops[0]["kind"] = 17
     with pytest.raises(ValueError):
-        native_records(r)
-    with pytest.raises(NotImplementedError):
-        per_call_records(r, 64, 64)
+        native_scene.flatten(packed)
 
 
-def test_cfg5_scene_flattens_to_the_benchmark_call_stream():
-    """The node-level cfg5 scene (100k nkRectangle + nkText per layer at full size) flattens to exactly the call stream
-    the benchmark replays; also exercises the multi-threaded path (more than 8192 nodes)."""
-    tr = ss.rects_and_glyphs(1920, 1080, n_rects=12000, n_glyphs=3000)
-    scene = ss.rects_and_glyphs_scene(1920, 1080, n_rects=12000, n_glyphs=3000)
-    calls = native_scene.flatten(scene, image_keys=ss.glyph_image_keys())
-    assert_same(calls, tr.calls)
+def test_curve_drawables_flatten_identically():
+    """Every curve case the reference's own tests pin (tests/ttransform.nim:269-525), natively and per call."""
+    red = fill(rgba(255, 0, 0, 255))
+    cases = [
+        ([drawableBezier([(0, 0), (10, 20), (20, 0)], steps=4)], RenderStroke(weight=2.0, fill=red), 0),
+        ([drawableLine((0, 0), (10, 0))], RenderStroke(weight=2.0, fill=red, cap=StrokeCap.scRound), 0),
+        ([drawableLine((0, 0), (10, 0))], RenderStroke(weight=2.0, fill=red, cap=StrokeCap.scSquare), 0),
+        ([drawableBezier([(0, 0), (10, 20), (20, -10), (30, 0)], steps=4)], RenderStroke(weight=2.0, fill=red), 0),
+        ([drawableBezier([(0, 0), (40, 200), (80, -200), (120, 0)])], RenderStroke(weight=2.0, fill=red), 0),
+        ([drawableArc((10, 10), 8.0, 0.0, 1.5707964, steps=4)], RenderStroke(weight=2.0, fill=red), 0),
+        ([drawableArc((90, 90), 80.0, 0.0, 3.1415927)], RenderStroke(weight=2.0, fill=red), 0),
+        ([drawableArc((10, 10), 8.0, 0.0, 1.5707964, steps=4)],
+         RenderStroke(weight=2.0, fill=red, cap=StrokeCap.scButt, join=StrokeJoin.sjBevel), 0),
+        ([drawableArc((10, 10), 8.0, 0.3, -2.5)], RenderStroke(weight=3.0, fill=red, cap=StrokeCap.scSquare, join=StrokeJoin.sjMiter), 0),
+        ([drawableBezier([(0, 0), (10, 20), (20, 0)]), drawableArc((20, 10), 8.0, 0.0, 1.5707964, steps=2)],
+         RenderStroke(weight=2.0, fill=red), 4),
+        ([drawableBezier([(0, 0), (30, 5)])], RenderStroke(weight=2.0, fill=red, cap=StrokeCap.scSquare), 0),
+    ]
+    for ui in (1.0, 2.0):
+        for ops_, stroke, node_steps in cases:
+            n = Fig(kind=FigKind.nkDrawable, screenBox=rect(5.0, 7.0, 30.0, 20.0), drawSteps=node_steps)
+            n.drawStroke = stroke
+            n.drawOps = list(ops_)
+            r = Renders()
+            r.addRoot(0, n)
+            assert_same(native_records(r, ui_scale=ui), per_call_records(r, 200, 200, ui_scale=ui))

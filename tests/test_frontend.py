@@ -109,3 +109,64 @@ def test_figidx_capacity():
     with pytest.raises(OverflowError):
         for _ in range(40000):
             lst.addChild(root, Fig(kind=FigKind.nkFrame))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Curve drawables: the reference's own call-count pins (tests/ttransform.nim:269-525), restated one to one.
+def _drawable_draws(ops_, stroke=None, node_steps=0, box=(5.0, 7.0, 30.0, 20.0)):
+    from figdraw_b200.fignodes import fill as solid_fill
+
+    node = Fig(kind=FigKind.nkDrawable, screenBox=rect(*box), drawSteps=node_steps)
+    node.drawStroke = stroke or RenderStroke(weight=2.0, fill=solid_fill(rgba(255, 0, 0, 255)))
+    node.drawOps = list(ops_)
+    r = Renders()
+    r.addRoot(0, node)
+    tb = TraceBackend()
+    renderRoot(tb, r)
+    calls = tb._buf[: tb._n]
+    return calls[calls["op"] >= 32]
+
+
+def test_curve_drawables_match_the_reference_call_counts():
+    from figdraw_b200.fignodes import StrokeCap, StrokeJoin, drawableArc, drawableBezier, drawableLine
+    from figdraw_b200.fignodes import fill as solid_fill
+
+    red = solid_fill(rgba(255, 0, 0, 255))
+    # :269 quadratic bezier = one sdf op, whatever `steps` says
+    assert len(_drawable_draws([drawableBezier([(0, 0), (10, 20), (20, 0)], steps=4)])) == 1
+    # :297 round capped line = segment + 2 caps; :316 square capped line = one extended segment
+    assert len(_drawable_draws([drawableLine((0, 0), (10, 0))], RenderStroke(weight=2.0, fill=red, cap=StrokeCap.scRound))) == 3
+    assert len(_drawable_draws([drawableLine((0, 0), (10, 0))], RenderStroke(weight=2.0, fill=red, cap=StrokeCap.scSquare))) == 1
+    # :335 higher order bezier -> quadratic sdf spans
+    d = _drawable_draws([drawableBezier([(0, 0), (10, 20), (20, -10), (30, 0)], steps=4)])
+    assert len(d) == 4 and all(int(o) == Op.BEZIER for o in d["op"])
+    # :364 adaptive decomposition grows with screen size
+    small = _drawable_draws([drawableBezier([(0, 0), (4, 20), (8, -20), (12, 0)])])
+    large = _drawable_draws([drawableBezier([(0, 0), (40, 200), (80, -200), (120, 0)])])
+    assert 0 < len(small) < len(large)
+    # :388 arc -> quadratic spans; :411 adaptive arcs
+    assert len(_drawable_draws([drawableArc((10, 10), 8.0, 0.0, 1.5707964, steps=4)])) == 4
+    small = _drawable_draws([drawableArc((16, 16), 8.0, 0.0, 3.1415927)])
+    large = _drawable_draws([drawableArc((90, 90), 80.0, 0.0, 3.1415927)])
+    assert 0 < len(small) < len(large)
+    # :454 explicit bevel joins: 4 spans + 3 joins (filled quads), butt caps draw nothing
+    d = _drawable_draws([drawableArc((10, 10), 8.0, 0.0, 1.5707964, steps=4)],
+                        RenderStroke(weight=2.0, fill=red, cap=StrokeCap.scButt, join=StrokeJoin.sjBevel))
+    assert len(d) == 7 and sum(int(o) == Op.FILLED_QUAD for o in d["op"]) == 3
+    # :479 node steps are the default for curve ops
+    d = _drawable_draws([drawableBezier([(0, 0), (10, 20), (20, 0)]), drawableArc((20, 10), 8.0, 0.0, 1.5707964, steps=2)],
+                        node_steps=4, box=(5.0, 7.0, 40.0, 30.0))
+    assert len(d) == 3
+
+
+def test_quadratic_sdf_padding_stays_in_physical_pixels():
+    """tests/ttransform.nim:510-524: uiScale 2 -> rect 48 x 18."""
+    from figdraw_b200.fignodes import drawableBezier
+
+    setFigUiScale(2.0)
+    try:
+        d = _drawable_draws([drawableBezier((0, 0), (10, 10), (20, 0))])
+        assert len(d) == 1
+        assert abs(float(d[0]["f"][2]) - 48.0) < 1e-4 and abs(float(d[0]["f"][3]) - 18.0) < 1e-4
+    finally:
+        setFigUiScale(1.0)

@@ -211,8 +211,7 @@ def native_frontend_probe(name: str, calls_np):
     ts = []
     for _ in range(7):
         t0 = time.perf_counter()
-        rc = lib.fdc_flatten_renders(scene.lists, len(scene.nodes), scene.glyphs.ctypes.data, scene.ops.ctypes.data,
-                                     scene.points.ctypes.data, ctypes.byref(env), out.ctypes.data, len(out), ctypes.byref(n))
+        rc = lib.fdc_flatten_renders(ctypes.byref(scene.scene), ctypes.byref(env), out.ctypes.data, len(out), ctypes.byref(n))
         ts.append(time.perf_counter() - t0)
     same = rc == 0 and n.value == len(calls_np) and out[: n.value].tobytes() == calls_np.tobytes()
     return {"nodes": scene.n_nodes, "records": int(n.value), "flatten_ms": round(float(np.median(ts[1:])) * 1e3, 3),

@@ -284,25 +284,32 @@ type
   FdcFig* {.importc: "fdc_fig", header: "figdraw_cuda.h", incompleteStruct.} = object
   FdcGlyph* {.importc: "fdc_glyph", header: "figdraw_cuda.h", incompleteStruct.} = object
   FdcDrawOp* {.importc: "fdc_draw_op", header: "figdraw_cuda.h", incompleteStruct.} = object
+  FdcTextRect* {.importc: "fdc_text_rect", header: "figdraw_cuda.h", incompleteStruct.} = object
   FdcRenderList* {.importc: "fdc_render_list", header: "figdraw_cuda.h", bycopy.} = object
     nodes*: ptr FdcFig
     n_nodes*: uint32
     root_ids*: ptr int32
     n_roots*: uint32
+  FdcScene* {.importc: "fdc_scene", header: "figdraw_cuda.h", bycopy.} = object
+    lists*: ptr FdcRenderList
+    n_lists*: uint32
+    glyphs*: ptr FdcGlyph
+    text_rects*: ptr FdcTextRect
+    ops*: ptr FdcDrawOp
+    points*: ptr cfloat
 
 proc fdc_submit_calls(ctx: FdcCtx, calls: ptr FdcCall, n: csize_t): cint {.importc, header: "figdraw_cuda.h".}
 proc fdc_submit_draws(ctx: FdcCtx, draws: ptr FdcCall, n: csize_t): cint {.importc, header: "figdraw_cuda.h".}
-proc fdc_render_frame(ctx: FdcCtx, lists: ptr FdcRenderList, nLists: uint32, glyphs: ptr FdcGlyph, ops: ptr FdcDrawOp,
-                      points: ptr cfloat, uiScale, frameW, frameH: cfloat, clearMain: cint, clearRgba: ptr cfloat): cint {.importc, header: "figdraw_cuda.h".}
+proc fdc_render_frame(ctx: FdcCtx, scene: ptr FdcScene, uiScale, frameW, frameH: cfloat, clearMain: cint,
+                      clearRgba: ptr cfloat): cint {.importc, header: "figdraw_cuda.h".}
 
 proc submitCalls*(ctx: CudaContext, calls: openArray[FdcCall]) =
   ## A recorded display list (one record per backend call) replayed as if the methods above had been called.
   if calls.len > 0: ctx.ck fdc_submit_calls(ctx.h, calls[0].unsafeAddr, calls.len.csize_t)
 
-proc renderFrameNative*(ctx: CudaContext, lists: openArray[FdcRenderList], glyphs: ptr FdcGlyph, ops: ptr FdcDrawOp,
-                        points: ptr cfloat, frameSize: Vec2, clearMain: bool, clearColor: Color) =
-  ## renderFrame (figrender.nim:1960-2002) with the node DFS done inside the library: `lists` point at POD copies of
+proc renderFrameNative*(ctx: CudaContext, scene: var FdcScene, frameSize: Vec2, clearMain: bool, clearColor: Color) =
+  ## renderFrame (figrender.nim:1960-2002) with the node DFS done inside the library: `scene.lists` point at POD copies of
   ## `Renders.layers[*].nodes` (fdc_fig), in table order.
   var rgba = [clearColor.r.cfloat, clearColor.g.cfloat, clearColor.b.cfloat, clearColor.a.cfloat]
-  ctx.ck fdc_render_frame(ctx.h, lists[0].unsafeAddr, lists.len.uint32, glyphs, ops, points, figUiScale().cfloat,
-                          frameSize.x.cfloat, frameSize.y.cfloat, clearMain.cint, rgba[0].addr)
+  ctx.ck fdc_render_frame(ctx.h, scene.addr, figUiScale().cfloat, frameSize.x.cfloat, frameSize.y.cfloat, clearMain.cint,
+                          rgba[0].addr)

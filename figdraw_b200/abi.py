@@ -107,7 +107,9 @@ FIG_DTYPE = np.dtype({
 })
 # kind-specific views of `payload` (the C union)
 FIG_RECT_DTYPE = np.dtype([("shadows", NODE_SHADOW_DTYPE, (4,)), ("stroke", NODE_STROKE_DTYPE)])
-FIG_TEXT_DTYPE = np.dtype([("first_glyph", "<u4"), ("n_glyphs", "<u4")])
+FIG_TEXT_DTYPE = np.dtype([("first_glyph", "<u4"), ("n_glyphs", "<u4"), ("first_rect", "<u4"), ("n_selection", "<u4"),
+                           ("n_decoration", "<u4")])
+TEXT_RECT_DTYPE = np.dtype([("rect", "<f4", (4,)), ("fill", NODE_FILL_DTYPE)])
 FIG_DRAWABLE_DTYPE = np.dtype([("stroke", NODE_STROKE_DTYPE), ("steps", "<i4"), ("aa", "<f4"), ("first_op", "<u4"),
                                ("n_ops", "<u4")])
 FIG_IMAGE_DTYPE = np.dtype([("id", "<u8"), ("fill", NODE_FILL_DTYPE)])
@@ -121,12 +123,18 @@ DRAW_OP_DTYPE = np.dtype([("kind", "<u4"), ("a", "<f4", (2,)), ("b", "<f4", (2,)
                           ("start_angle", "<f4"), ("sweep_angle", "<f4"), ("first_point", "<u4"), ("n_points", "<u4"),
                           ("steps", "<u4")])
 assert NODE_FILL_DTYPE.itemsize == 16 and NODE_SHADOW_DTYPE.itemsize == 36 and NODE_STROKE_DTYPE.itemsize == 24
+assert TEXT_RECT_DTYPE.itemsize == 32
 assert FIG_RECT_DTYPE.itemsize == FIG_PAYLOAD_BYTES and GLYPH_DTYPE.itemsize == 32 and DRAW_OP_DTYPE.itemsize == 92
 
 
 class FdcRenderList(ctypes.Structure):
     _fields_ = [("nodes", ctypes.c_void_p), ("n_nodes", ctypes.c_uint32), ("root_ids", ctypes.c_void_p),
                 ("n_roots", ctypes.c_uint32)]
+
+
+class FdcScene(ctypes.Structure):
+    _fields_ = [("lists", ctypes.POINTER(FdcRenderList)), ("n_lists", ctypes.c_uint32), ("glyphs", ctypes.c_void_p),
+                ("text_rects", ctypes.c_void_p), ("ops", ctypes.c_void_p), ("points", ctypes.c_void_p)]
 
 
 class FdcFlattenEnv(ctypes.Structure):
@@ -256,10 +264,9 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_debug_shade_stats", c.c_int, P, c.POINTER(c.c_uint64))
     sig("fdc_read_pixels_async", c.c_int, P, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p)
     sig("fdc_set_peer_gather", c.c_int, P, c.c_int, c.c_int)
-    sig("fdc_flatten_renders", c.c_int, c.POINTER(FdcRenderList), c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,
-        c.POINTER(FdcFlattenEnv), c.c_void_p, c.c_size_t, c.POINTER(c.c_size_t))
-    sig("fdc_render_frame", c.c_int, P, c.POINTER(FdcRenderList), c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p, c.c_float,
-        c.c_float, c.c_float, c.c_int, c.POINTER(c.c_float))
+    sig("fdc_flatten_renders", c.c_int, c.POINTER(FdcScene), c.POINTER(FdcFlattenEnv), c.c_void_p, c.c_size_t,
+        c.POINTER(c.c_size_t))
+    sig("fdc_render_frame", c.c_int, P, c.POINTER(FdcScene), c.c_float, c.c_float, c.c_float, c.c_int, c.POINTER(c.c_float))
     sig("fdc_debug_bins", c.c_int, P, c.c_int, u32p, c.c_size_t, u32p, c.c_size_t, c.POINTER(c.c_size_t),
         c.POINTER(c.c_size_t))
     if lib.fdc_abi_version() != ABI_VERSION:

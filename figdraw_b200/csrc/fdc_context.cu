@@ -1644,10 +1644,9 @@ int fdc_debug_shade_stats(fdc_ctx* ctx, uint64_t out[8]) {
 }
 
 // renderFrame (figrender.nim:1960-2002) with the front-end DFS run natively: beginFrame, the flattened scene, endFrame.
-int fdc_render_frame(fdc_ctx* ctx, const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs,
-                     const fdc_draw_op* ops, const float* points, float ui_scale, float frame_w, float frame_h,
-                     int clear_main, const float clear_rgba[4]) {
-  if (!ctx || (!lists && n_lists)) return FDC_ERR_INVALID;
+int fdc_render_frame(fdc_ctx* ctx, const fdc_scene* scene, float ui_scale, float frame_w, float frame_h, int clear_main,
+                     const float clear_rgba[4]) {
+  if (!ctx || !scene || (!scene->lists && scene->n_lists)) return FDC_ERR_INVALID;
   if (!(ui_scale > 0.0f)) return ctx->fail(FDC_ERR_INVALID, "ui_scale must be positive");
   std::vector<uint64_t> keys;
   keys.reserve(ctx->entries.size());
@@ -1666,7 +1665,7 @@ int fdc_render_frame(fdc_ctx* ctx, const fdc_render_list* lists, uint32_t n_list
   if (buf.cap < 1024 && !buf.reserve(1024)) return ctx->fail(FDC_ERR_CUDA, "cudaMallocHost failed");
   size_t n_calls = 0;
   for (int pass = 0; pass < 2; pass++) {
-    const char* err = fdc::flatten_renders(lists, n_lists, glyphs, ops, points, env, buf.p, buf.cap, &n_calls);
+    const char* err = fdc::flatten_renders(*scene, env, buf.p, buf.cap, &n_calls);
     if (err) return ctx->fail(FDC_ERR_INVALID, "%s", err);
     if (n_calls <= buf.cap) break;
     buf.n = 0;  // nothing to keep

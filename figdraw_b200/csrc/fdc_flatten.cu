@@ -149,6 +149,7 @@ struct Flattener {
   size_t cap, n = 0;
   fdc_call spill;      // where a record past the capacity is "written"
   const fdc_glyph* glyphs;
+  const fdc_text_rect* text_rects;
   const fdc_draw_op* ops;
   const float* points;
   const fdc_flatten_env& env;
@@ -157,8 +158,9 @@ struct Flattener {
   bool subpixel;
   const char* error = nullptr;
 
-  Flattener(fdc_call* o, size_t c, const fdc_glyph* g, const fdc_draw_op* d, const float* pts, const fdc_flatten_env& e)
-      : out(o), cap(c), glyphs(g), ops(d), points(pts), env(e), ui(e.ui_scale), aa(e.aa_factor), subpixel(e.subpixel_enabled != 0) {}
+  Flattener(fdc_call* o, size_t c, const fdc_scene& sc, const fdc_flatten_env& e)
+      : out(o), cap(c), glyphs(sc.glyphs), text_rects(sc.text_rects), ops(sc.ops), points(sc.points), env(e), ui(e.ui_scale),
+        aa(e.aa_factor), subpixel(e.subpixel_enabled != 0) {}
 
   // ---- the backend calls, recorded
   fdc_call& rec(uint32_t op) {
@@ -659,7 +661,8 @@ struct Flattener {
     drawable_ops(n);
     set_aa(old);
   }
-  // figrender.nim:417-497, glyph loop
+  // figrender.nim:417-497: selection rects, underline/strikethrough, then one atlas quad per glyph.  The text layout
+  // (pixie arrangement) is upstream: its results arrive as fdc_text_rect / fdc_glyph records.
   void text(const fdc_fig& n) {
     save();
     translate(n.screen_box[0] * ui, n.screen_box[1] * ui);
@@ -667,13 +670,42 @@ struct Flattener {
       translate(0.0f, n.screen_box[3] * ui);
       scale(1.0f, -1.0f);
     }
+    const Radii zero = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};
+    const fdc_text_rect* tr = text_rects ? text_rects + n.u.text.first_rect : nullptr;
+    if ((n.flags & FDC_NF_SELECT_TEXT) && fill_alpha_max(n.fill) > 0) {
+      for (uint32_t i = 0; i < n.u.text.n_selection && tr; i++) {
+        const float* r = tr[i].rect;
+        if (!(r[3] > 0.0f)) continue;
+        const float sel[4] = {r[0], r[1], std::max(r[2], 1.0f), r[3]};
+        float sb[4];
+        scaled_box(sel, sb);
+        rounded_rect(sb, to_backend_fill(n.fill), zero, FDC_SDF_CLIP_AA, 4.0f, 0.0f, 0.0f, 0.0f);
+      }
+    }
+    for (uint32_t i = 0; i < n.u.text.n_decoration && tr; i++) {  // drawTextDecoration :355-368
+      const fdc_text_rect& d = tr[n.u.text.n_selection + i];
+      if (d.rect[2] <= 0.0f || d.rect[3] <= 0.0f) continue;
+      float sb[4];
+      scaled_box(d.rect, sb);
+      rounded_rect(sb, to_backend_fill(d.fill), zero, FDC_SDF_CLIP_AA, 4.0f, 0.0f, 0.0f, 0.0f);
+    }
     for (uint32_t i = 0; i < n.u.text.n_glyphs; i++) {
       const fdc_glyph& g = glyphs[n.u.text.first_glyph + i];
-      set_subpixel_shift(0.0f);
-      if (!has_image(g.key)) continue;
+      float gx = g.pos[0], shift = 0.0f;
+      if (subpixel) {  // :462-471 (per-glyph variants are a different atlas key: the host's choice)
+        const float snapped = floorf(gx);
+        shift = std::max(0.0f, std::min(gx - snapped, 0.999f));
+        gx = snapped;
+      }
+      set_subpixel_shift(shift);
+      if (!has_image(g.key)) {
+        set_subpixel_shift(0.0f);
+        continue;
+      }
       uint32_t cols[4];
       gradient_colors(g.fill, cols);
-      draw_image(g.key, g.pos[0], g.pos[1], cols, 0.0f, 0.0f, false);
+      draw_image(g.key, gx, g.pos[1], cols, 0.0f, 0.0f, false);
+      if (subpixel) set_subpixel_shift(0.0f);
     }
     set_subpixel_shift(0.0f);
     restore();
@@ -791,11 +823,10 @@ struct RootRef {
 };
 
 // Flattens roots [r0, r1) of `roots` into out[0..cap); returns the record count needed.
-size_t flatten_roots(const fdc_render_list* lists, const std::vector<RootRef>& roots, size_t r0, size_t r1, const fdc_glyph* glyphs,
-                     const fdc_draw_op* ops, const float* points, const fdc_flatten_env& env, fdc_call* out, size_t cap,
-                     const char** error) {
-  Flattener F(out, cap, glyphs, ops, points, env);
-  for (size_t r = r0; r < r1 && !F.error; r++) F.render(lists[roots[r].list], roots[r].root, 0);
+size_t flatten_roots(const fdc_scene& scene, const std::vector<RootRef>& roots, size_t r0, size_t r1, const fdc_flatten_env& env,
+                     fdc_call* out, size_t cap, const char** error) {
+  Flattener F(out, cap, scene, env);
+  for (size_t r = r0; r < r1 && !F.error; r++) F.render(scene.lists[roots[r].list], roots[r].root, 0);
   if (F.error) *error = F.error;
   return F.n;
 }
@@ -805,8 +836,9 @@ size_t flatten_roots(const fdc_render_list* lists, const std::vector<RootRef>& r
 // Roots are independent of each other (a drawable restores the AA factor it changes; nothing else carries state from
 // one root to the next), so a large scene is flattened by several threads: one counting pass per chunk of roots gives
 // every chunk its output offset, the second pass writes the records in place.
-const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs, const fdc_draw_op* ops,
-                            const float* points, const fdc_flatten_env& env, fdc_call* out, size_t cap, size_t* n_out) {
+const char* flatten_renders(const fdc_scene& scene, const fdc_flatten_env& env, fdc_call* out, size_t cap, size_t* n_out) {
+  const fdc_render_list* lists = scene.lists;
+  const uint32_t n_lists = scene.n_lists;
   *n_out = 0;
   if (!(env.ui_scale > 0.0f)) return "ui_scale must be positive";
   std::vector<RootRef> roots;
@@ -819,7 +851,7 @@ const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, cons
   const char* error = nullptr;
   size_t n = 0;
   {  // renderFrame prologue: saveTransform, scale(pixelScale)
-    Flattener F(out, cap, glyphs, ops, points, env);
+    Flattener F(out, cap, scene, env);
     F.save();
     F.scale(env.pixel_scale, env.pixel_scale);
     n = F.n;
@@ -830,7 +862,7 @@ const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, cons
   if (const char* e = getenv("FDC_FLATTEN_THREADS")) n_threads = (unsigned)std::max(1, atoi(e));
   if (total_nodes < 8192 || roots.size() < 4 * n_threads) n_threads = 1;
   if (n_threads == 1) {
-    n += flatten_roots(lists, roots, 0, roots.size(), glyphs, ops, points, env, n < cap ? out + n : nullptr, n < cap ? cap - n : 0, &error);
+    n += flatten_roots(scene, roots, 0, roots.size(), env, n < cap ? out + n : nullptr, n < cap ? cap - n : 0, &error);
   } else {
     std::vector<size_t> count(n_threads, 0), r0(n_threads + 1, 0);
     std::vector<const char*> errs(n_threads, nullptr);
@@ -842,7 +874,7 @@ const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, cons
           fdc_call* dst = nullptr;
           size_t room = 0;
           if (write && offset[t] < cap) { dst = out + offset[t]; room = std::min(count[t], cap - offset[t]); }
-          const size_t c = flatten_roots(lists, roots, r0[t], r0[t + 1], glyphs, ops, points, env, dst, room, &errs[t]);
+          const size_t c = flatten_roots(scene, roots, r0[t], r0[t + 1], env, dst, room, &errs[t]);
           if (!write) count[t] = c;
         });
       for (auto& x : th) x.join();
@@ -857,7 +889,7 @@ const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, cons
     if (!error && n + 1 <= cap) run(true, offset);
   }
   {  // epilogue: restoreTransform
-    Flattener F(n < cap ? out + n : nullptr, n < cap ? cap - n : 0, glyphs, ops, points, env);
+    Flattener F(n < cap ? out + n : nullptr, n < cap ? cap - n : 0, scene, env);
     F.restore();
     n += F.n;
   }
@@ -868,12 +900,11 @@ const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, cons
 }  // namespace fdc
 
 static_assert(sizeof(fdc_node_fill) == 16 && sizeof(fdc_node_shadow) == 36 && sizeof(fdc_node_stroke) == 24, "scene POD layout");
-static_assert(sizeof(fdc_fig) == 248 && sizeof(fdc_glyph) == 32 && sizeof(fdc_draw_op) == 92, "scene POD layout");
+static_assert(sizeof(fdc_fig) == 248 && sizeof(fdc_glyph) == 32 && sizeof(fdc_draw_op) == 92 && sizeof(fdc_text_rect) == 32, "scene POD layout");
 
-extern "C" int fdc_flatten_renders(const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs, const fdc_draw_op* ops,
-                                   const float* points, const fdc_flatten_env* env, fdc_call* out, size_t cap, size_t* n_out) {
-  if ((!lists && n_lists) || !env || !n_out || (!out && cap)) return FDC_ERR_INVALID;
-  const char* err = fdc::flatten_renders(lists, n_lists, glyphs, ops, points, *env, out, cap, n_out);
+extern "C" int fdc_flatten_renders(const fdc_scene* scene, const fdc_flatten_env* env, fdc_call* out, size_t cap, size_t* n_out) {
+  if (!scene || (!scene->lists && scene->n_lists) || !env || !n_out || (!out && cap)) return FDC_ERR_INVALID;
+  const char* err = fdc::flatten_renders(*scene, *env, out, cap, n_out);
   if (err) return FDC_ERR_INVALID;
   return *n_out > cap ? FDC_ERR_CAPACITY : FDC_OK;
 }

@@ -8,7 +8,6 @@ namespace fdc {
 
 // Writes the body of renderFrame (figrender.nim:1960-2002) into out[0..cap); *n_out = records needed (may exceed cap:
 // the excess was not stored).  Returns nullptr or a static error message.
-const char* flatten_renders(const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs, const fdc_draw_op* ops,
-                            const float* points, const fdc_flatten_env& env, fdc_call* out, size_t cap, size_t* n_out);
+const char* flatten_renders(const fdc_scene& scene, const fdc_flatten_env& env, fdc_call* out, size_t cap, size_t* n_out);
 
 }  // namespace fdc

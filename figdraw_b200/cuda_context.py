@@ -119,7 +119,11 @@ class CudaContext(BackendContext):
     def setSdfAaFactor(self, aaFactor: float):
         self._ck(self._lib.fdc_set_sdf_aa_factor(self._h, float(aaFactor)))
 
+    def textSubpixelPositioningEnabled(self) -> bool:
+        return bool(getattr(self, "_subpixel", False))
+
     def setTextSubpixelPositioningEnabled(self, enabled: bool):
+        self._subpixel = bool(enabled)
         self._ck(self._lib.fdc_set_text_subpixel_positioning_enabled(self._h, 1 if enabled else 0))
 
     def setTextSubpixelShift(self, shift: float):

@@ -285,8 +285,11 @@ class Fig:
     # nkRectangle
     shadows: Sequence[RenderShadow] = ()
     stroke: RenderStroke = field(default_factory=RenderStroke)
-    # nkText
+    # nkText: what the (upstream) text layout produced -- glyphs, selection rects for NfSelectText (selectionRectsFor),
+    # underline / strikethrough rects with their span colour (renderTextDecorations, figrender.nim:370-415)
     glyphs: Sequence[Glyph] = ()
+    selectionRects: Sequence[Rect] = ()
+    decorations: Sequence[Tuple[Rect, Fill]] = ()
     # nkDrawable
     drawStroke: RenderStroke = field(default_factory=RenderStroke)
     drawSteps: int = 0

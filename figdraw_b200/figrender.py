@@ -651,18 +651,39 @@ def renderDrawable(ctx, node: Fig) -> None:
 
 # ----------------------------------------------------------------------------- text / images / blur
 def renderText(ctx, node: Fig) -> None:
-    """figrender.nim:417-497, glyph loop: one atlas quad per glyph, 4 vertex colours from the span fill."""
+    """figrender.nim:417-497: selection rects, decorations, then one atlas quad per glyph with 4 vertex colours from the
+    span fill.  The layout itself (pixie arrangement) is upstream; per-glyph subpixel VARIANTS select a different atlas
+    key and are therefore the caller's choice of `Glyph.key`."""
+    subpixel = ctx.textSubpixelPositioningEnabled()
     ctx.saveTransform()
     ctx.translate((float(scaled(node.screenBox.x)), float(scaled(node.screenBox.y))))
     if node.flags & FigFlags.NfInvertY:
         ctx.translate((0.0, float(scaled(node.screenBox.h))))
         ctx.scale((1.0, -1.0))
-    for glyph in node.glyphs:
-        ctx.setTextSubpixelShift(0.0)
-        if not ctx.hasImage(glyph.key):
+    if (node.flags & FigFlags.NfSelectText) and fillAlphaMax(node.fill) > 0:
+        for sel in node.selectionRects:
+            if sel.h > 0:
+                r = Rect(sel.x, sel.y, max(sel.w, f32(1.0)), sel.h)
+                ctx.drawRoundedRectSdf(rect=scaled(r).tuple(), fill=toBackendFill(node.fill), radii=ZeroRadii,
+                                       mode=SdfMode.sdfModeClipAA, factor=4.0, spread=0.0, shapeSize=(0.0, 0.0))
+    for deco, color in node.decorations:  # drawTextDecoration :355-368
+        if deco.w <= 0 or deco.h <= 0:
             continue
-        ctx.drawImage(glyph.key, (float(glyph.pos[0]), float(glyph.pos[1])), gradientColors(glyph.fill), (0.0, 0.0),
-                      False)
+        ctx.drawRoundedRectSdf(rect=scaled(deco).tuple(), fill=toBackendFill(color), radii=ZeroRadii,
+                               mode=SdfMode.sdfModeClipAA, factor=4.0, spread=0.0, shapeSize=(0.0, 0.0))
+    for glyph in node.glyphs:
+        gx, shift = f32(glyph.pos[0]), f32(0.0)
+        if subpixel:
+            snapped = f32(math.floor(float(gx)))
+            shift = max(f32(0.0), min(gx - snapped, f32(0.999)))
+            gx = snapped
+        ctx.setTextSubpixelShift(float(shift))
+        if not ctx.hasImage(glyph.key):
+            ctx.setTextSubpixelShift(0.0)
+            continue
+        ctx.drawImage(glyph.key, (float(gx), float(glyph.pos[1])), gradientColors(glyph.fill), (0.0, 0.0), False)
+        if subpixel:
+            ctx.setTextSubpixelShift(0.0)
     ctx.setTextSubpixelShift(0.0)
     ctx.restoreTransform()
 

@@ -44,18 +44,24 @@ def _put_shadow(dst, sh: RenderShadow) -> None:
 
 @dataclass
 class PackedScene:
-    """POD arrays + the `fdc_render_list` table pointing into them (kept alive together)."""
+    """POD arrays + the `fdc_scene` pointing into them (kept alive together)."""
 
     nodes: List[np.ndarray]
     roots: List[np.ndarray]
     glyphs: np.ndarray
     ops: np.ndarray
     lists: ctypes.Array
-    points: Optional[np.ndarray] = None  # Bezier control points (x, y pairs) the ops index
+    points: Optional[np.ndarray] = None      # Bezier control points (x, y pairs) the ops index
+    text_rects: Optional[np.ndarray] = None  # selection / decoration rects the text nodes index
+    scene: Optional[abi.FdcScene] = None
 
     def __post_init__(self):
         if self.points is None:
             self.points = np.zeros(2, dtype=np.float32)
+        if self.text_rects is None:
+            self.text_rects = np.zeros(1, dtype=abi.TEXT_RECT_DTYPE)
+        self.scene = abi.FdcScene(self.lists, len(self.nodes), self.glyphs.ctypes.data, self.text_rects.ctypes.data,
+                                  self.ops.ctypes.data, self.points.ctypes.data)
 
     @property
     def n_nodes(self) -> int:
@@ -66,7 +72,7 @@ def pack_renders(renders: Renders) -> PackedScene:
     glyphs: List[tuple] = []
     ops: List[tuple] = []
     node_arrays, root_arrays = [], []
-    glyph_rows, op_rows = [], []
+    glyph_rows, op_rows, rect_rows = [], [], []
     for _lvl, lst in renders.pairs():
         arr = np.zeros(len(lst.nodes), dtype=abi.FIG_DTYPE)
         for i, n in enumerate(lst.nodes):
@@ -93,6 +99,9 @@ def pack_renders(renders: Renders) -> PackedScene:
                 v = pay[: abi.FIG_TEXT_DTYPE.itemsize].view(abi.FIG_TEXT_DTYPE)[0]
                 v["first_glyph"], v["n_glyphs"] = len(glyph_rows), len(n.glyphs)
                 glyph_rows.extend(n.glyphs)
+                v["first_rect"], v["n_selection"], v["n_decoration"] = len(rect_rows), len(n.selectionRects), len(n.decorations)
+                rect_rows.extend((r, None) for r in n.selectionRects)
+                rect_rows.extend(n.decorations)
             elif n.kind == FigKind.nkDrawable:
                 v = pay[: abi.FIG_DRAWABLE_DTYPE.itemsize].view(abi.FIG_DRAWABLE_DTYPE)[0]
                 _put_stroke(v["stroke"], n.drawStroke)
@@ -140,13 +149,18 @@ def pack_renders(renders: Renders) -> PackedScene:
         for p in op.controls:
             pts.extend((float(p[0]), float(p[1])))
     parr = np.asarray(pts if pts else [0.0, 0.0], dtype=np.float32)
+    rarr = np.zeros(max(len(rect_rows), 1), dtype=abi.TEXT_RECT_DTYPE)
+    for i, (r, color) in enumerate(rect_rows):
+        rarr[i]["rect"] = r.tuple()
+        if color is not None:
+            _put_fill(rarr[i]["fill"], color)
     lists = (abi.FdcRenderList * max(len(node_arrays), 1))()
     for i, (na, ra) in enumerate(zip(node_arrays, root_arrays)):
         lists[i].nodes = na.ctypes.data
         lists[i].n_nodes = len(na)
         lists[i].root_ids = ra.ctypes.data
         lists[i].n_roots = len(ra)
-    return PackedScene(node_arrays, root_arrays, garr, oarr, lists, parr)
+    return PackedScene(node_arrays, root_arrays, garr, oarr, lists, parr, rarr)
 
 
 def flatten(scene: PackedScene, ui_scale: float = 1.0, pixel_scale: float = 1.0, aa_factor: float = 1.2,
@@ -157,11 +171,10 @@ def flatten(scene: PackedScene, ui_scale: float = 1.0, pixel_scale: float = 1.0,
     env = abi.FdcFlattenEnv(ui_scale, pixel_scale, aa_factor, 1 if subpixel_enabled else 0,
                             keys.ctypes.data if len(keys) else None, len(keys))
     n = ctypes.c_size_t(0)
-    cap = 64 + 8 * scene.n_nodes + 16 * len(scene.ops)
+    cap = 64 + 8 * scene.n_nodes + 16 * len(scene.ops) + len(scene.text_rects)
     for _ in range(2):
         out = np.zeros(cap, dtype=abi.CALL_DTYPE)
-        rc = lib.fdc_flatten_renders(scene.lists, len(scene.nodes), scene.glyphs.ctypes.data, scene.ops.ctypes.data,
-                                     scene.points.ctypes.data, ctypes.byref(env), out.ctypes.data, cap, ctypes.byref(n))
+        rc = lib.fdc_flatten_renders(ctypes.byref(scene.scene), ctypes.byref(env), out.ctypes.data, cap, ctypes.byref(n))
         if rc == 0:
             return out[: n.value].copy()
         if rc != 4:  # FDC_ERR_CAPACITY
@@ -174,5 +187,4 @@ def render_frame(ctx, scene: PackedScene, frame_size: Sequence[float], ui_scale:
                  clear_color=(1.0, 1.0, 1.0, 1.0)) -> None:
     """`fdc_render_frame` on a CudaContext: renderFrame with the DFS done natively."""
     rgba = (ctypes.c_float * 4)(*clear_color)
-    ctx._ck(ctx._lib.fdc_render_frame(ctx._h, scene.lists, len(scene.nodes), scene.glyphs.ctypes.data, scene.ops.ctypes.data,
-                                      scene.points.ctypes.data, float(ui_scale), float(frame_size[0]), float(frame_size[1]), 1 if clear_main else 0, rgba))
+    ctx._ck(ctx._lib.fdc_render_frame(ctx._h, ctypes.byref(scene.scene), float(ui_scale), float(frame_size[0]), float(frame_size[1]), 1 if clear_main else 0, rgba))

@@ -334,7 +334,7 @@ typedef struct fdc_fig {
   float corner_radii_y[4];     /* used with FDC_NF_ELLIPTICAL_CORNERS */
   union {                      /* kind-specific payload (the reference's variant object) */
     struct { fdc_node_shadow shadows[4]; fdc_node_stroke stroke; } rect;                       /* nkRectangle */
-    struct { uint32_t first_glyph, n_glyphs; } text;                                           /* nkText -> fdc_glyph[] */
+    struct { uint32_t first_glyph, n_glyphs, first_rect, n_selection, n_decoration; } text;     /* nkText -> fdc_glyph[], fdc_text_rect[] */
     struct { fdc_node_stroke stroke; int32_t steps; float aa; uint32_t first_op, n_ops; } drawable; /* -> fdc_draw_op[] */
     struct { uint64_t id; fdc_node_fill fill; } image;                                         /* nkImage */
     struct { uint64_t id; fdc_node_fill fill; float px_range, sd_threshold, stroke_weight; } msdf; /* nkMsdfImage / nkMtsdfImage */
@@ -345,9 +345,17 @@ typedef struct fdc_fig {
 
 typedef struct fdc_glyph {     /* what renderText consumes per glyph (figrender.nim:456-493) */
   uint64_t key;                /* atlas key of the glyph bitmap */
-  float pos[2];                /* glyphLocalPos + imageOffset, already scaled */
+  float pos[2];                /* glyphLocalPos + imageOffset, already scaled (snapped to whole pixels by the flattener when
+                                * subpixel positioning is on, the fraction going to setTextSubpixelShift) */
   fdc_node_fill fill;
 } fdc_glyph;                   /* 32 bytes */
+
+typedef struct fdc_text_rect { /* what the text layout hands renderText besides glyphs (figrender.nim:355-415, :434-453):
+                                * first the node's selection rects (drawn with the node fill when NfSelectText is set), then
+                                * its underline / strikethrough rects with their span colour; local text-box coordinates */
+  float rect[4];
+  fdc_node_fill fill;          /* decorations only */
+} fdc_text_rect;               /* 32 bytes */
 
 typedef struct fdc_draw_op {   /* DrawableOp, fignodes.nim:21-42 */
   uint32_t kind;               /* 0 line, 1 circle, 2 rectangle, 3 bezier, 4 arc, 5 ellipse */
@@ -378,16 +386,23 @@ typedef struct fdc_flatten_env {
   size_t n_image_keys;
 } fdc_flatten_env;
 
+typedef struct fdc_scene {     /* Renders (fignodes.nim:48-49) + the side arrays the node records index */
+  const fdc_render_list* lists;  /* layers in table order */
+  uint32_t n_lists;
+  const fdc_glyph* glyphs;
+  const fdc_text_rect* text_rects;
+  const fdc_draw_op* ops;
+  const float* points;
+} fdc_scene;
+
 /* Pure host function (no context, no GPU): the body of renderFrame between beginFrame and endFrame as `fdc_call`
  * records -- saveTransform, scale(pixelScale), every layer's roots in order, restoreTransform.  Writes at most `cap`
  * records; *n_out is the number needed (FDC_ERR_CAPACITY when cap was too small). */
-int fdc_flatten_renders(const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs, const fdc_draw_op* ops,
-                        const float* points, const fdc_flatten_env* env, fdc_call* out, size_t cap, size_t* n_out);
+int fdc_flatten_renders(const fdc_scene* scene, const fdc_flatten_env* env, fdc_call* out, size_t cap, size_t* n_out);
 
 /* renderFrame on a context: beginFrame(frame size * uiScale), the flattened scene, endFrame. */
-int fdc_render_frame(fdc_ctx* ctx, const fdc_render_list* lists, uint32_t n_lists, const fdc_glyph* glyphs,
-                     const fdc_draw_op* ops, const float* points, float ui_scale, float frame_w, float frame_h,
-                     int clear_main, const float clear_rgba[4]);
+int fdc_render_frame(fdc_ctx* ctx, const fdc_scene* scene, float ui_scale, float frame_w, float frame_h, int clear_main,
+                     const float clear_rgba[4]);
 
 #ifdef __cplusplus
 }

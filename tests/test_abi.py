@@ -75,7 +75,8 @@ def test_scene_pod_layouts_match_the_header(tmp_path):
 #define O(t, f) printf(#t "." #f " %zu\n", offsetof(t, f))
 int main(void) {
   S(fdc_call); S(fdc_node_fill); S(fdc_node_shadow); S(fdc_node_stroke); S(fdc_fig); S(fdc_glyph); S(fdc_draw_op);
-  S(fdc_render_list); S(fdc_flatten_env);
+  S(fdc_render_list); S(fdc_flatten_env); S(fdc_text_rect); S(fdc_scene);
+  O(fdc_scene, glyphs); O(fdc_scene, text_rects); O(fdc_scene, ops); O(fdc_scene, points); O(fdc_fig, u.text.n_decoration);
   O(fdc_fig, flags); O(fdc_fig, parent); O(fdc_fig, child_count); O(fdc_fig, screen_box); O(fdc_fig, rotation); O(fdc_fig, fill);
   O(fdc_fig, corners); O(fdc_fig, corner_radii_y); O(fdc_fig, u);
   O(fdc_fig, u.rect.stroke); O(fdc_fig, u.drawable.steps); O(fdc_fig, u.drawable.first_op); O(fdc_fig, u.msdf.px_range);
@@ -114,5 +115,10 @@ int main(void) {
     d = abi.DRAW_OP_DTYPE.fields
     for name in ("center", "box", "start_angle", "first_point", "steps"):
         assert c[f"fdc_draw_op.{name}"] == d[name][1], name
+    assert c["fdc_text_rect"] == abi.TEXT_RECT_DTYPE.itemsize
+    assert c["fdc_scene"] == ctypes.sizeof(abi.FdcScene)
+    for name in ("glyphs", "text_rects", "ops", "points"):
+        assert c[f"fdc_scene.{name}"] == getattr(abi.FdcScene, name).offset, name
+    assert c["fdc_fig.u.text.n_decoration"] == pay + abi.FIG_TEXT_DTYPE.fields["n_decoration"][1]
     assert c["fdc_render_list.root_ids"] == abi.FdcRenderList.root_ids.offset
     assert c["fdc_flatten_env.image_keys"] == abi.FdcFlattenEnv.image_keys.offset

@@ -144,6 +144,10 @@ def random_renders(seed: int) -> Renders:
                                                  steps=(0, 0, 1, 4)[ri(4)]))
         elif kind == FigKind.nkText:
             n.glyphs = [Glyph(key=1000 + ri(40), pos=(u(0, 300), u(0, 100)), fill=rfill()) for _ in range(ri(12))]
+            if ri(2):
+                n.flags = FigFlags(int(n.flags) | int(FigFlags.NfSelectText))
+            n.selectionRects = [rect(u(0, 200), u(0, 80), u(-1, 60), u(-2, 20)) for _ in range(ri(3))]
+            n.decorations = [(rect(u(0, 200), u(0, 80), u(-5, 120), u(-1, 3)), rfill()) for _ in range(ri(3))]
         elif kind == FigKind.nkImage:
             n.image = ImageStyle(id=(0, 77, 78)[ri(3)], fill=rfill())
         elif kind in (FigKind.nkMsdfImage, FigKind.nkMtsdfImage):
@@ -181,7 +185,8 @@ def test_random_trees_flatten_identically(seed):
     r = random_renders(seed)
     keys = [(1000 + k, np.zeros((4, 4, 4), np.uint8)) for k in range(0, 40, 3)]
     ui = (1.0, 1.0, 2.0, 0.75)[seed % 4]
-    assert_same(native_records(r, keys, ui_scale=ui), per_call_records(r, 640, 480, keys, ui_scale=ui))
+    sub = seed % 3 == 0  # subpixel positioning: glyph x snapped, the fraction goes to setTextSubpixelShift
+    assert_same(native_records(r, keys, ui_scale=ui, subpixel=sub), per_call_records(r, 640, 480, keys, ui_scale=ui, subpixel=sub))
 
 
 def test_unknown_drawable_kind_is_refused():

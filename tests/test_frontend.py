@@ -170,3 +170,113 @@ def test_quadratic_sdf_padding_stays_in_physical_pixels():
         assert abs(float(d[0]["f"][2]) - 48.0) < 1e-4 and abs(float(d[0]["f"][3]) - 18.0) < 1e-4
     finally:
         setFigUiScale(1.0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The remaining "nkTransform render behavior" pins of tests/ttransform.nim (:147-267, :421-452, :526-547).
+def _records(renders):
+    tb = TraceBackend()
+    renderRoot(tb, renders)
+    return tb._buf[: tb._n].copy()
+
+
+def _apply_transforms(calls, draw_index):
+    """Position of draw `draw_index`'s rect origin under the recorded transform stack (what RecordingBackend reports)."""
+    m, stack, k = np.eye(4, dtype=np.float64), [], -1
+    for c in calls:
+        op = int(c["op"])
+        if op == Op.SAVE_TRANSFORM:
+            stack.append(m.copy())
+        elif op == Op.RESTORE_TRANSFORM:
+            m = stack.pop()
+        elif op == Op.TRANSLATE:
+            t = np.eye(4)
+            t[0, 3], t[1, 3] = c["f"][0], c["f"][1]
+            m = m @ t
+        elif op == Op.SCALE:
+            m = m @ np.diag([c["f"][0], c["f"][1], 1.0, 1.0])
+        elif op == Op.APPLY_TRANSFORM:
+            m = m @ np.asarray(c["f"][:16], dtype=np.float64).reshape(4, 4).T  # vmath is column-major
+        elif op >= 32:
+            k += 1
+            if k == draw_index:
+                p = m @ np.array([c["f"][0], c["f"][1], 0.0, 1.0])
+                return float(p[0]), float(p[1])
+    raise IndexError(draw_index)
+
+
+def test_corner_axes_reach_the_backend():
+    from figdraw_b200.fignodes import BackdropBlurStyle
+    from figdraw_b200.fignodes import fill as solid_fill
+
+    r = Renders()
+    r.addRoot(0, Fig(kind=FigKind.nkRectangle, screenBox=rect(5, 7, 40, 20), fill=solid_fill(rgba(255, 0, 0, 255)),
+                     flags=FigFlags.NfEllipticalCorners, corners=(12, 10, 8, 6), cornerRadiiY=(4, 5, 6, 7)))
+    d = _records(r)
+    d = d[d["op"] == Op.ROUNDED_RECT]
+    assert len(d) == 1 and list(d[0]["f"][4:8]) == [12, 10, 8, 6] and list(d[0]["f"][8:12]) == [4, 5, 6, 7]
+    r = Renders()
+    r.addRoot(0, Fig(kind=FigKind.nkRectangle, screenBox=rect(5, 7, 40, 20), fill=solid_fill(rgba(255, 0, 0, 255)),
+                     corners=(12, 10, 8, 6)))
+    d = _records(r)
+    d = d[d["op"] == Op.ROUNDED_RECT]
+    assert len(d) == 1 and list(d[0]["f"][4:8]) == list(d[0]["f"][8:12])  # circular corners promoted to equal axes
+    r = Renders()
+    r.addRoot(0, Fig(kind=FigKind.nkBackdropBlur, flags=FigFlags.NfEllipticalCorners, screenBox=rect(5, 7, 40, 20),
+                     corners=(12, 10, 8, 6), cornerRadiiY=(4, 5, 6, 7), backdropBlur=BackdropBlurStyle(blur=10.0)))
+    d = _records(r)
+    d = d[d["op"] == Op.BACKDROP_BLUR]
+    assert len(d) == 1 and list(d[0]["f"][4:8]) == [12, 10, 8, 6] and list(d[0]["f"][8:12]) == [4, 5, 6, 7]
+
+
+def test_transform_nodes_apply_to_children():
+    from figdraw_b200.fignodes import TransformStyle, drawableRect
+    from figdraw_b200.fignodes import fill as solid_fill
+
+    def child():
+        n = Fig(kind=FigKind.nkDrawable, screenBox=rect(0, 0, 1, 1), fill=solid_fill(rgba(255, 0, 0, 255)))
+        n.drawOps = [drawableRect(rect(2, 2, 1, 1))]
+        return n
+
+    r = Renders()
+    root = r.addRoot(0, Fig(kind=FigKind.nkTransform, transform=TransformStyle(translation=(5.0, -4.0))))
+    r.addChild(0, root, child())
+    calls = _records(r)
+    assert (calls["op"] >= 32).sum() == 1
+    x, y = _apply_transforms(calls, 0)
+    assert abs(x - 7.0) < 1e-4 and abs(y - (-2.0)) < 1e-4
+    r = Renders()
+    m = np.diag([2.0, 3.0, 1.0, 1.0]).astype(np.float32)  # scale(vec3(2, 3, 1))
+    root = r.addRoot(0, Fig(kind=FigKind.nkTransform,
+                            transform=TransformStyle(translation=(10.0, 20.0), matrix=m.T.reshape(16).tolist(), useMatrix=True)))
+    r.addChild(0, root, child())
+    calls = _records(r)
+    x, y = _apply_transforms(calls, 0)
+    assert abs(x - 14.0) < 1e-4 and abs(y - 26.0) < 1e-4
+
+
+def test_ellipse_drawables_and_drawable_aa():
+    from figdraw_b200.fignodes import drawableEllipse, drawableRect
+    from figdraw_b200.fignodes import fill as solid_fill
+
+    n = Fig(kind=FigKind.nkDrawable, screenBox=rect(5, 7, 30, 20), fill=solid_fill(rgba(20, 40, 80, 255)))
+    n.drawStroke = RenderStroke(weight=2.0, fill=solid_fill(rgba(255, 0, 0, 255)))
+    n.drawOps = [drawableEllipse((10.0, 8.0), (6.25, 3.5))]
+    r = Renders()
+    r.addRoot(0, n)
+    d = _records(r)
+    d = d[d["op"] >= 32]
+    assert [int(u[0]) for u in d["u"]] == [SdfMode.sdfModeClipAA, SdfMode.sdfModeAnnularAA]
+    for c in d:
+        assert list(c["f"][4:8]) == [6.25] * 4 and list(c["f"][8:12]) == [3.5] * 4
+    assert [float(v) for v in d[0]["f"][0:4]] == [8.75, 11.5, 12.5, 7.0]
+    assert len(_drawable_draws([drawableEllipse((10.0, 10.0), (8.0, 0.0))])) == 0
+    # drawAa overrides the backend AA factor and restores it (:526-547)
+    n = Fig(kind=FigKind.nkDrawable, screenBox=rect(5, 7, 40, 30), fill=solid_fill(rgba(255, 0, 0, 255)), drawAa=0.75)
+    n.drawOps = [drawableRect(rect(2, 3, 10, 8))]
+    r = Renders()
+    r.addRoot(0, n)
+    calls = _records(r)
+    aa = [float(c["f"][0]) for c in calls if int(c["op"]) == Op.SET_AA]
+    assert (calls["op"] >= 32).sum() == 1 and len(aa) == 2
+    assert abs(aa[0] - 0.75) < 1e-4 and abs(aa[1] - 1.2) < 1e-4

@@ -462,3 +462,13 @@ def test_mask_nesting_limit():
         ctx.beginMask((0, 0, 64, 64), circularRadii((0, 0, 0, 0)))
     assert e.value.code == 4  # FDC_ERR_CAPACITY
     ctx.close()
+
+
+def test_reference_spot_pixels():
+    """The spot pixels asserted by the reference's own render tests, on the CUDA backend."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_oracle_golden import check_reference_spot_pixels
+
+    check_reference_spot_pixels(render_trace)

@@ -75,3 +75,41 @@ def test_fuzz_streams_are_deterministic_on_the_oracle():
         c1 = oracle.count_fragments(tr)
         _img, c2 = oracle.render_trace(tr, want_counts=True)
         assert np.array_equal(c1, c2)
+
+
+def _max_channel_delta(px, r, g, b):
+    return max(abs(int(px[0]) - r), abs(int(px[1]) - g), abs(int(px[2]) - b))
+
+
+def oneframe_scene():
+    """tests/tfigrender_oneframe_screenshot.nim:20-42: white root + one red rect, 240x160."""
+    from figdraw_b200.fignodes import Fig, FigKind, RenderList, Renders, fill, rect, rgba
+
+    lst = RenderList()
+    lst.addRoot(Fig(kind=FigKind.nkRectangle, screenBox=rect(0, 0, 240, 160), fill=fill(rgba(255, 255, 255, 255))))
+    lst.addRoot(Fig(kind=FigKind.nkRectangle, screenBox=rect(32, 24, 120, 80), fill=fill(rgba(220, 40, 40, 255))))
+    r = Renders()
+    r.setLayer(0, lst)
+    return r
+
+
+def check_reference_spot_pixels(render):
+    """The spot pixels the reference's render tests assert (img[x, y], tolerances as in the Nim tests)."""
+    from figdraw_b200.scenes_synth import trace_renders
+
+    img = render(trace_renders(oneframe_scene(), 240, 160))
+    assert img.shape[:2] == (160, 240)
+    assert _max_channel_delta(img[12, 12], 255, 255, 255) <= 12   # tfigrender_oneframe_screenshot.nim:90-92
+    assert _max_channel_delta(img[48, 64], 220, 40, 40) <= 12
+    img = render(scenes.golden_trace("linear_gradient"))            # trender_linear_gradient.nim:124-138
+    for (x, y), rgb in {(120, 140): (220, 40, 40), (300, 140): (40, 200, 90), (480, 140): (50, 90, 225),
+                        (190, 270): (240, 210, 40), (190, 430): (110, 60, 210)}.items():
+        assert _max_channel_delta(img[y, x], *rgb) <= 40, (x, y)
+    left, right = img[252, 365], img[252, 555]
+    assert int(left[0]) > int(left[2]) + 40 and int(right[2]) > int(right[0]) + 40
+    left, right = img[400, 602], img[400, 768]
+    assert int(left[0]) > int(left[2]) + 20 and int(right[2]) > int(right[0]) + 20
+
+
+def test_oracle_reference_spot_pixels():
+    check_reference_spot_pixels(oracle.render_trace)

@@ -7,6 +7,8 @@ A "step" is ONE FRAME of the hot path (setup + binning + shade [+ blur]) over on
   N = 1   : BASELINE.json's target scene -- 100k shadowed rounded rects + 20k glyph quads at 3840x2160 (cfg5).
   N > 1   : the same scene at 7680x4320 (all sizes x2, configs[4]), framebuffer partitioned into tile-row bands,
             one rank per GPU, NCCL all-gather of the bands at the end of every frame (strong scaling of one frame).
+            The line then carries `single_gpu_same_workload` -- the 8K frame timed on rank 0's GPU alone in the same
+            run -- because the N = 1 line is the 4K scene: scaling of THIS workload is value / (N x that value).
 `value` is Mpixels/s with the frame's inputs already resident in HBM (kernels only, CUDA events on the context's
 stream, max over ranks); `e2e` is the same metric through the C ABI with HOST buffers: fdc_begin_frame +
 fdc_submit_calls(host records) + fdc_end_frame + fdc_read_pixels(host), copies inside the timed region.

@@ -708,7 +708,10 @@ int execute_frame(fdc_ctx* ctx, bool upload) {
   if (!ctx->ext_fb) {
     if (ctx->flag_off && fb_bytes > ctx->flag_off)
       return ctx->fail(FDC_ERR_CAPACITY, "frame larger than the framebuffer reserved with fdc_reserve_framebuffer");
+    const size_t had = ctx->d_fb.cap;
     CK(ctx->d_fb.reserve(fb_bytes));
+    // a new framebuffer starts transparent black: a first frame without clearMain blends over defined pixels
+    if (ctx->d_fb.cap != had) CK(cudaMemsetAsync(ctx->d_fb.p, 0, ctx->d_fb.cap, st));
   }
   bool any_blur = false;
   for (auto& s : ctx->segments) any_blur = any_blur || s.has_blur;

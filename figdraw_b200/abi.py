@@ -80,6 +80,10 @@ FIRST_DRAW_OP = 32
 
 CALL_DTYPE = np.dtype([("op", "<u4"), ("u", "<u4", (9,)), ("f", "<f4", (22,))])
 assert CALL_DTYPE.itemsize == 128
+# compact rounded-rect record (fdc_rect64)
+RECT64_DTYPE = np.dtype([("rect", "<f4", (4,)), ("radii", "<f4", (4,)), ("factor", "<f4"), ("spread", "<f4"),
+                         ("shape_size", "<f4", (2,)), ("packed", "<u4"), ("c", "<u4", (3,))])
+assert RECT64_DTYPE.itemsize == 64
 
 
 class FdcFill(ctypes.Structure):
@@ -170,7 +174,7 @@ EXPORTS = [
     "fdc_draw_rounded_rect_sdf", "fdc_draw_image", "fdc_draw_msdf_image", "fdc_draw_quadratic_bezier_sdf",
     "fdc_draw_filled_quad", "fdc_draw_rect", "fdc_draw_backdrop_blur",
     "fdc_begin_mask", "fdc_end_mask", "fdc_pop_mask", "fdc_begin_rect_mask", "fdc_pop_rect_mask",
-    "fdc_submit_calls", "fdc_submit_draws",
+    "fdc_submit_calls", "fdc_submit_draws", "fdc_pack_rect64", "fdc_expand_rect64", "fdc_submit_rects64",
     "fdc_put_image", "fdc_update_image", "fdc_has_image", "fdc_get_image_rect", "fdc_remove_image",
     "fdc_reset_image_atlas", "fdc_atlas_size", "fdc_atlas_packed_area",
     "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers", "fdc_set_peer_gather", "fdc_reserve_framebuffer", "fdc_framebuffer_ipc_handle", "fdc_open_peer_framebuffer",
@@ -262,6 +266,9 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_open_peer_framebuffer", c.c_int, P, c.POINTER(c.c_uint8), c.POINTER(P))
     sig("fdc_get_frame_stats", c.c_int, P, c.POINTER(FdcFrameStats))
     sig("fdc_debug_shade_stats", c.c_int, P, c.POINTER(c.c_uint64))
+    sig("fdc_pack_rect64", c.c_int, c.c_void_p, c.c_void_p)
+    sig("fdc_expand_rect64", None, c.c_void_p, c.c_void_p)
+    sig("fdc_submit_rects64", c.c_int, P, c.c_void_p, c.c_size_t)
     sig("fdc_read_pixels_async", c.c_int, P, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p)
     sig("fdc_set_peer_gather", c.c_int, P, c.c_int, c.c_int)
     sig("fdc_flatten_renders", c.c_int, c.POINTER(FdcScene), c.POINTER(FdcFlattenEnv), c.c_void_p, c.c_size_t,

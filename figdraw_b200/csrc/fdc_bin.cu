@@ -193,9 +193,17 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.count) return;
   uint32_t di = a.first + i;
-  const DrawView d{s_draw[threadIdx.x]};
   int ri = find_run(a.runs, a.n_runs, di);
   const RunState rs = a.runs[ri];
+  if (rs.compact) {
+    // the run arrived as 64-byte fdc_rect64 records: expand mine over my staging slot (only this thread reads it)
+    const fdc_rect64 r = a.rects64[rs.src_off + (di - rs.first_draw)];
+    uint32_t w[32];
+    expand_rect64_words(r, w);
+#pragma unroll
+    for (int k = 0; k < 32; k++) s_draw[threadIdx.x][k] = w[k];
+  }
+  const DrawView d{s_draw[threadIdx.x]};
   const Xform xf = a.xforms[rs.xform];
   a.prim_call[i] = rs.call_index + (di - rs.first_draw);
 

@@ -255,6 +255,8 @@ struct fdc_ctx {
   DevBuf<uint8_t> d_fb, d_backdrop, d_temp;
   uint8_t* ext_fb = nullptr;
   DevBuf<uint8_t*> d_peers;
+  DevBuf<fdc_rect64> d_rects64;    // compact draw records of this frame (fdc_submit_rects64)
+  uint32_t n_rects64 = 0;
   std::vector<uint8_t*> h_peers;   // host copy of the peer framebuffer pointers (own entry = own framebuffer)
   size_t flag_off = 0;             // byte offset of the cross-rank flag array inside a reserved framebuffer (0: none)
   uint32_t frame_barrier_base = 0; // barrier_seq at the start of the frame in flight
@@ -651,6 +653,7 @@ BinBuffers bin_buffers(fdc_ctx* ctx) {
 SetupArgs setup_args(fdc_ctx* ctx, const Segment& s) {
   SetupArgs a;
   a.draws = ctx->d_draws.p;
+  a.rects64 = ctx->d_rects64.p;
   a.runs = ctx->d_runs.p;
   a.n_runs = (int)ctx->runs.n;
   a.xforms = ctx->d_xforms.p;
@@ -975,6 +978,7 @@ void fdc_destroy(fdc_ctx* ctx) {
   ctx->d_table.release();
   ctx->draws.release(); ctx->runs.release(); ctx->xforms.release(); ctx->rectmasks.release();
   ctx->flat[0].release(); ctx->flat[1].release();
+  ctx->d_rects64.release();
   ctx->d_draws.release(); ctx->d_runs.release(); ctx->d_xforms.release(); ctx->d_rectmasks.release();
   ctx->d_prims.release(); ctx->d_geoms.release(); ctx->d_exts.release(); ctx->d_prim_call.release();
   ctx->d_chunk_counts.release(); ctx->d_warp_counts.release(); ctx->d_cbin_start.release(); ctx->d_coarse_list.release();
@@ -1015,6 +1019,7 @@ int fdc_begin_frame(fdc_ctx* ctx, int width, int height, int clear_main, const f
   compute_frame_view(ctx);
   ctx->draws.n = ctx->runs.n = ctx->xforms.n = ctx->rectmasks.n = 0;
   ctx->n_draws = 0;
+  ctx->n_rects64 = 0;
   ctx->uploads.clear();
   ctx->segments.clear();
   start_segment(ctx);
@@ -1471,6 +1476,71 @@ int fdc_submit_draws(fdc_ctx* ctx, const fdc_call* draws, size_t n) {
   rc = add_direct_run(ctx, draws, n, ctx->call_ordinal);
   if (rc == FDC_OK) ctx->call_ordinal += (uint32_t)n;
   return rc;
+}
+
+// fdc_rect64 helpers (pure host) and the compact bulk path.
+int fdc_pack_rect64(const fdc_call* in, fdc_rect64* out) {
+  if (!in || !out || in->op != FDC_OP_ROUNDED_RECT) return 0;
+  const uint32_t mode = in->u[0], kind = in->u[1], axis = in->u[2];
+  if (mode > 255u || kind < (uint32_t)FDC_FILL_COLOR || kind > (uint32_t)FDC_FILL_LINEAR3 || axis > 3u) return 0;
+  if (memcmp(&in->f[4], &in->f[8], 4 * sizeof(float)) != 0) return 0;  // elliptical corners need the full record
+  fdc_rect64 r;
+  memset(&r, 0, sizeof(r));
+  for (int k = 0; k < 4; k++) { r.rect[k] = in->f[k]; r.radii[k] = in->f[4 + k]; }
+  r.factor = in->f[12]; r.spread = in->f[13];
+  r.shape_size[0] = in->f[14]; r.shape_size[1] = in->f[15];
+  r.c[0] = in->u[3]; r.c[1] = in->u[4]; r.c[2] = in->u[5];
+  uint32_t m = 0;
+  if (kind == (uint32_t)FDC_FILL_LINEAR3) {
+    const float mid = in->f[16];
+    if (!(mid >= 0.01f && mid <= 0.99f)) return 0;
+    m = (uint32_t)lrintf(mid * 255.0f);
+    if (m > 255u) return 0;
+  }
+  r.packed = mode | (kind << 8) | (axis << 10) | (m << 16);
+  // accept only what expands back to the very same 128 bytes (tries the neighbouring uint8 mid positions too)
+  for (int dm = 0; dm < 3; dm++) {
+    const int mm = (int)m + (dm == 0 ? 0 : (dm == 1 ? -1 : 1));
+    if (mm < 0 || mm > 255) continue;
+    r.packed = mode | (kind << 8) | (axis << 10) | ((uint32_t)mm << 16);
+    fdc_call back;
+    expand_rect64_words(r, reinterpret_cast<uint32_t*>(&back));
+    if (memcmp(&back, in, sizeof(fdc_call)) == 0) {
+      *out = r;
+      return 1;
+    }
+    if (kind != (uint32_t)FDC_FILL_LINEAR3) break;
+  }
+  return 0;
+}
+
+void fdc_expand_rect64(const fdc_rect64* in, fdc_call* out) {
+  if (in && out) expand_rect64_words(*in, reinterpret_cast<uint32_t*>(out));
+}
+
+int fdc_submit_rects64(fdc_ctx* ctx, const fdc_rect64* rects, size_t n) {
+  if (!ctx || (!rects && n)) return FDC_ERR_INVALID;
+  if (n == 0) return FDC_OK;
+  if (!ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "draw outside beginFrame/endFrame");
+  if (ctx->mask_begun) return ctx->fail(FDC_ERR_STATE, "fdc_submit_rects64 inside beginMask/endMask is not supported");
+  RunState rs = current_state(ctx);
+  rs.first_draw = ctx->n_draws;
+  rs.call_index = ctx->call_ordinal;
+  rs.compact = 1;
+  rs.src_off = ctx->n_rects64;
+  if (!ctx->runs.push(rs)) return ctx->fail(FDC_ERR_CUDA, "out of pinned memory");
+  CK(cudaSetDevice(ctx->device));
+  // the draw index space stays one: d_draws keeps (unused) room for these indices
+  CK(ctx->d_draws.reserve_keep((size_t)ctx->n_draws + n, ctx->n_draws, ctx->stream));
+  CK(ctx->d_rects64.reserve_keep((size_t)ctx->n_rects64 + n, ctx->n_rects64, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_rects64.p + ctx->n_rects64, rects, sizeof(fdc_rect64) * n, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->n_rects64 += (uint32_t)n;
+  ctx->n_draws += (uint32_t)n;
+  ctx->segments.back().count += (uint32_t)n;
+  ctx->last_draw_ordinal = ctx->call_ordinal + (uint32_t)n - 1;
+  ctx->call_ordinal += (uint32_t)n;
+  ctx->state_dirty = true;  // the next draw starts its own run
+  return FDC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------- atlas

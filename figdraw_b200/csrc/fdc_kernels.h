@@ -8,6 +8,7 @@ namespace fdc {
 
 struct SetupArgs {
   const fdc_call* draws;  // all draws of the frame (device)
+  const fdc_rect64* rects64;  // compact records of the runs marked `compact`
   const RunState* runs;
   int n_runs;
   const Xform* xforms;

@@ -121,8 +121,43 @@ struct alignas(16) RunState {
   uint32_t rectmask;     // 0 = none, else index+1 into the rect mask table
   int32_t clip_draw;     // draw index of the mask primitive whose bbox clips this run's draws, or -1
   uint32_t call_index;   // backend-call ordinal of the first draw (draws of a run are consecutive calls)
+  uint32_t compact;      // 1: the run's records are fdc_rect64 at rects64[src_off + (draw - first_draw)]
+  uint32_t src_off;
+  uint32_t pad_[2];
 };
-static_assert(sizeof(RunState) == 32, "RunState must be 32 bytes");
+static_assert(sizeof(RunState) == 48, "RunState must be 48 bytes");
+
+// fdc_rect64 -> the 32 words of the fdc_call it was packed from (op, u[9], f[22]).  Shared by the host helper and the
+// setup kernel, so what the tests check on the CPU is what runs on the device.
+#ifdef __CUDACC__
+#define FDC_HD __host__ __device__
+#else
+#define FDC_HD
+#endif
+FDC_HD inline void expand_rect64_words(const fdc_rect64& r, uint32_t* w) {
+  union { float f; uint32_t u; } cv;
+  for (int k = 0; k < 32; k++) w[k] = 0u;
+  w[0] = FDC_OP_ROUNDED_RECT;
+  const uint32_t kind = (r.packed >> 8) & 3u;
+  w[1] = r.packed & 255u;          // u[0] mode
+  w[2] = kind;                     // u[1] fill kind
+  w[3] = (r.packed >> 10) & 3u;    // u[2] axis
+  w[4] = r.c[0]; w[5] = r.c[1]; w[6] = r.c[2];
+  for (int k = 0; k < 4; k++) {
+    cv.f = r.rect[k]; w[10 + k] = cv.u;
+    cv.f = r.radii[k]; w[14 + k] = cv.u; w[18 + k] = cv.u;
+  }
+  cv.f = r.factor; w[22] = cv.u;
+  cv.f = r.spread; w[23] = cv.u;
+  cv.f = r.shape_size[0]; w[24] = cv.u;
+  cv.f = r.shape_size[1]; w[25] = cv.u;
+  float mid = 0.5f;
+  if (kind == (uint32_t)FDC_FILL_LINEAR3) {
+    mid = (float)((r.packed >> 16) & 255u) / 255.0f;
+    mid = mid < 0.01f ? 0.01f : (mid > 0.99f ? 0.99f : mid);
+  }
+  cv.f = mid; w[26] = cv.u;        // f[16] mid_pos
+}
 
 // 2-D affine part of the transform (vmath Mat4 columns 0, 1, 3; rows x, y).
 struct alignas(8) Xform {

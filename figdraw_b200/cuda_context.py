@@ -270,13 +270,22 @@ class CudaContext(BackendContext):
         self._ck(self._lib.fdc_submit_draws(self._h, draws.ctypes.data, len(draws)))
 
     def submitPrepared(self, prepared):
-        """Replay a `prepare_calls()` result: state ops record by record, runs of draws through fdc_submit_draws."""
+        """Replay a `prepare_calls()` result: state ops record by record, runs of draws through fdc_submit_draws,
+        runs of compact rounded-rect records through fdc_submit_rects64."""
         calls, runs = prepared
-        for is_draw, a, b in runs:
-            if is_draw:
+        for run in runs:
+            kind, a, b = run[0], run[1], run[2]
+            if kind == "rects64":
+                r = run[3]
+                self._ck(self._lib.fdc_submit_rects64(self._h, r.ctypes.data, len(r)))
+            elif kind in ("draws", True):
                 self._ck(self._lib.fdc_submit_draws(self._h, calls[a:b].ctypes.data, b - a))
             else:
                 self._ck(self._lib.fdc_submit_calls(self._h, calls[a:b].ctypes.data, b - a))
+
+    def submitRects64(self, rects: np.ndarray):
+        rects = np.ascontiguousarray(rects, dtype=abi.RECT64_DTYPE)
+        self._ck(self._lib.fdc_submit_rects64(self._h, rects.ctypes.data, len(rects)))
 
     def renderFrameNative(self, scene, frameSize, uiScale: float = 1.0, clearMain: bool = True,
                           clearColor=(1.0, 1.0, 1.0, 1.0)):
@@ -345,15 +354,73 @@ class CudaContext(BackendContext):
         self._ck(self._lib.fdc_set_peer_framebuffers(self._h, arr, len(ptrs)))
 
 
-def prepare_calls(calls: np.ndarray):
+def pack_rects64(calls: np.ndarray):
+    """Vectorised fdc_pack_rect64: (mask of representable records, their fdc_rect64 form).  A record is representable
+    when it is a rounded rect with radii_x == radii_y, a solid / 2-stop / 3-stop fill and a midPos on the uint8 grid;
+    the result expands back to the identical 128 bytes (tests/test_rect64.py checks that through the C helper)."""
+    calls = np.ascontiguousarray(calls)
+    u, f = calls["u"], calls["f"]
+    fb = f.view(np.uint32)
+    kind, axis, mode = u[:, 1], u[:, 2], u[:, 0]
+    ok = (calls["op"] == int(abi.Op.ROUNDED_RECT)) & (kind >= 1) & (kind <= 3) & (axis <= 3) & (mode <= 255)
+    ok &= (fb[:, 4:8] == fb[:, 8:12]).all(axis=1) & (u[:, 6:9] == 0).all(axis=1) & (fb[:, 17:22] == 0).all(axis=1)
+    lin3 = kind == 3
+    mid = f[:, 16]
+    m = np.zeros(len(calls), dtype=np.uint32)
+    found = ~lin3 & (fb[:, 16] == np.float32(0.5).view(np.uint32))
+    with np.errstate(invalid="ignore"):
+        m0 = np.clip(np.rint(np.nan_to_num(mid.astype(np.float64)) * 255.0), 0, 255).astype(np.int64)
+    for dm in (0, -1, 1):
+        cand = np.clip(m0 + dm, 0, 255)
+        back = np.clip(cand.astype(np.float32) / np.float32(255.0), np.float32(0.01), np.float32(0.99))
+        hit = lin3 & ~found & (back.view(np.uint32) == fb[:, 16])
+        m[hit] = cand[hit].astype(np.uint32)
+        found |= hit
+    ok &= found
+    r = np.zeros(int(ok.sum()), dtype=abi.RECT64_DTYPE)
+    sel = calls[ok]
+    r["rect"], r["radii"] = sel["f"][:, 0:4], sel["f"][:, 4:8]
+    r["factor"], r["spread"], r["shape_size"] = sel["f"][:, 12], sel["f"][:, 13], sel["f"][:, 14:16]
+    r["packed"] = sel["u"][:, 0] | (sel["u"][:, 1] << 8) | (sel["u"][:, 2] << 10) | (m[ok] << 16)
+    r["c"] = sel["u"][:, 3:6]
+    return ok, r
+
+
+def prepare_calls(calls: np.ndarray, compact: bool = False, min_compact_run: int = 256):
     """Split a call array once into maximal runs of draw records / other records (what a host that emits the calls
-    knows anyway), so replaying it needs no per-record inspection."""
+    knows anyway), so replaying it needs no per-record inspection.  `compact`: runs of representable rounded rects are
+    converted to 64-byte fdc_rect64 records (half the bytes over PCIe); runs: (kind, a, b[, rects64])."""
     calls = np.ascontiguousarray(calls)
     is_draw = calls["op"] >= abi.FIRST_DRAW_OP
-    edges = np.flatnonzero(np.diff(is_draw.astype(np.int8))) + 1
+    cls = is_draw.astype(np.int8)
+    rects = None
+    if compact:
+        ok, rects = pack_rects64(calls)
+        cls = cls + ok.astype(np.int8)  # 0 state, 1 draw, 2 compact draw
+        # short compact runs are not worth a separate submission: demote them to plain draws
+        edges = np.flatnonzero(np.diff(cls)) + 1
+        bounds = [0, *edges.tolist(), len(calls)]
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            if cls[a] == 2 and b - a < min_compact_run:
+                cls[a:b] = 1
+    edges = np.flatnonzero(np.diff(cls)) + 1
     bounds = [0, *edges.tolist(), len(calls)]
-    runs = [(bool(is_draw[a]), a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    runs = []
+    pos = np.cumsum(ok) - ok if compact else None  # index of each record in `rects`
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        if b <= a:
+            continue
+        if cls[a] == 2:
+            runs.append(("rects64", a, b, np.ascontiguousarray(rects[pos[a]:pos[a] + (b - a)])))
+        else:
+            runs.append(("draws" if cls[a] == 1 else "state", a, b))
     return calls, runs
+
+
+def prepared_upload_bytes(prepared) -> int:
+    """Bytes that cross host->device when a prepared frame is submitted."""
+    _calls, runs = prepared
+    return sum((64 if r[0] == "rects64" else 128) * (r[2] - r[1]) for r in runs)
 
 
 def submit_trace(trace: Trace, ctx: CudaContext) -> None:

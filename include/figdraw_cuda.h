@@ -212,6 +212,25 @@ int fdc_submit_calls(fdc_ctx* ctx, const fdc_call* calls, size_t n);
  * are dropped on the device.  Same lifetime rule for page-locked memory. */
 int fdc_submit_draws(fdc_ctx* ctx, const fdc_call* draws, size_t n);
 
+/* Compact form of the most common draw -- drawRoundedRectSdf with circular corner radii and a solid / 2-stop / 3-stop
+ * fill -- at half the size of fdc_call: what crosses PCIe per frame is mostly these.  A record expands to exactly the
+ * fdc_call it was packed from (fdc_expand_rect64 is what the setup kernel does on the device). */
+typedef struct fdc_rect64 {
+  float rect[4];
+  float radii[4];        /* TL, TR, BL, BR; used for both axes */
+  float factor, spread;
+  float shape_size[2];
+  uint32_t packed;       /* bits 0-7 fdc_sdf_mode, 8-9 fdc_fill_kind (1..3), 10-11 fdc_axis, 16-23 lin3 midPos as the uint8 of
+                          * the scene's Fill (mid_pos = clamp(u8 / 255, 0.01, 0.99), figbackend.nim:109-127) */
+  uint32_t c[3];         /* as fdc_fill.c[0..2] */
+} fdc_rect64;            /* 64 bytes */
+/* Host helpers.  fdc_pack_rect64 returns 1 and fills *out when `in` is representable (rounded rect, radii_x == radii_y,
+ * no 4-colour fill, midPos on the uint8 grid), else 0.  fdc_expand_rect64 is the inverse. */
+int fdc_pack_rect64(const fdc_call* in, fdc_rect64* out);
+void fdc_expand_rect64(const fdc_rect64* in, fdc_call* out);
+/* As fdc_submit_draws for a run of compact records (one run, one asynchronous copy of 64 bytes per draw). */
+int fdc_submit_rects64(fdc_ctx* ctx, const fdc_rect64* rects, size_t n);
+
 /* --- atlas: glcontext.nim:536-641, textures.nim:88-119 --- */
 /* putImage: packs (skyline, margin 4), uploads straight-alpha RGBA8 texels + a 2x2-box mip chain.
  * Re-putting an existing key allocates a new slot like GL does.  `out_rect` receives the

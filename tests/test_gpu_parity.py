@@ -472,3 +472,25 @@ def test_reference_spot_pixels():
     from test_oracle_golden import check_reference_spot_pixels
 
     check_reference_spot_pixels(render_trace)
+
+
+def test_compact_rect_records_render_identically():
+    """fdc_submit_rects64 (64-byte records expanded by the setup kernel) == the same frame from 128-byte records."""
+    from figdraw_b200.cuda_context import prepare_calls
+
+    for tr in (ss.config_trace(5, 1280, 720, n_rects=4000, n_glyphs=800), ss.config_trace(2, 1280, 720),
+               ss.config_trace(4, 1280, 720, rows=30, cols=6)):
+        want = render_trace(tr)
+        ctx = CudaContext(atlasSize=tr.atlas_size)
+        for _i, key, img in tr.images:
+            ctx.putImage(key, img)
+        prepared = prepare_calls(tr.calls, compact=True, min_compact_run=4)
+        assert any(r[0] == "rects64" for r in prepared[1])
+        for _ in range(2):
+            ctx.beginFrame((tr.width, tr.height), clearMain=tr.clear is not None, clearMainColor=tr.clear or (1.0, 1.0, 1.0, 1.0))
+            ctx.submitPrepared(prepared)
+            ctx.endFrame()
+            assert np.array_equal(ctx.readPixels(), want)
+        ctx.replayFrame()
+        assert np.array_equal(ctx.readPixels(), want)
+        ctx.close()

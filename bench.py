@@ -242,7 +242,7 @@ def main():
                     help="N>1: NCCL all-gather of the bands (nccl), fused peer stores from the shade kernel (p2p), or copy "
                          "engines shipping finished band slices to the peers while the next slice is shaded (ce)")
     ap.add_argument("--sub-bands", type=int, default=4)
-    ap.add_argument("--records", default="compact", choices=["compact", "full"],
+    ap.add_argument("--records", default=None, choices=["compact", "full"],
                     help="e2e upload: 64-byte fdc_rect64 records for rounded rects with circular corners, or 128-byte fdc_call only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
@@ -308,11 +308,14 @@ def main():
     out_host = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
     out_np = out_host.numpy()
     keep_pinned = []
+    # upload format of the e2e arm: compact records on one GPU (validated there, profiles/r01_e2e_records.md); the
+    # multi-GPU runs keep the plain 128-byte records unless asked otherwise
+    records = args.records or ("compact" if world == 1 else "full")
 
     def prepare_pinned(calls_pinned_np):
         """Run boundaries computed once (a host that emits the calls knows them); rounded rects with circular corners go
         as 64-byte fdc_rect64 records (`--records full` keeps everything at 128 bytes); every buffer page-locked."""
-        calls_, runs = prepare_calls(calls_pinned_np, compact=args.records == "compact")
+        calls_, runs = prepare_calls(calls_pinned_np, compact=records == "compact")
         out_runs = []
         for run in runs:
             if run[0] == "rects64":

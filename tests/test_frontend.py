@@ -280,3 +280,38 @@ def test_ellipse_drawables_and_drawable_aa():
     aa = [float(c["f"][0]) for c in calls if int(c["op"]) == Op.SET_AA]
     assert (calls["op"] >= 32).sum() == 1 and len(aa) == 2
     assert abs(aa[0] - 0.75) < 1e-4 and abs(aa[1] - 1.2) < 1e-4
+
+
+def test_text_node_call_order_and_subpixel_positioning():
+    """renderText (figrender.nim:417-497): selection rects, decorations, then glyphs; with subpixel positioning the glyph x is
+    snapped and its fraction goes to setTextSubpixelShift before the draw and back to 0 after it."""
+    from figdraw_b200.fignodes import Glyph
+    from figdraw_b200.fignodes import fill as solid_fill
+
+    n = Fig(kind=FigKind.nkText, screenBox=rect(10, 20, 200, 40), fill=solid_fill(rgba(0, 120, 255, 90)),
+            flags=FigFlags.NfSelectText)
+    n.selectionRects = [rect(4, 2, 0.25, 12), rect(4, 16, 30, 0)]            # width widened to 1, zero height skipped
+    n.decorations = [(rect(0, 14, 60, 1), solid_fill(rgba(255, 0, 0, 255))), (rect(0, 30, -2, 1), solid_fill(rgba(1, 2, 3, 255)))]
+    n.glyphs = [Glyph(key=501, pos=(3.75, 5.0)), Glyph(key=999, pos=(12.5, 5.0)), Glyph(key=502, pos=(20.0, 5.0))]
+    r = Renders()
+    r.addRoot(0, n)
+    tb = TraceBackend()
+    tb.putImage(501, np.zeros((4, 4, 4), np.uint8))
+    tb.putImage(502, np.zeros((4, 4, 4), np.uint8))
+    tb.setTextSubpixelPositioningEnabled(True)
+    renderRoot(tb, r)
+    calls = tb._buf[: tb._n]
+    seq = [Op(int(c["op"])) for c in calls][1:]  # after the SET_SUBPIXEL that enabled positioning
+    assert seq == [Op.SAVE_TRANSFORM, Op.TRANSLATE,
+                   Op.ROUNDED_RECT,                                    # one selection rect (the zero-height one is skipped)
+                   Op.ROUNDED_RECT,                                    # one decoration (the negative-width one is skipped)
+                   Op.SET_SUBPIXEL, Op.IMAGE, Op.SET_SUBPIXEL,        # glyph 501: shift .75, draw at x = 3, shift 0
+                   Op.SET_SUBPIXEL, Op.SET_SUBPIXEL,                  # glyph 999 is not resident: shift, reset, skip
+                   Op.SET_SUBPIXEL, Op.IMAGE, Op.SET_SUBPIXEL,        # glyph 502 on a whole pixel
+                   Op.SET_SUBPIXEL, Op.RESTORE_TRANSFORM]
+    sel = calls[3]
+    assert [float(v) for v in sel["f"][0:4]] == [4.0, 2.0, 1.0, 12.0] and int(sel["u"][3]) == rgba(0, 120, 255, 90)
+    shifts = [float(c["f"][0]) for c in calls[1:] if int(c["op"]) == Op.SET_SUBPIXEL]
+    assert shifts == [0.75, 0.0, 0.5, 0.0, 0.0, 0.0, 0.0]
+    img = [c for c in calls if int(c["op"]) == Op.IMAGE]
+    assert [float(c["f"][0]) for c in img] == [3.0, 20.0]

@@ -1,18 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the figdraw B200 render path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg5_4k|cfg5_8k|...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg5_4k|cfg5_8k|cfg2|...]
 
-A "step" is ONE FRAME of the hot path (setup + binning + shade [+ blur]) over one synthetic scene.
-  N = 1   : BASELINE.json's target scene -- 100k shadowed rounded rects + 20k glyph quads at 3840x2160 (cfg5).
-  N > 1   : the same scene at 7680x4320 (all sizes x2, configs[4]), framebuffer partitioned into tile-row bands,
-            one rank per GPU, NCCL all-gather of the bands at the end of every frame (strong scaling of one frame).
-            The line then carries `single_gpu_same_workload` -- the 8K frame timed on rank 0's GPU alone in the same
-            run -- because the N = 1 line is the 4K scene: scaling of THIS workload is value / (N x that value).
+A "step" is ONE FRAME of the hot path (setup + binning + shade [+ blur] [+ band all-gather]) over one synthetic scene.
+The workload is the SAME at every N: BASELINE.json's target scene -- 100k shadowed rounded rects + 20k glyph quads at
+3840x2160 (cfg5) -- so value(N) / (N x value(1)) is a real strong-scaling curve.  For N > 1 the framebuffer is
+partitioned into tile-row bands, one rank per GPU, and the bands are all-gathered at the end of every frame; the line
+then also carries `cfg5_8k`: BASELINE's multi-GPU config (the same scene at 7680x4320, all sizes x2) timed the same way
+next to the same frame on one GPU.
 `value` is Mpixels/s with the frame's inputs already resident in HBM (kernels only, CUDA events on the context's
 stream, max over ranks); `e2e` is the same metric through the C ABI with HOST buffers: fdc_begin_frame +
-fdc_submit_calls(host records) + fdc_end_frame + fdc_read_pixels(host), copies inside the timed region.
-`--impl reference` times the CPU restatement of the reference's GL path (oracle/) on all host cores.
+fdc_submit_*(host records) + fdc_end_frame + fdc_read_pixels(host), copies inside the timed region.
+`--impl reference` times the CPU restatement of the reference's GL path (oracle/) on all host cores, whole frames.
 """
 from __future__ import annotations
 
@@ -37,23 +37,52 @@ FLOPS_GRADIENT_EXTRA = 16
 FLOPS_BLUR_PER_PIXEL_PASS = 140
 N_MODES = 24
 
+WORKLOADS = {
+    "cfg5_4k": "cfg5: 100k shadowed rounded rects + 20k glyph quads, 3840x2160, seed 5",
+    "cfg5_8k": "cfg5 x2: 100k shadowed rounded rects + 20k glyph quads, 7680x4320, seed 5",
+    "cfg2": "cfg2: renderlist_100 shape (300 boxes, shadows, elliptical corners, 1 backdrop blur), 1920x1080",
+    "cfg3": "cfg3: 20k atlas glyph quads + MSDF/MTSDF star, 3840x2160",
+    "cfg3_msdf": "cfg3: 20k atlas glyph quads + 20k MSDF glyph quads + MSDF/MTSDF star, 3840x2160",
+    "cfg4": "cfg4: clip-mask table 180x12 (sub-clip), 3-stop gradients, 2 backdrop blurs, 3840x2160",
+    "cfg4_rectmask": "cfg4: clip-mask table 180x12 (rect-mask), 2 backdrop blurs, 3840x2160",
+}
+
 
 def workload_trace(name: str):
     from figdraw_b200 import scenes_synth as ss
 
+    if name not in WORKLOADS:
+        raise SystemExit(f"unknown workload {name}")
     if name == "cfg5_4k":
-        return ss.config_trace(5, 3840, 2160), "cfg5: 100k shadowed rounded rects + 20k glyph quads, 3840x2160, seed 5"
-    if name == "cfg5_8k":
-        return ss.config_trace(5, 7680, 4320, scale=2.0), "cfg5 x2: 100k shadowed rounded rects + 20k glyph quads, 7680x4320, seed 5"
-    if name == "cfg2":
-        return ss.config_trace(2), "cfg2: renderlist_100 shape (300 boxes, shadows, elliptical corners, 1 backdrop blur), 1920x1080"
-    if name == "cfg3":
-        return ss.config_trace(3), "cfg3: 20k atlas glyph quads + MSDF/MTSDF star, 3840x2160"
-    if name == "cfg4":
-        return ss.config_trace(4), "cfg4: clip-mask table 180x12 (sub-clip), 3-stop gradients, 2 backdrop blurs, 3840x2160"
-    if name == "cfg4_rectmask":
-        return ss.config_trace(4, rect_mask=True), "cfg4: clip-mask table 180x12 (rect-mask), 2 backdrop blurs, 3840x2160"
-    raise SystemExit(f"unknown workload {name}")
+        tr = ss.config_trace(5, 3840, 2160)
+    elif name == "cfg5_8k":
+        tr = ss.config_trace(5, 7680, 4320, scale=2.0)
+    elif name == "cfg2":
+        tr = ss.config_trace(2)
+    elif name == "cfg3":
+        tr = ss.config_trace(3)
+    elif name == "cfg3_msdf":
+        tr = ss.config_trace(3, msdf_glyphs=20000)
+    elif name == "cfg4":
+        tr = ss.config_trace(4)
+    else:
+        tr = ss.config_trace(4, rect_mask=True)
+    return tr, WORKLOADS[name]
+
+
+def bench_config(name: str, trace, world: int, gather: str = "nccl") -> dict:
+    """The `config` object of the JSON line -- ONE function for both arms, so `--impl reference` reports the very same
+    object as the GPU arm it is compared with."""
+    if world == 1:
+        part = "single GPU"
+    elif gather == "p2p":
+        part = f"{world} tile-row bands, band all-gather fused into the shade kernel (peer stores over NVLink)"
+    elif gather == "ce":
+        part = f"{world} tile-row bands, finished band slices copied to the peers by the copy engines (NVLink)"
+    else:
+        part = f"{world} tile-row bands + NCCL all-gather"
+    return {"workload": WORKLOADS[name], "frame": [trace.width, trace.height], "primitives": int(trace.n_draws),
+            "l2": "flushed between steps (256 MiB fill)", "partition": part}
 
 
 def algorithmic_flops(counts: np.ndarray) -> float:
@@ -162,37 +191,39 @@ def measured_peaks():
 
 
 def run_reference(args, rank: int, out=sys.stdout):
-    """CPU arm: the oracle port of the reference's GL path, all host threads, bounded sample per step."""
+    """CPU arm: the oracle port of the reference's GL path on all host threads.  Every step renders the WHOLE frame of the
+    GPU arm's workload (no row sample, no extrapolation); warm-up is capped at one frame so K + W steps stay in minutes."""
     if rank != 0:
         return
     from oracle import oracle as orc
 
-    name = args.workload or ("cfg5_4k" if args.gpus == 1 else "cfg5_8k")
-    trace, desc = workload_trace(name)
+    name = args.workload or "cfg5_4k"
+    trace, _desc = workload_trace(name)
     cores = orc.max_threads()
     o = orc.Oracle(trace.atlas_size)
     for _i, key, img in trace.images:
         o.put_image(key, img)
-    has_blur = bool((trace.calls["op"] == 13).any())
-    H = trace.height
-    rows = (0, H) if has_blur else (H // 2 - H // 32, H // 2 + H // 32)  # 1/16 of the frame, centred
-    for _ in range(args.warmup):
-        o.render(trace.width, H, trace.calls, clear=trace.clear, n_threads=cores, rows=rows)
-    t0 = time.perf_counter()
+    W, H = trace.width, trace.height
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        o.render(W, H, trace.calls, clear=trace.clear, n_threads=cores)
+    ts = []
     for _ in range(args.steps):
-        o.render(trace.width, H, trace.calls, clear=trace.clear, n_threads=cores, rows=rows)
-    dt = (time.perf_counter() - t0) / args.steps
-    px = trace.width * (rows[1] - rows[0])
-    val = px / dt / 1e6
-    sample = f"rows {rows[0]}..{rows[1]} of {H} ({px} px) of the same frame per step"
+        t0 = time.perf_counter()
+        o.render(W, H, trace.calls, clear=trace.clear, n_threads=cores)
+        ts.append(time.perf_counter() - t0)
+    dt = float(np.mean(ts))
+    val = W * H / dt / 1e6
+    sample = f"{args.steps} whole frames of the same scene ({W}x{H}), {dt:.2f} s each (min {min(ts):.2f} s), {warm} warm-up frame(s)"
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": METRIC, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3 * (trace.width * H) / px, 3),
+            "steps": args.steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "note": "restated-reference CPU rasteriser (oracle port of the GL path), not llvmpipe; "
-                       "ms_per_step extrapolated from the sample to the whole frame"},
+            "config": bench_config(name, trace, args.gpus, args.gather),
+            "note": "restated-reference CPU rasteriser (oracle port of the GL path, OpenMP over 64-row strips), not llvmpipe; "
+                    "whole frames, nothing extrapolated",
             "cpu_baseline": {"value": round(val, 3), "unit": METRIC, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(val, 3), "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "frames_per_s": round(val * 1e6 / (trace.width * H), 4)}
+            "frames_per_s": round(1.0 / dt, 4)}
     print(json.dumps(line), file=out, flush=True)
 
 
@@ -220,6 +251,29 @@ def native_frontend_probe(name: str, calls_np):
             "threads": min(16, os.cpu_count() or 1), "records_equal_benchmark_stream": bool(same)}
 
 
+def executed_view(name: str, world: int, shade_ms: float, sm_mhz: float):
+    """What the hardware executed for the dominant kernel, from the committed ncu --set full summary of this kernel
+    (profiles/shade_ncu_summary.json: which commit, which command).  NOT measured in this run -- ncu cannot run inside a
+    timed benchmark -- and labelled so; the live part is `issue_slots_per_cycle_live`: the stored instruction count over
+    this run's kernel time and clock."""
+    p = os.path.join(ROOT, "profiles", "shade_ncu_summary.json")
+    if name != "cfg5_4k" or world != 1 or not os.path.exists(p):
+        return None, None, None
+    s = json.load(open(p))
+    inst = float(s["warp_instructions"])
+    cycles = shade_ms * 1e-3 * sm_mhz * 1e6
+    ex = {"source": f"stored ncu --set full capture, {s['source']}", "captured_at_commit": s.get("commit"),
+          "warp_instructions": inst, "issue_slots_per_cycle_ncu": s.get("issue_active"),
+          "pipe_fma_pct_of_peak": s.get("pipe_fma_pct"), "pipe_alu_pct_of_peak": s.get("pipe_alu_pct"),
+          "pipe_xu_pct_of_peak": s.get("pipe_xu_pct"), "kernel_us_under_ncu": s.get("duration_us"),
+          # 4 schedulers per SM issue at most one warp instruction per cycle each
+          "issue_slots_per_cycle_live": round(inst / (cycles * 148 * 4), 4) if cycles > 0 else None,
+          "frac_executed": round(float(s.get("pipe_fma_pct") or 0.0) / 100.0, 4),
+          "note": "frac_executed = share of the FP32 (FMA) pipe's issue capacity the kernel used under ncu; the kernel is "
+                  "issue/latency-bound, the algorithmic `frac` above counts fragments it legitimately skips"}
+    return ex, s.get("traffic_bytes_per_launch"), f"stored: dram__bytes_read.sum + dram__bytes_write.sum of one launch, {s['source']}"
+
+
 def _claim_stdout():
     """Libraries (NCCL's version banner, torchrun warnings) print to fd 1; the driver wants ONE JSON line there.
     Point fd 1 at stderr for the run and keep the real stdout for the final line."""
@@ -229,62 +283,59 @@ def _claim_stdout():
     return real
 
 
-def main():
-    real_stdout = _claim_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours")
-    ap.add_argument("--workload", default=None)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="nccl", choices=["p2p", "nccl", "ce"],
-                    help="N>1: NCCL all-gather of the bands (nccl), fused peer stores from the shade kernel (p2p), or copy "
-                         "engines shipping finished band slices to the peers while the next slice is shaded (ce)")
-    ap.add_argument("--sub-bands", type=int, default=4)
-    ap.add_argument("--records", default=None, choices=["compact", "full"],
-                    help="e2e upload: 64-byte fdc_rect64 records for rounded rects with circular corners, or 128-byte fdc_call only")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
+class Env:
+    """torch / torch.distributed state shared by the measurements of one bench.py process."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    def __init__(self, args):
+        import torch
 
-    if args.impl == "reference":
-        run_reference(args, rank, real_stdout)
-        return
+        self.torch = torch
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.dev = torch.device("cuda", self.local_rank)
+        torch.cuda.set_device(self.dev)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
 
-    import torch
-    import __graft_entry__ as ge
+            dist.init_process_group("nccl", device_id=self.dev)
+            dist.barrier()
+            self.dist = dist
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
 
-    if rank == 0:
-        ge.build()
-    if world > 1:
-        import torch.distributed as dist
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist.barrier()
+    def max_over_ranks(self, values):
+        if self.dist is None:
+            return [float(v) for v in values]
+        t = self.torch.tensor(list(values), device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+
+def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
+    """One workload on env.world GPUs.  Returns a dict of raw results on every rank (values reduced to max over ranks)."""
+    torch, dist, args = env.torch, env.dist, env.args
+    rank, world, dev = env.rank, env.world, env.dev
+    from figdraw_b200 import bands
     from figdraw_b200.cuda_context import CudaContext, prepare_calls, prepared_upload_bytes
 
-    name = args.workload or ("cfg5_4k" if world == 1 else "cfg5_8k")
-    trace, desc = workload_trace(name)
+    trace, _desc = workload_trace(name)
     W, H = trace.width, trace.height
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-
-    ctx = CudaContext(atlasSize=trace.atlas_size, device=local_rank, rank=rank, nRanks=world)
+    ctx = CudaContext(atlasSize=trace.atlas_size, device=env.local_rank, rank=rank, nRanks=world)
     for _i, key, img in trace.images:
         ctx.putImage(key, img)
-
-    from figdraw_b200 import bands
-
     band_rows, _layout = bands.band_layout(H, world)
     # a backdrop blur under a band partition reads halo rows out of the neighbours' framebuffers: peer mappings needed
     has_blur = bool((trace.calls["op"] == 13).any())
     use_p2p = world > 1 and (args.gather in ("p2p", "ce") or has_blur)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    token = None
     if use_p2p:
         # Fused all-gather: every rank's shade kernel stores its finished pixels into all peers' framebuffers over
         # NVLink (CUDA IPC mappings); a one-element NCCL all-reduce on the same stream is the completion barrier.
@@ -301,16 +352,13 @@ def main():
         # Framebuffer owned by torch so NCCL can all-gather the bands in place; rows padded to equal bands.
         fb = torch.zeros((band_rows * world, W, 4), dtype=torch.uint8, device=dev)
         ctx.bindFramebuffer(fb.data_ptr())
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     calls_host = torch.from_numpy(trace.calls.view(np.uint8).reshape(-1, 128).copy()).pin_memory()
     calls_np = calls_host.numpy().view(trace.calls.dtype).reshape(-1)
     out_host = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
     out_np = out_host.numpy()
     keep_pinned = []
-    # upload format of the e2e arm: compact records on one GPU (validated there, profiles/r01_e2e_records.md); the
-    # multi-GPU runs keep the plain 128-byte records unless asked otherwise
-    records = args.records or ("compact" if world == 1 else "full")
+    records = args.records or "compact"
 
     def prepare_pinned(calls_pinned_np):
         """Run boundaries computed once (a host that emits the calls knows them); rounded rects with circular corners go
@@ -329,36 +377,37 @@ def main():
     prepared = prepare_pinned(calls_np)
 
     def gather():
+        if world == 1:
+            return
         if use_p2p:
             dist.all_reduce(token)  # all ranks' shade kernels (and their peer stores) are complete after this
         else:
             bands.allgather_bands(fb, rank, world)
 
+    def submit(c, prep):
+        c.beginFrame((W, H), clearMain=trace.clear is not None, clearMainColor=trace.clear or (1, 1, 1, 1))
+        c.submitPrepared(prep)
+        c.endFrame()
+
     def frame_e2e():
-        ctx.beginFrame((W, H), clearMain=trace.clear is not None, clearMainColor=trace.clear or (1, 1, 1, 1))
-        ctx.submitPrepared(prepared)
-        ctx.endFrame()
+        submit(ctx, prepared)
         with torch.cuda.stream(stream):
             gather()
         y0, y1 = ctx.bandRows() if world > 1 else (0, H)
         ctx.readPixels((0, y0, W, y1 - y0), out=out_np[y0:y1])
 
-    # first frame: uploads the recording, allocates everything
+    # first frame: uploads the recording, allocates everything; a bin-list overflow on ANY rank re-runs it on all
+    submit(ctx, prepared)
+    bands.resolve_across_ranks(ctx, world, dist)
     frame_e2e()
-    st = ctx.frameStats()
-    launches_per_frame = int(st.n_launches)
+    launches_per_frame = int(ctx.frameStats().n_launches)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed_loop(fn_step, steps):
+    def timed_loop(fn_step, n):
         """Each step individually bracketed by CUDA events on the context stream; L2 flushed between steps."""
         evs = []
-        for _ in range(steps):
+        for _ in range(n):
             with torch.cuda.stream(stream):
-                flush.fill_(0)
+                env.flush.fill_(0)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
                 fn_step()
@@ -371,25 +420,25 @@ def main():
         ctx.replayFrame()
         gather()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_resident()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    env.barrier()
+    sampler = ClockSampler(env.local_rank) if (headline and rank == 0) else None
+    if sampler:
         sampler.start()
-    barrier()
-    times = timed_loop(step_resident, args.steps)
-    barrier()
+    env.barrier()
+    times = timed_loop(step_resident, steps)
+    env.barrier()
     stats = ctx.frameStats()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_step = float(np.sum(times)) / args.steps
+    clocks = sampler.stop() if sampler else None
+    ms_step = float(np.sum(times)) / steps
 
     # e2e: host records in, host pixels out, wall clock bracketed by synchronisation (copies are inside)
     for _ in range(2):
         frame_e2e()
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(5, min(args.steps, 20))
+    e2e_steps = max(5, min(steps, 20))
     for _ in range(e2e_steps):
         frame_e2e()
     torch.cuda.synchronize()
@@ -397,14 +446,13 @@ def main():
 
     # e2e, pipelined (N = 1): three contexts on three streams, like a three-image swap chain.  Every step still copies
     # its own records host->device and its own frame device->host; in steady state frame k's readback, frame k+1's
-    # kernels and frame k+2's upload are in flight together.  Throughput over the steps, not latency.  (Measured: deeper
-    # rings and fdc_read_pixels_async change nothing -- 33 MB down + 31 MB up per frame is what PCIe sustains in ~0.96 ms.)
-    e2e_pipe_ms = None
-    if world == 1:
+    # kernels and frame k+2's upload are in flight together.  Throughput over the steps, not latency.
+    e2e_pipe_ms, depth = None, 1
+    if world == 1 and headline:
         ring = [(ctx, prepared, out_np)]
         extra_ctx = []
         for _ in range(max(1, int(os.environ.get("FDC_E2E_RING", "3")) - 1)):
-            c2 = CudaContext(atlasSize=trace.atlas_size, device=local_rank)
+            c2 = CudaContext(atlasSize=trace.atlas_size, device=env.local_rank)
             for _i, key, img in trace.images:
                 c2.putImage(key, img)
             o2 = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
@@ -413,16 +461,11 @@ def main():
             extra_ctx.append((c2, o2, k2))
         depth = len(ring)
 
-        def submit(c, calls):
-            c.beginFrame((W, H), clearMain=trace.clear is not None, clearMainColor=trace.clear or (1, 1, 1, 1))
-            c.submitPrepared(calls)
-            c.endFrame()
-
-        def pipelined(steps):
-            for k in range(min(depth - 1, steps)):
+        def pipelined(n):
+            for k in range(min(depth - 1, n)):
                 submit(ring[k % depth][0], ring[k % depth][1])
-            for k in range(steps):
-                if k + depth - 1 < steps:
+            for k in range(n):
+                if k + depth - 1 < n:
                     nxt = ring[(k + depth - 1) % depth]
                     submit(nxt[0], nxt[1])
                 cur = ring[k % depth]
@@ -434,62 +477,93 @@ def main():
         pipelined(e2e_steps)
         torch.cuda.synchronize()
         e2e_pipe_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        same = all(bool(np.array_equal(out_np, r[2])) for r in ring[1:])
-        if not same:
+        if not all(bool(np.array_equal(out_np, r[2])) for r in ring[1:]):
             raise SystemExit("pipelined contexts produced different frames")
         for c2, _o, _k in extra_ctx:
             c2.close()
 
-    gathered_ok = None
-    if world > 1 and rank == 0:
+    gathered_ok, single_gpu_ms = None, None
+    if world > 1:
         # the gathered frame on rank 0 must equal a single-context render of the whole frame, bit for bit
         ctx.replayFrame()
         with torch.cuda.stream(stream):
             gather()
         torch.cuda.synchronize()
-    if world > 1 and rank != 0:
-        ctx.replayFrame()
-        with torch.cuda.stream(stream):
-            gather()
-        torch.cuda.synchronize()
-    if world > 1 and rank == 0:
-        import ctypes
+        if rank == 0:
+            whole = np.empty((H, W, 4), dtype=np.uint8)
+            if use_p2p:
+                ctx._ck(ctx._lib.fdc_read_pixels(ctx._h, 0, 0, W, H, whole.ctypes.data))
+            else:
+                whole[:] = fb[:H].cpu().numpy()
+            ref_ctx = CudaContext(atlasSize=trace.atlas_size, device=env.local_rank)
+            for _i, key, img in trace.images:
+                ref_ctx.putImage(key, img)
+            submit(ref_ctx, prepared)
+            gathered_ok = bool(np.array_equal(ref_ctx.readPixels(), whole))
+            # the same frame on ONE GPU (this rank's), timed in the same process
+            single_ms = []
+            for _ in range(9):
+                env.flush.fill_(0)
+                torch.cuda.synchronize()
+                ref_ctx.replayFrame()
+                single_ms.append(float(ref_ctx.frameStats().gpu_ms))
+            single_gpu_ms = float(np.median(single_ms[2:]))
+            ref_ctx.close()
+        env.barrier()
+    ms_step, e2e_ms, shade_ms, bin_ms = env.max_over_ranks([ms_step, e2e_ms, stats.shade_ms, stats.bin_ms])
+    res = {"name": name, "trace": trace, "W": W, "H": H, "ms_step": ms_step, "e2e_ms": e2e_ms, "e2e_pipe_ms": e2e_pipe_ms,
+           "depth": depth, "shade_ms": shade_ms, "bin_ms": bin_ms, "clocks": clocks, "launches_per_frame": launches_per_frame,
+           "n_tile_entries": int(stats.n_tile_entries), "h2d": int(prepared_upload_bytes(prepared)), "out_np": out_np,
+           "calls_np": calls_np, "gathered_ok": gathered_ok, "single_gpu_ms": single_gpu_ms, "use_p2p": use_p2p,
+           "gather": "p2p" if (use_p2p and args.gather == "nccl") else args.gather}
+    ctx.close()
+    return res
 
-        whole = np.empty((H, W, 4), dtype=np.uint8)
-        if use_p2p:
-            ctx._ck(ctx._lib.fdc_read_pixels(ctx._h, 0, 0, W, H, whole.ctypes.data))
-        else:
-            whole[:] = fb[:H].cpu().numpy()
-        ref_ctx = CudaContext(atlasSize=trace.atlas_size, device=local_rank)
-        for _i, key, img in trace.images:
-            ref_ctx.putImage(key, img)
-        ref_ctx.beginFrame((W, H), clearMain=trace.clear is not None, clearMainColor=trace.clear or (1, 1, 1, 1))
-        ref_ctx.submitCalls(calls_np)
-        ref_ctx.endFrame()
-        gathered_ok = bool(np.array_equal(ref_ctx.readPixels(), whole))
-        # the same frame on ONE GPU, measured here so that a strong-scaling ratio for this workload can be formed
-        # (the N = 1 bench line runs the 4K target frame, BASELINE's multi-GPU config is the 8K one)
-        single_ms = []
-        for _ in range(7):
-            flush.fill_(0)
-            torch.cuda.synchronize()
-            ref_ctx.replayFrame()
-            single_ms.append(float(ref_ctx.frameStats().gpu_ms))
-        single_gpu_ms = float(np.median(single_ms[2:]))
-        ref_ctx.close()
-    if world > 1:
-        t = torch.tensor([ms_step, e2e_ms, stats.shade_ms, stats.bin_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, e2e_ms, shade_ms, bin_ms = (float(v) for v in t.tolist())
-    else:
-        shade_ms, bin_ms = float(stats.shade_ms), float(stats.bin_ms)
+
+def main():
+    real_stdout = _claim_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-8k", action="store_true", help="N > 1: skip the extra cfg5_8k measurement")
+    ap.add_argument("--gather", default="nccl", choices=["p2p", "nccl", "ce"],
+                    help="N>1: NCCL all-gather of the bands (nccl), fused peer stores from the shade kernel (p2p), or copy "
+                         "engines shipping finished band slices to the peers while the next slice is shaded (ce)")
+    ap.add_argument("--sub-bands", type=int, default=4)
+    ap.add_argument("--records", default=None, choices=["compact", "full"],
+                    help="e2e upload: 64-byte fdc_rect64 records for rounded rects with circular corners, or 128-byte fdc_call only")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, real_stdout)
+        return
+
+    import __graft_entry__ as ge
 
     if rank == 0:
+        ge.build()
+    env = Env(args)
+    world = env.world
+    name = args.workload or "cfg5_4k"
+    r = measure(env, name, args.steps, args.warmup, headline=True)
+    extra_8k = None
+    if world > 1 and args.workload is None and not args.no_8k:
+        extra_8k = measure(env, "cfg5_8k", max(5, min(args.steps, 20)), 3, headline=False)
+
+    if rank == 0:
+        trace, W, H = r["trace"], r["W"], r["H"]
+        ms_step, shade_ms, bin_ms, clocks = r["ms_step"], r["shade_ms"], r["bin_ms"], r["clocks"]
         peaks, peak_src = measured_peaks()
         mpx = W * H / 1e6
         value = mpx / (ms_step * 1e-3)
         # roofline of the dominant kernel (shade): algorithmic flops from the oracle's exact fragment counts
-        cpu_base, roof = None, None
+        cpu_base = None
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         peak_fp32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s per GPU, non-tensor FP32 at the clock seen under load
         from oracle import oracle as orc
@@ -497,17 +571,16 @@ def main():
         counts = orc.count_fragments(trace)  # exact fragments per mode (checker; counts only, nothing is shaded)
         n_frag = int(counts.sum())
         flops = algorithmic_flops(counts)
-        bytes_alg = W * H * 4 + trace.n_draws * 128 * 2 + int(stats.n_tile_entries) * 4 * world
+        bytes_alg = W * H * 4 + trace.n_draws * 128 * 2 + r["n_tile_entries"] * 8 * world
         ach = flops / (shade_ms * 1e-3) / 1e12 / world  # per GPU: every rank shades 1/world of the frame in shade_ms
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_shade_traffic.json")
-        if name == "cfg5_4k" and world == 1 and os.path.exists(tp):
-            traffic = json.load(open(tp)).get("traffic_bytes_per_launch")  # dram read+write from the ncu --set full capture
+        executed, traffic, traffic_src = executed_view(name, world, shade_ms, sm_mhz)
         roof = {"bound": "fp32", "kernel": "shade_kernel", "achieved": round(ach, 3), "peak": round(peak_fp32, 2),
-                "unit": "TFLOP/s", "frac": round(ach / peak_fp32, 4), "traffic": traffic,
+                "unit": "TFLOP/s", "frac": round(ach / peak_fp32, 4), "traffic": traffic, "traffic_source": traffic_src,
+                "definition": "ALGORITHMIC (SURVEY 8d): every fragment the reference's GL path would shade x flops per fragment "
+                              "by mode / shade-kernel time; the kernel provably skips occluded and trivially covered fragments, "
+                              "so this is not a utilisation figure (it can exceed 1) -- see `executed`",
+                "executed": executed,
                 "algorithmic_flops_per_frame": flops, "fragments_per_frame": n_frag,
-                "note": "algorithmic = every fragment the reference's GL path would shade; the kernel provably skips "
-                        "occluded and trivially covered ones, so this can exceed what is executed (see profiles/)",
                 "peak_source": f"148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (SM clock sampled during the timed region), per GPU",
                 "shade_ms": round(shade_ms, 4), "bin_ms": round(bin_ms, 4),
                 "hbm": {"algorithmic_bytes": bytes_alg, "achieved_gbs": round(bytes_alg / (ms_step * 1e-3) / 1e9 / world, 1),
@@ -522,40 +595,44 @@ def main():
             t0 = time.perf_counter()
             ref_img = o.render(W, H, trace.calls, clear=trace.clear, n_threads=cores)
             cpu_s = time.perf_counter() - t0
-            d = np.abs(out_np.astype(np.int16) - ref_img.astype(np.int16)).max(axis=2)
+            d = np.abs(r["out_np"].astype(np.int16) - ref_img.astype(np.int16)).max(axis=2)
             cpu_base = {"value": round(mpx / cpu_s, 3), "unit": METRIC, "cores": cores, "kind": "port",
                         "sample": f"1 full frame of the same scene ({W}x{H}, {n_frag} fragments) in {cpu_s:.2f} s"}
             roof["parity_vs_oracle"] = {"max_abs_diff_lsb": int(d.max()), "pixels_differing": int((d > 0).sum())}
-        h2d = int(prepared_upload_bytes(prepared))
-        d2h = int(W * H * 4)
+        e2e_best = r["e2e_pipe_ms"] or r["e2e_ms"]
         line = {"metric": METRIC, "value": round(value, 2), "unit": METRIC, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "frame": [W, H], "primitives": trace.n_draws, "l2": "flushed between steps (256 MiB fill)",
-                           "partition": "single GPU" if world == 1 else (
-                               (f"{world} tile-row bands, finished band slices copied to the peers by the copy engines (NVLink) while "
-                                "the next slice is shaded" if args.gather == "ce" else
-                                f"{world} tile-row bands, band all-gather fused into the shade kernel (peer stores over NVLink)")
-                               if use_p2p else f"{world} tile-row bands + NCCL all-gather")},
+                "config": bench_config(name, trace, world, r["gather"]),
                 "frames_per_s": round(1e3 / ms_step, 2),
-                "e2e": {"value": round(mpx / ((e2e_pipe_ms or e2e_ms) * 1e-3), 2), "unit": METRIC,
-                        "ms_per_step": round(e2e_pipe_ms or e2e_ms, 4), "latency_ms": round(e2e_ms, 4),
-                        "mode": (f"{depth} contexts in flight: step k's readback, step k+1's kernels and step k+2's upload overlap"
-                                 if e2e_pipe_ms else "one frame at a time"),
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches_per_frame * args.steps, "launches_per_frame": launches_per_frame,
+                "e2e": {"value": round(mpx / (e2e_best * 1e-3), 2), "unit": METRIC,
+                        "ms_per_step": round(e2e_best, 4), "latency_ms": round(r["e2e_ms"], 4),
+                        "mode": (f"{r['depth']} contexts in flight: step k's readback, step k+1's kernels and step k+2's upload overlap"
+                                 if r["e2e_pipe_ms"] else "one frame at a time"),
+                        "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": int(W * H * 4)},
+                "gpu_launches": r["launches_per_frame"] * args.steps, "launches_per_frame": r["launches_per_frame"],
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base}
-        if gathered_ok is not None:
-            line["gathered_frame_equals_single_gpu"] = gathered_ok
-            line["single_gpu_same_workload"] = {"ms_per_step": round(single_gpu_ms, 4), "value": round(mpx / (single_gpu_ms * 1e-3), 2),
-                                                "unit": METRIC, "note": "this rank-0 GPU alone on the same frame (no gather); "
-                                                "value / (n_gpus x this) is the strong-scaling efficiency of the workload"}
+        if r["gathered_ok"] is not None:
+            line["gathered_frame_equals_single_gpu"] = r["gathered_ok"]
+            line["single_gpu_same_workload"] = {"ms_per_step": round(r["single_gpu_ms"], 4),
+                                                "value": round(mpx / (r["single_gpu_ms"] * 1e-3), 2), "unit": METRIC,
+                                                "note": "rank 0's GPU alone on the same frame in the same process (no gather)"}
+        if extra_8k is not None:
+            x = extra_8k
+            mpx8 = x["W"] * x["H"] / 1e6
+            line["cfg5_8k"] = {"workload": WORKLOADS["cfg5_8k"], "ms_per_step": round(x["ms_step"], 4),
+                               "value": round(mpx8 / (x["ms_step"] * 1e-3), 2), "unit": METRIC,
+                               "single_gpu_ms": round(x["single_gpu_ms"], 4),
+                               "efficiency": round(x["single_gpu_ms"] / (world * x["ms_step"]), 4),
+                               "shade_ms": round(x["shade_ms"], 4), "bin_ms": round(x["bin_ms"], 4),
+                               "e2e_ms_per_step": round(x["e2e_ms"], 4), "h2d_bytes_per_step": x["h2d"],
+                               "gathered_frame_equals_single_gpu": x["gathered_ok"],
+                               "note": "BASELINE configs[4] (all sizes x2) on the same ranks; efficiency = single_gpu_ms / (n_gpus x ms_per_step)"}
         if world == 1 and name in ("cfg5_4k", "cfg5_8k"):
-            line["native_frontend"] = native_frontend_probe(name, calls_np)
+            line["native_frontend"] = native_frontend_probe(name, r["calls_np"])
         print(json.dumps(line), file=real_stdout, flush=True)
-    ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    if env.dist is not None:
+        env.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

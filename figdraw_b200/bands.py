@@ -34,11 +34,30 @@ def allgather_bands(fb, rank: int, world: int, group=None) -> None:
 
     rows = fb.shape[0] // world
     band = fb[rank * rows:(rank + 1) * rows]
-    try:
-        dist.all_gather_into_tensor(fb, band, group=group)
-    except (RuntimeError, NotImplementedError):
-        parts = [fb[r * rows:(r + 1) * rows] for r in range(world)]
-        tmp = [p.clone() for p in parts]
-        dist.all_gather(tmp, band.clone(), group=group)
-        for p, t in zip(parts, tmp):
-            p.copy_(t)
+    dist.all_gather_into_tensor(fb, band, group=group)  # in place; supported by both NCCL and gloo -- no silent fallback
+
+
+def resolve_across_ranks(ctx, world: int, dist=None, group=None, max_rounds: int = 4) -> int:
+    """Wait for the frame in flight on every rank and agree on its fate.  A rank whose bin lists overflowed regrows them
+    and reports FDC_ERR_RETRY (6) instead of re-running privately (peers gathered / read rows of the aborted frame): the
+    statuses are max-reduced and, if any rank said retry, EVERY rank calls fdc_retry_frame -- same barrier sequence, same
+    pixels.  `ctx` needs syncStatus() and retryFrame() (CudaContext); returns the number of re-runs."""
+    rounds = 0
+    while True:
+        rc = int(ctx.syncStatus())
+        if world > 1:
+            import torch
+
+            if dist is None:
+                import torch.distributed as dist  # noqa: PLW0642
+            backend = dist.get_backend(group)
+            dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+            t = torch.tensor([rc], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            rc = int(t.item())
+        if rc != 6:
+            return rounds
+        if rounds >= max_rounds:
+            raise RuntimeError("bin lists still overflow after %d cross-rank retries" % rounds)
+        ctx.retryFrame()
+        rounds += 1

@@ -8,12 +8,14 @@
 //   order so the integer quad corners -- and therefore the bin lists -- are bit-exact against the oracle.
 //
 // Binning -- two levels, both tile-major so list order == emission order without sorting or atomics on order:
-//   coarse: the frame (band) is cut into 128x128-px bins; primitives into chunks of 1024.  count[chunk][bin]
-//           by warp ballot + popc over the chunk staged in shared memory, a column scan over chunks, then the
-//           same ballot loop scatters with prefix ranks (stable compaction).
-//   fine:   one CTA per coarse bin walks its list; warp w owns tile row w of the 8x8 tiles; per 32 entries one
-//           ballot per tile column.  Counts -> CTA scan -> one atomicAdd reserves the bin's slice of the tile
-//           list (slice placement is the only non-deterministic thing and is not observable) -> scatter.
+//   coarse: the frame (band) is cut into 128x128-px bins; primitives into chunks of 512 (16 warps x 32).  Every lane
+//           marks the bin-row words its primitive touches; per marked word ONE 32x32 bit transpose across the warp
+//           turns "bins per primitive" into "primitives per bin" (count = popc, stable rank = bit order).
+//           count[bin][chunk] -> row scan over chunks -> the same walk scatters (stable compaction, no sorting).
+//   fine:   one CTA per coarse bin stages its list 1024 entries at a time; each warp takes groups of 32 entries, two
+//           transposes give lane t the entries of tiles t and 32+t.  Counts -> CTA scan -> one atomicAdd reserves
+//           the bin's slice of the tile list (slice placement is the only non-deterministic thing and is not
+//           observable) -> the lanes write their tiles' 8-byte TileEntry records in bit order.
 #include <cuda_runtime.h>
 
 #include "fdc_kernels.h"
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
 
   Prim p;
   memset(&p, 0, sizeof(p));
-  uint32_t flags = rs.flags & (PF_MASK_WRITE | PF_MASK_BEGIN | PF_DEPTH_MASK);
+  uint32_t flags = rs.flags & (PF_MASK_WRITE | PF_MASK_BEGIN | PF_MASK_WIDE | PF_DEPTH_MASK);
   bool empty = false;
   QuadPos q;
   float atx = 0, aty = 0, tox = 0, toy = 0;
@@ -363,6 +365,10 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
     cy0 = max(cy0, a.frame.band_y0); cy1 = min(cy1, a.frame.band_y1);
     if (cx0 >= cx1 || cy0 >= cy1) empty = true;
     p.bx0 = (int16_t)cx0; p.by0 = (int16_t)cy0; p.bx1 = (int16_t)cx1; p.by1 = (int16_t)cy1;
+    if (flags & PF_MASK_WIDE) {
+      // own clipped bbox for the slow path's inside test (shade_prim); the bin bbox is widened below
+      p.ix0 = (int16_t)cx0; p.iy0 = (int16_t)cy0; p.ix1 = (int16_t)cx1; p.iy1 = (int16_t)cy1;
+    }
 
     if (!empty) {
       p.aa = rs.aa;
@@ -488,12 +494,31 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
       }
     }
   }
-  if (empty) {
+  // First draw of a mask level that holds several draws: GL cleared the whole mask texture at beginMask
+  // (glcontext.nim:1901-1902) and content under such a level is not clipped to one primitive's bbox, so the level
+  // must read 0 wherever none of its draws lands -- bin this primitive over the parent's whole clip box.
+  int wx0 = 0, wy0 = 0, wx1 = 0, wy1 = 0;
+  const bool wide = (rs.flags & PF_MASK_WIDE) != 0;
+  if (wide) {
+    wx0 = 0; wx1 = a.frame.W; wy0 = a.frame.band_y0; wy1 = a.frame.band_y1;
+    apply_clip_chain(a, rs.clip_draw, wx0, wy0, wx1, wy1);
+  }
+  if (empty && wide && wx0 < wx1 && wy0 < wy1) {
+    memset(&p, 0, sizeof(p));
+    flags = (rs.flags & (PF_MASK_WRITE | PF_MASK_BEGIN | PF_MASK_WIDE | PF_DEPTH_MASK)) | PF_CLEAR_ONLY | (uint32_t)FDC_SDF_CLIP_AA;
+    p.bx0 = (int16_t)wx0; p.by0 = (int16_t)wy0; p.bx1 = (int16_t)wx1; p.by1 = (int16_t)wy1;
+  } else if (empty) {
     flags = PF_EMPTY;
     p.bx0 = p.by0 = p.bx1 = p.by1 = 0;
   } else {
     flags |= (uint32_t)mode & PF_MODE_MASK;
     flags |= ((uint32_t)fill_mode << PF_FILLMODE_SHIFT) & PF_FILLMODE_MASK;
+    if (wide) {
+      if (flags & PF_INNER) {
+        // fast mask write: ix0..iy1 hold the inner rect and the fast path tests the quad in SDF space -- keep both
+      }
+      p.bx0 = (int16_t)wx0; p.by0 = (int16_t)wy0; p.bx1 = (int16_t)wx1; p.by1 = (int16_t)wy1;
+    }
   }
   p.mode_flags = flags;
   a.prims[i] = p;
@@ -719,7 +744,8 @@ __global__ void __launch_bounds__(256) coarse_scan_kernel(uint32_t* __restrict__
   if (threadIdx.x == 0) {
     cbin_start[0] = 0;
     counters[2] = carry;
-    if (carry > coarse_cap) atomicOr(&counters[1], 1u);
+    atomicMax(&counters[5], carry);  // per-frame maximum over segments (resolve_frame regrows from it)
+    if (carry > coarse_cap) { atomicOr(&counters[1], 1u); atomicOr(&counters[4], 1u); }
   }
 }
 
@@ -877,7 +903,9 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
         if (lane == 31) {
           const uint32_t tot = incl;
           const uint32_t at = atomicAdd(&counters[0], tot);
-          if (at + tot > tile_cap) { atomicOr(&counters[1], 2u); s_alloc = 0xFFFFFFFFu; }
+          atomicMax(&counters[6], at + tot);  // per-frame maximum of the tile-list size a segment needs
+          atomicAdd(&counters[7], tot);       // tile entries of the whole frame (statistics)
+          if (at + tot > tile_cap) { atomicOr(&counters[1], 2u); atomicOr(&counters[4], 2u); s_alloc = 0xFFFFFFFFu; }
           else s_alloc = at;
         }
       }
@@ -988,7 +1016,9 @@ void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& f, con
                     int* n_launches) {
   const int n_bins = f.cbx * f.cby;
   const int n_chunks = (int)((n_prims + kChunk - 1) / kChunk);
-  // tiles of the band start empty; counters: tile cursor, overflow flags, coarse total, scan ticket
+  // tiles of the band start empty; per-segment counters: tile cursor, overflow flags, coarse total, scan ticket.
+  // counters[4..7] are per FRAME (sticky overflow flags, maxima of the list sizes, total entries): the caller zeroes
+  // them once per frame, so an overflow in any segment is still visible after later segments reset [0..3].
   cudaMemsetAsync(b.tile_count + (size_t)f.ty0 * f.tiles_x, 0, sizeof(uint32_t) * (size_t)(f.ty1 - f.ty0) * f.tiles_x, stream);
   cudaMemsetAsync(b.counters, 0, sizeof(uint32_t) * 4, stream);
   if (n_prims == 0 || n_bins == 0) return;

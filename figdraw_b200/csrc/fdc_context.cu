@@ -180,6 +180,7 @@ struct MaskLevel {
   std::vector<RunState> states;  // their run states (first_draw rewritten on emission)
   int32_t mask_draw = -1;        // draw index of the single clipping primitive, or -1 when not usable as a clip
   int32_t clip = -1;             // clip_draw for content at this level
+  int32_t first_run = -1;        // index in ctx->runs of the first mask draw's run (patched to PF_MASK_WIDE when a second draw arrives)
 };
 
 struct RectMaskEntry {
@@ -253,6 +254,10 @@ struct fdc_ctx {
   DevBuf<uint32_t> d_chunk_counts, d_cbin_start, d_coarse_list, d_tile_start, d_tile_count, d_counters;
   DevBuf<TileEntry> d_tile_list;
   DevBuf<uint8_t> d_fb, d_backdrop, d_temp;
+  DevBuf<uint8_t> d_snapshot;      // pre-frame pixels of a multi-segment frame without clearMain (restored before an overflow replay)
+  bool snapshot_valid = false;
+  bool frame_resolved = false;     // resolve_frame has already checked the frame in flight
+  uint32_t dbg_coarse_limit = 0, dbg_tile_limit = 0;  // fdc_debug_limit_lists: pretend the bin lists are this small (0: real size)
   uint8_t* ext_fb = nullptr;
   DevBuf<uint8_t*> d_peers;
   DevBuf<fdc_rect64> d_rects64;    // compact draw records of this frame (fdc_submit_rects64)
@@ -468,9 +473,22 @@ bool stage_draw(fdc_ctx* ctx, const fdc_call& d) {
   return true;
 }
 
+// The early-outs the reference takes before a quad is emitted (glcontext.nim:1463-1464, :1631-1632, :1305-1310).  The
+// device drops such records anyway; between beginMask and endMask the host must not count them as mask draws either.
+bool draws_nothing(fdc_ctx* ctx, const fdc_call& d) {
+  switch (d.op) {
+    case FDC_OP_ROUNDED_RECT: return d.f[2] <= 0.0f || d.f[3] <= 0.0f;
+    case FDC_OP_BEZIER: return d.f[2] <= 0.0f || d.f[3] <= 0.0f || d.f[10] <= 0.0f;
+    case FDC_OP_IMAGE:
+    case FDC_OP_MSDF: return ctx->entries.count((uint64_t)d.u[0] | ((uint64_t)d.u[1] << 32)) == 0;
+    default: return false;
+  }
+}
+
 // Appends one draw record under the current backend state.
 int add_draw(fdc_ctx* ctx, const fdc_call& d, uint32_t ordinal) {
   if (!ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "draw outside beginFrame/endFrame");
+  if (ctx->mask_begun && draws_nothing(ctx, d)) return FDC_OK;
   const uint32_t idx = ctx->n_draws;
   if (ctx->xform_dirty) current_xform(ctx);
   const bool consecutive = ctx->runs.n > 0 && ordinal == ctx->last_draw_ordinal + 1;
@@ -490,8 +508,19 @@ int add_draw(fdc_ctx* ctx, const fdc_call& d, uint32_t ordinal) {
     MaskLevel& ml = ctx->mask_levels[ctx->mask_write];
     ml.draws.push_back(d);
     ml.states.push_back(ctx->runs.p[ctx->runs.n - 1]);
-    if (ml.draws.size() == 1 && d.op == FDC_OP_ROUNDED_RECT) ml.mask_draw = (int32_t)idx;
-    else ml.mask_draw = -1;
+    if (ml.draws.size() == 1) ml.first_run = (int32_t)ctx->runs.n - 1;
+    if (ml.draws.size() == 1 && d.op == FDC_OP_ROUNDED_RECT) {
+      ml.mask_draw = (int32_t)idx;
+    } else {
+      // The level cannot be used as a clip box (several mask draws, or a shape that is not a rounded rect): content under
+      // it is binned everywhere, so the level must read 0 wherever no mask draw lands -- GL cleared the whole mask
+      // texture at beginMask (glcontext.nim:1901-1902).  The first draw carries that clear over the parent's clip box.
+      ml.mask_draw = -1;
+      if (ml.first_run >= 0 && !(ctx->runs.p[ml.first_run].flags & PF_MASK_WIDE)) {
+        ctx->runs.p[ml.first_run].flags |= PF_MASK_WIDE;
+        ml.states[0].flags |= PF_MASK_WIDE;
+      }
+    }
   }
   return FDC_OK;
 }
@@ -513,6 +542,7 @@ int begin_mask_impl(fdc_ctx* ctx, const float rect[4], const float rx[4], const 
   ml.draws.clear();
   ml.states.clear();
   ml.mask_draw = -1;
+  ml.first_run = -1;
   ml.clip = ctx->mask_levels[ctx->mask_write - 1].clip;
   ctx->state_dirty = true;
   ctx->begin_pending = true;
@@ -525,21 +555,18 @@ int begin_mask_impl(fdc_ctx* ctx, const float rect[4], const float rx[4], const 
   c.u[0] = FDC_SDF_CLIP_AA;
   c.u[1] = FDC_FILL_COLOR;
   c.u[3] = 0xFF0000FFu;
-  if (rect[2] <= 0.0f || rect[3] <= 0.0f) {
-    // the quad is dropped (early-out) but the level was still cleared: everything under it is invisible.
-    // Emit a zero-sized record so the level exists; its empty bbox clips all content away.
-    ml.clip = -2;  // "clip to nothing"
-    ctx->begin_pending = false;
-    return FDC_OK;
-  }
+  // A zero-sized clip rect is dropped (early-out, glcontext.nim:1463-1464) but the level was still cleared: the next mask
+  // draw, if any, carries the clear; a level that ends without a draw clips everything away (end_mask_impl).
   return add_draw(ctx, c, ordinal);
 }
 
 int end_mask_impl(fdc_ctx* ctx) {
   if (!ctx->mask_begun) return ctx->fail(FDC_ERR_STATE, "ctx.maskBegun has not been called.");
   ctx->mask_begun = false;
+  ctx->begin_pending = false;
   MaskLevel& ml = ctx->mask_levels[ctx->mask_write];
-  if (ml.clip != -2 && ml.mask_draw >= 0) ml.clip = ml.mask_draw;
+  if (ml.draws.empty()) ml.clip = -2;  // cleared and never drawn: "clip to nothing"
+  else if (ml.mask_draw >= 0) ml.clip = ml.mask_draw;
   ctx->state_dirty = true;
   return FDC_OK;
 }
@@ -629,7 +656,7 @@ int ensure_bin_buffers(fdc_ctx* ctx, uint32_t max_prims) {
   CK(ctx->d_cbin_start.reserve(n_bins + 1));
   CK(ctx->d_tile_start.reserve((size_t)f.tiles_x * f.tiles_y));
   CK(ctx->d_tile_count.reserve((size_t)f.tiles_x * f.tiles_y));
-  CK(ctx->d_counters.reserve(4));
+  CK(ctx->d_counters.reserve(8));
   CK(ctx->d_coarse_list.reserve(std::max<size_t>((size_t)max_prims * 3 + n_bins * 4, 1u << 16)));
   CK(ctx->d_tile_list.reserve(std::max<size_t>((size_t)max_prims * 24 + (size_t)f.tiles_x * f.tiles_y * 2, 1u << 20)));
   return FDC_OK;
@@ -642,10 +669,12 @@ BinBuffers bin_buffers(fdc_ctx* ctx) {
   b.cbin_start = ctx->d_cbin_start.p;
   b.coarse_list = ctx->d_coarse_list.p;
   b.coarse_cap = (uint32_t)std::min<size_t>(ctx->d_coarse_list.cap, 0xFFFFFFF0u);
+  if (ctx->dbg_coarse_limit) b.coarse_cap = std::min(b.coarse_cap, ctx->dbg_coarse_limit);
   b.tile_start = ctx->d_tile_start.p;
   b.tile_count = ctx->d_tile_count.p;
   b.tile_list = ctx->d_tile_list.p;
   b.tile_cap = (uint32_t)std::min<size_t>(ctx->d_tile_list.cap, 0xFFFFFFF0u);
+  if (ctx->dbg_tile_limit) b.tile_cap = std::min(b.tile_cap, ctx->dbg_tile_limit);
   b.counters = ctx->d_counters.p;
   return b;
 }
@@ -676,8 +705,9 @@ int ensure_copy_streams(fdc_ctx* ctx) {
   return FDC_OK;
 }
 
-// Launches every kernel of the recorded frame.  `upload`: copy the recording to the device first.
-int execute_frame(fdc_ctx* ctx, bool upload) {
+// Launches every kernel of the recorded frame.  `upload`: copy the recording to the device first.  `retry`: the frame is
+// being re-run because a bin list overflowed -- pixels a first attempt may already have blended are restored first.
+int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
   cudaStream_t st = ctx->stream;
   const uint32_t n_draws = ctx->n_draws;
   int rc = sync_table(ctx);
@@ -721,6 +751,23 @@ int execute_frame(fdc_ctx* ctx, bool upload) {
   if (any_blur) {
     CK(ctx->d_backdrop.reserve(fb_bytes));
     CK(ctx->d_temp.reserve(fb_bytes));
+  }
+  // Per-frame counters (sticky overflow flags, list-size maxima, entry total): zeroed once here; launch_binning resets
+  // only the per-segment words, so an overflow in ANY segment is still visible when the host looks after the frame.
+  CK(cudaMemsetAsync(ctx->d_counters.p + 4, 0, sizeof(uint32_t) * 4, st));
+  ctx->frame_resolved = false;
+  // A frame that blends over the previous pixels (no clearMain) in several segments cannot simply be re-run after an
+  // overflow in a later segment -- the earlier segments would be composited twice.  Keep the pre-frame pixels.
+  if (!ctx->clear && ctx->segments.size() > 1) {
+    if (retry && ctx->snapshot_valid) {
+      CK(cudaMemcpyAsync(ctx->fb(), ctx->d_snapshot.p, fb_bytes, cudaMemcpyDeviceToDevice, st));
+    } else if (!retry) {
+      CK(ctx->d_snapshot.reserve(fb_bytes));
+      CK(cudaMemcpyAsync(ctx->d_snapshot.p, ctx->fb(), fb_bytes, cudaMemcpyDeviceToDevice, st));
+      ctx->snapshot_valid = true;
+    }
+  } else if (!retry) {
+    ctx->snapshot_valid = false;
   }
   ctx->frame_barrier_base = ctx->barrier_seq;
   const bool banded_blur = ctx->n_ranks > 1 && any_blur;
@@ -861,15 +908,18 @@ int execute_frame(fdc_ctx* ctx, bool upload) {
   return FDC_OK;
 }
 
-// After a frame: wait, and if a bin list overflowed grow the lists and replay the frame once.
+// After a frame: wait, and if a bin list overflowed in any segment grow the lists and re-run the frame.  Under a
+// tile-band partition the re-run cannot be private to this rank (peers gathered or read rows of the aborted frame):
+// the lists are regrown and FDC_ERR_RETRY tells the host to call fdc_retry_frame on EVERY rank.
 int resolve_frame(fdc_ctx* ctx) {
   if (!ctx->have_frame) return FDC_OK;
-  for (int attempt = 0; attempt < 4; attempt++) {
+  for (int attempt = 0; attempt < 5; attempt++) {
     CK(cudaStreamSynchronize(ctx->stream));
-    uint32_t c[4] = {0, 0, 0, 0};
+    if (ctx->frame_resolved) return FDC_OK;
+    uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (!ctx->d_counters.p) return FDC_OK;
     CK(cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
-    ctx->stats.n_tile_entries = c[0];
+    ctx->stats.n_tile_entries = c[7];
     if (ctx->n_ranks > 1 && ctx->flag_off && ctx->barrier_seq != ctx->frame_barrier_base) {
       uint32_t late = 0;
       uint32_t* err = reinterpret_cast<uint32_t*>(ctx->d_fb.p + ctx->flag_off) + kFlagError;
@@ -880,16 +930,21 @@ int resolve_frame(fdc_ctx* ctx) {
         return ctx->fail(FDC_ERR_STATE, "blur halo barrier timed out waiting for rank mask 0x%x (did every rank submit the frame?)", late);
       }
     }
-    if (c[1] == 0) return FDC_OK;
-    // overflow: counters hold the required sizes (coarse total exact, tile cursor = total needed)
-    if (c[1] & 1u) CK(ctx->d_coarse_list.reserve((size_t)c[2] + (c[2] >> 2) + 1024));
-    if (c[1] & 2u) CK(ctx->d_tile_list.reserve((size_t)c[0] + (c[0] >> 2) + 1024));
-    // A private replay must not advance the cross-rank barrier sequence (the other ranks do not replay): it re-uses
-    // this frame's values, which the flags have already reached.  Blur halo rows then show the neighbours' current
-    // state; lists only overflow on the first frame of a much larger scene.
-    ctx->barrier_seq = ctx->frame_barrier_base;
+    if (c[4] == 0) {
+      ctx->frame_resolved = true;
+      return FDC_OK;
+    }
+    // overflow in some segment: c[5] / c[6] hold the largest coarse / tile list any segment needs
+    if (attempt == 4) break;
+    ctx->dbg_coarse_limit = ctx->dbg_tile_limit = 0;
+    if (c[4] & 1u) CK(ctx->d_coarse_list.reserve((size_t)c[5] + (c[5] >> 2) + 1024));
+    if (c[4] & 2u) CK(ctx->d_tile_list.reserve((size_t)c[6] + (c[6] >> 2) + 1024));
     ctx->n_replays++;
-    int rc = execute_frame(ctx, false);
+    if (ctx->n_ranks > 1) {
+      ctx->frame_resolved = true;  // checked; the verdict is "retry on every rank"
+      return ctx->fail(FDC_ERR_RETRY, "a bin list overflowed on rank %d; the lists were regrown -- call fdc_retry_frame on every rank", ctx->rank);
+    }
+    int rc = execute_frame(ctx, false, true);
     if (rc) return rc;
   }
   return ctx->fail(FDC_ERR_CAPACITY, "bin lists still overflow after regrowing");
@@ -983,7 +1038,7 @@ void fdc_destroy(fdc_ctx* ctx) {
   ctx->d_prims.release(); ctx->d_geoms.release(); ctx->d_exts.release(); ctx->d_prim_call.release();
   ctx->d_chunk_counts.release(); ctx->d_warp_counts.release(); ctx->d_cbin_start.release(); ctx->d_coarse_list.release();
   ctx->d_tile_start.release(); ctx->d_tile_count.release(); ctx->d_tile_list.release(); ctx->d_counters.release();
-  ctx->d_fb.release(); ctx->d_backdrop.release(); ctx->d_temp.release(); ctx->d_peers.release();
+  ctx->d_fb.release(); ctx->d_backdrop.release(); ctx->d_temp.release(); ctx->d_peers.release(); ctx->d_snapshot.release();
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   for (auto& cs : ctx->copy_streams) if (cs) cudaStreamDestroy(cs);
   for (auto& e : ctx->ev_sub) if (e) cudaEventDestroy(e);
@@ -1050,6 +1105,45 @@ int fdc_replay_frame(fdc_ctx* ctx) {
   if (!ctx->have_frame || ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "no completed frame to replay");
   CK(cudaSetDevice(ctx->device));
   return execute_frame(ctx, false);
+}
+
+// Re-runs the last frame on every rank of a tile-band partition after any rank's fdc_sync / fdc_read_pixels returned
+// FDC_ERR_RETRY (the host all-reduces the status).  Unlike fdc_replay_frame it restores pixels a first attempt already
+// blended; every rank runs the same cross-rank barrier sequence again, so blur halo rows are consistent.
+int fdc_retry_frame(fdc_ctx* ctx) {
+  if (!ctx) return FDC_ERR_INVALID;
+  if (!ctx->have_frame || ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "no completed frame to retry");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return execute_frame(ctx, false, true);
+}
+
+// Drops a frame that was begun but cannot be ended (a call in between failed): the recording, the mask / rect-mask
+// stacks and the transform stack are reset, the previous frame's pixels stay.  beginFrame may be called again.
+int fdc_abort_frame(fdc_ctx* ctx) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->frame_begun = false;
+  ctx->mask_begun = false;
+  ctx->begin_pending = false;
+  ctx->mask_write = 0;
+  ctx->rm_stack.clear();
+  ctx->mats.clear();
+  ctx->mat = mat_identity();
+  ctx->draws.n = ctx->runs.n = ctx->xforms.n = ctx->rectmasks.n = 0;
+  ctx->n_draws = 0;
+  ctx->n_rects64 = 0;
+  ctx->uploads.clear();
+  ctx->segments.clear();
+  ctx->state_dirty = ctx->xform_dirty = true;
+  ctx->have_frame = false;  // the resident recording was (partly) overwritten by direct uploads of the aborted frame
+  return FDC_OK;
+}
+
+int fdc_debug_limit_lists(fdc_ctx* ctx, uint32_t coarse_entries, uint32_t tile_entries) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->dbg_coarse_limit = coarse_entries;
+  ctx->dbg_tile_limit = tile_entries;
+  return FDC_OK;
 }
 
 static int enqueue_readback(fdc_ctx* ctx) {
@@ -1747,8 +1841,14 @@ int fdc_render_frame(fdc_ctx* ctx, const fdc_scene* scene, float ui_scale, float
   int rc = fdc_begin_frame(ctx, (int)(frame_w * ui_scale), (int)(frame_h * ui_scale), clear_main, clear_rgba);
   if (rc) return rc;
   rc = fdc_submit_calls(ctx, buf.p, n_calls);
-  if (rc) return rc;
-  return fdc_end_frame(ctx);
+  if (rc == FDC_OK) rc = fdc_end_frame(ctx);
+  if (rc != FDC_OK && ctx->frame_begun) {
+    // one bad frame must not wedge the context ("beginFrame has already been called" forever): drop it, keep the message
+    const std::string msg = ctx->error;
+    fdc_abort_frame(ctx);
+    ctx->error = msg;
+  }
+  return rc;
 }
 
 int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t offsets_cap, uint32_t* entries, size_t entries_cap,

@@ -1,12 +1,13 @@
 // Per-tile SDF shade-and-blend kernel (sm_100a).
 //
-// One CTA per 16x16-pixel tile, 8 warps, each warp owns an 8x4 pixel block, one pixel per thread.  A warp walks
-// the tile's ordered primitive list 32 entries at a time: every lane tests one primitive's clipped bbox against
-// the warp's block (ballot), then the warp shades the survivors one by one, all lanes on the same primitive, so
-// every branch on mode/flags is warp-uniform.  The pixel lives in registers as four floats holding exact RGBA8
+// One CTA of 8 warps owns up to 8 consecutive 16x16-pixel tiles = 64 blocks of 8x4 pixels, one pixel per thread; warps
+// pull blocks from a shared-memory counter.  For its block a warp walks the tile's ordered list of 8-byte entries 32 at
+// a time: every lane tests one entry's precomputed "overlaps my block" bit (ballot), then the warp shades the
+// survivors one by one, all lanes on the same primitive, so every branch on mode/flags is warp-uniform and comes from
+// the entry's dispatch bits before the primitive record is touched.  The pixel lives in registers as four floats holding exact RGBA8
 // values (0..255) and is re-quantised after EVERY blended primitive, which is what GL's UNORM8 render target
 // does (SURVEY.md 8a' trap 6).  Texture masks (clip stack) are evaluated analytically and kept per pixel as
-// up to eight UNORM8 levels packed in two registers, including the reference's a*a quirk (mask.frag:233 with
+// up to 15 UNORM8 levels (eight packed in two registers, the rest in shared memory), including the reference's a*a quirk (mask.frag:233 with
 // GL_BLEND still enabled).
 //
 // The arithmetic restates src/figdraw/opengl/glsl/atlas.frag (main :252-405, sdRoundedBox :51-69,
@@ -26,6 +27,9 @@
 #endif
 #ifndef FDC_SHADE_MIN_BLOCKS
 #define FDC_SHADE_MIN_BLOCKS 4
+#endif
+#ifndef FDC_DEEP_MASK
+#define FDC_DEEP_MASK 1  // A/B switch: texture-mask levels 9..15 in shared memory (0: levels 1..8 only, as in r01)
 #endif
 // (r01: staging primitive records into shared memory with cp.async or per-record cp.async.bulk/TMA + mbarrier was
 // built and measured slower than L1-resident uniform loads -- profiles/r01_shade_staging.md, commit 4cc6a20.)
@@ -219,16 +223,33 @@ struct Pixel {
   uint32_t mlo, mhi;  // texture-mask levels 1..8, UNORM8 each
 };
 
-__device__ __forceinline__ float mask_get(const Pixel& px, int level) {  // level 1..8
+// Texture-mask levels 9..15 (GL nests mask textures without a limit, glcontext.nim:171-201; the depth field of a tile
+// entry has four bits): two words per thread in shared memory, [word][thread] so a warp's accesses are conflict free.
+// Only touched by primitives drawn at those depths; the register path of levels 1..8 pays one predicate.
+__shared__ uint32_t s_deep_mask[2][256];
+
+__device__ __forceinline__ float mask_get(const Pixel& px, int level) {  // level 1..15
   const int i = level - 1;
+#if FDC_DEEP_MASK
+  const uint32_t w = i < 4 ? px.mlo : (i < 8 ? px.mhi : s_deep_mask[(i - 8) >> 2][threadIdx.x]);
+#else
   const uint32_t w = i < 4 ? px.mlo : px.mhi;
+#endif
   return (float)((w >> ((i & 3) * 8)) & 255u);
 }
 __device__ __forceinline__ void mask_set(Pixel& px, int level, float v) {
   const int i = level - 1, sh = (i & 3) * 8;
   const uint32_t b = (uint32_t)(int)v & 255u;
   if (i < 4) px.mlo = (px.mlo & ~(255u << sh)) | (b << sh);
+#if FDC_DEEP_MASK
+  else if (i < 8) px.mhi = (px.mhi & ~(255u << sh)) | (b << sh);
+  else {
+    uint32_t* w = &s_deep_mask[(i - 8) >> 2][threadIdx.x];
+    *w = (*w & ~(255u << sh)) | (b << sh);
+  }
+#else
   else px.mhi = (px.mhi & ~(255u << sh)) | (b << sh);
+#endif
 }
 
 // General (rotated) quad: top-left-rule inside test on the two triangles (3,0,1),(2,3,1) and affine (s,t).
@@ -452,8 +473,14 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
   const int depth = (int)((flags & PF_DEPTH_MASK) >> PF_DEPTH_SHIFT);
   const bool mask_write = flags & PF_MASK_WRITE;
   if (flags & PF_MASK_BEGIN) mask_set(px, depth, 0.0f);  // glClear(0) of the mask level, glcontext.nim:1901-1902
+  if (flags & PF_CLEAR_ONLY) return px;                   // first draw of a multi-draw mask level had an empty quad
 
-  const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
+  int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
+  if (flags & PF_MASK_WIDE) {
+    // binned over the parent's whole clip box (to clear the level everywhere); its own clipped bbox sits in ix0..iy1
+    const int4 q5 = __ldg(reinterpret_cast<const int4*>(P) + 5);
+    bx0 = (int16_t)(q5.z & 0xFFFF); by0 = (int16_t)(q5.z >> 16); bx1 = (int16_t)(q5.w & 0xFFFF); by1 = (int16_t)(q5.w >> 16);
+  }
   const bool in_box = ix >= bx0 && ix < bx1 && iy >= by0 && iy < by1;
   const float4 q0 = __ldg(Q + 7);  // (su, ou, sv, ov)
   // A rotated / arbitrary quad is two triangles (3,0,1),(2,3,1) drawn one after the other (glcontext.nim:418-429): a
@@ -633,7 +660,7 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
 template <int kTilesPerCta>
 __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ ShadeArgs a) {
   __shared__ uint32_t s_next;
-  if (a.counters[1] != 0) return;  // a bin list overflowed: host regrows and replays the frame
+  if (a.counters[4] != 0) return;  // a bin list overflowed in this or an earlier segment: host regrows and replays the frame
   if (threadIdx.x == 0) s_next = 0;
   __syncthreads();
   const FrameView& f = a.frame;
@@ -669,6 +696,9 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
       px.b = __uint_as_float(kBiasBits | ((c >> 16) & 255u));
       px.a = __uint_as_float(kBiasBits | (c >> 24));
       px.mlo = px.mhi = 0;
+#if FDC_DEEP_MASK
+      s_deep_mask[0][threadIdx.x] = s_deep_mask[1][threadIdx.x] = 0;
+#endif
     }
 
     const uint2* __restrict__ list = reinterpret_cast<const uint2*>(a.tile_list + a.tile_start[ty * f.tiles_x + tx]);

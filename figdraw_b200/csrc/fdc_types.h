@@ -18,7 +18,8 @@ constexpr int kTileW = 16;         // pixels
 constexpr int kTileH = 16;
 constexpr int kCoarse = 8;         // coarse bin = kCoarse x kCoarse tiles (128 x 128 px)
 constexpr int kChunk = 512;        // primitives per coarse-binning chunk (16 warps x 32)
-constexpr int kMaxMaskDepth = 8;   // texture-mask nesting the tile kernel keeps per pixel (GL: unbounded)
+constexpr int kMaxMaskDepth = 15;  // texture-mask nesting (GL: unbounded): levels 1..8 live in two registers per pixel, 9..15 in
+                                   // shared memory (the depth field of a tile entry has 4 bits)
 constexpr int kAtlasMargin = 4;    // glcontext.nim:257
 constexpr int kMaxAtlasLevels = 14;
 constexpr int kPrimFastBytes = 80; // q0..q4
@@ -42,6 +43,10 @@ constexpr uint32_t PF_FAST = 1u << 20;          // axis-aligned circular-corner 
 constexpr uint32_t PF_INNER = 1u << 21;         // inner rect (ix0..iy1) valid: coverage is exactly 1 there ...
 constexpr uint32_t PF_INNER_EMPTY = 1u << 22;   // ... or exactly 0 (interior of an AnnularAA stroke)
 constexpr uint32_t PF_VISIT_FULL = 1u << 23;    // shade kernel only: the warp's block lies inside the inner rect
+constexpr uint32_t PF_MASK_WIDE = 1u << 24;     // first primitive of a mask level that holds SEVERAL draws: binned over the parent's
+                                                // whole clip box so the level is cleared everywhere (GL clears the full mask texture,
+                                                // glcontext.nim:1901-1902); slow-path primitives keep their own bbox in ix0..iy1
+constexpr uint32_t PF_CLEAR_ONLY = 1u << 25;    // PF_MASK_WIDE primitive whose own quad is empty: clears the level, draws nothing
 constexpr uint32_t PF_EMPTY = 1u << 31;         // dropped (early-out or empty clipped bbox)
 
 // Tile-list entry (8 bytes): .x = primitive index (bit 31: unused), .y = everything the shade kernel needs to decide

@@ -94,6 +94,23 @@ class CudaContext(BackendContext):
     def sync(self):
         self._ck(self._lib.fdc_sync(self._h))
 
+    def syncStatus(self) -> int:
+        """fdc_sync without raising on FDC_ERR_RETRY (6): under a tile-band partition the host all-reduces this status
+        and calls retryFrame() on every rank when any rank reported 6 (bands.resolve_across_ranks does that)."""
+        rc = int(self._lib.fdc_sync(self._h))
+        if rc not in (0, int(Status.ERR_RETRY)):
+            self._ck(rc)
+        return rc
+
+    def retryFrame(self):
+        self._ck(self._lib.fdc_retry_frame(self._h))
+
+    def abortFrame(self):
+        self._ck(self._lib.fdc_abort_frame(self._h))
+
+    def debugLimitLists(self, coarseEntries: int = 0, tileEntries: int = 0):
+        self._ck(self._lib.fdc_debug_limit_lists(self._h, int(coarseEntries), int(tileEntries)))
+
     def readPixels(self, frame=(0, 0, 0, 0), readFront=False, out: Optional[np.ndarray] = None) -> np.ndarray:
         x, y, w, h = (int(v) for v in frame)
         if w <= 0 or h <= 0:

@@ -42,8 +42,10 @@ typedef enum fdc_status {
   FDC_ERR_INVALID = 1,     /* bad argument */
   FDC_ERR_CUDA = 2,        /* CUDA runtime/driver failure, or no device */
   FDC_ERR_STATE = 3,       /* call order violated (asserts in glcontext.nim:1888-1889, :1985-1986) */
-  FDC_ERR_CAPACITY = 4,    /* a documented fixed limit was exceeded (mask depth) */
-  FDC_ERR_MISSING_IMAGE = 5 /* draw of an image key that is not in the atlas (warn + skip in GL) */
+  FDC_ERR_CAPACITY = 4,    /* a documented fixed limit was exceeded (mask depth > 15, atlas > 16384) */
+  FDC_ERR_MISSING_IMAGE = 5, /* draw of an image key that is not in the atlas (warn + skip in GL) */
+  FDC_ERR_RETRY = 6         /* tile-band partition only: this rank's bin lists overflowed and were regrown; the frame
+                               must be re-run with fdc_retry_frame on EVERY rank (all-reduce the status) */
 } fdc_status;
 
 /* `SdfMode` -- values identical to figbackend.nim:36-52. */
@@ -156,6 +158,13 @@ int fdc_sync(fdc_ctx* ctx);
 /* Re-launches the kernels of the last completed frame on the data already resident in device memory (no
  * host->device copy).  Used to time the device path alone and by CUDA-graph style frame loops. */
 int fdc_replay_frame(fdc_ctx* ctx);
+/* Tile-band partitions: re-run the last frame after any rank reported FDC_ERR_RETRY (call on every rank, then gather
+ * again).  Restores pixels a first attempt already blended (frames without clear_main) before re-running. */
+int fdc_retry_frame(fdc_ctx* ctx);
+/* Drop a frame that was begun but cannot be ended because a call in between failed (mask nesting beyond the limit,
+ * restoreTransform on an empty stack, an unknown record ...).  Resets the recording and the mask / transform stacks;
+ * fdc_render_frame does this itself on its error paths.  (GL has no equivalent: its asserts abort the program.) */
+int fdc_abort_frame(fdc_ctx* ctx);
 
 /* --- transforms: glcontext.nim:1991-2017 --- */
 int fdc_translate(fdc_ctx* ctx, float x, float y);
@@ -291,6 +300,10 @@ int fdc_get_frame_stats(fdc_ctx* ctx, fdc_frame_stats* out);
  * are indices into that segment's primitive array in emission order.  Pass NULL to query sizes. */
 int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t offsets_cap, uint32_t* entries,
                    size_t entries_cap, size_t* n_offsets, size_t* n_entries);
+
+/* Test hook: pretend the coarse / tile bin lists hold at most this many entries (0 = real capacity) until the next
+ * regrow, to exercise the overflow -> regrow -> re-run path deterministically. */
+int fdc_debug_limit_lists(fdc_ctx* ctx, uint32_t coarse_entries, uint32_t tile_entries);
 
 /* Replays the last frame with counters enabled: out[0] primitive visits by shading warps, [1] of which with full
  * coverage, [2] of which on the general path, [3] 32-entry list steps walked, [4] occlusion-scan steps. */

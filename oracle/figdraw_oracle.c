@@ -461,6 +461,7 @@ typedef struct tctx {
   int level_quads[MAX_MASKS];
   int level_ok[MAX_MASKS];
   struct { int call_index; int box[4]; } level_rec[MAX_MASKS][8];
+  int64_t level_first_rec[MAX_MASKS];
 } tctx;
 
 /* vmath: m[col*4+row]; a*b with each entry summed left to right. */
@@ -793,14 +794,24 @@ static void raster_tri(tctx* t, const oquad_t* q, int ia, int ib, int ic, int ma
  * box of its single mask quad; a level with several mask quads does not clip; a level whose mask quad was dropped
  * clips everything.  Segments end at each backdrop blur; open mask levels are re-emitted at the start of the next. */
 static int sat_i(float v) { v = fminf(fmaxf(v, -30000.0f), 30000.0f); return (int)v; }
-static void emit_record(tctx* t, int call_index, const int box[4], int is_mask, int level) {
+static void emit_record_seg(tctx* t, int segment, int call_index, const int box[4], int is_mask, int level) {
   shared_t* sh = t->sh;
   if (sh->rec_n < sh->rec_cap) {
     int32_t* r = sh->rec + sh->rec_n * 8;
-    r[0] = sh->segment; r[1] = call_index; r[2] = box[0]; r[3] = box[1]; r[4] = box[2]; r[5] = box[3]; r[6] = is_mask; r[7] = level;
+    r[0] = segment; r[1] = call_index; r[2] = box[0]; r[3] = box[1]; r[4] = box[2]; r[5] = box[3]; r[6] = is_mask; r[7] = level;
   }
   sh->rec_n++;
 }
+static void emit_record(tctx* t, int call_index, const int box[4], int is_mask, int level) {
+  emit_record_seg(t, t->sh->segment, call_index, box, is_mask, level);
+}
+static int box_empty(const int* b) { return b[0] >= b[2] || b[1] >= b[3]; }
+/* Binning rule.  Content is binned into bbox(ceil'd corners) /\ frame /\ band /\ clip box of the mask
+ * level it is drawn under.  A level's clip box is the bin box of its single rounded-rect mask quad; a level with several
+ * mask quads (or a first quad that is not a rounded rect) does not clip, and because GL cleared the WHOLE mask texture
+ * at beginMask (glcontext.nim:1901-1902) its first quad is binned over the parent's whole clip box instead of its own
+ * bbox (it carries the clear).  That is only known when the second quad arrives: the first quad's record is then
+ * widened in place; a first quad with an empty bin box keeps a placeholder record (segment -1) for that purpose. */
 static void collect_quad(tctx* t, const oquad_t* q) {
   shared_t* sh = t->sh;
   int box[4];
@@ -810,26 +821,48 @@ static void collect_quad(tctx* t, const oquad_t* q) {
   box[3] = sat_i(fmaxf(fmaxf(q->pos[0].y, q->pos[1].y), fmaxf(q->pos[2].y, q->pos[3].y)));
   const int L = t->mask_write;
   const int* clip = t->mask_begun ? t->clip[L - 1] : t->clip[L];
-  if (box[0] < clip[0]) box[0] = clip[0];
-  if (box[1] < clip[1]) box[1] = clip[1];
-  if (box[2] > clip[2]) box[2] = clip[2];
-  if (box[3] > clip[3]) box[3] = clip[3];
-  if (box[0] < 0) box[0] = 0;
-  if (box[2] > sh->W) box[2] = sh->W;
-  if (box[1] < sh->band_y0) box[1] = sh->band_y0;
-  if (box[3] > sh->band_y1) box[3] = sh->band_y1;
-  int empty = box[0] >= box[2] || box[1] >= box[3];
+  int wide[4] = {clip[0], clip[1], clip[2], clip[3]};
+  if (wide[0] < 0) wide[0] = 0;
+  if (wide[2] > sh->W) wide[2] = sh->W;
+  if (wide[1] < sh->band_y0) wide[1] = sh->band_y0;
+  if (wide[3] > sh->band_y1) wide[3] = sh->band_y1;
+  if (box[0] < wide[0]) box[0] = wide[0];
+  if (box[1] < wide[1]) box[1] = wide[1];
+  if (box[2] > wide[2]) box[2] = wide[2];
+  if (box[3] > wide[3]) box[3] = wide[3];
+  int empty = box_empty(box);
   if (t->mask_begun) {
     int k = t->level_quads[L]++;
     int is_rect = q->is_rounded_rect;
-    if (k == 0 && is_rect) {
-      t->level_ok[L] = 1;
-      if (empty) { t->clip[L][0] = t->clip[L][1] = t->clip[L][2] = t->clip[L][3] = 0; }
-      else memcpy(t->clip[L], box, sizeof(box));
-    } else {
-      t->level_ok[L] = 0;
-      memcpy(t->clip[L], t->clip[L - 1], sizeof(box));
+    if (k == 0) {
+      t->level_first_rec[L] = sh->rec_n;
+      if (is_rect) {
+        t->level_ok[L] = 1;
+        if (empty) { t->clip[L][0] = t->clip[L][1] = t->clip[L][2] = t->clip[L][3] = 0; }
+        else memcpy(t->clip[L], box, sizeof(box));
+      } else {
+        t->level_ok[L] = 0;
+        memcpy(t->clip[L], t->clip[L - 1], sizeof(box));
+        memcpy(box, wide, sizeof(box));
+        empty = box_empty(box);
+      }
+      t->level_rec[L][0].call_index = q->call_index;
+      memcpy(t->level_rec[L][0].box, box, sizeof(box));
+      emit_record_seg(t, empty ? -1 : sh->segment, q->call_index, box, 1, L);
+      return;
     }
+    if (k == 1 && t->level_ok[L]) {
+      /* the level now holds several quads: the first one carries the clear of the whole parent clip box */
+      const int64_t at = t->level_first_rec[L];
+      if (at < sh->rec_cap) {
+        int32_t* r = sh->rec + at * 8;
+        r[0] = box_empty(wide) ? -1 : sh->segment;
+        r[2] = wide[0]; r[3] = wide[1]; r[4] = wide[2]; r[5] = wide[3];
+      }
+      memcpy(t->level_rec[L][0].box, wide, sizeof(wide));
+    }
+    t->level_ok[L] = 0;
+    memcpy(t->clip[L], t->clip[L - 1], sizeof(box));
     if (k < 8) { t->level_rec[L][k].call_index = q->call_index; memcpy(t->level_rec[L][k].box, box, sizeof(box)); }
   }
   if (!empty) emit_record(t, q->call_index, box, t->mask_begun, L);

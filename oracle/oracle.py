@@ -148,7 +148,7 @@ def reference_bins(trace, tile_w: int = 16, tile_h: int = 16, band: Optional[Tup
     rec = rec[:n]
     tx_n, ty_n = (W + tile_w - 1) // tile_w, (H + tile_h - 1) // tile_h
     out = []
-    n_seg = int(rec[:, 0].max()) + 1 if n else 1
+    n_seg = max(int(rec[:, 0].max()), 0) + 1 if n else 1  # segment -1: placeholder records (dropped first mask quads)
     for s in range(n_seg):
         r = rec[rec[:, 0] == s]
         tx0, ty0 = r[:, 2] // tile_w, r[:, 3] // tile_h

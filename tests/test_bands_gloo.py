@@ -48,6 +48,23 @@ def _worker(rank, world, port, out_dir):
     bands.allgather_bands(fb, rank, world)
     if rank == 0:
         np.save(os.path.join(out_dir, f"gathered_{world}.npy"), fb[: tr.height].numpy())
+
+    class FakeCtx:
+        """Stands in for CudaContext: the last rank's bin lists 'overflow' on the first attempt (FDC_ERR_RETRY = 6)."""
+
+        def __init__(self):
+            self.syncs, self.retries = 0, 0
+
+        def syncStatus(self):
+            self.syncs += 1
+            return 6 if (rank == world - 1 and self.retries == 0) else 0
+
+        def retryFrame(self):
+            self.retries += 1
+
+    fake = FakeCtx()
+    rounds = bands.resolve_across_ranks(fake, world, dist)
+    assert rounds == 1 and fake.retries == 1 and fake.syncs == 2  # EVERY rank re-runs the frame, once
     dist.barrier()
     dist.destroy_process_group()
 

@@ -81,6 +81,56 @@ def test_cfg5_scaled_x2():
     check(ss.config_trace(5, 1920, 1080, n_rects=6000, n_glyphs=1200, scale=2.0))
 
 
+# ------------------------------------------------------------------ BASELINE.json configs at their stated sizes
+def _check_bins(tr, ctx):
+    ref = oracle.reference_bins(tr)
+    assert ctx.frameStats().n_segments == len(ref)
+    for seg, (off_ref, ent_ref) in enumerate(ref):
+        off, ent = ctx.debugBins(seg)
+        assert np.array_equal(off, off_ref), f"segment {seg}: tile offsets differ"
+        assert np.array_equal(ent, ent_ref), f"segment {seg}: draw order differs"
+
+
+FULL_SIZE = {
+    "cfg3 text page + star 3840x2160": lambda: ss.config_trace(3),
+    "cfg3 + 20k MSDF glyph quads 3840x2160": lambda: ss.config_trace(3, msdf_glyphs=20000),
+    "cfg4 180x12 sub-clip 3840x2160": lambda: ss.config_trace(4),
+    "cfg4 180x12 rect-mask 3840x2160": lambda: ss.config_trace(4, rect_mask=True),
+    "cfg5 100k rects + 20k glyphs 3840x2160": lambda: ss.config_trace(5),
+    "cfg5 x2 7680x4320": lambda: ss.config_trace(5, 7680, 4320, scale=2.0),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL_SIZE))
+def test_baseline_configs_at_full_size(name):
+    """every BASELINE config at the size BASELINE.json states -- pixels within 2 LSB of the oracle
+    AND bin lists / draw order bit-exact."""
+    tr = FULL_SIZE[name]()
+    assert (tr.width, tr.height) in ((3840, 2160), (7680, 4320))
+    ctx = CudaContext(atlasSize=tr.atlas_size)
+    got = render_trace(tr, ctx)
+    want = oracle.render_trace(tr)
+    mx, frac = diff_stats(got, want)
+    assert mx <= MAX_DIFF, f"max diff {mx} LSB"
+    assert frac <= MAX_FRACTION, f"{frac:.4%} of pixels differ"
+    _check_bins(tr, ctx)
+    ctx.close()
+
+
+def test_cfg5_8k_bands_reassemble_the_frame():
+    """configs[4]: the 8K frame partitioned into 8 tile-row bands equals the single-context frame, bit for bit."""
+    tr = ss.config_trace(5, 7680, 4320, scale=2.0)
+    full = render_trace(tr)
+    out = np.zeros_like(full)
+    for r in range(8):
+        ctx = CudaContext(atlasSize=tr.atlas_size, rank=r, nRanks=8)
+        img = render_trace(tr, ctx)
+        y0, y1 = ctx.bandRows()
+        out[y0:y1] = img[y0:y1]
+        ctx.close()
+    assert np.array_equal(out, full)
+
+
 @pytest.mark.parametrize("builder", [
     lambda: scenes.golden_trace("layers_clip"),
     lambda: ss.config_trace(2),
@@ -433,35 +483,6 @@ def test_ragged_and_extreme_sizes():
         out[y0:y1] = img[y0:y1]
         ctx.close()
     assert np.array_equal(out, full)
-
-
-def test_mask_nesting_limit():
-    """Eight nested texture-mask levels render like the reference; the ninth is refused with FDC_ERR_CAPACITY."""
-    from figdraw_b200.figbackend import TraceBackend, circularRadii, solid
-    from figdraw_b200.fignodes import rgba
-
-    tb = TraceBackend()
-    tb.beginFrame((256, 256), clearMain=True)
-    for d in range(8):
-        tb.beginMask((8.0 + 9 * d, 6.0 + 7 * d, 230.0 - 15 * d, 236.0 - 13 * d), circularRadii((20, 6, 12, 0)))
-        tb.endMask()
-        tb.drawRoundedRectSdf((0.0, 0.0, 256.0, 256.0), solid(rgba(30 * d, 255 - 25 * d, 90, 130)), circularRadii((0, 0, 0, 0)))
-    for _ in range(8):
-        tb.popMask()
-    tb.endFrame()
-    tr = tb.trace()
-    got, want = render_trace(tr), oracle.render_trace(tr)
-    mx, _ = diff_stats(got, want)
-    assert mx <= MAX_DIFF
-    ctx = CudaContext()
-    ctx.beginFrame((64, 64), clearMain=True)
-    for d in range(8):
-        ctx.beginMask((0, 0, 64, 64), circularRadii((0, 0, 0, 0)))
-        ctx.endMask()
-    with pytest.raises(FigDrawError) as e:
-        ctx.beginMask((0, 0, 64, 64), circularRadii((0, 0, 0, 0)))
-    assert e.value.code == 4  # FDC_ERR_CAPACITY
-    ctx.close()
 
 
 def test_reference_spot_pixels():

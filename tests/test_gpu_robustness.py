@@ -1,0 +1,250 @@
+"""Failure paths of the CUDA backend: bin-list overflow in any segment, re-runs of frames that blend over the previous
+pixels, the cross-rank retry protocol of a tile-band partition, aborted frames, deep mask nesting and mask levels
+holding several draws.  Everything is compared with the CPU oracle or with an undisturbed context on the same input."""
+import numpy as np
+import pytest
+
+from figdraw_b200 import scenes_synth as ss
+from figdraw_b200.abi import Op, SdfMode
+from figdraw_b200.cuda_context import CudaContext, FigDrawError, render_trace
+from figdraw_b200.figbackend import TraceBackend, ZeroRadii, circularRadii, solid
+from figdraw_b200.fignodes import rgba
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _submit(c, tr, calls=None, clear=True):
+    c.beginFrame((tr.width, tr.height), clearMain=clear and tr.clear is not None, clearMainColor=tr.clear or (1.0, 1.0, 1.0, 1.0))
+    c.submitCalls(tr.calls if calls is None else calls)
+    c.endFrame()
+
+
+def _blur_sandwich(width=640, height=400, n_before=40, n_after=900, seed=11):
+    """A few rects, a backdrop blur, then many translucent rects: the segment AFTER the blur needs the longer lists."""
+    rng = np.random.default_rng(seed)
+    tb = TraceBackend()
+    tb.beginFrame((width, height), clearMain=True, clearMainColor=(0.95, 0.93, 0.9, 1.0))
+
+    def rects(n):
+        for _ in range(n):
+            x, y = rng.uniform(-20, width - 30), rng.uniform(-20, height - 30)
+            w, h = rng.uniform(20, 160), rng.uniform(14, 120)
+            col = rgba(int(rng.integers(256)), int(rng.integers(256)), int(rng.integers(256)), int(rng.integers(60, 200)))
+            tb.drawRoundedRectSdf((x, y, w, h), solid(col), circularRadii((6, 3, 9, 0)))
+
+    rects(n_before)
+    tb.drawBackdropBlur((120.0, 80.0, 300.0, 200.0), circularRadii((12, 12, 12, 12)), 14.0)
+    rects(n_after)
+    tb.endFrame()
+    return tb.trace()
+
+
+def test_overflow_in_the_first_segment_of_a_blur_frame():
+    """an overflow in a segment that is not the last used to be forgotten when the next segment
+    reset the counters -- the segment's content went missing for good.  The flags are sticky per frame now."""
+    tr = ss.config_trace(2, 1280, 720)
+    want = render_trace(tr)
+    ctx = CudaContext(atlasSize=tr.atlas_size)
+    for _i, key, img in tr.images:
+        ctx.putImage(key, img)
+    _submit(ctx, tr)
+    ctx.sync()
+    n_seg = ctx.frameStats().n_segments
+    assert n_seg >= 2
+    for coarse, tile in ((0, 2000), (64, 0), (64, 2000)):
+        ctx.debugLimitLists(coarse, tile)  # segment 0 (~700 primitives) overflows, the short last segment does not
+        _submit(ctx, tr)
+        got = ctx.readPixels()
+        assert np.array_equal(got, want), f"limits {coarse}/{tile}"
+    # n_tile_entries is the whole frame's, not the last segment's
+    total = sum(len(ent) for _off, ent in (ctx.debugBins(s) for s in range(n_seg)))
+    _submit(ctx, tr)
+    assert ctx.frameStats().n_tile_entries == total
+    ctx.close()
+
+
+def test_overflow_replay_does_not_composite_twice_without_clear():
+    """clearMain=false + overflow in a LATER segment: the earlier segments were already blended when
+    the frame is re-run; the pre-frame pixels are restored first."""
+    tr = _blur_sandwich()
+    base = ss.config_trace(5, tr.width, tr.height, n_rects=300, n_glyphs=0)
+
+    def run(limit):
+        ctx = CudaContext(atlasSize=base.atlas_size)
+        for _i, key, img in base.images:
+            ctx.putImage(key, img)
+        _submit(ctx, base)  # frame 1: something to blend over
+        _submit(ctx, tr, clear=False)  # sizes the lists
+        ctx.sync()
+        _submit(ctx, base)
+        if limit:
+            ctx.debugLimitLists(0, limit)
+        _submit(ctx, tr, clear=False)
+        out = ctx.readPixels().copy()
+        ctx.close()
+        return out
+
+    want = run(0)
+    seg0 = oracle.reference_bins(tr)[0][1].size
+    seg1 = oracle.reference_bins(tr)[1][1].size
+    assert seg1 > 2 * seg0  # a limit between the two overflows only the segment after the blur
+    got = run((seg0 + seg1) // 2)
+    assert np.array_equal(got, want)
+
+
+def test_banded_overflow_asks_every_rank_to_retry():
+    """under a tile-band partition a private re-run would show the neighbours' later state in the blur
+    halo.  The rank reports FDC_ERR_RETRY instead; every rank re-runs the frame (fdc_retry_frame)."""
+    from figdraw_b200.bands import padded_rows
+
+    tr = ss.config_trace(2, 1280, 720)
+    full = render_trace(tr)
+    n = 2
+    ctxs = [CudaContext(atlasSize=tr.atlas_size, rank=r, nRanks=n) for r in range(n)]
+    try:
+        for c in ctxs:
+            c.reserveFramebuffer(tr.width, padded_rows(tr.height, n))
+        ptrs = [c.framebufferPtr() for c in ctxs]
+        for c in ctxs:
+            c.setPeerFramebuffers(ptrs)
+            for _idx, key, img in tr.images:
+                c.putImage(key, img)
+        for c in ctxs:  # size the buffers one rank at a time, without cross-rank waits
+            _submit(c, tr, tr.calls[tr.calls["op"] != Op.BACKDROP_BLUR])
+            c.sync()
+        for c in ctxs:
+            _submit(c, tr)
+        for c in ctxs:
+            c.sync()
+        ctxs[1].debugLimitLists(0, 3000)
+        for c in ctxs:
+            _submit(c, tr)
+        status = [c.syncStatus() for c in ctxs]
+        assert status == [0, 6]  # FDC_ERR_RETRY on the rank whose lists overflowed
+        for c in ctxs:
+            c.retryFrame()
+        assert [c.syncStatus() for c in ctxs] == [0, 0]
+        for r, c in enumerate(ctxs):
+            assert np.array_equal(c.readPixels(), full), f"rank {r}"
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_a_failed_frame_does_not_wedge_the_context():
+    """an error between beginFrame and endFrame left frame_begun set for good."""
+    tr = ss.config_trace(5, 640, 360, n_rects=500, n_glyphs=0)
+    want = render_trace(tr)
+    ctx = CudaContext(atlasSize=tr.atlas_size)
+    for _i, key, img in tr.images:
+        ctx.putImage(key, img)
+    ctx.beginFrame((tr.width, tr.height), clearMain=True)
+    bad = tr.calls[:40].copy()
+    bad[20]["op"] = 99  # unknown record
+    with pytest.raises(FigDrawError):
+        ctx.submitCalls(bad)
+    with pytest.raises(FigDrawError, match="already"):
+        ctx.beginFrame((tr.width, tr.height), clearMain=True)
+    ctx.abortFrame()
+    assert np.array_equal(render_trace(tr, ctx), want)
+    ctx.close()
+
+
+def test_native_render_frame_aborts_itself_on_error():
+    """fdc_render_frame with clip nesting beyond the limit fails -- and the next frame renders normally."""
+    from figdraw_b200 import fignodes as fn, native_scene
+
+    def nested(depth):
+        r = fn.newRenders()
+        parent = None
+        for d in range(depth):
+            node = fn.Fig(kind=fn.FigKind.nkRectangle, screenBox=fn.rect(4.0 + 3 * d, 4.0 + 2 * d, 240.0 - 6 * d, 200.0 - 4 * d),
+                          fill=fn.fill(rgba(20 + 12 * d, 200 - 9 * d, 90, 255)), flags=fn.FigFlags.NfClipContent)
+            parent = r.addRoot(0, node) if parent is None else r.addChild(0, parent, node)
+        return r
+
+    ctx = CudaContext()
+    with pytest.raises(FigDrawError) as e:
+        ctx.renderFrameNative(native_scene.pack_renders(nested(17)), (256, 208))
+    assert e.value.code == 4
+    ok = nested(15)
+    ctx.renderFrameNative(native_scene.pack_renders(ok), (256, 208))
+    got = ctx.readPixels()
+    from figdraw_b200 import figrender
+    from figdraw_b200.figbackend import TraceBackend as TB
+
+    tb = TB()
+    figrender.setFigUiScale(1.0)
+    figrender.renderFrame(tb, ok, (256.0, 208.0))
+    want = oracle.render_trace(tb.trace())
+    assert int(np.abs(got.astype(np.int16) - want.astype(np.int16)).max()) <= 2
+    ctx.close()
+
+
+def test_fifteen_nested_mask_levels():
+    """GL nests mask textures without a limit (glcontext.nim:171-201); levels 9..15 live in shared memory here."""
+    tb = TraceBackend()
+    tb.beginFrame((320, 300), clearMain=True)
+    for d in range(15):
+        tb.beginMask((6.0 + 7 * d, 5.0 + 6 * d, 300.0 - 13 * d, 288.0 - 11 * d), circularRadii((20, 6, 12, 0)))
+        tb.endMask()
+        tb.drawRoundedRectSdf((0.0, 0.0, 320.0, 300.0), solid(rgba(16 * d, 255 - 15 * d, 90, 130)), ZeroRadii)
+    for d in range(15):
+        tb.popMask()
+        tb.drawRoundedRectSdf((10.0 * d, 0.0, 9.0, 300.0), solid(rgba(200, 10 * d, 30, 90)), ZeroRadii)
+    tb.endFrame()
+    tr = tb.trace()
+    got, want = render_trace(tr), oracle.render_trace(tr)
+    assert int(np.abs(got.astype(np.int16) - want.astype(np.int16)).max()) <= 2
+    ctx = CudaContext()
+    render_trace(tr, ctx)
+    for seg, (off_ref, ent_ref) in enumerate(oracle.reference_bins(tr)):
+        off, ent = ctx.debugBins(seg)
+        assert np.array_equal(off, off_ref) and np.array_equal(ent, ent_ref)
+    ctx.beginFrame((64, 64), clearMain=True)
+    for _ in range(15):
+        ctx.beginMask((0, 0, 64, 64), ZeroRadii)
+        ctx.endMask()
+    with pytest.raises(FigDrawError) as e:
+        ctx.beginMask((0, 0, 64, 64), ZeroRadii)
+    assert e.value.code == 4  # FDC_ERR_CAPACITY
+    ctx.abortFrame()
+    ctx.close()
+
+
+def test_mask_level_with_several_draws_is_cleared_everywhere():
+    """GL clears the whole mask texture at beginMask.  A level holding two shapes (content under it is
+    not clipped to one bbox) drawn after another mask of the same depth must not see that one's stale values; a dropped
+    (zero-sized) clip rect followed by a real shape clears too."""
+    for variant in range(3):
+        tb = TraceBackend()
+        tb.beginFrame((400, 300), clearMain=True, clearMainColor=(0.9, 0.9, 0.95, 1.0))
+        # level 1, used once and popped: leaves values behind at depth 1
+        tb.beginMask((30.0, 20.0, 340.0, 260.0), circularRadii((30, 30, 30, 30)))
+        tb.endMask()
+        tb.drawRoundedRectSdf((0.0, 0.0, 400.0, 300.0), solid(rgba(230, 60, 40, 120)), ZeroRadii)
+        tb.popMask()
+        # level 1 again, built from two shapes that do not cover the first mask's area
+        if variant == 2:
+            tb.beginMask((50.0, 50.0, 0.0, 40.0), ZeroRadii)  # dropped: zero width
+        else:
+            tb.beginMask((50.0, 40.0, 90.0, 70.0), circularRadii((12, 0, 12, 0)))
+        tb.drawRoundedRectSdf((220.0, 150.0, 120.0, 100.0), solid(rgba(255, 255, 255, 255)), circularRadii((20, 20, 20, 20)))
+        if variant == 1:
+            tb.drawQuadraticBezierSdf((100.0, 100.0, 200.0, 120.0), solid(rgba(255, 255, 255, 255)), (-80.0, -40.0), (0.0, 50.0),
+                                      (80.0, -30.0), 9.0, 1)
+        tb.endMask()
+        tb.drawRoundedRectSdf((0.0, 0.0, 400.0, 300.0), solid(rgba(20, 70, 220, 200)), ZeroRadii)
+        tb.popMask()
+        tb.endFrame()
+        tr = tb.trace()
+        got, want = render_trace(tr), oracle.render_trace(tr)
+        d = np.abs(got.astype(np.int16) - want.astype(np.int16)).max(axis=2)
+        assert int(d.max()) <= 2, f"variant {variant}: max {int(d.max())} LSB at {np.argwhere(d == d.max())[0]}"
+        ctx = CudaContext()
+        render_trace(tr, ctx)
+        for seg, (off_ref, ent_ref) in enumerate(oracle.reference_bins(tr)):
+            off, ent = ctx.debugBins(seg)
+            assert np.array_equal(off, off_ref) and np.array_equal(ent, ent_ref), f"variant {variant}: bins differ"
+        ctx.close()

@@ -875,6 +875,7 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
   __shared__ uint32_t s_gpos[kGroups][64];         // where group g's entries of tile t go in the tile list
   __shared__ uint32_t s_run[64];                   // pass 0: running tile counts; pass 1: write cursors
   __shared__ uint32_t s_base[64];
+  __shared__ uint32_t s_cls[64];                   // != 0: the tile holds something the shade kernel's lean loop cannot take
   __shared__ uint32_t s_alloc;
   if (!n_direct && counters[2] > coarse_cap) return;
   const int b = blockIdx.x;
@@ -884,7 +885,7 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
   const int tile_x0 = cbx_i * kCoarse, tile_y0 = f.cty0 + cby_i * kCoarse;
   const int px0 = tile_x0 * kTileW, py0 = tile_y0 * kTileH;
   const bool single = end - begin <= (uint32_t)kStage;
-  if (threadIdx.x < 64) s_run[threadIdx.x] = 0;
+  if (threadIdx.x < 64) { s_run[threadIdx.x] = 0; s_cls[threadIdx.x] = 0; }
 
   for (int pass = 0; pass < 2; pass++) {
     if (pass == 1) {
@@ -916,7 +917,7 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
         const int tx = tile_x0 + (t & 7), ty = tile_y0 + (t >> 3);
         if (tx < f.tiles_x && ty >= f.ty0 && ty < f.ty1) {
           tile_start[ty * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : alloc + s_base[t];
-          tile_count[ty * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : s_run[t];
+          tile_count[ty * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : (s_run[t] | (s_cls[t] ? kTileNeedsFullPath : 0u));
         }
       }
       if (alloc == 0xFFFFFFFFu) return;
@@ -958,8 +959,15 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
         for (int g = warp; g < n_groups; g += 8) {
           const uint32_t k = (uint32_t)g * 32u + lane;
           const uint32_t lo = k < ns ? s_lo[k] : 0u, hi = k < ns ? s_hi[k] : 0u;
-          s_gcnt[g][lane] = (uint8_t)__popc(transpose32(lo, lane));
-          s_gcnt[g][32 + lane] = (uint8_t)__popc(transpose32(hi, lane));
+          const uint32_t t_lo = transpose32(lo, lane), t_hi = transpose32(hi, lane);
+          s_gcnt[g][lane] = (uint8_t)__popc(t_lo);
+          s_gcnt[g][32 + lane] = (uint8_t)__popc(t_hi);
+          // tile class: anything but unmasked fast content sends the whole tile to the shade kernel's full loop
+          const uint32_t inf = k < ns ? s_info[k] : TE_FAST;
+          const bool not_lean = !(inf & TE_FAST) || (inf & ((15u << TE_DEPTH_SHIFT) | TE_RECTMASK | TE_MASKW | TE_MASKB)) != 0u;
+          const uint32_t nlm = __ballot_sync(0xFFFFFFFFu, not_lean);
+          if (t_lo & nlm) atomicOr(&s_cls[lane], 1u);
+          if (t_hi & nlm) atomicOr(&s_cls[32 + lane], 1u);
         }
         __syncthreads();
       }

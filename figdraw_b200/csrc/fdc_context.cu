@@ -1878,7 +1878,7 @@ int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t off
   size_t total = 0;
   const int ty0 = ctx->frame.ty0, ty1 = ctx->frame.ty1, tx_n = ctx->frame.tiles_x;
   for (int ty = ty0; ty < ty1; ty++)
-    for (int tx = 0; tx < tx_n; tx++) total += count[(size_t)ty * tx_n + tx];
+    for (int tx = 0; tx < tx_n; tx++) total += count[(size_t)ty * tx_n + tx] & kTileCountMask;
   if (n_offsets) *n_offsets = n_tiles + 1;
   if (n_entries) *n_entries = total;
   if (!tile_offsets || !entries) return FDC_OK;
@@ -1888,7 +1888,7 @@ int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t off
     tile_offsets[t] = (uint32_t)at;
     const int ty = (int)(t / tx_n);
     if (ty < ty0 || ty >= ty1) continue;
-    for (uint32_t k = 0; k < count[t]; k++) entries[at++] = calls[list[start[t] + k].pid];
+    for (uint32_t k = 0; k < (count[t] & kTileCountMask); k++) entries[at++] = calls[list[start[t] + k].pid];
   }
   tile_offsets[n_tiles] = (uint32_t)at;
   return FDC_OK;

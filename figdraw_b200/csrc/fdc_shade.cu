@@ -28,6 +28,9 @@
 #ifndef FDC_SHADE_MIN_BLOCKS
 #define FDC_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef FDC_LEAN_LOOP
+#define FDC_LEAN_LOOP 1  // A/B switch: call-free loop for tiles that hold only unmasked fast primitives
+#endif
 #ifndef FDC_DEEP_MASK
 #define FDC_DEEP_MASK 1  // A/B switch: texture-mask levels 9..15 in shared memory (0: levels 1..8 only, as in r01)
 #endif
@@ -352,11 +355,10 @@ __device__ __forceinline__ void blend(Pixel& px, float sr, float sg, float sb, f
   px.a = fmaf(255.0f - (px.a - kBias), sa, px.a);
 }
 
-// Hot path: axis-aligned, circular corners, ClipAA / AnnularAA / DropShadow, content (not a mask write), no rect mask.
-// PF_VISIT_FULL in `flags`: the warp's whole block lies in the primitive's inner rect where coverage is exactly 1.
-// Hot path: axis-aligned, circular corners, ClipAA / AnnularAA / DropShadow, content (not a mask write), no rect mask.
+// Fast path (PF_FAST primitives): axis-aligned quads -- rounded boxes with circular corners in ClipAA / AnnularAA /
+// DropShadow mode, atlas / MSDF quads at <= 1 texel per pixel -- as content, as ClipAA mask writes, or under a rect mask.
 // `info` is the TileEntry word; `full`: the warp's whole block lies in the primitive's inner rect (coverage exactly 1).
-template <bool kMasked>
+template <bool kMasked, bool kInlineTex>
 __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const PrimExt* __restrict__ E, const AtlasView& at,
                                            const RectMaskRec* __restrict__ rectmasks, uint32_t info, bool full, float fx, float fy,
                                            Pixel& px) {
@@ -392,7 +394,12 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
                         iy < (int16_t)(q6.y >> 16);
     const float s = fmaf(fx, q7.x, q7.y), t = fmaf(fy, q7.z, q7.w);
     float4 tex = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (inside) tex = tex_bilinear_call(at.level[0], at.size, fmaf(s, q0.y, q0.x), fmaf(t, q0.w, q0.z));
+    if (inside) {
+      // lean tiles (no call anywhere in their loop) fetch in line; the full loop keeps the fetch out of line so that it
+      // does not cost the rounded-box path registers
+      if (kInlineTex) tex = tex_bilinear(at.level[0], at.size, fmaf(s, q0.y, q0.x), fmaf(t, q0.w, q0.z));
+      else tex = tex_bilinear_call(at.level[0], at.size, fmaf(s, q0.y, q0.x), fmaf(t, q0.w, q0.z));
+    }
     const uint32_t kind = (info >> TE_KIND_SHIFT) & 3u;
     float sr = col.x, sg = col.y, sb = col.z, sa;
     if (kind == 0u) {
@@ -651,6 +658,63 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
 
 }  // namespace
 
+// One warp's walk over the ordered entry list of its tile for one 8x4-pixel block.
+//
+// kLean: the fine binner found nothing in this tile but unmasked PF_FAST primitives (tile_count bit 31 clear).  That
+// instantiation contains no call at all -- the general path (shade_prim) and the out-of-line helpers are the only
+// reason the other loop keeps a stack frame and spills its loop state around every visit (r02 profile: 4 local-memory
+// instructions and 13 % of the stall samples per visit on a path cfg5 never takes) -- and no mask code.
+//
+// Surviving entries of a 32-entry step are compacted into a per-warp queue in shared memory with the primitive's
+// ADDRESS already formed by the lane that owned the entry (one 64-bit multiply-add per lane, in parallel), so a visit
+// starts with one broadcast LDS.128 instead of find-first-set + two shuffles + address arithmetic (31 -> ~12
+// instructions of loop management per visit).
+template <bool kLean>
+__device__ __forceinline__ void walk_list(const ShadeArgs& a, const uint2* __restrict__ list, uint32_t n, uint32_t start, uint32_t ov_bit,
+                                          uint32_t full_bit, uint4* __restrict__ queue, int lane, int ix, int iy, float fx, float fy,
+                                          Pixel& px) {
+  const uint32_t lt = (1u << lane) - 1u;
+  for (uint32_t base = start; base < n; base += 32) {
+    const uint32_t idx = base + lane;
+    uint2 e = make_uint2(0u, 0u);
+    if (idx < n) e = __ldg(&list[idx]);
+    const bool hit = (e.y & ov_bit) != 0u;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (!kLean && a.stats) {
+      const uint32_t mf = __ballot_sync(0xFFFFFFFFu, hit && (e.y & full_bit));
+      const uint32_t ms = __ballot_sync(0xFFFFFFFFu, hit && !(e.y & TE_FAST));
+      if (lane == 0) {
+        atomicAdd(&a.stats[3], 1ull);
+        atomicAdd(&a.stats[0], (unsigned long long)__popc(m));
+        atomicAdd(&a.stats[1], (unsigned long long)__popc(mf));
+        atomicAdd(&a.stats[2], (unsigned long long)__popc(ms));
+      }
+    }
+    if (m == 0u) continue;
+    if (hit) {
+      const unsigned long long addr = reinterpret_cast<unsigned long long>(a.prims + e.x);
+      queue[__popc(m & lt)] = make_uint4((uint32_t)addr, (uint32_t)(addr >> 32), e.y, e.x);
+    }
+    __syncwarp();
+    const int cnt = __popc(m);
+    for (int k = 0; k < cnt; k++) {
+      const uint4 q = queue[k];  // same address in every lane: one broadcast
+      const float4* S = reinterpret_cast<const float4*>(((unsigned long long)q.y << 32) | (unsigned long long)q.x);
+      const uint32_t info = q.z;
+      const bool full = (info & full_bit) != 0u;
+      if (kLean) {
+        shade_fast<false, true>(S, a.exts + q.w, a.atlas, a.rectmasks, info, full, fx, fy, px);
+      } else if (info & TE_FAST) {
+        if (info & ((15u << TE_DEPTH_SHIFT) | TE_RECTMASK)) shade_fast<true, false>(S, a.exts + q.w, a.atlas, a.rectmasks, info, full, fx, fy, px);
+        else shade_fast<false, false>(S, a.exts + q.w, a.atlas, a.rectmasks, info, full, fx, fy, px);
+      } else {
+        px = shade_prim(&a, reinterpret_cast<const Prim*>(S), ix, iy, px);
+      }
+    }
+    __syncwarp();  // the queue is rewritten by the next step
+  }
+}
+
 // One CTA owns kTilesPerCta consecutive tiles = 8*kTilesPerCta blocks of 8x4 pixels.  Its 8 warps pull blocks from a
 // shared-memory counter instead of being pinned to one block of one tile: a warp that finishes a cheap block moves
 // on immediately (no intra-CTA tail: the slowest block of a tile used to hold 7 idle warps' registers), while the
@@ -660,8 +724,14 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
 template <int kTilesPerCta>
 __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ ShadeArgs a) {
   __shared__ uint32_t s_next;
+  __shared__ uint4 s_queue[8][32];  // per warp: surviving entries of the current 32-entry step (address, info, index)
   if (a.counters[4] != 0) return;  // a bin list overflowed in this or an earlier segment: host regrows and replays the frame
   if (threadIdx.x == 0) s_next = 0;
+#if FDC_DEEP_MASK
+  // levels 9..15 start at 0 like the register levels; within a block every level is cleared by its first mask
+  // primitive before anything reads it, so once per CTA is enough
+  s_deep_mask[0][threadIdx.x] = s_deep_mask[1][threadIdx.x] = 0;
+#endif
   __syncthreads();
   const FrameView& f = a.frame;
   const int lane = threadIdx.x & 31;
@@ -669,6 +739,7 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
   const int tile0 = blockIdx.x * kTilesPerCta;
   const uint32_t n_blocks = (uint32_t)min(kTilesPerCta, n_tiles - tile0) * 8u;
   uint32_t* fb32 = reinterpret_cast<uint32_t*>(a.fb);
+  uint4* queue = s_queue[threadIdx.x >> 5];
 
   for (;;) {
     uint32_t blk = 0;
@@ -681,7 +752,8 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
     const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
     const bool valid = ix < f.W && iy < f.H;
     const float fx = (float)ix, fy = (float)iy;
-    const uint32_t n = a.tile_count[ty * f.tiles_x + tx];
+    const uint32_t tc = a.tile_count[ty * f.tiles_x + tx];
+    const uint32_t n = tc & kTileCountMask;
 
     Pixel px;
     {
@@ -696,9 +768,6 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
       px.b = __uint_as_float(kBiasBits | ((c >> 16) & 255u));
       px.a = __uint_as_float(kBiasBits | (c >> 24));
       px.mlo = px.mhi = 0;
-#if FDC_DEEP_MASK
-      s_deep_mask[0][threadIdx.x] = s_deep_mask[1][threadIdx.x] = 0;
-#endif
     }
 
     const uint2* __restrict__ list = reinterpret_cast<const uint2*>(a.tile_list + a.tile_start[ty * f.tiles_x + tx]);
@@ -725,36 +794,8 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
       start = n;  // block entirely outside the frame
     }
 
-    for (uint32_t base = start; base < n; base += 32) {
-      const uint32_t idx = base + lane;
-      uint2 e = make_uint2(0u, 0u);
-      if (idx < n) e = __ldg(&list[idx]);
-      uint32_t m = __ballot_sync(0xFFFFFFFFu, (e.y & ov_bit) != 0u);
-      if (a.stats) {
-        const uint32_t mf = __ballot_sync(0xFFFFFFFFu, (e.y & ov_bit) && (e.y & full_bit));
-        const uint32_t ms = __ballot_sync(0xFFFFFFFFu, (e.y & ov_bit) && !(e.y & TE_FAST));
-        if (lane == 0) {
-          atomicAdd(&a.stats[3], 1ull);
-          atomicAdd(&a.stats[0], (unsigned long long)__popc(m));
-          atomicAdd(&a.stats[1], (unsigned long long)__popc(mf));
-          atomicAdd(&a.stats[2], (unsigned long long)__popc(ms));
-        }
-      }
-      while (m) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t p = __shfl_sync(0xFFFFFFFFu, e.x, j);
-        const uint32_t info = __shfl_sync(0xFFFFFFFFu, e.y, j);
-        if (info & TE_FAST) {
-          const float4* S = reinterpret_cast<const float4*>(a.prims + p);
-          const bool full = (info & full_bit) != 0u;
-          if (info & ((15u << TE_DEPTH_SHIFT) | TE_RECTMASK)) shade_fast<true>(S, a.exts + p, a.atlas, a.rectmasks, info, full, fx, fy, px);
-          else shade_fast<false>(S, a.exts + p, a.atlas, a.rectmasks, info, full, fx, fy, px);
-        } else {
-          px = shade_prim(&a, a.prims + p, ix, iy, px);
-        }
-      }
-    }
+    if ((tc & kTileNeedsFullPath) == 0u && FDC_LEAN_LOOP && !a.stats) walk_list<true>(a, list, n, start, ov_bit, full_bit, queue, lane, ix, iy, fx, fy, px);
+    else walk_list<false>(a, list, n, start, ov_bit, full_bit, queue, lane, ix, iy, fx, fy, px);
 
     if (valid) {
       const uint32_t out = (__float_as_uint(px.r) & 255u) | ((__float_as_uint(px.g) & 255u) << 8) |

@@ -72,6 +72,11 @@ constexpr uint32_t TE_MASKW = 1u << 23;  // fast ClipAA mask write (PF_MASK_WRIT
 constexpr uint32_t TE_DEPTH_SHIFT = 24;  // 4 bits: texture-mask level read by content (written by TE_MASKW)
 constexpr uint32_t TE_MASKB = 1u << 28;  // PF_MASK_BEGIN: clear the level first
 constexpr uint32_t TE_RECTMASK = 1u << 29;  // content under a first-level analytic rect mask (PF_RECTMASK)
+// tile_count[tile]: bits 0..23 the number of entries; bit 31 set by the fine binner when the tile holds anything but
+// unmasked PF_FAST content (a general-path primitive, a mask write, content under a texture mask or a rect mask) --
+// such tiles are shaded by the full loop, all others by the call-free lean loop.
+constexpr uint32_t kTileCountMask = 0x00FFFFFFu;
+constexpr uint32_t kTileNeedsFullPath = 1u << 31;
 struct alignas(8) TileEntry {
   uint32_t pid, info;
 };

@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restri
   const int row0 = blockIdx.y * rows_per_cta;
   const int row1 = min(row0 + rows_per_cta, f.cby);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (kScatter && counters[2] > coarse_cap) return;  // overflow: host regrows and replays
+  if (kScatter && counters[kCntCoarseTotal] > coarse_cap) return;  // overflow: host regrows and replays
   uint4* wc_global = reinterpret_cast<uint4*>(warp_counts + ((size_t)chunk * gridDim.y + blockIdx.y) * (size_t)(kWarps * kSlots));
   const uint32_t rect = coarse_rect(prims, base_idx + threadIdx.x, n, f);
 
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(256) coarse_scan_kernel(uint32_t* __restrict__
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(&counters[3], 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) is_last = atomicAdd(&counters[kCntTicket], 1u) == gridDim.x - 1;
   __syncthreads();
   if (!is_last) return;
   __threadfence();
@@ -743,9 +743,9 @@ __global__ void __launch_bounds__(256) coarse_scan_kernel(uint32_t* __restrict__
   }
   if (threadIdx.x == 0) {
     cbin_start[0] = 0;
-    counters[2] = carry;
-    atomicMax(&counters[5], carry);  // per-frame maximum over segments (resolve_frame regrows from it)
-    if (carry > coarse_cap) { atomicOr(&counters[1], 1u); atomicOr(&counters[4], 1u); }
+    counters[kCntCoarseTotal] = carry;
+    atomicMax(&counters[kCntMaxCoarse], carry);  // per-frame maximum over segments (resolve_frame regrows from it)
+    if (carry > coarse_cap) { atomicOr(&counters[kCntOverflow], 1u); atomicOr(&counters[kCntStickyOverflow], 1u); }
   }
 }
 
@@ -877,7 +877,7 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
   __shared__ uint32_t s_base[64];
   __shared__ uint32_t s_cls[64];                   // != 0: the tile holds something the shade kernel's lean loop cannot take
   __shared__ uint32_t s_alloc;
-  if (!n_direct && counters[2] > coarse_cap) return;
+  if (!n_direct && counters[kCntCoarseTotal] > coarse_cap) return;
   const int b = blockIdx.x;
   const int cbx_i = b % f.cbx, cby_i = b / f.cbx;
   const uint32_t begin = n_direct ? 0u : cbin_start[b], end = n_direct ? n_direct : cbin_start[b + 1];
@@ -903,10 +903,10 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
         s_base[2 * lane + 1] = incl - c1;
         if (lane == 31) {
           const uint32_t tot = incl;
-          const uint32_t at = atomicAdd(&counters[0], tot);
-          atomicMax(&counters[6], at + tot);  // per-frame maximum of the tile-list size a segment needs
-          atomicAdd(&counters[7], tot);       // tile entries of the whole frame (statistics)
-          if (at + tot > tile_cap) { atomicOr(&counters[1], 2u); atomicOr(&counters[4], 2u); s_alloc = 0xFFFFFFFFu; }
+          const uint32_t at = atomicAdd(&counters[kCntCursor], tot);
+          atomicMax(&counters[kCntMaxTile], at + tot);  // per-frame maximum of the tile-list size a segment needs
+          atomicAdd(&counters[kCntSumEntries], tot);    // tile entries of the whole frame (statistics)
+          if (at + tot > tile_cap) { atomicOr(&counters[kCntOverflow], 2u); atomicOr(&counters[kCntStickyOverflow], 2u); s_alloc = 0xFFFFFFFFu; }
           else s_alloc = at;
         }
       }
@@ -915,7 +915,11 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
       if (threadIdx.x < 64) {
         const int t = threadIdx.x;
         const int tx = tile_x0 + (t & 7), ty = tile_y0 + (t >> 3);
-        if (tx < f.tiles_x && ty >= f.ty0 && ty < f.ty1) {
+        const bool in_band = tx < f.tiles_x && ty >= f.ty0 && ty < f.ty1;
+        // how many tiles need the shade kernel's full loop (its launch returns at once when there are none)
+        const uint32_t fullm = __ballot_sync(0xFFFFFFFFu, in_band && alloc != 0xFFFFFFFFu && s_cls[t] != 0u && s_run[t] != 0u);
+        if ((t & 31) == 0 && fullm) atomicAdd(&counters[kCntFullTiles], (uint32_t)__popc(fullm));
+        if (in_band) {
           tile_start[ty * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : alloc + s_base[t];
           tile_count[ty * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : (s_run[t] | (s_cls[t] ? kTileNeedsFullPath : 0u));
         }
@@ -1025,10 +1029,10 @@ void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& f, con
   const int n_bins = f.cbx * f.cby;
   const int n_chunks = (int)((n_prims + kChunk - 1) / kChunk);
   // tiles of the band start empty; per-segment counters: tile cursor, overflow flags, coarse total, scan ticket.
-  // counters[4..7] are per FRAME (sticky overflow flags, maxima of the list sizes, total entries): the caller zeroes
-  // them once per frame, so an overflow in any segment is still visible after later segments reset [0..3].
+  // The per-FRAME words (kCntStickyOverflow ...) are zeroed once per frame by the caller, so an overflow in any segment
+  // is still visible after later segments reset the per-segment words.
   cudaMemsetAsync(b.tile_count + (size_t)f.ty0 * f.tiles_x, 0, sizeof(uint32_t) * (size_t)(f.ty1 - f.ty0) * f.tiles_x, stream);
-  cudaMemsetAsync(b.counters, 0, sizeof(uint32_t) * 4, stream);
+  cudaMemsetAsync(b.counters, 0, sizeof(uint32_t) * kCntStickyOverflow, stream);
   if (n_prims == 0 || n_bins == 0) return;
   if ((size_t)n_prims * (size_t)n_bins <= (size_t)kDirectFineLimit) {
     // Small scene: three launches of coarse binning cost more than letting every bin look at every primitive.

@@ -656,7 +656,7 @@ int ensure_bin_buffers(fdc_ctx* ctx, uint32_t max_prims) {
   CK(ctx->d_cbin_start.reserve(n_bins + 1));
   CK(ctx->d_tile_start.reserve((size_t)f.tiles_x * f.tiles_y));
   CK(ctx->d_tile_count.reserve((size_t)f.tiles_x * f.tiles_y));
-  CK(ctx->d_counters.reserve(8));
+  CK(ctx->d_counters.reserve(kNumCounters));
   CK(ctx->d_coarse_list.reserve(std::max<size_t>((size_t)max_prims * 3 + n_bins * 4, 1u << 16)));
   CK(ctx->d_tile_list.reserve(std::max<size_t>((size_t)max_prims * 24 + (size_t)f.tiles_x * f.tiles_y * 2, 1u << 20)));
   return FDC_OK;
@@ -754,7 +754,7 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
   }
   // Per-frame counters (sticky overflow flags, list-size maxima, entry total): zeroed once here; launch_binning resets
   // only the per-segment words, so an overflow in ANY segment is still visible when the host looks after the frame.
-  CK(cudaMemsetAsync(ctx->d_counters.p + 4, 0, sizeof(uint32_t) * 4, st));
+  CK(cudaMemsetAsync(ctx->d_counters.p + kCntStickyOverflow, 0, sizeof(uint32_t) * (kNumCounters - kCntStickyOverflow), st));
   ctx->frame_resolved = false;
   // A frame that blends over the previous pixels (no clearMain) in several segments cannot simply be re-run after an
   // overflow in a later segment -- the earlier segments would be composited twice.  Keep the pre-frame pixels.
@@ -832,7 +832,7 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
           ss.frame.ty0 = r0;
           ss.frame.ty1 = r1;
           launch_shade(ss, st);
-          launches++;
+          launches += 2;
           CK(cudaEventRecord(ctx->ev_sub[sb], st));
           const int y0 = r0 * kTileH, y1 = std::min(r1 * kTileH, ctx->H);
           const size_t off = (size_t)y0 * ctx->W * 4, bytes = (size_t)(y1 - y0) * ctx->W * 4;
@@ -851,7 +851,7 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
         }
       } else {
         launch_shade(sa, st);
-        launches++;
+        launches += 2;  // lean + full kernel
       }
     }
     if (s.has_blur) {
@@ -916,10 +916,10 @@ int resolve_frame(fdc_ctx* ctx) {
   for (int attempt = 0; attempt < 5; attempt++) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->frame_resolved) return FDC_OK;
-    uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t c[kNumCounters] = {};
     if (!ctx->d_counters.p) return FDC_OK;
     CK(cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
-    ctx->stats.n_tile_entries = c[7];
+    ctx->stats.n_tile_entries = c[kCntSumEntries];
     if (ctx->n_ranks > 1 && ctx->flag_off && ctx->barrier_seq != ctx->frame_barrier_base) {
       uint32_t late = 0;
       uint32_t* err = reinterpret_cast<uint32_t*>(ctx->d_fb.p + ctx->flag_off) + kFlagError;
@@ -930,15 +930,15 @@ int resolve_frame(fdc_ctx* ctx) {
         return ctx->fail(FDC_ERR_STATE, "blur halo barrier timed out waiting for rank mask 0x%x (did every rank submit the frame?)", late);
       }
     }
-    if (c[4] == 0) {
+    if (c[kCntStickyOverflow] == 0) {
       ctx->frame_resolved = true;
       return FDC_OK;
     }
-    // overflow in some segment: c[5] / c[6] hold the largest coarse / tile list any segment needs
+    // overflow in some segment: kCntMaxCoarse / kCntMaxTile hold the largest coarse / tile list any segment needs
     if (attempt == 4) break;
     ctx->dbg_coarse_limit = ctx->dbg_tile_limit = 0;
-    if (c[4] & 1u) CK(ctx->d_coarse_list.reserve((size_t)c[5] + (c[5] >> 2) + 1024));
-    if (c[4] & 2u) CK(ctx->d_tile_list.reserve((size_t)c[6] + (c[6] >> 2) + 1024));
+    if (c[kCntStickyOverflow] & 1u) CK(ctx->d_coarse_list.reserve((size_t)c[kCntMaxCoarse] + (c[kCntMaxCoarse] >> 2) + 1024));
+    if (c[kCntStickyOverflow] & 2u) CK(ctx->d_tile_list.reserve((size_t)c[kCntMaxTile] + (c[kCntMaxTile] >> 2) + 1024));
     ctx->n_replays++;
     if (ctx->n_ranks > 1) {
       ctx->frame_resolved = true;  // checked; the verdict is "retry on every rank"
@@ -1869,12 +1869,12 @@ int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t off
   std::vector<uint32_t> start(n_tiles, 0), count(n_tiles, 0), calls(std::max<uint32_t>(s.count, 1));
   uint32_t c[4];
   CK(cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
-  if (c[1]) return ctx->fail(FDC_ERR_CAPACITY, "bin lists overflowed during debug readback");
+  if (c[kCntOverflow]) return ctx->fail(FDC_ERR_CAPACITY, "bin lists overflowed during debug readback");
   CK(cudaMemcpy(start.data(), ctx->d_tile_start.p, n_tiles * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(count.data(), ctx->d_tile_count.p, n_tiles * 4, cudaMemcpyDeviceToHost));
   if (s.count) CK(cudaMemcpy(calls.data(), ctx->d_prim_call.p + s.first, (size_t)s.count * 4, cudaMemcpyDeviceToHost));
-  std::vector<TileEntry> list(std::max<uint32_t>(c[0], 1));
-  if (c[0]) CK(cudaMemcpy(list.data(), ctx->d_tile_list.p, (size_t)c[0] * sizeof(TileEntry), cudaMemcpyDeviceToHost));
+  std::vector<TileEntry> list(std::max<uint32_t>(c[kCntCursor], 1));
+  if (c[kCntCursor]) CK(cudaMemcpy(list.data(), ctx->d_tile_list.p, (size_t)c[kCntCursor] * sizeof(TileEntry), cudaMemcpyDeviceToHost));
   size_t total = 0;
   const int ty0 = ctx->frame.ty0, ty1 = ctx->frame.ty1, tx_n = ctx->frame.tiles_x;
   for (int ty = ty0; ty < ty1; ty++)

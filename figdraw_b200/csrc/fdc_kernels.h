@@ -32,8 +32,7 @@ struct BinBuffers {
   uint32_t* tile_count;    // [tiles_x * tiles_y]
   TileEntry* tile_list;    // [tile_cap]
   uint32_t tile_cap;
-  uint32_t* counters;      // [8]: per segment 0 tile cursor, 1 overflow flags, 2 coarse total, 3 scan ticket;
-                           //      per frame 4 sticky overflow flags, 5 max coarse total, 6 max tile total, 7 sum of tile entries
+  uint32_t* counters;      // [kNumCounters], see fdc_types.h (kCnt...)
 };
 void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& frame, const BinBuffers& b,
                     cudaStream_t stream, int* n_launches);
@@ -46,7 +45,7 @@ struct ShadeArgs {
   const uint32_t* tile_start;
   const uint32_t* tile_count;
   const TileEntry* tile_list;
-  const uint32_t* counters;  // [4] sticky overflow flags of the frame: the kernel leaves the pixels untouched when set
+  const uint32_t* counters;  // kCntStickyOverflow set: the kernels leave the pixels untouched; kCntFullTiles: work for the full loop
   uint8_t* fb;               // RGBA8 W*H, top-left origin
   const uint8_t* backdrop;   // RGBA8 W*H (blurred copy for sdfModeBackdropBlur) or nullptr
   AtlasView atlas;

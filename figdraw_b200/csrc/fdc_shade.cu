@@ -28,6 +28,21 @@
 #ifndef FDC_SHADE_MIN_BLOCKS
 #define FDC_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef FDC_SPLIT_KERNELS
+#define FDC_SPLIT_KERNELS 1  // A/B switch: lean tiles in their own kernel when few tiles need the full loop
+#endif
+#ifndef FDC_LEAN_MIN_BLOCKS
+#define FDC_LEAN_MIN_BLOCKS 6  // resident CTAs per SM the lean kernel is compiled for (register budget 65536 / (256 * n))
+#endif
+#ifndef FDC_QPTR
+#define FDC_QPTR 1   // A/B switch: queue loop steps a pointer (0: index + base)
+#endif
+#ifndef FDC_FDIV
+#define FDC_FDIV 0   // A/B switch: tile -> (tx, ty) through a float reciprocal (0: integer division)
+#endif
+#ifndef FDC_LEAN_HAND
+#define FDC_LEAN_HAND 0  // A/B switch: hand-ordered visit in the lean loop (0: the generic shade_fast)
+#endif
 #ifndef FDC_LEAN_LOOP
 #define FDC_LEAN_LOOP 1  // A/B switch: call-free loop for tiles that hold only unmasked fast primitives
 #endif
@@ -471,6 +486,68 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
   blend(px, col.x, col.y, col.z, sa);
 }
 
+// The lean loop's visit: shade_fast<false, true> restated for the tiles that hold nothing but unmasked fast primitives,
+// with the loads ordered by hand.  The r02 profile of the generic version showed two exposed L1 latencies per partial
+// visit -- the colour was loaded first (the occluder shortcut needs it), the SDF quads q0..q3 only after that branch
+// had been resolved; here everything a visit needs is requested before anything is consumed.
+__device__ __forceinline__ void shade_lean(const float4* __restrict__ S, const PrimExt* __restrict__ E, const AtlasView& at, uint32_t info,
+                                           bool full, float fx, float fy, Pixel& px) {
+  if (info & TE_TEX) {
+    shade_fast<false, true>(S, E, at, nullptr, info, full, fx, fy, px);
+    return;
+  }
+  float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
+  if (!full) { q0 = __ldg(S + 0); q1 = __ldg(S + 1); q2 = __ldg(S + 2); q3 = __ldg(S + 3); }
+  float4 col;
+  if (info & TE_SOLID) {
+    col = __ldg(S + 4);
+  } else {
+    const float4* X = reinterpret_cast<const float4*>(E);
+    const float4 a0 = __ldg(X + 1), d0 = __ldg(X + 2), a1 = __ldg(X + 3);
+    if (info & TE_GRAD3) {
+      const float4 e0 = __ldg(X + 0), d1 = __ldg(X + 4);
+      const float tt = sat(fmaf(fx, e0.x, fmaf(fy, e0.y, e0.z)));
+      const bool lo = tt <= e0.w;
+      col.x = fmaf(lo ? d0.x : d1.x, tt, lo ? a0.x : a1.x);
+      col.y = fmaf(lo ? d0.y : d1.y, tt, lo ? a0.y : a1.y);
+      col.z = fmaf(lo ? d0.z : d1.z, tt, lo ? a0.z : a1.z);
+      col.w = fmaf(lo ? d0.w : d1.w, tt, lo ? a0.w : a1.w);
+    } else {
+      col.x = fmaf(d0.x, fx, fmaf(a1.x, fy, a0.x));
+      col.y = fmaf(d0.y, fx, fmaf(a1.y, fy, a0.y));
+      col.z = fmaf(d0.z, fx, fmaf(a1.z, fy, a0.z));
+      col.w = fmaf(d0.w, fx, fmaf(a1.w, fy, a0.w));
+    }
+  }
+  float sa = col.w * (1.0f / 255.0f);
+  if (!full) {
+    const float ppx = fmaf(fx, q0.x, q0.y), ppy = fmaf(fy, q0.z, q0.w);  // (p.x, -p.y)
+    const float apx = fabsf(ppx), apy = fabsf(ppy);
+    const bool inside = apx < q1.x && apy < q1.y;  // pixel centre inside the ceil'd quad
+    const float rr = ppx > 0.0f ? (ppy > 0.0f ? q2.x : q2.y) : (ppy > 0.0f ? q2.z : q2.w);
+    const float qx = apx - q1.z + rr, qy = apy - q1.w + rr;
+    const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
+    const float dist = fminf(fmaxf(qx, qy), 0.0f) + fast_sqrt(fmaf(mx, mx, my * my)) - rr;
+    const uint32_t kind = (info >> TE_KIND_SHIFT) & 3u;
+    float cov;
+    if (kind == 2u) {  // DropShadow: sd > 0 ? exp(-.5 (sd/sigma)^2) : 1
+      const float sd = fmaxf(dist - q3.y, 0.0f);
+      cov = fast_ex2(q3.w * sd * sd);
+    } else {  // ClipAA (f = 0) / AnnularAA: |d + f| - f with f = factor / 2
+      const float f = kind == 0u ? 0.0f : q3.x * 0.5f;
+      const float d = kind == 0u ? dist : fabsf(dist + f) - f;
+      cov = sat(fmaf(-q3.z, d, 0.5f));
+    }
+    sa = inside ? sa * cov : 0.0f;
+  } else if (info & TE_OCCLUDER) {
+    // opaque, coverage exactly 1 on the whole block: the store is round(src) whatever dst was (earlier primitives were
+    // skipped for this block, so the result must not depend on dst even in the last ulp)
+    px.r = col.x + kBias; px.g = col.y + kBias; px.b = col.z + kBias; px.a = 255.0f + kBias;
+    return;
+  }
+  blend(px, col.x, col.y, col.z, sa);
+}
+
 __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const Prim* __restrict__ P, int ix, int iy, Pixel px) {
   const ShadeArgs& a = *ap;
   const float4* Q = reinterpret_cast<const float4*>(P);
@@ -696,14 +773,25 @@ __device__ __forceinline__ void walk_list(const ShadeArgs& a, const uint2* __res
       queue[__popc(m & lt)] = make_uint4((uint32_t)addr, (uint32_t)(addr >> 32), e.y, e.x);
     }
     __syncwarp();
+#if FDC_QPTR
+    const uint4* __restrict__ qp = queue;
+    const uint4* const qe = queue + __popc(m);
+    for (; qp != qe; qp++) {
+      const uint4 q = *qp;  // same address in every lane: one broadcast
+#else
     const int cnt = __popc(m);
     for (int k = 0; k < cnt; k++) {
       const uint4 q = queue[k];  // same address in every lane: one broadcast
+#endif
       const float4* S = reinterpret_cast<const float4*>(((unsigned long long)q.y << 32) | (unsigned long long)q.x);
       const uint32_t info = q.z;
       const bool full = (info & full_bit) != 0u;
       if (kLean) {
+#if FDC_LEAN_HAND
+        shade_lean(S, a.exts + q.w, a.atlas, info, full, fx, fy, px);
+#else
         shade_fast<false, true>(S, a.exts + q.w, a.atlas, a.rectmasks, info, full, fx, fy, px);
+#endif
       } else if (info & TE_FAST) {
         if (info & ((15u << TE_DEPTH_SHIFT) | TE_RECTMASK)) shade_fast<true, false>(S, a.exts + q.w, a.atlas, a.rectmasks, info, full, fx, fy, px);
         else shade_fast<false, false>(S, a.exts + q.w, a.atlas, a.rectmasks, info, full, fx, fy, px);
@@ -721,16 +809,29 @@ __device__ __forceinline__ void walk_list(const ShadeArgs& a, const uint2* __res
 // warps of a CTA still work on neighbouring blocks of the same tiles at the same time, so the primitive records
 // they load stay shared in L1.
 
-template <int kTilesPerCta>
-__global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ ShadeArgs a) {
+// Two kernels share this body.  The LEAN kernel shades tiles whose lists hold only unmasked fast primitives; it contains
+// no call, no mask code and no general path, so it is compiled for a smaller register budget (40 instead of 64
+// registers, no stack frame) and keeps 48 instead of 32 warps resident per SM.  The FULL kernel contains both loops.
+// Which one shades the frame is decided on the device from the fine binner's count of full-path tiles, identically by
+// both launches:
+//   no tile needs the full loop (cfg3, cfg5): the lean kernel shades everything, the full launch returns at once;
+//   otherwise (masks, elliptical corners, rotated quads ... -- cfg2, cfg4): the full kernel shades every tile, picking
+//          the loop per tile, and the lean launch returns at once.  (Splitting a mixed frame between the two launches
+//          was measured slower: they run back to back on one stream, so the tail of the heavy full-path tiles is no
+//          longer hidden behind lean work -- cfg4 0.387 -> 0.430 ms.)
+template <int kTilesPerCta, bool kLeanKernel>
+__global__ void __launch_bounds__(256, kLeanKernel ? FDC_LEAN_MIN_BLOCKS : FDC_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ ShadeArgs a) {
   __shared__ uint32_t s_next;
   __shared__ uint4 s_queue[8][32];  // per warp: surviving entries of the current 32-entry step (address, info, index)
-  if (a.counters[4] != 0) return;  // a bin list overflowed in this or an earlier segment: host regrows and replays the frame
+  if (a.counters[kCntStickyOverflow] != 0) return;  // a bin list overflowed in this or an earlier segment: host regrows and replays the frame
+  // debug counters live in the full loop only
+  const bool all_lean = FDC_LEAN_LOOP && FDC_SPLIT_KERNELS && a.stats == nullptr && a.counters[kCntFullTiles] == 0u;
+  if (kLeanKernel != all_lean) return;
   if (threadIdx.x == 0) s_next = 0;
 #if FDC_DEEP_MASK
   // levels 9..15 start at 0 like the register levels; within a block every level is cleared by its first mask
   // primitive before anything reads it, so once per CTA is enough
-  s_deep_mask[0][threadIdx.x] = s_deep_mask[1][threadIdx.x] = 0;
+  if (!kLeanKernel) s_deep_mask[0][threadIdx.x] = s_deep_mask[1][threadIdx.x] = 0;
 #endif
   __syncthreads();
   const FrameView& f = a.frame;
@@ -740,6 +841,7 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
   const uint32_t n_blocks = (uint32_t)min(kTilesPerCta, n_tiles - tile0) * 8u;
   uint32_t* fb32 = reinterpret_cast<uint32_t*>(a.fb);
   uint4* queue = s_queue[threadIdx.x >> 5];
+  const float inv_tiles_x = 1.0f / (float)f.tiles_x;
 
   for (;;) {
     uint32_t blk = 0;
@@ -747,13 +849,21 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
     blk = __shfl_sync(0xFFFFFFFFu, blk, 0);
     if (blk >= n_blocks) break;
     const int tile = tile0 + (int)(blk >> 3), sub = (int)(blk & 7u);
+    // tile / tiles_x through a float reciprocal (exact: tile < 2^22, the +0.5 keeps the quotient off integer boundaries)
+#if FDC_FDIV
+    const int trow = (int)(((float)tile + 0.5f) * inv_tiles_x);
+    int tx = tile - trow * f.tiles_x, ty = f.ty0 + trow;
+    if (tx < 0) { tx += f.tiles_x; ty--; } else if (tx >= f.tiles_x) { tx -= f.tiles_x; ty++; }  // never taken below ~16K-px frames
+#else
     const int tx = tile % f.tiles_x, ty = f.ty0 + tile / f.tiles_x;
+#endif
     const int wx0 = tx * kTileW + (sub & 1) * 8, wy0 = ty * kTileH + (sub >> 1) * 4;
     const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
     const bool valid = ix < f.W && iy < f.H;
     const float fx = (float)ix, fy = (float)iy;
     const uint32_t tc = a.tile_count[ty * f.tiles_x + tx];
     const uint32_t n = tc & kTileCountMask;
+    const bool lean_tile = FDC_LEAN_LOOP && (tc & kTileNeedsFullPath) == 0u && a.stats == nullptr;
 
     Pixel px;
     {
@@ -794,7 +904,7 @@ __global__ void __launch_bounds__(256, FDC_SHADE_MIN_BLOCKS) shade_kernel(const 
       start = n;  // block entirely outside the frame
     }
 
-    if ((tc & kTileNeedsFullPath) == 0u && FDC_LEAN_LOOP && !a.stats) walk_list<true>(a, list, n, start, ov_bit, full_bit, queue, lane, ix, iy, fx, fy, px);
+    if (kLeanKernel || lean_tile) walk_list<true>(a, list, n, start, ov_bit, full_bit, queue, lane, ix, iy, fx, fy, px);
     else walk_list<false>(a, list, n, start, ov_bit, full_bit, queue, lane, ix, iy, fx, fy, px);
 
     if (valid) {
@@ -817,10 +927,19 @@ void launch_shade(const ShadeArgs& a, cudaStream_t stream) {
   // Tiles per CTA: 8 keeps neighbouring blocks' records shared in L1, but a band of an 8-GPU partition or a small frame
   // must still give every SM several waves of CTAs (148 SMs x 4 resident CTAs): aim for >= 6 waves.
   const int slots = 148 * FDC_SHADE_MIN_BLOCKS * FDC_SHADE_WAVES;
-  if (n_tiles >= 8 * slots) shade_kernel<8><<<(n_tiles + 7) / 8, 256, 0, stream>>>(a);
-  else if (n_tiles >= 4 * slots) shade_kernel<4><<<(n_tiles + 3) / 4, 256, 0, stream>>>(a);
-  else if (n_tiles >= 2 * slots) shade_kernel<2><<<(n_tiles + 1) / 2, 256, 0, stream>>>(a);
-  else shade_kernel<1><<<n_tiles, 256, 0, stream>>>(a);
+  if (n_tiles >= 8 * slots) {
+    shade_kernel<8, true><<<(n_tiles + 7) / 8, 256, 0, stream>>>(a);
+    shade_kernel<8, false><<<(n_tiles + 7) / 8, 256, 0, stream>>>(a);
+  } else if (n_tiles >= 4 * slots) {
+    shade_kernel<4, true><<<(n_tiles + 3) / 4, 256, 0, stream>>>(a);
+    shade_kernel<4, false><<<(n_tiles + 3) / 4, 256, 0, stream>>>(a);
+  } else if (n_tiles >= 2 * slots) {
+    shade_kernel<2, true><<<(n_tiles + 1) / 2, 256, 0, stream>>>(a);
+    shade_kernel<2, false><<<(n_tiles + 1) / 2, 256, 0, stream>>>(a);
+  } else {
+    shade_kernel<1, true><<<n_tiles, 256, 0, stream>>>(a);
+    shade_kernel<1, false><<<n_tiles, 256, 0, stream>>>(a);
+  }
 }
 
 }  // namespace fdc

@@ -72,6 +72,21 @@ constexpr uint32_t TE_MASKW = 1u << 23;  // fast ClipAA mask write (PF_MASK_WRIT
 constexpr uint32_t TE_DEPTH_SHIFT = 24;  // 4 bits: texture-mask level read by content (written by TE_MASKW)
 constexpr uint32_t TE_MASKB = 1u << 28;  // PF_MASK_BEGIN: clear the level first
 constexpr uint32_t TE_RECTMASK = 1u << 29;  // content under a first-level analytic rect mask (PF_RECTMASK)
+// Device counters of the binning pipeline (BinBuffers::counters).  Words 0..7 are per SEGMENT (launch_binning zeroes
+// them), words 8..15 per FRAME (zeroed once by execute_frame): an overflow in any segment stays visible to the host.
+enum : int {
+  kCntCursor = 0,          // tile-list cursor: entries reserved so far (= size the segment needs when it overflows)
+  kCntOverflow = 1,        // bit 0 coarse list, bit 1 tile list overflowed in this segment
+  kCntCoarseTotal = 2,     // entries of the coarse list
+  kCntTicket = 3,          // coarse_scan_kernel's last-CTA ticket
+  kCntFullTiles = 4,       // tiles of this segment that need the shade kernel's full loop
+  kCntStickyOverflow = 8,  // OR of kCntOverflow over the frame's segments
+  kCntMaxCoarse = 9,       // largest coarse list any segment needs
+  kCntMaxTile = 10,        // largest tile list any segment needs
+  kCntSumEntries = 11,     // tile entries of the whole frame (statistics)
+  kNumCounters = 16
+};
+
 // tile_count[tile]: bits 0..23 the number of entries; bit 31 set by the fine binner when the tile holds anything but
 // unmasked PF_FAST content (a general-path primitive, a mask write, content under a texture mask or a rect mask) --
 // such tiles are shaded by the full loop, all others by the call-free lean loop.

@@ -75,6 +75,10 @@ def bench_config(name: str, trace, world: int, gather: str = "nccl") -> dict:
     object as the GPU arm it is compared with."""
     if world == 1:
         part = "single GPU"
+    elif gather in ("mc", "auto"):
+        part = f"{world} tile-row bands, band all-gather fused into the shade kernel's copy-out (NVSwitch multicast stores)"
+    elif gather == "symm-p2p":
+        part = f"{world} tile-row bands, band all-gather fused into the shade kernel's copy-out (peer stores, symmetric memory)"
     elif gather == "p2p":
         part = f"{world} tile-row bands, band all-gather fused into the shade kernel (peer stores over NVLink)"
     elif gather == "ce":
@@ -333,10 +337,41 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
     band_rows, _layout = bands.band_layout(H, world)
     # a backdrop blur under a band partition reads halo rows out of the neighbours' framebuffers: peer mappings needed
     has_blur = bool((trace.calls["op"] == 13).any())
-    use_p2p = world > 1 and (args.gather in ("p2p", "ce") or has_blur)
+    gather_mode = args.gather if world > 1 else "none"
+    symm_t = None
+    if gather_mode in ("auto", "mc"):
+        # Framebuffer in torch symmetric memory: every rank maps every copy, and behind an NVSwitch there is a multicast
+        # mapping -- the shade kernel's copy-out then writes each finished chunk once and the switch delivers it to all
+        # ranks (fdc_bind_shared_framebuffer).  No collective call in the frame loop; a flag barrier ends the frame.
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            nbytes = ((W * band_rows * world * 4 + 255) & ~255) + 4096
+            symm_t = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+            hdl = symm.rendezvous(symm_t, dist.group.WORLD)
+            mc_ptr = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            ok = torch.tensor([1 if (mc_ptr or gather_mode == "mc") else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                raise RuntimeError("no multicast mapping on some rank")
+            symm_t.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            ctx.bindSharedFramebuffer(symm_t.data_ptr(), nbytes, [int(p) for p in hdl.buffer_ptrs], mc_ptr, W, band_rows * world)
+            gather_mode = "mc" if mc_ptr else "symm-p2p"
+        except Exception as e:  # noqa: BLE001
+            if args.gather == "mc":
+                raise
+            sys.stderr.write(f"[bench] symmetric-memory framebuffer unavailable ({e!r}); falling back to NCCL all-gather\n")
+            symm_t = None
+            gather_mode = "nccl"
+    use_p2p = world > 1 and symm_t is None and (gather_mode in ("p2p", "ce") or has_blur)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
     token = None
-    if use_p2p:
+    fb = None
+    if symm_t is not None:
+        fb = symm_t[: band_rows * world * W * 4].view(band_rows * world, W, 4)
+    elif use_p2p:
         # Fused all-gather: every rank's shade kernel stores its finished pixels into all peers' framebuffers over
         # NVLink (CUDA IPC mappings); a one-element NCCL all-reduce on the same stream is the completion barrier.
         ctx.reserveFramebuffer(W, band_rows * world)
@@ -344,10 +379,11 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
         dist.all_gather_object(handles, ctx.framebufferIpcHandle())
         peers = [0 if r == rank else ctx.openPeerFramebuffer(handles[r]) for r in range(world)]
         ctx.setPeerFramebuffers(peers)
-        if args.gather == "ce":
+        if gather_mode == "ce":
             ctx.setPeerGather("copy", args.sub_bands)
         token = torch.zeros(1, dtype=torch.int32, device=dev)
-        fb = None
+        if gather_mode == "nccl":
+            gather_mode = "p2p"
     else:
         # Framebuffer owned by torch so NCCL can all-gather the bands in place; rows padded to equal bands.
         fb = torch.zeros((band_rows * world, W, 4), dtype=torch.uint8, device=dev)
@@ -377,8 +413,8 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
     prepared = prepare_pinned(calls_np)
 
     def gather():
-        if world == 1:
-            return
+        if world == 1 or symm_t is not None:
+            return  # single GPU, or fused into the shade kernel's copy-out (+ the frame's own flag barrier)
         if use_p2p:
             dist.all_reduce(token)  # all ranks' shade kernels (and their peer stores) are complete after this
         else:
@@ -491,7 +527,7 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
         torch.cuda.synchronize()
         if rank == 0:
             whole = np.empty((H, W, 4), dtype=np.uint8)
-            if use_p2p:
+            if fb is None:
                 ctx._ck(ctx._lib.fdc_read_pixels(ctx._h, 0, 0, W, H, whole.ctypes.data))
             else:
                 whole[:] = fb[:H].cpu().numpy()
@@ -515,7 +551,7 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
            "depth": depth, "shade_ms": shade_ms, "bin_ms": bin_ms, "clocks": clocks, "launches_per_frame": launches_per_frame,
            "n_tile_entries": int(stats.n_tile_entries), "h2d": int(prepared_upload_bytes(prepared)), "out_np": out_np,
            "calls_np": calls_np, "gathered_ok": gathered_ok, "single_gpu_ms": single_gpu_ms, "use_p2p": use_p2p,
-           "gather": "p2p" if (use_p2p and args.gather == "nccl") else args.gather}
+           "gather": gather_mode}
     ctx.close()
     return res
 
@@ -530,9 +566,10 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-8k", action="store_true", help="N > 1: skip the extra cfg5_8k measurement")
-    ap.add_argument("--gather", default="nccl", choices=["p2p", "nccl", "ce"],
-                    help="N>1: NCCL all-gather of the bands (nccl), fused peer stores from the shade kernel (p2p), or copy "
-                         "engines shipping finished band slices to the peers while the next slice is shaded (ce)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "mc", "p2p", "nccl", "ce"],
+                    help="N>1: how the bands reach every rank -- NVSwitch multicast stores fused into the shade kernel's copy-out "
+                         "(mc; needs torch symmetric memory), peer stores over IPC mappings (p2p), NCCL all-gather after the frame "
+                         "(nccl), copy engines shipping band slices (ce); auto = mc when available, else nccl")
     ap.add_argument("--sub-bands", type=int, default=4)
     ap.add_argument("--records", default=None, choices=["compact", "full"],
                     help="e2e upload: 64-byte fdc_rect64 records for rounded rects with circular corners, or 128-byte fdc_call only")

@@ -259,6 +259,8 @@ struct fdc_ctx {
   bool frame_resolved = false;     // resolve_frame has already checked the frame in flight
   uint32_t dbg_coarse_limit = 0, dbg_tile_limit = 0;  // fdc_debug_limit_lists: pretend the bin lists are this small (0: real size)
   uint8_t* ext_fb = nullptr;
+  uint8_t* mc_fb = nullptr;        // NVSwitch multicast mapping of the (shared) framebuffer, or nullptr
+  bool frame_barrier = false;      // end every frame with a cross-rank flag barrier (shared framebuffer: the gather is fused)
   DevBuf<uint8_t*> d_peers;
   DevBuf<fdc_rect64> d_rects64;    // compact draw records of this frame (fdc_submit_rects64)
   uint32_t n_rects64 = 0;
@@ -738,9 +740,9 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
   rc = ensure_bin_buffers(ctx, max_prims);
   if (rc) return rc;
   const size_t fb_bytes = (size_t)ctx->W * ctx->H * 4;
+  if (ctx->flag_off && fb_bytes > ctx->flag_off)
+    return ctx->fail(FDC_ERR_CAPACITY, "frame larger than the framebuffer reserved with fdc_reserve_framebuffer / fdc_bind_shared_framebuffer");
   if (!ctx->ext_fb) {
-    if (ctx->flag_off && fb_bytes > ctx->flag_off)
-      return ctx->fail(FDC_ERR_CAPACITY, "frame larger than the framebuffer reserved with fdc_reserve_framebuffer");
     const size_t had = ctx->d_fb.cap;
     CK(ctx->d_fb.reserve(fb_bytes));
     // a new framebuffer starts transparent black: a first frame without clearMain blends over defined pixels
@@ -771,12 +773,14 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
   }
   ctx->frame_barrier_base = ctx->barrier_seq;
   const bool banded_blur = ctx->n_ranks > 1 && any_blur;
+  const bool end_barrier = ctx->n_ranks > 1 && ctx->frame_barrier && ctx->n_peers == ctx->n_ranks && ctx->flag_off != 0;
   uint32_t* flag_ptrs[kMaxRanks] = {};
-  if (banded_blur) {
-    if (ctx->n_peers != ctx->n_ranks || ctx->flag_off == 0 || ctx->ext_fb)
-      return ctx->fail(FDC_ERR_STATE, "backdrop blur under a tile-band partition needs fdc_reserve_framebuffer + fdc_set_peer_framebuffers");
+  if (banded_blur || end_barrier) {
+    if (ctx->n_peers != ctx->n_ranks || ctx->flag_off == 0)
+      return ctx->fail(FDC_ERR_STATE, "backdrop blur under a tile-band partition needs a framebuffer the peers can reach: "
+                                      "fdc_reserve_framebuffer + fdc_set_peer_framebuffers, or fdc_bind_shared_framebuffer");
     for (int r = 0; r < ctx->n_ranks; r++) {
-      uint8_t* base = (r == ctx->rank || !ctx->h_peers[r]) ? ctx->d_fb.p : ctx->h_peers[r];
+      uint8_t* base = (r == ctx->rank || !ctx->h_peers[r]) ? ctx->fb() : ctx->h_peers[r];
       flag_ptrs[r] = reinterpret_cast<uint32_t*>(base + ctx->flag_off);
     }
   }
@@ -809,14 +813,18 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
       sa.clear_rgba8 = ctx->clear_rgba8;
       const bool last = si + 1 == ctx->segments.size();
       sa.stats = ctx->want_stats ? ctx->d_stats.p : nullptr;
-      sa.peers = (last && ctx->n_peers > 0) ? ctx->d_peers.p : nullptr;
-      sa.n_peers = (last && ctx->n_peers > 0) ? ctx->n_peers : 0;
+      // the band reaches the other ranks from the last segment's copy-out: one multicast store per chunk when the
+      // framebuffer has an NVSwitch multicast mapping, else one store per peer
+      sa.multicast = (last && ctx->n_ranks > 1) ? ctx->mc_fb : nullptr;
+      sa.peers = (last && ctx->n_peers > 0 && !sa.multicast) ? ctx->d_peers.p : nullptr;
+      sa.n_peers = (last && ctx->n_peers > 0 && !sa.multicast) ? ctx->n_peers : 0;
+      sa.fence_at_exit = (sa.n_peers > 0 || sa.multicast) && !end_barrier;
       if (pending_wait) {
         launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, pending_wait, st);
         pending_wait = 0;
         launches++;
       }
-      if (last && ctx->n_peers > 0 && ctx->gather_mode == FDC_GATHER_COPY && !ctx->ext_fb) {
+      if (last && ctx->n_peers > 0 && ctx->gather_mode == FDC_GATHER_COPY && !ctx->ext_fb && !ctx->mc_fb) {
         // Copy-engine gather: shade the band slice by slice; a finished slice travels to every peer over NVLink
         // (cudaMemcpyAsync on side streams) while the SMs shade the next one.
         sa.peers = nullptr;
@@ -874,7 +882,7 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
         ba.n_src = ctx->n_ranks;
         ba.band_px = std::max(1, ((ctx->frame.tiles_y + ctx->n_ranks - 1) / ctx->n_ranks) * kTileH);
         for (int r = 0; r < ctx->n_ranks; r++)
-          ba.src_rank[r] = (r == ctx->rank || !ctx->h_peers[r]) ? ctx->d_fb.p : ctx->h_peers[r];
+          ba.src_rank[r] = (r == ctx->rank || !ctx->h_peers[r]) ? ctx->fb() : ctx->h_peers[r];
       }
       ba.src = ctx->fb();
       ba.temp = ctx->d_temp.p;
@@ -894,6 +902,13 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
   if (pending_wait) {  // do not let the next frame's shade overwrite rows a neighbour may still be reading
     launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, pending_wait, st);
     launches++;
+  }
+  if (end_barrier) {
+    // Fused gather: once every rank has passed this barrier, every rank's framebuffer holds the whole frame.
+    const uint32_t v = ++ctx->barrier_seq;
+    launch_signal_flags(flag_ptrs, ctx->n_ranks, ctx->rank, v, st);
+    launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, v, st);
+    launches += 2;
   }
   cudaEventRecord(ctx->ev_end, st);
   CK(cudaGetLastError());
@@ -922,7 +937,7 @@ int resolve_frame(fdc_ctx* ctx) {
     ctx->stats.n_tile_entries = c[kCntSumEntries];
     if (ctx->n_ranks > 1 && ctx->flag_off && ctx->barrier_seq != ctx->frame_barrier_base) {
       uint32_t late = 0;
-      uint32_t* err = reinterpret_cast<uint32_t*>(ctx->d_fb.p + ctx->flag_off) + kFlagError;
+      uint32_t* err = reinterpret_cast<uint32_t*>(ctx->fb() + ctx->flag_off) + kFlagError;
       CK(cudaMemcpy(&late, err, 4, cudaMemcpyDeviceToHost));
       if (late) {
         CK(cudaMemset(err, 0, 4));
@@ -1394,9 +1409,9 @@ int fdc_draw_backdrop_blur(fdc_ctx* ctx, const float rect[4], const float radii_
   if (blur_radius <= 0.0f || rect[2] <= 0.0f || rect[3] <= 0.0f) return FDC_OK;  // glcontext.nim:1791-1792
   if (!ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "draw outside beginFrame/endFrame");
   if (ctx->mask_begun) return ctx->fail(FDC_ERR_STATE, "drawBackdropBlur inside beginMask/endMask is not supported");
-  if (ctx->n_ranks > 1 && (ctx->n_peers != ctx->n_ranks || ctx->flag_off == 0 || ctx->ext_fb))
+  if (ctx->n_ranks > 1 && (ctx->n_peers != ctx->n_ranks || ctx->flag_off == 0))
     return ctx->fail(FDC_ERR_STATE, "backdrop blur under a tile-band partition reads halo rows from the neighbours' framebuffers: "
-                                    "call fdc_reserve_framebuffer and fdc_set_peer_framebuffers (all ranks) first");
+                                    "call fdc_reserve_framebuffer and fdc_set_peer_framebuffers, or fdc_bind_shared_framebuffer (all ranks) first");
   Segment& s = ctx->segments.back();
   s.has_blur = true;
   s.blur_radius = blur_radius;
@@ -1722,6 +1737,48 @@ int fdc_set_peer_framebuffers(fdc_ctx* ctx, void* const* device_ptrs, int n) {
     CK(ctx->d_peers.reserve((size_t)n));
     CK(cudaMemcpy(ctx->d_peers.p, device_ptrs, sizeof(void*) * n, cudaMemcpyHostToDevice));
   }
+  return FDC_OK;
+}
+
+// A framebuffer the host allocated so that every rank can reach every copy (CUDA VMM / symmetric memory): this rank's
+// mapping, the peers' mappings and -- when the GPUs sit behind an NVSwitch -- the multicast mapping through which one
+// store lands in all copies.  `bytes` must cover width * rows * 4 pixels + 4096 bytes of cross-rank flags.
+int fdc_bind_shared_framebuffer(fdc_ctx* ctx, void* local_ptr, size_t bytes, void* const* peer_ptrs, int n, void* multicast_ptr,
+                                int width, int rows) {
+  if (!ctx || !local_ptr || width <= 0 || rows <= 0 || n != ctx->n_ranks || (n && !peer_ptrs)) return FDC_ERR_INVALID;
+  if (ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "cannot rebind the framebuffer inside a frame");
+  CK(cudaSetDevice(ctx->device));
+  int rc = resolve_frame(ctx);
+  if (rc) return rc;
+  const size_t pix = (((size_t)width * rows * 4) + 255) & ~(size_t)255;
+  if (bytes < pix + 4096) return ctx->fail(FDC_ERR_INVALID, "shared framebuffer needs %zu bytes (pixels + 4096 bytes of flags), got %zu", pix + 4096, bytes);
+  if (n > kMaxRanks) return ctx->fail(FDC_ERR_CAPACITY, "at most %d ranks", kMaxRanks);
+  ctx->ext_fb = (uint8_t*)local_ptr;
+  ctx->mc_fb = (uint8_t*)multicast_ptr;
+  ctx->flag_off = pix;
+  ctx->barrier_seq = 0;
+  ctx->frame_barrier = true;
+  ctx->n_peers = n;
+  ctx->h_peers.assign(n, nullptr);
+  for (int r = 0; r < n; r++) ctx->h_peers[r] = (r == ctx->rank) ? (uint8_t*)local_ptr : (uint8_t*)peer_ptrs[r];
+  CK(ctx->d_peers.reserve((size_t)n));
+  CK(cudaMemcpy(ctx->d_peers.p, ctx->h_peers.data(), sizeof(void*) * n, cudaMemcpyHostToDevice));
+  CK(cudaMemsetAsync((uint8_t*)local_ptr + pix, 0, 4096, ctx->stream));  // flags start at 0 on every rank
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->n_ranks > 1) {  // blur scratch up front: no allocation while peers spin on our flags
+    CK(ctx->d_backdrop.reserve((size_t)width * rows * 4));
+    CK(ctx->d_temp.reserve((size_t)width * rows * 4));
+  }
+  return FDC_OK;
+}
+
+// The cross-rank flag barrier that ends every frame on a shared framebuffer (default on).  A host that synchronises the
+// ranks itself, or that sizes several contexts of one process one after the other, can switch it off.
+int fdc_set_frame_barrier(fdc_ctx* ctx, int enabled) {
+  if (!ctx) return FDC_ERR_INVALID;
+  int rc = resolve_frame(ctx);
+  if (rc) return rc;
+  ctx->frame_barrier = enabled != 0;
   return FDC_OK;
 }
 

@@ -55,6 +55,8 @@ struct ShadeArgs {
   unsigned long long* stats; // optional [8] debug counters (nullptr in production): visits partial/full/slow, entries, occl steps
   uint8_t* const* peers;     // optional peer framebuffers (device array of n_peers pointers) or nullptr
   int n_peers;
+  uint8_t* multicast;        // optional NVSwitch multicast mapping of the framebuffer (all ranks' copies) or nullptr
+  int fence_at_exit;         // system-scope fence after the remote stores (no flag barrier follows on the stream)
 };
 void launch_shade(const ShadeArgs& a, cudaStream_t stream);
 

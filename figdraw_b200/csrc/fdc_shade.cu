@@ -821,13 +821,15 @@ __device__ __forceinline__ void walk_list(const ShadeArgs& a, const uint2* __res
 //          longer hidden behind lean work -- cfg4 0.387 -> 0.430 ms.)
 template <int kTilesPerCta, bool kLeanKernel>
 __global__ void __launch_bounds__(256, kLeanKernel ? FDC_LEAN_MIN_BLOCKS : FDC_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ ShadeArgs a) {
-  __shared__ uint32_t s_next;
+  __shared__ uint32_t s_next, s_dirty;
   __shared__ uint4 s_queue[8][32];  // per warp: surviving entries of the current 32-entry step (address, info, index)
+  // finished pixels of the CTA's tiles, written out at the end as 16-byte row chunks (see copy-out below)
+  __shared__ __align__(16) uint32_t s_out[kTilesPerCta][kTileW * kTileH];
   if (a.counters[kCntStickyOverflow] != 0) return;  // a bin list overflowed in this or an earlier segment: host regrows and replays the frame
   // debug counters live in the full loop only
   const bool all_lean = FDC_LEAN_LOOP && FDC_SPLIT_KERNELS && a.stats == nullptr && a.counters[kCntFullTiles] == 0u;
   if (kLeanKernel != all_lean) return;
-  if (threadIdx.x == 0) s_next = 0;
+  if (threadIdx.x == 0) { s_next = 0; s_dirty = 0; }
 #if FDC_DEEP_MASK
   // levels 9..15 start at 0 like the register levels; within a block every level is cleared by its first mask
   // primitive before anything reads it, so once per CTA is enough
@@ -872,7 +874,7 @@ __global__ void __launch_bounds__(256, kLeanKernel ? FDC_LEAN_MIN_BLOCKS : FDC_S
       // A later segment of the frame (after a backdrop blur) that paints nothing in this tile leaves its pixels alone.
       // (Both loads above are in flight together; peers still need the band's final pixels, so not when the gather is
       // fused into this kernel.)
-      if (n == 0u && a.load_dst && a.n_peers == 0) continue;
+      if (n == 0u && a.load_dst && a.n_peers == 0 && a.multicast == nullptr) continue;
       px.r = __uint_as_float(kBiasBits | (c & 255u));
       px.g = __uint_as_float(kBiasBits | ((c >> 8) & 255u));
       px.b = __uint_as_float(kBiasBits | ((c >> 16) & 255u));
@@ -907,18 +909,65 @@ __global__ void __launch_bounds__(256, kLeanKernel ? FDC_LEAN_MIN_BLOCKS : FDC_S
     if (kLeanKernel || lean_tile) walk_list<true>(a, list, n, start, ov_bit, full_bit, queue, lane, ix, iy, fx, fy, px);
     else walk_list<false>(a, list, n, start, ov_bit, full_bit, queue, lane, ix, iy, fx, fy, px);
 
-    if (valid) {
+    {
       const uint32_t out = (__float_as_uint(px.r) & 255u) | ((__float_as_uint(px.g) & 255u) << 8) |
                            ((__float_as_uint(px.b) & 255u) << 16) | ((__float_as_uint(px.a) & 255u) << 24);
-      fb32[(size_t)iy * f.W + ix] = out;
-      // fused band all-gather: the finished pixel goes straight to every peer's framebuffer over NVLink
-      for (int k = 0; k < a.n_peers; k++) {
-        uint32_t* peer = reinterpret_cast<uint32_t*>(a.peers[k]);
-        if (peer && peer != fb32) peer[(size_t)iy * f.W + ix] = out;
+      const int tl = (int)(blk >> 3);
+      s_out[tl][((sub >> 1) * 4 + (lane >> 3)) * kTileW + (sub & 1) * 8 + (lane & 7)] = out;
+      if (lane == 0) atomicOr(&s_dirty, 1u << tl);
+    }
+  }
+
+  // Copy-out: the CTA's finished tiles leave shared memory as 16-byte chunks, consecutive threads on consecutive
+  // addresses of a pixel row across the CTA's tiles (128-bit coalesced stores; up to 512 contiguous bytes per row
+  // instead of one 32-byte segment per warp row).  The same chunks are what reaches the other GPUs of a tile-band
+  // partition -- through the NVSwitch multicast mapping of the framebuffer (one multimem.st lands in every GPU's
+  // copy, the band all-gather costs no extra pass and no extra kernel) or as plain stores into each peer's framebuffer.
+  __syncthreads();
+  const uint32_t dirty = s_dirty;
+  if (dirty == 0u) return;
+  const bool vec_ok = (f.W & 3) == 0;
+  uint8_t* const mc = a.multicast;
+  for (int c = (int)threadIdx.x; c < kTilesPerCta * 64; c += 256) {
+    const int q = c & 3, tl = (c >> 2) % kTilesPerCta, r = (c >> 2) / kTilesPerCta;
+    if (!((dirty >> tl) & 1u)) continue;
+    const int tile = tile0 + tl;
+    const int trow = tile / f.tiles_x;
+    const int x = (tile - trow * f.tiles_x) * kTileW + q * 4, y = (f.ty0 + trow) * kTileH + r;
+    if (y >= f.H || x >= f.W) continue;
+    const uint4 v = *reinterpret_cast<const uint4*>(&s_out[tl][r * kTileW + q * 4]);
+    const size_t off = ((size_t)y * f.W + x) * 4;
+    if (vec_ok) {
+      if (mc) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + off), "f"(__uint_as_float(v.x)),
+                     "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                     : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(a.fb + off) = v;
+        for (int k = 0; k < a.n_peers; k++) {
+          uint8_t* peer = a.peers[k];
+          if (peer && peer != a.fb) *reinterpret_cast<uint4*>(peer + off) = v;
+        }
+      }
+    } else {
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      for (int i = 0; i < 4 && x + i < f.W; i++) {
+        if (mc) {
+          asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(mc + off + 4 * i), "r"(w[i]) : "memory");
+        } else {
+          *reinterpret_cast<uint32_t*>(a.fb + off + 4 * i) = w[i];
+          for (int k = 0; k < a.n_peers; k++) {
+            uint8_t* peer = a.peers[k];
+            if (peer && peer != a.fb) *reinterpret_cast<uint32_t*>(peer + off + 4 * i) = w[i];
+          }
+        }
       }
     }
   }
-  if (a.n_peers > 0) __threadfence_system();
+  // Remote stores are ordered for the peers by the release that follows on this stream: the frame's flag barrier
+  // (signal_flags_kernel fences at system scope before it stores the flag).  Only a host that brings its own barrier
+  // (legacy peer-store path) needs the fence here -- it costs every CTA a round trip before it can retire.
+  if (a.fence_at_exit) __threadfence_system();
 }
 
 void launch_shade(const ShadeArgs& a, cudaStream_t stream) {

@@ -366,6 +366,17 @@ class CudaContext(BackendContext):
         """"stores": the shade kernel writes every pixel to every peer; "copy": copy engines ship finished slices."""
         self._ck(self._lib.fdc_set_peer_gather(self._h, {"stores": 0, "copy": 1}[mode], int(subBands)))
 
+    def bindSharedFramebuffer(self, localPtr: int, nbytes: int, peerPtrs: Sequence[int], multicastPtr: int, width: int,
+                              rows: int):
+        """A framebuffer every rank can reach (torch symmetric memory): peers' mappings + the NVSwitch multicast mapping.
+        The band all-gather is then fused into the shade kernel's copy-out and every frame ends with a flag barrier."""
+        arr = (ctypes.c_void_p * len(peerPtrs))(*[ctypes.c_void_p(p) for p in peerPtrs])
+        self._ck(self._lib.fdc_bind_shared_framebuffer(self._h, ctypes.c_void_p(localPtr), int(nbytes), arr, len(peerPtrs),
+                                                       ctypes.c_void_p(multicastPtr or 0), int(width), int(rows)))
+
+    def setFrameBarrier(self, enabled: bool):
+        self._ck(self._lib.fdc_set_frame_barrier(self._h, 1 if enabled else 0))
+
     def setPeerFramebuffers(self, ptrs: Sequence[int]):
         arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])
         self._ck(self._lib.fdc_set_peer_framebuffers(self._h, arr, len(ptrs)))

@@ -270,6 +270,16 @@ void* fdc_stream(fdc_ctx* ctx);
  * After every rank's frame has completed (any cross-rank barrier on fdc_stream) each framebuffer holds the
  * whole frame. */
 int fdc_set_peer_framebuffers(fdc_ctx* ctx, void* const* device_ptrs, int n);
+/* Multi-GPU with a framebuffer every rank can reach (the host allocates it: CUDA VMM / torch symmetric memory): this
+ * rank's mapping (`bytes` >= width*rows*4 rounded up to 256, + 4096 bytes of cross-rank flags), the n_ranks peers'
+ * mappings of THEIR copies (own entry ignored) and, behind an NVSwitch, the multicast mapping of all copies (or NULL).
+ * With a multicast mapping the shade kernel's copy-out writes every finished 16-byte chunk ONCE with multimem.st and
+ * the switch delivers it to all ranks -- the band all-gather is fused into the kernel; without one it stores the chunk
+ * into each peer.  Every frame then ends with a cross-rank flag barrier on fdc_stream: when the stream has drained,
+ * every rank's copy holds the whole frame.  Backdrop blur halos are read from the peers' copies. */
+int fdc_bind_shared_framebuffer(fdc_ctx* ctx, void* local_ptr, size_t bytes, void* const* peer_ptrs, int n,
+                                void* multicast_ptr, int width, int rows);
+int fdc_set_frame_barrier(fdc_ctx* ctx, int enabled); /* the end-of-frame flag barrier of a shared framebuffer (default 1) */
 /* How the band reaches the peers registered above.  FDC_GATHER_STORES (default): the shade kernel stores every finished
  * pixel to every peer (fused, SM-driven).  FDC_GATHER_COPY: the last segment is shaded in `sub_bands` slices of tile
  * rows and each finished slice is copied to every peer by the copy engines (cudaMemcpyAsync over NVLink) while the

@@ -299,6 +299,47 @@ def test_copy_engine_gather_assembles_the_frame(n):
             assert np.array_equal(img, full), f"rank {r}/{n}"
 
 
+@pytest.mark.parametrize("n", [2, 3])
+def test_shared_framebuffer_fuses_the_gather(n):
+    """fdc_bind_shared_framebuffer: host-allocated framebuffers every rank can reach (here: torch tensors on one device,
+    no multicast mapping).  The copy-out stores every finished chunk into every copy and each frame ends with a flag
+    barrier; blur halos are read from the peers' copies.  Every copy must hold the single-context frame."""
+    import torch
+    from figdraw_b200.bands import padded_rows
+
+    for tr in (ss.config_trace(5, 1280, 720, n_rects=3000, n_glyphs=600), ss.config_trace(2, 1280, 720),
+               ss.config_trace(5, 333, 217, n_rects=300, n_glyphs=60)):  # 333: rows are not 16-byte multiples
+        full = render_trace(tr)
+        rows = padded_rows(tr.height, n)
+        nbytes = ((tr.width * rows * 4 + 255) & ~255) + 4096
+        bufs = [torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for _ in range(n)]
+        ctxs = [CudaContext(atlasSize=tr.atlas_size, rank=r, nRanks=n) for r in range(n)]
+        try:
+            for r, c in enumerate(ctxs):
+                c.bindSharedFramebuffer(bufs[r].data_ptr(), nbytes, [b.data_ptr() for b in bufs], 0, tr.width, rows)
+                for _idx, key, img in tr.images:
+                    c.putImage(key, img)
+            # Size every context's buffers one rank at a time without cross-rank waits: all ranks share this process and
+            # device, and an allocation (a device-wide sync) while a peer spins on our flags would stall both.
+            for c in ctxs:
+                c.setFrameBarrier(False)
+                _submit(c, tr, tr.calls[tr.calls["op"] != Op.BACKDROP_BLUR])
+                c.sync()
+                c.setFrameBarrier(True)
+            for _ in range(2):
+                for c in ctxs:
+                    _submit(c, tr, tr.calls)
+                for c in ctxs:
+                    c.sync()
+            torch.cuda.synchronize()
+            for r in range(n):
+                got = bufs[r][: tr.height * tr.width * 4].view(tr.height, tr.width, 4).cpu().numpy()
+                assert np.array_equal(got, full), f"copy {r}/{n} of a {tr.width}x{tr.height} frame"
+        finally:
+            for c in ctxs:
+                c.close()
+
+
 def test_backdrop_blur_under_bands_needs_peers():
     tr = ss.config_trace(2, 640, 360)
     ctx = CudaContext(atlasSize=tr.atlas_size, rank=0, nRanks=2)

@@ -308,6 +308,7 @@ class Env:
             dist.barrier()
             self.dist = dist
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.keep = []
 
     def barrier(self):
         if self.dist is not None:
@@ -339,25 +340,34 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
     has_blur = bool((trace.calls["op"] == 13).any())
     gather_mode = args.gather if world > 1 else "none"
     symm_t = None
+
+    def bind_symmetric(c):
+        """Framebuffer (+ flags + record exchange area) in torch symmetric memory, bound to context `c` on every rank."""
+        import torch.distributed._symmetric_memory as symm
+
+        nbytes = ((W * band_rows * world * 4 + 255) & ~255) + 4096 + 64 * (len(trace.calls) + 1024)
+        t = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+        hdl = symm.rendezvous(t, dist.group.WORLD)
+        mc_ptr = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        ok = torch.tensor([1 if (mc_ptr or args.gather == "mc") else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            raise RuntimeError("no multicast mapping on some rank")
+        t.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        c.bindSharedFramebuffer(t.data_ptr(), nbytes, [int(p) for p in hdl.buffer_ptrs], mc_ptr, W, band_rows * world)
+        # kept for the life of the process: torch caches rendezvous handles per allocation, a freed block that is handed out
+        # again for a larger tensor would come back with the stale (smaller) peer mappings
+        env.keep.append((t, hdl))
+        return t, mc_ptr
+
     if gather_mode in ("auto", "mc"):
         # Framebuffer in torch symmetric memory: every rank maps every copy, and behind an NVSwitch there is a multicast
         # mapping -- the shade kernel's copy-out then writes each finished chunk once and the switch delivers it to all
         # ranks (fdc_bind_shared_framebuffer).  No collective call in the frame loop; a flag barrier ends the frame.
         try:
-            import torch.distributed._symmetric_memory as symm
-
-            nbytes = ((W * band_rows * world * 4 + 255) & ~255) + 4096
-            symm_t = symm.empty(nbytes, dtype=torch.uint8, device=dev)
-            hdl = symm.rendezvous(symm_t, dist.group.WORLD)
-            mc_ptr = int(getattr(hdl, "multicast_ptr", 0) or 0)
-            ok = torch.tensor([1 if (mc_ptr or gather_mode == "mc") else 0], device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
-                raise RuntimeError("no multicast mapping on some rank")
-            symm_t.zero_()
-            torch.cuda.synchronize()
-            dist.barrier()
-            ctx.bindSharedFramebuffer(symm_t.data_ptr(), nbytes, [int(p) for p in hdl.buffer_ptrs], mc_ptr, W, band_rows * world)
+            symm_t, mc_ptr = bind_symmetric(ctx)
             gather_mode = "mc" if mc_ptr else "symm-p2p"
         except Exception as e:  # noqa: BLE001
             if args.gather == "mc":
@@ -484,11 +494,14 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
     # its own records host->device and its own frame device->host; in steady state frame k's readback, frame k+1's
     # kernels and frame k+2's upload are in flight together.  Throughput over the steps, not latency.
     e2e_pipe_ms, depth = None, 1
-    if world == 1 and headline:
+    y0b, y1b = ctx.bandRows() if world > 1 else (0, H)
+    if world == 1 or symm_t is not None:
         ring = [(ctx, prepared, out_np)]
         extra_ctx = []
         for _ in range(max(1, int(os.environ.get("FDC_E2E_RING", "3")) - 1)):
-            c2 = CudaContext(atlasSize=trace.atlas_size, device=env.local_rank)
+            c2 = CudaContext(atlasSize=trace.atlas_size, device=env.local_rank, rank=rank, nRanks=world)
+            if world > 1:
+                bind_symmetric(c2)  # its own shared framebuffer, flags and record exchange area
             for _i, key, img in trace.images:
                 c2.putImage(key, img)
             o2 = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
@@ -505,15 +518,18 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
                     nxt = ring[(k + depth - 1) % depth]
                     submit(nxt[0], nxt[1])
                 cur = ring[k % depth]
-                cur[0].readPixels((0, 0, W, H), out=cur[2])
+                cur[0].readPixels((0, y0b, W, y1b - y0b), out=cur[2][y0b:y1b])  # every rank reads its own band back
 
+        for c2, prep2, _o in ring[1:]:  # size the new contexts' buffers (a bin-list overflow re-runs on every rank)
+            submit(c2, prep2)
+            bands.resolve_across_ranks(c2, world, dist)
         pipelined(6)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         pipelined(e2e_steps)
         torch.cuda.synchronize()
         e2e_pipe_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        if not all(bool(np.array_equal(out_np, r[2])) for r in ring[1:]):
+        if not all(bool(np.array_equal(out_np[y0b:y1b], r[2][y0b:y1b])) for r in ring[1:]):
             raise SystemExit("pipelined contexts produced different frames")
         for c2, _o, _k in extra_ctx:
             c2.close()
@@ -546,10 +562,13 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
             single_gpu_ms = float(np.median(single_ms[2:]))
             ref_ctx.close()
         env.barrier()
-    ms_step, e2e_ms, shade_ms, bin_ms = env.max_over_ranks([ms_step, e2e_ms, stats.shade_ms, stats.bin_ms])
+    ms_step, e2e_ms, shade_ms, bin_ms, e2e_pipe_max = env.max_over_ranks([ms_step, e2e_ms, stats.shade_ms, stats.bin_ms, e2e_pipe_ms or 0.0])
+    if e2e_pipe_ms is not None:
+        e2e_pipe_ms = e2e_pipe_max
     res = {"name": name, "trace": trace, "W": W, "H": H, "ms_step": ms_step, "e2e_ms": e2e_ms, "e2e_pipe_ms": e2e_pipe_ms,
            "depth": depth, "shade_ms": shade_ms, "bin_ms": bin_ms, "clocks": clocks, "launches_per_frame": launches_per_frame,
            "n_tile_entries": int(stats.n_tile_entries), "h2d": int(prepared_upload_bytes(prepared)), "out_np": out_np,
+           "sharded_upload": bool(world > 1 and symm_t is not None),
            "calls_np": calls_np, "gathered_ok": gathered_ok, "single_gpu_ms": single_gpu_ms, "use_p2p": use_p2p,
            "gather": gather_mode}
     ctx.close()
@@ -646,7 +665,11 @@ def main():
                         "ms_per_step": round(e2e_best, 4), "latency_ms": round(r["e2e_ms"], 4),
                         "mode": (f"{r['depth']} contexts in flight: step k's readback, step k+1's kernels and step k+2's upload overlap"
                                  if r["e2e_pipe_ms"] else "one frame at a time"),
-                        "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": int(W * H * 4)},
+                        "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": int(W * H * 4),
+                        "bytes_note": ("whole job: every rank uploads 1/n of each long run of compact records over its own PCIe link "
+                                       "and pushes it to all ranks over NVLink; every rank reads its own band back"
+                                       if r["sharded_upload"] else
+                                       ("every rank uploads the whole stream and reads its own band back" if world > 1 else "one GPU"))},
                 "gpu_launches": r["launches_per_frame"] * args.steps, "launches_per_frame": r["launches_per_frame"],
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base}
         if r["gathered_ok"] is not None:
@@ -662,7 +685,8 @@ def main():
                                "single_gpu_ms": round(x["single_gpu_ms"], 4),
                                "efficiency": round(x["single_gpu_ms"] / (world * x["ms_step"]), 4),
                                "shade_ms": round(x["shade_ms"], 4), "bin_ms": round(x["bin_ms"], 4),
-                               "e2e_ms_per_step": round(x["e2e_ms"], 4), "h2d_bytes_per_step": x["h2d"],
+                               "e2e_ms_per_step": round(x["e2e_pipe_ms"] or x["e2e_ms"], 4), "e2e_latency_ms": round(x["e2e_ms"], 4),
+                               "h2d_bytes_per_step": x["h2d"],
                                "gathered_frame_equals_single_gpu": x["gathered_ok"],
                                "note": "BASELINE configs[4] (all sizes x2) on the same ranks; efficiency = single_gpu_ms / (n_gpus x ms_per_step)"}
         if world == 1 and name in ("cfg5_4k", "cfg5_8k"):

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <algorithm>
+
 #include "fdc_kernels.h"
 
 namespace fdc {
@@ -238,6 +240,31 @@ __global__ void wait_flags_kernel(uint32_t* flags, int n, uint32_t value) {
   }
 }
 }  // namespace
+
+namespace {
+__global__ void __launch_bounds__(256) push_to_peers_kernel(const uint4* __restrict__ src, size_t byte_off, size_t n16, uint8_t* multicast,
+                                                            uint8_t* const* __restrict__ peers, int n_peers, int my_rank) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = src[i];
+    if (multicast) {
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(multicast + byte_off + i * 16),
+                   "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                   : "memory");
+    } else {
+      for (int r = 0; r < n_peers; r++)
+        if (r != my_rank && peers[r]) *reinterpret_cast<uint4*>(peers[r] + byte_off + i * 16) = v;
+    }
+  }
+}
+}  // namespace
+
+void launch_push_to_peers(const uint8_t* src, size_t byte_off, size_t bytes, uint8_t* multicast, uint8_t* const* peers, int n_peers,
+                          int my_rank, cudaStream_t stream) {
+  const size_t n16 = bytes / 16;
+  if (n16 == 0) return;
+  const unsigned grid = (unsigned)std::min<size_t>((n16 + 255) / 256, 148 * 4);
+  push_to_peers_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), byte_off, n16, multicast, peers, n_peers, my_rank);
+}
 
 void launch_signal_flags(uint32_t* const* flag_arrays, int n, int my_rank, uint32_t value, cudaStream_t stream) {
   FlagPtrs f;

@@ -264,6 +264,13 @@ struct fdc_ctx {
   DevBuf<uint8_t*> d_peers;
   DevBuf<fdc_rect64> d_rects64;    // compact draw records of this frame (fdc_submit_rects64)
   uint32_t n_rects64 = 0;
+  // Record exchange area behind the flags of a shared framebuffer (tile-band partitions): every rank uploads only ITS
+  // 1/n_ranks slice of a long run of compact records over its own PCIe link and pushes the slice into all copies over
+  // NVLink (multicast or peer stores) -- the host->device traffic of the whole job is one copy of the stream, not n.
+  size_t rec_off = 0, rec_bytes = 0;
+  bool rec_shared_frame = false;   // this frame's compact records live in the exchange area
+  struct Exchange { uint32_t first, count; };  // record range this rank uploaded and has to push to the peers
+  std::vector<Exchange> exchanges;
   std::vector<uint8_t*> h_peers;   // host copy of the peer framebuffer pointers (own entry = own framebuffer)
   size_t flag_off = 0;             // byte offset of the cross-rank flag array inside a reserved framebuffer (0: none)
   uint32_t frame_barrier_base = 0; // barrier_seq at the start of the frame in flight
@@ -684,7 +691,7 @@ BinBuffers bin_buffers(fdc_ctx* ctx) {
 SetupArgs setup_args(fdc_ctx* ctx, const Segment& s) {
   SetupArgs a;
   a.draws = ctx->d_draws.p;
-  a.rects64 = ctx->d_rects64.p;
+  a.rects64 = ctx->rec_shared_frame ? reinterpret_cast<const fdc_rect64*>(ctx->fb() + ctx->rec_off) : ctx->d_rects64.p;
   a.runs = ctx->d_runs.p;
   a.n_runs = (int)ctx->runs.n;
   a.xforms = ctx->d_xforms.p;
@@ -735,6 +742,7 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
     if (ctx->rectmasks.n)
       CK(cudaMemcpyAsync(ctx->d_rectmasks.p, ctx->rectmasks.p, sizeof(RectMaskRec) * ctx->rectmasks.n, cudaMemcpyHostToDevice, st));
   }
+  const bool exchange = upload && !ctx->exchanges.empty();
   uint32_t max_prims = 0;
   for (auto& s : ctx->segments) max_prims = std::max(max_prims, s.count);
   rc = ensure_bin_buffers(ctx, max_prims);
@@ -775,7 +783,7 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
   const bool banded_blur = ctx->n_ranks > 1 && any_blur;
   const bool end_barrier = ctx->n_ranks > 1 && ctx->frame_barrier && ctx->n_peers == ctx->n_ranks && ctx->flag_off != 0;
   uint32_t* flag_ptrs[kMaxRanks] = {};
-  if (banded_blur || end_barrier) {
+  if (banded_blur || end_barrier || exchange) {
     if (ctx->n_peers != ctx->n_ranks || ctx->flag_off == 0)
       return ctx->fail(FDC_ERR_STATE, "backdrop blur under a tile-band partition needs a framebuffer the peers can reach: "
                                       "fdc_reserve_framebuffer + fdc_set_peer_framebuffers, or fdc_bind_shared_framebuffer");
@@ -783,6 +791,20 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
       uint8_t* base = (r == ctx->rank || !ctx->h_peers[r]) ? ctx->fb() : ctx->h_peers[r];
       flag_ptrs[r] = reinterpret_cast<uint32_t*>(base + ctx->flag_off);
     }
+  }
+  if (exchange) {
+    // Sharded upload: push the record slices this rank brought over PCIe into every rank's copy, then wait until all
+    // ranks have done the same.  (The peers' setup kernels of the PREVIOUS frame are long done: every rank passed that
+    // frame's end barrier after its own shade.)
+    for (auto& x : ctx->exchanges) {
+      const size_t off = ctx->rec_off + (size_t)x.first * sizeof(fdc_rect64);
+      launch_push_to_peers(ctx->fb() + off, off, (size_t)x.count * sizeof(fdc_rect64), ctx->mc_fb, ctx->d_peers.p, ctx->n_peers, ctx->rank, st);
+      launches++;
+    }
+    const uint32_t v = ++ctx->barrier_seq;
+    launch_signal_flags(flag_ptrs, ctx->n_ranks, ctx->rank, v, st);
+    launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, v, st);
+    launches += 2;
   }
   uint32_t pending_wait = 0;  // "neighbours finished reading my halo rows" value to wait for before the next shade
   for (size_t si = 0; si < ctx->segments.size(); si++) {
@@ -1090,6 +1112,8 @@ int fdc_begin_frame(fdc_ctx* ctx, int width, int height, int clear_main, const f
   ctx->draws.n = ctx->runs.n = ctx->xforms.n = ctx->rectmasks.n = 0;
   ctx->n_draws = 0;
   ctx->n_rects64 = 0;
+  ctx->rec_shared_frame = false;
+  ctx->exchanges.clear();
   ctx->uploads.clear();
   ctx->segments.clear();
   start_segment(ctx);
@@ -1493,6 +1517,7 @@ int fdc_pop_rect_mask(fdc_ctx* ctx) {
 // ------------------------------------------------------------------------------------------------- display list
 static inline bool is_draw_op(uint32_t op) { return op >= FDC_OP_ROUNDED_RECT && op <= FDC_OP_RECT; }
 constexpr size_t kDirectRunMin = 2048;  // records; shorter runs are staged
+constexpr size_t kShardRunMin = 1024;   // records per rank below which a run of compact records is uploaded whole by every rank
 
 // A long run of draw records issued under one backend state: one RunState, and the records go to the device in a
 // single copy straight from the caller's buffer (no host-side staging pass over 128 bytes per draw).
@@ -1641,8 +1666,24 @@ int fdc_submit_rects64(fdc_ctx* ctx, const fdc_rect64* rects, size_t n) {
   CK(cudaSetDevice(ctx->device));
   // the draw index space stays one: d_draws keeps (unused) room for these indices
   CK(ctx->d_draws.reserve_keep((size_t)ctx->n_draws + n, ctx->n_draws, ctx->stream));
-  CK(ctx->d_rects64.reserve_keep((size_t)ctx->n_rects64 + n, ctx->n_rects64, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->d_rects64.p + ctx->n_rects64, rects, sizeof(fdc_rect64) * n, cudaMemcpyHostToDevice, ctx->stream));
+  const bool fits_shared = ctx->n_ranks > 1 && ctx->ext_fb && ctx->frame_barrier && ctx->n_peers == ctx->n_ranks &&
+                           ctx->rec_bytes >= ((size_t)ctx->n_rects64 + n) * sizeof(fdc_rect64);
+  if (ctx->n_rects64 == 0) ctx->rec_shared_frame = fits_shared;  // every rank sees the same stream: same decision
+  if (ctx->rec_shared_frame) {
+    if (!fits_shared)
+      return ctx->fail(FDC_ERR_CAPACITY, "record exchange area of the shared framebuffer is too small for this frame (%zu bytes)", ctx->rec_bytes);
+    fdc_rect64* base = reinterpret_cast<fdc_rect64*>(ctx->fb() + ctx->rec_off) + ctx->n_rects64;
+    if (n >= kShardRunMin * (size_t)ctx->n_ranks) {
+      const size_t lo = n * (size_t)ctx->rank / ctx->n_ranks, hi = n * (size_t)(ctx->rank + 1) / ctx->n_ranks;
+      CK(cudaMemcpyAsync(base + lo, rects + lo, sizeof(fdc_rect64) * (hi - lo), cudaMemcpyHostToDevice, ctx->stream));
+      ctx->exchanges.push_back({ctx->n_rects64 + (uint32_t)lo, (uint32_t)(hi - lo)});
+    } else {
+      CK(cudaMemcpyAsync(base, rects, sizeof(fdc_rect64) * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  } else {
+    CK(ctx->d_rects64.reserve_keep((size_t)ctx->n_rects64 + n, ctx->n_rects64, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_rects64.p + ctx->n_rects64, rects, sizeof(fdc_rect64) * n, cudaMemcpyHostToDevice, ctx->stream));
+  }
   ctx->n_rects64 += (uint32_t)n;
   ctx->n_draws += (uint32_t)n;
   ctx->segments.back().count += (uint32_t)n;
@@ -1703,6 +1744,13 @@ int fdc_bind_framebuffer(fdc_ctx* ctx, void* device_rgba8) {
   if (ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "cannot rebind the framebuffer inside a frame");
   int rc = resolve_frame(ctx);
   if (rc) return rc;
+  if (ctx->ext_fb && ctx->frame_barrier) {  // leaving a shared framebuffer: forget its flags, peers and exchange area
+    ctx->mc_fb = nullptr;
+    ctx->frame_barrier = false;
+    ctx->flag_off = ctx->rec_off = ctx->rec_bytes = 0;
+    ctx->n_peers = 0;
+    ctx->h_peers.clear();
+  }
   ctx->ext_fb = (uint8_t*)device_rgba8;
   return FDC_OK;
 }
@@ -1756,6 +1804,8 @@ int fdc_bind_shared_framebuffer(fdc_ctx* ctx, void* local_ptr, size_t bytes, voi
   ctx->ext_fb = (uint8_t*)local_ptr;
   ctx->mc_fb = (uint8_t*)multicast_ptr;
   ctx->flag_off = pix;
+  ctx->rec_off = pix + 4096;
+  ctx->rec_bytes = bytes - ctx->rec_off;  // whatever the host gave beyond pixels + flags is the record exchange area
   ctx->barrier_seq = 0;
   ctx->frame_barrier = true;
   ctx->n_peers = n;

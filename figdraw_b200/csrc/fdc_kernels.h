@@ -80,6 +80,11 @@ void launch_backdrop_blur(const BlurArgs& a, cudaStream_t stream, int* n_launche
 void launch_signal_flags(uint32_t* const* flag_arrays, int n, int my_rank, uint32_t value, cudaStream_t stream);
 void launch_wait_flags(uint32_t* my_flags, int n, uint32_t value, cudaStream_t stream);
 
+// Copies `bytes` (a multiple of 16) at `src` (= own copy + byte_off) to the same offset of every rank's copy of a shared
+// buffer: one multimem.st per 16 bytes through the multicast mapping, or one store per peer.
+void launch_push_to_peers(const uint8_t* src, size_t byte_off, size_t bytes, uint8_t* multicast, uint8_t* const* peers, int n_peers,
+                          int my_rank, cudaStream_t stream);
+
 void launch_fill_u32(uint32_t* dst, uint32_t value, size_t n, cudaStream_t stream);
 // Builds mip level `l+1` region from level `l` (premultiplied 2x2 box, see oracle upload_chain).
 void launch_mip_down(const uint8_t* src, int src_size, uint8_t* dst, int dst_size, int sx, int sy, int sw, int sh,

@@ -27,7 +27,7 @@ def _worker(rank, world, port, out_dir):
     import torch.distributed._symmetric_memory as symm
 
     from figdraw_b200 import bands, scenes_synth as ss
-    from figdraw_b200.cuda_context import CudaContext
+    from figdraw_b200.cuda_context import CudaContext, prepare_calls
 
     dev = torch.device("cuda", rank)
     torch.cuda.set_device(dev)
@@ -36,7 +36,7 @@ def _worker(rank, world, port, out_dir):
     for name, tr in (("cfg5", ss.config_trace(5, 1920, 1080, n_rects=8000, n_glyphs=1500)), ("cfg2", ss.config_trace(2)),
                      ("cfg4", ss.config_trace(4, 1920, 1080, rows=60, cols=8))):
         rows = bands.padded_rows(tr.height, world)
-        nbytes = ((tr.width * rows * 4 + 255) & ~255) + 4096
+        nbytes = ((tr.width * rows * 4 + 255) & ~255) + 4096 + 64 * (len(tr.calls) + 64)  # pixels + flags + record exchange area
         t = symm.empty(nbytes, dtype=torch.uint8, device=dev)
         hdl = symm.rendezvous(t, dist.group.WORLD)
         t.zero_()
@@ -47,9 +47,14 @@ def _worker(rank, world, port, out_dir):
         ctx.bindSharedFramebuffer(t.data_ptr(), nbytes, [int(p) for p in hdl.buffer_ptrs], mc, tr.width, rows)
         for _i, key, img in tr.images:
             ctx.putImage(key, img)
-        for _ in range(3):
+        # compact records: long runs are uploaded 1/world per rank and pushed to all ranks over NVLink (sharded upload)
+        prepared = prepare_calls(tr.calls, compact=True, min_compact_run=64)
+        for k in range(3):
             ctx.beginFrame((tr.width, tr.height), clearMain=tr.clear is not None, clearMainColor=tr.clear or (1, 1, 1, 1))
-            ctx.submitCalls(tr.calls)
+            if k == 1:
+                ctx.submitCalls(tr.calls)  # plain 128-byte records: every rank uploads everything
+            else:
+                ctx.submitPrepared(prepared)
             ctx.endFrame()
             bands.resolve_across_ranks(ctx, world, dist)
         torch.cuda.synchronize()

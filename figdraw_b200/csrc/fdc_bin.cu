@@ -548,21 +548,8 @@ __device__ __forceinline__ bool rect_hits(uint32_t r, uint32_t bx, uint32_t by) 
   return (r & 255u) <= bx && bx <= ((r >> 16) & 255u) && ((r >> 8) & 255u) <= by && by <= (r >> 24);
 }
 
-// Sum of bytes 0..k-1 of 16 bytes (k = 0..15).
-__device__ __forceinline__ uint32_t bytes_below(const uint4& v, int k) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  uint32_t s = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const int n = k - 4 * j;  // bytes of word j that count
-    if (n >= 4) s = __dp4a(w[j], 0x01010101u, s);
-    else if (n > 0) s = __dp4a(w[j] & ((1u << (8 * n)) - 1u), 0x01010101u, s);
-  }
-  return s;
-}
-
 // 32x32 bit-matrix transpose across a warp: lane i passes row i (bit k = A[i][k]) and receives column i (bit k = A[k][i]).
-// Five butterfly steps swapping off-diagonal blocks of size 16, 8, 4, 2, 1.
+// Five butterfly steps swapping off-diagonal blocks of size 16, 8, 4, 2, 1.  (Used by the fine binner.)
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 #pragma unroll
   for (int j = 16; j >= 1; j >>= 1) {
@@ -573,107 +560,140 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
   return x;
 }
 
-// One CTA = one chunk of kChunk primitives x one range of coarse-bin rows.  A warp owns 4 consecutive groups of 32
-// primitives.  Per group: every lane marks the bins its primitive touches in a per-warp bitmap (one 32-bit word per
-// lane; a bin row takes `wpr` words), then the warp visits only the marked bins; for each, one ballot over the 32
-// primitives gives the count (popc) and the stable ranks (popc of lower lanes).  Counts accumulate per warp, a
-// prefix over the 8 warps orders them inside the chunk, the chunk/bin matrix orders chunks globally.
-constexpr int kSlots = 1024;  // bitmap bits per CTA: 32 words x 32 bins
+// ---- coarse level, r02: (primitive, bin) PAIRS instead of a bitmap walk.
+// A primitive covers a small rectangle of 128x128-px bins (1.8 on average at 4K).  The r01 kernels marked bins in a
+// bitmap and transposed every marked 32-bin word across the warp -- ~100 warp instructions per primitive, independent
+// of how few pairs there were.  Now a warp enumerates exactly the pairs of its 32 primitives, in primitive order, 32
+// pairs per round: a warp-level exclusive scan of the pair counts, a 5-step search for each pair's owner lane, and one
+// shuffle for the owner's rectangle.  Counting is a shared-memory histogram; the stable rank of a pair inside a round
+// is popc(match_any(bin) & lower lanes), rounds and warps are ordered by running offsets kept per (bin, warp).
+// Cost follows the number of pairs (a band of an 8-GPU partition has 1/8 of them), a full-frame primitive simply
+// contributes many rounds.
+constexpr int kSlots = 1024;  // coarse bins one CTA handles: a range of whole bin rows
 constexpr int kWarps = kChunk / 32;
 
-// kScatter == false: counts.  Writes chunk_counts[bin][chunk] and the per-warp counts (u8) to `warp_counts`.
-// kScatter == true : reads the per-warp counts back, orders warps with a prefix, and scatters primitive indices.
-template <bool kScatter>
-__global__ void __launch_bounds__(kChunk) coarse_bin_kernel(const Prim* __restrict__ prims, uint32_t n, FrameView f, int wpr,
-                                                            int rows_per_cta, uint32_t* __restrict__ chunk_counts,
-                                                            uint8_t* __restrict__ warp_counts,
-                                                            const uint32_t* __restrict__ cbin_start,
-                                                            uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
-                                                            uint32_t* __restrict__ counters) {
-  __shared__ uint4 wc8[kSlots];  // per slot: the 16 warps' counts, one byte each (a warp contributes at most 32)
-  __shared__ uint32_t bitmap[kWarps][32];
-  __shared__ uint32_t gbase[kScatter ? kSlots : 1];  // global position of this chunk's slice of each bin
+struct WarpPairs {
+  uint32_t packed;  // x0 | y0 << 8 | w << 16 of my primitive's bin rectangle clipped to the CTA's row range
+  int k;            // its number of bins
+  int excl, total;  // exclusive scan of k over the warp, and the warp's total
+};
+__device__ __forceinline__ WarpPairs warp_pairs(uint32_t rect, int row0, int row1, int lane) {
+  WarpPairs wp;
+  const int x0 = rect & 255u, y0 = (rect >> 8) & 255u, x1 = (rect >> 16) & 255u, y1 = rect >> 24;
+  const int ya = max(y0, row0), yb = min(y1, row1 - 1);
+  const int w = x1 - x0 + 1, h = yb - ya + 1;
+  wp.k = (w > 0 && h > 0) ? w * h : 0;  // empty primitives carry x0 = 255 > x1 = 0
+  wp.packed = (uint32_t)x0 | ((uint32_t)(ya & 255) << 8) | ((uint32_t)(w & 0xFFFF) << 16);
+  int incl = wp.k;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  wp.excl = incl - wp.k;
+  wp.total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  return wp;
+}
+// Pair number p of the warp (p < total): which lane owns it and which bin it is.  All lanes call this together.
+__device__ __forceinline__ void warp_pair(const WarpPairs& wp, int p, int& owner, int& bx, int& by) {
+  owner = 0;
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const int cand = owner + step;  // < 32 always: steps add up to at most 31
+    const int e = __shfl_sync(0xFFFFFFFFu, wp.excl, cand);
+    if (e <= p) owner = cand;       // ties: the highest lane wins, which skips lanes without pairs
+  }
+  const uint32_t r = __shfl_sync(0xFFFFFFFFu, wp.packed, owner);
+  const int j = p - __shfl_sync(0xFFFFFFFFu, wp.excl, owner);
+  const int w = max((int)(r >> 16), 1);
+  const int q = (int)(((float)j + 0.5f) * (1.0f / (float)w));  // j / w, exact for j < 2^16
+  bx = (int)(r & 255u) + (j - q * w);
+  by = (int)((r >> 8) & 255u) + q;
+}
+
+// Count pass: chunk_counts[bin][chunk] = pairs of this chunk in each bin of the CTA's row range.
+__global__ void __launch_bounds__(kChunk) coarse_count_kernel(const Prim* __restrict__ prims, uint32_t n, FrameView f, int rows_per_cta,
+                                                              uint32_t* __restrict__ chunk_counts) {
+  __shared__ uint32_t s_hist[kSlots];
   const uint32_t chunk = blockIdx.x;
-  const uint32_t base_idx = chunk * kChunk;
-  const int row0 = blockIdx.y * rows_per_cta;
-  const int row1 = min(row0 + rows_per_cta, f.cby);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (kScatter && counters[kCntCoarseTotal] > coarse_cap) return;  // overflow: host regrows and replays
-  uint4* wc_global = reinterpret_cast<uint4*>(warp_counts + ((size_t)chunk * gridDim.y + blockIdx.y) * (size_t)(kWarps * kSlots));
-  const uint32_t rect = coarse_rect(prims, base_idx + threadIdx.x, n, f);
-
-  // slots in use: (rows of this CTA) x (words per row) x 32 -- 544 of the 1024 at 4K; everything per-slot below is
-  // bounded by it (zeroing, the prefix over warps and the per-warp count array are the fixed cost of this kernel)
-  const int used = (row1 - row0) * wpr * 32;
-  if (!kScatter) {
-    for (int sl = threadIdx.x; sl < used; sl += blockDim.x) wc8[sl] = make_uint4(0u, 0u, 0u, 0u);
-  } else {
-    // per-warp counts of the count pass; base of this chunk's slice of each bin
-    for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {
-      wc8[sl] = __ldg(&wc_global[sl]);
-      const int r = row0 + (sl >> 5) / wpr, x = ((sl >> 5) % wpr) * 32 + (sl & 31);
-      if (r < row1 && x < f.cbx) {
-        const int b = r * f.cbx + x;
-        gbase[sl] = cbin_start[b] + chunk_counts[(size_t)b * gridDim.x + chunk];
-      }
-    }
-  }
-  bitmap[warp][lane] = 0;
+  const int row0 = blockIdx.y * rows_per_cta, row1 = min(row0 + rows_per_cta, f.cby);
+  const int lane = threadIdx.x & 31;
+  const int used = (row1 - row0) * f.cbx;
+  const uint32_t rect = coarse_rect(prims, chunk * kChunk + threadIdx.x, n, f);
+  for (int sl = threadIdx.x; sl < used; sl += blockDim.x) s_hist[sl] = 0;
   __syncthreads();
+  const WarpPairs wp = warp_pairs(rect, row0, row1, lane);
+  for (int base = 0; base < wp.total; base += 32) {
+    const int p = base + lane;
+    int owner, bx, by;
+    warp_pair(wp, min(p, wp.total - 1), owner, bx, by);
+    if (p < wp.total) atomicAdd(&s_hist[(by - row0) * f.cbx + bx], 1u);
+  }
+  __syncthreads();
+  for (int sl = threadIdx.x; sl < used; sl += blockDim.x)
+    chunk_counts[(size_t)(row0 * f.cbx + sl) * gridDim.x + chunk] = s_hist[sl];
+}
 
-  // mark the bins my primitive touches: one 32-bit word per lane, a bin row takes `wpr` words
-  {
-    const int x0 = rect & 255u, y0 = (rect >> 8) & 255u, x1 = (rect >> 16) & 255u, y1 = rect >> 24;
-    const int ya = max(y0, row0), yb = min(y1, row1 - 1);
-    for (int y = ya; y <= yb; y++) {
-      for (int wi = x0 >> 5; wi <= (x1 >> 5); wi++) {
-        const int lo = max(x0 - wi * 32, 0), hi = min(x1 - wi * 32, 31);
-        const uint32_t bits = (hi == 31 ? 0xFFFFFFFFu : ((2u << hi) - 1u)) & ~((1u << lo) - 1u);
-        atomicOr(&bitmap[warp][(y - row0) * wpr + wi], bits);
-      }
+// Scatter pass: the same enumeration; positions = bin start + pairs of earlier chunks + pairs of earlier warps of this
+// chunk + pairs of earlier rounds of this warp + rank inside the round.
+__global__ void __launch_bounds__(kChunk) coarse_scatter_kernel(const Prim* __restrict__ prims, uint32_t n, FrameView f, int rows_per_cta,
+                                                                const uint32_t* __restrict__ chunk_counts,
+                                                                const uint32_t* __restrict__ cbin_start,
+                                                                uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
+                                                                const uint32_t* __restrict__ counters) {
+  // per (bin, warp): first the pair count, then (after the prefix over warps) the running offset inside the chunk's
+  // slice of the bin.  16 bits each (a chunk puts at most 512 pairs into a bin), two warps per word.
+  __shared__ uint32_t s_pos[kSlots][kWarps / 2];
+  __shared__ uint32_t s_gbase[kSlots];
+  if (counters[kCntCoarseTotal] > coarse_cap) return;  // overflow: host regrows and re-runs the frame
+  const uint32_t chunk = blockIdx.x;
+  const int row0 = blockIdx.y * rows_per_cta, row1 = min(row0 + rows_per_cta, f.cby);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int used = (row1 - row0) * f.cbx;
+  const uint32_t rect = coarse_rect(prims, chunk * kChunk + threadIdx.x, n, f);
+  for (int i = threadIdx.x; i < used * (kWarps / 2); i += blockDim.x) (&s_pos[0][0])[i] = 0;
+  for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {
+    const int b = row0 * f.cbx + sl;
+    s_gbase[sl] = cbin_start[b] + chunk_counts[(size_t)b * gridDim.x + chunk];
+  }
+  __syncthreads();
+  const WarpPairs wp = warp_pairs(rect, row0, row1, lane);
+  const int word = warp >> 1, shift = (warp & 1) * 16;
+  for (int base = 0; base < wp.total; base += 32) {
+    const int p = base + lane;
+    int owner, bx, by;
+    warp_pair(wp, min(p, wp.total - 1), owner, bx, by);
+    if (p < wp.total) atomicAdd(&s_pos[(by - row0) * f.cbx + bx][word], 1u << shift);
+  }
+  __syncthreads();
+  for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {  // counts -> exclusive prefix over the 16 warps
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < kWarps / 2; k++) {
+      const uint32_t v = s_pos[sl][k];
+      const uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+      s_pos[sl][k] = run | ((run + lo) << 16);
+      run += lo + hi;
     }
   }
-  __syncwarp();
-  const uint32_t myword = bitmap[warp][lane];
-  uint32_t words = __ballot_sync(0xFFFFFFFFu, myword != 0);
-  // One marked bitmap word = 32 bins of one bin row.  Each lane builds the hit bits of ITS primitive inside the word,
-  // a 32x32 bit transpose across the warp turns "bins per primitive" into "primitives per bin": lane b then owns bin
-  // b of the word -- its count is a popc, its stable ranks are the order of the set bits.  The cost per word does not
-  // depend on how many bins are marked, so a full-frame primitive (510 bins at 4K) no longer serialises its warp
-  // (it used to: one ballot per marked bin, a 20-40 us tail in both passes, profiles/r01_binning.md).
-  const int rx0 = rect & 255u, ry0 = (rect >> 8) & 255u, rx1 = (rect >> 16) & 255u, ry1 = rect >> 24;
-  while (words) {
-    const int wi = __ffs(words) - 1;
-    words &= words - 1;
-    const int by = row0 + wi / wpr, bxw = (wi % wpr) * 32;
-    uint32_t hm = 0;
-    if (ry0 <= by && by <= ry1 && rx0 <= bxw + 31 && rx1 >= bxw && rx0 <= rx1) {
-      const int lo = max(rx0 - bxw, 0), hi = min(rx1 - bxw, 31);
-      hm = (hi == 31 ? 0xFFFFFFFFu : ((2u << hi) - 1u)) & ~((1u << lo) - 1u);
+  __syncthreads();
+  const uint32_t first = chunk * kChunk + (uint32_t)warp * 32u;
+  for (int base = 0; base < wp.total; base += 32) {
+    const int p = base + lane;
+    const bool active = p < wp.total;
+    int owner, bx, by;
+    warp_pair(wp, min(p, wp.total - 1), owner, bx, by);
+    const int sl = (by - row0) * f.cbx + bx;
+    // pairs of one round are in primitive order along the lanes: the rank among equal bins is the stable rank
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, active ? (uint32_t)sl : (0x80000000u | (uint32_t)lane));
+    if (active) {
+      const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+      const uint32_t off = (s_pos[sl][word] >> shift) & 0xFFFFu;
+      coarse_list[s_gbase[sl] + off + rank] = first + (uint32_t)owner;
     }
-    uint32_t cm = transpose32(hm, lane);
-    const int sl = wi * 32 + lane;
-    if (!kScatter) {
-      if (cm) reinterpret_cast<uint8_t*>(wc8)[sl * 16 + warp] = (uint8_t)__popc(cm);  // each warp visits a word once
-    } else if (cm) {
-      uint32_t pos = gbase[sl] + bytes_below(wc8[sl], warp);  // entries of earlier warps of this chunk come first
-      const uint32_t first = base_idx + (uint32_t)warp * 32u;
-      while (cm) {
-        const int pl = __ffs(cm) - 1;
-        cm &= cm - 1;
-        coarse_list[pos++] = first + (uint32_t)pl;
-      }
-    }
-  }
-  if (!kScatter) {
-    __syncthreads();
-    for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {
-      const int r = row0 + (sl >> 5) / wpr, x = ((sl >> 5) % wpr) * 32 + (sl & 31);
-      const uint4 v = wc8[sl];
-      wc_global[sl] = v;
-      const uint32_t tot = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
-      if (r < row1 && x < f.cbx) chunk_counts[(size_t)(r * f.cbx + x) * gridDim.x + chunk] = tot;
-    }
+    __syncwarp();
+    if (active && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&s_pos[sl][word], (uint32_t)__popc(peers) << shift);
+    __syncwarp();
   }
 }
 
@@ -1041,14 +1061,12 @@ void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& f, con
     if (n_launches) *n_launches += 1;
     return;
   }
-  const int wpr = (f.cbx + 31) / 32;             // bitmap words per coarse-bin row
-  const int rows_per_cta = 32 / wpr;             // 32 words per CTA
+  const int rows_per_cta = max(1, kSlots / max(f.cbx, 1));  // whole bin rows, at most kSlots bins per CTA
   dim3 grid(n_chunks, (f.cby + rows_per_cta - 1) / rows_per_cta);
-  coarse_bin_kernel<false><<<grid, kChunk, 0, stream>>>(prims, n_prims, f, wpr, rows_per_cta, b.chunk_counts, b.warp_counts, nullptr,
-                                                       nullptr, 0, b.counters);
+  coarse_count_kernel<<<grid, kChunk, 0, stream>>>(prims, n_prims, f, rows_per_cta, b.chunk_counts);
   coarse_scan_kernel<<<(n_bins + 7) / 8, 256, 0, stream>>>(b.chunk_counts, n_chunks, n_bins, b.cbin_start, b.coarse_cap, b.counters);
-  coarse_bin_kernel<true><<<grid, kChunk, 0, stream>>>(prims, n_prims, f, wpr, rows_per_cta, b.chunk_counts, b.warp_counts, b.cbin_start,
-                                                      b.coarse_list, b.coarse_cap, b.counters);
+  coarse_scatter_kernel<<<grid, kChunk, 0, stream>>>(prims, n_prims, f, rows_per_cta, b.chunk_counts, b.cbin_start, b.coarse_list,
+                                                     b.coarse_cap, b.counters);
   fine_bin_kernel<<<n_bins, 256, 0, stream>>>(prims, f, b.cbin_start, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count,
                                               b.tile_list, b.tile_cap, b.counters, 0u);
   if (n_launches) *n_launches += 4;

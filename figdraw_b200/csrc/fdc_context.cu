@@ -250,7 +250,6 @@ struct fdc_ctx {
   DevBuf<QuadGeom> d_geoms;
   DevBuf<PrimExt> d_exts;
   DevBuf<uint32_t> d_prim_call;
-  DevBuf<uint8_t> d_warp_counts;
   DevBuf<uint32_t> d_chunk_counts, d_cbin_start, d_coarse_list, d_tile_start, d_tile_count, d_counters;
   DevBuf<TileEntry> d_tile_list;
   DevBuf<uint8_t> d_fb, d_backdrop, d_temp;
@@ -657,11 +656,6 @@ int ensure_bin_buffers(fdc_ctx* ctx, uint32_t max_prims) {
   const size_t n_bins = (size_t)f.cbx * f.cby;
   const size_t n_chunks = (max_prims + kChunk - 1) / kChunk;
   CK(ctx->d_chunk_counts.reserve(std::max<size_t>(1, n_chunks * n_bins)));
-  {
-    const int wpr = (f.cbx + 31) / 32, rows_per_cta = 32 / std::max(wpr, 1);
-    const size_t n_ranges = (size_t)(f.cby + rows_per_cta - 1) / rows_per_cta;
-    CK(ctx->d_warp_counts.reserve(std::max<size_t>(1, n_chunks * std::max<size_t>(n_ranges, 1) * (kChunk / 32) * 1024)));
-  }
   CK(ctx->d_cbin_start.reserve(n_bins + 1));
   CK(ctx->d_tile_start.reserve((size_t)f.tiles_x * f.tiles_y));
   CK(ctx->d_tile_count.reserve((size_t)f.tiles_x * f.tiles_y));
@@ -674,7 +668,6 @@ int ensure_bin_buffers(fdc_ctx* ctx, uint32_t max_prims) {
 BinBuffers bin_buffers(fdc_ctx* ctx) {
   BinBuffers b;
   b.chunk_counts = ctx->d_chunk_counts.p;
-  b.warp_counts = ctx->d_warp_counts.p;
   b.cbin_start = ctx->d_cbin_start.p;
   b.coarse_list = ctx->d_coarse_list.p;
   b.coarse_cap = (uint32_t)std::min<size_t>(ctx->d_coarse_list.cap, 0xFFFFFFF0u);
@@ -1073,7 +1066,7 @@ void fdc_destroy(fdc_ctx* ctx) {
   ctx->d_rects64.release();
   ctx->d_draws.release(); ctx->d_runs.release(); ctx->d_xforms.release(); ctx->d_rectmasks.release();
   ctx->d_prims.release(); ctx->d_geoms.release(); ctx->d_exts.release(); ctx->d_prim_call.release();
-  ctx->d_chunk_counts.release(); ctx->d_warp_counts.release(); ctx->d_cbin_start.release(); ctx->d_coarse_list.release();
+  ctx->d_chunk_counts.release(); ctx->d_cbin_start.release(); ctx->d_coarse_list.release();
   ctx->d_tile_start.release(); ctx->d_tile_count.release(); ctx->d_tile_list.release(); ctx->d_counters.release();
   ctx->d_fb.release(); ctx->d_backdrop.release(); ctx->d_temp.release(); ctx->d_peers.release(); ctx->d_snapshot.release();
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);

@@ -24,7 +24,6 @@ void launch_prim_setup(const SetupArgs& a, cudaStream_t stream);
 
 struct BinBuffers {
   uint32_t* chunk_counts;  // [n_chunks * n_cbins]
-  uint8_t* warp_counts;    // [n_chunks * n_row_ranges * 16 warps * 1024 slots]
   uint32_t* cbin_start;    // [n_cbins + 1]
   uint32_t* coarse_list;   // [coarse_cap]
   uint32_t coarse_cap;

@@ -176,24 +176,8 @@ struct DrawView {
   __device__ __forceinline__ float f(int k) const { return __uint_as_float(w[10 + k]); }
 };
 
-__global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
-  // The CTA's 128 records (16 KB) come in with coalesced 16-byte loads and are read back from shared memory at a
-  // 33-word stride (no bank conflicts): one record per thread straight from global memory was a 128-byte-stride
-  // gather that left the kernel waiting on loads (issue slot utilisation 0.17, profiles/r01_binning.md).
-  __shared__ uint32_t s_draw[128][33];
-  {
-    const uint32_t first = blockIdx.x * 128u;
-    const uint32_t n_here = min(128u, a.count - first);
-    const uint4* src = reinterpret_cast<const uint4*>(a.draws + a.first + first);
-    for (uint32_t k = threadIdx.x; k < n_here * 8u; k += 128u) {
-      const uint4 v = __ldg(src + k);
-      uint32_t* dst = &s_draw[k >> 3][(k & 7u) * 4u];
-      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-    }
-  }
-  __syncthreads();
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.count) return;
+// Full setup of draw record `i` of the segment; `rec` is its staging slot in shared memory (33 words).
+__device__ void setup_record(const SetupArgs& a, uint32_t i, uint32_t* rec) {
   uint32_t di = a.first + i;
   int ri = find_run(a.runs, a.n_runs, di);
   const RunState rs = a.runs[ri];
@@ -203,9 +187,9 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
     uint32_t w[32];
     expand_rect64_words(r, w);
 #pragma unroll
-    for (int k = 0; k < 32; k++) s_draw[threadIdx.x][k] = w[k];
+    for (int k = 0; k < 32; k++) rec[k] = w[k];
   }
-  const DrawView d{s_draw[threadIdx.x]};
+  const DrawView d{rec};
   const Xform xf = a.xforms[rs.xform];
   a.prim_call[i] = rs.call_index + (di - rs.first_draw);
 
@@ -522,19 +506,104 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
   }
   p.mode_flags = flags;
   a.prims[i] = p;
+  PrimBin pb;
+  pb.bx0 = p.bx0; pb.by0 = p.by0; pb.bx1 = p.bx1; pb.by1 = p.by1;
+  pb.mode_flags = flags; pb.aux = p.aux;
+  pb.ix0 = p.ix0; pb.iy0 = p.iy0; pb.ix1 = p.ix1; pb.iy1 = p.iy1;
+  pb.pad_[0] = pb.pad_[1] = 0u;
+  a.prim_bins[i] = pb;
+}
+
+// Tile-band partitions: most records of a frame land outside a rank's band (7/8 of them on 8 GPUs).  A rounded rect is
+// outside exactly when the full setup would find its clipped bbox empty; this restates just that part -- the same
+// transform, ceil and bbox arithmetic -- so the rest of the setup is skipped for it.
+__device__ bool outside_band(const SetupArgs& a, uint32_t i, const uint32_t* rec, uint32_t* call_index) {
+  const uint32_t di = a.first + i;
+  const RunState rs = a.runs[find_run(a.runs, a.n_runs, di)];
+  *call_index = rs.call_index + (di - rs.first_draw);
+  if (rs.flags & PF_MASK_WIDE) return false;  // carries a clear over the parent's clip box whatever its own quad is
+  float x, y, w, h;
+  if (rs.compact) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(&a.rects64[rs.src_off + (di - rs.first_draw)]));
+    x = r.x; y = r.y; w = r.z; h = r.w;
+  } else {
+    const DrawView d{rec};
+    if (d.op() != FDC_OP_ROUNDED_RECT) return false;
+    x = d.f(0); y = d.f(1); w = d.f(2); h = d.f(3);
+  }
+  if (w <= 0.0f || h <= 0.0f) return true;
+  QuadPos q;
+  quad_from_rect(a.xforms[rs.xform], x, y, fadd(x, w), fadd(y, h), q);
+  int bx0, by0, bx1, by1;
+  quad_bbox(q, bx0, by0, bx1, by1);
+  return max(bx0, 0) >= min(bx1, a.frame.W) || max(by0, a.frame.band_y0) >= min(by1, a.frame.band_y1);
+}
+
+template <bool kBanded>
+__global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
+  // The CTA's 128 records (16 KB) come in with coalesced 16-byte loads and are read back from shared memory at a
+  // 33-word stride (no bank conflicts): one record per thread straight from global memory was a 128-byte-stride
+  // gather that left the kernel waiting on loads (issue slot utilisation 0.17, profiles/r01_binning.md).
+  __shared__ uint32_t s_draw[128][33];
+  __shared__ uint32_t s_keep[128];
+  __shared__ uint32_t s_nkeep;
+  const uint32_t first = blockIdx.x * 128u;
+  const uint32_t n_here = min(128u, a.count - first);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.draws + a.first + first);
+    for (uint32_t k = threadIdx.x; k < n_here * 8u; k += 128u) {
+      const uint4 v = __ldg(src + k);
+      uint32_t* dst = &s_draw[k >> 3][(k & 7u) * 4u];
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+  }
+  if (kBanded && threadIdx.x == 0) s_nkeep = 0;
+  __syncthreads();
+  if (!kBanded) {
+    if (threadIdx.x < n_here) setup_record(a, first + threadIdx.x, s_draw[threadIdx.x]);
+    return;
+  }
+  // Band partition: weed out the records that land outside the band first (they only get their PF_EMPTY marker), then
+  // the CTA's threads share the survivors -- dense warps instead of a few live lanes in every warp.
+  bool keep = false;
+  if (threadIdx.x < n_here) {
+    uint32_t call_index;
+    keep = !outside_band(a, first + threadIdx.x, s_draw[threadIdx.x], &call_index);
+    if (!keep) {
+      const uint32_t i = first + threadIdx.x;
+      a.prim_call[i] = call_index;
+      reinterpret_cast<int4*>(&a.prims[i])[6] = make_int4(0, 0, (int)PF_EMPTY, 0);
+      int4* pb = reinterpret_cast<int4*>(&a.prim_bins[i]);
+      pb[0] = make_int4(0, 0, (int)PF_EMPTY, 0);
+      pb[1] = make_int4(0, 0, 0, 0);
+    }
+  }
+  const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+  uint32_t wbase = 0;
+  if ((threadIdx.x & 31) == 0 && km) wbase = atomicAdd(&s_nkeep, (uint32_t)__popc(km));
+  wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+  if (keep) s_keep[wbase + __popc(km & ((1u << (threadIdx.x & 31)) - 1u))] = threadIdx.x;
+  __syncthreads();
+  const uint32_t n_keep = s_nkeep;
+  for (uint32_t k = threadIdx.x; k < n_keep; k += 128u) {
+    const uint32_t j = s_keep[k];
+    setup_record(a, first + j, s_draw[j]);
+  }
 }
 
 void launch_prim_setup(const SetupArgs& a, cudaStream_t stream) {
   if (a.count == 0) return;
-  prim_setup_kernel<<<(a.count + 127) / 128, 128, 0, stream>>>(a);
+  const bool banded = a.frame.band_y0 > 0 || a.frame.band_y1 < a.frame.H;
+  if (banded) prim_setup_kernel<true><<<(a.count + 127) / 128, 128, 0, stream>>>(a);
+  else prim_setup_kernel<false><<<(a.count + 127) / 128, 128, 0, stream>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------ coarse binning
 // Coarse rect of a primitive in band-local coarse-bin coordinates, inclusive, packed x0 | y0<<8 | x1<<16 | y1<<24.
 // Empty primitives get x0 = 255 > x1 = 0 so they never match.
-__device__ __forceinline__ uint32_t coarse_rect(const Prim* prims, uint32_t idx, uint32_t n, const FrameView& f) {
+__device__ __forceinline__ uint32_t coarse_rect(const PrimBin* prims, uint32_t idx, uint32_t n, const FrameView& f) {
   if (idx >= n) return 0x000000FFu;
-  const int4 q6 = __ldg(reinterpret_cast<const int4*>(&prims[idx]) + 6);
+  const int4 q6 = __ldg(reinterpret_cast<const int4*>(&prims[idx]));
   if ((uint32_t)q6.z & PF_EMPTY) return 0x000000FFu;
   int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
   const int cpx = kTileW * kCoarse, cpy = kTileH * kCoarse;
@@ -612,7 +681,7 @@ __device__ __forceinline__ void warp_pair(const WarpPairs& wp, int p, int& owner
 }
 
 // Count pass: chunk_counts[bin][chunk] = pairs of this chunk in each bin of the CTA's row range.
-__global__ void __launch_bounds__(kChunk) coarse_count_kernel(const Prim* __restrict__ prims, uint32_t n, FrameView f, int rows_per_cta,
+__global__ void __launch_bounds__(kChunk) coarse_count_kernel(const PrimBin* __restrict__ prims, uint32_t n, FrameView f, int rows_per_cta,
                                                               uint32_t* __restrict__ chunk_counts) {
   __shared__ uint32_t s_hist[kSlots];
   const uint32_t chunk = blockIdx.x;
@@ -636,14 +705,14 @@ __global__ void __launch_bounds__(kChunk) coarse_count_kernel(const Prim* __rest
 
 // Scatter pass: the same enumeration; positions = bin start + pairs of earlier chunks + pairs of earlier warps of this
 // chunk + pairs of earlier rounds of this warp + rank inside the round.
-__global__ void __launch_bounds__(kChunk) coarse_scatter_kernel(const Prim* __restrict__ prims, uint32_t n, FrameView f, int rows_per_cta,
+__global__ void __launch_bounds__(kChunk) coarse_scatter_kernel(const PrimBin* __restrict__ prims, uint32_t n, FrameView f, int rows_per_cta,
                                                                 const uint32_t* __restrict__ chunk_counts,
                                                                 const uint32_t* __restrict__ cbin_start,
                                                                 uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
                                                                 const uint32_t* __restrict__ counters) {
   // per (bin, warp): first the pair count, then (after the prefix over warps) the running offset inside the chunk's
   // slice of the bin.  16 bits each (a chunk puts at most 512 pairs into a bin), two warps per word.
-  __shared__ uint32_t s_pos[kSlots][kWarps / 2];
+  __shared__ uint32_t s_pos[kWarps / 2][kSlots];  // [word][bin]: consecutive threads on consecutive banks
   __shared__ uint32_t s_gbase[kSlots];
   if (counters[kCntCoarseTotal] > coarse_cap) return;  // overflow: host regrows and re-runs the frame
   const uint32_t chunk = blockIdx.x;
@@ -651,7 +720,8 @@ __global__ void __launch_bounds__(kChunk) coarse_scatter_kernel(const Prim* __re
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int used = (row1 - row0) * f.cbx;
   const uint32_t rect = coarse_rect(prims, chunk * kChunk + threadIdx.x, n, f);
-  for (int i = threadIdx.x; i < used * (kWarps / 2); i += blockDim.x) (&s_pos[0][0])[i] = 0;
+  for (int k = 0; k < kWarps / 2; k++)
+    for (int sl = threadIdx.x; sl < used; sl += blockDim.x) s_pos[k][sl] = 0;
   for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {
     const int b = row0 * f.cbx + sl;
     s_gbase[sl] = cbin_start[b] + chunk_counts[(size_t)b * gridDim.x + chunk];
@@ -663,16 +733,16 @@ __global__ void __launch_bounds__(kChunk) coarse_scatter_kernel(const Prim* __re
     const int p = base + lane;
     int owner, bx, by;
     warp_pair(wp, min(p, wp.total - 1), owner, bx, by);
-    if (p < wp.total) atomicAdd(&s_pos[(by - row0) * f.cbx + bx][word], 1u << shift);
+    if (p < wp.total) atomicAdd(&s_pos[word][(by - row0) * f.cbx + bx], 1u << shift);
   }
   __syncthreads();
   for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {  // counts -> exclusive prefix over the 16 warps
     uint32_t run = 0;
 #pragma unroll
     for (int k = 0; k < kWarps / 2; k++) {
-      const uint32_t v = s_pos[sl][k];
+      const uint32_t v = s_pos[k][sl];
       const uint32_t lo = v & 0xFFFFu, hi = v >> 16;
-      s_pos[sl][k] = run | ((run + lo) << 16);
+      s_pos[k][sl] = run | ((run + lo) << 16);
       run += lo + hi;
     }
   }
@@ -688,11 +758,11 @@ __global__ void __launch_bounds__(kChunk) coarse_scatter_kernel(const Prim* __re
     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, active ? (uint32_t)sl : (0x80000000u | (uint32_t)lane));
     if (active) {
       const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-      const uint32_t off = (s_pos[sl][word] >> shift) & 0xFFFFu;
+      const uint32_t off = (s_pos[word][sl] >> shift) & 0xFFFFu;
       coarse_list[s_gbase[sl] + off + rank] = first + (uint32_t)owner;
     }
     __syncwarp();
-    if (active && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&s_pos[sl][word], (uint32_t)__popc(peers) << shift);
+    if (active && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&s_pos[word][sl], (uint32_t)__popc(peers) << shift);
     __syncwarp();
   }
 }
@@ -876,7 +946,7 @@ constexpr size_t kDirectFineLimit = FDC_DIRECT_FINE_LIMIT;  // primitives x coar
 // warp turn "tiles per entry" into "entries per tile", and lane t then owns tiles t and 32+t of the bin: the count is
 // a popc, the emission order is the order of the set bits.  (Before: warp w owned tile row w and every warp walked
 // every entry with one ballot per tile column -- 8x the instructions for the same lists; profiles/r01_binning.md.)
-__global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ prims, FrameView f,
+__global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict__ prims, FrameView f,
                                                        const uint32_t* __restrict__ cbin_start,
                                                        const uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
                                                        uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile_count,
@@ -966,10 +1036,10 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const Prim* __restrict__ 
           }
 #pragma unroll
           for (int j = 0; j < 4; j++)
-            q6[j] = pid[j] != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const int4*>(&prims[pid[j]]) + 6) : make_int4(0, 0, 0, 0);
+            q6[j] = pid[j] != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const int4*>(&prims[pid[j]])) : make_int4(0, 0, 0, 0);
 #pragma unroll
           for (int j = 0; j < 4; j++)
-            ir[j] = (pid[j] != 0xFFFFFFFFu && ((uint32_t)q6[j].z & PF_INNER)) ? __ldg(reinterpret_cast<const int2*>(&prims[pid[j]]) + 11)
+            ir[j] = (pid[j] != 0xFFFFFFFFu && ((uint32_t)q6[j].z & PF_INNER)) ? __ldg(reinterpret_cast<const int2*>(&prims[pid[j]]) + 2)
                                                                               : make_int2(0, 0);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
@@ -1044,7 +1114,7 @@ void launch_fill_u32(uint32_t* dst, uint32_t value, size_t n, cudaStream_t strea
   fill_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dst, value, n);
 }
 
-void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& f, const BinBuffers& b, cudaStream_t stream,
+void launch_binning(const PrimBin* prims, uint32_t n_prims, const FrameView& f, const BinBuffers& b, cudaStream_t stream,
                     int* n_launches) {
   const int n_bins = f.cbx * f.cby;
   const int n_chunks = (int)((n_prims + kChunk - 1) / kChunk);

@@ -247,6 +247,7 @@ struct fdc_ctx {
   DevBuf<Xform> d_xforms;
   DevBuf<RectMaskRec> d_rectmasks;
   DevBuf<Prim> d_prims;
+  DevBuf<PrimBin> d_prim_bins;
   DevBuf<QuadGeom> d_geoms;
   DevBuf<PrimExt> d_exts;
   DevBuf<uint32_t> d_prim_call;
@@ -691,6 +692,7 @@ SetupArgs setup_args(fdc_ctx* ctx, const Segment& s) {
   a.first = s.first;
   a.count = s.count;
   a.prims = ctx->d_prims.p + s.first;
+  a.prim_bins = ctx->d_prim_bins.p + s.first;
   a.geoms = ctx->d_geoms.p + s.first;
   a.exts = ctx->d_exts.p + s.first;
   a.prim_call = ctx->d_prim_call.p + s.first;
@@ -724,6 +726,7 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
     CK(ctx->d_xforms.reserve(std::max<size_t>(ctx->xforms.n, 1)));
     CK(ctx->d_rectmasks.reserve(std::max<size_t>(ctx->rectmasks.n, 1)));
     CK(ctx->d_prims.reserve(std::max<uint32_t>(n_draws, 1)));
+    CK(ctx->d_prim_bins.reserve(std::max<uint32_t>(n_draws, 1)));
     CK(ctx->d_geoms.reserve(std::max<uint32_t>(n_draws, 1)));
     CK(ctx->d_exts.reserve(std::max<uint32_t>(n_draws, 1)));
     CK(ctx->d_prim_call.reserve(std::max<uint32_t>(n_draws, 1)));
@@ -806,7 +809,7 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
       Timed t(ctx, 0);
       launch_prim_setup(setup_args(ctx, s), st);
       launches += s.count ? 1 : 0;
-      launch_binning(ctx->d_prims.p + s.first, s.count, ctx->frame, bin_buffers(ctx), st, &launches);
+      launch_binning(ctx->d_prim_bins.p + s.first, s.count, ctx->frame, bin_buffers(ctx), st, &launches);
     }
     {
       Timed t(ctx, 1);
@@ -1065,7 +1068,7 @@ void fdc_destroy(fdc_ctx* ctx) {
   ctx->flat[0].release(); ctx->flat[1].release();
   ctx->d_rects64.release();
   ctx->d_draws.release(); ctx->d_runs.release(); ctx->d_xforms.release(); ctx->d_rectmasks.release();
-  ctx->d_prims.release(); ctx->d_geoms.release(); ctx->d_exts.release(); ctx->d_prim_call.release();
+  ctx->d_prims.release(); ctx->d_prim_bins.release(); ctx->d_geoms.release(); ctx->d_exts.release(); ctx->d_prim_call.release();
   ctx->d_chunk_counts.release(); ctx->d_cbin_start.release(); ctx->d_coarse_list.release();
   ctx->d_tile_start.release(); ctx->d_tile_count.release(); ctx->d_tile_list.release(); ctx->d_counters.release();
   ctx->d_fb.release(); ctx->d_backdrop.release(); ctx->d_temp.release(); ctx->d_peers.release(); ctx->d_snapshot.release();
@@ -1963,7 +1966,7 @@ int fdc_debug_bins(fdc_ctx* ctx, int segment, uint32_t* tile_offsets, size_t off
   // Re-run setup + binning for this segment (the lists are reused between segments), then read them back.
   int launches = 0;
   launch_prim_setup(setup_args(ctx, s), ctx->stream);
-  launch_binning(ctx->d_prims.p + s.first, s.count, ctx->frame, bin_buffers(ctx), ctx->stream, &launches);
+  launch_binning(ctx->d_prim_bins.p + s.first, s.count, ctx->frame, bin_buffers(ctx), ctx->stream, &launches);
   CK(cudaStreamSynchronize(ctx->stream));
   const size_t n_tiles = (size_t)ctx->frame.tiles_x * ctx->frame.tiles_y;
   std::vector<uint32_t> start(n_tiles, 0), count(n_tiles, 0), calls(std::max<uint32_t>(s.count, 1));

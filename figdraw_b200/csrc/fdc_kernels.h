@@ -14,6 +14,7 @@ struct SetupArgs {
   const Xform* xforms;
   uint32_t first, count;  // this segment's draw range [first, first+count)
   Prim* prims;            // [count] output
+  PrimBin* prim_bins;     // [count] output: bbox / flags / inner rect for the binning kernels
   QuadGeom* geoms;        // [count] output (only PF_GENERAL entries are meaningful)
   PrimExt* exts;          // [count] output (only gradient PF_FAST entries are meaningful)
   uint32_t* prim_call;    // [count] backend-call ordinal per primitive (debug bins)
@@ -33,7 +34,7 @@ struct BinBuffers {
   uint32_t tile_cap;
   uint32_t* counters;      // [kNumCounters], see fdc_types.h (kCnt...)
 };
-void launch_binning(const Prim* prims, uint32_t n_prims, const FrameView& frame, const BinBuffers& b,
+void launch_binning(const PrimBin* prim_bins, uint32_t n_prims, const FrameView& frame, const BinBuffers& b,
                     cudaStream_t stream, int* n_launches);
 
 struct ShadeArgs {

@@ -17,7 +17,10 @@ namespace fdc {
 constexpr int kTileW = 16;         // pixels
 constexpr int kTileH = 16;
 constexpr int kCoarse = 8;         // coarse bin = kCoarse x kCoarse tiles (128 x 128 px)
-constexpr int kChunk = 512;        // primitives per coarse-binning chunk (16 warps x 32)
+#ifndef FDC_CHUNK
+#define FDC_CHUNK 512
+#endif
+constexpr int kChunk = FDC_CHUNK;  // primitives per coarse-binning chunk (one CTA; 32 per warp)
 constexpr int kMaxMaskDepth = 15;  // texture-mask nesting (GL: unbounded): levels 1..8 live in two registers per pixel, 9..15 in
                                    // shared memory (the depth field of a tile entry has 4 bits)
 constexpr int kAtlasMargin = 4;    // glcontext.nim:257
@@ -121,6 +124,17 @@ struct alignas(16) Prim {
   float su, ou, sv, ov;
 };
 static_assert(sizeof(Prim) == 128, "Prim must be 128 bytes");
+
+// What the binning kernels need of a primitive, 32 bytes in an array of its own: they stream / gather these instead of
+// two 16-byte pieces out of every 128-byte Prim (4x fewer sectors for the coarse passes, one sector per gathered entry
+// in the fine pass).
+struct alignas(32) PrimBin {
+  int16_t bx0, by0, bx1, by1;  // = Prim q6: clipped bin bbox
+  uint32_t mode_flags, aux;
+  int16_t ix0, iy0, ix1, iy1;  // = Prim inner rect (valid with PF_INNER)
+  uint32_t pad_[2];
+};
+static_assert(sizeof(PrimBin) == 32, "PrimBin must be 32 bytes");
 
 // Gradient colours of a PF_FAST primitive as floats (0..255), evaluated straight from the pixel index.
 //   3-stop (fill mode 1..4): tt = sat(x*ta + y*tb + tc); colour = tt <= mid ? a0 + d0*tt : a1 + d1*tt

@@ -494,6 +494,7 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
     # its own records host->device and its own frame device->host; in steady state frame k's readback, frame k+1's
     # kernels and frame k+2's upload are in flight together.  Throughput over the steps, not latency.
     e2e_pipe_ms, depth = None, 1
+    present_ms, present_ok = None, None
     y0b, y1b = ctx.bandRows() if world > 1 else (0, H)
     if world == 1 or symm_t is not None:
         ring = [(ctx, prepared, out_np)]
@@ -531,6 +532,29 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
         e2e_pipe_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
         if not all(bool(np.array_equal(out_np[y0b:y1b], r[2][y0b:y1b])) for r in ring[1:]):
             raise SystemExit("pipelined contexts produced different frames")
+        # e2e, presenter variant (N = 1): the frame stays on the device in an exported allocation a presenter imports
+        # (fdc_export_framebuffer) -- records still cross PCIe every step, pixels never do.
+        if world == 1 and headline:
+            try:
+                for c, _p, _o in ring:
+                    c.exportFramebuffer(W, H)
+
+                def presented(n):
+                    for k in range(n):
+                        c, prep, _o = ring[k % depth]
+                        submit(c, prep)  # beginFrame waits for the frame this context rendered `depth` steps ago
+                    for c, _p, _o in ring:
+                        c.sync()
+
+                presented(6)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                presented(e2e_steps)
+                torch.cuda.synchronize()
+                present_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+                present_ok = bool(np.array_equal(ring[0][0].readPixels(), out_np))
+            except Exception as e:  # noqa: BLE001
+                present_ms, present_ok = None, repr(e)[:200]
         for c2, _o, _k in extra_ctx:
             c2.close()
 
@@ -568,7 +592,7 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
     res = {"name": name, "trace": trace, "W": W, "H": H, "ms_step": ms_step, "e2e_ms": e2e_ms, "e2e_pipe_ms": e2e_pipe_ms,
            "depth": depth, "shade_ms": shade_ms, "bin_ms": bin_ms, "clocks": clocks, "launches_per_frame": launches_per_frame,
            "n_tile_entries": int(stats.n_tile_entries), "h2d": int(prepared_upload_bytes(prepared)), "out_np": out_np,
-           "sharded_upload": bool(world > 1 and symm_t is not None),
+           "sharded_upload": bool(world > 1 and symm_t is not None), "present_ms": present_ms, "present_ok": present_ok,
            "calls_np": calls_np, "gathered_ok": gathered_ok, "single_gpu_ms": single_gpu_ms, "use_p2p": use_p2p,
            "gather": gather_mode}
     ctx.close()
@@ -672,6 +696,11 @@ def main():
                                        ("every rank uploads the whole stream and reads its own band back" if world > 1 else "one GPU"))},
                 "gpu_launches": r["launches_per_frame"] * args.steps, "launches_per_frame": r["launches_per_frame"],
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base}
+        if r["present_ms"]:
+            line["e2e_present"] = {"value": round(mpx / (r["present_ms"] * 1e-3), 2), "unit": METRIC, "ms_per_step": round(r["present_ms"], 4),
+                                   "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 0, "frame_equals_readback": r["present_ok"],
+                                   "note": "same steps as e2e but the frame is left in an exported device allocation a presenter "
+                                           "imports (fdc_export_framebuffer): no read-back.  Not the headline: e2e above reads pixels to the host"}
         if r["gathered_ok"] is not None:
             line["gathered_frame_equals_single_gpu"] = r["gathered_ok"]
             line["single_gpu_same_workload"] = {"ms_per_step": round(r["single_gpu_ms"], 4),

@@ -179,7 +179,7 @@ EXPORTS = [
     "fdc_submit_calls", "fdc_submit_draws", "fdc_pack_rect64", "fdc_expand_rect64", "fdc_submit_rects64",
     "fdc_put_image", "fdc_update_image", "fdc_has_image", "fdc_get_image_rect", "fdc_remove_image",
     "fdc_reset_image_atlas", "fdc_atlas_size", "fdc_atlas_packed_area",
-    "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers", "fdc_bind_shared_framebuffer", "fdc_set_frame_barrier", "fdc_set_peer_gather", "fdc_reserve_framebuffer", "fdc_framebuffer_ipc_handle", "fdc_open_peer_framebuffer",
+    "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers", "fdc_bind_shared_framebuffer", "fdc_set_frame_barrier", "fdc_export_framebuffer", "fdc_set_peer_gather", "fdc_reserve_framebuffer", "fdc_framebuffer_ipc_handle", "fdc_open_peer_framebuffer",
     "fdc_get_frame_stats", "fdc_debug_bins", "fdc_debug_shade_stats",
     "fdc_flatten_renders", "fdc_render_frame",
 ]
@@ -277,6 +277,7 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_read_pixels_async", c.c_int, P, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p)
     sig("fdc_set_peer_gather", c.c_int, P, c.c_int, c.c_int)
     sig("fdc_set_frame_barrier", c.c_int, P, c.c_int)
+    sig("fdc_export_framebuffer", c.c_int, P, c.c_int, c.c_int, c.POINTER(c.c_int), c.POINTER(c.c_size_t))
     sig("fdc_bind_shared_framebuffer", c.c_int, P, P, c.c_size_t, c.POINTER(P), c.c_int, P, c.c_int, c.c_int)
     sig("fdc_flatten_renders", c.c_int, c.POINTER(FdcScene), c.POINTER(FdcFlattenEnv), c.c_void_p, c.c_size_t,
         c.POINTER(c.c_size_t))

@@ -632,48 +632,65 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 // ---- coarse level, r02: (primitive, bin) PAIRS instead of a bitmap walk.
 // A primitive covers a small rectangle of 128x128-px bins (1.8 on average at 4K).  The r01 kernels marked bins in a
 // bitmap and transposed every marked 32-bin word across the warp -- ~100 warp instructions per primitive, independent
-// of how few pairs there were.  Now a warp enumerates exactly the pairs of its 32 primitives, in primitive order, 32
-// pairs per round: a warp-level exclusive scan of the pair counts, a 5-step search for each pair's owner lane, and one
-// shuffle for the owner's rectangle.  Counting is a shared-memory histogram; the stable rank of a pair inside a round
-// is popc(match_any(bin) & lower lanes), rounds and warps are ordered by running offsets kept per (bin, warp).
-// Cost follows the number of pairs (a band of an 8-GPU partition has 1/8 of them), a full-frame primitive simply
-// contributes many rounds.
+// of how few pairs there were.  Now a CTA enumerates exactly the pairs of its chunk of primitives, in primitive order:
+// an exclusive scan of the per-primitive pair counts, then every warp takes an equal, contiguous share of the pair
+// sequence 32 pairs at a time (a binary search finds each pair's owner), so a full-frame primitive with hundreds of
+// pairs is spread over all warps instead of serialising one.  Counting is a shared-memory histogram; the stable rank
+// of a pair inside a round is popc(match_any(bin) & lower lanes); rounds and warps are ordered by running offsets
+// kept per (bin, warp).  Cost follows the number of pairs -- a band of an 8-GPU partition has 1/8 of them.
 constexpr int kSlots = 1024;  // coarse bins one CTA handles: a range of whole bin rows
 constexpr int kWarps = kChunk / 32;
 
-struct WarpPairs {
-  uint32_t packed;  // x0 | y0 << 8 | w << 16 of my primitive's bin rectangle clipped to the CTA's row range
-  int k;            // its number of bins
-  int excl, total;  // exclusive scan of k over the warp, and the warp's total
+struct ChunkPairs {
+  uint32_t* excl;    // [kChunk] exclusive scan of the pair counts
+  uint32_t* rect;    // [kChunk] x0 | y0 << 8 | w << 16 of each primitive's bin rectangle clipped to the CTA's row range
+  uint32_t total;    // pairs of the chunk
+  uint32_t lo, hi;   // this warp's share [lo, hi)
 };
-__device__ __forceinline__ WarpPairs warp_pairs(uint32_t rect, int row0, int row1, int lane) {
-  WarpPairs wp;
+// All threads of the CTA call this; ends with a __syncthreads().
+__device__ __forceinline__ ChunkPairs chunk_pairs(uint32_t rect, int row0, int row1, uint32_t* s_excl, uint32_t* s_rect,
+                                                  uint32_t* s_wtot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x0 = rect & 255u, y0 = (rect >> 8) & 255u, x1 = (rect >> 16) & 255u, y1 = rect >> 24;
   const int ya = max(y0, row0), yb = min(y1, row1 - 1);
   const int w = x1 - x0 + 1, h = yb - ya + 1;
-  wp.k = (w > 0 && h > 0) ? w * h : 0;  // empty primitives carry x0 = 255 > x1 = 0
-  wp.packed = (uint32_t)x0 | ((uint32_t)(ya & 255) << 8) | ((uint32_t)(w & 0xFFFF) << 16);
-  int incl = wp.k;
+  const uint32_t k = (w > 0 && h > 0) ? (uint32_t)(w * h) : 0u;  // empty primitives carry x0 = 255 > x1 = 0
+  s_rect[threadIdx.x] = (uint32_t)x0 | ((uint32_t)(ya & 255) << 8) | ((uint32_t)(w & 0xFFFF) << 16);
+  uint32_t incl = k;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
     if (lane >= o) incl += t;
   }
-  wp.excl = incl - wp.k;
-  wp.total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-  return wp;
-}
-// Pair number p of the warp (p < total): which lane owns it and which bin it is.  All lanes call this together.
-__device__ __forceinline__ void warp_pair(const WarpPairs& wp, int p, int& owner, int& bx, int& by) {
-  owner = 0;
+  if (lane == 31) s_wtot[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0, total = 0;
 #pragma unroll
-  for (int step = 16; step >= 1; step >>= 1) {
-    const int cand = owner + step;  // < 32 always: steps add up to at most 31
-    const int e = __shfl_sync(0xFFFFFFFFu, wp.excl, cand);
-    if (e <= p) owner = cand;       // ties: the highest lane wins, which skips lanes without pairs
+  for (int j = 0; j < kWarps; j++) {
+    const uint32_t t = s_wtot[j];
+    if (j < warp) wbase += t;
+    total += t;
   }
-  const uint32_t r = __shfl_sync(0xFFFFFFFFu, wp.packed, owner);
-  const int j = p - __shfl_sync(0xFFFFFFFFu, wp.excl, owner);
+  s_excl[threadIdx.x] = wbase + incl - k;
+  __syncthreads();
+  ChunkPairs cp;
+  cp.excl = s_excl;
+  cp.rect = s_rect;
+  cp.total = total;
+  const uint32_t rounds = (total + 31u) >> 5, per_warp = (rounds + kWarps - 1) / kWarps;
+  cp.lo = min(total, (uint32_t)warp * per_warp * 32u);
+  cp.hi = min(total, cp.lo + per_warp * 32u);
+  return cp;
+}
+// Pair number p of the chunk (p < total): its owner (index inside the chunk) and its bin.
+__device__ __forceinline__ void chunk_pair(const ChunkPairs& cp, uint32_t p, int& owner, int& bx, int& by) {
+  int o = 0;
+#pragma unroll
+  for (int step = kChunk / 2; step >= 1; step >>= 1)
+    if (cp.excl[o + step] <= p) o += step;  // largest index with excl <= p; ties: the highest wins, skipping empty ones
+  owner = o;
+  const uint32_t r = cp.rect[o];
+  const int j = (int)(p - cp.excl[o]);
   const int w = max((int)(r >> 16), 1);
   const int q = (int)(((float)j + 0.5f) * (1.0f / (float)w));  // j / w, exact for j < 2^16
   bx = (int)(r & 255u) + (j - q * w);
@@ -684,26 +701,28 @@ __device__ __forceinline__ void warp_pair(const WarpPairs& wp, int p, int& owner
 __global__ void __launch_bounds__(kChunk) coarse_count_kernel(const PrimBin* __restrict__ prims, uint32_t n, FrameView f, int rows_per_cta,
                                                               uint32_t* __restrict__ chunk_counts) {
   __shared__ uint32_t s_hist[kSlots];
+  __shared__ uint32_t s_excl[kChunk], s_rect[kChunk], s_wtot[kWarps];
   const uint32_t chunk = blockIdx.x;
   const int row0 = blockIdx.y * rows_per_cta, row1 = min(row0 + rows_per_cta, f.cby);
   const int lane = threadIdx.x & 31;
   const int used = (row1 - row0) * f.cbx;
   const uint32_t rect = coarse_rect(prims, chunk * kChunk + threadIdx.x, n, f);
   for (int sl = threadIdx.x; sl < used; sl += blockDim.x) s_hist[sl] = 0;
-  __syncthreads();
-  const WarpPairs wp = warp_pairs(rect, row0, row1, lane);
-  for (int base = 0; base < wp.total; base += 32) {
-    const int p = base + lane;
-    int owner, bx, by;
-    warp_pair(wp, min(p, wp.total - 1), owner, bx, by);
-    if (p < wp.total) atomicAdd(&s_hist[(by - row0) * f.cbx + bx], 1u);
+  const ChunkPairs cp = chunk_pairs(rect, row0, row1, s_excl, s_rect, s_wtot);
+  for (uint32_t base = cp.lo; base < cp.hi; base += 32) {
+    const uint32_t p = base + lane;
+    if (p < cp.hi) {
+      int owner, bx, by;
+      chunk_pair(cp, p, owner, bx, by);
+      atomicAdd(&s_hist[(by - row0) * f.cbx + bx], 1u);
+    }
   }
   __syncthreads();
   for (int sl = threadIdx.x; sl < used; sl += blockDim.x)
     chunk_counts[(size_t)(row0 * f.cbx + sl) * gridDim.x + chunk] = s_hist[sl];
 }
 
-// Scatter pass: the same enumeration; positions = bin start + pairs of earlier chunks + pairs of earlier warps of this
+// Scatter pass: the same enumeration; position = bin start + pairs of earlier chunks + pairs of earlier warps of this
 // chunk + pairs of earlier rounds of this warp + rank inside the round.
 __global__ void __launch_bounds__(kChunk) coarse_scatter_kernel(const PrimBin* __restrict__ prims, uint32_t n, FrameView f, int rows_per_cta,
                                                                 const uint32_t* __restrict__ chunk_counts,
@@ -711,9 +730,11 @@ __global__ void __launch_bounds__(kChunk) coarse_scatter_kernel(const PrimBin* _
                                                                 uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
                                                                 const uint32_t* __restrict__ counters) {
   // per (bin, warp): first the pair count, then (after the prefix over warps) the running offset inside the chunk's
-  // slice of the bin.  16 bits each (a chunk puts at most 512 pairs into a bin), two warps per word.
-  __shared__ uint32_t s_pos[kWarps / 2][kSlots];  // [word][bin]: consecutive threads on consecutive banks
+  // slice of the bin.  16 bits each (a chunk puts at most kChunk pairs into a bin), two warps per word; [word][bin] so
+  // that consecutive threads hit consecutive banks.
+  __shared__ uint32_t s_pos[kWarps / 2][kSlots];
   __shared__ uint32_t s_gbase[kSlots];
+  __shared__ uint32_t s_excl[kChunk], s_rect[kChunk], s_wtot[kWarps];
   if (counters[kCntCoarseTotal] > coarse_cap) return;  // overflow: host regrows and re-runs the frame
   const uint32_t chunk = blockIdx.x;
   const int row0 = blockIdx.y * rows_per_cta, row1 = min(row0 + rows_per_cta, f.cby);
@@ -726,17 +747,18 @@ __global__ void __launch_bounds__(kChunk) coarse_scatter_kernel(const PrimBin* _
     const int b = row0 * f.cbx + sl;
     s_gbase[sl] = cbin_start[b] + chunk_counts[(size_t)b * gridDim.x + chunk];
   }
-  __syncthreads();
-  const WarpPairs wp = warp_pairs(rect, row0, row1, lane);
+  const ChunkPairs cp = chunk_pairs(rect, row0, row1, s_excl, s_rect, s_wtot);
   const int word = warp >> 1, shift = (warp & 1) * 16;
-  for (int base = 0; base < wp.total; base += 32) {
-    const int p = base + lane;
-    int owner, bx, by;
-    warp_pair(wp, min(p, wp.total - 1), owner, bx, by);
-    if (p < wp.total) atomicAdd(&s_pos[word][(by - row0) * f.cbx + bx], 1u << shift);
+  for (uint32_t base = cp.lo; base < cp.hi; base += 32) {
+    const uint32_t p = base + lane;
+    if (p < cp.hi) {
+      int owner, bx, by;
+      chunk_pair(cp, p, owner, bx, by);
+      atomicAdd(&s_pos[word][(by - row0) * f.cbx + bx], 1u << shift);
+    }
   }
   __syncthreads();
-  for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {  // counts -> exclusive prefix over the 16 warps
+  for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {  // counts -> exclusive prefix over the warps
     uint32_t run = 0;
 #pragma unroll
     for (int k = 0; k < kWarps / 2; k++) {
@@ -747,12 +769,12 @@ __global__ void __launch_bounds__(kChunk) coarse_scatter_kernel(const PrimBin* _
     }
   }
   __syncthreads();
-  const uint32_t first = chunk * kChunk + (uint32_t)warp * 32u;
-  for (int base = 0; base < wp.total; base += 32) {
-    const int p = base + lane;
-    const bool active = p < wp.total;
-    int owner, bx, by;
-    warp_pair(wp, min(p, wp.total - 1), owner, bx, by);
+  const uint32_t first = chunk * kChunk;
+  for (uint32_t base = cp.lo; base < cp.hi; base += 32) {
+    const uint32_t p = base + lane;
+    const bool active = p < cp.hi;
+    int owner = 0, bx = 0, by = row0;
+    if (active) chunk_pair(cp, p, owner, bx, by);
     const int sl = (by - row0) * f.cbx + bx;
     // pairs of one round are in primitive order along the lanes: the rank among equal bins is the stable rank
     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, active ? (uint32_t)sl : (0x80000000u | (uint32_t)lane));

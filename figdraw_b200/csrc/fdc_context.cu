@@ -7,11 +7,13 @@
 //     prim_setup -> coarse count -> coarse scan -> coarse scatter -> fine bin -> shade   [-> blur H -> blur V] ...
 // once per segment (a segment ends at each backdrop blur, which must read everything painted before it).
 // All quad arithmetic (ceil, radii packing, gradient colours, mode encoding) happens on the device.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <string>
@@ -259,6 +261,8 @@ struct fdc_ctx {
   bool frame_resolved = false;     // resolve_frame has already checked the frame in flight
   uint32_t dbg_coarse_limit = 0, dbg_tile_limit = 0;  // fdc_debug_limit_lists: pretend the bin lists are this small (0: real size)
   uint8_t* ext_fb = nullptr;
+  // fdc_export_framebuffer: the framebuffer as a CUDA VMM allocation whose POSIX file descriptor a presenter imports
+  struct { unsigned long long handle = 0, va = 0; size_t size = 0; int fd = -1; } exported;
   uint8_t* mc_fb = nullptr;        // NVSwitch multicast mapping of the (shared) framebuffer, or nullptr
   bool frame_barrier = false;      // end every frame with a cross-rank flag barrier (shared framebuffer: the gather is fused)
   DevBuf<uint8_t*> d_peers;
@@ -746,6 +750,8 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
   const size_t fb_bytes = (size_t)ctx->W * ctx->H * 4;
   if (ctx->flag_off && fb_bytes > ctx->flag_off)
     return ctx->fail(FDC_ERR_CAPACITY, "frame larger than the framebuffer reserved with fdc_reserve_framebuffer / fdc_bind_shared_framebuffer");
+  if (ctx->exported.va && ctx->ext_fb == (uint8_t*)ctx->exported.va && fb_bytes > ctx->exported.size)
+    return ctx->fail(FDC_ERR_CAPACITY, "frame larger than the framebuffer exported with fdc_export_framebuffer");
   if (!ctx->ext_fb) {
     const size_t had = ctx->d_fb.cap;
     CK(ctx->d_fb.reserve(fb_bytes));
@@ -1005,6 +1011,34 @@ uint8_t quant8(float x) {
 
 }  // namespace
 
+namespace {
+// Driver API entry points through the runtime (the library links cudart statically and must load where no driver is
+// installed, e.g. for the ABI checks on a CPU-only machine).
+template <typename F>
+bool driver_fn(const char* name, F* out) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || !p || q != cudaDriverEntryPointSuccess) return false;
+  *out = reinterpret_cast<F>(p);
+  return true;
+}
+void release_export(fdc_ctx* ctx) {
+  auto& e = ctx->exported;
+  if (!e.va) return;
+  CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*addr_free)(CUdeviceptr, size_t) = nullptr;
+  if (driver_fn("cuMemUnmap", &unmap) && driver_fn("cuMemRelease", &release) && driver_fn("cuMemAddressFree", &addr_free)) {
+    unmap((CUdeviceptr)e.va, e.size);
+    release((CUmemGenericAllocationHandle)e.handle);
+    addr_free((CUdeviceptr)e.va, e.size);
+  }
+  if (e.fd >= 0) close(e.fd);
+  if (ctx->ext_fb == (uint8_t*)e.va) ctx->ext_fb = nullptr;
+  e = {};
+}
+}  // namespace
+
 // ================================================================================================= C ABI
 extern "C" {
 
@@ -1062,6 +1096,7 @@ void fdc_destroy(fdc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  release_export(ctx);
   for (int l = 0; l < ctx->n_levels; l++) cudaFree(ctx->levels[l]);
   ctx->d_table.release();
   ctx->draws.release(); ctx->runs.release(); ctx->xforms.release(); ctx->rectmasks.release();
@@ -1781,6 +1816,67 @@ int fdc_set_peer_framebuffers(fdc_ctx* ctx, void* const* device_ptrs, int n) {
     CK(ctx->d_peers.reserve((size_t)n));
     CK(cudaMemcpy(ctx->d_peers.p, device_ptrs, sizeof(void*) * n, cudaMemcpyHostToDevice));
   }
+  return FDC_OK;
+}
+
+// Present without a read-back (replaces readPixels, glcontext.nim:2094-2135, for a presenter on the same machine): the
+// framebuffer becomes a CUDA VMM allocation exported as a POSIX file descriptor.  A Vulkan (VK_KHR_external_memory_fd,
+// OPAQUE_FD) or OpenGL (EXT_memory_object_fd) presenter -- or another CUDA process, cuMemImportFromShareableHandle --
+// imports it once and samples / blits the RGBA8 rows (pitch width*4, top-left origin) after fdc_sync; no pixel crosses
+// PCIe.  The descriptor stays owned by the context (dup() it to keep it beyond fdc_destroy).
+int fdc_export_framebuffer(fdc_ctx* ctx, int width, int rows, int* out_fd, size_t* out_bytes) {
+  if (!ctx || width <= 0 || rows <= 0 || !out_fd) return FDC_ERR_INVALID;
+  if (ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "cannot replace the framebuffer inside a frame");
+  CK(cudaSetDevice(ctx->device));
+  int rc = resolve_frame(ctx);
+  if (rc) return rc;
+  CUresult (*get_gran)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*export_fd)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+  if (!driver_fn("cuMemGetAllocationGranularity", &get_gran) || !driver_fn("cuMemCreate", &create) ||
+      !driver_fn("cuMemAddressReserve", &reserve) || !driver_fn("cuMemMap", &map) || !driver_fn("cuMemSetAccess", &set_access) ||
+      !driver_fn("cuMemExportToShareableHandle", &export_fd))
+    return ctx->fail(FDC_ERR_CUDA, "the CUDA driver does not provide the virtual memory management API");
+  release_export(ctx);
+  CUmemAllocationProp prop;
+  memset(&prop, 0, sizeof(prop));
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = ctx->device;
+  prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  size_t gran = 0;
+  if (get_gran(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0)
+    return ctx->fail(FDC_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+  const size_t size = (((size_t)width * rows * 4) + gran - 1) / gran * gran;
+  CUmemGenericAllocationHandle h = 0;
+  CUdeviceptr va = 0;
+  CUresult r = create(&h, size, &prop, 0);
+  if (r != CUDA_SUCCESS) return ctx->fail(FDC_ERR_CUDA, "cuMemCreate(%zu bytes, exportable) failed with %d", size, (int)r);
+  r = reserve(&va, size, gran, 0, 0);
+  if (r == CUDA_SUCCESS) r = map(va, size, 0, h, 0);
+  CUmemAccessDesc acc;
+  memset(&acc, 0, sizeof(acc));
+  acc.location = prop.location;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  if (r == CUDA_SUCCESS) r = set_access(va, size, &acc, 1);
+  int fd = -1;
+  if (r == CUDA_SUCCESS) r = export_fd(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+  if (r != CUDA_SUCCESS) return ctx->fail(FDC_ERR_CUDA, "mapping / exporting the framebuffer failed with %d", (int)r);
+  ctx->exported.handle = (unsigned long long)h;
+  ctx->exported.va = (unsigned long long)va;
+  ctx->exported.size = size;
+  ctx->exported.fd = fd;
+  CK(cudaMemsetAsync((void*)va, 0, size, ctx->stream));  // a fresh back buffer is transparent black
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->ext_fb = (uint8_t*)va;
+  ctx->mc_fb = nullptr;
+  ctx->frame_barrier = false;
+  ctx->flag_off = ctx->rec_off = ctx->rec_bytes = 0;
+  *out_fd = fd;
+  if (out_bytes) *out_bytes = size;
   return FDC_OK;
 }
 

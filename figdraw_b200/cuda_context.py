@@ -374,6 +374,13 @@ class CudaContext(BackendContext):
         self._ck(self._lib.fdc_bind_shared_framebuffer(self._h, ctypes.c_void_p(localPtr), int(nbytes), arr, len(peerPtrs),
                                                        ctypes.c_void_p(multicastPtr or 0), int(width), int(rows)))
 
+    def exportFramebuffer(self, width: int, rows: int) -> Tuple[int, int]:
+        """The framebuffer as an exportable allocation: (POSIX file descriptor, bytes).  A presenter imports the descriptor
+        (Vulkan / GL external memory, or CUDA) and reads the rows after sync(); no read-back over PCIe."""
+        fd, nbytes = ctypes.c_int(-1), ctypes.c_size_t(0)
+        self._ck(self._lib.fdc_export_framebuffer(self._h, int(width), int(rows), ctypes.byref(fd), ctypes.byref(nbytes)))
+        return fd.value, nbytes.value
+
     def setFrameBarrier(self, enabled: bool):
         self._ck(self._lib.fdc_set_frame_barrier(self._h, 1 if enabled else 0))
 

@@ -270,6 +270,12 @@ void* fdc_stream(fdc_ctx* ctx);
  * After every rank's frame has completed (any cross-rank barrier on fdc_stream) each framebuffer holds the
  * whole frame. */
 int fdc_set_peer_framebuffers(fdc_ctx* ctx, void* const* device_ptrs, int n);
+/* --- present without a read-back (replaces readPixels glcontext.nim:2094-2135 for a presenter on the
+ * same machine).  The framebuffer becomes an exportable allocation of at least width*rows*4 bytes (CUDA virtual memory
+ * management) and *out_fd receives its POSIX file descriptor: a Vulkan (VK_KHR_external_memory_fd, OPAQUE_FD), OpenGL
+ * (EXT_memory_object_fd) or CUDA (cuMemImportFromShareableHandle) consumer imports it once and reads RGBA8 rows of
+ * pitch width*4 after fdc_sync -- no pixel crosses PCIe.  The context keeps owning the descriptor. */
+int fdc_export_framebuffer(fdc_ctx* ctx, int width, int rows, int* out_fd, size_t* out_bytes);
 /* Multi-GPU with a framebuffer every rank can reach (the host allocates it: CUDA VMM / torch symmetric memory): this
  * rank's mapping (`bytes` >= width*rows*4 rounded up to 256, + 4096 bytes of cross-rank flags), the n_ranks peers'
  * mappings of THEIR copies (own entry ignored) and, behind an NVSwitch, the multicast mapping of all copies (or NULL).

@@ -104,6 +104,13 @@ __device__ void gradient_colors(int kind, int axis, const uint32_t* c, float mid
   for (int k = 0; k < 4; k++) out[k] = sample_color(kind, c, mid, ts[axis & 3][k]);
 }
 
+__device__ __forceinline__ int find_run_in(const RunState* runs, int lo, int hi, uint32_t draw) {
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (runs[mid].first_draw <= draw) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
 __device__ __forceinline__ int find_run(const RunState* runs, int n_runs, uint32_t draw) {
   int lo = 0, hi = n_runs - 1;
   while (lo < hi) {
@@ -177,9 +184,9 @@ struct DrawView {
 };
 
 // Full setup of draw record `i` of the segment; `rec` is its staging slot in shared memory (33 words).
-__device__ void setup_record(const SetupArgs& a, uint32_t i, uint32_t* rec) {
+__device__ void setup_record(const SetupArgs& a, uint32_t i, uint32_t* rec, int run_lo, int run_hi) {
   uint32_t di = a.first + i;
-  int ri = find_run(a.runs, a.n_runs, di);
+  int ri = find_run_in(a.runs, run_lo, run_hi, di);  // the CTA's records usually share one run: no search at all
   const RunState rs = a.runs[ri];
   if (rs.compact) {
     // the run arrived as 64-byte fdc_rect64 records: expand mine over my staging slot (only this thread reads it)
@@ -517,9 +524,9 @@ __device__ void setup_record(const SetupArgs& a, uint32_t i, uint32_t* rec) {
 // Tile-band partitions: most records of a frame land outside a rank's band (7/8 of them on 8 GPUs).  A rounded rect is
 // outside exactly when the full setup would find its clipped bbox empty; this restates just that part -- the same
 // transform, ceil and bbox arithmetic -- so the rest of the setup is skipped for it.
-__device__ bool outside_band(const SetupArgs& a, uint32_t i, const uint32_t* rec, uint32_t* call_index) {
+__device__ bool outside_band(const SetupArgs& a, uint32_t i, const uint32_t* rec, uint32_t* call_index, int run_lo, int run_hi) {
   const uint32_t di = a.first + i;
-  const RunState rs = a.runs[find_run(a.runs, a.n_runs, di)];
+  const RunState rs = a.runs[find_run_in(a.runs, run_lo, run_hi, di)];
   *call_index = rs.call_index + (di - rs.first_draw);
   if (rs.flags & PF_MASK_WIDE) return false;  // carries a clear over the parent's clip box whatever its own quad is
   float x, y, w, h;
@@ -539,28 +546,41 @@ __device__ bool outside_band(const SetupArgs& a, uint32_t i, const uint32_t* rec
   return max(bx0, 0) >= min(bx1, a.frame.W) || max(by0, a.frame.band_y0) >= min(by1, a.frame.band_y1);
 }
 
+#ifndef FDC_SETUP_MIN_BLOCKS
+#define FDC_SETUP_MIN_BLOCKS 1
+#endif
 template <bool kBanded>
-__global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
+__global__ void __launch_bounds__(128, FDC_SETUP_MIN_BLOCKS) prim_setup_kernel(SetupArgs a) {
   // The CTA's 128 records (16 KB) come in with coalesced 16-byte loads and are read back from shared memory at a
   // 33-word stride (no bank conflicts): one record per thread straight from global memory was a 128-byte-stride
   // gather that left the kernel waiting on loads (issue slot utilisation 0.17, profiles/r01_binning.md).
   __shared__ uint32_t s_draw[128][33];
   __shared__ uint32_t s_keep[128];
   __shared__ uint32_t s_nkeep;
+  __shared__ int s_run[3];  // runs of the CTA's first and last record; 1 when all of them arrived as compact records
   const uint32_t first = blockIdx.x * 128u;
   const uint32_t n_here = min(128u, a.count - first);
-  {
+  if (threadIdx.x == 0) {
+    const int lo = find_run(a.runs, a.n_runs, a.first + first);
+    const int hi = find_run_in(a.runs, lo, a.n_runs - 1, a.first + first + n_here - 1u);
+    int all_compact = 1;
+    for (int r = lo; r <= hi; r++) all_compact &= (int)a.runs[r].compact;
+    s_run[0] = lo; s_run[1] = hi; s_run[2] = all_compact;
+    if (kBanded) s_nkeep = 0;
+  }
+  __syncthreads();
+  const int run_lo = s_run[0], run_hi = s_run[1];
+  if (!s_run[2]) {  // compact runs have no fdc_call records to stage (their slots in `draws` are unused)
     const uint4* src = reinterpret_cast<const uint4*>(a.draws + a.first + first);
     for (uint32_t k = threadIdx.x; k < n_here * 8u; k += 128u) {
       const uint4 v = __ldg(src + k);
       uint32_t* dst = &s_draw[k >> 3][(k & 7u) * 4u];
       dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
     }
+    __syncthreads();
   }
-  if (kBanded && threadIdx.x == 0) s_nkeep = 0;
-  __syncthreads();
   if (!kBanded) {
-    if (threadIdx.x < n_here) setup_record(a, first + threadIdx.x, s_draw[threadIdx.x]);
+    if (threadIdx.x < n_here) setup_record(a, first + threadIdx.x, s_draw[threadIdx.x], run_lo, run_hi);
     return;
   }
   // Band partition: weed out the records that land outside the band first (they only get their PF_EMPTY marker), then
@@ -568,7 +588,7 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
   bool keep = false;
   if (threadIdx.x < n_here) {
     uint32_t call_index;
-    keep = !outside_band(a, first + threadIdx.x, s_draw[threadIdx.x], &call_index);
+    keep = !outside_band(a, first + threadIdx.x, s_draw[threadIdx.x], &call_index, run_lo, run_hi);
     if (!keep) {
       const uint32_t i = first + threadIdx.x;
       a.prim_call[i] = call_index;
@@ -587,7 +607,7 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(SetupArgs a) {
   const uint32_t n_keep = s_nkeep;
   for (uint32_t k = threadIdx.x; k < n_keep; k += 128u) {
     const uint32_t j = s_keep[k];
-    setup_record(a, first + j, s_draw[j]);
+    setup_record(a, first + j, s_draw[j], run_lo, run_hi);
   }
 }
 

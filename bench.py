@@ -86,7 +86,8 @@ def bench_config(name: str, trace, world: int, gather: str = "nccl") -> dict:
     else:
         part = f"{world} tile-row bands + NCCL all-gather"
     return {"workload": WORKLOADS[name], "frame": [trace.width, trace.height], "primitives": int(trace.n_draws),
-            "l2": "flushed between steps (256 MiB fill)", "partition": part}
+            "l2": "flushed between steps (256 MiB fill)", "partition": part,
+            "replay": "one CUDA-graph launch per frame (setup, binning, shade, barriers captured once)"}
 
 
 def algorithmic_flops(counts: np.ndarray) -> float:
@@ -475,9 +476,21 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
     env.barrier()
     times = timed_loop(step_resident, steps)
     env.barrier()
-    stats = ctx.frameStats()
     clocks = sampler.stop() if sampler else None
     ms_step = float(np.sum(times)) / steps
+    # per-phase times (setup + binning / shade) of the same frame: replayed launch by launch, because the timed steps above
+    # are single CUDA-graph launches and events inside a graph cannot be timed
+    ctx.setReplayGraph(False)
+    phase = []
+    for _ in range(5):
+        with torch.cuda.stream(stream):
+            env.flush.fill_(0)
+        step_resident()
+        st_ = ctx.frameStats()
+        phase.append((float(st_.shade_ms), float(st_.bin_ms), float(st_.gpu_ms)))
+    ctx.setReplayGraph(True)
+    stats = ctx.frameStats()
+    shade_plain, bin_plain, gpu_plain = (float(v) for v in np.median(np.array(phase), axis=0))
 
     # e2e: host records in, host pixels out, wall clock bracketed by synchronisation (copies are inside)
     for _ in range(2):
@@ -586,13 +599,13 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
             single_gpu_ms = float(np.median(single_ms[2:]))
             ref_ctx.close()
         env.barrier()
-    ms_step, e2e_ms, shade_ms, bin_ms, e2e_pipe_max = env.max_over_ranks([ms_step, e2e_ms, stats.shade_ms, stats.bin_ms, e2e_pipe_ms or 0.0])
+    ms_step, e2e_ms, shade_ms, bin_ms, e2e_pipe_max = env.max_over_ranks([ms_step, e2e_ms, shade_plain, bin_plain, e2e_pipe_ms or 0.0])
     if e2e_pipe_ms is not None:
         e2e_pipe_ms = e2e_pipe_max
     res = {"name": name, "trace": trace, "W": W, "H": H, "ms_step": ms_step, "e2e_ms": e2e_ms, "e2e_pipe_ms": e2e_pipe_ms,
            "depth": depth, "shade_ms": shade_ms, "bin_ms": bin_ms, "clocks": clocks, "launches_per_frame": launches_per_frame,
            "n_tile_entries": int(stats.n_tile_entries), "h2d": int(prepared_upload_bytes(prepared)), "out_np": out_np,
-           "sharded_upload": bool(world > 1 and symm_t is not None), "present_ms": present_ms, "present_ok": present_ok,
+           "sharded_upload": bool(world > 1 and symm_t is not None), "gpu_plain_ms": gpu_plain, "present_ms": present_ms, "present_ok": present_ok,
            "calls_np": calls_np, "gathered_ok": gathered_ok, "single_gpu_ms": single_gpu_ms, "use_p2p": use_p2p,
            "gather": gather_mode}
     ctx.close()
@@ -663,6 +676,8 @@ def main():
                 "algorithmic_flops_per_frame": flops, "fragments_per_frame": n_frag,
                 "peak_source": f"148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (SM clock sampled during the timed region), per GPU",
                 "shade_ms": round(shade_ms, 4), "bin_ms": round(bin_ms, 4),
+                "phase_note": "shade_ms / bin_ms: the same frame replayed launch by launch (%.4f ms per frame that way); the timed "
+                              "steps are single CUDA-graph launches" % r["gpu_plain_ms"],
                 "hbm": {"algorithmic_bytes": bytes_alg, "achieved_gbs": round(bytes_alg / (ms_step * 1e-3) / 1e9 / world, 1),
                         "peak_gbs": peaks.get("hbm_gbs"),
                         "frac": round(bytes_alg / (ms_step * 1e-3) / 1e9 / world / peaks.get("hbm_gbs", 6650.0), 4),

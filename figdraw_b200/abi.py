@@ -168,7 +168,7 @@ class FdcFrameStats(ctypes.Structure):
 EXPORTS = [
     "fdc_create", "fdc_destroy", "fdc_last_error", "fdc_abi_version",
     "fdc_begin_frame", "fdc_end_frame", "fdc_read_pixels", "fdc_read_pixels_async", "fdc_sync", "fdc_replay_frame",
-    "fdc_retry_frame", "fdc_abort_frame", "fdc_debug_limit_lists",
+    "fdc_retry_frame", "fdc_abort_frame", "fdc_debug_limit_lists", "fdc_set_replay_graph",
     "fdc_translate", "fdc_rotate", "fdc_scale", "fdc_apply_transform", "fdc_save_transform",
     "fdc_restore_transform", "fdc_transform_mirrors_y", "fdc_get_transform",
     "fdc_sdf_aa_factor", "fdc_set_sdf_aa_factor", "fdc_set_text_subpixel_positioning_enabled",
@@ -223,6 +223,7 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_sync", c.c_int, P)
     sig("fdc_replay_frame", c.c_int, P)
     sig("fdc_retry_frame", c.c_int, P)
+    sig("fdc_set_replay_graph", c.c_int, P, c.c_int)
     sig("fdc_abort_frame", c.c_int, P)
     sig("fdc_debug_limit_lists", c.c_int, P, c.c_uint32, c.c_uint32)
     sig("fdc_translate", c.c_int, P, c.c_float, c.c_float)

@@ -211,17 +211,26 @@ namespace {
 struct FlagPtrs {
   uint32_t* p[kMaxRanks];
 };
-__global__ void signal_flags_kernel(FlagPtrs f, int n, int my_rank, uint32_t value) {
+// The barrier VALUES live on the device (two counters in the rank's own flag page), not in kernel arguments: every
+// rank runs the same sequence of signals and waits, so "the k-th wait waits for the k-th signal of every rank" needs no
+// host bookkeeping -- and a frame captured into a CUDA graph can be replayed with the barriers inside it.
+__global__ void signal_flags_kernel(FlagPtrs f, int n, int my_rank) {
+  __shared__ uint32_t value;
+  if (threadIdx.x == 0) value = ++f.p[my_rank][kFlagSignalSeq];
+  __syncthreads();
   const int r = threadIdx.x;
   if (r >= n) return;
   __threadfence_system();  // everything this stream wrote before (the segment's pixels) is visible system-wide first
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[r] + my_rank), "r"(value) : "memory");
 }
-// Spin until every rank's slot reached `value`.  A peer that never arrives (crashed process, a frame submitted on
-// one rank only) must not hang the GPU: after kBarrierTimeoutNs the kernel records the failure in flags[kFlagError]
-// and lets the stream continue; the host reports it when the frame is resolved.
+// Spin until every rank's slot reached this rank's next wait number.  A peer that never arrives (crashed process, a
+// frame submitted on one rank only) must not hang the GPU: after kBarrierTimeoutNs the kernel records the failure in
+// flags[kFlagError] and lets the stream continue; the host reports it when the frame is resolved.
 constexpr unsigned long long kBarrierTimeoutNs = 2000000000ull;
-__global__ void wait_flags_kernel(uint32_t* flags, int n, uint32_t value) {
+__global__ void wait_flags_kernel(uint32_t* flags, int n) {
+  __shared__ uint32_t value;
+  if (threadIdx.x == 0) value = ++flags[kFlagWaitSeq];
+  __syncthreads();
   const int r = threadIdx.x;
   if (r >= n) return;
   unsigned long long t0;
@@ -266,13 +275,13 @@ void launch_push_to_peers(const uint8_t* src, size_t byte_off, size_t bytes, uin
   push_to_peers_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), byte_off, n16, multicast, peers, n_peers, my_rank);
 }
 
-void launch_signal_flags(uint32_t* const* flag_arrays, int n, int my_rank, uint32_t value, cudaStream_t stream) {
+void launch_signal_flags(uint32_t* const* flag_arrays, int n, int my_rank, cudaStream_t stream) {
   FlagPtrs f;
   for (int r = 0; r < kMaxRanks; r++) f.p[r] = r < n ? flag_arrays[r] : nullptr;
-  signal_flags_kernel<<<1, 32, 0, stream>>>(f, n, my_rank, value);
+  signal_flags_kernel<<<1, 32, 0, stream>>>(f, n, my_rank);
 }
-void launch_wait_flags(uint32_t* my_flags, int n, uint32_t value, cudaStream_t stream) {
-  wait_flags_kernel<<<1, 32, 0, stream>>>(my_flags, n, value);
+void launch_wait_flags(uint32_t* my_flags, int n, cudaStream_t stream) {
+  wait_flags_kernel<<<1, 32, 0, stream>>>(my_flags, n);
 }
 
 void launch_mip_down(const uint8_t* src, int src_size, uint8_t* dst, int dst_size, int sx, int sy, int sw, int sh, int dx,

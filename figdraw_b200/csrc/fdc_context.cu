@@ -278,7 +278,10 @@ struct fdc_ctx {
   std::vector<uint8_t*> h_peers;   // host copy of the peer framebuffer pointers (own entry = own framebuffer)
   size_t flag_off = 0;             // byte offset of the cross-rank flag array inside a reserved framebuffer (0: none)
   uint32_t frame_barrier_base = 0; // barrier_seq at the start of the frame in flight
-  uint32_t barrier_seq = 0;        // cross-rank barrier values handed out so far (every rank runs the same sequence)
+  uint32_t barrier_seq = 0;        // cross-rank barriers issued so far (the values themselves are counted on the device)
+  // fdc_replay_frame: the resident frame's launches captured once into a CUDA graph, then one cudaGraphLaunch per replay
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_enabled = true, capturing = false;
   DevBuf<unsigned long long> d_stats;
   bool want_stats = false;
   int n_peers = 0;
@@ -648,8 +651,11 @@ cudaEvent_t next_event(fdc_ctx* ctx, int* index) {
 struct Timed {
   fdc_ctx* ctx;
   int a, kind;
-  Timed(fdc_ctx* c, int k) : ctx(c), kind(k) { cudaEventRecord(next_event(c, &a), c->stream); }
+  Timed(fdc_ctx* c, int k) : ctx(c), a(-1), kind(k) {
+    if (!c->capturing) cudaEventRecord(next_event(c, &a), c->stream);  // (events inside a captured graph cannot be timed)
+  }
   ~Timed() {
+    if (a < 0) return;
     int b;
     cudaEventRecord(next_event(ctx, &b), ctx->stream);
     ctx->spans.push_back({a, b, kind});
@@ -720,10 +726,12 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
   const uint32_t n_draws = ctx->n_draws;
   int rc = sync_table(ctx);
   if (rc) return rc;
-  ctx->ev_used = 0;
-  ctx->spans.clear();
+  if (!ctx->capturing) {
+    ctx->ev_used = 0;
+    ctx->spans.clear();
+    cudaEventRecord(ctx->ev_begin, st);
+  }
   int launches = 0;
-  cudaEventRecord(ctx->ev_begin, st);
   if (upload) {
     CK(ctx->d_draws.reserve_keep(std::max<uint32_t>(n_draws, 1), n_draws, st));
     CK(ctx->d_runs.reserve(std::max<size_t>(ctx->runs.n, 1)));
@@ -803,9 +811,9 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
       launch_push_to_peers(ctx->fb() + off, off, (size_t)x.count * sizeof(fdc_rect64), ctx->mc_fb, ctx->d_peers.p, ctx->n_peers, ctx->rank, st);
       launches++;
     }
-    const uint32_t v = ++ctx->barrier_seq;
-    launch_signal_flags(flag_ptrs, ctx->n_ranks, ctx->rank, v, st);
-    launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, v, st);
+    ctx->barrier_seq++;
+    launch_signal_flags(flag_ptrs, ctx->n_ranks, ctx->rank, st);
+    launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, st);
     launches += 2;
   }
   uint32_t pending_wait = 0;  // "neighbours finished reading my halo rows" value to wait for before the next shade
@@ -844,7 +852,7 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
       sa.n_peers = (last && ctx->n_peers > 0 && !sa.multicast) ? ctx->n_peers : 0;
       sa.fence_at_exit = (sa.n_peers > 0 || sa.multicast) && !end_barrier;
       if (pending_wait) {
-        launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, pending_wait, st);
+        launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, st);
         pending_wait = 0;
         launches++;
       }
@@ -896,10 +904,10 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
         // Halo exchange over peer memory: (1) everyone has finished shading this segment, (2) the H pass reads the rows
         // it needs straight out of the owners' framebuffers, (3) tell everyone the halo has been read so the next
         // segment may overwrite those rows.  Every rank runs the same barrier sequence, with or without work.
-        const uint32_t v_shaded = ++ctx->barrier_seq;
-        v_done = ++ctx->barrier_seq;
-        launch_signal_flags(flag_ptrs, ctx->n_ranks, ctx->rank, v_shaded, st);
-        launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, v_shaded, st);
+        ctx->barrier_seq += 2;
+        v_done = 1;
+        launch_signal_flags(flag_ptrs, ctx->n_ranks, ctx->rank, st);
+        launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, st);
         launches += 2;
         by0 = std::max(by0, ctx->frame.band_y0);
         by1 = std::min(by1, ctx->frame.band_y1);
@@ -917,24 +925,24 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
       launch_backdrop_blur(ba, st, &launches);
       if (banded_blur) {
         // (the H pass is the only reader of remote rows and precedes this signal in stream order)
-        launch_signal_flags(flag_ptrs, ctx->n_ranks, ctx->rank, v_done, st);
+        launch_signal_flags(flag_ptrs, ctx->n_ranks, ctx->rank, st);
         launches++;
         pending_wait = v_done;
       }
     }
   }
   if (pending_wait) {  // do not let the next frame's shade overwrite rows a neighbour may still be reading
-    launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, pending_wait, st);
+    launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, st);
     launches++;
   }
   if (end_barrier) {
     // Fused gather: once every rank has passed this barrier, every rank's framebuffer holds the whole frame.
-    const uint32_t v = ++ctx->barrier_seq;
-    launch_signal_flags(flag_ptrs, ctx->n_ranks, ctx->rank, v, st);
-    launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, v, st);
+    ctx->barrier_seq++;
+    launch_signal_flags(flag_ptrs, ctx->n_ranks, ctx->rank, st);
+    launch_wait_flags(flag_ptrs[ctx->rank], ctx->n_ranks, st);
     launches += 2;
   }
-  cudaEventRecord(ctx->ev_end, st);
+  if (!ctx->capturing) cudaEventRecord(ctx->ev_end, st);
   CK(cudaGetLastError());
   ctx->stats.n_prims = n_draws;
   ctx->stats.n_segments = (uint32_t)ctx->segments.size();
@@ -945,6 +953,11 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
   ctx->stats.n_launches = launches;
   ctx->have_frame = true;
   return FDC_OK;
+}
+
+void drop_graph(fdc_ctx* ctx) {
+  if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+  ctx->graph_exec = nullptr;
 }
 
 // After a frame: wait, and if a bin list overflowed in any segment grow the lists and re-run the frame.  Under a
@@ -975,6 +988,7 @@ int resolve_frame(fdc_ctx* ctx) {
     }
     // overflow in some segment: kCntMaxCoarse / kCntMaxTile hold the largest coarse / tile list any segment needs
     if (attempt == 4) break;
+    drop_graph(ctx);  // the lists are about to move
     ctx->dbg_coarse_limit = ctx->dbg_tile_limit = 0;
     if (c[kCntStickyOverflow] & 1u) CK(ctx->d_coarse_list.reserve((size_t)c[kCntMaxCoarse] + (c[kCntMaxCoarse] >> 2) + 1024));
     if (c[kCntStickyOverflow] & 2u) CK(ctx->d_tile_list.reserve((size_t)c[kCntMaxTile] + (c[kCntMaxTile] >> 2) + 1024));
@@ -1096,6 +1110,7 @@ void fdc_destroy(fdc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  drop_graph(ctx);
   release_export(ctx);
   for (int l = 0; l < ctx->n_levels; l++) cudaFree(ctx->levels[l]);
   ctx->d_table.release();
@@ -1128,6 +1143,7 @@ int fdc_begin_frame(fdc_ctx* ctx, int width, int height, int clear_main, const f
   int rc = sync_frame(ctx);  // previous frame (and its read-back) must be complete before its recording is dropped
   if (rc) return rc;
   ctx->have_frame = false;
+  drop_graph(ctx);
   if (ctx->ext_fb == nullptr && (width != ctx->W || height != ctx->H)) {
     // new size: the internal framebuffer starts black/transparent like a fresh GL back buffer
     CK(ctx->d_fb.reserve((size_t)width * height * 4));
@@ -1170,11 +1186,59 @@ int fdc_end_frame(fdc_ctx* ctx) {
   return execute_frame(ctx, true);
 }
 
+// Replays the resident frame.  The first replay of a frame captures its launches (memsets, setup, binning, shade,
+// blur, cross-rank barriers) into a CUDA graph; later replays are ONE cudaGraphLaunch -- no per-kernel launch latency,
+// which is most of a small frame (cfg1: 8 primitives).  Anything that changes what the launches look like (a new
+// recording, regrown lists, another framebuffer) drops the graph.
 int fdc_replay_frame(fdc_ctx* ctx) {
   if (!ctx) return FDC_ERR_INVALID;
   if (!ctx->have_frame || ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "no completed frame to replay");
   CK(cudaSetDevice(ctx->device));
-  return execute_frame(ctx, false);
+  const bool side_streams = ctx->n_peers > 0 && ctx->gather_mode == FDC_GATHER_COPY;
+  if (!ctx->graph_enabled || ctx->want_stats || side_streams) return execute_frame(ctx, false);
+  int rc = FDC_OK;
+  if (ctx->table_dirty) drop_graph(ctx);  // atlas entries (or the atlas itself) changed since the capture
+  if (!ctx->graph_exec) {
+    rc = resolve_frame(ctx);  // capture against lists known to be large enough (an overflow regrows them and drops the graph)
+    if (rc) return rc;
+    rc = sync_table(ctx);
+    if (rc) return rc;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    ctx->capturing = true;
+    rc = execute_frame(ctx, false);
+    ctx->capturing = false;
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc != FDC_OK || e != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (rc != FDC_OK) return rc;
+      return execute_frame(ctx, false);  // capture refused (e.g. an allocation happened): plain launches
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) {
+      ctx->graph_exec = nullptr;
+      cudaGetLastError();
+      return execute_frame(ctx, false);
+    }
+  }
+  ctx->ev_used = 0;
+  ctx->spans.clear();  // per-phase times are not available from inside a graph; gpu_ms is
+  CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
+  CK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+  CK(cudaEventRecord(ctx->ev_end, ctx->stream));
+  ctx->frame_resolved = false;
+  return FDC_OK;
+}
+
+// Graph replay on / off (default on).  Off: fdc_replay_frame re-issues the launches one by one, which also times the
+// phases (bin_ms / shade_ms / blur_ms of fdc_get_frame_stats).
+int fdc_set_replay_graph(fdc_ctx* ctx, int enabled) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->graph_enabled = enabled != 0;
+  if (!enabled) drop_graph(ctx);
+  return FDC_OK;
 }
 
 // Re-runs the last frame on every rank of a tile-band partition after any rank's fdc_sync / fdc_read_pixels returned
@@ -1211,6 +1275,7 @@ int fdc_abort_frame(fdc_ctx* ctx) {
 
 int fdc_debug_limit_lists(fdc_ctx* ctx, uint32_t coarse_entries, uint32_t tile_entries) {
   if (!ctx) return FDC_ERR_INVALID;
+  drop_graph(ctx);
   ctx->dbg_coarse_limit = coarse_entries;
   ctx->dbg_tile_limit = tile_entries;
   return FDC_OK;
@@ -1775,6 +1840,7 @@ int fdc_bind_framebuffer(fdc_ctx* ctx, void* device_rgba8) {
   if (ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "cannot rebind the framebuffer inside a frame");
   int rc = resolve_frame(ctx);
   if (rc) return rc;
+  drop_graph(ctx);
   if (ctx->ext_fb && ctx->frame_barrier) {  // leaving a shared framebuffer: forget its flags, peers and exchange area
     ctx->mc_fb = nullptr;
     ctx->frame_barrier = false;
@@ -1798,6 +1864,7 @@ int fdc_set_peer_framebuffers(fdc_ctx* ctx, void* const* device_ptrs, int n) {
   CK(cudaSetDevice(ctx->device));
   int rc = resolve_frame(ctx);
   if (rc) return rc;
+  drop_graph(ctx);
   ctx->n_peers = n;
   ctx->h_peers.assign(n, nullptr);
   if (n) {
@@ -1830,6 +1897,7 @@ int fdc_export_framebuffer(fdc_ctx* ctx, int width, int rows, int* out_fd, size_
   CK(cudaSetDevice(ctx->device));
   int rc = resolve_frame(ctx);
   if (rc) return rc;
+  drop_graph(ctx);
   CUresult (*get_gran)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
   CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
   CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
@@ -1890,6 +1958,7 @@ int fdc_bind_shared_framebuffer(fdc_ctx* ctx, void* local_ptr, size_t bytes, voi
   CK(cudaSetDevice(ctx->device));
   int rc = resolve_frame(ctx);
   if (rc) return rc;
+  drop_graph(ctx);
   const size_t pix = (((size_t)width * rows * 4) + 255) & ~(size_t)255;
   if (bytes < pix + 4096) return ctx->fail(FDC_ERR_INVALID, "shared framebuffer needs %zu bytes (pixels + 4096 bytes of flags), got %zu", pix + 4096, bytes);
   if (n > kMaxRanks) return ctx->fail(FDC_ERR_CAPACITY, "at most %d ranks", kMaxRanks);
@@ -1920,6 +1989,7 @@ int fdc_set_frame_barrier(fdc_ctx* ctx, int enabled) {
   if (!ctx) return FDC_ERR_INVALID;
   int rc = resolve_frame(ctx);
   if (rc) return rc;
+  drop_graph(ctx);
   ctx->frame_barrier = enabled != 0;
   return FDC_OK;
 }
@@ -1928,6 +1998,7 @@ int fdc_set_peer_gather(fdc_ctx* ctx, int mode, int sub_bands) {
   if (!ctx || (mode != FDC_GATHER_STORES && mode != FDC_GATHER_COPY)) return FDC_ERR_INVALID;
   int rc = resolve_frame(ctx);
   if (rc) return rc;
+  drop_graph(ctx);
   ctx->gather_mode = mode;
   if (sub_bands > 0) ctx->gather_sub_bands = sub_bands;
   return FDC_OK;
@@ -1939,6 +2010,7 @@ int fdc_reserve_framebuffer(fdc_ctx* ctx, int width, int rows) {
   CK(cudaSetDevice(ctx->device));
   int rc = resolve_frame(ctx);
   if (rc) return rc;
+  drop_graph(ctx);
   // pixels, then (256-byte aligned) a small array of cross-rank flags that peers write for the blur halo barrier
   const size_t pix = (((size_t)width * rows * 4) + 255) & ~(size_t)255;
   const size_t bytes = pix + 4096;
@@ -1983,10 +2055,12 @@ int fdc_get_frame_stats(fdc_ctx* ctx, fdc_frame_stats* out) {
   if (ctx->have_frame) {
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) ctx->stats.gpu_ms = ms;
-    float acc[3] = {0, 0, 0};
-    for (auto& sp : ctx->spans)
-      if (cudaEventElapsedTime(&ms, ctx->ev_pool[sp.a], ctx->ev_pool[sp.b]) == cudaSuccess) acc[sp.kind] += ms;
-    ctx->stats.bin_ms = acc[0]; ctx->stats.shade_ms = acc[1]; ctx->stats.blur_ms = acc[2];
+    if (!ctx->spans.empty()) {  // (a graph replay has no per-phase events: the last launch-by-launch values stay)
+      float acc[3] = {0, 0, 0};
+      for (auto& sp : ctx->spans)
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[sp.a], ctx->ev_pool[sp.b]) == cudaSuccess) acc[sp.kind] += ms;
+      ctx->stats.bin_ms = acc[0]; ctx->stats.shade_ms = acc[1]; ctx->stats.blur_ms = acc[2];
+    }
   }
   *out = ctx->stats;
   return FDC_OK;

@@ -62,6 +62,7 @@ void launch_shade(const ShadeArgs& a, cudaStream_t stream);
 
 constexpr int kMaxRanks = 16;
 constexpr int kFlagError = 32;  // word of a rank's flag array that records barrier time-outs (bit r: rank r never arrived)
+constexpr int kFlagSignalSeq = 40, kFlagWaitSeq = 41;  // this rank's running signal / wait numbers (local use only)
 struct BlurArgs {
   const uint8_t* src;  // framebuffer
   // Tile-band partition: rows [r*band_px, (r+1)*band_px) of the frame live in src_rank[r] (this rank's own framebuffer or
@@ -75,10 +76,11 @@ struct BlurArgs {
   float radius;        // blurRadius as passed to drawBackdropBlur
 };
 void launch_backdrop_blur(const BlurArgs& a, cudaStream_t stream, int* n_launches);
-// Cross-rank stream-ordered barrier over peer memory: store `value` into slot `my_rank` of every rank's flag array,
-// then (wait) spin until all `n` slots of the local array have reached `value`.
-void launch_signal_flags(uint32_t* const* flag_arrays, int n, int my_rank, uint32_t value, cudaStream_t stream);
-void launch_wait_flags(uint32_t* my_flags, int n, uint32_t value, cudaStream_t stream);
+// Cross-rank stream-ordered barrier over peer memory: store this rank's next signal number into slot `my_rank` of every
+// rank's flag array; (wait) spin until all `n` slots of the local array have reached this rank's next wait number.
+// Signals and waits pair up in issue order; every rank issues the same sequence.
+void launch_signal_flags(uint32_t* const* flag_arrays, int n, int my_rank, cudaStream_t stream);
+void launch_wait_flags(uint32_t* my_flags, int n, cudaStream_t stream);
 
 // Copies `bytes` (a multiple of 16) at `src` (= own copy + byte_off) to the same offset of every rank's copy of a shared
 // buffer: one multimem.st per 16 bytes through the multicast mapping, or one store per peer.

@@ -91,6 +91,10 @@ class CudaContext(BackendContext):
     def replayFrame(self):
         self._ck(self._lib.fdc_replay_frame(self._h))
 
+    def setReplayGraph(self, enabled: bool):
+        """replayFrame as one CUDA-graph launch (default) or launch by launch (which also times the phases)."""
+        self._ck(self._lib.fdc_set_replay_graph(self._h, 1 if enabled else 0))
+
     def sync(self):
         self._ck(self._lib.fdc_sync(self._h))
 

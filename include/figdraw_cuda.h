@@ -155,9 +155,12 @@ int fdc_read_pixels(fdc_ctx* ctx, int x, int y, int w, int h, uint8_t* out_rgba)
 int fdc_read_pixels_async(fdc_ctx* ctx, int x, int y, int w, int h, uint8_t* out_rgba);
 /* Blocks until all submitted frames are complete. */
 int fdc_sync(fdc_ctx* ctx);
-/* Re-launches the kernels of the last completed frame on the data already resident in device memory (no
- * host->device copy).  Used to time the device path alone and by CUDA-graph style frame loops. */
+/* Re-runs the last completed frame on the data already resident in device memory (no host->device copy).  The first
+ * replay captures the frame's launches into a CUDA graph, later ones are a single cudaGraphLaunch;
+ * fdc_set_replay_graph(ctx, 0) re-issues the launches one by one instead, which also times the phases for
+ * fdc_get_frame_stats (bin_ms / shade_ms / blur_ms are not available from inside a graph, gpu_ms is). */
 int fdc_replay_frame(fdc_ctx* ctx);
+int fdc_set_replay_graph(fdc_ctx* ctx, int enabled);
 /* Tile-band partitions: re-run the last frame after any rank reported FDC_ERR_RETRY (call on every rank, then gather
  * again).  Restores pixels a first attempt already blended (frames without clear_main) before re-running. */
 int fdc_retry_frame(fdc_ctx* ctx);

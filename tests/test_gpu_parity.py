@@ -179,6 +179,42 @@ def test_replay_and_rerender_are_idempotent():
     ctx.close()
 
 
+def test_graph_replay_equals_plain_replay():
+    """fdc_replay_frame as ONE CUDA-graph launch (default) == the launches issued one by one, for frames with blurs,
+    masks and several segments; a new recording, regrown lists or a rebound framebuffer drop the graph."""
+    for tr in (ss.config_trace(2, 1280, 720), ss.config_trace(4, 1280, 720, rows=30, cols=6), scenes.golden_trace("layers_clip"),
+               ss.config_trace(5, 1280, 720, n_rects=3000, n_glyphs=500)):
+        ctx = CudaContext(atlasSize=tr.atlas_size)
+        want = render_trace(tr, ctx).copy()
+        ctx.setReplayGraph(False)
+        ctx.replayFrame()
+        assert np.array_equal(ctx.readPixels(), want)
+        ctx.setReplayGraph(True)
+        for _ in range(3):  # first one captures, the others launch the graph
+            ctx.replayFrame()
+            assert np.array_equal(ctx.readPixels(), want)
+        assert ctx.frameStats().gpu_ms > 0.0
+        # a different recording on the same context drops the graph; then the first one again
+        k = len(tr.calls) // 2
+        while tr.calls[k]["op"] < 32 and k + 1 < len(tr.calls):
+            k += 1
+        if not (tr.calls["op"][:k] == Op.BEGIN_MASK).any() and not (tr.calls["op"][:k] == Op.SAVE_TRANSFORM).any():
+            ctx.beginFrame((tr.width, tr.height), clearMain=True)
+            ctx.submitCalls(tr.calls[:k])
+            ctx.endFrame()
+            half = ctx.readPixels().copy()
+            ctx.replayFrame()
+            ctx.replayFrame()
+            assert np.array_equal(ctx.readPixels(), half)
+        assert np.array_equal(render_trace(tr, ctx), want)
+        ctx.debugLimitLists(0, 64)  # the replay overflows, regrows and re-captures
+        ctx.replayFrame()
+        assert np.array_equal(ctx.readPixels(), want)
+        ctx.replayFrame()
+        assert np.array_equal(ctx.readPixels(), want)
+        ctx.close()
+
+
 def test_split_frame_equals_single_frame():
     """Per-draw UNORM8 quantisation makes the frame splittable at any draw: second half with clearMain=false."""
     tr = ss.config_trace(5, 1280, 720, n_rects=4000, n_glyphs=0)

@@ -29,19 +29,25 @@ for name, build in cases:
     tr = build()
     ctx = CudaContext(atlasSize=tr.atlas_size)
     got = render_trace(tr, ctx)
-    times = []
+    times, graph_ms = [], []
+    ctx.setReplayGraph(False)  # launch by launch: per-phase times
     for _ in range(int(os.environ.get("FDC_REPLAYS", "12"))):
         ctx.replayFrame()
         st = ctx.frameStats()
         times.append((st.gpu_ms, st.bin_ms, st.shade_ms, st.blur_ms))
+    ctx.setReplayGraph(True)   # one CUDA-graph launch per frame
+    for _ in range(int(os.environ.get("FDC_REPLAYS", "12")) + 1):
+        ctx.replayFrame()
+        graph_ms.append(ctx.frameStats().gpu_ms)
     t = np.median(np.array(times), axis=0)
+    g = float(np.median(np.array(graph_ms[1:])))
     t0 = time.time()
     want = got if os.environ.get("FDC_SKIP_ORACLE") else oracle.render_trace(tr)
     cpu_s = time.time() - t0
     d = np.abs(got.astype(np.int16) - want.astype(np.int16)).max(axis=2)
     mpx = tr.width * tr.height / 1e6
     row = {"config": name, "draws": tr.n_draws, "segments": int(st.n_segments), "launches": int(st.n_launches),
-           "gpu_ms": round(float(t[0]), 4), "bin_ms": round(float(t[1]), 4), "shade_ms": round(float(t[2]), 4),
+           "gpu_ms": round(float(t[0]), 4), "graph_ms": round(g, 4), "bin_ms": round(float(t[1]), 4), "shade_ms": round(float(t[2]), 4),
            "blur_ms": round(float(t[3]), 4), "mpix_per_s": round(mpx / (t[0] * 1e-3), 1), "fps": round(1e3 / t[0], 1),
            "cpu_oracle_s": round(cpu_s, 3), "cpu_threads": oracle.max_threads(), "max_diff_lsb": int(d.max()),
            "pixels_differing": int((d > 0).sum())}

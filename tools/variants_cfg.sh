@@ -7,5 +7,5 @@ for v in "$@"; do
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d = json.loads(l); print('  %-44s gpu %.4f shade %.4f bin %.4f' % (d['config'], d['gpu_ms'], d['shade_ms'], d['bin_ms']))"
+        d = json.loads(l); print('  %-44s gpu %.4f graph %.4f shade %.4f bin %.4f' % (d['config'], d['gpu_ms'], d.get('graph_ms', 0), d['shade_ms'], d['bin_ms']))"
 done

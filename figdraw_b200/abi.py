@@ -164,6 +164,15 @@ class FdcFrameStats(ctypes.Structure):
     ]
 
 
+class FdcAtlasUsage(ctypes.Structure):
+    """AtlasUsage, figbackend.nim:76-89."""
+
+    _fields_ = [("atlas_size", ctypes.c_int32), ("entry_count", ctypes.c_int32), ("image_count", ctypes.c_int32),
+                ("glyph_count", ctypes.c_int32), ("generated_count", ctypes.c_int32), ("unknown_count", ctypes.c_int32),
+                ("atlas_area", ctypes.c_int64), ("used_area", ctypes.c_int64), ("packed_area", ctypes.c_int64),
+                ("generation", ctypes.c_uint64), ("rebuild_count", ctypes.c_uint64)]
+
+
 # Every symbol include/figdraw_cuda.h declares (checked by tests/test_abi.py against the header text).
 EXPORTS = [
     "fdc_create", "fdc_destroy", "fdc_last_error", "fdc_abi_version",
@@ -172,13 +181,15 @@ EXPORTS = [
     "fdc_translate", "fdc_rotate", "fdc_scale", "fdc_apply_transform", "fdc_save_transform",
     "fdc_restore_transform", "fdc_transform_mirrors_y", "fdc_get_transform",
     "fdc_sdf_aa_factor", "fdc_set_sdf_aa_factor", "fdc_set_text_subpixel_positioning_enabled",
-    "fdc_set_text_subpixel_shift", "fdc_pixel_scale",
+    "fdc_set_text_subpixel_shift", "fdc_pixel_scale", "fdc_set_pixelate",
     "fdc_draw_rounded_rect_sdf", "fdc_draw_image", "fdc_draw_msdf_image", "fdc_draw_quadratic_bezier_sdf",
     "fdc_draw_filled_quad", "fdc_draw_rect", "fdc_draw_backdrop_blur",
     "fdc_begin_mask", "fdc_end_mask", "fdc_pop_mask", "fdc_begin_rect_mask", "fdc_pop_rect_mask",
     "fdc_submit_calls", "fdc_submit_draws", "fdc_pack_rect64", "fdc_expand_rect64", "fdc_submit_rects64",
     "fdc_put_image", "fdc_update_image", "fdc_has_image", "fdc_get_image_rect", "fdc_remove_image",
     "fdc_reset_image_atlas", "fdc_atlas_size", "fdc_atlas_packed_area",
+    "fdc_mark_entry", "fdc_clear_font_glyphs", "fdc_clear_typeface_glyphs", "fdc_retain_owner", "fdc_release_owner",
+    "fdc_get_atlas_usage", "fdc_set_atlas_replay",
     "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers", "fdc_bind_shared_framebuffer", "fdc_set_frame_barrier", "fdc_export_framebuffer", "fdc_set_peer_gather", "fdc_reserve_framebuffer", "fdc_framebuffer_ipc_handle", "fdc_open_peer_framebuffer",
     "fdc_get_frame_stats", "fdc_debug_bins", "fdc_debug_shade_stats",
     "fdc_flatten_renders", "fdc_render_frame",
@@ -239,6 +250,7 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_set_text_subpixel_positioning_enabled", c.c_int, P, c.c_int)
     sig("fdc_set_text_subpixel_shift", c.c_int, P, c.c_float)
     sig("fdc_pixel_scale", c.c_float, P)
+    sig("fdc_set_pixelate", c.c_int, P, c.c_int)
     sig("fdc_draw_rounded_rect_sdf", c.c_int, P, fp, c.POINTER(FdcFill), fp, fp, c.c_int, c.c_float, c.c_float, fp)
     sig("fdc_draw_image", c.c_int, P, c.c_uint64, fp, u32p, fp, c.c_int)
     sig("fdc_draw_msdf_image", c.c_int, P, c.c_uint64, fp, c.c_uint32, fp, c.c_float, c.c_float, c.c_float,
@@ -262,6 +274,13 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_reset_image_atlas", c.c_int, P, c.c_int)
     sig("fdc_atlas_size", c.c_int, P)
     sig("fdc_atlas_packed_area", c.c_int, P)
+    sig("fdc_mark_entry", c.c_int, P, c.c_uint64, c.c_int, c.c_uint64, c.c_uint64)
+    sig("fdc_clear_font_glyphs", c.c_int, P, c.c_uint64)
+    sig("fdc_clear_typeface_glyphs", c.c_int, P, c.c_uint64)
+    sig("fdc_retain_owner", c.c_int, P, c.c_int, c.c_uint64, c.c_uint64)
+    sig("fdc_release_owner", c.c_int, P, c.c_int, c.c_uint64, c.c_uint64, c.POINTER(c.c_int))
+    sig("fdc_get_atlas_usage", c.c_int, P, c.POINTER(FdcAtlasUsage))
+    sig("fdc_set_atlas_replay", c.c_int, P, c.c_int)
     sig("fdc_bind_framebuffer", c.c_int, P, P)
     sig("fdc_framebuffer_ptr", P, P)
     sig("fdc_band_rows", c.c_int, P, c.POINTER(c.c_int), c.POINTER(c.c_int))

@@ -197,6 +197,7 @@ struct fdc_ctx {
   cudaStream_t stream = nullptr;
   std::string error;
   float pixel_scale = 1.0f;
+  bool pixelate = false;  // `newContext(pixelate = true)`: the atlas magnifies with GL_NEAREST
   int rank = 0, n_ranks = 1;
 
   // ---- atlas
@@ -205,6 +206,14 @@ struct fdc_ctx {
   std::vector<uint16_t> heights;
   struct Rect4 { float x, y, w, h; };
   std::unordered_map<uint64_t, Rect4> entries;
+  // What the reference keeps beside `entries` (figbackend.nim:61-75 AtlasEntryMeta, :185-187 owner sets), for hosts that
+  // let the library do the bookkeeping: texel rect + insertion order (re-packing on regrow), entry kind and ids
+  // (clearFontGlyphs / clearTypefaceGlyphs), owner tokens (eviction when the last owner lets go).
+  struct EntryInfo { int px = 0, py = 0, w = 0, h = 0; uint64_t order = 0; int kind = 0; uint64_t a = 0, b = 0; };
+  std::unordered_map<uint64_t, EntryInfo> entry_info;
+  std::unordered_map<uint64_t, std::vector<uint64_t>> image_owners, font_owners;
+  uint64_t put_counter = 0, atlas_generation = 1, atlas_rebuilds = 0;
+  bool atlas_replay = false;  // on regrow re-pack the live entries natively instead of dropping them
   // fdc_render_frame: two page-locked record buffers used alternately -- frame k+1 is flattened into one while the
   // asynchronous upload of frame k may still be reading the other (fdc_begin_frame(k+1) then waits for frame k)
   PinnedBuf<fdc_call> flat[2];
@@ -322,10 +331,12 @@ struct fdc_ctx {
 
 namespace {
 
-int atlas_alloc(fdc_ctx* ctx, int size) {
-  for (int l = 0; l < ctx->n_levels; l++) {
-    cudaFree(ctx->levels[l]);
-    ctx->levels[l] = nullptr;
+int atlas_alloc(fdc_ctx* ctx, int size, bool free_old = true) {
+  if (free_old) {
+    for (int l = 0; l < ctx->n_levels; l++) {
+      cudaFree(ctx->levels[l]);
+      ctx->levels[l] = nullptr;
+    }
   }
   ctx->n_levels = 0;
   ctx->atlas_size = size;
@@ -337,6 +348,81 @@ int atlas_alloc(fdc_ctx* ctx, int size) {
   }
   ctx->heights.assign((size_t)size, 0);
   ctx->entries.clear();
+  ctx->table_dirty = true;
+  return FDC_OK;
+}
+
+int find_empty_rect(fdc_ctx* ctx, int width, int height, int* rx, int* ry, bool* grew);
+int build_mips(fdc_ctx* ctx, int x, int y, int w, int h);
+
+// grow (glcontext.nim:536-539) = resetImageAtlas at twice the size.  The reference drops every entry and relies on the
+// host to replay its images (noteAtlasRebuilt -> replayImageMessages, figbackend.nim:202-207); with atlas_replay the
+// library does it: the live entries are packed into the new atlas in their original insertion order and their texels
+// copied device-to-device out of the old one (removed entries are not carried over, which is what reclaims their space).
+int atlas_grow(fdc_ctx* ctx) {
+  ctx->atlas_generation++;
+  ctx->atlas_rebuilds++;
+  if (!ctx->atlas_replay) {
+    ctx->entry_info.clear();
+    return atlas_alloc(ctx, ctx->atlas_size * 2);
+  }
+  uint8_t* old_levels[kMaxAtlasLevels];
+  const int old_n = ctx->n_levels, old_size = ctx->atlas_size;
+  for (int l = 0; l < old_n; l++) old_levels[l] = ctx->levels[l];
+  std::vector<std::pair<uint64_t, uint64_t>> live;  // (insertion order, key)
+  for (auto& kv : ctx->entries) {
+    auto it = ctx->entry_info.find(kv.first);
+    if (it != ctx->entry_info.end()) live.push_back({it->second.order, kv.first});
+  }
+  std::sort(live.begin(), live.end());
+  int size = old_size;
+  for (;;) {  // a size at which everything fits again
+    size *= 2;
+    if (size > 16384) return ctx->fail(FDC_ERR_CAPACITY, "atlas cannot grow beyond 16384");
+    int rc = atlas_alloc(ctx, size, false);
+    if (rc) return rc;
+    bool ok = true;
+    for (auto& ok_key : live) {
+      fdc_ctx::EntryInfo& e = ctx->entry_info[ok_key.second];
+      int rx = 0, ry = 0;
+      bool grew = false;
+      // find_empty_rect must not recurse into another grow here: probe the height map directly
+      const int imgW = e.w + kAtlasMargin * 2, imgH = e.h + kAtlasMargin * 2;
+      int lowest = ctx->atlas_size, at = 0;
+      for (int i = 0; i < ctx->atlas_size; i++) {
+        const int v = ctx->heights[i];
+        if (v < lowest) {
+          bool fit = true;
+          for (int j = 0; j <= imgW; j++) {
+            if (i + j >= ctx->atlas_size || (int)ctx->heights[i + j] > v) { fit = false; break; }
+          }
+          if (fit) { lowest = v; at = i; }
+        }
+      }
+      (void)grew;
+      if (lowest + imgH > ctx->atlas_size) { ok = false; break; }
+      for (int j = at; j < at + imgW; j++) ctx->heights[j] = (uint16_t)(lowest + imgH + kAtlasMargin * 2);
+      rx = at + kAtlasMargin;
+      ry = lowest + kAtlasMargin;
+      if (e.w > 1 && e.h > 1) {
+        CK(cudaMemcpy2DAsync(ctx->levels[0] + ((size_t)ry * size + rx) * 4, (size_t)size * 4,
+                             old_levels[0] + ((size_t)e.py * old_size + e.px) * 4, (size_t)old_size * 4, (size_t)e.w * 4, (size_t)e.h,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+        rc = build_mips(ctx, rx, ry, e.w, e.h);
+        if (rc) return rc;
+      }
+      e.px = rx; e.py = ry;
+      const float as = (float)size;
+      ctx->entries[ok_key.second] = {(float)rx / as, (float)ry / as, (float)e.w / as, (float)e.h / as};
+    }
+    if (ok) break;
+    for (int l = 0; l < ctx->n_levels; l++) cudaFree(ctx->levels[l]);  // still too small: try the next size
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int l = 0; l < old_n; l++) cudaFree(old_levels[l]);
+  // entry_info of keys that are no longer live goes too
+  for (auto it = ctx->entry_info.begin(); it != ctx->entry_info.end();)
+    it = ctx->entries.count(it->first) ? std::next(it) : ctx->entry_info.erase(it);
   ctx->table_dirty = true;
   return FDC_OK;
 }
@@ -359,7 +445,7 @@ int find_empty_rect(fdc_ctx* ctx, int width, int height, int* rx, int* ry, bool*
     }
     if (lowest + imgH > ctx->atlas_size) {
       if (ctx->atlas_size >= 16384) return ctx->fail(FDC_ERR_CAPACITY, "atlas cannot grow beyond 16384 for a %dx%d image", width, height);
-      int rc = atlas_alloc(ctx, ctx->atlas_size * 2);  // grow -> resetImageAtlas, glcontext.nim:536-539
+      int rc = atlas_grow(ctx);  // grow -> resetImageAtlas, glcontext.nim:536-539
       if (rc) return rc;
       *grew = true;
       continue;
@@ -371,11 +457,8 @@ int find_empty_rect(fdc_ctx* ctx, int width, int height, int* rx, int* ry, bool*
   }
 }
 
-int upload_chain(fdc_ctx* ctx, int x, int y, int w, int h, const uint8_t* rgba) {
-  // updateSubImage (textures.nim:106-119): level 0 copy, then GPU box filter per level while w>1 && h>1
-  if (!(w > 1 && h > 1)) return FDC_OK;  // the reference's loop uploads nothing for 1-pixel-wide images
-  CK(cudaMemcpy2DAsync(ctx->levels[0] + ((size_t)y * ctx->atlas_size + x) * 4, (size_t)ctx->atlas_size * 4, rgba, (size_t)w * 4,
-                       (size_t)w * 4, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
+// The mip chain of a level-0 region: GPU box filter per level while w > 1 && h > 1 (updateSubImage, textures.nim:106-119).
+int build_mips(fdc_ctx* ctx, int x, int y, int w, int h) {
   int level = 0;
   while (true) {
     int nw = w / 2, nh = h / 2;
@@ -387,6 +470,14 @@ int upload_chain(fdc_ctx* ctx, int x, int y, int w, int h, const uint8_t* rgba) 
   }
   CK(cudaGetLastError());
   return FDC_OK;
+}
+
+int upload_chain(fdc_ctx* ctx, int x, int y, int w, int h, const uint8_t* rgba) {
+  // updateSubImage (textures.nim:106-119): level 0 copy, then the mip chain
+  if (!(w > 1 && h > 1)) return FDC_OK;  // the reference's loop uploads nothing for 1-pixel-wide images
+  CK(cudaMemcpy2DAsync(ctx->levels[0] + ((size_t)y * ctx->atlas_size + x) * 4, (size_t)ctx->atlas_size * 4, rgba, (size_t)w * 4,
+                       (size_t)w * 4, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
+  return build_mips(ctx, x, y, w, h);
 }
 
 int sync_table(fdc_ctx* ctx) {
@@ -418,6 +509,7 @@ AtlasView atlas_view(fdc_ctx* ctx) {
   v.table_mask = ctx->table_cap ? ctx->table_cap - 1 : 0;
   v.size = ctx->atlas_size;
   v.n_levels = ctx->n_levels;
+  v.pixelate = ctx->pixelate ? 1 : 0;
   return v;
 }
 
@@ -430,6 +522,11 @@ int put_image_impl(fdc_ctx* ctx, uint64_t key, int w, int h, const uint8_t* rgba
   const float as = (float)ctx->atlas_size;
   fdc_ctx::Rect4 r = {(float)rx / as, (float)ry / as, (float)w / as, (float)h / as};
   ctx->entries[key] = r;
+  {
+    fdc_ctx::EntryInfo& e = ctx->entry_info[key];  // kind and ids survive a re-put (replaceImageInAtlas keeps the meta)
+    e.px = rx; e.py = ry; e.w = w; e.h = h;
+    e.order = ++ctx->put_counter;
+  }
   ctx->table_dirty = true;
   if (out_rect) { out_rect[0] = r.x; out_rect[1] = r.y; out_rect[2] = r.w; out_rect[3] = r.h; }
   if (out_rebuilt) *out_rebuilt = grew ? 1 : 0;
@@ -1424,6 +1521,15 @@ int fdc_set_text_subpixel_shift(fdc_ctx* ctx, float shift) {
   return FDC_OK;
 }
 float fdc_pixel_scale(fdc_ctx* ctx) { return ctx ? ctx->pixel_scale : 1.0f; }
+// `pixelate` of newContext (glcontext.nim:255-282): the atlas texture's magnification filter becomes GL_NEAREST
+// (:165-168); minified sampling stays trilinear.  (Mask and backdrop textures are only ever sampled at texel centres.)
+int fdc_set_pixelate(fdc_ctx* ctx, int enabled) {
+  if (!ctx) return FDC_ERR_INVALID;
+  if (ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "cannot change the atlas filter inside a frame");
+  ctx->pixelate = enabled != 0;
+  drop_graph(ctx);
+  return FDC_OK;
+}
 
 // ------------------------------------------------------------------------------------------------- draws
 static void put_fill(fdc_call& c, const fdc_fill* fill) {
@@ -1815,6 +1921,7 @@ int fdc_get_image_rect(fdc_ctx* ctx, uint64_t key, float out_rect[4]) {
 int fdc_remove_image(fdc_ctx* ctx, uint64_t key) {
   if (!ctx) return FDC_ERR_INVALID;
   if (ctx->entries.erase(key)) ctx->table_dirty = true;  // entries.del(key): the texels stay, as in GL
+  ctx->entry_info.erase(key);
   return FDC_OK;
 }
 int fdc_reset_image_atlas(fdc_ctx* ctx, int minimum_size) {
@@ -1824,7 +1931,92 @@ int fdc_reset_image_atlas(fdc_ctx* ctx, int minimum_size) {
   int size = std::max(ctx->initial_atlas_size, 1);  // plannedAtlasSize figbackend.nim:223-227
   const int minimum = std::max(minimum_size, size);
   while (size < minimum) size *= 2;
+  ctx->entry_info.clear();
+  ctx->atlas_generation++;
+  ctx->atlas_rebuilds++;
   return atlas_alloc(ctx, size);
+}
+// ---- atlas residency bookkeeping for hosts without the reference's Nim tables
+// markImageEntry / markGlyphEntry / markGeneratedEntry, figbackend.nim:359-398
+int fdc_mark_entry(fdc_ctx* ctx, uint64_t key, int kind, uint64_t id_a, uint64_t id_b) {
+  if (!ctx || kind < FDC_ENTRY_UNKNOWN || kind > FDC_ENTRY_GENERATED) return FDC_ERR_INVALID;
+  auto it = ctx->entry_info.find(key);
+  if (it == ctx->entry_info.end()) return ctx->fail(FDC_ERR_MISSING_IMAGE, "markEntry: unknown key");
+  it->second.kind = kind; it->second.a = id_a; it->second.b = id_b;
+  return FDC_OK;
+}
+static int remove_matching(fdc_ctx* ctx, int kind, bool by_b, uint64_t id) {
+  int n = 0;
+  for (auto it = ctx->entry_info.begin(); it != ctx->entry_info.end();) {
+    if (it->second.kind == kind && (by_b ? it->second.b : it->second.a) == id) {
+      ctx->entries.erase(it->first);  // removeAtlasEntry, figbackend.nim:355-357
+      it = ctx->entry_info.erase(it);
+      n++;
+    } else {
+      ++it;
+    }
+  }
+  if (n) ctx->table_dirty = true;
+  return n;
+}
+// clearFontGlyphs / clearTypefaceGlyphs, figbackend.nim:416-432; return the number of entries removed
+int fdc_clear_font_glyphs(fdc_ctx* ctx, uint64_t font_id) { return ctx ? remove_matching(ctx, FDC_ENTRY_GLYPH, false, font_id) : 0; }
+int fdc_clear_typeface_glyphs(fdc_ctx* ctx, uint64_t typeface_id) { return ctx ? remove_matching(ctx, FDC_ENTRY_GLYPH, true, typeface_id) : 0; }
+// retainImageOwner / retainFontOwner, figbackend.nim:434-437, :452-455
+int fdc_retain_owner(fdc_ctx* ctx, int what, uint64_t id, uint64_t token) {
+  if (!ctx || (what != FDC_OWNER_IMAGE && what != FDC_OWNER_FONT)) return FDC_ERR_INVALID;
+  auto& owners = (what == FDC_OWNER_IMAGE ? ctx->image_owners : ctx->font_owners)[id];
+  if (std::find(owners.begin(), owners.end(), token) == owners.end()) owners.push_back(token);
+  return FDC_OK;
+}
+// releaseImageOwner / releaseFontOwner, figbackend.nim:439-450, :457-468.  *out_last = 1 when that was the last owner;
+// the entries it kept alive are then evicted here (what the reference's callers do next: removeImage / clearFontGlyphs).
+int fdc_release_owner(fdc_ctx* ctx, int what, uint64_t id, uint64_t token, int* out_last) {
+  if (!ctx || (what != FDC_OWNER_IMAGE && what != FDC_OWNER_FONT)) return FDC_ERR_INVALID;
+  if (out_last) *out_last = 0;
+  auto& table = what == FDC_OWNER_IMAGE ? ctx->image_owners : ctx->font_owners;
+  auto it = table.find(id);
+  if (it == table.end()) return FDC_OK;
+  auto& owners = it->second;
+  owners.erase(std::remove(owners.begin(), owners.end(), token), owners.end());
+  if (!owners.empty()) return FDC_OK;
+  table.erase(it);
+  if (out_last) *out_last = 1;
+  if (what == FDC_OWNER_IMAGE) remove_matching(ctx, FDC_ENTRY_IMAGE, false, id);
+  else remove_matching(ctx, FDC_ENTRY_GLYPH, false, id);
+  return FDC_OK;
+}
+// atlasUsage, figbackend.nim:303-333
+int fdc_get_atlas_usage(fdc_ctx* ctx, fdc_atlas_usage* out) {
+  if (!ctx || !out) return FDC_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  out->atlas_size = ctx->atlas_size;
+  out->generation = ctx->atlas_generation;
+  out->rebuild_count = ctx->atlas_rebuilds;
+  out->atlas_area = (int64_t)ctx->atlas_size * ctx->atlas_size;
+  out->entry_count = (int32_t)ctx->entries.size();
+  for (auto& kv : ctx->entries) {
+    const int w = std::max(0, (int)lroundf(kv.second.w * (float)ctx->atlas_size)), h = std::max(0, (int)lroundf(kv.second.h * (float)ctx->atlas_size));
+    out->used_area += (int64_t)w * h;
+    auto it = ctx->entry_info.find(kv.first);
+    const int kind = it == ctx->entry_info.end() ? FDC_ENTRY_UNKNOWN : it->second.kind;
+    if (kind == FDC_ENTRY_IMAGE) out->image_count++;
+    else if (kind == FDC_ENTRY_GLYPH) out->glyph_count++;
+    else if (kind == FDC_ENTRY_GENERATED) out->generated_count++;
+    else out->unknown_count++;
+  }
+  out->packed_area = std::max<int64_t>(fdc_atlas_packed_area(ctx), out->used_area);
+  out->used_area = std::min(out->used_area, out->atlas_area);
+  out->packed_area = std::min(out->packed_area, out->atlas_area);
+  return FDC_OK;
+}
+// Native replay on regrow: when the atlas has to double, the live entries are re-packed and their texels carried over
+// on the device (out_rebuilt of fdc_put_image still reports that every rect changed).  Default off = the reference's
+// protocol, where the host replays its images itself (noteAtlasRebuilt, figbackend.nim:202-207).
+int fdc_set_atlas_replay(fdc_ctx* ctx, int enabled) {
+  if (!ctx) return FDC_ERR_INVALID;
+  ctx->atlas_replay = enabled != 0;
+  return FDC_OK;
 }
 int fdc_atlas_size(fdc_ctx* ctx) { return ctx ? ctx->atlas_size : 0; }
 int fdc_atlas_packed_area(fdc_ctx* ctx) {

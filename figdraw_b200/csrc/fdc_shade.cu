@@ -219,9 +219,19 @@ __device__ float4 tex_bilinear(const uint8_t* __restrict__ img, int size, float 
   return r;
 }
 
-// texture(atlasTex, uv): min LINEAR_MIPMAP_LINEAR / mag LINEAR (glcontext.nim:157-169).  lambda = log2(rho).
+// GL_NEAREST + GL_REPEAT on level 0 (a `pixelate` context magnifies with it); (tu,tv) are texel coordinates minus 0.5.
+__device__ __forceinline__ float4 tex_nearest(const uint8_t* __restrict__ img, int size, float tu, float tv) {
+  const int i = wrap_i((int)floorf(tu + 0.5f), size), j = wrap_i((int)floorf(tv + 0.5f), size);
+  return unpack255(__ldg(reinterpret_cast<const uint32_t*>(img) + (size_t)j * size + i));
+}
+// Level 0 through the magnification filter (lambda <= 0 and textureLod(.., 0)).
+__device__ __forceinline__ float4 tex_mag(const AtlasView& at, float tu, float tv) {
+  return at.pixelate ? tex_nearest(at.level[0], at.size, tu, tv) : tex_bilinear(at.level[0], at.size, tu, tv);
+}
+
+// texture(atlasTex, uv): min LINEAR_MIPMAP_LINEAR / mag LINEAR or NEAREST (glcontext.nim:157-169).  lambda = log2(rho).
 __device__ float4 atlas_sample(const AtlasView& at, float tu, float tv, float lambda) {
-  if (lambda <= 0.0f) return tex_bilinear(at.level[0], at.size, tu, tv);
+  if (lambda <= 0.0f) return tex_mag(at, tu, tv);
   const int maxl = at.n_levels - 1;
   const float cu = tu + 0.5f, cv = tv + 0.5f;  // level-0 texel-space coordinate
   if (lambda >= (float)maxl) {
@@ -357,9 +367,7 @@ __device__ float rect_mask_alpha(const RectMaskRec& rm, float aa, float px, floa
 __device__ __noinline__ float rect_mask_alpha_call(const RectMaskRec* __restrict__ rm, float aa, float px, float py) {
   return rect_mask_alpha(*rm, aa, px, py);
 }
-__device__ __noinline__ float4 tex_bilinear_call(const uint8_t* __restrict__ img, int size, float tu, float tv) {
-  return tex_bilinear(img, size, tu, tv);
-}
+__device__ __noinline__ float4 tex_mag_call(const AtlasView* __restrict__ at, float tu, float tv) { return tex_mag(*at, tu, tv); }
 
 __device__ __forceinline__ void blend(Pixel& px, float sr, float sg, float sb, float sa) {
   // rgb = s*sa + d*(1-sa); a = sa + da*(1-sa)  (glBlendFuncSeparate, glutils.nim:150-154), then UNORM8 store:
@@ -412,8 +420,8 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
     if (inside) {
       // lean tiles (no call anywhere in their loop) fetch in line; the full loop keeps the fetch out of line so that it
       // does not cost the rounded-box path registers
-      if (kInlineTex) tex = tex_bilinear(at.level[0], at.size, fmaf(s, q0.y, q0.x), fmaf(t, q0.w, q0.z));
-      else tex = tex_bilinear_call(at.level[0], at.size, fmaf(s, q0.y, q0.x), fmaf(t, q0.w, q0.z));
+      if (kInlineTex) tex = tex_mag(at, fmaf(s, q0.y, q0.x), fmaf(t, q0.w, q0.z));
+      else tex = tex_mag_call(&at, fmaf(s, q0.y, q0.x), fmaf(t, q0.w, q0.z));
     }
     const uint32_t kind = (info >> TE_KIND_SHIFT) & 3u;
     float sr = col.x, sg = col.y, sb = col.z, sa;
@@ -628,7 +636,7 @@ __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const
     const float4 q7 = __ldg(Q + 0);  // atlas texel map
     const float tu = fmaf(s, q7.y, q7.x), tv = fmaf(t, q7.w, q7.z);
     float4 tex = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (inside) tex = tex_bilinear(a.atlas.level[0], a.atlas.size, tu, tv);  // textureLod(.., 0)
+    if (inside) tex = tex_mag(a.atlas, tu, tv);  // textureLod(.., 0): lambda = 0 selects the magnification filter
     const bool mtsdf = mode == FDC_SDF_MTSDF || mode == FDC_SDF_MTSDF_ANNULAR;
     const bool stroke = mode == FDC_SDF_MSDF_ANNULAR || mode == FDC_SDF_MTSDF_ANNULAR;
     const float sd = (mtsdf ? tex.w : fmaxf(fminf(tex.x, tex.y), fminf(fmaxf(tex.x, tex.y), tex.z))) * (1.0f / 255.0f);

@@ -226,6 +226,7 @@ struct AtlasView {
   uint32_t table_mask;  // capacity - 1 (power of two)
   int size;
   int n_levels;
+  int pixelate;  // magnification filter GL_NEAREST (`newContext(pixelate = true)`, glcontext.nim:165-168)
 };
 
 struct FrameView {

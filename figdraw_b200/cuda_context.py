@@ -50,7 +50,7 @@ def _fill(fill: BackendFill) -> FdcFill:
 
 class CudaContext(BackendContext):
     def __init__(self, atlasSize: int = 1024, pixelScale: float = 1.0, device: int = 0, rank: int = 0,
-                 nRanks: int = 1):
+                 nRanks: int = 1, pixelate: bool = False):
         self._lib = abi.load_library()
         self._h = ctypes.c_void_p()
         rc = self._lib.fdc_create(ctypes.byref(self._h), int(device), int(atlasSize), float(pixelScale), int(rank),
@@ -61,6 +61,8 @@ class CudaContext(BackendContext):
             raise FigDrawError(rc, msg.decode() if msg else "fdc_create failed")
         self.missing_images = 0
         self._frame: Optional[Tuple[int, int]] = None
+        if pixelate:  # newContext(pixelate = true), glcontext.nim:255-282
+            self._ck(self._lib.fdc_set_pixelate(self._h, 1))
 
     # -- plumbing
     def close(self):
@@ -182,6 +184,33 @@ class CudaContext(BackendContext):
 
     def removeImage(self, key: int):
         self._ck(self._lib.fdc_remove_image(self._h, ctypes.c_uint64(key & (2**64 - 1))))
+
+    # -- atlas residency without the reference's Nim tables (figbackend.nim:355-468)
+    def markEntry(self, key: int, kind: int, idA: int = 0, idB: int = 0):
+        """kind: 1 image (idA = ImageId), 2 glyph (idA = FontId, idB = TypefaceId), 3 generated."""
+        self._ck(self._lib.fdc_mark_entry(self._h, ctypes.c_uint64(key & (2**64 - 1)), int(kind), ctypes.c_uint64(idA), ctypes.c_uint64(idB)))
+
+    def clearFontGlyphs(self, fontId: int) -> int:
+        return int(self._lib.fdc_clear_font_glyphs(self._h, ctypes.c_uint64(fontId)))
+
+    def clearTypefaceGlyphs(self, typefaceId: int) -> int:
+        return int(self._lib.fdc_clear_typeface_glyphs(self._h, ctypes.c_uint64(typefaceId)))
+
+    def retainOwner(self, what: int, id_: int, token: int):
+        self._ck(self._lib.fdc_retain_owner(self._h, int(what), ctypes.c_uint64(id_), ctypes.c_uint64(token)))
+
+    def releaseOwner(self, what: int, id_: int, token: int) -> bool:
+        last = ctypes.c_int(0)
+        self._ck(self._lib.fdc_release_owner(self._h, int(what), ctypes.c_uint64(id_), ctypes.c_uint64(token), ctypes.byref(last)))
+        return bool(last.value)
+
+    def atlasUsage(self):
+        u = abi.FdcAtlasUsage()
+        self._ck(self._lib.fdc_get_atlas_usage(self._h, ctypes.byref(u)))
+        return u
+
+    def setAtlasReplay(self, enabled: bool):
+        self._ck(self._lib.fdc_set_atlas_replay(self._h, 1 if enabled else 0))
 
     def resetImageAtlas(self, minimumSize: int):
         self._ck(self._lib.fdc_reset_image_atlas(self._h, int(minimumSize)))

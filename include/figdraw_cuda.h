@@ -185,6 +185,8 @@ int fdc_set_sdf_aa_factor(fdc_ctx* ctx, float aa);
 int fdc_set_text_subpixel_positioning_enabled(fdc_ctx* ctx, int enabled);
 int fdc_set_text_subpixel_shift(fdc_ctx* ctx, float shift);
 float fdc_pixel_scale(fdc_ctx* ctx);
+/* `pixelate` argument of newContext (glcontext.nim:255-282): GL_NEAREST magnification of the atlas (:165-168). */
+int fdc_set_pixelate(fdc_ctx* ctx, int enabled);
 
 /* --- draws --- */
 /* drawRoundedRectSdf, all three overloads (glcontext.nim:1420-1617): `fill->kind` selects which. */
@@ -258,6 +260,30 @@ int fdc_remove_image(fdc_ctx* ctx, uint64_t key);
 int fdc_reset_image_atlas(fdc_ctx* ctx, int minimum_size); /* resetImageAtlas glcontext.nim:634-641 */
 int fdc_atlas_size(fdc_ctx* ctx);
 int fdc_atlas_packed_area(fdc_ctx* ctx);
+/* Atlas residency for hosts that do not keep the reference's Nim tables.  A Nim CudaContext keeps
+ * using the base-class procs over its own tables (figbackend.nim:355-468); these are their native equivalents:
+ *   fdc_mark_entry            markImageEntry / markGlyphEntry / markGeneratedEntry :359-398 (id_a = ImageId or FontId,
+ *                             id_b = TypefaceId)
+ *   fdc_clear_font_glyphs, fdc_clear_typeface_glyphs   :416-432 (return the number of entries removed)
+ *   fdc_retain_owner, fdc_release_owner                :434-468; releasing the last owner evicts what it kept alive
+ *   fdc_get_atlas_usage       atlasUsage :303-333
+ *   fdc_set_atlas_replay(1)   when the atlas has to double, re-pack the live entries and carry their texels over on the
+ *                             device instead of dropping everything for the host to replay (noteAtlasRebuilt :202-207);
+ *                             removed entries are not carried over, which is what reclaims their space. */
+typedef enum fdc_entry_kind { FDC_ENTRY_UNKNOWN = 0, FDC_ENTRY_IMAGE = 1, FDC_ENTRY_GLYPH = 2, FDC_ENTRY_GENERATED = 3 } fdc_entry_kind;
+typedef enum fdc_owner_kind { FDC_OWNER_IMAGE = 0, FDC_OWNER_FONT = 1 } fdc_owner_kind;
+typedef struct fdc_atlas_usage { /* AtlasUsage, figbackend.nim:76-89 */
+  int32_t atlas_size, entry_count, image_count, glyph_count, generated_count, unknown_count;
+  int64_t atlas_area, used_area, packed_area;
+  uint64_t generation, rebuild_count;
+} fdc_atlas_usage;
+int fdc_mark_entry(fdc_ctx* ctx, uint64_t key, int kind, uint64_t id_a, uint64_t id_b);
+int fdc_clear_font_glyphs(fdc_ctx* ctx, uint64_t font_id);
+int fdc_clear_typeface_glyphs(fdc_ctx* ctx, uint64_t typeface_id);
+int fdc_retain_owner(fdc_ctx* ctx, int what, uint64_t id, uint64_t token);
+int fdc_release_owner(fdc_ctx* ctx, int what, uint64_t id, uint64_t token, int* out_last);
+int fdc_get_atlas_usage(fdc_ctx* ctx, fdc_atlas_usage* out);
+int fdc_set_atlas_replay(fdc_ctx* ctx, int enabled);
 
 /* --- multi-GPU / zero-copy plumbing (new; no reference equivalent) --- */
 /* Render into caller-owned device memory (W*H*4 bytes, row pitch W*4) instead of the context's own

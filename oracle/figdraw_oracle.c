@@ -69,6 +69,7 @@ typedef struct oracle {
   uint16_t* heights;
   entry_t* entries; int n_entries, cap_entries;
   int rebuilds;
+  int pixelate; /* newContext(pixelate = true): magnification filter GL_NEAREST (glcontext.nim:165-168) */
 } oracle;
 
 static void atlas_alloc(oracle* o, int size) {
@@ -98,6 +99,7 @@ void orc_destroy(oracle* o) {
   free(o);
 }
 int orc_atlas_size(oracle* o) { return o->atlas_size; }
+void orc_set_pixelate(oracle* o, int on) { o->pixelate = on != 0; }
 int orc_rebuilds(oracle* o) { return o->rebuilds; }
 
 static entry_t* find_entry(oracle* o, uint64_t key) {
@@ -388,14 +390,26 @@ static v4 tex_bilinear_rgba(const uint8_t* img, int size, float u, float v) {
   return r;
 }
 
-/* texture(atlasTex, uv) with implicit LOD: min LINEAR_MIPMAP_LINEAR, mag LINEAR (glcontext.nim:157-169).
+/* GL_NEAREST with GL_REPEAT on one level: the texel whose cell contains the coordinate. */
+static v4 tex_nearest_rgba(const uint8_t* img, int size, float u, float v) {
+  int i = wrap_repeat((int)floorf(u * (float)size), size), j = wrap_repeat((int)floorf(v * (float)size), size);
+  const uint8_t* t = img + ((size_t)j * size + i) * 4;
+  v4 r = {(float)t[0] / 255.0f, (float)t[1] / 255.0f, (float)t[2] / 255.0f, (float)t[3] / 255.0f};
+  return r;
+}
+/* Level 0 through the MAGNIFICATION filter (lambda <= 0, and textureLod(.., 0)): LINEAR, or NEAREST in a `pixelate` context. */
+static v4 tex_mag_rgba(const oracle* o, float u, float v) {
+  return o->pixelate ? tex_nearest_rgba(o->levels[0], o->atlas_size, u, v) : tex_bilinear_rgba(o->levels[0], o->atlas_size, u, v);
+}
+
+/* texture(atlasTex, uv) with implicit LOD: min LINEAR_MIPMAP_LINEAR, mag LINEAR / NEAREST (glcontext.nim:157-169).
  * duv* are the screen-space derivatives of the normalised coordinate. */
 static v4 atlas_sample_lod(const oracle* o, float u, float v, float dudx, float dvdx, float dudy, float dvdy) {
   float s = (float)o->atlas_size;
   float rx = length2(dudx * s, dvdx * s), ry = length2(dudy * s, dvdy * s);
   float rho = fmaxf(rx, ry);
   float lambda = (rho > 0.0f) ? log2f(rho) : -1000.0f;
-  if (lambda <= 0.0f) return tex_bilinear_rgba(o->levels[0], o->atlas_size, u, v);
+  if (lambda <= 0.0f) return tex_mag_rgba(o, u, v);
   int maxl = o->n_levels - 1;
   if (lambda >= (float)maxl) return tex_bilinear_rgba(o->levels[maxl], o->atlas_size >> maxl, u, v);
   int d1 = (int)floorf(lambda);
@@ -571,7 +585,7 @@ static v4 main_frag(const tctx* t, const oquad_t* q, const frag_in* in, int mask
     frag.x = tex.x * in->color.x; frag.y = tex.y * in->color.y; frag.z = tex.z * in->color.z; frag.w = tex.w * in->color.w;
   } else if (mode == M_MSDF || mode == M_MTSDF || mode == M_MSDF_ANN || mode == M_MTSDF_ANN) {
     float pxRange = q->factors.x, thr = q->factors.y;
-    v4 tex = tex_bilinear_rgba(sh->o->levels[0], sh->o->atlas_size, in->uv.x, in->uv.y); /* textureLod(.., 0) */
+    v4 tex = tex_mag_rgba(sh->o, in->uv.x, in->uv.y); /* textureLod(.., 0): lambda = 0 selects the magnification filter */
     int isMtsdf = (mode == M_MTSDF || mode == M_MTSDF_ANN), isStroke = (mode == M_MSDF_ANN || mode == M_MTSDF_ANN);
     float sd = isMtsdf ? tex.w : median3(tex.x, tex.y, tex.z);
     /* msdfScreenPxRange, atlas.frag:45-49; fwidth = |dFdx| + |dFdy| */

@@ -35,6 +35,7 @@ def _lib() -> ctypes.CDLL:
         lib.orc_create.restype = c.c_void_p
         lib.orc_create.argtypes = [c.c_int]
         lib.orc_destroy.argtypes = [c.c_void_p]
+        lib.orc_set_pixelate.argtypes = [c.c_void_p, c.c_int]
         lib.orc_atlas_size.argtypes = [c.c_void_p]
         lib.orc_rebuilds.argtypes = [c.c_void_p]
         lib.orc_get_image_rect.argtypes = [c.c_void_p, c.c_uint64, c.POINTER(c.c_float)]
@@ -63,8 +64,10 @@ def max_threads() -> int:
 class Oracle:
     """One GL-context-equivalent: an atlas plus the frame interpreter."""
 
-    def __init__(self, atlas_size: int = 1024):
+    def __init__(self, atlas_size: int = 1024, pixelate: bool = False):
         self._h = _lib().orc_create(int(atlas_size))
+        if pixelate:
+            _lib().orc_set_pixelate(self._h, 1)
 
     def close(self):
         if self._h:
@@ -170,9 +173,9 @@ def reference_bins(trace, tile_w: int = 16, tile_h: int = 16, band: Optional[Tup
 
 
 def render_trace(trace, n_threads: int = 0, want_counts: bool = False, oracle: Optional[Oracle] = None,
-                 rows: Optional[Tuple[int, int]] = None):
+                 rows: Optional[Tuple[int, int]] = None, pixelate: bool = False):
     """Render a figdraw_b200.figbackend.Trace: uploads its images (in order), then replays its calls."""
-    o = oracle or Oracle(trace.atlas_size)
+    o = oracle or Oracle(trace.atlas_size, pixelate=pixelate)
     if oracle is None:
         for _idx, key, img in trace.images:
             o.put_image(key, img)

@@ -248,3 +248,87 @@ def test_mask_level_with_several_draws_is_cleared_everywhere():
             off, ent = ctx.debugBins(seg)
             assert np.array_equal(off, off_ref) and np.array_equal(ent, ent_ref), f"variant {variant}: bins differ"
         ctx.close()
+
+
+def test_pixelate_context_magnifies_with_nearest():
+    """`newContext(pixelate = true)` (glcontext.nim:165-168): GL_NEAREST magnification of the atlas -- magnified images,
+    1:1 glyphs and MSDF quads (textureLod(.., 0) goes through the magnification filter); minified images stay trilinear."""
+    from figdraw_b200 import scenes, scenes_fuzz
+
+    traces = [scenes.golden_trace("image"), ss.config_trace(3, 1280, 720, n_glyphs=1500, msdf_glyphs=300)]
+    traces += [scenes_fuzz.random_trace(s) for s in (1, 4, 9)]
+    n_changed = 0
+    for tr in traces:
+        ctx = CudaContext(atlasSize=tr.atlas_size, pixelate=True)
+        got = render_trace(tr, ctx)
+        ctx.close()
+        want = oracle.render_trace(tr, pixelate=True)
+        d = np.abs(got.astype(np.int16) - want.astype(np.int16)).max(axis=2)
+        assert int(d.max()) <= 2, f"max {int(d.max())} LSB"
+        assert float((d > 0).mean()) <= 0.03
+        n_changed += int((want != oracle.render_trace(tr)).any())
+    assert n_changed >= 2  # the filter really changes these frames
+
+
+def test_atlas_residency_eviction_and_native_replay_on_regrow():
+    """entry kinds, owner tokens, eviction, and the atlas doubling WITHOUT losing the live images
+    (fdc_set_atlas_replay): every image drawn after the regrow still matches the oracle, evicted ones are gone and their
+    space is reclaimed."""
+    rng = np.random.default_rng(21)
+    imgs = {}
+    for k in range(60):
+        w, h = int(rng.integers(8, 40)), int(rng.integers(8, 40))
+        img = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+        img[..., 3] = 255
+        imgs[5000 + k] = img
+    ctx = CudaContext(atlasSize=128)
+    ctx.setAtlasReplay(True)
+    keys = list(imgs)
+    grew = 0
+    for i, key in enumerate(keys[:40]):
+        _rect, rebuilt = ctx.putImage(key, imgs[key])
+        grew += int(rebuilt)
+        if i < 20:
+            ctx.markEntry(key, 2, idA=7 if i % 2 else 8, idB=3)  # glyphs of font 7 / 8, typeface 3
+        else:
+            ctx.markEntry(key, 1, idA=key)
+            ctx.retainOwner(0, key, 111)
+            ctx.retainOwner(0, key, 222)
+    assert grew >= 1 and ctx.atlasSize() > 128
+    u = ctx.atlasUsage()
+    assert (u.entry_count, u.glyph_count, u.image_count) == (40, 20, 20) and u.rebuild_count >= 1
+    assert all(ctx.hasImage(k) for k in keys[:40])  # nothing was dropped by the regrow
+    # eviction: font 7's glyphs, and an image whose last owner lets go
+    assert ctx.clearFontGlyphs(7) == 10
+    assert not ctx.releaseOwner(0, keys[25], 111) and ctx.hasImage(keys[25])
+    assert ctx.releaseOwner(0, keys[25], 222) and not ctx.hasImage(keys[25])
+    assert ctx.clearTypefaceGlyphs(3) == 10
+    live = [k for k in keys[20:40] if k != keys[25]]
+    assert ctx.atlasUsage().entry_count == len(live) == 19
+    # more images: the next regrow carries only the live ones over
+    for key in keys[40:]:
+        ctx.putImage(key, imgs[key])
+        live.append(key)
+    assert all(ctx.hasImage(k) for k in live) and not ctx.hasImage(keys[0])
+
+    # draw every live image 1:1 and magnified; the oracle gets the same images (its packer places them elsewhere, the
+    # pixels must not care)
+    tb = TraceBackend(atlasSize=1024)
+    for key in live:
+        tb.putImage(key, imgs[key])
+    tb.beginFrame((640, 480), clearMain=True, clearMainColor=(0.2, 0.2, 0.25, 1.0))
+    for n, key in enumerate(live):
+        x, y = 8 + (n % 10) * 62, 6 + (n // 10) * 90
+        tb.drawImage(key, (float(x), float(y)), [0xFFFFFFFF] * 4)
+        tb.drawImage(key, (float(x), float(y) + 44.0), [0xFFFFFFFF] * 4, (50.0, 40.0))
+    tb.endFrame()
+    tr = tb.trace()
+    ctx.beginFrame((640, 480), clearMain=True, clearMainColor=(0.2, 0.2, 0.25, 1.0))
+    ctx.submitCalls(tr.calls)
+    ctx.endFrame()
+    got = ctx.readPixels()
+    want = oracle.render_trace(tr)
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16)).max(axis=2)
+    assert int(d.max()) <= 2, f"max {int(d.max())} LSB"
+    assert ctx.missing_images == 0
+    ctx.close()

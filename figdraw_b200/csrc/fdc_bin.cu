@@ -981,6 +981,10 @@ constexpr int kGroups = kStage / 32;
 #ifndef FDC_DIRECT_FINE_LIMIT
 #define FDC_DIRECT_FINE_LIMIT 262144
 #endif
+#ifndef FDC_FINE_SPLIT_BINS
+#define FDC_FINE_SPLIT_BINS 296
+#endif
+constexpr int kFineSplitBins = FDC_FINE_SPLIT_BINS;  // at most this many bins: two CTAs per bin (148 SMs x 4 CTAs = 592 slots)
 constexpr size_t kDirectFineLimit = FDC_DIRECT_FINE_LIMIT;  // primitives x coarse bins below which the coarse pass is skipped
 
 // One CTA per coarse bin (8x8 tiles).  Staged entries are handled 32 at a time ("groups"), one group per warp: every
@@ -1018,6 +1022,9 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
   const int px0 = tile_x0 * kTileW, py0 = tile_y0 * kTileH;
   const bool single = end - begin <= (uint32_t)kStage;
   if (threadIdx.x < 64) { s_run[threadIdx.x] = 0; s_cls[threadIdx.x] = 0; }
+  // Few bins (a band of a multi-GPU partition, a small frame) leave most SMs idle with one CTA per bin: the launch then
+  // has two CTAs per bin, each building the lists of one half of the bin's tiles (tile rows 0-3 / 4-7).
+  const bool do_lo = gridDim.y == 1 || blockIdx.y == 0, do_hi = gridDim.y == 1 || blockIdx.y == 1;
 
   for (int pass = 0; pass < 2; pass++) {
     if (pass == 1) {
@@ -1047,7 +1054,7 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
       if (threadIdx.x < 64) {
         const int t = threadIdx.x;
         const int tx = tile_x0 + (t & 7), ty = tile_y0 + (t >> 3);
-        const bool in_band = tx < f.tiles_x && ty >= f.ty0 && ty < f.ty1;
+        const bool in_band = tx < f.tiles_x && ty >= f.ty0 && ty < f.ty1 && (t < 32 ? do_lo : do_hi);
         // how many tiles need the shade kernel's full loop (its launch returns at once when there are none)
         const uint32_t fullm = __ballot_sync(0xFFFFFFFFu, in_band && alloc != 0xFFFFFFFFu && s_cls[t] != 0u && s_run[t] != 0u);
         if ((t & 31) == 0 && fullm) atomicAdd(&counters[kCntFullTiles], (uint32_t)__popc(fullm));
@@ -1095,7 +1102,7 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
         for (int g = warp; g < n_groups; g += 8) {
           const uint32_t k = (uint32_t)g * 32u + lane;
           const uint32_t lo = k < ns ? s_lo[k] : 0u, hi = k < ns ? s_hi[k] : 0u;
-          const uint32_t t_lo = transpose32(lo, lane), t_hi = transpose32(hi, lane);
+          const uint32_t t_lo = do_lo ? transpose32(lo, lane) : 0u, t_hi = do_hi ? transpose32(hi, lane) : 0u;
           s_gcnt[g][lane] = (uint8_t)__popc(t_lo);
           s_gcnt[g][32 + lane] = (uint8_t)__popc(t_hi);
           // tile class: anything but unmasked fast content sends the whole tile to the shade kernel's full loop
@@ -1124,6 +1131,7 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
         const uint32_t lo = k < ns ? s_lo[k] : 0u, hi = k < ns ? s_hi[k] : 0u;
 #pragma unroll
         for (int half = 0; half < 2; half++) {
+          if (half == 0 ? !do_lo : !do_hi) continue;
           uint32_t m = transpose32(half ? hi : lo, lane);  // entries of this group that hit tile t
           const int t = half * 32 + lane, r = t >> 3, c = t & 7;
           uint32_t pos = s_gpos[g][t];
@@ -1168,8 +1176,9 @@ void launch_binning(const PrimBin* prims, uint32_t n_prims, const FrameView& f, 
   if (n_prims == 0 || n_bins == 0) return;
   if ((size_t)n_prims * (size_t)n_bins <= (size_t)kDirectFineLimit) {
     // Small scene: three launches of coarse binning cost more than letting every bin look at every primitive.
-    fine_bin_kernel<<<n_bins, 256, 0, stream>>>(prims, f, b.cbin_start, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count,
-                                                b.tile_list, b.tile_cap, b.counters, n_prims);
+    fine_bin_kernel<<<dim3(n_bins, n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(prims, f, b.cbin_start, b.coarse_list, b.coarse_cap,
+                                                                                    b.tile_start, b.tile_count, b.tile_list, b.tile_cap,
+                                                                                    b.counters, n_prims);
     if (n_launches) *n_launches += 1;
     return;
   }
@@ -1179,8 +1188,9 @@ void launch_binning(const PrimBin* prims, uint32_t n_prims, const FrameView& f, 
   coarse_scan_kernel<<<(n_bins + 7) / 8, 256, 0, stream>>>(b.chunk_counts, n_chunks, n_bins, b.cbin_start, b.coarse_cap, b.counters);
   coarse_scatter_kernel<<<grid, kChunk, 0, stream>>>(prims, n_prims, f, rows_per_cta, b.chunk_counts, b.cbin_start, b.coarse_list,
                                                      b.coarse_cap, b.counters);
-  fine_bin_kernel<<<n_bins, 256, 0, stream>>>(prims, f, b.cbin_start, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count,
-                                              b.tile_list, b.tile_cap, b.counters, 0u);
+  fine_bin_kernel<<<dim3(n_bins, n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(prims, f, b.cbin_start, b.coarse_list, b.coarse_cap,
+                                                                                  b.tile_start, b.tile_count, b.tile_list, b.tile_cap,
+                                                                                  b.counters, 0u);
   if (n_launches) *n_launches += 4;
 }
 

@@ -164,6 +164,12 @@ class FdcFrameStats(ctypes.Structure):
     ]
 
 
+OUTLINE_SEG_DTYPE = np.dtype([("x0", "<f4"), ("y0", "<f4"), ("x1", "<f4"), ("y1", "<f4"), ("cx", "<f4"), ("cy", "<f4"),
+                              ("kind", "<u4"), ("_pad", "<u4")])
+GLYPH_JOB_DTYPE = np.dtype([("key", "<u8"), ("first_seg", "<u4"), ("n_segs", "<u4"), ("width", "<i4"), ("height", "<i4")])
+assert OUTLINE_SEG_DTYPE.itemsize == 32 and GLYPH_JOB_DTYPE.itemsize == 24
+
+
 class FdcAtlasUsage(ctypes.Structure):
     """AtlasUsage, figbackend.nim:76-89."""
 
@@ -189,7 +195,7 @@ EXPORTS = [
     "fdc_put_image", "fdc_update_image", "fdc_has_image", "fdc_get_image_rect", "fdc_remove_image",
     "fdc_reset_image_atlas", "fdc_atlas_size", "fdc_atlas_packed_area",
     "fdc_mark_entry", "fdc_clear_font_glyphs", "fdc_clear_typeface_glyphs", "fdc_retain_owner", "fdc_release_owner",
-    "fdc_get_atlas_usage", "fdc_set_atlas_replay",
+    "fdc_get_atlas_usage", "fdc_set_atlas_replay", "fdc_rasterize_glyphs",
     "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers", "fdc_bind_shared_framebuffer", "fdc_set_frame_barrier", "fdc_export_framebuffer", "fdc_set_peer_gather", "fdc_reserve_framebuffer", "fdc_framebuffer_ipc_handle", "fdc_open_peer_framebuffer",
     "fdc_get_frame_stats", "fdc_debug_bins", "fdc_debug_shade_stats",
     "fdc_flatten_renders", "fdc_render_frame",
@@ -281,6 +287,7 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_release_owner", c.c_int, P, c.c_int, c.c_uint64, c.c_uint64, c.POINTER(c.c_int))
     sig("fdc_get_atlas_usage", c.c_int, P, c.POINTER(FdcAtlasUsage))
     sig("fdc_set_atlas_replay", c.c_int, P, c.c_int)
+    sig("fdc_rasterize_glyphs", c.c_int, P, c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_int, c.POINTER(c.c_int))
     sig("fdc_bind_framebuffer", c.c_int, P, P)
     sig("fdc_framebuffer_ptr", P, P)
     sig("fdc_band_rows", c.c_int, P, c.POINTER(c.c_int), c.POINTER(c.c_int))

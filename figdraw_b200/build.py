@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libfigdraw_cuda.so")
-SOURCES = ["fdc_context.cu", "fdc_bin.cu", "fdc_shade.cu", "fdc_blur.cu", "fdc_flatten.cu"]
+SOURCES = ["fdc_context.cu", "fdc_bin.cu", "fdc_shade.cu", "fdc_blur.cu", "fdc_flatten.cu", "fdc_glyph.cu"]
 HEADERS = ["fdc_types.h", "fdc_kernels.h", "fdc_flatten.h", os.path.join("..", "..", "include", "figdraw_cuda.h")]
 
 NVCC_FLAGS = [

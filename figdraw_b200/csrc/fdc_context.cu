@@ -1936,6 +1936,64 @@ int fdc_reset_image_atlas(fdc_ctx* ctx, int minimum_size) {
   ctx->atlas_rebuilds++;
   return atlas_alloc(ctx, size);
 }
+// Glyph bitmaps rasterised on the device, straight into their atlas slots (fdc_glyph.cu).
+int fdc_rasterize_glyphs(fdc_ctx* ctx, const fdc_glyph_job* jobs, size_t n_jobs, const fdc_outline_seg* segs, size_t n_segs,
+                         int lcd_filter, int* out_rebuilt) {
+  if (!ctx || (!jobs && n_jobs) || (!segs && n_segs)) return FDC_ERR_INVALID;
+  if (out_rebuilt) *out_rebuilt = 0;
+  if (n_jobs == 0) return FDC_OK;
+  CK(cudaSetDevice(ctx->device));
+  struct GlyphDev { uint32_t first_seg, n_segs; int32_t w, h, ax, ay; };
+  std::vector<GlyphDev> dev(n_jobs);
+  size_t valid_from = 0;  // jobs placed before the last regrow lost their slots (unless the atlas replays itself)
+  for (size_t i = 0; i < n_jobs; i++) {
+    const fdc_glyph_job& j = jobs[i];
+    if (j.width <= 0 || j.height <= 0 || j.width > 4096 || j.height > 4096 || (size_t)j.first_seg + j.n_segs > n_segs)
+      return ctx->fail(FDC_ERR_INVALID, "rasterizeGlyphs: bad job %zu (%dx%d, segments %u+%u of %zu)", i, j.width, j.height, j.first_seg,
+                       j.n_segs, n_segs);
+    int rx = 0, ry = 0;
+    bool grew = false;
+    int rc = find_empty_rect(ctx, j.width, j.height, &rx, &ry, &grew);
+    if (rc) return rc;
+    if (grew) {
+      if (out_rebuilt) *out_rebuilt = 1;
+      if (!ctx->atlas_replay) valid_from = i;
+      else
+        for (size_t k = 0; k < i; k++) {  // re-packed: the earlier jobs' slots moved
+          auto it = ctx->entry_info.find(jobs[k].key);
+          if (it != ctx->entry_info.end()) { dev[k].ax = it->second.px; dev[k].ay = it->second.py; }
+        }
+    }
+    const float as = (float)ctx->atlas_size;
+    ctx->entries[j.key] = {(float)rx / as, (float)ry / as, (float)j.width / as, (float)j.height / as};
+    fdc_ctx::EntryInfo& e = ctx->entry_info[j.key];
+    e.px = rx; e.py = ry; e.w = j.width; e.h = j.height;
+    e.order = ++ctx->put_counter;
+    if (e.kind == FDC_ENTRY_UNKNOWN) e.kind = FDC_ENTRY_GLYPH;
+    dev[i] = {j.first_seg, j.n_segs, j.width, j.height, rx, ry};
+  }
+  for (size_t k = 0; k < valid_from; k++) dev[k].w = dev[k].h = 0;
+  ctx->table_dirty = true;
+  void* d_jobs = nullptr;
+  fdc_outline_seg* d_segs = nullptr;
+  CK(cudaMalloc(&d_jobs, n_jobs * sizeof(GlyphDev)));
+  CK(cudaMalloc(&d_segs, std::max<size_t>(n_segs, 1) * sizeof(fdc_outline_seg)));
+  CK(cudaMemcpyAsync(d_jobs, dev.data(), n_jobs * sizeof(GlyphDev), cudaMemcpyHostToDevice, ctx->stream));
+  if (n_segs) CK(cudaMemcpyAsync(d_segs, segs, n_segs * sizeof(fdc_outline_seg), cudaMemcpyHostToDevice, ctx->stream));
+  launch_glyph_raster(d_jobs, (int)n_jobs, d_segs, ctx->levels[0], ctx->atlas_size, lcd_filter, ctx->stream);
+  CK(cudaGetLastError());
+  for (size_t k = valid_from; k < n_jobs; k++) {
+    if (dev[k].w > 1 && dev[k].h > 1) {
+      int rc = build_mips(ctx, dev[k].ax, dev[k].ay, dev[k].w, dev[k].h);
+      if (rc) return rc;
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));  // `dev` and the caller's arrays are pageable
+  cudaFree(d_jobs);
+  cudaFree(d_segs);
+  return FDC_OK;
+}
+
 // ---- atlas residency bookkeeping for hosts without the reference's Nim tables
 // markImageEntry / markGlyphEntry / markGeneratedEntry, figbackend.nim:359-398
 int fdc_mark_entry(fdc_ctx* ctx, uint64_t key, int kind, uint64_t id_a, uint64_t id_b) {

@@ -87,6 +87,11 @@ void launch_wait_flags(uint32_t* my_flags, int n, cudaStream_t stream);
 void launch_push_to_peers(const uint8_t* src, size_t byte_off, size_t bytes, uint8_t* multicast, uint8_t* const* peers, int n_peers,
                           int my_rank, cudaStream_t stream);
 
+// One CTA per glyph: signed-area accumulation of the outline, alpha into the glyph's atlas slot (fdc_glyph.cu).
+// `glyphs_dev`: device array of {first_seg, n_segs, w, h, atlas_x, atlas_y} (six 32-bit words each).
+void launch_glyph_raster(const void* glyphs_dev, int n_glyphs, const fdc_outline_seg* segs_dev, uint8_t* atlas_level0, int atlas_size,
+                         int lcd_filter, cudaStream_t stream);
+
 void launch_fill_u32(uint32_t* dst, uint32_t value, size_t n, cudaStream_t stream);
 // Builds mip level `l+1` region from level `l` (premultiplied 2x2 box, see oracle upload_chain).
 void launch_mip_down(const uint8_t* src, int src_size, uint8_t* dst, int dst_size, int sx, int sy, int sw, int sh,

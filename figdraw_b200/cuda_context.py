@@ -212,6 +212,16 @@ class CudaContext(BackendContext):
     def setAtlasReplay(self, enabled: bool):
         self._ck(self._lib.fdc_set_atlas_replay(self._h, 1 if enabled else 0))
 
+    def rasterizeGlyphs(self, jobs: np.ndarray, segs: np.ndarray, lcdFilter: bool = False) -> bool:
+        """Glyph bitmaps from outlines, rasterised on the GPU straight into the atlas (abi.GLYPH_JOB_DTYPE /
+        abi.OUTLINE_SEG_DTYPE arrays).  Returns whether the atlas was rebuilt."""
+        jobs = np.ascontiguousarray(jobs, dtype=abi.GLYPH_JOB_DTYPE)
+        segs = np.ascontiguousarray(segs, dtype=abi.OUTLINE_SEG_DTYPE)
+        rebuilt = ctypes.c_int(0)
+        self._ck(self._lib.fdc_rasterize_glyphs(self._h, jobs.ctypes.data, len(jobs), segs.ctypes.data, len(segs),
+                                                1 if lcdFilter else 0, ctypes.byref(rebuilt)))
+        return bool(rebuilt.value)
+
     def resetImageAtlas(self, minimumSize: int):
         self._ck(self._lib.fdc_reset_image_atlas(self._h, int(minimumSize)))
 

@@ -285,6 +285,29 @@ int fdc_release_owner(fdc_ctx* ctx, int what, uint64_t id, uint64_t token, int* 
 int fdc_get_atlas_usage(fdc_ctx* ctx, fdc_atlas_usage* out);
 int fdc_set_atlas_replay(fdc_ctx* ctx, int enabled);
 
+/* --- glyph coverage rasterisation on the GPU.  Replaces, for hosts that hand over OUTLINES, the
+ * per-glyph CPU rasterisation + putImage of the reference (common/textrasters/pixie_raster.nim:45-95 renderPixieGlyph:
+ * typeset one rune, image.fillText, optional applyLcdFilter :12-43, loadGlyphImage -> putImage).  Each job is one glyph
+ * bitmap: `width` x `height` texels, its outline as `n_segs` segments starting at `first_seg` in the shared segment
+ * array -- lines and quadratic Beziers in the bitmap's pixel space (x right, y down), closed contours, holes wound
+ * opposite to the outer contour (TrueType order).  The library packs a slot for `key` (as fdc_put_image does), writes
+ * area-coverage texels (255,255,255,alpha) straight into the atlas and builds the mip chain; `lcd_filter` applies the
+ * reference's 5-tap filter.  PARITY UNPINNED against pixie's own anti-aliasing (pixie is not vendored); the oracle is
+ * the same signed-area accumulation written sequentially (oracle/glyph_oracle.c). */
+typedef struct fdc_outline_seg {
+  float x0, y0, x1, y1; /* end points */
+  float cx, cy;         /* control point (kind 1) */
+  uint32_t kind;        /* 0 line, 1 quadratic Bezier */
+  uint32_t _pad;
+} fdc_outline_seg;      /* 32 bytes */
+typedef struct fdc_glyph_job {
+  uint64_t key;         /* atlas key, e.g. hash((2344, fontId, glyphId, lcd, variant)), common/fontglyphs.nim:54-59 */
+  uint32_t first_seg, n_segs;
+  int32_t width, height;
+} fdc_glyph_job;        /* 24 bytes */
+int fdc_rasterize_glyphs(fdc_ctx* ctx, const fdc_glyph_job* jobs, size_t n_jobs, const fdc_outline_seg* segs, size_t n_segs,
+                         int lcd_filter, int* out_rebuilt);
+
 /* --- multi-GPU / zero-copy plumbing (new; no reference equivalent) --- */
 /* Render into caller-owned device memory (W*H*4 bytes, row pitch W*4) instead of the context's own
  * framebuffer; NULL restores the internal one.  Lets a host framework all-gather bands in place. */

@@ -20,8 +20,8 @@ N_MODES = 24
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "figdraw_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "figdraw_oracle.c"), os.path.join(_HERE, "glyph_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(p) for p in srcs):
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
     return _SO
 
@@ -45,6 +45,7 @@ def _lib() -> ctypes.CDLL:
         lib.orc_render_rows.argtypes = lib.orc_render.argtypes + [c.c_int, c.c_int]
         lib.orc_max_threads.restype = c.c_int
         lib.orc_count_fragments.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_int64, c.c_void_p, c.c_int]
+        lib.orc_rasterize_glyph.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p]
         lib.orc_collect_quads.restype = c.c_int64
         lib.orc_collect_quads.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int64,
                                           c.c_void_p, c.c_int64]
@@ -181,3 +182,15 @@ def render_trace(trace, n_threads: int = 0, want_counts: bool = False, oracle: O
             o.put_image(key, img)
     return o.render(trace.width, trace.height, trace.calls, clear=trace.clear, n_threads=n_threads,
                     want_counts=want_counts, rows=rows)
+
+
+def rasterize_glyph(segs: np.ndarray, width: int, height: int, lcd_filter: bool = False) -> np.ndarray:
+    """CPU oracle of the glyph coverage rasteriser (oracle/glyph_oracle.c): `segs` is an array of 32-byte outline
+    segments (x0, y0, x1, y1, cx, cy, kind, pad); returns height x width x 4 straight-alpha RGBA8."""
+    segs = np.ascontiguousarray(segs)
+    assert segs.dtype.itemsize == 32
+    out = np.zeros((height, width, 4), dtype=np.uint8)
+    rc = _lib().orc_rasterize_glyph(segs.ctypes.data, len(segs), int(width), int(height), 1 if lcd_filter else 0, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"oracle: glyph rasterisation failed with status {rc}")
+    return out

@@ -101,8 +101,9 @@ def test_cuda_glyph_rasteriser_equals_the_oracle(lcd):
 
     glyphs = go.sample_glyphs(seed=7, count=24) + go.sample_glyphs(seed=8, count=4, size=(150, 210))  # incl. multi-strip bitmaps
     jobs, segs, keys = go.jobs_for(glyphs)
-    ctx = CudaContext(atlasSize=512)
-    ctx.setAtlasReplay(True)
+    # same atlas size and insertion order on both sides: the packer then places every glyph identically, which matters for
+    # the minified draws (the reference builds mip levels from the slot's own origin, so their phase follows its parity)
+    ctx = CudaContext(atlasSize=2048)
     ctx.rasterizeGlyphs(jobs, segs, lcdFilter=lcd)
     assert all(ctx.hasImage(k) for k in keys) and ctx.atlasUsage().glyph_count == len(keys)
     # draw every glyph 1:1 on black with a white tint: the frame then shows the atlas texels themselves
@@ -132,4 +133,38 @@ def test_cuda_glyph_rasteriser_equals_the_oracle(lcd):
     d = np.abs(got.astype(np.int16) - want.astype(np.int16)).max(axis=2)
     assert int(d.max()) <= 2, f"max {int(d.max())} LSB at {np.argwhere(d == d.max())[0]}"
     assert got[..., :3].max() > 200 and ctx.missing_images == 0
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_cuda_glyph_batch_survives_an_atlas_regrow():
+    """The atlas doubles in the middle of a batch (native replay on): every glyph of the batch, placed before or after the
+    regrow, must still come out right (1:1 draws: texel-exact positions do not depend on where the packer put them)."""
+    from figdraw_b200.cuda_context import CudaContext
+    from figdraw_b200.figbackend import TraceBackend
+
+    glyphs = go.sample_glyphs(seed=11, count=40, size=(40, 52))
+    jobs, segs, keys = go.jobs_for(glyphs)
+    ctx = CudaContext(atlasSize=256)
+    ctx.setAtlasReplay(True)
+    assert ctx.rasterizeGlyphs(jobs, segs) is True and ctx.atlasSize() > 256
+    assert all(ctx.hasImage(k) for k in keys)
+    W, H = 1024, 400
+    tb = TraceBackend(atlasSize=2048)
+    for (w, h, s), key in zip(glyphs, keys):
+        tb.putImage(key, oracle.rasterize_glyph(go.to_array(s), w, h))
+    tb.beginFrame((W, H), clearMain=True, clearMainColor=(0.0, 0.0, 0.0, 1.0))
+    x = y = 3
+    for (w, h, _s), key in zip(glyphs, keys):
+        if x + w + 3 > W:
+            x, y = 3, y + 62
+        tb.drawImage(key, (float(x), float(y)), [0xFFFFFFFF] * 4)
+        x += w + 3
+    tb.endFrame()
+    tr = tb.trace()
+    ctx.beginFrame((W, H), clearMain=True, clearMainColor=(0.0, 0.0, 0.0, 1.0))
+    ctx.submitCalls(tr.calls)
+    ctx.endFrame()
+    d = np.abs(ctx.readPixels().astype(np.int16) - oracle.render_trace(tr).astype(np.int16)).max(axis=2)
+    assert int(d.max()) <= 2 and ctx.missing_images == 0
     ctx.close()

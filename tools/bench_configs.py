@@ -46,9 +46,20 @@ for name, build in cases:
     cpu_s = time.time() - t0
     d = np.abs(got.astype(np.int16) - want.astype(np.int16)).max(axis=2)
     mpx = tr.width * tr.height / 1e6
+    # algorithmic roofline of the shade kernel: fragments the reference's GL path would shade x flops per mode
+    import bench as B  # noqa: E402  (repo root is on sys.path)
+
+    counts = oracle.count_fragments(tr)
+    flops = B.algorithmic_flops(counts)
+    n_blur = int((tr.calls["op"] == 13).sum())
+    peak = 148 * 128 * 2 * 1965e6 / 1e12
     row = {"config": name, "draws": tr.n_draws, "segments": int(st.n_segments), "launches": int(st.n_launches),
            "gpu_ms": round(float(t[0]), 4), "graph_ms": round(g, 4), "bin_ms": round(float(t[1]), 4), "shade_ms": round(float(t[2]), 4),
            "blur_ms": round(float(t[3]), 4), "mpix_per_s": round(mpx / (t[0] * 1e-3), 1), "fps": round(1e3 / t[0], 1),
+           "fragments": int(counts.sum()), "algorithmic_gflop": round(flops / 1e9, 3),
+           "shade_algorithmic_tflops": round(flops / (t[2] * 1e-3) / 1e12, 2) if t[2] > 0 else None,
+           "shade_frac_of_fp32_peak_at_1965MHz": round(flops / (t[2] * 1e-3) / 1e12 / peak, 3) if t[2] > 0 else None,
+           "blur_nodes": n_blur,
            "cpu_oracle_s": round(cpu_s, 3), "cpu_threads": oracle.max_threads(), "max_diff_lsb": int(d.max()),
            "pixels_differing": int((d > 0).sum())}
     rows.append(row)

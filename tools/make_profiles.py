@@ -25,7 +25,14 @@ WANT = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active
 
 
 def raw_rows(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """Rows of an ncu raw page: from the CSV exported on the GPU box (name_raw.csv) or from the report itself."""
+    as_csv = rep.replace(".ncu-rep", "_raw.csv")
+    if os.path.exists(as_csv):
+        raw = open(as_csv).read()
+    elif os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
+        return [], [], []
     rr = list(csv.reader(raw.splitlines()))
     if len(rr) < 3:
         return [], [], []
@@ -127,10 +134,7 @@ with open(os.path.join(P, f"{tag}_ncu_configs.md"), "w") as fh:
              "capture of each kernel (a frame replayed launch by launch).  Blur roofline: a pass reads and writes 4 bytes per region pixel; "
              "`hbm_frac` = (read + written algorithmic bytes) / duration / 6545 GB/s (MEASURED_PEAKS.json).\n")
     for c in (2, 3, 4):
-        rep = os.path.join(G, f"final_cfg{c}.ncu-rep")
-        if not os.path.exists(rep):
-            continue
-        hh, units, data = raw_rows(rep)
+        hh, units, data = raw_rows(os.path.join(G, f"final_cfg{c}.ncu-rep"))
         if not hh:
             continue
         idx = {n: i for i, n in enumerate(hh)}

@@ -82,12 +82,42 @@ proc fdc_remove_image(ctx: FdcCtx, key: uint64): cint {.importc, header: hdr.}
 proc fdc_reset_image_atlas(ctx: FdcCtx, minimumSize: cint): cint {.importc, header: hdr.}
 proc fdc_atlas_size(ctx: FdcCtx): cint {.importc, header: hdr.}
 proc fdc_atlas_packed_area(ctx: FdcCtx): cint {.importc, header: hdr.}
+# round 2: error recovery, replay, pixelate, atlas residency, glyph rasterisation, present, shared framebuffer
+proc fdc_sync(ctx: FdcCtx): cint {.importc, header: hdr.}
+proc fdc_abort_frame(ctx: FdcCtx): cint {.importc, header: hdr.}
+proc fdc_retry_frame(ctx: FdcCtx): cint {.importc, header: hdr.}
+proc fdc_replay_frame(ctx: FdcCtx): cint {.importc, header: hdr.}
+proc fdc_set_replay_graph(ctx: FdcCtx, enabled: cint): cint {.importc, header: hdr.}
+proc fdc_set_pixelate(ctx: FdcCtx, enabled: cint): cint {.importc, header: hdr.}
+proc fdc_mark_entry(ctx: FdcCtx, key: uint64, kind: cint, idA, idB: uint64): cint {.importc, header: hdr.}
+proc fdc_clear_font_glyphs(ctx: FdcCtx, fontId: uint64): cint {.importc, header: hdr.}
+proc fdc_clear_typeface_glyphs(ctx: FdcCtx, typefaceId: uint64): cint {.importc, header: hdr.}
+proc fdc_retain_owner(ctx: FdcCtx, what: cint, id, token: uint64): cint {.importc, header: hdr.}
+proc fdc_release_owner(ctx: FdcCtx, what: cint, id, token: uint64, outLast: ptr cint): cint {.importc, header: hdr.}
+proc fdc_set_atlas_replay(ctx: FdcCtx, enabled: cint): cint {.importc, header: hdr.}
+proc fdc_export_framebuffer(ctx: FdcCtx, width, rows: cint, outFd: ptr cint, outBytes: ptr csize_t): cint {.importc, header: hdr.}
+proc fdc_bind_shared_framebuffer(ctx: FdcCtx, local: pointer, bytes: csize_t, peers: ptr pointer, n: cint,
+                                 multicast: pointer, width, rows: cint): cint {.importc, header: hdr.}
+
+type
+  FdcOutlineSeg {.bycopy.} = object ## 32 bytes: a line (kind 0) or quadratic Bezier (kind 1) in bitmap pixel space
+    x0, y0, cx, cy, x1, y1: cfloat
+    kind, pad: uint32
+  FdcGlyphJob {.bycopy.} = object   ## 24 bytes
+    key: uint64
+    firstSeg, nSegs: uint32
+    width, height: int32
+
+proc fdc_rasterize_glyphs(ctx: FdcCtx, jobs: ptr FdcGlyphJob, nJobs: csize_t, segs: ptr FdcOutlineSeg, nSegs: csize_t,
+                          lcdFilter: cint, outRebuilt: ptr cint): cint {.importc, header: hdr.}
 
 template ck(ctx: CudaContext, call: untyped) =
   ## Non-zero fdc_status -> FigDrawError (common/shared.nim:19), like GL errors surface as exceptions.
   let rc = call
   if rc != 0 and rc != 5: # 5 = FDC_ERR_MISSING_IMAGE: GL only warns (glcontext.nim:1305-1310)
-    raise newException(FigDrawError, "cuda backend: " & $fdc_last_error(ctx.h))
+    let msg = $fdc_last_error(ctx.h)
+    discard fdc_abort_frame(ctx.h) # drop a half-recorded frame so the next beginFrame is legal (no-op outside a frame)
+    raise newException(FigDrawError, "cuda backend: " & msg)
 
 func pack(c: ColorRGBA): uint32 =
   c.r.uint32 or (c.g.uint32 shl 8) or (c.b.uint32 shl 16) or (c.a.uint32 shl 24)
@@ -108,11 +138,13 @@ template radX(r: CornerRadii2D[float32]): array[4, cfloat] =
 template radY(r: CornerRadii2D[float32]): array[4, cfloat] =
   [r.y[dcTopLeft].cfloat, r.y[dcTopRight].cfloat, r.y[dcBottomLeft].cfloat, r.y[dcBottomRight].cfloat]
 
-proc newContext*(atlasSize = 1024, pixelScale = 1.0, device = 0, rank = 0, nRanks = 1): CudaContext =
-  ## Mirrors `newContext` of glcontext.nim:255.  Raises when there is no B200: there is no CPU fallback.
+proc newContext*(atlasSize = 1024, pixelScale = 1.0, pixelate = false, device = 0, rank = 0, nRanks = 1): CudaContext =
+  ## Mirrors `newContext` of glcontext.nim:255 (`pixelate` = GL_NEAREST magnification of atlas texels).
+  ## Raises when there is no B200: there is no CPU fallback.
   result = CudaContext()
   if fdc_create(result.h.addr, device.cint, atlasSize.cint, pixelScale.cfloat, rank.cint, nRanks.cint) != 0:
     raise newException(FigDrawError, "cuda backend: " & $fdc_last_error(FdcCtx(nil)))
+  if pixelate: discard fdc_set_pixelate(result.h, 1)
   result.entries = initTable[Hash, Rect]()
   result.atlasEntryMeta = initTable[Hash, figbackend.AtlasEntryMeta]()
   result.ensureImageMessageSubscription()
@@ -313,3 +345,31 @@ proc renderFrameNative*(ctx: CudaContext, scene: var FdcScene, frameSize: Vec2, 
   var rgba = [clearColor.r.cfloat, clearColor.g.cfloat, clearColor.b.cfloat, clearColor.a.cfloat]
   ctx.ck fdc_render_frame(ctx.h, scene.addr, figUiScale().cfloat, frameSize.x.cfloat, frameSize.y.cfloat, clearMain.cint,
                           rgba[0].addr)
+
+
+# ---- round-2 additions: optional fast paths a maintainer can adopt one by one ------------------------------------------
+
+proc exportFramebuffer*(ctx: CudaContext, size: Vec2): tuple[fd: cint, bytes: int] =
+  ## Present without `readPixels`: import `fd` once with Vulkan (OPAQUE_FD) / GL (EXT_memory_object_fd) / CUDA and sample
+  ## the RGBA8 rows (pitch = width * 4) after every `endFrame`.  Replaces the glReadPixels path of glcontext.nim:2094-2135
+  ## for a presenter on the same machine.
+  var bytes: csize_t
+  ctx.ck fdc_export_framebuffer(ctx.h, size.x.cint, size.y.cint, result.fd.addr, bytes.addr)
+  result.bytes = bytes.int
+
+proc replayFrame*(ctx: CudaContext) =
+  ## Re-render the recorded frame unchanged (one CUDA-graph launch): what `renderFrame` amounts to when the `Renders`
+  ## did not change since the previous frame.
+  ctx.ck fdc_replay_frame(ctx.h)
+
+proc generateGlyphs*(ctx: CudaContext, jobs: openArray[FdcGlyphJob], segs: openArray[FdcOutlineSeg], lcd: bool) =
+  ## GPU replacement for pixie_raster.nim:45-95 (`generateGlyphImage` + `putImage`): outlines in, atlas texels out.
+  ## The caller fills `segs` from `typeface.getGlyphPath(rune)` scaled to the bitmap (y down).  Parity unpinned: the
+  ## anti-aliasing is exact-area, not pixie's.
+  var rebuilt: cint
+  ctx.ck fdc_rasterize_glyphs(ctx.h, jobs[0].unsafeAddr, jobs.len.csize_t, segs[0].unsafeAddr, segs.len.csize_t,
+                              lcd.cint, rebuilt.addr)
+  if rebuilt != 0:
+    ctx.entries.clear()
+    ctx.atlasEntryMeta.clear()
+    ctx.noteAtlasRebuilt()

@@ -524,15 +524,29 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
             extra_ctx.append((c2, o2, k2))
         depth = len(ring)
 
+        # FDC_E2E_ASYNC_READ=1 queues every read-back right behind its frame (fdc_read_pixels_async).  Measured slower on
+        # this platform (0.97 vs 0.85 ms per 4K frame, same box): the device-to-host copy then runs against the next
+        # frames' uploads the whole time, and the PCIe link does worse in both directions at once than taking turns.
+        async_read = os.environ.get("FDC_E2E_ASYNC_READ", "0") != "0"
+
+        def queue_frame(slot):
+            # records up, kernels, and the read-back of this rank's band queued right behind them (fdc_read_pixels_async):
+            # the device-to-host copy starts the moment the frame is finished, not when the host gets round to asking
+            submit(slot[0], slot[1])
+            if async_read:
+                slot[0].readPixelsAsync(slot[2][y0b:y1b], (0, y0b, W, y1b - y0b))
+
         def pipelined(n):
             for k in range(min(depth - 1, n)):
-                submit(ring[k % depth][0], ring[k % depth][1])
+                queue_frame(ring[k % depth])
             for k in range(n):
                 if k + depth - 1 < n:
-                    nxt = ring[(k + depth - 1) % depth]
-                    submit(nxt[0], nxt[1])
+                    queue_frame(ring[(k + depth - 1) % depth])
                 cur = ring[k % depth]
-                cur[0].readPixels((0, y0b, W, y1b - y0b), out=cur[2][y0b:y1b])  # every rank reads its own band back
+                if async_read:
+                    cur[0].sync()  # frame k's pixels are in host memory
+                else:
+                    cur[0].readPixels((0, y0b, W, y1b - y0b), out=cur[2][y0b:y1b])
 
         for c2, prep2, _o in ring[1:]:  # size the new contexts' buffers (a bin-list overflow re-runs on every rank)
             submit(c2, prep2)

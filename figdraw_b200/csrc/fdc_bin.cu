@@ -557,20 +557,19 @@ __global__ void __launch_bounds__(128, FDC_SETUP_MIN_BLOCKS) prim_setup_kernel(S
   __shared__ uint32_t s_draw[128][33];
   __shared__ uint32_t s_keep[128];
   __shared__ uint32_t s_nkeep;
-  __shared__ int s_run[3];  // runs of the CTA's first and last record; 1 when all of them arrived as compact records
   const uint32_t first = blockIdx.x * 128u;
   const uint32_t n_here = min(128u, a.count - first);
-  if (threadIdx.x == 0) {
-    const int lo = find_run(a.runs, a.n_runs, a.first + first);
-    const int hi = find_run_in(a.runs, lo, a.n_runs - 1, a.first + first + n_here - 1u);
-    int all_compact = 1;
-    for (int r = lo; r <= hi; r++) all_compact &= (int)a.runs[r].compact;
-    s_run[0] = lo; s_run[1] = hi; s_run[2] = all_compact;
-    if (kBanded) s_nkeep = 0;
+  // Runs of the CTA's first and last record (most CTAs sit inside one run), found by every thread for itself: the
+  // loads are uniform, so this costs one broadcast per step and saves the barrier a single searching thread needed.
+  const int run_lo = find_run(a.runs, a.n_runs, a.first + first);
+  const int run_hi = find_run_in(a.runs, run_lo, a.n_runs - 1, a.first + first + n_here - 1u);
+  bool all_compact = true;
+  for (int r = run_lo; r <= run_hi; r++) all_compact = all_compact && a.runs[r].compact != 0;
+  if (kBanded) {
+    if (threadIdx.x == 0) s_nkeep = 0;
+    __syncthreads();
   }
-  __syncthreads();
-  const int run_lo = s_run[0], run_hi = s_run[1];
-  if (!s_run[2]) {  // compact runs have no fdc_call records to stage (their slots in `draws` are unused)
+  if (!all_compact) {  // compact runs have no fdc_call records to stage (their slots in `draws` are unused)
     const uint4* src = reinterpret_cast<const uint4*>(a.draws + a.first + first);
     for (uint32_t k = threadIdx.x; k < n_here * 8u; k += 128u) {
       const uint4 v = __ldg(src + k);
@@ -658,6 +657,9 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 // pairs is spread over all warps instead of serialising one.  Counting is a shared-memory histogram; the stable rank
 // of a pair inside a round is popc(match_any(bin) & lower lanes); rounds and warps are ordered by running offsets
 // kept per (bin, warp).  Cost follows the number of pairs -- a band of an 8-GPU partition has 1/8 of them.
+#ifndef FDC_COARSE_FUSED
+#define FDC_COARSE_FUSED 1
+#endif
 constexpr int kSlots = 1024;  // coarse bins one CTA handles: a range of whole bin rows
 constexpr int kWarps = kChunk / 32;
 
@@ -809,6 +811,106 @@ __global__ void __launch_bounds__(kChunk) coarse_scatter_kernel(const PrimBin* _
   }
 }
 
+// ---- coarse level as ONE kernel (FDC_COARSE_FUSED, default): count, place and scatter in the same CTA.
+// The three-kernel form above needs a grid-wide scan between counting and scattering only because every bin's list is
+// contiguous.  Nothing requires that: the fine binner reads a bin's entries in CHUNK order, so a bin's list may as well
+// be one segment per chunk, anywhere in the coarse list, as long as a table says where.  A CTA counts its chunk's pairs
+// per bin, scans its own bins, reserves its region of the list with one atomicAdd (placement is not observable, order
+// is: segments are read in chunk order and written in primitive order), writes seg[bin][chunk] = (start, count) and
+// scatters.  Two launches and a 1 MB round trip fewer; the fine binner maps "entry k of the bin" to (chunk, offset)
+// with a binary search over the scanned counts of its bin's row of the table.
+__global__ void __launch_bounds__(kChunk) coarse_pairs_kernel(const PrimBin* __restrict__ prims, uint32_t n, FrameView f, int rows_per_cta,
+                                                              uint2* __restrict__ seg, uint32_t* __restrict__ coarse_list,
+                                                              uint32_t coarse_cap, uint32_t* __restrict__ counters) {
+  __shared__ uint32_t s_pos[kWarps / 2][kSlots];  // as in coarse_scatter_kernel
+  __shared__ uint32_t s_gbase[kSlots];
+  __shared__ uint32_t s_excl[kChunk], s_rect[kChunk], s_wtot[kWarps];
+  __shared__ uint32_t s_region;
+  const uint32_t chunk = blockIdx.x;
+  const int row0 = blockIdx.y * rows_per_cta, row1 = min(row0 + rows_per_cta, f.cby);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int used = (row1 - row0) * f.cbx;
+  const uint32_t rect = coarse_rect(prims, chunk * kChunk + threadIdx.x, n, f);
+  for (int k = 0; k < kWarps / 2; k++)
+    for (int sl = threadIdx.x; sl < used; sl += blockDim.x) s_pos[k][sl] = 0;
+  const ChunkPairs cp = chunk_pairs(rect, row0, row1, s_excl, s_rect, s_wtot);
+  const int word = warp >> 1, shift = (warp & 1) * 16;
+  for (uint32_t base = cp.lo; base < cp.hi; base += 32) {
+    const uint32_t p = base + lane;
+    if (p < cp.hi) {
+      int owner, bx, by;
+      chunk_pair(cp, p, owner, bx, by);
+      atomicAdd(&s_pos[word][(by - row0) * f.cbx + bx], 1u << shift);
+    }
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t at = cp.total ? atomicAdd(&counters[kCntCoarseTotal], cp.total) : 0u;
+    if (cp.total) atomicMax(&counters[kCntMaxCoarse], at + cp.total);  // the last reservation's end = pairs of the segment
+    if (at + cp.total > coarse_cap) { atomicOr(&counters[kCntOverflow], 1u); atomicOr(&counters[kCntStickyOverflow], 1u); }
+    s_region = at;
+  }
+  __syncthreads();
+  for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {  // counts -> exclusive prefix over the warps; bin total
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < kWarps / 2; k++) {
+      const uint32_t v = s_pos[k][sl];
+      const uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+      s_pos[k][sl] = run | ((run + lo) << 16);
+      run += lo + hi;
+    }
+    s_gbase[sl] = run;
+  }
+  __syncthreads();
+  // exclusive scan over the CTA's bins: thread t owns slots 2t and 2t + 1 (kSlots = 2 * kChunk)
+  static_assert(kSlots == 2 * kChunk, "one pair of bin slots per thread");
+  const int sl0 = 2 * (int)threadIdx.x;
+  const uint32_t c0 = sl0 < used ? s_gbase[sl0] : 0u, c1 = sl0 + 1 < used ? s_gbase[sl0 + 1] : 0u;
+  uint32_t incl = c0 + c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_wtot[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0;
+#pragma unroll
+  for (int j = 0; j < kWarps; j++)
+    if (j < warp) wbase += s_wtot[j];
+  const uint32_t region = s_region;
+  const bool fits = region + cp.total <= coarse_cap;
+  const uint32_t e0 = region + wbase + incl - c0 - c1, e1 = e0 + c0;
+  const size_t n_chunks = gridDim.x;
+  if (sl0 < used) {
+    s_gbase[sl0] = e0;
+    seg[(size_t)(row0 * f.cbx + sl0) * n_chunks + chunk] = make_uint2(e0, fits ? c0 : 0u);
+  }
+  if (sl0 + 1 < used) {
+    s_gbase[sl0 + 1] = e1;
+    seg[(size_t)(row0 * f.cbx + sl0 + 1) * n_chunks + chunk] = make_uint2(e1, fits ? c1 : 0u);
+  }
+  __syncthreads();
+  if (!fits) return;  // overflow: host regrows and re-runs the frame
+  const uint32_t first = chunk * kChunk;
+  for (uint32_t base = cp.lo; base < cp.hi; base += 32) {
+    const uint32_t p = base + lane;
+    const bool active = p < cp.hi;
+    int owner = 0, bx = 0, by = row0;
+    if (active) chunk_pair(cp, p, owner, bx, by);
+    const int sl = (by - row0) * f.cbx + bx;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, active ? (uint32_t)sl : (0x80000000u | (uint32_t)lane));
+    if (active) {
+      const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+      const uint32_t off = (s_pos[word][sl] >> shift) & 0xFFFFu;
+      coarse_list[s_gbase[sl] + off + rank] = first + (uint32_t)owner;
+    }
+    __syncwarp();
+    if (active && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&s_pos[word][sl], (uint32_t)__popc(peers) << shift);
+    __syncwarp();
+  }
+}
+
 // Exclusive scan over chunks for every bin (one warp per bin), then -- in the last CTA to finish -- the scan over
 // bins that yields cbin_start.  counters[3] is the completion ticket.
 __global__ void __launch_bounds__(256) coarse_scan_kernel(uint32_t* __restrict__ chunk_counts, int n_chunks, int n_bins,
@@ -889,6 +991,7 @@ __global__ void __launch_bounds__(256) coarse_scan_kernel(uint32_t* __restrict__
 // "bbox overlaps" and "inside the inner rect" bits, so the shading warps never touch the primitive for culling.
 constexpr int kStage = 1024;  // = 4 entries per thread of a 256-thread CTA
 static_assert(kTileW == 16 && kTileH == 16 && kCoarse == 8, "fine_bin_kernel shifts assume 16x16 tiles, 8x8 tiles per bin");
+static_assert(TE_OV_SHIFT == 0 && TE_FULL_SHIFT == 8, "fine_bin_kernel builds the overlap and inner-rect bytes as one 16-bit value");
 
 // bits [a..b] of a 32-bit word (empty when b < a)
 __device__ __forceinline__ uint32_t bit_range(int a, int b) {
@@ -940,8 +1043,19 @@ __device__ __forceinline__ uint32_t spread_nibble_to_bytes(uint32_t r) {
 }
 
 // Everything the shade kernel needs per (tile, primitive), derived once per staged coarse entry.
+// four nibbles of a 16-bit value -> the low nibbles of four bytes
+__device__ __forceinline__ uint32_t nibbles_to_bytes(uint32_t x) {
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  return (x | (x << 4)) & 0x0F0F0F0Fu;
+}
+// four bit pairs of an 8-bit value -> bits 0..1 of four bytes
+__device__ __forceinline__ uint32_t pairs_to_bytes(uint32_t x) {
+  x = (x | (x << 12)) & 0x000F000Fu;
+  return (x | (x << 6)) & 0x03030303u;
+}
+
 __device__ __forceinline__ void stage_entry(uint32_t k, uint32_t pid, const int4& q6, const int2& ir, int px0, int py0, const FrameView& f,
-                                            uint32_t* s_pid, uint32_t* s_cols, uint32_t* s_rows_ov, uint32_t* s_rows_full,
+                                            uint32_t* s_pid, uint32_t* s_rm0, uint32_t* s_rm1, uint32_t* s_cm0, uint32_t* s_cm1,
                                             uint32_t* s_info, uint32_t* s_lo, uint32_t* s_hi) {
   const uint32_t fl = (uint32_t)q6.z;
   const int bx0 = (int16_t)(q6.x & 0xFFFF), by0 = (int16_t)(q6.x >> 16), bx1 = (int16_t)(q6.y & 0xFFFF), by1 = (int16_t)(q6.y >> 16);
@@ -969,17 +1083,26 @@ __device__ __forceinline__ void stage_entry(uint32_t k, uint32_t pid, const int4
   if (fl & PF_MASK_BEGIN) info |= kInfoBegin;
   const uint32_t tr = nibbles_nonzero(rows_ov), tc = pairs_nonzero(cols & 0xFFFFu);
   s_pid[k] = pid;
-  s_cols[k] = cols;
-  s_rows_ov[k] = rows_ov;
-  s_rows_full[k] = rows_full;
+  // What the write loop needs per (entry, tile), pre-packed so that a tile's share is one byte of one word:
+  //   row words (tile rows 0-3 / 4-7): byte i = overlap bits of the tile row's four block rows | inner-rect bits << 4
+  //   column words (tile columns 0-3 / 4-7): byte i = overlap bits of the tile column's two block columns | inner bits << 4
+  s_rm0[k] = nibbles_to_bytes(rows_ov & 0xFFFFu) | (nibbles_to_bytes(rows_full & 0xFFFFu) << 4);
+  s_rm1[k] = nibbles_to_bytes(rows_ov >> 16) | (nibbles_to_bytes(rows_full >> 16) << 4);
+  s_cm0[k] = pairs_to_bytes(cols & 0xFFu) | (pairs_to_bytes((cols >> 16) & 0xFFu) << 4);
+  s_cm1[k] = pairs_to_bytes((cols >> 8) & 0xFFu) | (pairs_to_bytes(cols >> 24) << 4);
   s_info[k] = info;
   s_lo[k] = tc * spread_nibble_to_bytes(tr & 15u);
   s_hi[k] = tc * spread_nibble_to_bytes(tr >> 4);
 }
 
 constexpr int kGroups = kStage / 32;
+constexpr int kSegBlock = 1024;  // chunks whose segments of a bin are addressed at a time (= 512 k primitives)
+static_assert(kGroups * 64 == 2 * kSegBlock, "segment table block and s_gpos share storage");
 #ifndef FDC_DIRECT_FINE_LIMIT
 #define FDC_DIRECT_FINE_LIMIT 262144
+#endif
+#ifndef FDC_FINE_SPLIT_BIG
+#define FDC_FINE_SPLIT_BIG 0
 #endif
 #ifndef FDC_FINE_SPLIT_BINS
 #define FDC_FINE_SPLIT_BINS 296
@@ -993,22 +1116,30 @@ constexpr size_t kDirectFineLimit = FDC_DIRECT_FINE_LIMIT;  // primitives x coar
 // a popc, the emission order is the order of the set bits.  (Before: warp w owned tile row w and every warp walked
 // every entry with one ballot per tile column -- 8x the instructions for the same lists; profiles/r01_binning.md.)
 __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict__ prims, FrameView f,
-                                                       const uint32_t* __restrict__ cbin_start,
-                                                       const uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
+                                                       const uint32_t* __restrict__ cbin_start, const uint2* __restrict__ seg,
+                                                       int n_chunks, const uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
                                                        uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile_count,
                                                        TileEntry* __restrict__ tile_list, uint32_t tile_cap,
-                                                       uint32_t* __restrict__ counters, uint32_t n_direct) {
+                                                       uint32_t* __restrict__ counters, uint32_t n_direct, int split_big) {
   // n_direct != 0: small scene, no coarse pass was run -- every bin stages primitives 0..n_direct-1 themselves (those
   // that miss the bin get an empty tile mask); otherwise the bin's coarse list.
   // per staged coarse entry, computed once: 16 block columns (8 px) and 32 block rows (4 px) of this 128x128-px bin
   __shared__ uint32_t s_pid[kStage];
-  __shared__ uint32_t s_cols[kStage];     // overlap bits 0..15 | covered-by-inner bits 16..31
-  __shared__ uint32_t s_rows_ov[kStage];
-  __shared__ uint32_t s_rows_full[kStage];
+  __shared__ uint32_t s_rm0[kStage], s_rm1[kStage];  // block-row bits per tile row (stage_entry)
+  __shared__ uint32_t s_cm0[kStage], s_cm1[kStage];  // block-column bits per tile column
   __shared__ uint32_t s_info[kStage];
-  __shared__ uint32_t s_lo[kStage], s_hi[kStage];  // tile-hit masks: tile rows 0-3 / 4-7, bit = row*8 + column
+  // tile-hit masks: tile rows 0-3 / 4-7, bit = row*8 + column.  Staged per entry; the counting step replaces every group
+  // of 32 words by its transpose (word t of the group = the group's entries that hit tile t), which the write loop reads.
+  __shared__ uint32_t s_lo[kStage], s_hi[kStage];
   __shared__ uint8_t s_gcnt[kGroups][64];          // entries of group g in tile t
-  __shared__ uint32_t s_gpos[kGroups][64];         // where group g's entries of tile t go in the tile list
+  // s_gpos: where group g's entries of tile t go in the tile list (written after a stage is counted, read by the write
+  // loop).  The same 8 KB hold, while a stage is being gathered, the bin's row of the segment table for up to kSegBlock
+  // chunks: scanned counts and segment starts (coarse_pairs_kernel).
+  __shared__ union {
+    uint32_t gpos[kGroups][64];
+    struct { uint32_t excl[kSegBlock]; uint32_t start[kSegBlock]; } seg;
+  } s_u;
+  __shared__ uint32_t s_wsum[8];
   __shared__ uint32_t s_run[64];                   // pass 0: running tile counts; pass 1: write cursors
   __shared__ uint32_t s_base[64];
   __shared__ uint32_t s_cls[64];                   // != 0: the tile holds something the shade kernel's lean loop cannot take
@@ -1016,15 +1147,27 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
   if (!n_direct && counters[kCntCoarseTotal] > coarse_cap) return;
   const int b = blockIdx.x;
   const int cbx_i = b % f.cbx, cby_i = b / f.cbx;
-  const uint32_t begin = n_direct ? 0u : cbin_start[b], end = n_direct ? n_direct : cbin_start[b + 1];
+  // Where the bin's entries come from: primitives 0..n_direct-1 themselves, one contiguous slice of the coarse list
+  // (three-kernel coarse pass), or one segment per chunk (coarse_pairs_kernel), addressed kSegBlock chunks at a time.
+  const bool use_seg = !n_direct && seg != nullptr;
+  const uint32_t begin = (n_direct || use_seg) ? 0u : cbin_start[b];
+  const uint2* seg_row = use_seg ? seg + (size_t)b * (size_t)n_chunks : nullptr;
+  const int n_blocks = use_seg ? (n_chunks + kSegBlock - 1) / kSegBlock : 1;
+  uint32_t blk_total = n_direct ? n_direct : (use_seg ? 0u : cbin_start[b + 1] - begin);  // entries of the current block
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_x0 = cbx_i * kCoarse, tile_y0 = f.cty0 + cby_i * kCoarse;
   const int px0 = tile_x0 * kTileW, py0 = tile_y0 * kTileH;
-  const bool single = end - begin <= (uint32_t)kStage;
+  bool single = !use_seg && blk_total <= (uint32_t)kStage;  // the whole bin fits one stage: pass 1 reuses what pass 0 staged
   if (threadIdx.x < 64) { s_run[threadIdx.x] = 0; s_cls[threadIdx.x] = 0; }
   // Few bins (a band of a multi-GPU partition, a small frame) leave most SMs idle with one CTA per bin: the launch then
   // has two CTAs per bin, each building the lists of one half of the bin's tiles (tile rows 0-3 / 4-7).
-  const bool do_lo = gridDim.y == 1 || blockIdx.y == 0, do_hi = gridDim.y == 1 || blockIdx.y == 1;
+  // With many bins (split_big, grid.y = 2 as well) only the bins that need more than one stage are shared by two CTAs
+  // -- they are the launch's critical path, each stage is gathered twice -- and the second CTA of any other bin leaves.
+  bool do_lo = gridDim.y == 1 || blockIdx.y == 0, do_hi = gridDim.y == 1 || blockIdx.y == 1;
+  if (split_big && !use_seg && single) {
+    if (blockIdx.y == 1) return;
+    do_lo = do_hi = true;
+  }
 
   for (int pass = 0; pass < 2; pass++) {
     if (pass == 1) {
@@ -1067,11 +1210,56 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
       __syncthreads();
       if (threadIdx.x < 64) s_run[threadIdx.x] = alloc + s_base[threadIdx.x];
     }
-    for (uint32_t s0 = begin; s0 < end; s0 += kStage) {
-      const uint32_t ns = min((uint32_t)kStage, end - s0);
-      const int n_groups = (int)((ns + 31u) >> 5);
+    for (int cb = 0; cb < n_blocks; cb++)
+    for (uint32_t s0 = 0; s0 == 0 || s0 < blk_total; s0 += kStage) {
       if (pass == 0 || !single) {
         __syncthreads();  // previous stage fully consumed
+        if (use_seg && (pass == 1 || s0 == 0)) {
+          // (pass 1 overwrote the table with write positions: every stage loads it again)
+          const int c0 = cb * kSegBlock, n_seg = min(kSegBlock, n_chunks - c0);
+#pragma unroll
+          for (int j = 0; j < kSegBlock / 256; j++) {
+            const int idx = (int)threadIdx.x + j * 256;
+            const uint2 v = idx < n_seg ? __ldg(&seg_row[c0 + idx]) : make_uint2(0u, 0u);
+            s_u.seg.start[idx] = v.x;
+            s_u.seg.excl[idx] = v.y;
+          }
+          __syncthreads();
+          uint32_t cnt[kSegBlock / 256], sum = 0;
+#pragma unroll
+          for (int j = 0; j < kSegBlock / 256; j++) { cnt[j] = s_u.seg.excl[threadIdx.x * (kSegBlock / 256) + j]; sum += cnt[j]; }
+          uint32_t incl = sum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          if (lane == 31) s_wsum[warp] = incl;
+          __syncthreads();
+          uint32_t run = incl - sum, total = 0;
+#pragma unroll
+          for (int w = 0; w < 8; w++) {
+            const uint32_t t = s_wsum[w];
+            if (w < warp) run += t;
+            total += t;
+          }
+#pragma unroll
+          for (int j = 0; j < kSegBlock / 256; j++) { s_u.seg.excl[threadIdx.x * (kSegBlock / 256) + j] = run; run += cnt[j]; }
+          blk_total = total;
+          if (pass == 0 && cb == 0 && s0 == 0) {
+            single = n_blocks == 1 && total <= (uint32_t)kStage;
+            if (split_big && single) {
+              if (blockIdx.y == 1) return;
+              do_lo = do_hi = true;
+            }
+          }
+          __syncthreads();
+        }
+      }
+      if (s0 >= blk_total) break;  // (an empty block)
+      const uint32_t ns = min((uint32_t)kStage, blk_total - s0);
+      const int n_groups = (int)((ns + 31u) >> 5);
+      if (pass == 0 || !single) {
         // Four entries per thread with the three dependent gathers (list -> bbox -> inner rect) issued level by level,
         // so a stage costs three memory latencies instead of twelve.
         {
@@ -1081,7 +1269,19 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             const uint32_t k = threadIdx.x + j * 256u;
-            pid[j] = k < ns ? (n_direct ? s0 + k : __ldg(&coarse_list[s0 + k])) : 0xFFFFFFFFu;
+            if (k >= ns) pid[j] = 0xFFFFFFFFu;
+            else if (n_direct) pid[j] = s0 + k;
+            else if (!use_seg) pid[j] = __ldg(&coarse_list[begin + s0 + k]);
+            else {
+              // entry q of the block -> its chunk: the last chunk whose scanned count is <= q (empty chunks tie with
+              // their successor and lose)
+              const uint32_t q = s0 + k;
+              int o = 0;
+#pragma unroll
+              for (int step = kSegBlock / 2; step >= 1; step >>= 1)
+                if (s_u.seg.excl[o + step] <= q) o += step;
+              pid[j] = __ldg(&coarse_list[s_u.seg.start[o] + (q - s_u.seg.excl[o])]);
+            }
           }
 #pragma unroll
           for (int j = 0; j < 4; j++)
@@ -1094,7 +1294,7 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
           for (int j = 0; j < 4; j++) {
             const uint32_t k = threadIdx.x + j * 256u;
             if (k >= ns) break;
-            stage_entry(k, pid[j], q6[j], ir[j], px0, py0, f, s_pid, s_cols, s_rows_ov, s_rows_full, s_info, s_lo, s_hi);
+            stage_entry(k, pid[j], q6[j], ir[j], px0, py0, f, s_pid, s_rm0, s_rm1, s_cm0, s_cm1, s_info, s_lo, s_hi);
           }
         }
         __syncthreads();
@@ -1105,6 +1305,8 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
           const uint32_t t_lo = do_lo ? transpose32(lo, lane) : 0u, t_hi = do_hi ? transpose32(hi, lane) : 0u;
           s_gcnt[g][lane] = (uint8_t)__popc(t_lo);
           s_gcnt[g][32 + lane] = (uint8_t)__popc(t_hi);
+          s_lo[k] = t_lo;  // (own slot: read above by this thread only)
+          s_hi[k] = t_hi;
           // tile class: anything but unmasked fast content sends the whole tile to the shade kernel's full loop
           const uint32_t inf = k < ns ? s_info[k] : TE_FAST;
           const bool not_lean = !(inf & TE_FAST) || (inf & ((15u << TE_DEPTH_SHIFT) | TE_RECTMASK | TE_MASKW | TE_MASKB)) != 0u;
@@ -1119,34 +1321,41 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
         const int t = threadIdx.x;
         uint32_t run = s_run[t];
         for (int g = 0; g < n_groups; g++) {
-          if (pass == 1) s_gpos[g][t] = run;
+          if (pass == 1) s_u.gpos[g][t] = run;
           run += s_gcnt[g][t];
         }
         s_run[t] = run;
       }
       if (pass == 0) continue;
       __syncthreads();
+      // The write loop.  Lane t owns tiles t and 32 + t; its share of an entry is one byte of a row word and one byte
+      // of a column word: overlap and inner-rect bits travel together as two bytes of one register (TileEntry bits 0..15).
+      const uint32_t sel_r = 0x4440u | (uint32_t)((lane >> 3) & 3), sel_c = 0x4440u | (uint32_t)(lane & 3);
+      const uint32_t* s_cm = (lane & 4) ? s_cm1 : s_cm0;
       for (int g = warp; g < n_groups; g += 8) {
         const uint32_t k = (uint32_t)g * 32u + lane;
-        const uint32_t lo = k < ns ? s_lo[k] : 0u, hi = k < ns ? s_hi[k] : 0u;
 #pragma unroll
         for (int half = 0; half < 2; half++) {
           if (half == 0 ? !do_lo : !do_hi) continue;
-          uint32_t m = transpose32(half ? hi : lo, lane);  // entries of this group that hit tile t
-          const int t = half * 32 + lane, r = t >> 3, c = t & 7;
-          uint32_t pos = s_gpos[g][t];
+          uint32_t m = half ? s_hi[k] : s_lo[k];  // entries of this group that hit my tile (transposed while counting)
+          const uint32_t* s_rm = half ? s_rm1 : s_rm0;
+          uint32_t pos = s_u.gpos[g][half * 32 + lane];
           while (m) {
             const int e = __ffs(m) - 1;
             m &= m - 1;
             const uint32_t ke = (uint32_t)g * 32u + (uint32_t)e;
-            const uint32_t cols = s_cols[ke], info = s_info[ke];
-            uint32_t ov = spread_rows((s_rows_ov[ke] >> (4 * r)) & 15u) & spread_cols((cols >> (2 * c)) & 3u);
-            uint32_t full = spread_rows((s_rows_full[ke] >> (4 * r)) & 15u) & spread_cols((cols >> (16 + 2 * c)) & 3u);
-            if (info & kInfoEmptyInner) { ov &= ~full; full = 0; }  // inside an AnnularAA stroke: nothing to shade
-            if (info & kInfoBegin) ov = 0xFFu;                      // PF_MASK_BEGIN: every block resets the level
+            const uint32_t info = s_info[ke];
+            uint32_t rb = __byte_perm(s_rm[ke], 0u, sel_r);          // my tile row: overlap nibble | inner nibble << 4
+            rb = (rb | (rb << 4)) & 0x0F0Fu;                          // -> one nibble per byte
+            rb = (rb | (rb << 2)) & 0x3333u;                          // each row bit doubled (block = row * 2 + column),
+            rb = ((rb | (rb << 1)) & 0x5555u) * 3u;                   //   both bytes at once
+            const uint32_t cb = __byte_perm(0xFFAA5500u, 0u, __byte_perm(s_cm[ke], 0u, sel_c));  // column pairs -> 0x55 / 0xAA patterns
+            uint32_t of = rb & cb;                                    // bits 0..7 overlap, 8..15 inside the inner rect
+            if (info & kInfoEmptyInner) of = of & ~(of >> 8) & 0xFFu;  // inside an AnnularAA stroke: nothing to shade
+            if (info & kInfoBegin) of |= 0xFFu;                        // PF_MASK_BEGIN: every block resets the level
             TileEntry te;
             te.pid = s_pid[ke];
-            te.info = (info & 0x3FFFFFFFu) | (ov << TE_OV_SHIFT) | (full << TE_FULL_SHIFT);
+            te.info = (info & 0x3FFFFFFFu) | of;
             tile_list[pos++] = te;
           }
         }
@@ -1175,23 +1384,32 @@ void launch_binning(const PrimBin* prims, uint32_t n_prims, const FrameView& f, 
   cudaMemsetAsync(b.counters, 0, sizeof(uint32_t) * kCntStickyOverflow, stream);
   if (n_prims == 0 || n_bins == 0) return;
   if ((size_t)n_prims * (size_t)n_bins <= (size_t)kDirectFineLimit) {
-    // Small scene: three launches of coarse binning cost more than letting every bin look at every primitive.
-    fine_bin_kernel<<<dim3(n_bins, n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(prims, f, b.cbin_start, b.coarse_list, b.coarse_cap,
-                                                                                    b.tile_start, b.tile_count, b.tile_list, b.tile_cap,
-                                                                                    b.counters, n_prims);
+    // Small scene: the launches of coarse binning cost more than letting every bin look at every primitive.
+    fine_bin_kernel<<<dim3(n_bins, n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(prims, f, b.cbin_start, nullptr, 0, b.coarse_list,
+                                                                                    b.coarse_cap, b.tile_start, b.tile_count, b.tile_list,
+                                                                                    b.tile_cap, b.counters, n_prims, 0);
     if (n_launches) *n_launches += 1;
     return;
   }
   const int rows_per_cta = max(1, kSlots / max(f.cbx, 1));  // whole bin rows, at most kSlots bins per CTA
   dim3 grid(n_chunks, (f.cby + rows_per_cta - 1) / rows_per_cta);
+#if FDC_COARSE_FUSED
+  uint2* seg = reinterpret_cast<uint2*>(b.chunk_counts);  // [bin][chunk] (start, count)
+  coarse_pairs_kernel<<<grid, kChunk, 0, stream>>>(prims, n_prims, f, rows_per_cta, seg, b.coarse_list, b.coarse_cap, b.counters);
+  fine_bin_kernel<<<dim3(n_bins, FDC_FINE_SPLIT_BIG || n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(
+      prims, f, b.cbin_start, seg, n_chunks, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count, b.tile_list, b.tile_cap, b.counters, 0u,
+      FDC_FINE_SPLIT_BIG && n_bins > kFineSplitBins);
+  if (n_launches) *n_launches += 2;
+#else
   coarse_count_kernel<<<grid, kChunk, 0, stream>>>(prims, n_prims, f, rows_per_cta, b.chunk_counts);
   coarse_scan_kernel<<<(n_bins + 7) / 8, 256, 0, stream>>>(b.chunk_counts, n_chunks, n_bins, b.cbin_start, b.coarse_cap, b.counters);
   coarse_scatter_kernel<<<grid, kChunk, 0, stream>>>(prims, n_prims, f, rows_per_cta, b.chunk_counts, b.cbin_start, b.coarse_list,
                                                      b.coarse_cap, b.counters);
-  fine_bin_kernel<<<dim3(n_bins, n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(prims, f, b.cbin_start, b.coarse_list, b.coarse_cap,
-                                                                                  b.tile_start, b.tile_count, b.tile_list, b.tile_cap,
-                                                                                  b.counters, 0u);
+  fine_bin_kernel<<<dim3(n_bins, FDC_FINE_SPLIT_BIG || n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(
+      prims, f, b.cbin_start, nullptr, 0, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count, b.tile_list, b.tile_cap, b.counters, 0u,
+      FDC_FINE_SPLIT_BIG && n_bins > kFineSplitBins);
   if (n_launches) *n_launches += 4;
+#endif
 }
 
 }  // namespace fdc

@@ -763,7 +763,7 @@ int ensure_bin_buffers(fdc_ctx* ctx, uint32_t max_prims) {
   const FrameView& f = ctx->frame;
   const size_t n_bins = (size_t)f.cbx * f.cby;
   const size_t n_chunks = (max_prims + kChunk - 1) / kChunk;
-  CK(ctx->d_chunk_counts.reserve(std::max<size_t>(1, n_chunks * n_bins)));
+  CK(ctx->d_chunk_counts.reserve(std::max<size_t>(2, 2 * n_chunks * n_bins)));  // (start, count) per (bin, chunk)
   CK(ctx->d_cbin_start.reserve(n_bins + 1));
   CK(ctx->d_tile_start.reserve((size_t)f.tiles_x * f.tiles_y));
   CK(ctx->d_tile_count.reserve((size_t)f.tiles_x * f.tiles_y));

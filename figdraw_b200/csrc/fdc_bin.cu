@@ -559,6 +559,8 @@ __global__ void __launch_bounds__(128, FDC_SETUP_MIN_BLOCKS) prim_setup_kernel(S
   __shared__ uint32_t s_nkeep;
   const uint32_t first = blockIdx.x * 128u;
   const uint32_t n_here = min(128u, a.count - first);
+  // the binning kernels that follow start from zeroed counters (this replaces a memset node per segment)
+  if (blockIdx.x == 0 && (int)threadIdx.x < a.zero_counters) a.counters[threadIdx.x] = 0u;
   // Runs of the CTA's first and last record (most CTAs sit inside one run), found by every thread for itself: the
   // loads are uniform, so this costs one broadcast per step and saves the barrier a single searching thread needed.
   const int run_lo = find_run(a.runs, a.n_runs, a.first + first);
@@ -1115,7 +1117,10 @@ constexpr size_t kDirectFineLimit = FDC_DIRECT_FINE_LIMIT;  // primitives x coar
 // warp turn "tiles per entry" into "entries per tile", and lane t then owns tiles t and 32+t of the bin: the count is
 // a popc, the emission order is the order of the set bits.  (Before: warp w owned tile row w and every warp walked
 // every entry with one ballot per tile column -- 8x the instructions for the same lists; profiles/r01_binning.md.)
-__global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict__ prims, FrameView f,
+#ifndef FDC_FINE_MIN_BLOCKS
+#define FDC_FINE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, FDC_FINE_MIN_BLOCKS) fine_bin_kernel(const PrimBin* __restrict__ prims, FrameView f,
                                                        const uint32_t* __restrict__ cbin_start, const uint2* __restrict__ seg,
                                                        int n_chunks, const uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
                                                        uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile_count,
@@ -1203,10 +1208,17 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
         if ((t & 31) == 0 && fullm) atomicAdd(&counters[kCntFullTiles], (uint32_t)__popc(fullm));
         if (in_band) {
           tile_start[ty * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : alloc + s_base[t];
+#ifdef FDC_FINE_EXP  // timing experiments only (tools/variants_cfg.sh): the tiles stay empty, the lists are not (all) written
+          tile_count[ty * f.tiles_x + tx] = 0u;
+#else
           tile_count[ty * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : (s_run[t] | (s_cls[t] ? kTileNeedsFullPath : 0u));
+#endif
         }
       }
       if (alloc == 0xFFFFFFFFu) return;
+#if defined(FDC_FINE_EXP) && FDC_FINE_EXP == 2
+      return;
+#endif
       __syncthreads();
       if (threadIdx.x < 64) s_run[threadIdx.x] = alloc + s_base[threadIdx.x];
     }
@@ -1332,6 +1344,9 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
       // of a column word: overlap and inner-rect bits travel together as two bytes of one register (TileEntry bits 0..15).
       const uint32_t sel_r = 0x4440u | (uint32_t)((lane >> 3) & 3), sel_c = 0x4440u | (uint32_t)(lane & 3);
       const uint32_t* s_cm = (lane & 4) ? s_cm1 : s_cm0;
+#ifndef FDC_FINE_PAIR
+#define FDC_FINE_PAIR 1
+#endif
       for (int g = warp; g < n_groups; g += 8) {
         const uint32_t k = (uint32_t)g * 32u + lane;
 #pragma unroll
@@ -1340,6 +1355,13 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
           uint32_t m = half ? s_hi[k] : s_lo[k];  // entries of this group that hit my tile (transposed while counting)
           const uint32_t* s_rm = half ? s_rm1 : s_rm0;
           uint32_t pos = s_u.gpos[g][half * 32 + lane];
+#if defined(FDC_FINE_EXP) && FDC_FINE_EXP == 1
+          m = 0;
+#endif
+#if FDC_FINE_PAIR
+          uint2 held = make_uint2(0u, 0u);  // an entry at an even position waiting for its neighbour: the two leave as 16 bytes
+          bool holding = false;
+#endif
           while (m) {
             const int e = __ffs(m) - 1;
             m &= m - 1;
@@ -1356,7 +1378,24 @@ __global__ void __launch_bounds__(256) fine_bin_kernel(const PrimBin* __restrict
             TileEntry te;
             te.pid = s_pid[ke];
             te.info = (info & 0x3FFFFFFFu) | of;
+#if defined(FDC_FINE_EXP) && FDC_FINE_EXP == 3  // everything but the stores (the sink keeps the arithmetic alive)
+            if (te.info == 0x12345678u && te.pid == 0x9ABCDEFu) tile_list[pos] = te;
+            pos++;
+#elif FDC_FINE_PAIR
+            // half as many store transactions: 8-byte entries written one by one are one partial 32-byte sector each
+            if (holding) {
+              *reinterpret_cast<uint4*>(&tile_list[pos - 1]) = make_uint4(held.x, held.y, te.pid, te.info);
+              holding = false;
+            } else if (!(pos & 1u) && m) {
+              held = make_uint2(te.pid, te.info);
+              holding = true;
+            } else {
+              tile_list[pos] = te;
+            }
+            pos++;
+#else
             tile_list[pos++] = te;
+#endif
           }
         }
       }
@@ -1380,9 +1419,14 @@ void launch_binning(const PrimBin* prims, uint32_t n_prims, const FrameView& f, 
   // tiles of the band start empty; per-segment counters: tile cursor, overflow flags, coarse total, scan ticket.
   // The per-FRAME words (kCntStickyOverflow ...) are zeroed once per frame by the caller, so an overflow in any segment
   // is still visible after later segments reset the per-segment words.
-  cudaMemsetAsync(b.tile_count + (size_t)f.ty0 * f.tiles_x, 0, sizeof(uint32_t) * (size_t)(f.ty1 - f.ty0) * f.tiles_x, stream);
-  cudaMemsetAsync(b.counters, 0, sizeof(uint32_t) * kCntStickyOverflow, stream);
-  if (n_prims == 0 || n_bins == 0) return;
+  if (n_prims == 0 || n_bins == 0) {
+    cudaMemsetAsync(b.tile_count + (size_t)f.ty0 * f.tiles_x, 0, sizeof(uint32_t) * (size_t)(f.ty1 - f.ty0) * f.tiles_x, stream);
+    cudaMemsetAsync(b.counters, 0, sizeof(uint32_t) * kCntStickyOverflow, stream);
+    return;
+  }
+  // Otherwise nothing to clear: the setup kernel of this segment zeroed the per-segment counters, and the fine binner
+  // writes start and count of EVERY tile of the band, empty ones included.  (After a list overflow it leaves them
+  // stale -- and every later kernel of the frame returns at once on the sticky flag.)
   if ((size_t)n_prims * (size_t)n_bins <= (size_t)kDirectFineLimit) {
     // Small scene: the launches of coarse binning cost more than letting every bin look at every primitive.
     fine_bin_kernel<<<dim3(n_bins, n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(prims, f, b.cbin_start, nullptr, 0, b.coarse_list,

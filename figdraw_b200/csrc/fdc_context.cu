@@ -805,6 +805,8 @@ SetupArgs setup_args(fdc_ctx* ctx, const Segment& s) {
   a.prim_call = ctx->d_prim_call.p + s.first;
   a.atlas = atlas_view(ctx);
   a.frame = ctx->frame;
+  a.counters = ctx->d_counters.p;
+  a.zero_counters = (int)kCntStickyOverflow;
   return a;
 }
 
@@ -871,7 +873,10 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
   }
   // Per-frame counters (sticky overflow flags, list-size maxima, entry total): zeroed once here; launch_binning resets
   // only the per-segment words, so an overflow in ANY segment is still visible when the host looks after the frame.
-  CK(cudaMemsetAsync(ctx->d_counters.p + kCntStickyOverflow, 0, sizeof(uint32_t) * (kNumCounters - kCntStickyOverflow), st));
+  // (a frame whose first segment has primitives lets that segment's setup kernel zero all the words instead)
+  const bool setup_zeroes_all = !ctx->segments.empty() && ctx->segments[0].count > 0;
+  if (!setup_zeroes_all)
+    CK(cudaMemsetAsync(ctx->d_counters.p + kCntStickyOverflow, 0, sizeof(uint32_t) * (kNumCounters - kCntStickyOverflow), st));
   ctx->frame_resolved = false;
   // A frame that blends over the previous pixels (no clearMain) in several segments cannot simply be re-run after an
   // overflow in a later segment -- the earlier segments would be composited twice.  Keep the pre-frame pixels.
@@ -918,7 +923,9 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
     const Segment& s = ctx->segments[si];
     {
       Timed t(ctx, 0);
-      launch_prim_setup(setup_args(ctx, s), st);
+      SetupArgs sargs = setup_args(ctx, s);
+      if (si == 0 && setup_zeroes_all) sargs.zero_counters = (int)kNumCounters;
+      launch_prim_setup(sargs, st);
       launches += s.count ? 1 : 0;
       launch_binning(ctx->d_prim_bins.p + s.first, s.count, ctx->frame, bin_buffers(ctx), st, &launches);
     }

@@ -20,6 +20,8 @@ struct SetupArgs {
   uint32_t* prim_call;    // [count] backend-call ordinal per primitive (debug bins)
   AtlasView atlas;
   FrameView frame;
+  uint32_t* counters;     // binning counters: the kernel zeroes the first `zero_counters` words for the binning that follows
+  int zero_counters;
 };
 void launch_prim_setup(const SetupArgs& a, cudaStream_t stream);
 

@@ -70,7 +70,7 @@ def workload_trace(name: str):
     return tr, WORKLOADS[name]
 
 
-def bench_config(name: str, trace, world: int, gather: str = "nccl") -> dict:
+def bench_config(name: str, trace, world: int, gather: str = "nccl", band_policy: str = "balanced") -> dict:
     """The `config` object of the JSON line -- ONE function for both arms, so `--impl reference` reports the very same
     object as the GPU arm it is compared with."""
     if world == 1:
@@ -85,6 +85,8 @@ def bench_config(name: str, trace, world: int, gather: str = "nccl") -> dict:
         part = f"{world} tile-row bands, finished band slices copied to the peers by the copy engines (NVLink)"
     else:
         part = f"{world} tile-row bands + NCCL all-gather"
+    if world > 1 and gather in ("mc", "auto", "symm-p2p"):
+        part += ("; bands of equal tile-entry cost (profile of the previous frame)" if band_policy == "balanced" else "; bands of equal height")
     return {"workload": WORKLOADS[name], "frame": [trace.width, trace.height], "primitives": int(trace.n_draws),
             "l2": "flushed between steps (256 MiB fill)", "partition": part,
             "replay": "one CUDA-graph launch per frame (setup, binning, shade, barriers captured once)"}
@@ -223,7 +225,7 @@ def run_reference(args, rank: int, out=sys.stdout):
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": METRIC, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": bench_config(name, trace, args.gpus, args.gather),
+            "config": bench_config(name, trace, args.gpus, args.gather, args.bands),
             "note": "restated-reference CPU rasteriser (oracle port of the GL path, OpenMP over 64-row strips), not llvmpipe; "
                     "whole frames, nothing extrapolated",
             "cpu_baseline": {"value": round(val, 3), "unit": METRIC, "cores": cores, "kind": "port", "sample": sample},
@@ -446,6 +448,15 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
     # first frame: uploads the recording, allocates everything; a bin-list overflow on ANY rank re-runs it on all
     submit(ctx, prepared)
     bands.resolve_across_ranks(ctx, world, dist)
+    # Bands of equal COST instead of equal height: the frame just rendered tells every rank how many tile entries each
+    # of its tile rows holds; the summed profile is split into `world` contiguous bands of equal cost and every rank
+    # adopts the same boundaries (fdc_get_tile_row_costs / fdc_set_band_tile_rows).  Only with a framebuffer the ranks
+    # share: an all-gather of equal slices does not apply to unequal bands.
+    band_bounds = None
+    if world > 1 and symm_t is not None and args.bands == "balanced" and not has_blur:
+        band_bounds = bands.rebalance_across_ranks(ctx, world, (W + 15) // 16, dist)
+        submit(ctx, prepared)
+        bands.resolve_across_ranks(ctx, world, dist)
     frame_e2e()
     launches_per_frame = int(ctx.frameStats().n_launches)
 
@@ -516,6 +527,8 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
             c2 = CudaContext(atlasSize=trace.atlas_size, device=env.local_rank, rank=rank, nRanks=world)
             if world > 1:
                 bind_symmetric(c2)  # its own shared framebuffer, flags and record exchange area
+                if band_bounds is not None:
+                    c2.setBandTileRows(band_bounds)
             for _i, key, img in trace.images:
                 c2.putImage(key, img)
             o2 = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
@@ -618,7 +631,7 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
         e2e_pipe_ms = e2e_pipe_max
     res = {"name": name, "trace": trace, "W": W, "H": H, "ms_step": ms_step, "e2e_ms": e2e_ms, "e2e_pipe_ms": e2e_pipe_ms,
            "depth": depth, "shade_ms": shade_ms, "bin_ms": bin_ms, "clocks": clocks, "launches_per_frame": launches_per_frame,
-           "n_tile_entries": int(stats.n_tile_entries), "h2d": int(prepared_upload_bytes(prepared)), "out_np": out_np,
+           "n_tile_entries": int(stats.n_tile_entries), "h2d": int(prepared_upload_bytes(prepared)), "out_np": out_np, "band_bounds": band_bounds,
            "sharded_upload": bool(world > 1 and symm_t is not None), "gpu_plain_ms": gpu_plain, "present_ms": present_ms, "present_ok": present_ok,
            "calls_np": calls_np, "gathered_ok": gathered_ok, "single_gpu_ms": single_gpu_ms, "use_p2p": use_p2p,
            "gather": gather_mode}
@@ -641,6 +654,8 @@ def main():
                          "(mc; needs torch symmetric memory), peer stores over IPC mappings (p2p), NCCL all-gather after the frame "
                          "(nccl), copy engines shipping band slices (ce); auto = mc when available, else nccl")
     ap.add_argument("--sub-bands", type=int, default=4)
+    ap.add_argument("--bands", default="balanced", choices=["balanced", "equal"],
+                    help="N > 1 with a shared framebuffer: bands of equal tile-entry cost (default) or of equal height")
     ap.add_argument("--records", default=None, choices=["compact", "full"],
                     help="e2e upload: 64-byte fdc_rect64 records for rounded rects with circular corners, or 128-byte fdc_call only")
     args = ap.parse_args()
@@ -712,7 +727,7 @@ def main():
         line = {"metric": METRIC, "value": round(value, 2), "unit": METRIC, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": bench_config(name, trace, world, r["gather"]),
+                "config": bench_config(name, trace, world, r["gather"], "balanced" if r.get("band_bounds") else "equal"),
                 "frames_per_s": round(1e3 / ms_step, 2),
                 "e2e": {"value": round(mpx / (e2e_best * 1e-3), 2), "unit": METRIC,
                         "ms_per_step": round(e2e_best, 4), "latency_ms": round(r["e2e_ms"], 4),
@@ -735,6 +750,8 @@ def main():
             line["single_gpu_same_workload"] = {"ms_per_step": round(r["single_gpu_ms"], 4),
                                                 "value": round(mpx / (r["single_gpu_ms"] * 1e-3), 2), "unit": METRIC,
                                                 "note": "rank 0's GPU alone on the same frame in the same process (no gather)"}
+        if r.get("band_bounds"):
+            line["band_tile_rows"] = r["band_bounds"]
         if extra_8k is not None:
             x = extra_8k
             mpx8 = x["W"] * x["H"] / 1e6
@@ -745,7 +762,7 @@ def main():
                                "shade_ms": round(x["shade_ms"], 4), "bin_ms": round(x["bin_ms"], 4),
                                "e2e_ms_per_step": round(x["e2e_pipe_ms"] or x["e2e_ms"], 4), "e2e_latency_ms": round(x["e2e_ms"], 4),
                                "h2d_bytes_per_step": x["h2d"],
-                               "gathered_frame_equals_single_gpu": x["gathered_ok"],
+                               "gathered_frame_equals_single_gpu": x["gathered_ok"], "band_tile_rows": x.get("band_bounds"),
                                "note": "BASELINE configs[4] (all sizes x2) on the same ranks; efficiency = single_gpu_ms / (n_gpus x ms_per_step)"}
         if world == 1 and name in ("cfg5_4k", "cfg5_8k"):
             line["native_frontend"] = native_frontend_probe(name, r["calls_np"])

@@ -196,7 +196,7 @@ EXPORTS = [
     "fdc_reset_image_atlas", "fdc_atlas_size", "fdc_atlas_packed_area",
     "fdc_mark_entry", "fdc_clear_font_glyphs", "fdc_clear_typeface_glyphs", "fdc_retain_owner", "fdc_release_owner",
     "fdc_get_atlas_usage", "fdc_set_atlas_replay", "fdc_rasterize_glyphs",
-    "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_stream", "fdc_set_peer_framebuffers", "fdc_bind_shared_framebuffer", "fdc_set_frame_barrier", "fdc_export_framebuffer", "fdc_set_peer_gather", "fdc_reserve_framebuffer", "fdc_framebuffer_ipc_handle", "fdc_open_peer_framebuffer",
+    "fdc_bind_framebuffer", "fdc_framebuffer_ptr", "fdc_band_rows", "fdc_get_tile_row_costs", "fdc_set_band_tile_rows", "fdc_stream", "fdc_set_peer_framebuffers", "fdc_bind_shared_framebuffer", "fdc_set_frame_barrier", "fdc_export_framebuffer", "fdc_set_peer_gather", "fdc_reserve_framebuffer", "fdc_framebuffer_ipc_handle", "fdc_open_peer_framebuffer",
     "fdc_get_frame_stats", "fdc_debug_bins", "fdc_debug_shade_stats",
     "fdc_flatten_renders", "fdc_render_frame",
 ]
@@ -291,6 +291,8 @@ def load_library() -> ctypes.CDLL:
     sig("fdc_bind_framebuffer", c.c_int, P, P)
     sig("fdc_framebuffer_ptr", P, P)
     sig("fdc_band_rows", c.c_int, P, c.POINTER(c.c_int), c.POINTER(c.c_int))
+    sig("fdc_get_tile_row_costs", c.c_int, P, c.POINTER(c.c_uint32), c.c_int, c.POINTER(c.c_int))
+    sig("fdc_set_band_tile_rows", c.c_int, P, c.POINTER(c.c_int), c.c_int)
     sig("fdc_stream", P, P)
     sig("fdc_set_peer_framebuffers", c.c_int, P, c.POINTER(P), c.c_int)
     sig("fdc_reserve_framebuffer", c.c_int, P, c.c_int, c.c_int)

@@ -61,3 +61,64 @@ def resolve_across_ranks(ctx, world: int, dist=None, group=None, max_rounds: int
             raise RuntimeError("bin lists still overflow after %d cross-rank retries" % rounds)
         ctx.retryFrame()
         rounds += 1
+
+
+def balance_rows(costs, world: int) -> List[int]:
+    """Contiguous partition of the tile rows into `world` bands that minimises the largest band cost.  Returns world + 1
+    boundaries (tile rows).  Every band gets at least one row while there are rows to give."""
+    c = [float(v) for v in costs]
+    n = len(c)
+    if world <= 1 or n == 0:
+        return [0] + [n] * max(world, 1)
+
+    def bands_needed(limit: float) -> int:
+        used, run = 1, 0.0
+        for v in c:
+            if run + v > limit and run > 0.0:
+                used, run = used + 1, 0.0
+            run += v
+        return used
+
+    lo, hi = max(c), sum(c)
+    for _ in range(48):  # smallest limit that `world` bands can meet
+        mid = 0.5 * (lo + hi)
+        if bands_needed(mid) <= world:
+            hi = mid
+        else:
+            lo = mid
+    bounds, run = [0], 0.0
+    for i, v in enumerate(c):
+        rows_left, bands_left = n - i, world - (len(bounds) - 1)
+        # start a new band when this row would break the limit -- or when the rows left are only just enough to give
+        # every remaining band one
+        if len(bounds) <= world - 1 and i > bounds[-1] and (run + v > hi * (1.0 + 1e-9) or rows_left < bands_left):
+            bounds.append(i)
+            run = 0.0
+        run += v
+    while len(bounds) < world:  # fewer rows than bands, or the limit left bands over: give the tail single rows / nothing
+        bounds.append(min(n, bounds[-1] + 1) if bounds[-1] < n and n - bounds[-1] > world - len(bounds) else n)
+    bounds.append(n)
+    return bounds
+
+
+def rebalance_across_ranks(ctx, world: int, tiles_x: int, dist=None, group=None, tile_cost: float = 3.0) -> List[int]:
+    """Choose bands from the tile-entry profile of the frame every rank has just rendered: sum the ranks' per-row entry
+    counts (each rank knows its own rows), add a constant per tile (clearing, copying a tile out costs about as much as
+    shading `tile_cost` entries), split into `world` contiguous bands of equal cost and hand the boundaries to the
+    context (fdc_set_band_tile_rows).  Every rank computes the same boundaries.  Returns them."""
+    import numpy as np
+
+    costs = np.asarray(ctx.tileRowCosts(), dtype=np.int64)
+    if world > 1:
+        import torch
+
+        if dist is None:
+            import torch.distributed as dist  # noqa: PLW0642
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(costs).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        costs = t.cpu().numpy()
+    bounds = balance_rows(costs.astype(np.float64) + tile_cost * float(tiles_x), world)
+    ctx.setBandTileRows(bounds)
+    return bounds

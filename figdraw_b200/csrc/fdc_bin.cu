@@ -561,6 +561,8 @@ __global__ void __launch_bounds__(128, FDC_SETUP_MIN_BLOCKS) prim_setup_kernel(S
   const uint32_t n_here = min(128u, a.count - first);
   // the binning kernels that follow start from zeroed counters (this replaces a memset node per segment)
   if (blockIdx.x == 0 && (int)threadIdx.x < a.zero_counters) a.counters[threadIdx.x] = 0u;
+  if (blockIdx.x == 0 && a.zero_counters == (int)kNumCounters)
+    for (int r = threadIdx.x; r < a.n_row_cost; r += 128) a.row_cost[r] = 0u;
   // Runs of the CTA's first and last record (most CTAs sit inside one run), found by every thread for itself: the
   // loads are uniform, so this costs one broadcast per step and saves the barrier a single searching thread needed.
   const int run_lo = find_run(a.runs, a.n_runs, a.first + first);
@@ -1125,7 +1127,8 @@ __global__ void __launch_bounds__(256, FDC_FINE_MIN_BLOCKS) fine_bin_kernel(cons
                                                        int n_chunks, const uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
                                                        uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile_count,
                                                        TileEntry* __restrict__ tile_list, uint32_t tile_cap,
-                                                       uint32_t* __restrict__ counters, uint32_t n_direct, int split_big) {
+                                                       uint32_t* __restrict__ counters, uint32_t* __restrict__ row_cost,
+                                                       uint32_t n_direct, int split_big) {
   // n_direct != 0: small scene, no coarse pass was run -- every bin stages primitives 0..n_direct-1 themselves (those
   // that miss the bin get an empty tile mask); otherwise the bin's coarse list.
   // per staged coarse entry, computed once: 16 block columns (8 px) and 32 block rows (4 px) of this 128x128-px bin
@@ -1206,6 +1209,13 @@ __global__ void __launch_bounds__(256, FDC_FINE_MIN_BLOCKS) fine_bin_kernel(cons
         // how many tiles need the shade kernel's full loop (its launch returns at once when there are none)
         const uint32_t fullm = __ballot_sync(0xFFFFFFFFu, in_band && alloc != 0xFFFFFFFFu && s_cls[t] != 0u && s_run[t] != 0u);
         if ((t & 31) == 0 && fullm) atomicAdd(&counters[kCntFullTiles], (uint32_t)__popc(fullm));
+        if (row_cost) {  // tile entries per tile row of the frame: what a host balances the bands of a partition with
+          uint32_t rsum = (in_band && alloc != 0xFFFFFFFFu) ? s_run[t] : 0u;
+          rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, 1);
+          rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, 2);
+          rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, 4);
+          if ((t & 7) == 0 && rsum) atomicAdd(&row_cost[ty], rsum);
+        }
         if (in_band) {
           tile_start[ty * f.tiles_x + tx] = alloc == 0xFFFFFFFFu ? 0u : alloc + s_base[t];
 #ifdef FDC_FINE_EXP  // timing experiments only (tools/variants_cfg.sh): the tiles stay empty, the lists are not (all) written
@@ -1431,7 +1441,7 @@ void launch_binning(const PrimBin* prims, uint32_t n_prims, const FrameView& f, 
     // Small scene: the launches of coarse binning cost more than letting every bin look at every primitive.
     fine_bin_kernel<<<dim3(n_bins, n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(prims, f, b.cbin_start, nullptr, 0, b.coarse_list,
                                                                                     b.coarse_cap, b.tile_start, b.tile_count, b.tile_list,
-                                                                                    b.tile_cap, b.counters, n_prims, 0);
+                                                                                    b.tile_cap, b.counters, b.row_cost, n_prims, 0);
     if (n_launches) *n_launches += 1;
     return;
   }
@@ -1441,8 +1451,8 @@ void launch_binning(const PrimBin* prims, uint32_t n_prims, const FrameView& f, 
   uint2* seg = reinterpret_cast<uint2*>(b.chunk_counts);  // [bin][chunk] (start, count)
   coarse_pairs_kernel<<<grid, kChunk, 0, stream>>>(prims, n_prims, f, rows_per_cta, seg, b.coarse_list, b.coarse_cap, b.counters);
   fine_bin_kernel<<<dim3(n_bins, FDC_FINE_SPLIT_BIG || n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(
-      prims, f, b.cbin_start, seg, n_chunks, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count, b.tile_list, b.tile_cap, b.counters, 0u,
-      FDC_FINE_SPLIT_BIG && n_bins > kFineSplitBins);
+      prims, f, b.cbin_start, seg, n_chunks, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count, b.tile_list, b.tile_cap, b.counters, b.row_cost,
+      0u, FDC_FINE_SPLIT_BIG && n_bins > kFineSplitBins);
   if (n_launches) *n_launches += 2;
 #else
   coarse_count_kernel<<<grid, kChunk, 0, stream>>>(prims, n_prims, f, rows_per_cta, b.chunk_counts);
@@ -1450,8 +1460,8 @@ void launch_binning(const PrimBin* prims, uint32_t n_prims, const FrameView& f, 
   coarse_scatter_kernel<<<grid, kChunk, 0, stream>>>(prims, n_prims, f, rows_per_cta, b.chunk_counts, b.cbin_start, b.coarse_list,
                                                      b.coarse_cap, b.counters);
   fine_bin_kernel<<<dim3(n_bins, FDC_FINE_SPLIT_BIG || n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(
-      prims, f, b.cbin_start, nullptr, 0, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count, b.tile_list, b.tile_cap, b.counters, 0u,
-      FDC_FINE_SPLIT_BIG && n_bins > kFineSplitBins);
+      prims, f, b.cbin_start, nullptr, 0, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count, b.tile_list, b.tile_cap, b.counters, b.row_cost,
+      0u, FDC_FINE_SPLIT_BIG && n_bins > kFineSplitBins);
   if (n_launches) *n_launches += 4;
 #endif
 }

@@ -44,11 +44,13 @@ constexpr int kMaxReach = 66;   // ceil(8 * 64/8) + 1 + slack
 
 struct RowSources {
   const uint32_t* rank[kMaxRanks];
-  int n, band_px;
+  int n;
+  int band_end[kMaxRanks];  // first row NOT owned by rank r
 };
 __device__ __forceinline__ const uint32_t* row_base(const RowSources& rs, const uint32_t* src, int y) {
   if (rs.n == 0) return src;
-  const int r = min(y / rs.band_px, rs.n - 1);
+  int r = 0;
+  while (r < rs.n - 1 && y >= rs.band_end[r]) r++;
   return rs.rank[r];
 }
 
@@ -186,8 +188,10 @@ void launch_backdrop_blur(const BlurArgs& a, cudaStream_t stream, int* n_launche
   const uint32_t* src = reinterpret_cast<const uint32_t*>(a.src);
   RowSources rs;
   rs.n = a.n_src;
-  rs.band_px = a.band_px > 0 ? a.band_px : 1;
-  for (int r = 0; r < kMaxRanks; r++) rs.rank[r] = r < a.n_src ? reinterpret_cast<const uint32_t*>(a.src_rank[r]) : nullptr;
+  for (int r = 0; r < kMaxRanks; r++) {
+    rs.rank[r] = r < a.n_src ? reinterpret_cast<const uint32_t*>(a.src_rank[r]) : nullptr;
+    rs.band_end[r] = r < a.n_src ? a.band_end_px[r] : 0;
+  }
   uint32_t* temp = reinterpret_cast<uint32_t*>(a.temp);
   uint32_t* dst = reinterpret_cast<uint32_t*>(a.dst);
   // H pass over the rows the V pass will read

@@ -263,6 +263,8 @@ struct fdc_ctx {
   DevBuf<PrimExt> d_exts;
   DevBuf<uint32_t> d_prim_call;
   DevBuf<uint32_t> d_chunk_counts, d_cbin_start, d_coarse_list, d_tile_start, d_tile_count, d_counters;
+  DevBuf<uint32_t> d_row_cost;          // tile entries per tile row of the last frame (fdc_get_tile_row_costs)
+  std::vector<int> band_bounds;         // fdc_set_band_tile_rows: n_ranks + 1 tile-row boundaries; empty = equal bands
   DevBuf<TileEntry> d_tile_list;
   DevBuf<uint8_t> d_fb, d_backdrop, d_temp;
   DevBuf<uint8_t> d_snapshot;      // pre-frame pixels of a multi-segment frame without clearMain (restored before an overflow replay)
@@ -768,6 +770,7 @@ int ensure_bin_buffers(fdc_ctx* ctx, uint32_t max_prims) {
   CK(ctx->d_tile_start.reserve((size_t)f.tiles_x * f.tiles_y));
   CK(ctx->d_tile_count.reserve((size_t)f.tiles_x * f.tiles_y));
   CK(ctx->d_counters.reserve(kNumCounters));
+  CK(ctx->d_row_cost.reserve(std::max(1, f.tiles_y)));
   CK(ctx->d_coarse_list.reserve(std::max<size_t>((size_t)max_prims * 3 + n_bins * 4, 1u << 16)));
   CK(ctx->d_tile_list.reserve(std::max<size_t>((size_t)max_prims * 24 + (size_t)f.tiles_x * f.tiles_y * 2, 1u << 20)));
   return FDC_OK;
@@ -786,6 +789,7 @@ BinBuffers bin_buffers(fdc_ctx* ctx) {
   b.tile_cap = (uint32_t)std::min<size_t>(ctx->d_tile_list.cap, 0xFFFFFFF0u);
   if (ctx->dbg_tile_limit) b.tile_cap = std::min(b.tile_cap, ctx->dbg_tile_limit);
   b.counters = ctx->d_counters.p;
+  b.row_cost = ctx->d_row_cost.p;
   return b;
 }
 
@@ -807,7 +811,17 @@ SetupArgs setup_args(fdc_ctx* ctx, const Segment& s) {
   a.frame = ctx->frame;
   a.counters = ctx->d_counters.p;
   a.zero_counters = (int)kCntStickyOverflow;
+  a.row_cost = ctx->d_row_cost.p;
+  a.n_row_cost = ctx->frame.tiles_y;
   return a;
+}
+
+// First tile row that rank r does NOT own (equal bands unless the host set its own).
+int band_end_tile_row(const fdc_ctx* ctx, int r) {
+  const int tiles_y = ctx->frame.tiles_y;
+  if ((int)ctx->band_bounds.size() == ctx->n_ranks + 1 && ctx->band_bounds.back() == tiles_y) return ctx->band_bounds[r + 1];
+  const int per = (tiles_y + ctx->n_ranks - 1) / ctx->n_ranks;
+  return std::min((r + 1) * per, tiles_y);
 }
 
 int ensure_copy_streams(fdc_ctx* ctx) {
@@ -875,8 +889,10 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
   // only the per-segment words, so an overflow in ANY segment is still visible when the host looks after the frame.
   // (a frame whose first segment has primitives lets that segment's setup kernel zero all the words instead)
   const bool setup_zeroes_all = !ctx->segments.empty() && ctx->segments[0].count > 0;
-  if (!setup_zeroes_all)
+  if (!setup_zeroes_all) {
     CK(cudaMemsetAsync(ctx->d_counters.p + kCntStickyOverflow, 0, sizeof(uint32_t) * (kNumCounters - kCntStickyOverflow), st));
+    if (ctx->d_row_cost.p) CK(cudaMemsetAsync(ctx->d_row_cost.p, 0, sizeof(uint32_t) * (size_t)std::max(1, ctx->frame.tiles_y), st));
+  }
   ctx->frame_resolved = false;
   // A frame that blends over the previous pixels (no clearMain) in several segments cannot simply be re-run after an
   // overflow in a later segment -- the earlier segments would be composited twice.  Keep the pre-frame pixels.
@@ -1016,7 +1032,7 @@ int execute_frame(fdc_ctx* ctx, bool upload, bool retry = false) {
         by0 = std::max(by0, ctx->frame.band_y0);
         by1 = std::min(by1, ctx->frame.band_y1);
         ba.n_src = ctx->n_ranks;
-        ba.band_px = std::max(1, ((ctx->frame.tiles_y + ctx->n_ranks - 1) / ctx->n_ranks) * kTileH);
+        for (int r = 0; r < ctx->n_ranks; r++) ba.band_end_px[r] = band_end_tile_row(ctx, r) * kTileH;
         for (int r = 0; r < ctx->n_ranks; r++)
           ba.src_rank[r] = (r == ctx->rank || !ctx->h_peers[r]) ? ctx->fb() : ctx->h_peers[r];
       }
@@ -1112,9 +1128,14 @@ void compute_frame_view(fdc_ctx* ctx) {
   f.W = ctx->W; f.H = ctx->H;
   f.tiles_x = (ctx->W + kTileW - 1) / kTileW;
   f.tiles_y = (ctx->H + kTileH - 1) / kTileH;
-  const int per = (f.tiles_y + ctx->n_ranks - 1) / ctx->n_ranks;
-  f.ty0 = std::min(ctx->rank * per, f.tiles_y);
-  f.ty1 = std::min(f.ty0 + per, f.tiles_y);
+  if ((int)ctx->band_bounds.size() == ctx->n_ranks + 1 && ctx->band_bounds.back() == f.tiles_y) {
+    f.ty0 = ctx->band_bounds[ctx->rank];  // bands chosen by the host (fdc_set_band_tile_rows)
+    f.ty1 = ctx->band_bounds[ctx->rank + 1];
+  } else {
+    const int per = (f.tiles_y + ctx->n_ranks - 1) / ctx->n_ranks;
+    f.ty0 = std::min(ctx->rank * per, f.tiles_y);
+    f.ty1 = std::min(f.ty0 + per, f.tiles_y);
+  }
   f.cty0 = (f.ty0 / kCoarse) * kCoarse;
   f.cbx = (f.tiles_x + kCoarse - 1) / kCoarse;
   f.cby = f.ty1 > f.ty0 ? (f.ty1 - f.cty0 + kCoarse - 1) / kCoarse : 0;
@@ -1225,6 +1246,7 @@ void fdc_destroy(fdc_ctx* ctx) {
   ctx->d_prims.release(); ctx->d_prim_bins.release(); ctx->d_geoms.release(); ctx->d_exts.release(); ctx->d_prim_call.release();
   ctx->d_chunk_counts.release(); ctx->d_cbin_start.release(); ctx->d_coarse_list.release();
   ctx->d_tile_start.release(); ctx->d_tile_count.release(); ctx->d_tile_list.release(); ctx->d_counters.release();
+  ctx->d_row_cost.release();
   ctx->d_fb.release(); ctx->d_backdrop.release(); ctx->d_temp.release(); ctx->d_peers.release(); ctx->d_snapshot.release();
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   for (auto& cs : ctx->copy_streams) if (cs) cudaStreamDestroy(cs);
@@ -2109,6 +2131,45 @@ int fdc_bind_framebuffer(fdc_ctx* ctx, void* device_rgba8) {
   return FDC_OK;
 }
 void* fdc_framebuffer_ptr(fdc_ctx* ctx) { return ctx ? ctx->fb() : nullptr; }
+// Bands chosen by the host instead of equal ones: n_ranks + 1 tile-row boundaries (16-px rows), bounds[0] = 0,
+// non-decreasing, bounds[n_ranks] = ceil(H / 16) of the frames to come.  Takes effect at once for replays of the
+// recorded frame and for every later frame of that height; n_bounds = 0 restores equal bands.  Every rank must be given
+// the same boundaries.  Needs a framebuffer the ranks share or reach (the NCCL / copy-engine gathers want equal bands).
+int fdc_set_band_tile_rows(fdc_ctx* ctx, const int* bounds, int n_bounds) {
+  if (!ctx) return FDC_ERR_INVALID;
+  if (ctx->frame_begun) return ctx->fail(FDC_ERR_STATE, "fdc_set_band_tile_rows inside a frame");
+  if (n_bounds == 0) {
+    ctx->band_bounds.clear();
+  } else {
+    if (!bounds || n_bounds != ctx->n_ranks + 1 || bounds[0] != 0) return ctx->fail(FDC_ERR_INVALID, "band boundaries: need n_ranks + 1 values starting at 0");
+    for (int r = 0; r < ctx->n_ranks; r++)
+      if (bounds[r + 1] < bounds[r]) return ctx->fail(FDC_ERR_INVALID, "band boundaries must not decrease");
+    ctx->band_bounds.assign(bounds, bounds + n_bounds);
+  }
+  CK(cudaSetDevice(ctx->device));
+  int rc = resolve_frame(ctx);  // nothing of the old partition may still be in flight
+  if (rc != FDC_OK && rc != FDC_ERR_RETRY) return rc;
+  drop_graph(ctx);
+  if (ctx->W > 0 && ctx->H > 0) compute_frame_view(ctx);
+  return FDC_OK;
+}
+
+// Tile entries per 16-px tile row, summed over the segments of the last completed frame: this rank's rows only (0
+// elsewhere), so a sum over the ranks gives the profile of the whole frame.  A host balances the bands with it.
+int fdc_get_tile_row_costs(fdc_ctx* ctx, uint32_t* out, int cap, int* n_rows) {
+  if (!ctx) return FDC_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int rc = resolve_frame(ctx);
+  if (rc) return rc;
+  if (!ctx->have_frame) return ctx->fail(FDC_ERR_STATE, "no completed frame");
+  const int n = ctx->frame.tiles_y;
+  if (n_rows) *n_rows = n;
+  if (!out) return FDC_OK;
+  if (cap < n) return ctx->fail(FDC_ERR_INVALID, "fdc_get_tile_row_costs: %d rows, room for %d", n, cap);
+  if (n > 0) CK(cudaMemcpy(out, ctx->d_row_cost.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+  return FDC_OK;
+}
+
 int fdc_band_rows(fdc_ctx* ctx, int* y0, int* y1) {
   if (!ctx || !y0 || !y1) return FDC_ERR_INVALID;
   *y0 = ctx->frame.band_y0;

@@ -22,6 +22,8 @@ struct SetupArgs {
   FrameView frame;
   uint32_t* counters;     // binning counters: the kernel zeroes the first `zero_counters` words for the binning that follows
   int zero_counters;
+  uint32_t* row_cost;     // per-frame tile-entry totals per tile row (fine binner adds; band balancing reads); zeroed with the
+  int n_row_cost;         //   per-frame counters (zero_counters == kNumCounters)
 };
 void launch_prim_setup(const SetupArgs& a, cudaStream_t stream);
 
@@ -35,6 +37,7 @@ struct BinBuffers {
   TileEntry* tile_list;    // [tile_cap]
   uint32_t tile_cap;
   uint32_t* counters;      // [kNumCounters], see fdc_types.h (kCnt...)
+  uint32_t* row_cost;      // [tiles_y] tile entries per tile row, accumulated over the frame's segments (may be null)
 };
 void launch_binning(const PrimBin* prim_bins, uint32_t n_prims, const FrameView& frame, const BinBuffers& b,
                     cudaStream_t stream, int* n_launches);
@@ -67,10 +70,11 @@ constexpr int kFlagError = 32;  // word of a rank's flag array that records barr
 constexpr int kFlagSignalSeq = 40, kFlagWaitSeq = 41;  // this rank's running signal / wait numbers (local use only)
 struct BlurArgs {
   const uint8_t* src;  // framebuffer
-  // Tile-band partition: rows [r*band_px, (r+1)*band_px) of the frame live in src_rank[r] (this rank's own framebuffer or
+  // Tile-band partition: rows [band_end_px[r-1], band_end_px[r]) of the frame live in src_rank[r] (this rank's own framebuffer or
   // a peer's, read over NVLink for the blur halo).  n_src == 0: everything is in `src`.
   const uint8_t* src_rank[kMaxRanks];
-  int n_src, band_px;
+  int n_src;
+  int band_end_px[kMaxRanks];  // rank r owns rows [band_end_px[r-1], band_end_px[r])
   uint8_t* temp;       // H-pass output
   uint8_t* dst;        // backdrop (V-pass output)
   int W, H;

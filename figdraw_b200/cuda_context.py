@@ -382,6 +382,20 @@ class CudaContext(BackendContext):
         self._ck(self._lib.fdc_band_rows(self._h, ctypes.byref(y0), ctypes.byref(y1)))
         return y0.value, y1.value
 
+    def tileRowCosts(self) -> np.ndarray:
+        """Tile entries per 16-px tile row of the last frame (this rank's rows; 0 elsewhere): fdc_get_tile_row_costs."""
+        n = ctypes.c_int(0)
+        self._ck(self._lib.fdc_get_tile_row_costs(self._h, None, 0, ctypes.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=np.uint32)
+        self._ck(self._lib.fdc_get_tile_row_costs(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), int(out.size), ctypes.byref(n)))
+        return out[: n.value]
+
+    def setBandTileRows(self, bounds) -> None:
+        """Bands chosen by the host: n_ranks + 1 tile-row boundaries (same on every rank); None / empty = equal bands."""
+        b = [int(v) for v in (bounds if bounds is not None else [])]
+        arr = (ctypes.c_int * max(len(b), 1))(*b)
+        self._ck(self._lib.fdc_set_band_tile_rows(self._h, arr, len(b)))
+
     def bindFramebuffer(self, device_ptr: Optional[int]):
         self._ck(self._lib.fdc_bind_framebuffer(self._h, ctypes.c_void_p(device_ptr or 0)))
 

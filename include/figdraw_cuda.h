@@ -315,6 +315,14 @@ int fdc_bind_framebuffer(fdc_ctx* ctx, void* device_rgba8);
 void* fdc_framebuffer_ptr(fdc_ctx* ctx);
 /* Rows [*y0,*y1) this rank owns for the current frame size. */
 int fdc_band_rows(fdc_ctx* ctx, int* y0, int* y1);
+/* Band balancing: tile entries per 16-px tile row of the last completed frame (this rank's rows; 0 elsewhere -- sum over
+ * the ranks for the whole frame), and bands chosen by the host instead of equal ones: n_ranks + 1 tile-row boundaries,
+ * bounds[0] = 0, non-decreasing, bounds[n_ranks] = ceil(H / 16); the same on every rank; n_bounds = 0 restores equal
+ * bands.  Takes effect for replays of the recorded frame and for later frames of that height.  Needs a framebuffer the
+ * ranks share or reach (fdc_bind_shared_framebuffer / fdc_set_peer_framebuffers); an all-gather of equal slices does
+ * not apply to unequal bands. */
+int fdc_get_tile_row_costs(fdc_ctx* ctx, uint32_t* out, int cap, int* n_rows);
+int fdc_set_band_tile_rows(fdc_ctx* ctx, const int* bounds, int n_bounds);
 /* The CUDA stream (cudaStream_t) frames are launched on. */
 void* fdc_stream(fdc_ctx* ctx);
 /* Peer framebuffers: when set (n_ranks entries, own entry may be NULL), the shade kernel stores every

@@ -254,6 +254,50 @@ def test_tile_bands_reassemble_the_frame():
         assert np.array_equal(out, full)
 
 
+def test_host_chosen_bands_reassemble_the_frame_and_row_costs_add_up():
+    """fdc_set_band_tile_rows: unequal bands (one of them a single tile row) give the same frame; a tile's list does not
+    depend on the partition, so the ranks' per-row entry counts (fdc_get_tile_row_costs) sum to the single-context
+    profile -- which is what bands.balance_rows splits."""
+    from figdraw_b200.bands import balance_rows
+
+    tr = ss.config_trace(5, 1280, 720, n_rects=4000, n_glyphs=800)
+    one = CudaContext(atlasSize=tr.atlas_size)
+    full = render_trace(tr, one)
+    profile = one.tileRowCosts().astype(np.int64)
+    one.close()
+    tiles_y = (tr.height + 15) // 16
+    assert profile.shape == (tiles_y,) and profile.sum() > 0
+    balanced = balance_rows(profile + 3 * ((tr.width + 15) // 16), 4)
+    for bounds in ([0, 3, 20, 21, tiles_y], balanced):
+        out = np.zeros_like(full)
+        total = np.zeros(tiles_y, dtype=np.int64)
+        for r in range(4):
+            ctx = CudaContext(atlasSize=tr.atlas_size, rank=r, nRanks=4)
+            ctx.setBandTileRows(bounds)
+            img = render_trace(tr, ctx)
+            y0, y1 = ctx.bandRows()
+            assert (y0, y1) == (bounds[r] * 16, min(bounds[r + 1] * 16, tr.height))
+            out[y0:y1] = img[y0:y1]
+            costs = ctx.tileRowCosts().astype(np.int64)
+            assert not costs[: bounds[r]].any() and not costs[bounds[r + 1]:].any()
+            total += costs
+            ctx.close()
+        assert np.array_equal(out, full)
+        assert np.array_equal(total, profile)
+    # the balanced split is no worse than the equal one on the cost it was given
+    cost = profile + 3 * ((tr.width + 15) // 16)
+    per = (tiles_y + 3) // 4
+    worst = lambda b: max(int(cost[b[i]:b[i + 1]].sum()) for i in range(4))  # noqa: E731
+    assert worst(balanced) <= worst([min(i * per, tiles_y) for i in range(5)])
+    # bad boundaries are refused
+    ctx = CudaContext(atlasSize=tr.atlas_size, rank=0, nRanks=4)
+    with pytest.raises(FigDrawError):
+        ctx.setBandTileRows([0, 5, 4, 20, tiles_y])
+    with pytest.raises(FigDrawError):
+        ctx.setBandTileRows([0, tiles_y])
+    ctx.close()
+
+
 def _band_contexts(tr, n, gather="stores"):
     from figdraw_b200.bands import padded_rows
 
@@ -275,12 +319,15 @@ def _submit(c, tr, calls):
     c.endFrame()
 
 
-def _render_banded_with_peers(tr, n, gather="stores"):
+def _render_banded_with_peers(tr, n, gather="stores", bounds=None):
     """n band contexts on one device, framebuffers cross-registered as peers: every rank submits the frame, the shade
     kernel's last segment stores each band into every framebuffer (or the copy engines ship it slice by slice), blur
     halo rows are read from the owner."""
     ctxs = _band_contexts(tr, n, gather)
     try:
+        if bounds is not None:
+            for c in ctxs:
+                c.setBandTileRows(bounds)
         # Size every context's buffers one rank at a time with the blur calls removed (no cross-rank waits): all ranks
         # share this process and device, and an allocation while a peer spins on our flags would stall both.
         for c in ctxs:
@@ -322,6 +369,16 @@ def test_backdrop_blur_halo_exchange_across_bands(n):
         for r, img in enumerate(_render_banded_with_peers(tr, n)):
             mx, frac = diff_stats(img, full)
             assert np.array_equal(img, full), f"rank {r}/{n}: max {mx} LSB, {frac:.5%} of pixels"
+
+
+def test_backdrop_blur_halo_exchange_across_unequal_bands():
+    """Host-chosen bands: the blur's halo rows come from whichever rank owns them under the boundaries in force."""
+    tr = ss.config_trace(2, 1280, 720)
+    tiles_y = (tr.height + 15) // 16
+    full = _render_banded_with_peers(tr, 1)[0]
+    for bounds in ([0, 10, 12, tiles_y], [0, 30, 31, tiles_y]):
+        for r, img in enumerate(_render_banded_with_peers(tr, 3, bounds=bounds)):
+            assert np.array_equal(img, full), f"rank {r}, bounds {bounds}"
 
 
 @pytest.mark.parametrize("n", [2])

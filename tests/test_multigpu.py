@@ -62,6 +62,18 @@ def _worker(rank, world, port, out_dir):
         results[name] = t[: tr.height * tr.width * 4].view(tr.height, tr.width, 4).cpu().numpy().copy()
         results[name + "_mc"] = np.array([mc != 0])
         dist.barrier()
+        # bands of equal cost instead of equal height (every rank adopts the same boundaries), blur halos included
+        bounds = bands.rebalance_across_ranks(ctx, world, (tr.width + 15) // 16, dist)
+        for _k in range(2):
+            ctx.beginFrame((tr.width, tr.height), clearMain=tr.clear is not None, clearMainColor=tr.clear or (1, 1, 1, 1))
+            ctx.submitPrepared(prepared)
+            ctx.endFrame()
+            bands.resolve_across_ranks(ctx, world, dist)
+        torch.cuda.synchronize()
+        dist.barrier()
+        results[name + "_balanced"] = t[: tr.height * tr.width * 4].view(tr.height, tr.width, 4).cpu().numpy().copy()
+        results[name + "_bounds"] = np.array(bounds)
+        dist.barrier()
         ctx.close()
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **results)
     dist.destroy_process_group()
@@ -82,4 +94,5 @@ def test_multicast_gather_gives_every_rank_the_whole_frame(tmp_path):
         got = np.load(tmp_path / f"rank{r}.npz")
         for name, img in want.items():
             assert np.array_equal(got[name], img), f"rank {r}: {name} differs from the single-GPU frame"
+            assert np.array_equal(got[name + "_balanced"], img), f"rank {r}: {name} differs under balanced bands {got[name + '_bounds']}"
         print("rank", r, "multicast mapping:", bool(got["cfg5_mc"][0]))

@@ -7,7 +7,7 @@ timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/fina
 python bench.py 2> gpurun_out/final_bench.err > gpurun_out/final_bench.json
 python bench.py --impl reference --steps 5 --warmup 1 2>> gpurun_out/final_bench.err > gpurun_out/final_bench_reference.json
 ncu --metrics gpu__time_duration.sum --clock-control none -s 190 -c 64 --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --import-source on --clock-control none -k regex:"shade_kernel|fine_bin|coarse_count|coarse_scatter|prim_setup|coarse_scan" -s 14 -c 7 -o gpurun_out/final_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+ncu --set full --import-source on --clock-control none -k regex:"shade_kernel|fine_bin|coarse_pairs|prim_setup" -s 10 -c 5 -o gpurun_out/final_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 # (reports are turned into raw-page CSVs here and deleted: gpurun only brings back 64 MiB)
 ncu -i gpurun_out/final_full.ncu-rep --page raw --csv > gpurun_out/final_full_raw.csv 2>/dev/null
 for c in 2 3 4; do

@@ -103,8 +103,8 @@ for r in data:
 summary = None
 with open(os.path.join(P, f"{tag}_ncu_full_kernels.md"), "w") as fh:
     fh.write(f"# ncu --set full summary ({tag}, commit {commit}), cfg5 3840x2160\n\n")
-    fh.write("`ncu --set full --import-source on --clock-control none -k regex:\"shade_kernel|fine_bin|coarse_count|coarse_scatter|"
-             "prim_setup|coarse_scan\" -s 14 -c 7 python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n(read with `ncu -i ... --page raw "
+    fh.write("`ncu --set full --import-source on --clock-control none -k regex:\"shade_kernel|fine_bin|coarse_pairs|"
+             "prim_setup\" -s 10 -c 5 python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n(read with `ncu -i ... --page raw "
              "--csv`).  ncu flushes caches before every kernel, so DRAM bytes of the binning kernels are cold-cache figures; in a frame their "
              "input was just written by the previous kernel and sits in L2.\n")
     for name, r in seen.items():

@@ -96,6 +96,8 @@ proc fdc_retain_owner(ctx: FdcCtx, what: cint, id, token: uint64): cint {.import
 proc fdc_release_owner(ctx: FdcCtx, what: cint, id, token: uint64, outLast: ptr cint): cint {.importc, header: hdr.}
 proc fdc_set_atlas_replay(ctx: FdcCtx, enabled: cint): cint {.importc, header: hdr.}
 proc fdc_export_framebuffer(ctx: FdcCtx, width, rows: cint, outFd: ptr cint, outBytes: ptr csize_t): cint {.importc, header: hdr.}
+proc fdc_get_tile_row_costs(ctx: FdcCtx, outCosts: ptr uint32, cap: cint, nRows: ptr cint): cint {.importc, header: hdr.}
+proc fdc_set_band_tile_rows(ctx: FdcCtx, bounds: ptr cint, nBounds: cint): cint {.importc, header: hdr.}
 proc fdc_bind_shared_framebuffer(ctx: FdcCtx, local: pointer, bytes: csize_t, peers: ptr pointer, n: cint,
                                  multicast: pointer, width, rows: cint): cint {.importc, header: hdr.}
 

@@ -181,22 +181,75 @@ struct DrawView {
   __device__ __forceinline__ uint32_t op() const { return w[0]; }
   __device__ __forceinline__ uint32_t u(int k) const { return w[1 + k]; }
   __device__ __forceinline__ float f(int k) const { return __uint_as_float(w[10 + k]); }
+  __device__ __forceinline__ const uint32_t* colors() const { return w + 4; }                              // u[3..6]
+  __device__ __forceinline__ const float* radii_x() const { return reinterpret_cast<const float*>(w + 14); }  // f[4..7]
+  __device__ __forceinline__ const float* radii_y() const { return reinterpret_cast<const float*>(w + 18); }  // f[8..11]
+};
+
+// The same view of a 64-byte compact record (fdc_rect64), straight from registers: what expand_rect64_words would have
+// written, field by field (every index below is a literal at the call sites, so the switches fold away), without the
+// round trip through the staging slot.  A compact record is always a rounded rect: the other cases of setup_record's
+// switch are not even compiled into this instantiation.
+struct RectView {
+  fdc_rect64 r;
+  float mid;
+  __device__ __forceinline__ explicit RectView(const fdc_rect64& rec) : r(rec), mid(0.5f) {
+    if (((r.packed >> 8) & 3u) == (uint32_t)FDC_FILL_LINEAR3) {
+      mid = (float)((r.packed >> 16) & 255u) / 255.0f;
+      mid = mid < 0.01f ? 0.01f : (mid > 0.99f ? 0.99f : mid);
+    }
+  }
+  __device__ __forceinline__ uint32_t op() const { return FDC_OP_ROUNDED_RECT; }
+  __device__ __forceinline__ uint32_t u(int k) const {
+    switch (k) {
+      case 0: return r.packed & 255u;
+      case 1: return (r.packed >> 8) & 3u;
+      case 2: return (r.packed >> 10) & 3u;
+      case 3: return r.c[0];
+      case 4: return r.c[1];
+      case 5: return r.c[2];
+      default: return 0u;
+    }
+  }
+  __device__ __forceinline__ float f(int k) const {
+    switch (k) {
+      case 0: case 1: case 2: case 3: return r.rect[k];
+      case 4: case 5: case 6: case 7: return r.radii[k - 4];
+      case 8: case 9: case 10: case 11: return r.radii[k - 8];
+      case 12: return r.factor;
+      case 13: return r.spread;
+      case 14: return r.shape_size[0];
+      case 15: return r.shape_size[1];
+      case 16: return mid;
+      default: return 0.0f;
+    }
+  }
+  __device__ __forceinline__ const uint32_t* colors() const { return r.c; }
+  __device__ __forceinline__ const float* radii_x() const { return r.radii; }
+  __device__ __forceinline__ const float* radii_y() const { return r.radii; }
 };
 
 // Full setup of draw record `i` of the segment; `rec` is its staging slot in shared memory (33 words).
+template <class Rec>
+__device__ __forceinline__ void setup_record_from(const SetupArgs& a, uint32_t i, const Rec& d, const RunState& rs);
+
 __device__ void setup_record(const SetupArgs& a, uint32_t i, uint32_t* rec, int run_lo, int run_hi) {
-  uint32_t di = a.first + i;
-  int ri = find_run_in(a.runs, run_lo, run_hi, di);  // the CTA's records usually share one run: no search at all
+  const uint32_t di = a.first + i;
+  const int ri = find_run_in(a.runs, run_lo, run_hi, di);  // the CTA's records usually share one run: no search at all
   const RunState rs = a.runs[ri];
   if (rs.compact) {
-    // the run arrived as 64-byte fdc_rect64 records: expand mine over my staging slot (only this thread reads it)
-    const fdc_rect64 r = a.rects64[rs.src_off + (di - rs.first_draw)];
-    uint32_t w[32];
-    expand_rect64_words(r, w);
-#pragma unroll
-    for (int k = 0; k < 32; k++) rec[k] = w[k];
+    // the run arrived as 64-byte fdc_rect64 records
+    const RectView d(a.rects64[rs.src_off + (di - rs.first_draw)]);
+    setup_record_from(a, i, d, rs);
+  } else {
+    const DrawView d{rec};
+    setup_record_from(a, i, d, rs);
   }
-  const DrawView d{rec};
+}
+
+template <class Rec>
+__device__ __forceinline__ void setup_record_from(const SetupArgs& a, uint32_t i, const Rec& d, const RunState& rs) {
+  const uint32_t di = a.first + i;
   const Xform xf = a.xforms[rs.xform];
   a.prim_call[i] = rs.call_index + (di - rs.first_draw);
 
@@ -224,7 +277,7 @@ __device__ void setup_record(const SetupArgs& a, uint32_t i, uint32_t* rec, int 
         p.c_mid = d.u(4);
         p.c_stop = d.u(5);
       } else {
-        gradient_colors(fkind, axis, d.w + 4, d.f(16), cols);
+        gradient_colors(fkind, axis, d.colors(), d.f(16), cols);
       }
       float qhx = fmul(w, 0.5f), qhy = fmul(h, 0.5f);
       bool inset = (mode == FDC_SDF_INSET_SHADOW);
@@ -235,7 +288,7 @@ __device__ void setup_record(const SetupArgs& a, uint32_t i, uint32_t* rec, int 
       p.p2 = inset ? ssx : shx;
       p.p3 = inset ? ssy : shy;
       float rr[4];
-      if (rounded_radii_vec(reinterpret_cast<const float*>(d.w + 14), reinterpret_cast<const float*>(d.w + 18), shx, shy, rr)) flags |= PF_ELLIPTICAL;
+      if (rounded_radii_vec(d.radii_x(), d.radii_y(), shx, shy, rr)) flags |= PF_ELLIPTICAL;
       p.r0 = rr[0]; p.r1 = rr[1]; p.r2 = rr[2]; p.r3 = rr[3];
       p.factor = d.f(12);
       p.spread = fill_mode == 0 ? d.f(13) : clampf(d.f(16), 0.01f, 0.99f);
@@ -285,7 +338,7 @@ __device__ void setup_record(const SetupArgs& a, uint32_t i, uint32_t* rec, int 
         p.c_mid = d.u(4);
         p.c_stop = d.u(5);
       } else {
-        gradient_colors(fkind, axis, d.w + 4, d.f(16), cols);
+        gradient_colors(fkind, axis, d.colors(), d.f(16), cols);
       }
       p.qhx = fmul(d.f(2), 0.5f); p.qhy = fmul(d.f(3), 0.5f); p.p2 = d.f(4); p.p3 = d.f(5);
       p.r0 = d.f(6); p.r1 = d.f(7); p.r2 = d.f(8); p.r3 = d.f(9);

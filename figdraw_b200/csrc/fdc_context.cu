@@ -387,7 +387,6 @@ int atlas_grow(fdc_ctx* ctx) {
     for (auto& ok_key : live) {
       fdc_ctx::EntryInfo& e = ctx->entry_info[ok_key.second];
       int rx = 0, ry = 0;
-      bool grew = false;
       // find_empty_rect must not recurse into another grow here: probe the height map directly
       const int imgW = e.w + kAtlasMargin * 2, imgH = e.h + kAtlasMargin * 2;
       int lowest = ctx->atlas_size, at = 0;
@@ -401,7 +400,6 @@ int atlas_grow(fdc_ctx* ctx) {
           if (fit) { lowest = v; at = i; }
         }
       }
-      (void)grew;
       if (lowest + imgH > ctx->atlas_size) { ok = false; break; }
       for (int j = at; j < at + imgW; j++) ctx->heights[j] = (uint16_t)(lowest + imgH + kAtlasMargin * 2);
       rx = at + kAtlasMargin;

@@ -37,12 +37,6 @@
 #ifndef FDC_QPTR
 #define FDC_QPTR 1   // A/B switch: queue loop steps a pointer (0: index + base)
 #endif
-#ifndef FDC_FDIV
-#define FDC_FDIV 0   // A/B switch: tile -> (tx, ty) through a float reciprocal (0: integer division)
-#endif
-#ifndef FDC_LEAN_HAND
-#define FDC_LEAN_HAND 0  // A/B switch: hand-ordered visit in the lean loop (0: the generic shade_fast)
-#endif
 #ifndef FDC_LEAN_LOOP
 #define FDC_LEAN_LOOP 1  // A/B switch: call-free loop for tiles that hold only unmasked fast primitives
 #endif
@@ -494,68 +488,6 @@ __device__ __forceinline__ void shade_fast(const float4* __restrict__ S, const P
   blend(px, col.x, col.y, col.z, sa);
 }
 
-// The lean loop's visit: shade_fast<false, true> restated for the tiles that hold nothing but unmasked fast primitives,
-// with the loads ordered by hand.  The r02 profile of the generic version showed two exposed L1 latencies per partial
-// visit -- the colour was loaded first (the occluder shortcut needs it), the SDF quads q0..q3 only after that branch
-// had been resolved; here everything a visit needs is requested before anything is consumed.
-__device__ __forceinline__ void shade_lean(const float4* __restrict__ S, const PrimExt* __restrict__ E, const AtlasView& at, uint32_t info,
-                                           bool full, float fx, float fy, Pixel& px) {
-  if (info & TE_TEX) {
-    shade_fast<false, true>(S, E, at, nullptr, info, full, fx, fy, px);
-    return;
-  }
-  float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
-  if (!full) { q0 = __ldg(S + 0); q1 = __ldg(S + 1); q2 = __ldg(S + 2); q3 = __ldg(S + 3); }
-  float4 col;
-  if (info & TE_SOLID) {
-    col = __ldg(S + 4);
-  } else {
-    const float4* X = reinterpret_cast<const float4*>(E);
-    const float4 a0 = __ldg(X + 1), d0 = __ldg(X + 2), a1 = __ldg(X + 3);
-    if (info & TE_GRAD3) {
-      const float4 e0 = __ldg(X + 0), d1 = __ldg(X + 4);
-      const float tt = sat(fmaf(fx, e0.x, fmaf(fy, e0.y, e0.z)));
-      const bool lo = tt <= e0.w;
-      col.x = fmaf(lo ? d0.x : d1.x, tt, lo ? a0.x : a1.x);
-      col.y = fmaf(lo ? d0.y : d1.y, tt, lo ? a0.y : a1.y);
-      col.z = fmaf(lo ? d0.z : d1.z, tt, lo ? a0.z : a1.z);
-      col.w = fmaf(lo ? d0.w : d1.w, tt, lo ? a0.w : a1.w);
-    } else {
-      col.x = fmaf(d0.x, fx, fmaf(a1.x, fy, a0.x));
-      col.y = fmaf(d0.y, fx, fmaf(a1.y, fy, a0.y));
-      col.z = fmaf(d0.z, fx, fmaf(a1.z, fy, a0.z));
-      col.w = fmaf(d0.w, fx, fmaf(a1.w, fy, a0.w));
-    }
-  }
-  float sa = col.w * (1.0f / 255.0f);
-  if (!full) {
-    const float ppx = fmaf(fx, q0.x, q0.y), ppy = fmaf(fy, q0.z, q0.w);  // (p.x, -p.y)
-    const float apx = fabsf(ppx), apy = fabsf(ppy);
-    const bool inside = apx < q1.x && apy < q1.y;  // pixel centre inside the ceil'd quad
-    const float rr = ppx > 0.0f ? (ppy > 0.0f ? q2.x : q2.y) : (ppy > 0.0f ? q2.z : q2.w);
-    const float qx = apx - q1.z + rr, qy = apy - q1.w + rr;
-    const float mx = fmaxf(qx, 0.0f), my = fmaxf(qy, 0.0f);
-    const float dist = fminf(fmaxf(qx, qy), 0.0f) + fast_sqrt(fmaf(mx, mx, my * my)) - rr;
-    const uint32_t kind = (info >> TE_KIND_SHIFT) & 3u;
-    float cov;
-    if (kind == 2u) {  // DropShadow: sd > 0 ? exp(-.5 (sd/sigma)^2) : 1
-      const float sd = fmaxf(dist - q3.y, 0.0f);
-      cov = fast_ex2(q3.w * sd * sd);
-    } else {  // ClipAA (f = 0) / AnnularAA: |d + f| - f with f = factor / 2
-      const float f = kind == 0u ? 0.0f : q3.x * 0.5f;
-      const float d = kind == 0u ? dist : fabsf(dist + f) - f;
-      cov = sat(fmaf(-q3.z, d, 0.5f));
-    }
-    sa = inside ? sa * cov : 0.0f;
-  } else if (info & TE_OCCLUDER) {
-    // opaque, coverage exactly 1 on the whole block: the store is round(src) whatever dst was (earlier primitives were
-    // skipped for this block, so the result must not depend on dst even in the last ulp)
-    px.r = col.x + kBias; px.g = col.y + kBias; px.b = col.z + kBias; px.a = 255.0f + kBias;
-    return;
-  }
-  blend(px, col.x, col.y, col.z, sa);
-}
-
 __device__ __noinline__ Pixel shade_prim(const ShadeArgs* __restrict__ ap, const Prim* __restrict__ P, int ix, int iy, Pixel px) {
   const ShadeArgs& a = *ap;
   const float4* Q = reinterpret_cast<const float4*>(P);
@@ -795,11 +727,7 @@ __device__ __forceinline__ void walk_list(const ShadeArgs& a, const uint2* __res
       const uint32_t info = q.z;
       const bool full = (info & full_bit) != 0u;
       if (kLean) {
-#if FDC_LEAN_HAND
-        shade_lean(S, a.exts + q.w, a.atlas, info, full, fx, fy, px);
-#else
         shade_fast<false, true>(S, a.exts + q.w, a.atlas, a.rectmasks, info, full, fx, fy, px);
-#endif
       } else if (info & TE_FAST) {
         if (info & ((15u << TE_DEPTH_SHIFT) | TE_RECTMASK)) shade_fast<true, false>(S, a.exts + q.w, a.atlas, a.rectmasks, info, full, fx, fy, px);
         else shade_fast<false, false>(S, a.exts + q.w, a.atlas, a.rectmasks, info, full, fx, fy, px);
@@ -851,7 +779,6 @@ __global__ void __launch_bounds__(256, kLeanKernel ? FDC_LEAN_MIN_BLOCKS : FDC_S
   const uint32_t n_blocks = (uint32_t)min(kTilesPerCta, n_tiles - tile0) * 8u;
   uint32_t* fb32 = reinterpret_cast<uint32_t*>(a.fb);
   uint4* queue = s_queue[threadIdx.x >> 5];
-  const float inv_tiles_x = 1.0f / (float)f.tiles_x;
 
   for (;;) {
     uint32_t blk = 0;
@@ -859,14 +786,8 @@ __global__ void __launch_bounds__(256, kLeanKernel ? FDC_LEAN_MIN_BLOCKS : FDC_S
     blk = __shfl_sync(0xFFFFFFFFu, blk, 0);
     if (blk >= n_blocks) break;
     const int tile = tile0 + (int)(blk >> 3), sub = (int)(blk & 7u);
-    // tile / tiles_x through a float reciprocal (exact: tile < 2^22, the +0.5 keeps the quotient off integer boundaries)
-#if FDC_FDIV
-    const int trow = (int)(((float)tile + 0.5f) * inv_tiles_x);
-    int tx = tile - trow * f.tiles_x, ty = f.ty0 + trow;
-    if (tx < 0) { tx += f.tiles_x; ty--; } else if (tx >= f.tiles_x) { tx -= f.tiles_x; ty++; }  // never taken below ~16K-px frames
-#else
+    // (a float reciprocal instead of this integer division was measured slower: register allocation, profiles/r02_shade_experiments.md)
     const int tx = tile % f.tiles_x, ty = f.ty0 + tile / f.tiles_x;
-#endif
     const int wx0 = tx * kTileW + (sub & 1) * 8, wy0 = ty * kTileH + (sub >> 1) * 4;
     const int ix = wx0 + (lane & 7), iy = wy0 + (lane >> 3);
     const bool valid = ix < f.W && iy < f.H;

@@ -8,14 +8,13 @@
 //   order so the integer quad corners -- and therefore the bin lists -- are bit-exact against the oracle.
 //
 // Binning -- two levels, both tile-major so list order == emission order without sorting or atomics on order:
-//   coarse: the frame (band) is cut into 128x128-px bins; primitives into chunks of 512 (16 warps x 32).  Every lane
-//           marks the bin-row words its primitive touches; per marked word ONE 32x32 bit transpose across the warp
-//           turns "bins per primitive" into "primitives per bin" (count = popc, stable rank = bit order).
-//           count[bin][chunk] -> row scan over chunks -> the same walk scatters (stable compaction, no sorting).
-//   fine:   one CTA per coarse bin stages its list 1024 entries at a time; each warp takes groups of 32 entries, two
-//           transposes give lane t the entries of tiles t and 32+t.  Counts -> CTA scan -> one atomicAdd reserves
-//           the bin's slice of the tile list (slice placement is the only non-deterministic thing and is not
-//           observable) -> the lanes write their tiles' 8-byte TileEntry records in bit order.
+//   coarse: the frame (band) is cut into 128x128-px bins; primitives into chunks of 512.  ONE kernel: a CTA enumerates
+//           the (primitive, bin) pairs of its chunk in primitive order, counts them per bin, reserves a region of the
+//           coarse list and scatters; a table says where each (bin, chunk) segment sits (coarse_pairs_kernel).
+//   fine:   one CTA per coarse bin stages its entries 1024 at a time (chunk by chunk through the table); each warp takes
+//           groups of 32 entries, two transposes give lane t the entries of tiles t and 32+t.  Counts -> CTA scan -> one
+//           atomicAdd reserves the bin's slice of the tile list (slice placement is the only non-deterministic thing
+//           and is not observable) -> the lanes write their tiles' 8-byte TileEntry records in bit order.
 #include <cuda_runtime.h>
 
 #include "fdc_kernels.h"
@@ -714,9 +713,6 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 // pairs is spread over all warps instead of serialising one.  Counting is a shared-memory histogram; the stable rank
 // of a pair inside a round is popc(match_any(bin) & lower lanes); rounds and warps are ordered by running offsets
 // kept per (bin, warp).  Cost follows the number of pairs -- a band of an 8-GPU partition has 1/8 of them.
-#ifndef FDC_COARSE_FUSED
-#define FDC_COARSE_FUSED 1
-#endif
 constexpr int kSlots = 1024;  // coarse bins one CTA handles: a range of whole bin rows
 constexpr int kWarps = kChunk / 32;
 
@@ -776,110 +772,22 @@ __device__ __forceinline__ void chunk_pair(const ChunkPairs& cp, uint32_t p, int
   by = (int)((r >> 8) & 255u) + q;
 }
 
-// Count pass: chunk_counts[bin][chunk] = pairs of this chunk in each bin of the CTA's row range.
-__global__ void __launch_bounds__(kChunk) coarse_count_kernel(const PrimBin* __restrict__ prims, uint32_t n, FrameView f, int rows_per_cta,
-                                                              uint32_t* __restrict__ chunk_counts) {
-  __shared__ uint32_t s_hist[kSlots];
-  __shared__ uint32_t s_excl[kChunk], s_rect[kChunk], s_wtot[kWarps];
-  const uint32_t chunk = blockIdx.x;
-  const int row0 = blockIdx.y * rows_per_cta, row1 = min(row0 + rows_per_cta, f.cby);
-  const int lane = threadIdx.x & 31;
-  const int used = (row1 - row0) * f.cbx;
-  const uint32_t rect = coarse_rect(prims, chunk * kChunk + threadIdx.x, n, f);
-  for (int sl = threadIdx.x; sl < used; sl += blockDim.x) s_hist[sl] = 0;
-  const ChunkPairs cp = chunk_pairs(rect, row0, row1, s_excl, s_rect, s_wtot);
-  for (uint32_t base = cp.lo; base < cp.hi; base += 32) {
-    const uint32_t p = base + lane;
-    if (p < cp.hi) {
-      int owner, bx, by;
-      chunk_pair(cp, p, owner, bx, by);
-      atomicAdd(&s_hist[(by - row0) * f.cbx + bx], 1u);
-    }
-  }
-  __syncthreads();
-  for (int sl = threadIdx.x; sl < used; sl += blockDim.x)
-    chunk_counts[(size_t)(row0 * f.cbx + sl) * gridDim.x + chunk] = s_hist[sl];
-}
-
-// Scatter pass: the same enumeration; position = bin start + pairs of earlier chunks + pairs of earlier warps of this
-// chunk + pairs of earlier rounds of this warp + rank inside the round.
-__global__ void __launch_bounds__(kChunk) coarse_scatter_kernel(const PrimBin* __restrict__ prims, uint32_t n, FrameView f, int rows_per_cta,
-                                                                const uint32_t* __restrict__ chunk_counts,
-                                                                const uint32_t* __restrict__ cbin_start,
-                                                                uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
-                                                                const uint32_t* __restrict__ counters) {
-  // per (bin, warp): first the pair count, then (after the prefix over warps) the running offset inside the chunk's
-  // slice of the bin.  16 bits each (a chunk puts at most kChunk pairs into a bin), two warps per word; [word][bin] so
-  // that consecutive threads hit consecutive banks.
-  __shared__ uint32_t s_pos[kWarps / 2][kSlots];
-  __shared__ uint32_t s_gbase[kSlots];
-  __shared__ uint32_t s_excl[kChunk], s_rect[kChunk], s_wtot[kWarps];
-  if (counters[kCntCoarseTotal] > coarse_cap) return;  // overflow: host regrows and re-runs the frame
-  const uint32_t chunk = blockIdx.x;
-  const int row0 = blockIdx.y * rows_per_cta, row1 = min(row0 + rows_per_cta, f.cby);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int used = (row1 - row0) * f.cbx;
-  const uint32_t rect = coarse_rect(prims, chunk * kChunk + threadIdx.x, n, f);
-  for (int k = 0; k < kWarps / 2; k++)
-    for (int sl = threadIdx.x; sl < used; sl += blockDim.x) s_pos[k][sl] = 0;
-  for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {
-    const int b = row0 * f.cbx + sl;
-    s_gbase[sl] = cbin_start[b] + chunk_counts[(size_t)b * gridDim.x + chunk];
-  }
-  const ChunkPairs cp = chunk_pairs(rect, row0, row1, s_excl, s_rect, s_wtot);
-  const int word = warp >> 1, shift = (warp & 1) * 16;
-  for (uint32_t base = cp.lo; base < cp.hi; base += 32) {
-    const uint32_t p = base + lane;
-    if (p < cp.hi) {
-      int owner, bx, by;
-      chunk_pair(cp, p, owner, bx, by);
-      atomicAdd(&s_pos[word][(by - row0) * f.cbx + bx], 1u << shift);
-    }
-  }
-  __syncthreads();
-  for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {  // counts -> exclusive prefix over the warps
-    uint32_t run = 0;
-#pragma unroll
-    for (int k = 0; k < kWarps / 2; k++) {
-      const uint32_t v = s_pos[k][sl];
-      const uint32_t lo = v & 0xFFFFu, hi = v >> 16;
-      s_pos[k][sl] = run | ((run + lo) << 16);
-      run += lo + hi;
-    }
-  }
-  __syncthreads();
-  const uint32_t first = chunk * kChunk;
-  for (uint32_t base = cp.lo; base < cp.hi; base += 32) {
-    const uint32_t p = base + lane;
-    const bool active = p < cp.hi;
-    int owner = 0, bx = 0, by = row0;
-    if (active) chunk_pair(cp, p, owner, bx, by);
-    const int sl = (by - row0) * f.cbx + bx;
-    // pairs of one round are in primitive order along the lanes: the rank among equal bins is the stable rank
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, active ? (uint32_t)sl : (0x80000000u | (uint32_t)lane));
-    if (active) {
-      const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-      const uint32_t off = (s_pos[word][sl] >> shift) & 0xFFFFu;
-      coarse_list[s_gbase[sl] + off + rank] = first + (uint32_t)owner;
-    }
-    __syncwarp();
-    if (active && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&s_pos[word][sl], (uint32_t)__popc(peers) << shift);
-    __syncwarp();
-  }
-}
-
-// ---- coarse level as ONE kernel (FDC_COARSE_FUSED, default): count, place and scatter in the same CTA.
-// The three-kernel form above needs a grid-wide scan between counting and scattering only because every bin's list is
-// contiguous.  Nothing requires that: the fine binner reads a bin's entries in CHUNK order, so a bin's list may as well
-// be one segment per chunk, anywhere in the coarse list, as long as a table says where.  A CTA counts its chunk's pairs
-// per bin, scans its own bins, reserves its region of the list with one atomicAdd (placement is not observable, order
-// is: segments are read in chunk order and written in primitive order), writes seg[bin][chunk] = (start, count) and
-// scatters.  Two launches and a 1 MB round trip fewer; the fine binner maps "entry k of the bin" to (chunk, offset)
-// with a binary search over the scanned counts of its bin's row of the table.
+// One kernel: count, place and scatter in the same CTA.  (Round 1 and the first half of round 2 had three -- count,
+// a grid-wide scan, scatter -- because every bin's list was contiguous.)  Nothing requires that: the fine binner reads a
+// bin's entries in CHUNK order, so a bin's list may as well be one segment per chunk, anywhere in the coarse list, as long
+// as a table says where.  A CTA counts its chunk's pairs per bin (shared-memory histogram, one 16-bit counter per (bin,
+// warp)), turns the counts into running offsets over the warps, scans its own bins, reserves its region of the list with
+// one atomicAdd (placement is not observable, order is: segments are read in chunk order and written in primitive
+// order), writes seg[bin][chunk] = (start, count) and scatters: position = segment start + pairs of earlier warps +
+// pairs of earlier rounds of this warp + rank inside the round.  The fine binner maps "entry k of the bin" to (chunk,
+// offset) with a binary search over the scanned counts of its bin's row of the table.
 __global__ void __launch_bounds__(kChunk) coarse_pairs_kernel(const PrimBin* __restrict__ prims, uint32_t n, FrameView f, int rows_per_cta,
                                                               uint2* __restrict__ seg, uint32_t* __restrict__ coarse_list,
                                                               uint32_t coarse_cap, uint32_t* __restrict__ counters) {
-  __shared__ uint32_t s_pos[kWarps / 2][kSlots];  // as in coarse_scatter_kernel
+  // per (bin, warp): first the pair count, then (after the prefix over warps) the running offset inside the chunk's
+  // segment of the bin.  16 bits each (a chunk puts at most kChunk pairs into a bin), two warps per word; [word][bin] so
+  // that consecutive threads hit consecutive banks.
+  __shared__ uint32_t s_pos[kWarps / 2][kSlots];
   __shared__ uint32_t s_gbase[kSlots];
   __shared__ uint32_t s_excl[kChunk], s_rect[kChunk], s_wtot[kWarps];
   __shared__ uint32_t s_region;
@@ -965,78 +873,6 @@ __global__ void __launch_bounds__(kChunk) coarse_pairs_kernel(const PrimBin* __r
     __syncwarp();
     if (active && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&s_pos[word][sl], (uint32_t)__popc(peers) << shift);
     __syncwarp();
-  }
-}
-
-// Exclusive scan over chunks for every bin (one warp per bin), then -- in the last CTA to finish -- the scan over
-// bins that yields cbin_start.  counters[3] is the completion ticket.
-__global__ void __launch_bounds__(256) coarse_scan_kernel(uint32_t* __restrict__ chunk_counts, int n_chunks, int n_bins,
-                                                          uint32_t* __restrict__ cbin_start, uint32_t coarse_cap,
-                                                          uint32_t* __restrict__ counters) {
-  __shared__ uint32_t warp_sums[8];
-  __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x * 8 + warp;
-  if (b < n_bins) {
-    // [bin][chunk] layout: a warp reads 32 consecutive chunk counts per step.  The loads of 16 steps (512 chunks) are
-    // issued together; only the carry chains the steps.
-    uint32_t carry = 0;
-    uint32_t* row = chunk_counts + (size_t)b * n_chunks;
-    for (int blk0 = 0; blk0 < n_chunks; blk0 += 512) {
-      uint32_t v[16];
-#pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const int c = blk0 + k * 32 + lane;
-        v[k] = c < n_chunks ? row[c] : 0u;
-      }
-#pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const int c = blk0 + k * 32 + lane;
-        uint32_t incl = v[k];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        if (c < n_chunks) row[c] = carry + incl - v[k];
-        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
-      }
-    }
-    if (lane == 0) cbin_start[b + 1] = carry;  // bin totals, shifted by one; turned into offsets by the last CTA
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(&counters[kCntTicket], 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // inclusive scan of the totals stored at cbin_start[1..n_bins]
-  uint32_t carry = 0;
-  volatile uint32_t* vs = cbin_start;
-  for (int b0 = 0; b0 < n_bins; b0 += 256) {
-    const int i = b0 + threadIdx.x;
-    const uint32_t v = i < n_bins ? vs[i + 1] : 0u;
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    uint32_t wbase = 0;
-    for (int w = 0; w < warp; w++) wbase += warp_sums[w];
-    uint32_t blk = 0;
-    for (int w = 0; w < 8; w++) blk += warp_sums[w];
-    if (i < n_bins) vs[i + 1] = carry + wbase + incl;
-    carry += blk;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    cbin_start[0] = 0;
-    counters[kCntCoarseTotal] = carry;
-    atomicMax(&counters[kCntMaxCoarse], carry);  // per-frame maximum over segments (resolve_frame regrows from it)
-    if (carry > coarse_cap) { atomicOr(&counters[kCntOverflow], 1u); atomicOr(&counters[kCntStickyOverflow], 1u); }
   }
 }
 
@@ -1176,7 +1012,7 @@ constexpr size_t kDirectFineLimit = FDC_DIRECT_FINE_LIMIT;  // primitives x coar
 #define FDC_FINE_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(256, FDC_FINE_MIN_BLOCKS) fine_bin_kernel(const PrimBin* __restrict__ prims, FrameView f,
-                                                       const uint32_t* __restrict__ cbin_start, const uint2* __restrict__ seg,
+                                                       const uint2* __restrict__ seg,
                                                        int n_chunks, const uint32_t* __restrict__ coarse_list, uint32_t coarse_cap,
                                                        uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile_count,
                                                        TileEntry* __restrict__ tile_list, uint32_t tile_cap,
@@ -1208,13 +1044,12 @@ __global__ void __launch_bounds__(256, FDC_FINE_MIN_BLOCKS) fine_bin_kernel(cons
   if (!n_direct && counters[kCntCoarseTotal] > coarse_cap) return;
   const int b = blockIdx.x;
   const int cbx_i = b % f.cbx, cby_i = b / f.cbx;
-  // Where the bin's entries come from: primitives 0..n_direct-1 themselves, one contiguous slice of the coarse list
-  // (three-kernel coarse pass), or one segment per chunk (coarse_pairs_kernel), addressed kSegBlock chunks at a time.
-  const bool use_seg = !n_direct && seg != nullptr;
-  const uint32_t begin = (n_direct || use_seg) ? 0u : cbin_start[b];
+  // Where the bin's entries come from: primitives 0..n_direct-1 themselves, or one segment of the coarse list per chunk
+  // (coarse_pairs_kernel), addressed kSegBlock chunks at a time.
+  const bool use_seg = !n_direct;
   const uint2* seg_row = use_seg ? seg + (size_t)b * (size_t)n_chunks : nullptr;
   const int n_blocks = use_seg ? (n_chunks + kSegBlock - 1) / kSegBlock : 1;
-  uint32_t blk_total = n_direct ? n_direct : (use_seg ? 0u : cbin_start[b + 1] - begin);  // entries of the current block
+  uint32_t blk_total = n_direct;  // entries of the current block of chunks (segments: known once the block is loaded)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_x0 = cbx_i * kCoarse, tile_y0 = f.cty0 + cby_i * kCoarse;
   const int px0 = tile_x0 * kTileW, py0 = tile_y0 * kTileH;
@@ -1225,7 +1060,7 @@ __global__ void __launch_bounds__(256, FDC_FINE_MIN_BLOCKS) fine_bin_kernel(cons
   // With many bins (split_big, grid.y = 2 as well) only the bins that need more than one stage are shared by two CTAs
   // -- they are the launch's critical path, each stage is gathered twice -- and the second CTA of any other bin leaves.
   bool do_lo = gridDim.y == 1 || blockIdx.y == 0, do_hi = gridDim.y == 1 || blockIdx.y == 1;
-  if (split_big && !use_seg && single) {
+  if (split_big && !use_seg && single) {  // (direct mode: the whole "list" is known up front)
     if (blockIdx.y == 1) return;
     do_lo = do_hi = true;
   }
@@ -1346,7 +1181,6 @@ __global__ void __launch_bounds__(256, FDC_FINE_MIN_BLOCKS) fine_bin_kernel(cons
             const uint32_t k = threadIdx.x + j * 256u;
             if (k >= ns) pid[j] = 0xFFFFFFFFu;
             else if (n_direct) pid[j] = s0 + k;
-            else if (!use_seg) pid[j] = __ldg(&coarse_list[begin + s0 + k]);
             else {
               // entry q of the block -> its chunk: the last chunk whose scanned count is <= q (empty chunks tie with
               // their successor and lose)
@@ -1491,32 +1325,21 @@ void launch_binning(const PrimBin* prims, uint32_t n_prims, const FrameView& f, 
   // writes start and count of EVERY tile of the band, empty ones included.  (After a list overflow it leaves them
   // stale -- and every later kernel of the frame returns at once on the sticky flag.)
   if ((size_t)n_prims * (size_t)n_bins <= (size_t)kDirectFineLimit) {
-    // Small scene: the launches of coarse binning cost more than letting every bin look at every primitive.
-    fine_bin_kernel<<<dim3(n_bins, n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(prims, f, b.cbin_start, nullptr, 0, b.coarse_list,
-                                                                                    b.coarse_cap, b.tile_start, b.tile_count, b.tile_list,
-                                                                                    b.tile_cap, b.counters, b.row_cost, n_prims, 0);
+    // Small scene: the launch of coarse binning costs more than letting every bin look at every primitive.
+    fine_bin_kernel<<<dim3(n_bins, n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(prims, f, nullptr, 0, b.coarse_list, b.coarse_cap,
+                                                                                    b.tile_start, b.tile_count, b.tile_list, b.tile_cap,
+                                                                                    b.counters, b.row_cost, n_prims, 0);
     if (n_launches) *n_launches += 1;
     return;
   }
   const int rows_per_cta = max(1, kSlots / max(f.cbx, 1));  // whole bin rows, at most kSlots bins per CTA
   dim3 grid(n_chunks, (f.cby + rows_per_cta - 1) / rows_per_cta);
-#if FDC_COARSE_FUSED
-  uint2* seg = reinterpret_cast<uint2*>(b.chunk_counts);  // [bin][chunk] (start, count)
+  uint2* seg = reinterpret_cast<uint2*>(b.seg_table);  // [bin][chunk] (start, count)
   coarse_pairs_kernel<<<grid, kChunk, 0, stream>>>(prims, n_prims, f, rows_per_cta, seg, b.coarse_list, b.coarse_cap, b.counters);
   fine_bin_kernel<<<dim3(n_bins, FDC_FINE_SPLIT_BIG || n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(
-      prims, f, b.cbin_start, seg, n_chunks, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count, b.tile_list, b.tile_cap, b.counters, b.row_cost,
+      prims, f, seg, n_chunks, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count, b.tile_list, b.tile_cap, b.counters, b.row_cost,
       0u, FDC_FINE_SPLIT_BIG && n_bins > kFineSplitBins);
   if (n_launches) *n_launches += 2;
-#else
-  coarse_count_kernel<<<grid, kChunk, 0, stream>>>(prims, n_prims, f, rows_per_cta, b.chunk_counts);
-  coarse_scan_kernel<<<(n_bins + 7) / 8, 256, 0, stream>>>(b.chunk_counts, n_chunks, n_bins, b.cbin_start, b.coarse_cap, b.counters);
-  coarse_scatter_kernel<<<grid, kChunk, 0, stream>>>(prims, n_prims, f, rows_per_cta, b.chunk_counts, b.cbin_start, b.coarse_list,
-                                                     b.coarse_cap, b.counters);
-  fine_bin_kernel<<<dim3(n_bins, FDC_FINE_SPLIT_BIG || n_bins <= kFineSplitBins ? 2 : 1), 256, 0, stream>>>(
-      prims, f, b.cbin_start, nullptr, 0, b.coarse_list, b.coarse_cap, b.tile_start, b.tile_count, b.tile_list, b.tile_cap, b.counters, b.row_cost,
-      0u, FDC_FINE_SPLIT_BIG && n_bins > kFineSplitBins);
-  if (n_launches) *n_launches += 4;
-#endif
 }
 
 }  // namespace fdc

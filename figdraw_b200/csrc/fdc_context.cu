@@ -262,7 +262,7 @@ struct fdc_ctx {
   DevBuf<QuadGeom> d_geoms;
   DevBuf<PrimExt> d_exts;
   DevBuf<uint32_t> d_prim_call;
-  DevBuf<uint32_t> d_chunk_counts, d_cbin_start, d_coarse_list, d_tile_start, d_tile_count, d_counters;
+  DevBuf<uint32_t> d_seg_table, d_coarse_list, d_tile_start, d_tile_count, d_counters;
   DevBuf<uint32_t> d_row_cost;          // tile entries per tile row of the last frame (fdc_get_tile_row_costs)
   std::vector<int> band_bounds;         // fdc_set_band_tile_rows: n_ranks + 1 tile-row boundaries; empty = equal bands
   DevBuf<TileEntry> d_tile_list;
@@ -763,8 +763,7 @@ int ensure_bin_buffers(fdc_ctx* ctx, uint32_t max_prims) {
   const FrameView& f = ctx->frame;
   const size_t n_bins = (size_t)f.cbx * f.cby;
   const size_t n_chunks = (max_prims + kChunk - 1) / kChunk;
-  CK(ctx->d_chunk_counts.reserve(std::max<size_t>(2, 2 * n_chunks * n_bins)));  // (start, count) per (bin, chunk)
-  CK(ctx->d_cbin_start.reserve(n_bins + 1));
+  CK(ctx->d_seg_table.reserve(std::max<size_t>(2, 2 * n_chunks * n_bins)));  // (start, count) per (bin, chunk)
   CK(ctx->d_tile_start.reserve((size_t)f.tiles_x * f.tiles_y));
   CK(ctx->d_tile_count.reserve((size_t)f.tiles_x * f.tiles_y));
   CK(ctx->d_counters.reserve(kNumCounters));
@@ -776,8 +775,7 @@ int ensure_bin_buffers(fdc_ctx* ctx, uint32_t max_prims) {
 
 BinBuffers bin_buffers(fdc_ctx* ctx) {
   BinBuffers b;
-  b.chunk_counts = ctx->d_chunk_counts.p;
-  b.cbin_start = ctx->d_cbin_start.p;
+  b.seg_table = ctx->d_seg_table.p;
   b.coarse_list = ctx->d_coarse_list.p;
   b.coarse_cap = (uint32_t)std::min<size_t>(ctx->d_coarse_list.cap, 0xFFFFFFF0u);
   if (ctx->dbg_coarse_limit) b.coarse_cap = std::min(b.coarse_cap, ctx->dbg_coarse_limit);
@@ -1242,7 +1240,7 @@ void fdc_destroy(fdc_ctx* ctx) {
   ctx->d_rects64.release();
   ctx->d_draws.release(); ctx->d_runs.release(); ctx->d_xforms.release(); ctx->d_rectmasks.release();
   ctx->d_prims.release(); ctx->d_prim_bins.release(); ctx->d_geoms.release(); ctx->d_exts.release(); ctx->d_prim_call.release();
-  ctx->d_chunk_counts.release(); ctx->d_cbin_start.release(); ctx->d_coarse_list.release();
+  ctx->d_seg_table.release(); ctx->d_coarse_list.release();
   ctx->d_tile_start.release(); ctx->d_tile_count.release(); ctx->d_tile_list.release(); ctx->d_counters.release();
   ctx->d_row_cost.release();
   ctx->d_fb.release(); ctx->d_backdrop.release(); ctx->d_temp.release(); ctx->d_peers.release(); ctx->d_snapshot.release();

@@ -28,8 +28,7 @@ struct SetupArgs {
 void launch_prim_setup(const SetupArgs& a, cudaStream_t stream);
 
 struct BinBuffers {
-  uint32_t* chunk_counts;  // [2 * n_chunks * n_cbins]: per (bin, chunk) the segment (start, count) of the coarse list
-  uint32_t* cbin_start;    // [n_cbins + 1]
+  uint32_t* seg_table;     // [2 * n_chunks * n_cbins]: per (bin, chunk) the segment (start, count) of the coarse list
   uint32_t* coarse_list;   // [coarse_cap]
   uint32_t coarse_cap;
   uint32_t* tile_start;    // [tiles_x * tiles_y]

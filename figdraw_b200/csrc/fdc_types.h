@@ -81,7 +81,6 @@ enum : int {
   kCntCursor = 0,          // tile-list cursor: entries reserved so far (= size the segment needs when it overflows)
   kCntOverflow = 1,        // bit 0 coarse list, bit 1 tile list overflowed in this segment
   kCntCoarseTotal = 2,     // entries of the coarse list
-  kCntTicket = 3,          // coarse_scan_kernel's last-CTA ticket
   kCntFullTiles = 4,       // tiles of this segment that need the shade kernel's full loop
   kCntStickyOverflow = 8,  // OR of kCntOverflow over the frame's segments
   kCntMaxCoarse = 9,       // largest coarse list any segment needs

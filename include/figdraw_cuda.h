@@ -318,7 +318,8 @@ int fdc_band_rows(fdc_ctx* ctx, int* y0, int* y1);
 /* Band balancing: tile entries per 16-px tile row of the last completed frame (this rank's rows; 0 elsewhere -- sum over
  * the ranks for the whole frame), and bands chosen by the host instead of equal ones: n_ranks + 1 tile-row boundaries,
  * bounds[0] = 0, non-decreasing, bounds[n_ranks] = ceil(H / 16); the same on every rank; n_bounds = 0 restores equal
- * bands.  Takes effect for replays of the recorded frame and for later frames of that height.  Needs a framebuffer the
+ * bands.  Takes effect for replays of the recorded frame and for later frames of that height (a frame of another height
+ * is partitioned into equal bands until boundaries for it are set).  Needs a framebuffer the
  * ranks share or reach (fdc_bind_shared_framebuffer / fdc_set_peer_framebuffers); an all-gather of equal slices does
  * not apply to unequal bands. */
 int fdc_get_tile_row_costs(fdc_ctx* ctx, uint32_t* out, int cap, int* n_rows);

@@ -438,12 +438,22 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
         c.submitPrepared(prep)
         c.endFrame()
 
+    trace_host = os.environ.get("FDC_E2E_TRACE", "0") != "0"  # host-side split of a single frame's latency, to stderr
+    host_t = [0.0, 0.0, 0.0, 0]
+
     def frame_e2e():
+        t0 = time.perf_counter()
         submit(ctx, prepared)
+        t1 = time.perf_counter()
         with torch.cuda.stream(stream):
             gather()
         y0, y1 = ctx.bandRows() if world > 1 else (0, H)
+        if trace_host:
+            ctx.sync()
+        t2 = time.perf_counter()
         ctx.readPixels((0, y0, W, y1 - y0), out=out_np[y0:y1])
+        t3 = time.perf_counter()
+        host_t[0] += t1 - t0; host_t[1] += t2 - t1; host_t[2] += t3 - t2; host_t[3] += 1
 
     # first frame: uploads the recording, allocates everything; a bin-list overflow on ANY rank re-runs it on all
     submit(ctx, prepared)
@@ -513,6 +523,9 @@ def measure(env: Env, name: str, steps: int, warmup: int, headline: bool):
         frame_e2e()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if trace_host and host_t[3]:
+        sys.stderr.write("[bench] rank %d single-frame split: submit (host) %.3f ms, wait for the frame %.3f ms, read-back %.3f ms\n"
+                         % (rank, host_t[0] / host_t[3] * 1e3, host_t[1] / host_t[3] * 1e3, host_t[2] / host_t[3] * 1e3))
 
     # e2e, pipelined (N = 1): three contexts on three streams, like a three-image swap chain.  Every step still copies
     # its own records host->device and its own frame device->host; in steady state frame k's readback, frame k+1's

@@ -117,6 +117,21 @@ def test_baseline_configs_at_full_size(name):
     ctx.close()
 
 
+def test_more_chunks_than_one_segment_table_block():
+    """541 893 primitives = 1 059 chunks of 512: the fine binner addresses a bin's segments 1 024 chunks at a time, so this
+    scene takes the second block of the table (no BASELINE config does).  Pixels within 2 LSB, bin lists bit-exact."""
+    tr = ss.config_trace(5, 1920, 1080, n_rects=240000, n_glyphs=2000, scale=0.35)
+    assert tr.n_draws > 1024 * 512
+    ctx = CudaContext(atlasSize=tr.atlas_size)
+    got = render_trace(tr, ctx)
+    want = oracle.render_trace(tr)
+    mx, frac = diff_stats(got, want)
+    assert mx <= MAX_DIFF, f"max diff {mx} LSB"
+    assert frac <= MAX_FRACTION, f"{frac:.4%} of pixels differ"
+    _check_bins(tr, ctx)
+    ctx.close()
+
+
 def test_cfg5_8k_bands_reassemble_the_frame():
     """configs[4]: the 8K frame partitioned into 8 tile-row bands equals the single-context frame, bit for bit."""
     tr = ss.config_trace(5, 7680, 4320, scale=2.0)

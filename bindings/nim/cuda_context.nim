@@ -375,3 +375,47 @@ proc generateGlyphs*(ctx: CudaContext, jobs: openArray[FdcGlyphJob], segs: openA
     ctx.entries.clear()
     ctx.atlasEntryMeta.clear()
     ctx.noteAtlasRebuilt()
+
+
+# ---- the rest of include/figdraw_cuda.h: plumbing a host may want, declared so that the binding is complete --------------
+type
+  FdcRect64* {.importc: "fdc_rect64", header: "figdraw_cuda.h", bycopy.} = object   ## 64-byte rounded-rect record
+  FdcFrameStats* {.importc: "fdc_frame_stats", header: "figdraw_cuda.h", bycopy.} = object
+  FdcAtlasUsage* {.importc: "fdc_atlas_usage", header: "figdraw_cuda.h", bycopy.} = object
+  FdcFlattenEnv* {.importc: "fdc_flatten_env", header: "figdraw_cuda.h", bycopy.} = object
+
+proc fdc_abi_version(): cint {.importc, header: hdr.}
+proc fdc_read_pixels_async(ctx: FdcCtx, x, y, w, h: cint, outRgba: ptr uint8): cint {.importc, header: hdr.}
+proc fdc_get_transform(ctx: FdcCtx, outMat4: ptr cfloat): cint {.importc, header: hdr.}
+proc fdc_has_image(ctx: FdcCtx, key: uint64): cint {.importc, header: hdr.}
+proc fdc_get_image_rect(ctx: FdcCtx, key: uint64, outRect: ptr cfloat): cint {.importc, header: hdr.}
+proc fdc_get_atlas_usage(ctx: FdcCtx, outUsage: ptr FdcAtlasUsage): cint {.importc, header: hdr.}
+proc fdc_get_frame_stats(ctx: FdcCtx, outStats: ptr FdcFrameStats): cint {.importc, header: hdr.}
+# compact records
+proc fdc_pack_rect64(call: ptr FdcCall, outRect: ptr FdcRect64): cint {.importc, header: hdr.}
+proc fdc_expand_rect64(rect: ptr FdcRect64, outCall: ptr FdcCall) {.importc, header: hdr.}
+proc fdc_submit_rects64(ctx: FdcCtx, rects: ptr FdcRect64, n: csize_t): cint {.importc, header: hdr.}
+# native front-end without a context (tests: byte-identity with the per-call front-end)
+proc fdc_flatten_renders(scene: ptr FdcScene, env: ptr FdcFlattenEnv, outCalls: ptr FdcCall, cap: csize_t,
+                         nOut: ptr csize_t): cint {.importc, header: hdr.}
+# framebuffer plumbing: caller-owned memory, bands, peers over CUDA IPC, gather mode
+proc fdc_bind_framebuffer(ctx: FdcCtx, deviceRgba8: pointer): cint {.importc, header: hdr.}
+proc fdc_framebuffer_ptr(ctx: FdcCtx): pointer {.importc, header: hdr.}
+proc fdc_band_rows(ctx: FdcCtx, y0, y1: ptr cint): cint {.importc, header: hdr.}
+proc fdc_stream(ctx: FdcCtx): pointer {.importc, header: hdr.}
+proc fdc_set_peer_framebuffers(ctx: FdcCtx, devicePtrs: ptr pointer, n: cint): cint {.importc, header: hdr.}
+proc fdc_set_frame_barrier(ctx: FdcCtx, enabled: cint): cint {.importc, header: hdr.}
+proc fdc_set_peer_gather(ctx: FdcCtx, mode, subBands: cint): cint {.importc, header: hdr.}
+proc fdc_reserve_framebuffer(ctx: FdcCtx, width, rows: cint): cint {.importc, header: hdr.}
+proc fdc_framebuffer_ipc_handle(ctx: FdcCtx, outHandle: ptr uint8): cint {.importc, header: hdr.}
+proc fdc_open_peer_framebuffer(ctx: FdcCtx, handle: ptr uint8, outDevicePtr: ptr pointer): cint {.importc, header: hdr.}
+# debugging
+proc fdc_debug_bins(ctx: FdcCtx, segment: cint, tileOffsets: ptr uint32, offsetsCap: csize_t, entries: ptr uint32,
+                    entriesCap: csize_t, nOffsets, nEntries: ptr csize_t): cint {.importc, header: hdr.}
+proc fdc_debug_limit_lists(ctx: FdcCtx, coarseEntries, tileEntries: uint32): cint {.importc, header: hdr.}
+proc fdc_debug_shade_stats(ctx: FdcCtx, outStats: ptr uint64): cint {.importc, header: hdr.}
+
+proc rebalanceBands*(ctx: CudaContext, bounds: openArray[cint]) =
+  ## Bands chosen by the host (the same boundaries on every rank): tile rows, `bounds[0] = 0`, `bounds[^1] = ceil(H / 16)`.
+  ## The profile to split comes from `fdc_get_tile_row_costs`, summed over the ranks.
+  ctx.ck fdc_set_band_tile_rows(ctx.h, bounds[0].unsafeAddr, bounds.len.cint)

@@ -122,3 +122,18 @@ int main(void) {
     assert c["fdc_fig.u.text.n_decoration"] == pay + abi.FIG_TEXT_DTYPE.fields["n_decoration"][1]
     assert c["fdc_render_list.root_ids"] == abi.FdcRenderList.root_ids.offset
     assert c["fdc_flatten_env.image_keys"] == abi.FdcFlattenEnv.image_keys.offset
+
+
+def test_nim_shim_declares_every_entry_point():
+    """bindings/nim/cuda_context.nim is the reference-side binding a maintainer would add (not compilable here: no Nim):
+    it must at least declare an importc proc for every function of the header, and mention no function the header lacks."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "figdraw_cuda.h")).read()
+    nim = open(os.path.join(root, "bindings", "nim", "cuda_context.nim")).read()
+    declared = set(re.findall(r"^(?:int|void|void\*|float|const char\*)\s+\*?(fdc_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
+    assert len(declared) >= 80
+    in_nim = set(re.findall(r"^proc\s+(fdc_[a-z0-9_]+)\b", nim, flags=re.M))
+    assert declared - in_nim == set(), f"no importc for {sorted(declared - in_nim)}"
+    assert in_nim - declared == set(), f"the shim binds functions the header does not declare: {sorted(in_nim - declared)}"
